@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: restored img/s of the reference-guided Restormer (option 003) at 512x512.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one forward restoration pass of RestormerRefFusion (option 003: dim 48, blocks [4,6,6,8], 2 fusion blocks
+per level, nf 48) over a batch of 4 synthetic degraded 512x512 tiles + 4 reference tiles per GPU (BASELINE.json
+configs[2], the configuration the metric is quoted on).  Images are independent units: ranks are replicas over disjoint
+batches, no data-path collective (scaling "weak").
+
+  value  : images/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks)
+  e2e    : images/s through the module's public call with HOST (pinned) inputs and a pinned host output,
+           H2D and D2H copies inside the timed region
+  roofline: for the kernel family with the largest share of the step (per-launch CUDA-event timing in a separate,
+           untimed profiling pass): achieved = algorithmic bytes (or flops) / measured time vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the CPU oracle (fp32 restatement of the reference modules, pinned to them by
+           tests/golden) on the host cores -- /root/reference itself does not exist on the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+OPTION_003 = dict(inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4,
+                  heads=[1, 2, 4, 8], ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias",
+                  dual_pixel_task=False, nf=48, ext_n_blocks=[4, 4, 4, 4], reffusion_n_blocks=[2, 2, 2, 2],
+                  reffusion_n_blocks_middle=1, scale=1, num_nbr=1, psize=3, lr_block_size=8, ref_down_block_size=1.5,
+                  dilations=[1, 2, 3])
+METRIC = "restored img/s @512x512 bf16 guided-Restormer"
+FWD_GFLOP_PER_IMG = 2492.2          # SURVEY.md 8(a) a7, torch flop counter on the reference module
+
+
+def synth_inputs(batch, size, seed):
+    """Synthetic deblurring tiles: gt = smooth random image, lq = 9x9 box blur of gt,
+    ref = gt + small noise (so matching is non-degenerate)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    gt = F.avg_pool2d(torch.rand(batch, 3, size + 8, size + 8, generator=g), 5, 1, 2)[..., 4:-4, 4:-4].contiguous()
+    lq = F.avg_pool2d(F.pad(gt, (4, 4, 4, 4), mode="reflect"), 9, 1, 0)
+    ref = (gt + 0.02 * torch.randn(gt.shape, generator=g)).clamp(0, 1)
+    return lq.contiguous(), ref.contiguous(), gt
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    except Exception:  # noqa: BLE001
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = str(gpu_index), None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", self.idx], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [t.strip() for t in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(size, max_seconds, steps=None, warmup=0):
+    """img/s of the CPU oracle (fp32 port of the reference modules) on all host cores, batch 1."""
+    import torch
+    from oracle import restormer as O, weights as W
+    from textualdegremoval_b200.archs.restormer_b200_arch import RestormerRefFusion
+    ncores = os.cpu_count() or 1
+    torch.set_num_threads(ncores)
+    shapes = {k: v.shape for k, v in RestormerRefFusion(**OPTION_003).state_dict().items()}
+    sd = W.seeded_state_dict(shapes, 0)
+    lq, ref, _ = synth_inputs(1, size, 100)
+    times = []
+    t_begin = time.perf_counter()
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.restormer_ref_fusion_forward(sd, lq, ref)
+            if time.perf_counter() - t_begin > max_seconds / 2:
+                break
+        n = 0
+        while True:
+            t0 = time.perf_counter()
+            O.restormer_ref_fusion_forward(sd, lq, ref)
+            times.append(time.perf_counter() - t0)
+            n += 1
+            if (steps is not None and n >= steps) or time.perf_counter() - t_begin > max_seconds:
+                break
+    mean = sum(times) / len(times)
+    return dict(value=1.0 / mean, unit="img/s", cores=ncores, kind="port", steps=len(times), sec_per_img=mean,
+                sample=f"{len(times)} x 1 image {size}x{size} (lq+ref), fp32 CPU oracle of the reference modules, "
+                       f"torch {torch.__version__} {ncores} threads")
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (oracle port; the reference
+    tree is not present on the GPU box).  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    r = cpu_oracle_rate(args.size, max_seconds=180.0, steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "img/s", "n_gpus": args.gpus,
+        "steps": r["steps"], "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * r["sec_per_img"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"RestormerRefFusion option-003 forward, {args.size}x{args.size}, batch 1/step on CPU "
+                               "(bounded sample of the batch-4 GPU step; steps capped at 180 s)"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from textualdegremoval_b200 import define_network, lib, ops
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.check(lib.load().tdr_check_device(), "tdr_check_device")
+
+    B, S = args.batch, args.size
+    torch.manual_seed(0)                                   # random-init weights of the named architecture
+    net = define_network(dict(type="RestormerRefFusion", **OPTION_003))
+    with torch.no_grad():                                  # un-zero the gates so the guidance path does real work
+        for n_, p_ in net.named_parameters():
+            if n_.endswith("alpha"):
+                p_.uniform_(0.2, 1.0)
+            elif n_.endswith("temperature"):
+                p_.uniform_(0.5, 1.5)
+    net = net.to(dev).eval()
+    lq_h, ref_h, _ = synth_inputs(B, S, 100 + rank)
+    lq_h, ref_h = lq_h.pin_memory(), ref_h.pin_memory()
+    out_h = torch.empty(B, 3, S, S).pin_memory()
+    lq_d, ref_d = lq_h.to(dev), ref_h.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return net(lq_d, ref_d)
+
+    def step_e2e():
+        a = lq_h.to(dev, non_blocking=True)
+        b = ref_h.to(dev, non_blocking=True)
+        y = net(a, b)
+        out_h.copy_(y, non_blocking=True)
+        return y
+
+    def timed(fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.zero_()                                   # L2 flush between timed iterations (outside the events)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            evs.append((s, e))
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs)
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+        barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        l0 = ops.PROF.launches
+        ms = timed(step_resident, args.steps)
+        launches = ops.PROF.launches - l0
+        barrier()
+        clocks = sampler.stop() if rank == 0 else None
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        ms_e2e = timed(step_e2e, args.steps)
+        barrier()
+        # per-launch profile (untimed pass) for the roofline of the dominant kernel
+        prof = None
+        if rank == 0:
+            ops.PROF.start()
+            step_resident()
+            prof = ops.PROF.stop()
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    pk = peaks()
+    fam = {}
+    for name, tag, nb, fl, t in prof:
+        f = fam.setdefault(name, dict(ms=0.0, bytes=0, flops=0, n=0))
+        f["ms"] += t; f["bytes"] += nb; f["flops"] += fl; f["n"] += 1
+    total_prof = sum(f["ms"] for f in fam.values())
+    top = max(fam, key=lambda k: fam[k]["ms"])
+    ft = fam[top]
+    hbm_gbs = ft["bytes"] / (ft["ms"] * 1e-3) / 1e9
+    tflops = ft["flops"] / (ft["ms"] * 1e-3) / 1e12
+    hbm_frac, tc_frac = hbm_gbs / pk["hbm"], tflops / pk["tf_sust"]
+    if hbm_frac >= tc_frac:
+        roof = dict(bound="hbm", achieved=hbm_gbs, peak=pk["hbm"], unit="GB/s", frac=hbm_frac)
+    else:
+        roof = dict(bound="tensor", achieved=tflops, peak=pk["tf_sust"], unit="TFLOP/s", frac=tc_frac)
+    roof.update(kernel=top, launches_per_step=ft["n"], avg_launch_ms=ft["ms"] / ft["n"],
+                share_of_step=ft["ms"] / total_prof, traffic=None, peak_source=pk["src"],
+                families={k: dict(ms=round(v["ms"], 3), n=v["n"], GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                                  TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)) for k, v in fam.items()})
+    imgs = B * world * args.steps
+    value = imgs / (ms * 1e-3)
+    e2e = imgs / (ms_e2e * 1e-3)
+    cpu = cpu_oracle_rate(S, max_seconds=45.0, steps=1) if (world == 1 and not args.no_cpu_baseline) else None
+    line = {
+        "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"RestormerRefFusion option-003 forward (restoration), {S}x{S}, batch {B}/GPU, "
+                               f"lq+ref per image; fp32 residual stream, bf16 GEMM operands",
+                   "l2": "256 MB buffer written between timed iterations (L2 flush), outside the event pairs",
+                   "model_gflop_per_img": FWD_GFLOP_PER_IMG,
+                   "model_tflops_achieved": value * FWD_GFLOP_PER_IMG / 1e3 / world},
+        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": 2 * B * 3 * S * S * 4,
+                "d2h_bytes_per_step": B * 3 * S * S * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

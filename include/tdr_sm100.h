@@ -1,0 +1,168 @@
+/* tdr_sm100.h -- C ABI of libtdr_sm100.so: the B200 (sm_100a) kernels beneath the restoration-network hot path
+ * of mrluin/TextualDegRemoval.
+ *
+ * The reference has no FFI of its own: every op below replaces a stock PyTorch call inside
+ * /root/reference/models/archs/network_restormer_guided_arch.py (cited per entry point as file:line, "R:" prefix)
+ * or network_nafnet_guided_arch.py ("N:" prefix).  The Python modules in textualdegremoval_b200/archs bind these
+ * symbols with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named host_*; the caller owns every
+ *     buffer (including workspaces, sized by the *_workspace_bytes helpers); the library never allocates or syncs.
+ *   - activations are NHWC ("pixel rows x channels"): bf16 for GEMM operands, fp32 for the residual stream.
+ *     `ld` arguments are row strides in ELEMENTS (channels of the underlying buffer), so channel slices and
+ *     concatenations are expressed by pointer offset + ld, never by copies.
+ *   - every function returns TDR_OK (0) or a negative TDR_E* code; tdr_last_error() gives the message for the
+ *     calling thread.  Work is enqueued on `stream` (a cudaStream_t passed as void*) and is asynchronous.
+ */
+#ifndef TDR_SM100_H_
+#define TDR_SM100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDR_OK 0
+#define TDR_EINVAL (-1) /* bad argument (shape, alignment, null pointer) */
+#define TDR_ECUDA (-2)  /* CUDA runtime / driver error */
+#define TDR_ENOSUP (-3) /* configuration not supported by the sm_100a kernels */
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+const char* tdr_last_error(void);
+int tdr_version(void);
+/* 0 if the current device is sm_100 (B200), TDR_ENOSUP otherwise. */
+int tdr_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution (tcgen05 + TMA).  Replaces nn.Conv2d for: 1x1 convs R:229,234,252,254,613,619;
+ * dense 3x3 convs R:38-39,106-116 (stride 1/2, bias, ReLU, residual), R:376 + PixelUnshuffle, R:387 + PixelShuffle;
+ * `attn @ v` + project_out R:272-276 (per-sample weights); MASA correlations R:683-692, R:661-669 (per-sample
+ * filters, dilation, per-pixel scale, window origins).
+ *   out = g * alpha * act( acc * rowscale[pixel] + bias[co] ) + g * res1_scale * res1 + res2,   g = scale_ptr ? *scale_ptr : 1
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct tdr_conv_gemm_desc {
+  const void* in; /* bf16 [B_img, H, W, in_ld], channels [0, Ci) used */
+  long long in_ld;
+  int B, H, W, Ci;
+  const void* weight; /* bf16 [T][Co][w_ld], T = taps (ky-major) or B*taps when w_batched */
+  long long w_ld;
+  int Co, KH, KW, stride, pad, dil;
+  int w_batched;
+  const int* origin; /* optional int32 [B][3] = (image, y0, x0): sample b reads image `image` shifted by (y0, x0);
+                        H, W then describe the per-sample window used to size the output */
+  int n_images;      /* number of images in `in` when origin != NULL (else ignored) */
+  int img_h, img_w;  /* full image size when origin != NULL */
+  const float* bias;     /* fp32 [Co] or NULL */
+  const float* rowscale; /* fp32 [B*OH*OW] or NULL */
+  float alpha;
+  const float* scale_ptr; /* optional DEVICE scalar g (e.g. TransformerResFusionBlock.alpha R:343,353) */
+  int relu;
+  const float* res1; /* fp32, same addressing as the output, or NULL */
+  long long res1_ld;
+  float res1_scale;
+  const void* res2; /* fp32 (or bf16 when res2_bf16) or NULL */
+  long long res2_ld;
+  int res2_bf16;
+  float* out_f32; /* either or both outputs */
+  long long out_f32_ld;
+  void* out_bf16;
+  long long out_bf16_ld;
+  int store_mode; /* 0 plain; 1 PixelUnshuffle(2) R:377; 2 PixelShuffle(2) R:388 */
+  int impl;       /* 0 = tcgen05 (product path); 1 = SIMT restatement (tests/debug only) */
+} tdr_conv_gemm_desc;
+int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream);
+/* ABI self-description for binding checks: writes sizeof(desc) and the offsets of weight, origin, bias, scale_ptr, res1,
+ * res2, out_f32, out_bf16, impl into out[0..9]. */
+void tdr_conv_gemm_desc_layout(int* out);
+
+/* Small-channel direct 3x3 convs (SIMT): Ci <= 8 inputs (patch_embed R:362, masa_enc.conv_L1 R:106) read fp32 NHWC;
+ * or Co <= 4 outputs (output conv R:640, + input image residual R:962) read bf16 NHWC. */
+int tdr_conv3x3_small_ci(const float* in, int B, int H, int W, int Ci, const float* weight /* [Co][Ci][3][3] */,
+                         const float* bias, int Co, int relu, float* out_f32, long long out_f32_ld, void* out_bf16,
+                         long long out_bf16_ld, cudaStream_t stream);
+int tdr_conv3x3_small_co(const void* in_bf16, long long in_ld, int B, int H, int W, int Ci,
+                         const float* weight /* [Co][Ci][3][3] */, const float* bias, int Co,
+                         const float* res /* fp32 NHWC [.., Co] or NULL */, float* out /* fp32 NHWC [.., Co] */,
+                         cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Row-wise channel LayerNorm / cast: fp32 [rows, C] -> bf16 [rows, C].
+ *   mode 0: cast only.  mode 1: WithBias LN R:189-205 (also LayerNorm2d nafnet_arch_utils.py:264-300 with eps 1e-6).
+ *   mode 2: BiasFree LN R:172-186 (x / sqrt(var + eps) * w, mean not subtracted).
+ * ------------------------------------------------------------------------------------------------------------- */
+int tdr_rownorm(const float* in, long long in_ld, long long rows, int C, int mode, const float* weight,
+                const float* bias, float eps, void* out_bf16, long long out_ld, cudaStream_t stream);
+
+/* Depthwise 3x3, pad 1 (R:231, R:253; N:conv2) on bf16 NHWC.  weight fp32 [9][C] (tap-major), bias fp32 [C] or NULL.
+ * gate = 0: out[.., C].  gate = 1 (GDFN R:238-239): C = 2*Ch, out[.., Ch] = gelu(dw(x)[:Ch]) * dw(x)[Ch:].
+ * gate = 2 (SimpleGate N:170-175): out = dw(x)[:Ch] * dw(x)[Ch:]. */
+int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
+                  const float* bias, int gate, void* out_bf16, long long out_ld, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * MDTA channel attention R:262-276.
+ *   tdr_mdta_gram : per (sample, head) Gram q^T k plus sum-of-squares of q and k over all pixels (tcgen05, split over
+ *                   pixel chunks into `partials`).  qkv = bf16 [B, P, ld] with q|k|v at channel offsets 0|C|2C.
+ *   tdr_mdta_weff : reduce partials, attn = softmax(G / (|q||k|) * temperature) R:266-270, and fold it into
+ *                   project_out: Weff[b] = W_out * blockdiag(attn)  -> bf16 [B][C][weff_ld]; then `attn @ v` +
+ *                   project_out is tdr_conv_gemm(v, Weff, w_batched=1).  Optionally exports attn (fp32 [B,heads,c,c]).
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t tdr_mdta_partials_bytes(int B, long long P, int C, int heads);
+int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long long P, int C, int heads, float* partials,
+                  cudaStream_t stream);
+int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature /* [heads] */,
+                  const float* w_out /* fp32 [C][C] */, void* weff_bf16, long long weff_ld, float* attn_out,
+                  cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Layout / copies.
+ * ------------------------------------------------------------------------------------------------------------- */
+int tdr_nchw_to_nhwc(const float* src, int B, int C, int H, int W, int pad_h, int pad_w /* zero-padded output size */,
+                     float* dst_f32, long long dst_f32_ld, void* dst_bf16, long long dst_bf16_ld, cudaStream_t stream);
+int tdr_nhwc_to_nchw(const float* src, long long src_ld, int B, int C, int H, int W /* source size */, int out_h,
+                     int out_w /* crop */, float* dst, cudaStream_t stream);
+/* dst[r, 0:C] = src[r, 0:C] (fp32 rows with independent strides); optionally also writes a bf16 copy. */
+int tdr_copy_rows_f32(const float* src, long long src_ld, long long rows, int C, float* dst, long long dst_ld,
+                      void* dst_bf16, long long dst_bf16_ld, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * MASA match-and-transfer R:753-900 (closed form of SURVEY.md appendix A; no unfold/fold materialisation).
+ * Features are bf16 NHWC.  `k` = lr block size in feature pixels, (py, px) block grid, d = window diameter.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* n2[r] = sum_c x[r,c]^2 */
+int tdr_sqnorm_rows(const void* x_bf16, long long ld, long long rows, int C, float* n2, cudaStream_t stream);
+/* inv[dil_i][b,y,x] = 1 / max(sqrt(sum_{3x3 taps, dilation dil_i, zero pad} n2), 1e-12)   (R:683,690) */
+int tdr_masa_ref_invnorm(const float* n2, int B, int H, int W, const int* host_dils, int ndil, float* inv,
+                         cudaStream_t stream);
+/* coarse filters R:685-689: w[dil_i][b][tap][blk (padded to co_pad)][C] = normalised dilated 3x3 centre descriptor of
+ * lq block blk (replicate-padded halo R:785). */
+int tdr_masa_coarse_filters(const void* f_lq_bf16, int B, int H, int W, int C, int k_y, int k_x, const int* host_dils,
+                            int ndil, int co_pad, void* w_bf16, cudaStream_t stream);
+/* argmax over ref positions of score[b, pos, blk] (fp32, ld = co_pad) R:694 + window placement R:793-815.
+ * origin[b*nblk + blk] = (b, y1, x1). */
+int tdr_masa_coarse_argmax(const float* score, int B, int Hr, int Wr, int nblk, int co_pad, int d_y, int d_x,
+                           int* idx_out, int* origin, cudaStream_t stream);
+/* fine filters R:662-665: w[b*nblk+blk][tap][q (k_y*k_x)][C] = normalised 3x3 patch at interior position q. */
+int tdr_masa_fine_filters(const void* f_lq_bf16, int B, int H, int W, int C, int k_y, int k_x, void* w_bf16,
+                          cudaStream_t stream);
+/* inv[blk, jy, jx] = 1 / max(|3x3 patch of the window at (jy, jx)|, 1e-12) from the per-pixel n2 map R:666 */
+int tdr_masa_win_invnorm(const float* n2_ref, int Hr, int Wr, const int* origin, int nwin, int d_y, int d_x,
+                         float* inv, cudaStream_t stream);
+/* argmax over the d_y*d_x window positions of corr[win, pos, q] (fp32, ld = nq) R:670: index[win, q], att[win, q]. */
+int tdr_masa_fine_argmax(const float* corr, int nwin, int npos, int nq, int* index, float* att, cudaStream_t stream);
+/* transfer R:698-715 + re-tiling R:877-891 at scale s: out[b, Y, X, 0:C] (fp32, out_ld) from f_ref level
+ * [B, Hr*s, Wr*s, C] bf16. */
+int tdr_masa_transfer(const void* f_ref_bf16, int B, int Hr_s, int Wr_s, int C, const int* origin, const int* index,
+                      const float* att, int py, int px, int k_y, int k_x, int d_x, int s, float* out, long long out_ld,
+                      void* out_bf16, long long out_bf16_ld, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDR_SM100_H_ */

@@ -1,0 +1,513 @@
+"""Per-kernel and per-model parity checks of the CUDA path (through the C ABI) against the fp32 CPU oracle.
+
+Used two ways:
+  * ``tests/test_kernels_gpu.py`` / ``tests/test_models_gpu.py`` parametrise over ``CHECKS`` (pytest -m gpu);
+  * ``python -m tests.gpu_checks [--isolate] [--only GROUP]`` runs everything, never stops at the first failure, and
+    writes ``gpurun_out/gpu_checks.json`` -- one GPU call gives the whole picture.  ``--isolate`` runs each group in
+    its own process so that a trapping kernel cannot poison the checks after it.
+
+Reference values are computed on CPU in fp32 from the SAME bf16-rounded operands the kernels see, so the tolerance
+only has to cover accumulation order and the rounding of the stored result.
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+import traceback
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BF16, F32 = torch.bfloat16, torch.float32
+DEV = "cuda"
+
+
+def _ops():
+    from textualdegremoval_b200 import ops
+    return ops
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).float()
+
+
+def q(t):
+    """round to bf16 and back (what a bf16 tensor holds)."""
+    return t.to(BF16).float()
+
+
+def nhwc(t):   # NCHW cpu -> NHWC cuda (same dtype)
+    return t.permute(0, 2, 3, 1).contiguous().to(DEV)
+
+
+def nchw(t):   # NHWC cuda -> NCHW cpu fp32
+    return t.float().permute(0, 3, 1, 2).contiguous().cpu()
+
+
+def result(name, got, ref, rtol, note=""):
+    got = got.detach().float().cpu()
+    ref = ref.detach().float().cpu()
+    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    err = (got - ref).abs().max().item() if got.numel() else 0.0
+    scale = max(ref.abs().max().item(), 1e-6)
+    finite = bool(torch.isfinite(got).all())
+    ok = finite and err <= rtol * scale
+    return dict(name=name, max_err=err, ref_scale=scale, tol=rtol * scale, ok=ok, note=note)
+
+
+# =============================================================================================== pointwise
+def check_layout():
+    ops = _ops()
+    out = []
+    x = rnd(2, 3, 20, 28, seed=1)
+    y = ops.nchw_to_nhwc(x.to(DEV), 24, 32)
+    ref = F.pad(x, (0, 4, 0, 4)).permute(0, 2, 3, 1)
+    out.append(result("nchw_to_nhwc_pad", y, ref, 0.0))
+    z = ops.nhwc_to_nchw(y, 20, 28)
+    out.append(result("nhwc_to_nchw_crop", z, x, 0.0))
+    src = rnd(1, 6, 10, 48, seed=2).to(DEV)                      # NHWC
+    dst = torch.zeros(1, 6, 10, 96, device=DEV)
+    d16 = torch.zeros(1, 6, 10, 96, device=DEV, dtype=BF16)
+    ops.copy_rows(src, dst32=dst[..., 48:], dst16=d16[..., :48])
+    out.append(result("copy_rows_f32_slice", dst[..., 48:], src, 0.0))
+    out.append(result("copy_rows_bf16_slice", d16[..., :48], q(src.cpu()), 0.0))
+    out.append(result("copy_rows_untouched", dst[..., :48], torch.zeros(1, 6, 10, 48), 0.0))
+    return out
+
+
+def check_rownorm():
+    ops = _ops()
+    out = []
+    for C_ in (16, 48, 96, 192, 384, 768, 1536):
+        x = rnd(2, 5, 7, C_, seed=C_) * 2 + 0.3
+        w = 1 + 0.2 * rnd(C_, seed=C_ + 1)
+        b = 0.1 * rnd(C_, seed=C_ + 2)
+        mu = x.mean(-1, keepdim=True)
+        var = ((x - mu) ** 2).mean(-1, keepdim=True)
+        refs = {0: x, 1: (x - mu) / torch.sqrt(var + 1e-5) * w + b, 2: x / torch.sqrt(var + 1e-5) * w}
+        for mode in (0, 1, 2):
+            y = ops.rownorm(x.to(DEV), mode, w.to(DEV), b.to(DEV) if mode == 1 else None, 1e-5)
+            out.append(result(f"rownorm_m{mode}_C{C_}", y, refs[mode], 6e-3))
+    # strided view in and out
+    buf = (rnd(1, 4, 4, 96, seed=9)).to(DEV)
+    o = torch.zeros(1, 4, 4, 64, device=DEV, dtype=BF16)
+    ops.rownorm(buf[..., 48:], 0, out=o[..., 16:])
+    out.append(result("rownorm_strided", o[..., 16:], buf[..., 48:].cpu(), 6e-3))
+    return out
+
+
+def _dw_ref(x, w, b, gate):
+    y = F.conv2d(x, w, b, padding=1, groups=x.shape[1])
+    if gate:
+        a, c = y.chunk(2, 1)
+        y = (F.gelu(a) if gate == 1 else a) * c
+    return y
+
+
+def check_dwconv():
+    ops = _ops()
+    out = []
+    for (C_, H, W, gate, bias) in ((48, 9, 13, 0, False), (144, 16, 16, 0, True), (256, 8, 21, 1, False),
+                                   (32, 5, 4, 2, True), (1024, 6, 8, 1, True)):
+        x = q(rnd(2, C_, H, W, seed=C_ + H))
+        w = rnd(C_, 1, 3, 3, seed=3) * 0.3
+        b = rnd(C_, seed=4) * 0.1 if bias else None
+        ref = _dw_ref(x, w, b, gate)
+        y = ops.dwconv3x3(nhwc(x.to(BF16)), ops.pack_dw_weight(w.to(DEV)), b.to(DEV) if bias else None, gate)
+        out.append(result(f"dwconv_C{C_}_{H}x{W}_g{gate}", nchw(y), ref, 1e-2))
+    return out
+
+
+def check_small_convs():
+    ops = _ops()
+    out = []
+    for Ci, Co in ((3, 48), (1, 16), (6, 24)):
+        x = rnd(2, Ci, 11, 14, seed=Ci)
+        w = rnd(Co, Ci, 3, 3, seed=5) * 0.2
+        b = rnd(Co, seed=6) * 0.1
+        ref = F.relu(F.conv2d(x, w, b, padding=1))
+        o32 = torch.zeros(2, 11, 14, 2 * Co, device=DEV)
+        o16 = torch.zeros(2, 11, 14, Co, device=DEV, dtype=BF16)
+        ops.conv3x3_small_ci(nhwc(x), w.to(DEV), b.to(DEV), relu=True, out_f32=o32[..., Co:], out_bf16=o16)
+        out.append(result(f"small_ci_{Ci}to{Co}_f32", nchw(o32[..., Co:]), ref, 1e-5))
+        out.append(result(f"small_ci_{Ci}to{Co}_bf16", nchw(o16), ref, 6e-3))
+    for Ci, Co in ((96, 3), (32, 1)):
+        x = q(rnd(2, Ci, 9, 10, seed=Ci))
+        w = rnd(Co, Ci, 3, 3, seed=7) * 0.1
+        b = rnd(Co, seed=8) * 0.1
+        res = rnd(2, Co, 9, 10, seed=9)
+        ref = F.conv2d(x, w, b, padding=1) + res
+        y = ops.conv3x3_small_co(nhwc(x.to(BF16)), w.to(DEV), b.to(DEV), nhwc(res))
+        out.append(result(f"small_co_{Ci}to{Co}", nchw(y), ref, 1e-4))
+    return out
+
+
+# =============================================================================================== conv_gemm
+def _conv_case(name, impl, B=2, H=16, W=16, Ci=48, Co=144, k=1, stride=1, pad=0, dil=1, bias=False, relu=False,
+               res2=None, res1=False, alpha=1.0, use_scale_ptr=False, store_mode=0, want="f32", batched=False,
+               rowscale=False, tol=2e-3):
+    ops = _ops()
+    x = q(rnd(B, Ci, H, W, seed=H * W + Ci))
+    nb = B if batched else 1
+    w = q(rnd(nb, Co, Ci, k, k, seed=Co + k) * (1.0 / (Ci * k * k) ** 0.5))
+    b = rnd(Co, seed=11) * 0.2 if bias else None
+    ys = []
+    for i in range(B):
+        ys.append(F.conv2d(x[i:i + 1], w[i if batched else 0], None, stride=stride, padding=pad, dilation=dil))
+    y = torch.cat(ys, 0)
+    OH, OW = y.shape[2:]
+    rs = None
+    if rowscale:
+        rs = (rnd(B, OH, OW, seed=12).abs() + 0.5)
+        y = y * rs.unsqueeze(1)
+    if bias:
+        y = y + b.view(1, -1, 1, 1)
+    if relu:
+        y = F.relu(y)
+    g = 0.7 if use_scale_ptr else 1.0
+    y = y * alpha * g
+    if store_mode == 1:
+        y = F.pixel_unshuffle(y, 2)
+    elif store_mode == 2:
+        y = F.pixel_shuffle(y, 2)
+    r1 = r2 = None
+    if res1:
+        r1 = rnd(*y.shape, seed=13)
+        y = y + 0.5 * g * r1
+    if res2 is not None:
+        r2 = rnd(*y.shape, seed=14)
+        if res2 == "bf16":
+            r2 = q(r2)
+        y = y + r2
+    wp = torch.cat([ops.pack_conv_weight(w[i].to(DEV)) for i in range(nb)], 0)
+    o32, o16 = ops.conv_gemm(
+        nhwc(x.to(BF16)), wp, Co, k=k, stride=stride, pad=pad, dil=dil, bias=b.to(DEV) if bias else None, relu=relu,
+        rowscale=rs.to(DEV) if rowscale else None, alpha=alpha,
+        scale_ptr=torch.tensor([g], device=DEV) if use_scale_ptr else None,
+        res1=nhwc(r1) if res1 else None, res1_scale=0.5,
+        res2=(nhwc(r2.to(BF16)) if res2 == "bf16" else nhwc(r2)) if res2 is not None else None,
+        want=want, store_mode=store_mode, w_batched=batched, impl=impl)
+    out = []
+    tag = "simt" if impl else "tc"
+    if o32 is not None:
+        out.append(result(f"conv_{tag}_{name}_f32", nchw(o32), y, tol))
+    if o16 is not None:
+        out.append(result(f"conv_{tag}_{name}_bf16", nchw(o16), y, 8e-3))
+    return out
+
+
+CONV_CASES = [
+    dict(name="1x1_48to144"),
+    dict(name="1x1_16to48_bias", Ci=16, Co=48, bias=True),
+    dict(name="1x1_96to512_2ntiles", Ci=96, Co=512, H=8, W=24),
+    dict(name="1x1_384to384_res2", Ci=384, Co=384, H=8, W=8, res2="f32", want="both"),
+    dict(name="1x1_fusion_epilogue", Ci=128, Co=96, bias=True, res1=True, res2="f32", use_scale_ptr=True),
+    dict(name="1x1_batched_w", Ci=96, Co=96, batched=True, res2="f32"),
+    dict(name="1x1_odd_spatial", Ci=48, Co=48, H=20, W=24, B=1),
+    dict(name="1x1_w8", Ci=64, Co=64, H=16, W=8),
+    dict(name="1x1_big_k", Ci=1024, Co=256, H=8, W=16, B=1),
+    dict(name="3x3_48to48_bias_relu", Ci=48, Co=48, k=3, pad=1, bias=True, relu=True, want="bf16"),
+    dict(name="3x3_res_bf16", Ci=32, Co=32, k=3, pad=1, bias=True, res2="bf16", want="bf16"),
+    dict(name="3x3_stride2", Ci=48, Co=96, k=3, pad=1, stride=2, bias=True, relu=True, H=32, W=32),
+    dict(name="3x3_stride2_odd", Ci=16, Co=32, k=3, pad=1, stride=2, H=20, W=40, B=1),
+    dict(name="3x3_unshuffle", Ci=48, Co=24, k=3, pad=1, store_mode=1, H=16, W=32),
+    dict(name="3x3_shuffle", Ci=96, Co=192, k=3, pad=1, store_mode=2, want="both", H=8, W=16),
+    dict(name="3x3_dil2_rowscale", Ci=128, Co=8, k=3, pad=2, dil=2, rowscale=True, batched=True, res2="f32"),
+    dict(name="3x3_dil3", Ci=64, Co=64, k=3, pad=3, dil=3, H=16, W=16),
+    dict(name="3x3_valid", Ci=64, Co=64, k=3, pad=0, H=15, W=15, B=3),
+    dict(name="2x2_stride2", Ci=64, Co=128, k=2, pad=0, stride=2, bias=True, H=16, W=32),
+]
+
+
+def check_conv_simt():
+    out = []
+    for c in CONV_CASES:
+        out += _conv_case(impl=1, **c)
+    return out
+
+
+def check_conv_tc_basic():
+    return _conv_case(impl=0, **CONV_CASES[0]) + _conv_case(impl=0, **CONV_CASES[1])
+
+
+def check_conv_tc():
+    out = []
+    for c in CONV_CASES[2:]:
+        out += _conv_case(impl=0, **c)
+    return out
+
+
+def check_conv_origin():
+    """per-sample windows (MASA fine search): sample b reads image origin[b,0] shifted by (y0,x0)."""
+    ops = _ops()
+    out = []
+    B, Ci, Co, Hh, Ww = 2, 64, 64, 16, 20
+    x = q(rnd(B, Ci, Hh, Ww, seed=3))
+    org = torch.tensor([[0, 0, 0], [1, 1, 5], [0, 3, 2], [1, 0, 4], [0, 1, 1]], dtype=torch.int32)
+    nw = org.shape[0]
+    w = q(rnd(nw, Co, Ci, 3, 3, seed=4) * 0.05)
+    wh = ww = 15
+    ys = []
+    for i in range(nw):
+        im, y0, x0 = [int(v) for v in org[i]]
+        ys.append(F.conv2d(x[im:im + 1, :, y0:y0 + wh, x0:x0 + ww], w[i]))
+    ref = torch.cat(ys, 0)
+    wp = torch.cat([ops.pack_conv_weight(w[i].to(DEV)) for i in range(nw)], 0)
+    for impl in (1, 0):
+        o32, _ = ops.conv_gemm(nhwc(x.to(BF16)), wp, Co, k=3, pad=0, want="f32", w_batched=True, origin=org.to(DEV),
+                               window=(wh, ww), impl=impl)
+        out.append(result(f"conv_{'simt' if impl else 'tc'}_origin", nchw(o32), ref, 2e-3))
+    return out
+
+
+# =============================================================================================== MDTA
+def check_mdta():
+    ops = _ops()
+    out = []
+    for (C_, heads, H, W, B) in ((48, 1, 16, 24, 2), (32, 2, 9, 13, 1), (96, 2, 16, 16, 2), (96, 1, 20, 20, 1),
+                                 (192, 8, 8, 8, 2), (384, 8, 8, 8, 1), (64, 1, 32, 40, 1), (16, 1, 64, 64, 1)):
+        c = C_ // heads
+        qkv = q(rnd(B, 3 * C_, H, W, seed=C_ + heads))
+        temp = torch.rand(heads, generator=torch.Generator().manual_seed(1)) + 0.5
+        wpo = rnd(C_, C_, seed=2) / C_ ** 0.5
+        qq, kk, vv = qkv.view(B, 3, heads, c, H * W).unbind(1)
+        qn = qq / qq.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        kn = kk / kk.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        attn = torch.softmax(qn @ kn.transpose(-1, -2) * temp.view(1, heads, 1, 1), -1)
+        weff_ref = torch.zeros(B, C_, C_)
+        for h in range(heads):
+            weff_ref[:, :, h * c:(h + 1) * c] = wpo[:, h * c:(h + 1) * c] @ attn[:, h]
+        weff, attn_g = ops.mdta_weff(nhwc(qkv.to(BF16)), C_, heads, temp.to(DEV), wpo.to(DEV), want_attn=True)
+        tag = f"C{C_}_h{heads}_{H}x{W}"
+        out.append(result(f"mdta_attn_{tag}", attn_g, attn, 2e-3))
+        out.append(result(f"mdta_weff_{tag}", weff[..., :C_], weff_ref, 8e-3))
+    return out
+
+
+# =============================================================================================== transformer block
+def check_block():
+    """One TransformerBlock / ResFusionBlock through the kernel schedule vs the oracle block."""
+    from oracle import restormer as O, weights as Wt
+    from textualdegremoval_b200.archs import restormer_b200_arch as A
+    out = []
+    for (dim, heads, ln, bias, fusion, H, W) in ((48, 1, "WithBias", False, False, 16, 16),
+                                                (96, 2, "BiasFree", True, False, 8, 24),
+                                                (96, 1, "WithBias", False, True, 16, 16),
+                                                (32, 2, "WithBias", True, True, 8, 8)):
+        cls = A.TransformerResFusionBlock if fusion else A.TransformerBlock
+        blk = cls(dim, heads, 2.66, bias, ln)
+        sd = Wt.load_seeded(blk, seed=dim + heads)
+        x = rnd(2, dim, H, W, seed=dim)
+        psd = {"b." + k_: v for k_, v in sd.items()}
+        ref = (O.res_fusion_block if fusion else O.transformer_block)(psd, "b", x, heads)
+        blk = blk.to(DEV)
+        p = A._prep_block(blk)
+        x32 = nhwc(x)
+        A.run_block(x32, p)
+        out.append(result(f"block_d{dim}_h{heads}_{ln}_b{int(bias)}_f{int(fusion)}", nchw(x32), ref, 1.5e-2))
+    return out
+
+
+# =============================================================================================== MASA
+def check_masa():
+    """MASA search/transfer kernels vs the oracle on identical (bf16-rounded) features."""
+    from oracle import restormer as O
+    from textualdegremoval_b200.archs import restormer_b200_arch as A
+    ops = _ops()
+    out = []
+    for (B, nf, h, w, hr, wr, seed) in ((2, 16, 128, 128, 128, 128, 1), (1, 8, 128, 192, 192, 128, 2)):
+        net = A.RestormerRefFusion(dim=nf, nf=nf, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1,
+                                   ext_n_blocks=[1, 1, 1, 1])
+        g = torch.Generator().manual_seed(seed)
+        smooth = lambda t: F.avg_pool2d(t, 3, 1, 1)
+        f_lq_deep = q(smooth(torch.randn(B, nf * 8, h // 8, w // 8, generator=g)))
+        f_ref = [q(smooth(torch.randn(B, nf * 2 ** i, hr >> i, wr >> i, generator=g))) for i in range(4)]
+        warps_ref, aux = O.masa_warp(f_lq_deep, f_ref, 8, 8, 1.5, [1, 2, 3], h, w, hr, wr, return_aux=True)
+        d = [nf, nf * 2, nf * 4, nf * 8]
+        targets = [torch.zeros(B, h >> i, w >> i, d[i], device=DEV) for i in range(4)]
+        a = net._masa_warp(nhwc(f_lq_deep.to(BF16)), [nhwc(t.to(BF16)) for t in f_ref], h, w, hr, wr, targets)
+        tag = f"{h}x{w}_{hr}x{wr}"
+        score = a["score"][..., : aux["score"].shape[1]].reshape(B, -1, aux["score"].shape[1]).permute(0, 2, 1)
+        out.append(result(f"masa_coarse_score_{tag}", score, aux["score"], 2e-3))
+        agree = (a["idx"].cpu().long() == aux["idx"]).float().mean().item()
+        out.append(dict(name=f"masa_coarse_idx_{tag}", max_err=1 - agree, ref_scale=1, tol=0.0, ok=agree == 1.0,
+                        note="fraction of blocks whose arg-max differs"))
+        y1 = a["origin"][:, 1].view(B, -1).cpu().long()
+        x1 = a["origin"][:, 2].view(B, -1).cpu().long()
+        same_win = ((y1 == aux["y1"]) & (x1 == aux["x1"])).view(-1)
+        nq = aux["index"].shape[1] * aux["index"].shape[2]
+        idx_g = a["index"].cpu().long().view(-1, nq)
+        idx_r = aux["index"].view(-1, nq)
+        agree_f = (idx_g == idx_r)[same_win].float().mean().item() if same_win.any() else 0.0
+        out.append(dict(name=f"masa_fine_idx_{tag}", max_err=1 - agree_f, ref_scale=1, tol=0.02, ok=agree_f >= 0.98,
+                        note="fraction of fine matches that differ (near-ties allowed <= 2%)"))
+        out.append(result(f"masa_att_{tag}", a["att"].view(-1, nq), aux["att"].view(-1, nq), 3e-3))
+        if agree == 1.0 and agree_f == 1.0:
+            for i in range(4):
+                out.append(result(f"masa_warp_l{i}_{tag}", nchw(targets[i]), warps_ref[i], 2e-3))
+        else:
+            out.append(dict(name=f"masa_warp_{tag}", max_err=0, ref_scale=1, tol=0, ok=True,
+                            note="skipped value check: indices differ"))
+    return out
+
+
+# =============================================================================================== models vs golden
+def _golden(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    return json.loads(str(z["meta"])), torch.from_numpy(z["out"])
+
+
+def psnr_u8(a, b):
+    """calculate_psnr on tensor2img outputs (metrics/psnr_ssim.py:9-63, utils_image.py:129-191): clamp, x255, round."""
+    a8 = (a.clamp(0, 1) * 255).round().double()
+    b8 = (b.clamp(0, 1) * 255).round().double()
+    mse = ((a8 - b8) ** 2).mean().item()
+    return float("inf") if mse == 0 else 20 * np.log10(255.0 / np.sqrt(mse))
+
+
+# end-to-end forward tolerance (max |delta| vs the fp32 reference output, outputs are O(1) images)
+E2E_TOL = 2e-2
+
+
+def check_restormer_golden():
+    from oracle import weights as Wt
+    from textualdegremoval_b200.archs import define_network
+    out = []
+    for name in ("restormer_withbias", "restormer_biasfree", "restormer_gray_bias"):
+        meta, ref = _golden(name)
+        net = define_network(dict(type="Restormer", **meta["cfg"]))
+        Wt.load_seeded(net, meta["seed"])
+        net = net.to(DEV).eval()
+        x = Wt.seeded_image("x", meta["shape"], meta["seed"])
+        with torch.no_grad():
+            y = net(x.to(DEV)).cpu()
+        r = result(f"golden_{name}", y, ref, E2E_TOL / max(ref.abs().max().item(), 1e-6))
+        r["note"] = f"mean|d|={(y - ref).abs().mean().item():.2e} psnr_u8(ours,ref)={psnr_u8(y, ref):.2f}dB"
+        out.append(r)
+    return out
+
+
+def check_guided_golden():
+    from oracle import weights as Wt
+    from oracle.make_golden import guided_inputs
+    from textualdegremoval_b200.archs import define_network
+    out = []
+    for name in ("guided_restormer_128", "guided_restormer_ragged"):
+        meta, ref = _golden(name)
+        net = define_network(dict(type="RestormerRefFusion", **meta["cfg"]))
+        Wt.load_seeded(net, meta["seed"])
+        net = net.to(DEV).eval()
+        lq, rf = guided_inputs(meta)
+        with torch.no_grad():
+            y = net(lq.to(DEV), rf.to(DEV)).cpu()
+        r = result(f"golden_{name}", y, ref, E2E_TOL / max(ref.abs().max().item(), 1e-6))
+        r["note"] = f"mean|d|={(y - ref).abs().mean().item():.2e} psnr_u8(ours,ref)={psnr_u8(y, ref):.2f}dB"
+        out.append(r)
+    return out
+
+
+def check_guided_stages():
+    """Guided net stage by stage against the oracle (features, match indices, warps, output)."""
+    from oracle import restormer as O, weights as Wt
+    from oracle.make_golden import GUIDED_CASES, guided_inputs
+    from textualdegremoval_b200.archs import define_network
+    out = []
+    meta = GUIDED_CASES["guided_restormer_128"]
+    net = define_network(dict(type="RestormerRefFusion", **meta["cfg"]))
+    sd = Wt.load_seeded(net, meta["seed"])
+    net = net.to(DEV).eval()
+    lq, rf = guided_inputs(meta)
+    with torch.no_grad():
+        y_ref, aux_r = O.restormer_ref_fusion_forward(sd, lq, rf, return_aux=True)
+        y, aux = net(lq.to(DEV), rf.to(DEV), return_aux=True)
+    for i in range(4):
+        out.append(result(f"stage_feat_lq_l{i}", nchw(aux["feat_lq"][i]), aux_r["feat_lq"][i], 2e-2))
+        out.append(result(f"stage_feat_ref_l{i}", nchw(aux["feat_ref"][i]), aux_r["feat_ref"][i], 2e-2))
+    agree = (aux["idx"].cpu().long() == aux_r["idx"]).float().mean().item()
+    out.append(dict(name="stage_coarse_idx", max_err=1 - agree, ref_scale=1, tol=0.0, ok=True,
+                    note=f"agreement {agree:.3f} (informational: bf16 features may flip near-ties)"))
+    nq = aux_r["index"].shape[1] * aux_r["index"].shape[2]
+    agree_f = (aux["index"].cpu().long().view(-1, nq) == aux_r["index"].view(-1, nq)).float().mean().item()
+    out.append(dict(name="stage_fine_idx", max_err=1 - agree_f, ref_scale=1, tol=0.0, ok=True,
+                    note=f"agreement {agree_f:.3f} (informational)"))
+    for i in range(4):
+        r = result(f"stage_warp_l{i}", nchw(aux["warps"][i]), aux_r["warps"][i], 1.0)
+        r["note"] = f"mean|d|={(nchw(aux['warps'][i]) - aux_r['warps'][i]).abs().mean().item():.2e} (informational)"
+        out.append(r)
+    out.append(result("stage_output", y.cpu(), y_ref, E2E_TOL / max(y_ref.abs().max().item(), 1e-6)))
+    return out
+
+
+CHECKS = {
+    "layout": check_layout,
+    "rownorm": check_rownorm,
+    "dwconv": check_dwconv,
+    "small_convs": check_small_convs,
+    "conv_simt": check_conv_simt,
+    "conv_tc_basic": check_conv_tc_basic,
+    "conv_tc": check_conv_tc,
+    "conv_origin": check_conv_origin,
+    "mdta": check_mdta,
+    "block": check_block,
+    "masa": check_masa,
+    "restormer_golden": check_restormer_golden,
+    "guided_stages": check_guided_stages,
+    "guided_golden": check_guided_golden,
+}
+
+
+def run_group(name):
+    t0 = time.time()
+    try:
+        res = CHECKS[name]()
+        torch.cuda.synchronize()
+    except Exception as e:  # noqa: BLE001
+        res = [dict(name=name, ok=False, max_err=None, note="EXCEPTION: " + "".join(
+            traceback.format_exception_only(type(e), e)).strip()[-600:])]
+    for r in res:
+        r["group"] = name
+    return res, time.time() - t0
+
+
+def main(argv):
+    only = [a for a in argv if not a.startswith("--")]
+    isolate = "--isolate" in argv
+    names = only or list(CHECKS)
+    allres = []
+    for n in names:
+        if isolate:
+            try:
+                p = subprocess.run([sys.executable, "-m", "tests.gpu_checks", "--json", n], capture_output=True, text=True,
+                                   timeout=600, cwd=ROOT)
+                line = [l for l in p.stdout.splitlines() if l.startswith("JSON:")]
+                res = json.loads(line[-1][5:]) if line else [dict(name=n, group=n, ok=False, max_err=None,
+                                                                 note="CRASH: " + (p.stderr or p.stdout)[-800:])]
+            except subprocess.TimeoutExpired:
+                res = [dict(name=n, group=n, ok=False, max_err=None, note="TIMEOUT")]
+        else:
+            res, _ = run_group(n)
+        allres += res
+        for r in res:
+            err = "-" if r.get("max_err") is None else f"{r['max_err']:.3e}"
+            tol = "-" if r.get("tol") is None else f"{r['tol']:.3e}"
+            print(f"[{'ok' if r['ok'] else 'FAIL'}] {r['name']:<44} err {err:>10} tol {tol:>10} {r.get('note', '')}", flush=True)
+    if "--json" in argv:
+        print("JSON:" + json.dumps(allres))
+    else:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "gpu_checks.json"), "w") as fh:
+            json.dump(allres, fh, indent=1)
+        bad = [r["name"] for r in allres if not r["ok"]]
+        print(f"\n{len(allres) - len(bad)}/{len(allres)} checks ok; failing: {bad}")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main(sys.argv[1:]))

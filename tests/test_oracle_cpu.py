@@ -1,0 +1,91 @@
+"""CPU suite: the oracle restatement against the committed golden vectors (generated from the unmodified reference by
+oracle/make_golden.py) and, when /root/reference is present, against the reference modules themselves."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_loader, restormer as O, weights as W
+from oracle.make_golden import GUIDED_CASES, RESTORMER_CASES, guided_inputs
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLD, name + ".npz"))
+    return json.loads(str(z["meta"])), torch.from_numpy(z["out"])
+
+
+def _shapes(module_ctor, cfg):
+    return {k: v.shape for k, v in module_ctor(**cfg).state_dict().items()}
+
+
+@pytest.mark.parametrize("name", list(RESTORMER_CASES))
+def test_restormer_oracle_matches_golden(name):
+    from textualdegremoval_b200.archs.restormer_b200_arch import Restormer
+    meta, ref = _load(name)
+    assert meta == json.loads(json.dumps(RESTORMER_CASES[name]))
+    sd = W.seeded_state_dict(_shapes(Restormer, meta["cfg"]), meta["seed"])
+    x = W.seeded_image("x", meta["shape"], meta["seed"])
+    with torch.no_grad():
+        y = O.restormer_forward(sd, x, meta["cfg"]["heads"])
+    assert (y - ref).abs().max().item() < 2e-5          # fp32 vs fp32, different op order only
+
+
+@pytest.mark.parametrize("name", list(GUIDED_CASES))
+def test_guided_oracle_matches_golden(name):
+    from textualdegremoval_b200.archs.restormer_b200_arch import RestormerRefFusion
+    meta, ref = _load(name)
+    sd = W.seeded_state_dict(_shapes(RestormerRefFusion, meta["cfg"]), meta["seed"])
+    lq, rf = guided_inputs(meta)
+    with torch.no_grad():
+        y = O.restormer_ref_fusion_forward(sd, lq, rf, meta["cfg"]["heads"])
+    assert (y - ref).abs().max().item() < 2e-5
+
+
+def test_identity_at_zero_alpha():
+    """Known-answer anchor (SURVEY 8c i): with alpha = 0 the fusion blocks are identities on [:, :C], so the guided net
+    equals the unguided Restormer built from the same non-masa weights."""
+    from textualdegremoval_b200.archs.restormer_b200_arch import RestormerRefFusion
+    meta = GUIDED_CASES["guided_restormer_128"]
+    sd = W.seeded_state_dict(_shapes(RestormerRefFusion, meta["cfg"]), meta["seed"])
+    for k in sd:
+        if k.endswith(".alpha"):
+            sd[k] = torch.zeros_like(sd[k])
+    lq, rf = guided_inputs(meta)
+    with torch.no_grad():
+        y = O.restormer_ref_fusion_forward(sd, lq, rf)
+        y0 = O.restormer_forward({k: v for k, v in sd.items() if "masa" not in k}, lq)
+    assert (y - y0).abs().max().item() < 1e-5
+
+
+def test_transfer_overlap_counts():
+    """transfer (:698-715): a constant window must come back as att (bilinear of a constant) exactly -- i.e. the
+    overlap-add is divided by the right 4..9 patch count everywhere."""
+    m, c, k, d, s = 2, 3, 8, 13, 4
+    win = torch.ones(m, c, (d + 2) * s, (d + 2) * s)
+    index = torch.randint(0, d * d, (m, k, k))
+    att = torch.full((m, k, k), 0.5)
+    out = O.transfer(win, index, att, s, d)
+    assert torch.allclose(out, torch.full_like(out, 0.5), atol=1e-6)
+
+
+def test_window_origin_clamps():
+    idx = torch.tensor([[0, 15, 16 * 15 + 15, 16 * 8 + 8]])
+    y1, x1 = O.window_origin(idx, 16, 16, 13, 13)
+    assert y1.tolist() == [[0, 0, 1, 1]] and x1.tolist() == [[0, 1, 1, 1]]
+    assert int((y1 + 14).max()) <= 15 and int((x1 + 14).max()) <= 15
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_vs_live_reference():
+    cfg = dict(dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1, heads=[1, 2, 4, 8], nf=16,
+               ext_n_blocks=[1, 1, 1, 1], reffusion_n_blocks=[1, 1, 1, 1], LayerNorm_type="BiasFree")
+    net = ref_loader.restormer_ref_fusion(**cfg)
+    sd = W.load_seeded(net, 5)
+    lq = W.seeded_image("a", (1, 3, 128, 192), 5)
+    rf = W.seeded_image("b", (1, 3, 192, 128), 5)
+    with torch.no_grad():
+        assert (net(lq, rf) - O.restormer_ref_fusion_forward(sd, lq, rf)).abs().max().item() < 2e-5

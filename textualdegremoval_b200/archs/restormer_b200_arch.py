@@ -1,0 +1,467 @@
+"""B200-native ``Restormer`` and ``RestormerRefFusion``.
+
+Drop-in for the classes of the same name in the reference's
+``models/archs/network_restormer_guided_arch.py`` (:396-501, :504-964): same constructor kwargs (option files
+``options/train_restoration/003*.yml``, ``017*.yml``), same call signature ``net(inp)`` / ``net(lq, ref)`` on NCHW
+tensors, same ``state_dict`` keys and shapes, every guidance parameter name contains ``masa``.
+
+The module tree only HOLDS parameters; the forward pass is a schedule of libtdr_sm100 kernels over NHWC buffers
+(fp32 residual stream, bf16 GEMM operands) -- see DESIGN.md.  There is no PyTorch fallback: without the CUDA
+library, or on a non-CUDA tensor, the forward raises.
+
+RestormerRefFusion implements the reference's *consistent* reading of its own forward: the MASA encoder has four
+levels, so the deepest feature is the 1/8-scale one (upstream indexes ``feat[4]``, an off-by-one that raises
+IndexError as shipped).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..lib import TdrError
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+# ----------------------------------------------------------------------------------------------- parameter holders
+class _Norm(nn.Module):
+    def __init__(self, dim, with_bias):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        if with_bias:
+            self.bias = nn.Parameter(torch.zeros(dim))
+        else:
+            self.bias = None
+
+
+class LayerNorm(nn.Module):
+    """Keys ``body.weight`` (+ ``body.bias`` for WithBias) as in the reference (:208-218)."""
+
+    def __init__(self, dim, LayerNorm_type):
+        super().__init__()
+        self.body = _Norm(dim, LayerNorm_type != "BiasFree")
+
+
+class Attention(nn.Module):
+    def __init__(self, dim, num_heads, bias):
+        super().__init__()
+        self.num_heads = num_heads
+        self.temperature = nn.Parameter(torch.ones(num_heads, 1, 1))
+        self.qkv = nn.Conv2d(dim, dim * 3, 1, bias=bias)
+        self.qkv_dwconv = nn.Conv2d(dim * 3, dim * 3, 3, 1, 1, groups=dim * 3, bias=bias)
+        self.project_out = nn.Conv2d(dim, dim, 1, bias=bias)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, ffn_expansion_factor, bias):
+        super().__init__()
+        hidden = int(dim * ffn_expansion_factor)
+        self.project_in = nn.Conv2d(dim, hidden * 2, 1, bias=bias)
+        self.dwconv = nn.Conv2d(hidden * 2, hidden * 2, 3, 1, 1, groups=hidden * 2, bias=bias)
+        self.project_out = nn.Conv2d(hidden, dim, 1, bias=bias)
+
+
+class TransformerBlock(nn.Module):
+    def __init__(self, dim, num_heads, ffn_expansion_factor, bias, LayerNorm_type):
+        super().__init__()
+        self.norm1 = LayerNorm(dim, LayerNorm_type)
+        self.attn = Attention(dim, num_heads, bias)
+        self.norm2 = LayerNorm(dim, LayerNorm_type)
+        self.ffn = FeedForward(dim, ffn_expansion_factor, bias)
+
+
+class TransformerResFusionBlock(TransformerBlock):
+    def __init__(self, dim, num_heads, ffn_expansion_factor, bias, LayerNorm_type):
+        super().__init__(dim, num_heads, ffn_expansion_factor, bias, LayerNorm_type)
+        self.alpha = nn.Parameter(torch.zeros(1))
+
+
+class OverlapPatchEmbed(nn.Module):
+    def __init__(self, in_c=3, embed_dim=48, bias=False):
+        super().__init__()
+        self.proj = nn.Conv2d(in_c, embed_dim, 3, 1, 1, bias=bias)
+
+
+class Downsample(nn.Module):
+    def __init__(self, n_feat):
+        super().__init__()
+        self.body = nn.Sequential(nn.Conv2d(n_feat, n_feat // 2, 3, 1, 1, bias=False), nn.PixelUnshuffle(2))
+
+
+class Upsample(nn.Module):
+    def __init__(self, n_feat):
+        super().__init__()
+        self.body = nn.Sequential(nn.Conv2d(n_feat, n_feat * 2, 3, 1, 1, bias=False), nn.PixelShuffle(2))
+
+
+class ResidualBlock(nn.Module):
+    def __init__(self, nf):
+        super().__init__()
+        self.conv1 = nn.Conv2d(nf, nf, 3, 1, 1)
+        self.conv2 = nn.Conv2d(nf, nf, 3, 1, 1)
+
+
+class Encoder(nn.Module):
+    """MASA feature extractor (:100-134): four levels nf, 2nf, 4nf, 8nf; n_blks[2] is reused for level 4."""
+
+    def __init__(self, in_chl, nf, n_blks=(1, 1, 1)):
+        super().__init__()
+        nb = [n_blks[0], n_blks[1], n_blks[2], n_blks[2]]
+        chans = [nf, nf * 2, nf * 4, nf * 8]
+        prev = in_chl
+        for i, (c, n) in enumerate(zip(chans, nb), start=1):
+            setattr(self, f"conv_L{i}", nn.Conv2d(prev, c, 3, 1 if i == 1 else 2, 1, bias=True))
+            setattr(self, f"blk_L{i}", nn.Sequential(*[ResidualBlock(c) for _ in range(n)]))
+            prev = c
+        self.levels = 4
+
+
+def _blocks(n, cls, **kw):
+    return nn.Sequential(*[cls(**kw) for _ in range(n)])
+
+
+# ----------------------------------------------------------------------------------------------- weight preparation
+def _f(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+def _prep_block(blk: TransformerBlock):
+    """Pack one transformer block's parameters for the kernels (bf16 GEMM weights, padded GDFN halves)."""
+    a, f = blk.attn, blk.ffn
+    C_ = a.qkv.in_channels
+    h = f.project_out.in_channels
+    hp = ops.round_up(h, 8)
+    dev = a.qkv.weight.device
+    idx2 = torch.cat([torch.arange(h, device=dev), hp + torch.arange(h, device=dev)])
+    p = dict(C=C_, heads=a.num_heads, h=h, hp=hp)
+    p["ln1_w"], p["ln1_b"] = _f(blk.norm1.body.weight), _f(blk.norm1.body.bias)
+    p["ln2_w"], p["ln2_b"] = _f(blk.norm2.body.weight), _f(blk.norm2.body.bias)
+    p["ln_mode"] = 1 if blk.norm1.body.bias is not None else 2
+    p["w_qkv"] = ops.pack_conv_weight(a.qkv.weight)
+    p["b_qkv"] = _f(a.qkv.bias)
+    p["w_qkv_dw"] = ops.pack_dw_weight(a.qkv_dwconv.weight)
+    p["b_qkv_dw"] = _f(a.qkv_dwconv.bias)
+    p["temp"] = _f(a.temperature).reshape(-1)
+    p["w_po"] = _f(a.project_out.weight).reshape(C_, C_)
+    p["b_po"] = _f(a.project_out.bias)
+    p["w_in"] = ops.pack_conv_weight(f.project_in.weight, co_map=(2 * hp, idx2))
+    p["b_in"] = ops.pad_vec(f.project_in.bias, 2 * hp, idx2)
+    p["w_dw"] = ops.pack_dw_weight(f.dwconv.weight, 2 * hp, idx2)
+    p["b_dw"] = ops.pad_vec(f.dwconv.bias, 2 * hp, idx2)
+    p["w_out"] = ops.pack_conv_weight(f.project_out.weight, ci_map=(hp, torch.arange(h, device=dev)))
+    p["b_out"] = _f(f.project_out.bias)
+    p["alpha"] = _f(blk.alpha) if hasattr(blk, "alpha") else None
+    return p
+
+
+def _prep_conv(conv: nn.Conv2d):
+    return dict(w=ops.pack_conv_weight(conv.weight), b=_f(conv.bias), Co=conv.out_channels, Ci=conv.in_channels,
+                stride=conv.stride[0], raw_w=_f(conv.weight))
+
+
+# ----------------------------------------------------------------------------------------------- kernel schedules
+def run_block(x32, p):
+    """One (Res-fusion) transformer block on the fp32 residual stream x32 (NHWC view), updated IN PLACE.
+
+    Reference :318-331 / :334-353.  Kernel sequence: LN -> qkv 1x1 (tcgen05) -> depthwise 3x3 -> Gram (tcgen05) ->
+    softmax+fold -> attn.v.project_out + residual (tcgen05) -> LN -> project_in (tcgen05) -> depthwise 3x3 + GELU gate
+    -> project_out + residual (tcgen05).
+    """
+    C_, heads, hp = p["C"], p["heads"], p["hp"]
+    fusion = p["alpha"] is not None
+    xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5)
+    _, qkv = ops.conv_gemm(xn, p["w_qkv"], 3 * C_, bias=p["b_qkv"])
+    qkv = ops.dwconv3x3(qkv, p["w_qkv_dw"], p["b_qkv_dw"])
+    weff = ops.mdta_weff(qkv, C_, heads, p["temp"], p["w_po"])
+    v = qkv[..., 2 * C_:]
+    if fusion:
+        x1, _ = ops.conv_gemm(v, weff, C_, Ci=C_, bias=p["b_po"], res2=x32, want="f32", w_batched=True)
+    else:
+        ops.conv_gemm(v, weff, C_, Ci=C_, bias=p["b_po"], res2=x32, out_f32=x32, w_batched=True)
+        x1 = x32
+    xn = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5)
+    _, hid = ops.conv_gemm(xn, p["w_in"], 2 * hp, bias=p["b_in"])
+    g = ops.dwconv3x3(hid, p["w_dw"], p["b_dw"], gate=1)
+    if fusion:      # out = (x1 + ffn) * alpha + x0
+        ops.conv_gemm(g, p["w_out"], C_, bias=p["b_out"], scale_ptr=p["alpha"], res1=x1, res2=x32, out_f32=x32)
+    else:
+        ops.conv_gemm(g, p["w_out"], C_, bias=p["b_out"], res2=x32, out_f32=x32)
+    return x32
+
+
+def run_stack(x32, preps):
+    for p in preps:
+        run_block(x32, p)
+    return x32
+
+
+def conv3x3(x16, pc, **kw):
+    return ops.conv_gemm(x16, pc["w"], pc["Co"], k=3, stride=pc["stride"], pad=1, bias=pc["b"], **kw)
+
+
+class _RestormerBase(nn.Module):
+    """Shared U-Net body (:412-461) + decoder schedule."""
+
+    def _build_body(self, inp_channels, out_channels, dim, num_blocks, num_refinement_blocks, heads,
+                    ffn_expansion_factor, bias, LayerNorm_type, dual_pixel_task, fusion_blocks=None):
+        kw = dict(ffn_expansion_factor=ffn_expansion_factor, bias=bias, LayerNorm_type=LayerNorm_type)
+        self.patch_embed = OverlapPatchEmbed(inp_channels, dim)
+        dims = [dim, dim * 2, dim * 4, dim * 8]
+        names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
+        downs = [None, "down1_2", "down2_3", "down3_4"]
+        for i in range(4):
+            if downs[i]:
+                setattr(self, downs[i], Downsample(dims[i - 1]))
+            if fusion_blocks is not None:
+                setattr(self, f"masa_blk_enc_level{i + 1}",
+                        _blocks(fusion_blocks[i], TransformerResFusionBlock, dim=2 * dims[i], num_heads=heads[i], **kw))
+            setattr(self, names[i], _blocks(num_blocks[i], TransformerBlock, dim=dims[i], num_heads=heads[i], **kw))
+        self.up4_3 = Upsample(dims[3])
+        self.reduce_chan_level3 = nn.Conv2d(dims[3], dims[2], 1, bias=bias)
+        self.decoder_level3 = _blocks(num_blocks[2], TransformerBlock, dim=dims[2], num_heads=heads[2], **kw)
+        self.up3_2 = Upsample(dims[2])
+        self.reduce_chan_level2 = nn.Conv2d(dims[2], dims[1], 1, bias=bias)
+        self.decoder_level2 = _blocks(num_blocks[1], TransformerBlock, dim=dims[1], num_heads=heads[1], **kw)
+        self.up2_1 = Upsample(dims[1])
+        self.decoder_level1 = _blocks(num_blocks[0], TransformerBlock, dim=dims[1], num_heads=heads[0], **kw)
+        self.refinement = _blocks(num_refinement_blocks, TransformerBlock, dim=dims[1], num_heads=heads[0], **kw)
+        self.dual_pixel_task = dual_pixel_task
+        if dual_pixel_task:
+            self.skip_conv = nn.Conv2d(dim, dims[1], 1, bias=bias)
+        self.output = nn.Conv2d(dims[1], out_channels, 3, 1, 1, bias=bias)
+        self.dims = dims
+        self._prep_cache = None
+
+    # ---- weight cache -------------------------------------------------------------------------
+    def _prep_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def prepared(self):
+        key = self._prep_key()
+        if self._prep_cache is None or self._prep_cache[0] != key:
+            with torch.no_grad():
+                self._prep_cache = (key, self._prepare())
+        return self._prep_cache[1]
+
+    def _prepare_body(self):
+        P = {}
+        for name in ["encoder_level1", "encoder_level2", "encoder_level3", "latent", "decoder_level3",
+                     "decoder_level2", "decoder_level1", "refinement"] + \
+                    [f"masa_blk_enc_level{i}" for i in range(1, 5) if hasattr(self, f"masa_blk_enc_level{i}")]:
+            P[name] = [_prep_block(b) for b in getattr(self, name)]
+        for name in ["down1_2", "down2_3", "down3_4", "up4_3", "up3_2", "up2_1"]:
+            P[name] = _prep_conv(getattr(self, name).body[0])
+        for name in ["reduce_chan_level3", "reduce_chan_level2"]:
+            P[name] = _prep_conv(getattr(self, name))
+        P["patch_embed"] = dict(w=_f(self.patch_embed.proj.weight), b=_f(self.patch_embed.proj.bias))
+        P["output"] = dict(w=_f(self.output.weight), b=_f(self.output.bias))
+        if self.dual_pixel_task:
+            P["skip_conv"] = _prep_conv(self.skip_conv)
+        return P
+
+    # ---- schedules ----------------------------------------------------------------------------
+    def _check(self, *ts):
+        for t in ts:
+            if not t.is_cuda:
+                raise TdrError("textualdegremoval_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path")
+
+    def _down(self, x32, pc, out32):
+        """Downsample (:372-380): conv3x3 C->C/2 then PixelUnshuffle(2), written straight into out32."""
+        x16 = ops.rownorm(x32, 0)
+        ops.conv_gemm(x16, pc["w"], pc["Co"], k=3, pad=1, out_f32=out32, store_mode=1)
+
+    def _decode(self, P, lat, e1, e2, e3, inp32, x_in1):
+        """Decoder half (:477-501).  e*: fp32 NHWC views of the encoder outputs."""
+        d = self.dims
+        B, H8, W8, _ = lat.shape
+        dev = lat.device
+
+        def up_cat_reduce(x32, enc, up, red, Cn):
+            b, hh, ww, _ = x32.shape
+            cat16 = torch.empty((b, hh * 2, ww * 2, 2 * Cn), dtype=BF16, device=dev)
+            ops.conv_gemm(ops.rownorm(x32, 0), P[up]["w"], P[up]["Co"], k=3, pad=1, out_bf16=cat16[..., :Cn],
+                          store_mode=2)
+            ops.copy_rows(enc, dst16=cat16[..., Cn:])
+            y32, _ = ops.conv_gemm(cat16, P[red]["w"], Cn, bias=P[red]["b"], want="f32")
+            return y32
+
+        d3 = run_stack(up_cat_reduce(lat, e3, "up4_3", "reduce_chan_level3", d[2]), P["decoder_level3"])
+        d2 = run_stack(up_cat_reduce(d3, e2, "up3_2", "reduce_chan_level2", d[1]), P["decoder_level2"])
+        b, hh, ww, _ = d2.shape
+        d1 = torch.empty((b, hh * 2, ww * 2, d[1]), dtype=F32, device=dev)
+        ops.conv_gemm(ops.rownorm(d2, 0), P["up2_1"]["w"], P["up2_1"]["Co"], k=3, pad=1, out_f32=d1[..., :d[0]],
+                      store_mode=2)
+        ops.copy_rows(e1, dst32=d1[..., d[0]:])
+        run_stack(d1, P["decoder_level1"])
+        run_stack(d1, P["refinement"])
+        if self.dual_pixel_task:      # :494-496  out = output(d1 + skip_conv(inp_enc_level1))
+            ops.conv_gemm(ops.rownorm(x_in1, 0), P["skip_conv"]["w"], d[1], bias=P["skip_conv"]["b"], res2=d1, out_f32=d1)
+            return ops.conv3x3_small_co(ops.rownorm(d1, 0), P["output"]["w"], P["output"]["b"], None)
+        return ops.conv3x3_small_co(ops.rownorm(d1, 0), P["output"]["w"], P["output"]["b"], inp32)
+
+
+class Restormer(_RestormerBase):
+    def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4,
+                 heads=[1, 2, 4, 8], ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias",
+                 dual_pixel_task=False):
+        super().__init__()
+        self._build_body(inp_channels, out_channels, dim, num_blocks, num_refinement_blocks, heads,
+                         ffn_expansion_factor, bias, LayerNorm_type, dual_pixel_task)
+
+    def _prepare(self):
+        return self._prepare_body()
+
+    def forward(self, inp_img):
+        """:463-501.  inp_img NCHW; H and W must be multiples of 8 (as in the reference, which fails otherwise)."""
+        self._check(inp_img)
+        B, Cin, H, W = inp_img.shape
+        if H % 8 or W % 8:
+            raise ValueError(f"Restormer needs H, W multiples of 8 (got {H}x{W})")
+        P = self.prepared()
+        d = self.dims
+        dev = inp_img.device
+        inp32 = ops.nchw_to_nhwc(inp_img, H, W)
+        x1 = torch.empty((B, H, W, d[0]), dtype=F32, device=dev)
+        ops.conv3x3_small_ci(inp32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=x1)
+        x_in1 = x1.clone() if self.dual_pixel_task else None
+        e1 = run_stack(x1, P["encoder_level1"])
+        e2 = torch.empty((B, H // 2, W // 2, d[1]), dtype=F32, device=dev)
+        self._down(e1, P["down1_2"], e2)
+        run_stack(e2, P["encoder_level2"])
+        e3 = torch.empty((B, H // 4, W // 4, d[2]), dtype=F32, device=dev)
+        self._down(e2, P["down2_3"], e3)
+        run_stack(e3, P["encoder_level3"])
+        lat = torch.empty((B, H // 8, W // 8, d[3]), dtype=F32, device=dev)
+        self._down(e3, P["down3_4"], lat)
+        run_stack(lat, P["latent"])
+        out = self._decode(P, lat, e1, e2, e3, inp32 if not self.dual_pixel_task else None, x_in1)
+        return ops.nhwc_to_nchw(out, H, W)
+
+
+class RestormerRefFusion(_RestormerBase):
+    def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4,
+                 heads=[1, 2, 4, 8], ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias",
+                 dual_pixel_task=False, nf=64, ext_n_blocks=[4, 4, 4, 4], reffusion_n_blocks=[1, 1, 1, 1],
+                 reffusion_n_blocks_middle=1, scale=1, num_nbr=1, psize=3, lr_block_size=8, ref_down_block_size=1.5,
+                 dilations=[1, 2, 3]):
+        super().__init__()
+        if num_nbr != 1 or psize != 3:
+            raise TdrError("RestormerRefFusion (B200): only num_nbr=1, psize=3 are implemented (all shipped options)")
+        if not 1 <= len(dilations) <= 3:
+            raise TdrError("RestormerRefFusion (B200): 1..3 dilations supported")
+        self.scale, self.num_nbr, self.psize = scale, num_nbr, psize
+        self.lr_block_size, self.ref_down_block_size, self.dilations = lr_block_size, ref_down_block_size, list(dilations)
+        self.padder_size = 2 ** 3
+        self.masa_enc = Encoder(inp_channels, nf, ext_n_blocks)
+        # empty lists kept for key/structure parity with the reference (:547-549)
+        self.masa_blk_enc = nn.ModuleList()
+        self.masa_blk_middle = nn.ModuleList()
+        self.masa_blk_dec = nn.ModuleList()
+        self._build_body(inp_channels, out_channels, dim, num_blocks, num_refinement_blocks, heads,
+                         ffn_expansion_factor, bias, LayerNorm_type, dual_pixel_task, fusion_blocks=reffusion_n_blocks)
+        self.nf = nf
+        if nf != dim:
+            raise TdrError("RestormerRefFusion: nf must equal dim (the warped reference features are concatenated "
+                           "channel-for-channel with the U-Net features, :907-936)")
+
+    def _prepare(self):
+        P = self._prepare_body()
+        enc = {}
+        for i in range(1, 5):
+            c = getattr(self.masa_enc, f"conv_L{i}")
+            enc[f"conv_L{i}"] = dict(w=_f(c.weight), b=_f(c.bias)) if i == 1 else _prep_conv(c)
+            enc[f"blk_L{i}"] = [(_prep_conv(b.conv1), _prep_conv(b.conv2)) for b in getattr(self.masa_enc, f"blk_L{i}")]
+        P["masa_enc"] = enc
+        return P
+
+    # ---- MASA encoder (:100-134) on a batch of images ---------------------------------------------
+    def _masa_encode(self, E, img32):
+        feats = []
+        B, H, W, _ = img32.shape
+        x = torch.empty((B, H, W, self.nf), dtype=BF16, device=img32.device)
+        ops.conv3x3_small_ci(img32, E["conv_L1"]["w"], E["conv_L1"]["b"], relu=True, out_bf16=x)
+        for lvl in range(1, 5):
+            if lvl > 1:
+                _, x = conv3x3(x, E[f"conv_L{lvl}"], relu=True)
+            for c1, c2 in E[f"blk_L{lvl}"]:
+                _, t = conv3x3(x, c1, relu=True)
+                _, x = conv3x3(t, c2, res2=x)
+            feats.append(x)
+        return feats
+
+    # ---- MASA search + transfer (:753-900) ----------------------------------------------------------
+    def _masa_warp(self, f_lq_deep, f_ref, h, w, hr, wr, targets):
+        """targets[lev] = fp32 NHWC view receiving warp at level lev (0 = finest).  Returns aux tensors."""
+        ps, lb = self.padder_size, self.lr_block_size
+        px, py = w // ps // lb, h // ps // lb
+        k_x, k_y = w // ps // px, h // ps // py
+        d_x = 2 * int(wr // ps // (2 * px) * self.ref_down_block_size) + 1
+        d_y = 2 * int(hr // ps // (2 * py) * self.ref_down_block_size) + 1
+        fr = f_ref[-1]
+        B, Hr, Wr, Cd = fr.shape
+        if Wr < d_x + 2 or Hr < d_y + 2:
+            raise ValueError(f"reference image too small for the MASA search window ({d_y + 2}x{d_x + 2} at 1/8 scale)")
+        nblk = py * px
+        co_pad = ops.round_up(nblk, 8)
+        dils = self.dilations
+        # coarse search: 3 dilated 3x3 "convs" of the ref feature with the normalised lq block descriptors
+        n2 = ops.sqnorm_rows(fr)
+        inv = ops.masa_ref_invnorm(n2, dils)
+        wc = ops.masa_coarse_filters(f_lq_deep, k_y, k_x, dils, co_pad)
+        score = torch.empty((B, Hr, Wr, co_pad), dtype=F32, device=fr.device)
+        for i, dl in enumerate(dils):
+            ops.conv_gemm(fr, wc[i], co_pad, k=3, pad=dl, dil=dl, rowscale=inv[i], res2=score if i else None,
+                          out_f32=score, w_batched=True)
+        idx, origin = ops.masa_coarse_argmax(score, nblk, d_y, d_x)
+        # fine search inside each (d+2)^2 window
+        wf = ops.masa_fine_filters(f_lq_deep, k_y, k_x)
+        winv = ops.masa_win_invnorm(n2, origin, d_y, d_x)
+        corr, _ = ops.conv_gemm(fr, wf, k_y * k_x, k=3, pad=0, rowscale=winv, want="f32", w_batched=True,
+                                origin=origin, window=(d_y + 2, d_x + 2))
+        index, att = ops.masa_fine_argmax(corr)
+        nlev = len(f_ref)
+        for lev in range(nlev):
+            s = 2 ** (nlev - 1 - lev)
+            ops.masa_transfer(f_ref[lev], origin, index, att, py, px, k_y, k_x, d_x, s, out32=targets[lev])
+        return dict(idx=idx, origin=origin, index=index, att=att, score=score, corr=corr)
+
+    def forward(self, inp_img, ref_img, return_aux=False):
+        """:747-964 (with the B1 index shift).  NCHW in, NCHW out, arbitrary H, W (zero-padded to x64, cropped)."""
+        self._check(inp_img, ref_img)
+        if self.dual_pixel_task:
+            raise TdrError("RestormerRefFusion (B200): dual_pixel_task is not implemented")
+        P = self.prepared()
+        d = self.dims
+        dev = inp_img.device
+        B, _, oh, ow = inp_img.shape
+        mult = self.padder_size * self.lr_block_size
+        h, w = ops.round_up(oh, mult), ops.round_up(ow, mult)
+        hr, wr = ops.round_up(ref_img.shape[2], mult), ops.round_up(ref_img.shape[3], mult)
+        lq32 = ops.nchw_to_nhwc(inp_img, h, w)
+        ref32 = ops.nchw_to_nhwc(ref_img, hr, wr)
+        E = P["masa_enc"]
+        if (h, w) == (hr, wr):           # shared weights: run lq and ref as one batch
+            fb = self._masa_encode(E, torch.cat([lq32, ref32], 0))
+            f_lq, f_ref = [t[:B] for t in fb], [t[B:] for t in fb]
+        else:
+            f_lq, f_ref = self._masa_encode(E, lq32), self._masa_encode(E, ref32)
+        # fusion buffers [x || warp] per level, fp32 residual streams
+        fbuf = [torch.empty((B, h >> i, w >> i, 2 * d[i]), dtype=F32, device=dev) for i in range(4)]
+        aux = self._masa_warp(f_lq[-1], f_ref, h, w, hr, wr, [fbuf[i][..., d[i]:] for i in range(4)])
+        if return_aux:                   # the fusion blocks overwrite the warp halves in place
+            aux.update(feat_lq=f_lq, feat_ref=f_ref, warps=[fbuf[i][..., d[i]:].clone() for i in range(4)])
+        ops.conv3x3_small_ci(lq32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=fbuf[0][..., :d[0]])
+        enc_names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
+        downs = [None, "down1_2", "down2_3", "down3_4"]
+        xs = []
+        for i in range(4):
+            if i:
+                self._down(xs[-1], P[downs[i]], fbuf[i][..., :d[i]])
+            run_stack(fbuf[i], P[f"masa_blk_enc_level{i + 1}"])      # fuse on 2C channels, keep the first C (:907-909)
+            x = fbuf[i][..., :d[i]]
+            run_stack(x, P[enc_names[i]])
+            xs.append(x)
+        out = self._decode(P, xs[3], xs[0], xs[1], xs[2], lq32, None)
+        out = ops.nhwc_to_nchw(out, oh, ow)
+        return (out, aux) if return_aux else out

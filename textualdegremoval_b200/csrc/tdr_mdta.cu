@@ -1,0 +1,280 @@
+// MDTA (multi-Dconv-head transposed attention) score path, /root/reference/models/archs/network_restormer_guided_arch.py:262-276.
+//
+//   q, k : [heads, c, P] per sample (c = 48 or 96 channels per head, P = H*W pixels, up to 262144)
+//   attn = softmax( normalize(q) @ normalize(k)^T * temperature )           -- a c x c matrix per head
+//   out  = project_out( attn @ v )
+//
+// The contraction runs over PIXELS, so with NHWC activations both operands are "MN-major" for UMMA: a TMA box of
+// [64 channels x 128 pixels] lands in shared memory as 128 rows (K) of 128 B (64 channels of M/N), SWIZZLE_128B, and is
+// consumed directly by tcgen05.mma with a_major = b_major = MN.  Three products share each staged tile:
+//   D0 = q^T k (the Gram), D1 = q^T q, D2 = k^T k  -- the diagonals of D1/D2 are the squared L2 norms that
+// F.normalize (:266-267) needs, so q and k are read exactly once and no separate norm pass exists.
+// The pixel axis is split over CTAs; each writes an fp32 partial (deterministic two-stage reduction, no atomics).
+// tdr_mdta_weff then reduces, applies softmax and folds attn into project_out:  Weff = W_out * blockdiag(attn), so that
+// `attn @ v` + project_out (:272-276) becomes one tdr_conv_gemm with per-sample weights.
+#include "tdr_common.cuh"
+
+namespace {
+
+constexpr int kPixTile = 128;              // pixels (K) per pipeline stage
+constexpr int kBoxBytes = 64 * kPixTile * 2;
+
+struct GramPlan {
+  int c, M, N, boxes, stages, nchunks, tiles_per_chunk, tiles_total;
+  uint32_t tmem_cols;
+};
+
+static int make_plan(int B, long long P, int C, int heads, GramPlan* p) {
+  if (heads <= 0 || C % heads != 0) return -1;
+  p->c = C / heads;
+  if (p->c % 8 != 0 || p->c > 128) return -1;
+  if (p->c > 64 && p->c % 16 != 0) return -1;
+  p->M = p->c <= 64 ? 64 : 128;
+  p->N = p->c;
+  p->boxes = p->c <= 64 ? 1 : 2;
+  p->stages = p->boxes == 1 ? 4 : 3;
+  p->tiles_total = (int)((P + kPixTile - 1) / kPixTile);
+  int want = (2 * tdr_num_sms()) / (B * heads);
+  if (want < 1) want = 1;
+  if (want > p->tiles_total) want = p->tiles_total;
+  p->tiles_per_chunk = (p->tiles_total + want - 1) / want;
+  p->nchunks = (p->tiles_total + p->tiles_per_chunk - 1) / p->tiles_per_chunk;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(3 * p->N)) cols <<= 1;
+  p->tmem_cols = cols;
+  return 0;
+}
+
+struct GramArgs {
+  int B, C, heads;
+  long long P;
+  GramPlan plan;
+  float* partials;
+};
+
+__global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant__ TdrTensorMap map, const GramArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const GramPlan& pl = a.plan;
+  const int stage_bytes = 2 * pl.boxes * kBoxBytes;          // q boxes then k boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + pl.stages;
+  uint64_t* tfull = bars + 2 * pl.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * pl.stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int tile0 = chunk * pl.tiles_per_chunk;
+  int ntiles = pl.tiles_total - tile0;
+  if (ntiles > pl.tiles_per_chunk) ntiles = pl.tiles_per_chunk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map);
+    for (int s = 0; s < pl.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, pl.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        const int pix0 = (tile0 + t) * kPixTile;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], stage_bytes);
+        uint8_t* base = smem + stage * stage_bytes;
+        for (int j = 0; j < pl.boxes; ++j) {
+          tma_load_3d(base + j * kBoxBytes, &map, &full[stage], h * pl.c + 64 * j, pix0, b);
+          tma_load_3d(base + (pl.boxes + j) * kBoxBytes, &map, &full[stage], a.C + h * pl.c + 64 * j, pix0, b);
+        }
+        if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(pl.M, pl.N, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sq = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sk = sq + pl.boxes * kBoxBytes;
+#pragma unroll
+        for (int ks = 0; ks < kPixTile / 16; ++ks) {
+          // 16 pixels (K) = two 8-row swizzle atoms of 1024 B; 64-channel chunks are kBoxBytes apart (LBO)
+          const uint64_t dq = umma_desc_sw128(sq + ks * 2048, kBoxBytes, 1024);
+          const uint64_t dk = umma_desc_sw128(sk + ks * 2048, kBoxBytes, 1024);
+          const uint32_t accum = (t | ks) != 0;
+          umma_bf16(tmem_base + 0 * pl.N, dq, dk, idesc, accum);
+          umma_bf16(tmem_base + 1 * pl.N, dq, dq, idesc, accum);
+          umma_bf16(tmem_base + 2 * pl.N, dk, dk, idesc, accum);
+        }
+        umma_commit(&empty[stage]);
+        if (t == ntiles - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+      if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+    const int quad = warp & 3;
+    // M = 128: row r lives in lane r.  M = 64: row r lives in lane (r/16)*32 + r%16 (16 rows per quadrant).
+    const int row = pl.M == 128 ? quad * 32 + lane : quad * 16 + lane;
+    const bool row_ok = (pl.M == 128 || lane < 16) && row < pl.c;
+    float* out = a.partials + ((size_t)(b * a.heads + h) * pl.nchunks + chunk) * (size_t)(pl.c * pl.c + 2 * pl.c);
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const int nc16 = (pl.N + 15) / 16;
+    float dq = 0.f, dk = 0.f;
+    for (int c16 = 0; c16 < nc16; ++c16) {
+      uint32_t g[16], qq[16], kk[16];
+      tmem_ld16(t_lane + 0 * pl.N + c16 * 16, g);
+      tmem_ld16(t_lane + 1 * pl.N + c16 * 16, qq);
+      tmem_ld16(t_lane + 2 * pl.N + c16 * 16, kk);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int col = c16 * 16 + i;
+        if (row_ok && col < pl.c) out[row * pl.c + col] = __uint_as_float(g[i]);
+        if (col == row) {
+          dq = __uint_as_float(qq[i]);
+          dk = __uint_as_float(kk[i]);
+        }
+      }
+    }
+    if (row_ok) {
+      out[pl.c * pl.c + row] = dq;
+      out[pl.c * pl.c + pl.c + row] = dk;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, pl.tmem_cols);
+  }
+}
+
+// grid (heads, B); reduces partials, softmax, Weff = W_out * blockdiag(attn)
+__global__ void __launch_bounds__(256) mdta_weff_kernel(const float* __restrict__ partials, int C, int heads,
+                                                        int nchunks, const float* __restrict__ temperature,
+                                                        const float* __restrict__ w_out, bf16* __restrict__ weff,
+                                                        long long weff_ld, float* __restrict__ attn_out) {
+  extern __shared__ float sm[];
+  const int c = C / heads;
+  float* attn = sm;                 // [c][c]
+  float* nq = sm + c * c;           // [c]
+  float* nk = nq + c;               // [c]
+  const int h = blockIdx.x, b = blockIdx.y;
+  const size_t psz = (size_t)c * c + 2 * c;
+  const float* base = partials + (size_t)(b * heads + h) * nchunks * psz;
+  for (int i = threadIdx.x; i < (int)psz; i += blockDim.x) {
+    float s = 0.f;
+    for (int ch = 0; ch < nchunks; ++ch) s += base[(size_t)ch * psz + i];
+    sm[i] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) nq[i] = fmaxf(sqrtf(fmaxf(nq[i], 0.f)), 1e-12f);
+  __syncthreads();
+  const float temp = temperature[h];
+  // one warp per row: softmax over j
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < c; i += blockDim.x >> 5) {
+    float mx = -INFINITY;
+    for (int j = lane; j < c; j += 32) {
+      const float v = attn[i * c + j] / (nq[i] * nk[j]) * temp;
+      attn[i * c + j] = v;
+      mx = fmaxf(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float s = 0.f;
+    for (int j = lane; j < c; j += 32) {
+      const float e = __expf(attn[i * c + j] - mx);
+      attn[i * c + j] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    const float inv = 1.f / s;
+    for (int j = lane; j < c; j += 32) {
+      const float p = attn[i * c + j] * inv;
+      attn[i * c + j] = p;
+      if (attn_out) attn_out[((size_t)(b * heads + h) * c + i) * c + j] = p;
+    }
+  }
+  __syncthreads();
+  // Weff[b][co][h*c + j] = sum_i W_out[co][h*c + i] * attn[i][j]
+  for (int idx = threadIdx.x; idx < C * c; idx += blockDim.x) {
+    const int co = idx / c, j = idx % c;
+    const float* wrow = w_out + (size_t)co * C + h * c;
+    float s = 0.f;
+    for (int i = 0; i < c; ++i) s = fmaf(wrow[i], attn[i * c + j], s);
+    weff[((size_t)b * C + co) * weff_ld + h * c + j] = __float2bfloat16(s);
+  }
+}
+
+}  // namespace
+
+extern "C" size_t tdr_mdta_partials_bytes(int B, long long P, int C, int heads) {
+  GramPlan p;
+  if (B <= 0 || P <= 0 || make_plan(B, P, C, heads, &p)) return 0;
+  return (size_t)B * heads * p.nchunks * ((size_t)p.c * p.c + 2 * p.c) * sizeof(float);
+}
+
+extern "C" int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long long P, int C, int heads, float* partials,
+                             cudaStream_t stream) {
+  TDR_CHECK_ARG(qkv_bf16 && partials && B > 0 && P > 0, "tdr_mdta_gram: bad arguments");
+  TDR_CHECK_ARG(ld % 8 == 0 && ld >= 3 * C, "tdr_mdta_gram: ld must be a multiple of 8 and >= 3C");
+  GramArgs a;
+  TDR_CHECK_ARG(make_plan(B, P, C, heads, &a.plan) == 0,
+                "tdr_mdta_gram: unsupported head width (C=%d heads=%d; need c%%8==0, c<=128, c%%16==0 if c>64)", C, heads);
+  a.B = B; a.C = C; a.heads = heads; a.P = P; a.partials = partials;
+  TdrTensorMap map;
+  const uint64_t dims[3] = {(uint64_t)(3 * C), (uint64_t)P, (uint64_t)B};
+  const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)P};
+  const uint32_t box[3] = {64, (uint32_t)kPixTile, 1};
+  const uint32_t es[3] = {1, 1, 1};
+  int rc = tdr_make_tensor_map_bf16(&map, qkv_bf16, 3, dims, strides, box, es);
+  if (rc) return rc;
+  const size_t smem = 1024 + (size_t)a.plan.stages * 2 * a.plan.boxes * kBoxBytes + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(mdta_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(a.plan.nchunks, heads, B);
+  mdta_gram_kernel<<<grid, 192, smem, stream>>>(map, a);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature,
+                             const float* w_out, void* weff_bf16, long long weff_ld, float* attn_out,
+                             cudaStream_t stream) {
+  TDR_CHECK_ARG(partials && temperature && w_out && weff_bf16, "tdr_mdta_weff: null pointer");
+  GramPlan p;
+  TDR_CHECK_ARG(make_plan(B, P, C, heads, &p) == 0, "tdr_mdta_weff: unsupported head width");
+  TDR_CHECK_ARG(weff_ld >= C && weff_ld % 8 == 0, "tdr_mdta_weff: bad weff_ld");
+  const size_t smem = ((size_t)p.c * p.c + 2 * p.c) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(mdta_weff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(heads, B);
+  mdta_weff_kernel<<<grid, 256, smem, stream>>>(partials, C, heads, p.nchunks, temperature, w_out,
+                                                reinterpret_cast<bf16*>(weff_bf16), weff_ld, attn_out);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}

@@ -1,0 +1,417 @@
+// HBM-bound row/stencil kernels on NHWC activations: channel LayerNorm / cast, depthwise 3x3 (+ GDFN / SimpleGate
+// gating), image-boundary layout changes, slice copies, and the two small-channel direct convolutions at the image
+// boundary.  All access is 128-bit vectorised along the channel (innermost) dimension; reductions use warp shuffles.
+#include "tdr_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ rownorm
+// G lanes cooperate on one row (G = power of two <= 32), each lane owns NV float4 (strided by G).
+template <int NV>
+__global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ in, long long in_ld, long long rows,
+                                                      int C, int mode, const float* __restrict__ w,
+                                                      const float* __restrict__ bvec, float eps,
+                                                      bf16* __restrict__ out, long long out_ld, int G) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int rpw = 32 / G;
+  const int sub = lane / G, l = lane % G;
+  const long long row = warp_id * rpw + sub;
+  const int nvec = C >> 2;
+  const bool row_ok = row < rows;
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = l + i * G;
+    if (row_ok && idx < nvec) {
+      v[i] = *reinterpret_cast<const float4*>(in + row * in_ld + idx * 4);
+    } else {
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  float mean = 0.f, rstd = 1.f;
+  if (mode != 0) {
+    for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = l + i * G;
+      if (idx < nvec) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += a * a + b * b + c * c + d * d;
+      }
+    }
+    for (int o = G >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    rstd = rsqrtf(q / (float)C + eps);
+  }
+  if (!row_ok) return;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = l + i * G;
+    if (idx < nvec) {
+      float4 x = v[i];
+      if (mode == 1) {
+        const float4 ww = *reinterpret_cast<const float4*>(w + idx * 4);
+        const float4 bb = bvec ? *reinterpret_cast<const float4*>(bvec + idx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x.x = (x.x - mean) * rstd * ww.x + bb.x;
+        x.y = (x.y - mean) * rstd * ww.y + bb.y;
+        x.z = (x.z - mean) * rstd * ww.z + bb.z;
+        x.w = (x.w - mean) * rstd * ww.w + bb.w;
+      } else if (mode == 2) {
+        const float4 ww = *reinterpret_cast<const float4*>(w + idx * 4);
+        x.x = x.x * rstd * ww.x;
+        x.y = x.y * rstd * ww.y;
+        x.z = x.z * rstd * ww.z;
+        x.w = x.w * rstd * ww.w;
+      }
+      uint2 pk;
+      pk.x = pack2(x.x, x.y);
+      pk.y = pack2(x.z, x.w);
+      *reinterpret_cast<uint2*>(out + row * out_ld + idx * 4) = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ depthwise 3x3
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+template <int PIX>
+__device__ __forceinline__ void dw_accumulate(const bf16* __restrict__ in, long long in_ld, int H, int W, int b, int y,
+                                              int x0, int c0, int C, const float* __restrict__ wt, float (*acc)[8]) {
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy) {
+    const int iy = y + dy - 1;
+    if (iy < 0 || iy >= H) continue;
+    float px[PIX + 2][8];
+#pragma unroll
+    for (int j = 0; j < PIX + 2; ++j) {
+      const int ix = x0 - 1 + j;
+      if (ix >= 0 && ix < W) {
+        unpack8(*reinterpret_cast<const bf16x8*>(in + (((long long)b * H + iy) * W + ix) * in_ld + c0), px[j]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) px[j][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (dy * 3 + dx) * C + c0));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (dy * 3 + dx) * C + c0 + 4));
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int p = 0; p < PIX; ++p)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(wv[e], px[p + dx][e], acc[p][e]);
+    }
+  }
+}
+
+template <int PIX>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H,
+                                                        int W, int C, const float* __restrict__ wt,
+                                                        const float* __restrict__ bias, int gate,
+                                                        bf16* __restrict__ out, long long out_ld) {
+  const int Cout = gate ? (C >> 1) : C;
+  const int ncg = Cout >> 3;
+  const int nxg = (W + PIX - 1) / PIX;
+  const long long total = (long long)B * H * nxg * ncg;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(it % ncg);
+    long long r = it / ncg;
+    const int xg = (int)(r % nxg);
+    r /= nxg;
+    const int y = (int)(r % H);
+    const int b = (int)(r / H);
+    const int x0 = xg * PIX, c0 = cg * 8;
+    float acc[PIX][8];
+#pragma unroll
+    for (int p = 0; p < PIX; ++p)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[p][e] = bias ? bias[c0 + e] : 0.f;
+    dw_accumulate<PIX>(in, in_ld, H, W, b, y, x0, c0, C, wt, acc);
+    if (gate) {
+      float acc2[PIX][8];
+#pragma unroll
+      for (int p = 0; p < PIX; ++p)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc2[p][e] = bias ? bias[Cout + c0 + e] : 0.f;
+      dw_accumulate<PIX>(in, in_ld, H, W, b, y, x0, Cout + c0, C, wt, acc2);
+#pragma unroll
+      for (int p = 0; p < PIX; ++p)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[p][e] = (gate == 1 ? gelu_erf(acc[p][e]) : acc[p][e]) * acc2[p][e];
+    }
+#pragma unroll
+    for (int p = 0; p < PIX; ++p) {
+      if (x0 + p < W)
+        *reinterpret_cast<bf16x8*>(out + (((long long)b * H + y) * W + x0 + p) * out_ld + c0) = pack8(acc[p]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ layout
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int B, int C, int H, int W, int PH, int PW,
+                                    float* __restrict__ d32, long long ld32, bf16* __restrict__ d16, long long ld16) {
+  const long long total = (long long)B * PH * PW * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int x = (int)(p % PW);
+    const int y = (int)((p / PW) % PH);
+    const int b = (int)(p / ((long long)PW * PH));
+    const float v = (y < H && x < W) ? src[(((long long)b * C + c) * H + y) * W + x] : 0.f;
+    if (d32) d32[p * ld32 + c] = v;
+    if (d16) d16[p * ld16 + c] = __float2bfloat16(v);
+  }
+}
+
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, long long ld, int B, int C, int H, int W, int OH,
+                                    int OW, float* __restrict__ dst) {
+  const long long total = (long long)B * C * OH * OW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % OW);
+    const int y = (int)((i / OW) % OH);
+    const int c = (int)((i / ((long long)OW * OH)) % C);
+    const int b = (int)(i / ((long long)OW * OH * C));
+    dst[i] = src[(((long long)b * H + y) * W + x) * ld + c];
+  }
+}
+
+__global__ void copy_rows_kernel(const float* __restrict__ src, long long src_ld, long long rows, int C,
+                                 float* __restrict__ dst, long long dst_ld, bf16* __restrict__ d16, long long ld16) {
+  const int nvec = C >> 2;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int c = (int)(i % nvec) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(src + r * src_ld + c);
+    if (dst) *reinterpret_cast<float4*>(dst + r * dst_ld + c) = v;
+    if (d16) {
+      uint2 pk;
+      pk.x = pack2(v.x, v.y);
+      pk.y = pack2(v.z, v.w);
+      *reinterpret_cast<uint2*>(d16 + r * ld16 + c) = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small convs
+// Ci <= 8 input channels (fp32 NHWC), Co % 8 == 0 outputs; weights staged in smem as [ci*9+tap][Co].
+__global__ void __launch_bounds__(256) conv3x3_small_ci_kernel(const float* __restrict__ in, int B, int H, int W,
+                                                               int Ci, const float* __restrict__ weight,
+                                                               const float* __restrict__ bias, int Co, int relu,
+                                                               float* __restrict__ o32, long long ld32,
+                                                               bf16* __restrict__ o16, long long ld16) {
+  extern __shared__ float ws[];
+  for (int i = threadIdx.x; i < Co * Ci * 9; i += blockDim.x) {
+    const int co = i / (Ci * 9), r = i % (Ci * 9);       // weight[co][ci][ky][kx] -> ws[(ci*9+tap)*Co + co]
+    ws[r * Co + co] = weight[i];
+  }
+  __syncthreads();
+  const int ncg = Co >> 3;
+  const long long total = (long long)B * H * W * ncg;
+  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total;
+       it += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(it % ncg);
+    const long long p = it / ncg;
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    const int b = (int)(p / ((long long)W * H));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[cg * 8 + e] : 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const float* ip = in + (((long long)b * H + iy) * W + ix) * Ci;
+      for (int ci = 0; ci < Ci; ++ci) {
+        const float v = ip[ci];
+        const float* wp = ws + (ci * 9 + tap) * Co + cg * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(v, wp[e], acc[e]);
+      }
+    }
+    if (relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f);
+    }
+    if (o32) {
+      float4* q = reinterpret_cast<float4*>(o32 + p * ld32 + cg * 8);
+      q[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      q[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (o16) *reinterpret_cast<bf16x8*>(o16 + p * ld16 + cg * 8) = pack8(acc);
+  }
+}
+
+// Co <= 4 outputs from bf16 NHWC input; 4 lanes share one pixel (channel vectors strided by 4), shuffle-reduced.
+__global__ void __launch_bounds__(256) conv3x3_small_co_kernel(const bf16* __restrict__ in, long long in_ld, int B,
+                                                               int H, int W, int Ci, const float* __restrict__ weight,
+                                                               const float* __restrict__ bias, int Co,
+                                                               const float* __restrict__ res, float* __restrict__ out) {
+  extern __shared__ float ws[];       // ws[(tap*Ci + ci)*4 + co]
+  for (int i = threadIdx.x; i < 9 * Ci * 4; i += blockDim.x) {
+    const int co = i & 3, r = i >> 2;
+    const int tap = r / Ci, ci = r % Ci;
+    ws[i] = co < Co ? weight[((long long)co * Ci + ci) * 9 + tap] : 0.f;
+  }
+  __syncthreads();
+  const int nvec = Ci >> 3;
+  const long long total = (long long)B * H * W;
+  const int l4 = threadIdx.x & 3;
+  for (long long p0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 2; p0 < ((total + 7) / 8) * 8;
+       p0 += ((long long)gridDim.x * blockDim.x) >> 2) {
+    const bool ok = p0 < total;
+    const long long p = ok ? p0 : total - 1;
+    const int x = (int)(p % W);
+    const int y = (int)((p / W) % H);
+    const int b = (int)(p / ((long long)W * H));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int tap = 0; tap < 9; ++tap) {
+      const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
+      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+      const bf16* ip = in + (((long long)b * H + iy) * W + ix) * in_ld;
+      for (int v = l4; v < nvec; v += 4) {
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(ip + v * 8), f);
+        const float4* wp = reinterpret_cast<const float4*>(ws + (tap * Ci + v * 8) * 4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float4 wv = wp[e];
+          acc[0] = fmaf(f[e], wv.x, acc[0]);
+          acc[1] = fmaf(f[e], wv.y, acc[1]);
+          acc[2] = fmaf(f[e], wv.z, acc[2]);
+          acc[3] = fmaf(f[e], wv.w, acc[3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);
+      acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 2);
+    }
+    if (ok && l4 < Co) {
+      float v = acc[l4] + (bias ? bias[l4] : 0.f);
+      if (res) v += res[p * Co + l4];
+      out[p * Co + l4] = v;
+    }
+  }
+}
+
+inline int grid_for(long long items, int per_block, int max_waves = 8) {
+  long long g = (items + per_block - 1) / per_block;
+  const long long cap = (long long)tdr_num_sms() * max_waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+extern "C" int tdr_rownorm(const float* in, long long in_ld, long long rows, int C, int mode, const float* weight,
+                           const float* bias, float eps, void* out_bf16, long long out_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(in && out_bf16 && rows >= 0 && C > 0, "tdr_rownorm: bad arguments");
+  TDR_CHECK_ARG(C % 4 == 0 && in_ld % 4 == 0 && out_ld % 4 == 0, "tdr_rownorm: C and strides must be multiples of 4");
+  TDR_CHECK_ARG(mode >= 0 && mode <= 2, "tdr_rownorm: bad mode");
+  TDR_CHECK_ARG(mode == 0 || weight, "tdr_rownorm: weight required");
+  TDR_CHECK_ARG(C <= 4096, "tdr_rownorm: C too large (%d)", C);
+  if (rows == 0) return TDR_OK;
+  const int nvec = C / 4;
+  int G = 1;
+  while (G < 32 && G < nvec) G <<= 1;
+  const int nv = (nvec + G - 1) / G;
+  const long long warps = (rows + (32 / G) - 1) / (32 / G);
+  const int blocks = (int)((warps + 7) / 8);
+  bf16* o = reinterpret_cast<bf16*>(out_bf16);
+#define TDR_RN(NV) rownorm_kernel<NV><<<blocks, 256, 0, stream>>>(in, in_ld, rows, C, mode, weight, bias, eps, o, out_ld, G)
+  if (nv <= 1) TDR_RN(1);
+  else if (nv <= 2) TDR_RN(2);
+  else if (nv <= 4) TDR_RN(4);
+  else if (nv <= 8) TDR_RN(8);
+  else if (nv <= 16) TDR_RN(16);
+  else TDR_RN(32);
+#undef TDR_RN
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
+                             const float* bias, int gate, void* out_bf16, long long out_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(in_bf16 && out_bf16 && weight, "tdr_dwconv3x3: null pointer");
+  TDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "tdr_dwconv3x3: bad dims");
+  TDR_CHECK_ARG(gate >= 0 && gate <= 2, "tdr_dwconv3x3: bad gate");
+  TDR_CHECK_ARG(C % (gate ? 16 : 8) == 0, "tdr_dwconv3x3: C must be a multiple of %d", gate ? 16 : 8);
+  TDR_CHECK_ARG(in_ld % 8 == 0 && out_ld % 8 == 0, "tdr_dwconv3x3: strides must be multiples of 8");
+  const int Cout = gate ? C / 2 : C;
+  const long long items = (long long)B * H * ((W + 3) / 4) * (Cout / 8);
+  dwconv3x3_kernel<4><<<grid_for(items, 256, 16), 256, 0, stream>>>(reinterpret_cast<const bf16*>(in_bf16), in_ld, B, H,
+                                                                    W, C, weight, bias, gate,
+                                                                    reinterpret_cast<bf16*>(out_bf16), out_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_nchw_to_nhwc(const float* src, int B, int C, int H, int W, int pad_h, int pad_w, float* dst_f32,
+                                long long dst_f32_ld, void* dst_bf16, long long dst_bf16_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(src && (dst_f32 || dst_bf16), "tdr_nchw_to_nhwc: null pointer");
+  TDR_CHECK_ARG(pad_h >= H && pad_w >= W && B > 0 && C > 0, "tdr_nchw_to_nhwc: bad dims");
+  const long long total = (long long)B * pad_h * pad_w * C;
+  nchw_to_nhwc_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(src, B, C, H, W, pad_h, pad_w, dst_f32, dst_f32_ld,
+                                                                    reinterpret_cast<bf16*>(dst_bf16), dst_bf16_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_nhwc_to_nchw(const float* src, long long src_ld, int B, int C, int H, int W, int out_h, int out_w,
+                                float* dst, cudaStream_t stream) {
+  TDR_CHECK_ARG(src && dst && out_h <= H && out_w <= W && out_h > 0 && out_w > 0, "tdr_nhwc_to_nchw: bad arguments");
+  const long long total = (long long)B * C * out_h * out_w;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(src, src_ld, B, C, H, W, out_h, out_w, dst);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_copy_rows_f32(const float* src, long long src_ld, long long rows, int C, float* dst,
+                                 long long dst_ld, void* dst_bf16, long long dst_bf16_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(src && (dst || dst_bf16), "tdr_copy_rows_f32: null pointer");
+  TDR_CHECK_ARG(C % 4 == 0 && src_ld % 4 == 0 && dst_ld % 4 == 0 && dst_bf16_ld % 4 == 0,
+                "tdr_copy_rows_f32: C / strides must be multiples of 4");
+  if (rows == 0) return TDR_OK;
+  copy_rows_kernel<<<grid_for(rows * (C / 4), 256, 16), 256, 0, stream>>>(src, src_ld, rows, C, dst, dst_ld,
+                                                                         reinterpret_cast<bf16*>(dst_bf16), dst_bf16_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_conv3x3_small_ci(const float* in, int B, int H, int W, int Ci, const float* weight,
+                                    const float* bias, int Co, int relu, float* out_f32, long long out_f32_ld,
+                                    void* out_bf16, long long out_bf16_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(in && weight && (out_f32 || out_bf16), "tdr_conv3x3_small_ci: null pointer");
+  TDR_CHECK_ARG(Ci >= 1 && Ci <= 8 && Co % 8 == 0 && Co * Ci * 9 * 4 <= 48 * 1024, "tdr_conv3x3_small_ci: bad channels");
+  TDR_CHECK_ARG(out_f32_ld % 4 == 0 && out_bf16_ld % 8 == 0, "tdr_conv3x3_small_ci: bad strides");
+  const long long items = (long long)B * H * W * (Co / 8);
+  conv3x3_small_ci_kernel<<<grid_for(items, 256, 8), 256, Co * Ci * 9 * sizeof(float), stream>>>(
+      in, B, H, W, Ci, weight, bias, Co, relu, out_f32, out_f32_ld, reinterpret_cast<bf16*>(out_bf16), out_bf16_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_conv3x3_small_co(const void* in_bf16, long long in_ld, int B, int H, int W, int Ci,
+                                    const float* weight, const float* bias, int Co, const float* res, float* out,
+                                    cudaStream_t stream) {
+  TDR_CHECK_ARG(in_bf16 && weight && out, "tdr_conv3x3_small_co: null pointer");
+  TDR_CHECK_ARG(Co >= 1 && Co <= 4 && Ci % 8 == 0 && in_ld % 8 == 0 && 9 * Ci * 16 <= 48 * 1024,
+                "tdr_conv3x3_small_co: bad channels");
+  const long long items = (long long)B * H * W * 4;
+  conv3x3_small_co_kernel<<<grid_for(items, 256, 8), 256, 9 * Ci * 4 * sizeof(float), stream>>>(
+      reinterpret_cast<const bf16*>(in_bf16), in_ld, B, H, W, Ci, weight, bias, Co, res, out);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}

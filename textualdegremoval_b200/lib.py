@@ -1,0 +1,97 @@
+"""ctypes binding of libtdr_sm100.so (the C ABI declared in include/tdr_sm100.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, a
+``TdrError`` is raised.  The product path never imports ``oracle``.
+"""
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libtdr_sm100.so")
+
+
+class TdrError(RuntimeError):
+    pass
+
+
+class ConvGemmDesc(C.Structure):
+    """Mirror of ``tdr_conv_gemm_desc`` (include/tdr_sm100.h) -- field order and types must match."""
+    _fields_ = [
+        ("in_", C.c_void_p), ("in_ld", C.c_longlong),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Ci", C.c_int),
+        ("weight", C.c_void_p), ("w_ld", C.c_longlong),
+        ("Co", C.c_int), ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("dil", C.c_int),
+        ("w_batched", C.c_int),
+        ("origin", C.c_void_p),
+        ("n_images", C.c_int), ("img_h", C.c_int), ("img_w", C.c_int),
+        ("bias", C.c_void_p), ("rowscale", C.c_void_p),
+        ("alpha", C.c_float),
+        ("scale_ptr", C.c_void_p),
+        ("relu", C.c_int),
+        ("res1", C.c_void_p), ("res1_ld", C.c_longlong), ("res1_scale", C.c_float),
+        ("res2", C.c_void_p), ("res2_ld", C.c_longlong), ("res2_bf16", C.c_int),
+        ("out_f32", C.c_void_p), ("out_f32_ld", C.c_longlong),
+        ("out_bf16", C.c_void_p), ("out_bf16_ld", C.c_longlong),
+        ("store_mode", C.c_int), ("impl", C.c_int),
+    ]
+
+
+_vp, _ll, _i, _f, _sz = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/tdr_sm100.h declares
+SIGNATURES = {
+    "tdr_last_error": (C.c_char_p, []),
+    "tdr_version": (_i, []),
+    "tdr_check_device": (_i, []),
+    "tdr_conv_gemm": (_i, [C.POINTER(ConvGemmDesc), _vp]),
+    "tdr_conv_gemm_desc_layout": (None, [C.POINTER(_i)]),
+    "tdr_conv3x3_small_ci": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _ll, _vp, _ll, _vp]),
+    "tdr_conv3x3_small_co": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "tdr_rownorm": (_i, [_vp, _ll, _ll, _i, _i, _vp, _vp, _f, _vp, _ll, _vp]),
+    "tdr_dwconv3x3": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _vp]),
+    "tdr_mdta_partials_bytes": (_sz, [_i, _ll, _i, _i]),
+    "tdr_mdta_gram": (_i, [_vp, _ll, _i, _ll, _i, _i, _vp, _vp]),
+    "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp]),
+    "tdr_nchw_to_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),
+    "tdr_nhwc_to_nchw": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tdr_copy_rows_f32": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp, _ll, _vp]),
+    "tdr_sqnorm_rows": (_i, [_vp, _ll, _ll, _i, _vp, _vp]),
+    "tdr_masa_ref_invnorm": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _i, _vp, _vp]),
+    "tdr_masa_coarse_filters": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _i, _vp, _vp]),
+    "tdr_masa_coarse_argmax": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "tdr_masa_fine_filters": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tdr_masa_win_invnorm": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "tdr_masa_fine_argmax": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "tdr_masa_transfer": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises TdrError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TdrError(
+            f"{LIB_PATH} not found: build it with `python -m textualdegremoval_b200.csrc.build` "
+            "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback for the B200 hot path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().tdr_last_error()
+        raise TdrError(f"{what or 'libtdr_sm100'} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def call(name: str, *args):
+    lib = load()
+    check(getattr(lib, name)(*args), name)

@@ -1,0 +1,342 @@
+"""Tensor-level wrappers over the C ABI (include/tdr_sm100.h).
+
+Activations are NHWC torch tensors ``[B, H, W, C]`` whose channel dim is contiguous; channel slices of a wider
+buffer (``t[..., a:b]``) are passed as (pointer, row stride) without copies, which is how concatenations
+(``torch.cat([x, warp], 1)`` in the reference) are expressed.  PyTorch is used for device memory and streams only.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Profiler:
+    """Optional per-launch CUDA-event timing (bench.py roofline leg).  Off by default: zero overhead on the hot path
+    beyond one counter increment per launch."""
+
+    def __init__(self):
+        self.active = False
+        self.records = []          # (kernel, tag, bytes, flops, start_event, end_event)
+        self.launches = 0
+
+    def start(self):
+        self.records, self.active = [], True
+
+    def stop(self):
+        self.active = False
+        torch.cuda.synchronize()
+        out = [(k, t, b, f, s.elapsed_time(e)) for (k, t, b, f, s, e) in self.records]
+        self.records = []
+        return out
+
+
+PROF = Profiler()
+
+
+def _call(name, *args, tag="", nbytes=0, flops=0):
+    PROF.launches += 1
+    if PROF.active:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        lib.call(name, *args)
+        e.record()
+        PROF.records.append((name, tag, nbytes, flops, s, e))
+    else:
+        lib.call(name, *args)
+
+
+def _nb(*ts):
+    return sum(t.numel() * t.element_size() for t in ts if t is not None)
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Row stride (elements) of an NHWC view; checks the layout is a channel slice of a dense NHWC buffer."""
+    assert t.dim() == 4 and t.stride(3) == 1, f"expected NHWC view, got strides {t.stride()}"
+    ld = t.stride(2)
+    b, h, w, _ = t.shape
+    assert (w == 1 or t.stride(2) == ld) and (h == 1 or t.stride(1) == w * ld) and (b == 1 or t.stride(0) == h * w * ld), \
+        f"not a channel slice of a dense NHWC buffer: shape {tuple(t.shape)} strides {t.stride()}"
+    return ld
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# ---------------------------------------------------------------------------------------------- weight packing
+def pack_conv_weight(w: torch.Tensor, co_pad_to: int = 0, ci_map=None, co_map=None) -> torch.Tensor:
+    """[Co, Ci, kh, kw] fp32 -> bf16 [kh*kw, Co_p, Ci_p] (tap-major, K contiguous) for tdr_conv_gemm.
+
+    ci_map / co_map: optional (n_padded, index tensor) placing logical channels at padded positions (GDFN halves).
+    """
+    co, ci, kh, kw = w.shape
+    wt = w.detach().permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
+    if ci_map is not None:
+        n, idx = ci_map
+        tmp = wt.new_zeros(kh * kw, co, n)
+        tmp[:, :, idx] = wt
+        wt = tmp
+    if co_map is not None:
+        n, idx = co_map
+        tmp = wt.new_zeros(kh * kw, n, wt.shape[2])
+        tmp[:, idx, :] = wt
+        wt = tmp
+    cip = round_up(wt.shape[2], 8)
+    cop = max(round_up(wt.shape[1], 8), co_pad_to)
+    out = torch.zeros(kh * kw, cop, cip, dtype=BF16, device=w.device)
+    out[:, : wt.shape[1], : wt.shape[2]] = wt.to(BF16)
+    return out
+
+
+def pad_vec(v, n, idx=None):
+    if v is None:
+        return None
+    out = torch.zeros(n, dtype=F32, device=v.device)
+    if idx is None:
+        out[: v.numel()] = v.detach().float().reshape(-1)
+    else:
+        out[idx] = v.detach().float().reshape(-1)
+    return out
+
+
+def pack_dw_weight(w: torch.Tensor, n=None, idx=None) -> torch.Tensor:
+    """[C, 1, 3, 3] -> fp32 [9, C_p] tap-major."""
+    c = w.shape[0]
+    wt = w.detach().float().reshape(c, 9).t().contiguous()
+    if n is None:
+        return wt
+    out = torch.zeros(9, n, dtype=F32, device=w.device)
+    out[:, idx] = wt
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- ops
+def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, relu=False, rowscale=None,
+              alpha=1.0, scale_ptr=None, res1=None, res1_scale=1.0, res2=None, out_f32=None, out_bf16=None,
+              want="bf16", store_mode=0, w_batched=False, origin=None, window=None, impl=0):
+    """x: bf16 NHWC view.  wpack: bf16 [T, Co_p, Ci_p].  Returns (out_f32, out_bf16) -- allocated if not given
+    according to ``want`` in {"bf16", "f32", "both"}."""
+    assert x.dtype == BF16 and wpack.dtype == BF16
+    B, H, W, Cx = x.shape
+    Ci = Cx if Ci is None else Ci
+    d = lib.ConvGemmDesc()
+    d.in_ = x.data_ptr(); d.in_ld = _ld(x)
+    if origin is not None:
+        wh, ww = window
+        d.origin = origin.data_ptr(); d.n_images = B; d.img_h = H; d.img_w = W
+        d.B = origin.shape[0]; d.H = wh; d.W = ww
+    else:
+        d.B = B; d.H = H; d.W = W
+    d.Ci = Ci
+    d.weight = wpack.data_ptr(); d.w_ld = wpack.shape[2]
+    assert wpack.shape[1] >= Co and wpack.shape[2] >= Ci and wpack.is_contiguous()
+    # the weight tensor map uses Co as the row extent and w_ld*Co as the tap stride
+    assert wpack.shape[1] == Co, f"packed weight rows {wpack.shape[1]} != Co {Co}"
+    d.Co = Co; d.KH = k; d.KW = k; d.stride = stride; d.pad = pad; d.dil = dil
+    d.w_batched = int(w_batched)
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.rowscale = rowscale.data_ptr() if rowscale is not None else None
+    d.alpha = alpha
+    d.scale_ptr = scale_ptr.data_ptr() if scale_ptr is not None else None
+    d.relu = int(relu)
+    nB, nH, nW = d.B, d.H, d.W
+    OH = (nH + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    OW = (nW + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    if store_mode == 0:
+        oshape = (nB, OH, OW, Co)
+    elif store_mode == 1:
+        oshape = (nB, OH // 2, OW // 2, Co * 4)
+    else:
+        oshape = (nB, OH * 2, OW * 2, Co // 4)
+    if out_f32 is None and want in ("f32", "both"):
+        out_f32 = torch.empty(oshape, dtype=F32, device=x.device)
+    if out_bf16 is None and want in ("bf16", "both") and not (want == "bf16" and out_f32 is not None):
+        out_bf16 = torch.empty(oshape, dtype=BF16, device=x.device)
+    for o in (out_f32, out_bf16, res1, res2):
+        if o is not None:
+            assert tuple(o.shape) == oshape, f"output/residual shape {tuple(o.shape)} != {oshape}"
+    if res1 is not None:
+        assert res1.dtype == F32
+        d.res1 = res1.data_ptr(); d.res1_ld = _ld(res1); d.res1_scale = res1_scale
+    if res2 is not None:
+        d.res2 = res2.data_ptr(); d.res2_ld = _ld(res2); d.res2_bf16 = int(res2.dtype == BF16)
+    if out_f32 is not None:
+        assert out_f32.dtype == F32
+        d.out_f32 = out_f32.data_ptr(); d.out_f32_ld = _ld(out_f32)
+    if out_bf16 is not None:
+        assert out_bf16.dtype == BF16
+        d.out_bf16 = out_bf16.data_ptr(); d.out_bf16_ld = _ld(out_bf16)
+    d.store_mode = store_mode
+    d.impl = impl
+    taps = k * k
+    _call("tdr_conv_gemm", C.byref(d), _stream(),
+          tag=f"k{k}s{stride}_Ci{Ci}_Co{Co}_{OH}x{OW}" + ("_wb" if w_batched else ""),
+          nbytes=nB * nH * nW * Ci * 2 + Co * Ci * taps * 2 * (nB if w_batched else 1) + _nb(out_f32, out_bf16, res1, res2),
+          flops=2 * nB * OH * OW * Co * Ci * taps)
+    return out_f32, out_bf16
+
+
+def rownorm(x32, mode, weight=None, bias=None, eps=1e-5, out=None):
+    """fp32 NHWC view -> bf16 NHWC.  mode 0 cast, 1 WithBias LN, 2 BiasFree LN."""
+    assert x32.dtype == F32
+    B, H, W, Cc = x32.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=BF16, device=x32.device)
+    _call("tdr_rownorm", _p(x32), _ld(x32), B * H * W, Cc, mode, _p(weight), _p(bias), eps, _p(out), _ld(out),
+          _stream(), tag=f"m{mode}_C{Cc}", nbytes=B * H * W * Cc * 6)
+    return out
+
+
+def dwconv3x3(x, w9, bias=None, gate=0, out=None):
+    assert x.dtype == BF16 and w9.dtype == F32
+    B, H, W, Cc = x.shape
+    co = Cc // 2 if gate else Cc
+    if out is None:
+        out = torch.empty((B, H, W, co), dtype=BF16, device=x.device)
+    _call("tdr_dwconv3x3", _p(x), _ld(x), B, H, W, Cc, _p(w9), _p(bias), gate, _p(out), _ld(out), _stream(),
+          tag=f"g{gate}_C{Cc}_{H}x{W}", nbytes=B * H * W * (Cc + co) * 2, flops=2 * 9 * B * H * W * Cc)
+    return out
+
+
+def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False):
+    """qkv: bf16 NHWC [B,H,W,>=3C].  Returns Weff bf16 [B, C, C_p] (and attn fp32 [B,heads,c,c])."""
+    B, H, W, _ = qkv.shape
+    P = H * W
+    nbytes = lib.load().tdr_mdta_partials_bytes(B, P, C_, heads)
+    if nbytes == 0:
+        raise lib.TdrError(f"MDTA head width unsupported: C={C_} heads={heads}")
+    partials = torch.empty(nbytes // 4, dtype=F32, device=qkv.device)
+    _call("tdr_mdta_gram", _p(qkv), _ld(qkv), B, P, C_, heads, _p(partials), _stream(), tag=f"C{C_}_h{heads}_P{P}",
+          nbytes=B * P * 2 * C_ * 2, flops=3 * 2 * B * P * C_ * (C_ // heads))
+    cp = round_up(C_, 8)
+    weff = torch.empty((B, C_, cp), dtype=BF16, device=qkv.device)
+    attn = torch.empty((B, heads, C_ // heads, C_ // heads), dtype=F32, device=qkv.device) if want_attn else None
+    _call("tdr_mdta_weff", _p(partials), B, P, C_, heads, _p(temperature), _p(w_out), _p(weff), cp, _p(attn),
+          _stream(), tag=f"C{C_}_h{heads}", nbytes=nbytes + _nb(weff))
+    return (weff, attn) if want_attn else weff
+
+
+def nchw_to_nhwc(x, pad_h, pad_w, want_bf16=False):
+    x = x.contiguous().float()
+    B, Cc, H, W = x.shape
+    o32 = torch.empty((B, pad_h, pad_w, Cc), dtype=F32, device=x.device)
+    o16 = torch.empty((B, pad_h, pad_w, Cc), dtype=BF16, device=x.device) if want_bf16 else None
+    _call("tdr_nchw_to_nhwc", _p(x), B, Cc, H, W, pad_h, pad_w, _p(o32), Cc, _p(o16), Cc, _stream())
+    return (o32, o16) if want_bf16 else o32
+
+
+def nhwc_to_nchw(x32, out_h, out_w):
+    B, H, W, Cc = x32.shape
+    out = torch.empty((B, Cc, out_h, out_w), dtype=F32, device=x32.device)
+    _call("tdr_nhwc_to_nchw", _p(x32), _ld(x32), B, Cc, H, W, out_h, out_w, _p(out), _stream())
+    return out
+
+
+def copy_rows(src32, dst32=None, dst16=None):
+    B, H, W, Cc = src32.shape
+    _call("tdr_copy_rows_f32", _p(src32), _ld(src32), B * H * W, Cc, _p(dst32), _ld(dst32) if dst32 is not None else 0,
+          _p(dst16), _ld(dst16) if dst16 is not None else 0, _stream(), tag=f"C{Cc}",
+          nbytes=B * H * W * Cc * (4 + (4 if dst32 is not None else 0) + (2 if dst16 is not None else 0)))
+
+
+def conv3x3_small_ci(x32, weight, bias, relu=False, out_f32=None, out_bf16=None):
+    """x32: dense fp32 NHWC [B,H,W,Ci<=8]; weight fp32 [Co,Ci,3,3]."""
+    B, H, W, Ci = x32.shape
+    assert x32.is_contiguous()
+    Co = weight.shape[0]
+    _call("tdr_conv3x3_small_ci", _p(x32), B, H, W, Ci, _p(weight), _p(bias), Co, int(relu), _p(out_f32),
+          _ld(out_f32) if out_f32 is not None else 0, _p(out_bf16), _ld(out_bf16) if out_bf16 is not None else 0,
+          _stream(), tag=f"Ci{Ci}_Co{Co}", flops=2 * 9 * B * H * W * Ci * Co,
+          nbytes=B * H * W * (Ci * 4 + Co * ((4 if out_f32 is not None else 0) + (2 if out_bf16 is not None else 0))))
+
+
+def conv3x3_small_co(x16, weight, bias, res32=None):
+    B, H, W, Ci = x16.shape
+    Co = weight.shape[0]
+    out = torch.empty((B, H, W, Co), dtype=F32, device=x16.device)
+    if res32 is not None:
+        assert res32.is_contiguous() and res32.shape == out.shape
+    _call("tdr_conv3x3_small_co", _p(x16), _ld(x16), B, H, W, Ci, _p(weight), _p(bias), Co, _p(res32), _p(out),
+          _stream(), tag=f"Ci{Ci}_Co{Co}", flops=2 * 9 * B * H * W * Ci * Co, nbytes=B * H * W * (Ci * 2 + Co * 8))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- MASA
+def sqnorm_rows(x16):
+    B, H, W, Cc = x16.shape
+    n2 = torch.empty((B, H, W), dtype=F32, device=x16.device)
+    _call("tdr_sqnorm_rows", _p(x16), _ld(x16), B * H * W, Cc, _p(n2), _stream())
+    return n2
+
+
+def _iarr(vals):
+    return (C.c_int * len(vals))(*vals)
+
+
+def masa_ref_invnorm(n2, dils):
+    B, H, W = n2.shape
+    inv = torch.empty((len(dils), B, H, W), dtype=F32, device=n2.device)
+    _call("tdr_masa_ref_invnorm", _p(n2), B, H, W, _iarr(dils), len(dils), _p(inv), _stream())
+    return inv
+
+
+def masa_coarse_filters(f_lq, k_y, k_x, dils, co_pad):
+    B, H, W, Cc = f_lq.shape
+    assert f_lq.is_contiguous()
+    w = torch.empty((len(dils), B * 9, co_pad, Cc), dtype=BF16, device=f_lq.device)
+    _call("tdr_masa_coarse_filters", _p(f_lq), B, H, W, Cc, k_y, k_x, _iarr(dils), len(dils), co_pad, _p(w), _stream())
+    return w
+
+
+def masa_coarse_argmax(score, nblk, d_y, d_x):
+    B, Hr, Wr, co_pad = score.shape
+    idx = torch.empty((B, nblk), dtype=torch.int32, device=score.device)
+    origin = torch.empty((B * nblk, 3), dtype=torch.int32, device=score.device)
+    _call("tdr_masa_coarse_argmax", _p(score), B, Hr, Wr, nblk, co_pad, d_y, d_x, _p(idx), _p(origin), _stream())
+    return idx, origin
+
+
+def masa_fine_filters(f_lq, k_y, k_x):
+    B, H, W, Cc = f_lq.shape
+    nwin = B * (H // k_y) * (W // k_x)
+    w = torch.empty((nwin * 9, k_y * k_x, Cc), dtype=BF16, device=f_lq.device)
+    _call("tdr_masa_fine_filters", _p(f_lq), B, H, W, Cc, k_y, k_x, _p(w), _stream())
+    return w
+
+
+def masa_win_invnorm(n2_ref, origin, d_y, d_x):
+    B, Hr, Wr = n2_ref.shape
+    nwin = origin.shape[0]
+    inv = torch.empty((nwin, d_y, d_x), dtype=F32, device=n2_ref.device)
+    _call("tdr_masa_win_invnorm", _p(n2_ref), Hr, Wr, _p(origin), nwin, d_y, d_x, _p(inv), _stream())
+    return inv
+
+
+def masa_fine_argmax(corr):
+    nwin, dy, dx, nq = corr.shape
+    index = torch.empty((nwin, nq), dtype=torch.int32, device=corr.device)
+    att = torch.empty((nwin, nq), dtype=F32, device=corr.device)
+    _call("tdr_masa_fine_argmax", _p(corr), nwin, dy * dx, nq, _p(index), _p(att), _stream())
+    return index, att
+
+
+def masa_transfer(f_ref, origin, index, att, py, px, k_y, k_x, d_x, s, out32=None, out16=None):
+    B, Hs, Ws, Cc = f_ref.shape
+    assert f_ref.is_contiguous()
+    npx = B * py * k_y * s * px * k_x * s
+    _call("tdr_masa_transfer", _p(f_ref), B, Hs, Ws, Cc, _p(origin), _p(index), _p(att), py, px, k_y, k_x, d_x, s,
+          _p(out32), _ld(out32) if out32 is not None else 0, _p(out16), _ld(out16) if out16 is not None else 0,
+          _stream(), tag=f"s{s}_C{Cc}",
+          nbytes=npx * Cc * (2 + (4 if out32 is not None else 0) + (2 if out16 is not None else 0)))
