@@ -211,6 +211,15 @@ def run_b200(args):
         torch.cuda.synchronize()
         return sum(s.elapsed_time(e) for s, e in evs)
 
+    if args.ncu:
+        with torch.no_grad():
+            step_resident()
+            torch.cuda.synchronize()
+            for _ in range(args.steps):
+                step_resident()
+            torch.cuda.synchronize()
+        print(json.dumps({"ncu_mode": True, "launches_per_step": ops.PROF.launches // (1 + args.steps)}))
+        return 0
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             step_resident()
@@ -299,6 +308,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu", action="store_true", help="profiling mode: 1 warm-up + --steps forwards, nothing else "
+                                                       "(numbers printed under a profiler are never bench values)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -218,6 +218,7 @@ CONV_CASES = [
     dict(name="3x3_stride2", Ci=48, Co=96, k=3, pad=1, stride=2, bias=True, relu=True, H=32, W=32),
     dict(name="3x3_stride2_odd", Ci=16, Co=32, k=3, pad=1, stride=2, H=20, W=40, B=1),
     dict(name="3x3_unshuffle", Ci=48, Co=24, k=3, pad=1, store_mode=1, H=16, W=32),
+    dict(name="3x3_unshuffle_co12", Ci=24, Co=12, k=3, pad=1, store_mode=1, H=16, W=16, want="both"),
     dict(name="3x3_shuffle", Ci=96, Co=192, k=3, pad=1, store_mode=2, want="both", H=8, W=16),
     dict(name="3x3_dil2_rowscale", Ci=128, Co=8, k=3, pad=2, dil=2, rowscale=True, batched=True, res2="f32"),
     dict(name="3x3_dil3", Ci=64, Co=64, k=3, pad=3, dil=3, H=16, W=16),
@@ -248,7 +249,7 @@ def check_conv_origin():
     """per-sample windows (MASA fine search): sample b reads image origin[b,0] shifted by (y0,x0)."""
     ops = _ops()
     out = []
-    B, Ci, Co, Hh, Ww = 2, 64, 64, 16, 20
+    B, Ci, Co, Hh, Ww = 2, 64, 64, 18, 20
     x = q(rnd(B, Ci, Hh, Ww, seed=3))
     org = torch.tensor([[0, 0, 0], [1, 1, 5], [0, 3, 2], [1, 0, 4], [0, 1, 1]], dtype=torch.int32)
     nw = org.shape[0]

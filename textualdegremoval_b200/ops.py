@@ -76,8 +76,9 @@ def round_up(x: int, m: int) -> int:
 
 
 # ---------------------------------------------------------------------------------------------- weight packing
-def pack_conv_weight(w: torch.Tensor, co_pad_to: int = 0, ci_map=None, co_map=None) -> torch.Tensor:
-    """[Co, Ci, kh, kw] fp32 -> bf16 [kh*kw, Co_p, Ci_p] (tap-major, K contiguous) for tdr_conv_gemm.
+def pack_conv_weight(w: torch.Tensor, ci_map=None, co_map=None) -> torch.Tensor:
+    """[Co, Ci, kh, kw] fp32 -> bf16 [kh*kw, Co, Ci_p] (tap-major, K contiguous, Ci padded to 8) for tdr_conv_gemm.
+    Rows are NOT padded: the kernel's TMA box zero-fills beyond Co.
 
     ci_map / co_map: optional (n_padded, index tensor) placing logical channels at padded positions (GDFN halves).
     """
@@ -94,9 +95,8 @@ def pack_conv_weight(w: torch.Tensor, co_pad_to: int = 0, ci_map=None, co_map=No
         tmp[:, idx, :] = wt
         wt = tmp
     cip = round_up(wt.shape[2], 8)
-    cop = max(round_up(wt.shape[1], 8), co_pad_to)
-    out = torch.zeros(kh * kw, cop, cip, dtype=BF16, device=w.device)
-    out[:, : wt.shape[1], : wt.shape[2]] = wt.to(BF16)
+    out = torch.zeros(kh * kw, wt.shape[1], cip, dtype=BF16, device=w.device)
+    out[:, :, : wt.shape[2]] = wt.to(BF16)
     return out
 
 
