@@ -259,6 +259,18 @@ def run_b200(args):
         f = fam.setdefault(name, dict(ms=0.0, bytes=0, flops=0, n=0))
         f["ms"] += t; f["bytes"] += nb; f["flops"] += fl; f["n"] += 1
     total_prof = sum(f["ms"] for f in fam.values())
+    if args.dump_prof:
+        tags = {}
+        for name, tag, nb, fl, t in prof:
+            d_ = tags.setdefault(f"{name}:{tag}", dict(ms=0.0, n=0, bytes=0, flops=0))
+            d_["ms"] += t; d_["n"] += 1; d_["bytes"] += nb; d_["flops"] += fl
+        rows = sorted(tags.items(), key=lambda kv: -kv[1]["ms"])
+        with open(args.dump_prof, "w") as fh:
+            json.dump([dict(key=k, ms=round(v["ms"], 4), n=v["n"], us_per=round(1e3 * v["ms"] / v["n"], 1),
+                            GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                            TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1),
+                            hbm_frac=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"], 3)) for k, v in rows], fh,
+                      indent=0)
     top = max(fam, key=lambda k: fam[k]["ms"])
     ft = fam[top]
     hbm_gbs = ft["bytes"] / (ft["ms"] * 1e-3) / 1e9
@@ -308,6 +320,7 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-prof", default="", help="write the per-(kernel, shape) event-timed profile to this json")
     ap.add_argument("--ncu", action="store_true", help="profiling mode: 1 warm-up + --steps forwards, nothing else "
                                                        "(numbers printed under a profiler are never bench values)")
     args = ap.parse_args()

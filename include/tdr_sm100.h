@@ -111,13 +111,14 @@ int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H, int W, int
  *                   pixel chunks into `partials`).  qkv = bf16 [B, P, ld] with q|k|v at channel offsets 0|C|2C.
  *   tdr_mdta_weff : reduce partials, attn = softmax(G / (|q||k|) * temperature) R:266-270, and fold it into
  *                   project_out: Weff[b] = W_out * blockdiag(attn)  -> bf16 [B][C][weff_ld]; then `attn @ v` +
- *                   project_out is tdr_conv_gemm(v, Weff, w_batched=1).  Optionally exports attn (fp32 [B,heads,c,c]).
+ *                   project_out is tdr_conv_gemm(v, Weff, w_batched=1).  attn_ws: fp32 [B,heads,c,c] workspace that
+ *                   receives the attention maps (two launches: softmax, fold).
  * ------------------------------------------------------------------------------------------------------------- */
 size_t tdr_mdta_partials_bytes(int B, long long P, int C, int heads);
 int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long long P, int C, int heads, float* partials,
                   cudaStream_t stream);
 int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature /* [heads] */,
-                  const float* w_out /* fp32 [C][C] */, void* weff_bf16, long long weff_ld, float* attn_out,
+                  const float* w_out /* fp32 [C][C] */, void* weff_bf16, long long weff_ld, float* attn_ws,
                   cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ static int make_plan(int B, long long P, int C, int heads, GramPlan* p) {
   p->boxes = p->c <= 64 ? 1 : 2;
   p->stages = p->boxes == 1 ? 4 : 3;
   p->tiles_total = (int)((P + kPixTile - 1) / kPixTile);
-  int want = (2 * tdr_num_sms()) / (B * heads);
+  int want = tdr_num_sms() / (B * heads);
   if (want < 1) want = 1;
   if (want > p->tiles_total) want = p->tiles_total;
   p->tiles_per_chunk = (p->tiles_total + want - 1) / want;
@@ -167,60 +167,88 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
   }
 }
 
-// grid (heads, B); reduces partials, softmax, Weff = W_out * blockdiag(attn)
-__global__ void __launch_bounds__(256) mdta_weff_kernel(const float* __restrict__ partials, int C, int heads,
-                                                        int nchunks, const float* __restrict__ temperature,
-                                                        const float* __restrict__ w_out, bf16* __restrict__ weff,
-                                                        long long weff_ld, float* __restrict__ attn_out) {
-  extern __shared__ float sm[];
+// Stage 1 of the finalize: grid (ceil(c/8), heads, B), one warp per attention row.  Reduces the per-chunk partial
+// Grams (deterministic order), applies the F.normalize denominators, temperature and the row softmax.
+__global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restrict__ partials, int C, int heads,
+                                                           int nchunks, const float* __restrict__ temperature,
+                                                           float* __restrict__ attn) {
   const int c = C / heads;
-  float* attn = sm;                 // [c][c]
-  float* nq = sm + c * c;           // [c]
-  float* nk = nq + c;               // [c]
-  const int h = blockIdx.x, b = blockIdx.y;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= c) return;
   const size_t psz = (size_t)c * c + 2 * c;
   const float* base = partials + (size_t)(b * heads + h) * nchunks * psz;
-  for (int i = threadIdx.x; i < (int)psz; i += blockDim.x) {
-    float s = 0.f;
-    for (int ch = 0; ch < nchunks; ++ch) s += base[(size_t)ch * psz + i];
-    sm[i] = s;
+  float g[4] = {0.f, 0.f, 0.f, 0.f}, nk[4] = {0.f, 0.f, 0.f, 0.f};
+  float nq = 0.f;
+  for (int ch = 0; ch < nchunks; ++ch) {
+    const float* p = base + (size_t)ch * psz;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int j = lane + 32 * t;
+      if (j < c) {
+        g[t] += p[i * c + j];
+        nk[t] += p[c * c + c + j];
+      }
+    }
+    nq += p[c * c + i];
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) nq[i] = fmaxf(sqrtf(fmaxf(nq[i], 0.f)), 1e-12f);
-  __syncthreads();
+  const float nqi = fmaxf(sqrtf(fmaxf(nq, 0.f)), 1e-12f);
   const float temp = temperature[h];
-  // one warp per row: softmax over j
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = warp; i < c; i += blockDim.x >> 5) {
-    float mx = -INFINITY;
-    for (int j = lane; j < c; j += 32) {
-      const float v = attn[i * c + j] / (nq[i] * nk[j]) * temp;
-      attn[i * c + j] = v;
-      mx = fmaxf(mx, v);
-    }
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float s = 0.f;
-    for (int j = lane; j < c; j += 32) {
-      const float e = __expf(attn[i * c + j] - mx);
-      attn[i * c + j] = e;
-      s += e;
-    }
-    s = warp_sum(s);
-    const float inv = 1.f / s;
-    for (int j = lane; j < c; j += 32) {
-      const float p = attn[i * c + j] * inv;
-      attn[i * c + j] = p;
-      if (attn_out) attn_out[((size_t)(b * heads + h) * c + i) * c + j] = p;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int j = lane + 32 * t;
+    if (j < c) {
+      g[t] = g[t] / (nqi * fmaxf(sqrtf(fmaxf(nk[t], 0.f)), 1e-12f)) * temp;
+      mx = fmaxf(mx, g[t]);
     }
   }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int j = lane + 32 * t;
+    if (j < c) {
+      g[t] = __expf(g[t] - mx);
+      sum += g[t];
+    }
+  }
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  float* out = attn + ((size_t)(b * heads + h) * c + i) * c;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int j = lane + 32 * t;
+    if (j < c) out[j] = g[t] * inv;
+  }
+}
+
+// Stage 2: grid (ceil(C/32), heads, B).  Weff[b][co][h*c + j] = sum_i W_out[co][h*c + i] * attn[b,h,i,j]
+__global__ void __launch_bounds__(256) mdta_fold_kernel(const float* __restrict__ attn, int C, int heads,
+                                                        const float* __restrict__ w_out, bf16* __restrict__ weff,
+                                                        long long weff_ld) {
+  extern __shared__ float sm[];
+  const int c = C / heads;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int co0 = blockIdx.x * 32;
+  float* a = sm;                   // [c][c]
+  float* wsm = sm + c * c;         // [32][c]
+  const float* src = attn + (size_t)(b * heads + h) * c * c;
+  for (int t = threadIdx.x; t < c * c; t += blockDim.x) a[t] = src[t];
+  for (int t = threadIdx.x; t < 32 * c; t += blockDim.x) {
+    const int co = co0 + t / c;
+    wsm[t] = co < C ? w_out[(size_t)co * C + h * c + t % c] : 0.f;
+  }
   __syncthreads();
-  // Weff[b][co][h*c + j] = sum_i W_out[co][h*c + i] * attn[i][j]
-  for (int idx = threadIdx.x; idx < C * c; idx += blockDim.x) {
-    const int co = idx / c, j = idx % c;
-    const float* wrow = w_out + (size_t)co * C + h * c;
+  for (int idx = threadIdx.x; idx < 32 * c; idx += blockDim.x) {
+    const int r = idx / c, j = idx % c;
+    if (co0 + r >= C) break;
+    const float* wr = wsm + r * c;
     float s = 0.f;
-    for (int i = 0; i < c; ++i) s = fmaf(wrow[i], attn[i * c + j], s);
-    weff[((size_t)b * C + co) * weff_ld + h * c + j] = __float2bfloat16(s);
+#pragma unroll 4
+    for (int i = 0; i < c; ++i) s = fmaf(wr[i], a[i * c + j], s);
+    weff[((size_t)b * C + co0 + r) * weff_ld + h * c + j] = __float2bfloat16(s);
   }
 }
 
@@ -260,21 +288,25 @@ extern "C" int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long lon
 }
 
 extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature,
-                             const float* w_out, void* weff_bf16, long long weff_ld, float* attn_out,
+                             const float* w_out, void* weff_bf16, long long weff_ld, float* attn_ws,
                              cudaStream_t stream) {
-  TDR_CHECK_ARG(partials && temperature && w_out && weff_bf16, "tdr_mdta_weff: null pointer");
+  TDR_CHECK_ARG(partials && temperature && w_out && weff_bf16 && attn_ws, "tdr_mdta_weff: null pointer");
   GramPlan p;
   TDR_CHECK_ARG(make_plan(B, P, C, heads, &p) == 0, "tdr_mdta_weff: unsupported head width");
   TDR_CHECK_ARG(weff_ld >= C && weff_ld % 8 == 0, "tdr_mdta_weff: bad weff_ld");
-  const size_t smem = ((size_t)p.c * p.c + 2 * p.c) * sizeof(float);
+  {
+    dim3 grid((p.c + 7) / 8, heads, B);
+    mdta_softmax_kernel<<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws);
+    TDR_CHECK_LAUNCH();
+  }
+  const size_t smem = ((size_t)p.c * p.c + 32 * p.c) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(mdta_weff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(mdta_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  dim3 grid(heads, B);
-  mdta_weff_kernel<<<grid, 256, smem, stream>>>(partials, C, heads, p.nchunks, temperature, w_out,
-                                                reinterpret_cast<bf16*>(weff_bf16), weff_ld, attn_out);
+  dim3 grid((C + 31) / 32, heads, B);
+  mdta_fold_kernel<<<grid, 256, smem, stream>>>(attn_ws, C, heads, w_out, reinterpret_cast<bf16*>(weff_bf16), weff_ld);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

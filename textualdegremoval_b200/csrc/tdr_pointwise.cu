@@ -76,80 +76,129 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ depthwise 3x3
+// Column-strip sliding window: a thread owns one x position and VEC channels (8 when ungated, 4 + 4 of the two GDFN
+// halves when gated) and walks down R rows.  Each input row is loaded once per thread (3 vectors: x-1, x, x+1) and
+// immediately scattered into the three pending output rows it contributes to, so nothing but 3 accumulator rows and the
+// 9 x VEC fp32 weights live in registers.  x-neighbours are served by L1 (adjacent threads = adjacent channel groups of
+// the same pixel, so every warp load is a contiguous 512 B run); rows are re-used from registers, never re-read.
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
-template <int PIX>
-__device__ __forceinline__ void dw_accumulate(const bf16* __restrict__ in, long long in_ld, int H, int W, int b, int y,
-                                              int x0, int c0, int C, const float* __restrict__ wt, float (*acc)[8]) {
+template <int VEC>
+struct PackT;
+template <>
+struct PackT<8> {
+  typedef uint4 type;
+};
+template <>
+struct PackT<4> {
+  typedef uint2 type;
+};
+
+template <int VEC>
+__device__ __forceinline__ void load_vec(const bf16* p, bool ok, float* f) {
+  typename PackT<VEC>::type raw;
+  if (ok) {
+    raw = __ldg(reinterpret_cast<const typename PackT<VEC>::type*>(p));
+  } else {
+    memset(&raw, 0, sizeof(raw));
+  }
+  const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
-  for (int dy = 0; dy < 3; ++dy) {
-    const int iy = y + dy - 1;
-    if (iy < 0 || iy >= H) continue;
-    float px[PIX + 2][8];
-#pragma unroll
-    for (int j = 0; j < PIX + 2; ++j) {
-      const int ix = x0 - 1 + j;
-      if (ix >= 0 && ix < W) {
-        unpack8(*reinterpret_cast<const bf16x8*>(in + (((long long)b * H + iy) * W + ix) * in_ld + c0), px[j]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) px[j][e] = 0.f;
-      }
-    }
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (dy * 3 + dx) * C + c0));
-      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (dy * 3 + dx) * C + c0 + 4));
-      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-      for (int p = 0; p < PIX; ++p)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(wv[e], px[p + dx][e], acc[p][e]);
-    }
+  for (int i = 0; i < VEC / 2; ++i) {
+    f[2 * i] = __uint_as_float(u[i] << 16);
+    f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
   }
 }
 
-template <int PIX>
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H,
-                                                        int W, int C, const float* __restrict__ wt,
-                                                        const float* __restrict__ bias, int gate,
-                                                        bf16* __restrict__ out, long long out_ld) {
-  const int Cout = gate ? (C >> 1) : C;
-  const int ncg = Cout >> 3;
-  const int nxg = (W + PIX - 1) / PIX;
-  const long long total = (long long)B * H * nxg * ncg;
-  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(it % ncg);
-    long long r = it / ncg;
-    const int xg = (int)(r % nxg);
-    r /= nxg;
-    const int y = (int)(r % H);
-    const int b = (int)(r / H);
-    const int x0 = xg * PIX, c0 = cg * 8;
-    float acc[PIX][8];
+template <int VEC>
+__device__ __forceinline__ void store_vec(bf16* p, const float* f) {
+  typename PackT<VEC>::type raw;
+  uint32_t* u = reinterpret_cast<uint32_t*>(&raw);
 #pragma unroll
-    for (int p = 0; p < PIX; ++p)
+  for (int i = 0; i < VEC / 2; ++i) u[i] = pack2(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<typename PackT<VEC>::type*>(p) = raw;
+}
+
+// NH = number of channel halves handled per thread (1 ungated, 2 gated); VEC channels per half.
+template <int NH, int VEC, int R>
+__global__ void __launch_bounds__(256) dwconv3x3_strip_kernel(const bf16* __restrict__ in, long long in_ld, int H, int W,
+                                                              int C, const float* __restrict__ wt,
+                                                              const float* __restrict__ bias, int gate,
+                                                              bf16* __restrict__ out, long long out_ld) {
+  const int Cout = NH == 2 ? (C >> 1) : C;
+  const int ncg = Cout / VEC;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= W * ncg) return;
+  const int cg = item % ncg, x = item / ncg;
+  const int y0 = blockIdx.y * R;
+  const int b = blockIdx.z;
+  const int c0 = cg * VEC;
+
+  float w[NH][9][VEC];
+  float bv[NH][VEC];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[p][e] = bias ? bias[c0 + e] : 0.f;
-    dw_accumulate<PIX>(in, in_ld, H, W, b, y, x0, c0, C, wt, acc);
-    if (gate) {
-      float acc2[PIX][8];
+  for (int h = 0; h < NH; ++h) {
 #pragma unroll
-      for (int p = 0; p < PIX; ++p)
+    for (int t = 0; t < 9; ++t)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc2[p][e] = bias ? bias[Cout + c0 + e] : 0.f;
-      dw_accumulate<PIX>(in, in_ld, H, W, b, y, x0, Cout + c0, C, wt, acc2);
+      for (int e = 0; e < VEC; e += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * C + h * Cout + c0 + e));
+        w[h][t][e] = v.x; w[h][t][e + 1] = v.y; w[h][t][e + 2] = v.z; w[h][t][e + 3] = v.w;
+      }
 #pragma unroll
-      for (int p = 0; p < PIX; ++p)
+    for (int e = 0; e < VEC; ++e) bv[h][e] = bias ? bias[h * Cout + c0 + e] : 0.f;
+  }
+  // acc[k] = pending output row (r - 1 + k) while consuming input row r
+  float acc[3][NH][VEC];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[p][e] = (gate == 1 ? gelu_erf(acc[p][e]) : acc[p][e]) * acc2[p][e];
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc[k][h][e] = bv[h][e];
+
+  const bool xl_ok = x > 0, xr_ok = x + 1 < W;
+  const bf16* base = in + ((size_t)b * H * W) * in_ld + c0;
+  const int r_end = min(y0 + R, H);
+  for (int r = y0 - 1; r <= r_end; ++r) {
+    if (r >= 0 && r < H) {
+      const bf16* rowp = base + ((size_t)r * W + x) * in_ld;
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+        float v[3][VEC];
+        load_vec<VEC>(rowp + h * Cout - in_ld, xl_ok, v[0]);
+        load_vec<VEC>(rowp + h * Cout, true, v[1]);
+        load_vec<VEC>(rowp + h * Cout + in_ld, xr_ok, v[2]);
+        // input row r is tap ky = 2 of output row r-1, ky = 1 of row r, ky = 0 of row r+1
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[k][h][e] = fmaf(w[h][(2 - k) * 3 + kx][e], v[kx][e], acc[k][h][e]);
+      }
+    }
+    // output row r-1 is complete
+    const int ro = r - 1;
+    if (ro >= y0 && ro < r_end) {
+      float o[VEC];
+      if (NH == 2) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o[e] = (gate == 1 ? gelu_erf(acc[0][0][e]) : acc[0][0][e]) * acc[0][NH - 1][e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o[e] = acc[0][0][e];
+      }
+      store_vec<VEC>(out + (((size_t)b * H + ro) * W + x) * out_ld + c0, o);
     }
 #pragma unroll
-    for (int p = 0; p < PIX; ++p) {
-      if (x0 + p < W)
-        *reinterpret_cast<bf16x8*>(out + (((long long)b * H + y) * W + x0 + p) * out_ld + c0) = pack8(acc[p]);
-    }
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        acc[0][h][e] = acc[1][h][e];
+        acc[1][h][e] = acc[2][h][e];
+        acc[2][h][e] = bv[h][e];
+      }
   }
 }
 
@@ -347,13 +396,22 @@ extern "C" int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H,
   TDR_CHECK_ARG(in_bf16 && out_bf16 && weight, "tdr_dwconv3x3: null pointer");
   TDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "tdr_dwconv3x3: bad dims");
   TDR_CHECK_ARG(gate >= 0 && gate <= 2, "tdr_dwconv3x3: bad gate");
-  TDR_CHECK_ARG(C % (gate ? 16 : 8) == 0, "tdr_dwconv3x3: C must be a multiple of %d", gate ? 16 : 8);
-  TDR_CHECK_ARG(in_ld % 8 == 0 && out_ld % 8 == 0, "tdr_dwconv3x3: strides must be multiples of 8");
-  const int Cout = gate ? C / 2 : C;
-  const long long items = (long long)B * H * ((W + 3) / 4) * (Cout / 8);
-  dwconv3x3_kernel<4><<<grid_for(items, 256, 16), 256, 0, stream>>>(reinterpret_cast<const bf16*>(in_bf16), in_ld, B, H,
-                                                                    W, C, weight, bias, gate,
-                                                                    reinterpret_cast<bf16*>(out_bf16), out_ld);
+  TDR_CHECK_ARG(C % 8 == 0, "tdr_dwconv3x3: C must be a multiple of 8");
+  TDR_CHECK_ARG(in_ld % 8 == 0 && out_ld % 4 == 0, "tdr_dwconv3x3: bad strides");
+  TDR_CHECK_ARG(((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)out_bf16 & 7) == 0, "tdr_dwconv3x3: alignment");
+  constexpr int R = 16;
+  const bf16* in = reinterpret_cast<const bf16*>(in_bf16);
+  bf16* out = reinterpret_cast<bf16*>(out_bf16);
+  if (gate) {
+    const int items = W * (C / 2 / 4);
+    dim3 grid((items + 255) / 256, (H + R - 1) / R, B);
+    dwconv3x3_strip_kernel<2, 4, R><<<grid, 256, 0, stream>>>(in, in_ld, H, W, C, weight, bias, gate, out, out_ld);
+  } else {
+    TDR_CHECK_ARG(out_ld % 8 == 0 && ((uintptr_t)out_bf16 & 15) == 0, "tdr_dwconv3x3: output alignment");
+    const int items = W * (C / 8);
+    dim3 grid((items + 255) / 256, (H + R - 1) / R, B);
+    dwconv3x3_strip_kernel<1, 8, R><<<grid, 256, 0, stream>>>(in, in_ld, H, W, C, weight, bias, gate, out, out_ld);
+  }
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -222,7 +222,7 @@ def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False):
           nbytes=B * P * 2 * C_ * 2, flops=3 * 2 * B * P * C_ * (C_ // heads))
     cp = round_up(C_, 8)
     weff = torch.empty((B, C_, cp), dtype=BF16, device=qkv.device)
-    attn = torch.empty((B, heads, C_ // heads, C_ // heads), dtype=F32, device=qkv.device) if want_attn else None
+    attn = torch.empty((B, heads, C_ // heads, C_ // heads), dtype=F32, device=qkv.device)
     _call("tdr_mdta_weff", _p(partials), B, P, C_, heads, _p(temperature), _p(w_out), _p(weff), cp, _p(attn),
           _stream(), tag=f"C{C_}_h{heads}", nbytes=nbytes + _nb(weff))
     return (weff, attn) if want_attn else weff
