@@ -19,6 +19,8 @@
 //               overlaps the main loop of tile i+1.  tcgen05.commit releases smem stages / publishes TMEM.
 //   warps 2..9  epilogue: tcgen05.ld (thread = pixel row) -> bias / ReLU / row-scale / alpha / two residuals
 //               -> 128-bit stores, fp32 and/or bf16, plain or pixel-(un)shuffled addressing.
+#include <string.h>
+
 #include "tdr_common.cuh"
 
 namespace {
@@ -29,6 +31,7 @@ constexpr int kChunkK = 64;                       // bf16 elements = 128 B = one
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kEpiStageBytes = 32 * 128;          // per epilogue warp: 32 rows x 128 B, 16 B chunks XOR-swizzled
 
 struct ConvGemmArgs {
   int B, OH, OW;
@@ -51,52 +54,20 @@ struct ConvGemmArgs {
   float* out_f32;     long long out_f32_ld;
   bf16* out_bf16;     long long out_bf16_ld;
   int store_mode;               // 0 plain, 1 pixel-unshuffle(2), 2 pixel-shuffle(2)
+  int epi_mode;                 // 0 generic staged stores; 1 bf16-only output through TMA stores (map_o)
 };
-
-__device__ __forceinline__ void store_run8(const ConvGemmArgs& a, float r1s, long long row, int col, const float* v) {
-  // 8 consecutive output channels of one pixel row (plain addressing)
-  float o[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = v[i];
-  if (a.res1) {
-    const float4* r = reinterpret_cast<const float4*>(a.res1 + row * a.res1_ld + col);
-    float4 r0 = r[0], r1 = r[1];
-    o[0] += r1s * r0.x; o[1] += r1s * r0.y; o[2] += r1s * r0.z; o[3] += r1s * r0.w;
-    o[4] += r1s * r1.x; o[5] += r1s * r1.y; o[6] += r1s * r1.z; o[7] += r1s * r1.w;
-  }
-  if (a.res2) {
-    if (a.res2_bf16) {
-      float r[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(reinterpret_cast<const bf16*>(a.res2) + row * a.res2_ld + col), r);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += r[i];
-    } else {
-      const float4* r = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res2) + row * a.res2_ld + col);
-      float4 r0 = r[0], r1 = r[1];
-      o[0] += r0.x; o[1] += r0.y; o[2] += r0.z; o[3] += r0.w;
-      o[4] += r1.x; o[5] += r1.y; o[6] += r1.z; o[7] += r1.w;
-    }
-  }
-  if (a.out_f32) {
-    float4* p = reinterpret_cast<float4*>(a.out_f32 + row * a.out_f32_ld + col);
-    p[0] = make_float4(o[0], o[1], o[2], o[3]);
-    p[1] = make_float4(o[4], o[5], o[6], o[7]);
-  }
-  if (a.out_bf16) {
-    *reinterpret_cast<bf16x8*>(a.out_bf16 + row * a.out_bf16_ld + col) = pack8(o);
-  }
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_constant__ TdrTensorMap map_w,
-                 const ConvGemmArgs a) {
+                 const __grid_constant__ TdrTensorMap map_o, const ConvGemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages][barriers][tmem ptr]; base rounded up to 1024 B for SWIZZLE_128B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = a.BN * kChunkK * 2;
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + kStages * b_bytes);
+  uint8_t* smem_epi = smem_b + kStages * b_bytes;              // kEpiWarps x 4 KiB store-staging tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiWarps * kEpiStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* tfull = bars + 2 * kStages;
@@ -109,6 +80,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
+    if (a.epi_mode == 1) tma_prefetch_desc(&map_o);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -216,50 +188,190 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * a.BN;
-      for (int c16 = c_begin; c16 < c_end; ++c16) {
-        uint32_t raw[16];
-        tmem_ld16(t_base + c16 * 16, raw);
-        tmem_ld_wait();
-        const int col0 = nt * a.BN + c16 * 16;
-        if (valid && col0 < a.Co) {
-          float v[16];
+      if (a.epi_mode == 1) {
+        // bf16-only output: phase 1 (thread = pixel row) applies the column-wise epilogue and writes a SWIZZLE_128B
+        // [32 pixels x 64 channels] staging tile; one lane then hands the tile to the TMA engine, which clips it
+        // against Co / OW / OH and writes full 128 B lines.  64-column sub-blocks alternate between the two warps
+        // of a TMEM lane quadrant.
+        uint8_t* stg = smem_epi + ew * kEpiStageBytes;
+        const bool plain = !a.bias && !a.rowscale && !a.relu && alpha == 1.f;
+        const int box_w = a.TW < 32 ? a.TW : 32;                 // pixels per staged image row
+        const int tx0 = (r % a.tiles_x) * a.TW + (a.TW > 32 ? quad * 32 : 0);
+        const int ty0 = (r / a.tiles_x) * a.TH + (a.TW > 32 ? 0 : quad * (32 / box_w));
+        for (int sb = half; sb * 64 < a.BN; sb += 2) {
+          const int cs = sb * 64;
+          if (nt * a.BN + cs >= a.Co) break;
+          uint32_t raw[4][16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float x = __uint_as_float(raw[i]) * rs;
-            if (a.bias && col0 + i < a.Co) x += a.bias[col0 + i];
-            if (a.relu) x = fmaxf(x, 0.f);
-            v[i] = x * alpha;
-          }
-          if (a.store_mode == 0) {
-            store_run8(a, r1s, pix, col0, v);
-            if (col0 + 8 < a.Co) store_run8(a, r1s, pix, col0 + 8, v + 8);
-          } else if (a.store_mode == 1) {
-            // PixelUnshuffle(2): out[b, oy/2, ox/2, co*4 + (oy&1)*2 + (ox&1)]
-            const long long row = ((long long)b * (a.OH >> 1) + (oy >> 1)) * (a.OW >> 1) + (ox >> 1);
-            const int sub = ((oy & 1) << 1) | (ox & 1);
+          for (int j = 0; j < 4; ++j) tmem_ld16(t_base + cs + j * 16, raw[j]);
+          tmem_ld_wait();
+          if (lane == 0) tma_store_wait_read();                  // previous bulk store has finished reading stg
+          __syncwarp();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int co = col0 + i;
-              if (co < a.Co) {
-                if (a.out_f32) a.out_f32[row * a.out_f32_ld + co * 4 + sub] = v[i];
-                if (a.out_bf16) a.out_bf16[row * a.out_bf16_ld + co * 4 + sub] = __float2bfloat16(v[i]);
+          for (int j = 0; j < 4; ++j) {
+            const int col0 = nt * a.BN + cs + j * 16;
+            float v[16];
+            if (plain) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[j][i]);
+            } else {
+              float bb[16];
+#pragma unroll
+              for (int i4 = 0; i4 < 4; ++i4) {
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (a.bias && col0 + i4 * 4 < a.Co) t = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i4 * 4));
+                bb[i4 * 4] = t.x; bb[i4 * 4 + 1] = t.y; bb[i4 * 4 + 2] = t.z; bb[i4 * 4 + 3] = t.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float x = fmaf(__uint_as_float(raw[j][i]), rs, bb[i]);
+                if (a.relu) x = fmaxf(x, 0.f);
+                v[i] = x * alpha;
               }
             }
-          } else {
-            // PixelShuffle(2): out[b, 2*oy + i, 2*ox + j, co/4] with (i, j) = ((co%4)/2, co%2)
 #pragma unroll
-            for (int sub = 0; sub < 4; ++sub) {
-              const long long row = ((long long)b * (a.OH * 2) + (oy * 2 + (sub >> 1))) * (a.OW * 2) + ox * 2 + (sub & 1);
-              const int cq = col0 >> 2;        // 4 consecutive output channels
-              if (col0 < a.Co) {
-                if (a.out_f32)
-                  *reinterpret_cast<float4*>(a.out_f32 + row * a.out_f32_ld + cq) =
-                      make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
+            for (int hh = 0; hh < 2; ++hh) {
+              const int ch = j * 2 + hh;
+              *reinterpret_cast<bf16x8*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) = pack8(v + hh * 8);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_4d(&map_o, stg, nt * a.BN + cs, tx0, ty0, b);
+            tma_store_commit();
+          }
+        }
+      } else if (a.store_mode == 0) {
+        // Coalesced stores through a per-warp staging tile: phase 1 (thread = pixel row) applies the column-wise
+        // epilogue and writes 16 B chunks, XOR-swizzled by (row & 7); phase 2 re-reads them with 8 lanes per row so
+        // that every global access of the warp is 4 full 128 B lines (residual loads included).
+        uint8_t* stg = smem_epi + ew * kEpiStageBytes;
+        const bool direct16 = a.out_bf16 && !a.out_f32 && !a.res1 && !a.res2;
+        const int sub_cols = direct16 ? 64 : 32;
+        const int col_hi = c_end * 16;
+        for (int cs = c_begin * 16; cs < col_hi; cs += sub_cols) {
+          const int ncols = min(sub_cols, col_hi - cs);
+          const int n16 = ncols >> 4;
+          uint32_t raw[4][16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < n16) tmem_ld16(t_base + cs + j * 16, raw[j]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < n16) {
+              const int col0 = nt * a.BN + cs + j * 16;
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float x = __uint_as_float(raw[j][i]) * rs;
+                if (a.bias && col0 + i < a.Co) x += a.bias[col0 + i];
+                if (a.relu) x = fmaxf(x, 0.f);
+                v[i] = x * alpha;
+              }
+              if (direct16) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const int ch = j * 2 + hh;
+                  *reinterpret_cast<bf16x8*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) = pack8(v + hh * 8);
+                }
+              } else {
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                  const int ch = j * 4 + hh;        // j < 2 here (32 columns per sub-block)
+                  *reinterpret_cast<float4*>(stg + lane * 128 + (((ch & 7) ^ (lane & 7)) << 4)) =
+                      make_float4(v[hh * 4], v[hh * 4 + 1], v[hh * 4 + 2], v[hh * 4 + 3]);
+                }
+              }
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int rl = i8 * 4 + (lane >> 3), ch = lane & 7;
+            const int v_r = __shfl_sync(0xffffffffu, (int)valid, rl);
+            const long long pix_r = __shfl_sync(0xffffffffu, pix, rl);
+            const uint4 val = *reinterpret_cast<const uint4*>(stg + rl * 128 + ((ch ^ (rl & 7)) << 4));
+            if (direct16) {
+              const int col = nt * a.BN + cs + ch * 8;
+              if (v_r && ch * 8 < ncols && col < a.Co)
+                *reinterpret_cast<uint4*>(a.out_bf16 + pix_r * a.out_bf16_ld + col) = val;
+            } else {
+              const int col = nt * a.BN + cs + ch * 4;
+              if (v_r && ch * 4 < ncols && col < a.Co) {
+                float4 o = *reinterpret_cast<const float4*>(&val);
+                if (a.res1) {
+                  const float4 r = *reinterpret_cast<const float4*>(a.res1 + pix_r * a.res1_ld + col);
+                  o.x += r1s * r.x; o.y += r1s * r.y; o.z += r1s * r.z; o.w += r1s * r.w;
+                }
+                if (a.res2) {
+                  if (a.res2_bf16) {
+                    const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(a.res2) +
+                                                                    pix_r * a.res2_ld + col);
+                    o.x += __uint_as_float(r.x << 16); o.y += __uint_as_float(r.x & 0xffff0000u);
+                    o.z += __uint_as_float(r.y << 16); o.w += __uint_as_float(r.y & 0xffff0000u);
+                  } else {
+                    const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res2) +
+                                                                      pix_r * a.res2_ld + col);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                  }
+                }
+                if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + pix_r * a.out_f32_ld + col) = o;
                 if (a.out_bf16) {
                   uint2 pk;
-                  pk.x = pack2(v[sub], v[4 + sub]);
-                  pk.y = pack2(v[8 + sub], v[12 + sub]);
-                  *reinterpret_cast<uint2*>(a.out_bf16 + row * a.out_bf16_ld + cq) = pk;
+                  pk.x = pack2(o.x, o.y);
+                  pk.y = pack2(o.z, o.w);
+                  *reinterpret_cast<uint2*>(a.out_bf16 + pix_r * a.out_bf16_ld + col) = pk;
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        for (int c16 = c_begin; c16 < c_end; ++c16) {
+          uint32_t raw[16];
+          tmem_ld16(t_base + c16 * 16, raw);
+          tmem_ld_wait();
+          const int col0 = nt * a.BN + c16 * 16;
+          if (valid && col0 < a.Co) {
+            float v[16];
+  #pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float x = __uint_as_float(raw[i]) * rs;
+              if (a.bias && col0 + i < a.Co) x += a.bias[col0 + i];
+              if (a.relu) x = fmaxf(x, 0.f);
+              v[i] = x * alpha;
+            }
+            if (a.store_mode == 1) {
+              // PixelUnshuffle(2): out[b, oy/2, ox/2, co*4 + (oy&1)*2 + (ox&1)]
+              const long long row = ((long long)b * (a.OH >> 1) + (oy >> 1)) * (a.OW >> 1) + (ox >> 1);
+              const int sub = ((oy & 1) << 1) | (ox & 1);
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int co = col0 + i;
+                if (co < a.Co) {
+                  if (a.out_f32) a.out_f32[row * a.out_f32_ld + co * 4 + sub] = v[i];
+                  if (a.out_bf16) a.out_bf16[row * a.out_bf16_ld + co * 4 + sub] = __float2bfloat16(v[i]);
+                }
+              }
+            } else {
+              // PixelShuffle(2): out[b, 2*oy + i, 2*ox + j, co/4] with (i, j) = ((co%4)/2, co%2)
+  #pragma unroll
+              for (int sub = 0; sub < 4; ++sub) {
+                const long long row = ((long long)b * (a.OH * 2) + (oy * 2 + (sub >> 1))) * (a.OW * 2) + ox * 2 + (sub & 1);
+                const int cq = col0 >> 2;        // 4 consecutive output channels
+                if (col0 < a.Co) {
+                  if (a.out_f32)
+                    *reinterpret_cast<float4*>(a.out_f32 + row * a.out_f32_ld + cq) =
+                        make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
+                  if (a.out_bf16) {
+                    uint2 pk;
+                    pk.x = pack2(v[sub], v[4 + sub]);
+                    pk.y = pack2(v[8 + sub], v[12 + sub]);
+                    *reinterpret_cast<uint2*>(a.out_bf16 + row * a.out_bf16_ld + cq) = pk;
+                  }
                 }
               }
             }
@@ -270,6 +382,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
+    if (a.epi_mode == 1 && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -374,10 +487,23 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   if (OH == 1) { a.TW = 128; a.TH = 1; }         // flat [rows, C] GEMM view
   a.tiles_x = tdr_cdiv(OW, a.TW);
   a.tiles_y = tdr_cdiv(OH, a.TH);
-  // N tiling: equal tiles of at most 256 columns, multiples of 16
-  const int co16 = tdr_cdiv(d->Co, 16) * 16;
-  a.n_tiles = tdr_cdiv(co16, 256);
-  a.BN = tdr_cdiv(tdr_cdiv(co16, a.n_tiles), 16) * 16;
+  a.epi_mode = (d->impl == 0 && d->store_mode == 0 && d->out_bf16 && !d->out_f32 && !d->res1 && !d->res2 &&
+                ((uintptr_t)d->out_bf16 & 15) == 0 && d->out_bf16_ld % 8 == 0) ? 1 : 0;
+  if (a.epi_mode == 1) {
+    // TMA-store epilogue works on 64-column sub-blocks: N tiles are multiples of 64 (<= 256), minimising padding
+    int best_bn = 256, best_tot = 1 << 30;
+    for (int bn = 64; bn <= 256; bn += 64) {
+      const int tot = tdr_cdiv(d->Co, bn) * bn;
+      if (tot < best_tot || (tot == best_tot && bn > best_bn)) { best_tot = tot; best_bn = bn; }
+    }
+    a.BN = best_bn;
+    a.n_tiles = tdr_cdiv(d->Co, a.BN);
+  } else {
+    // N tiling: equal tiles of at most 256 columns, multiples of 16
+    const int co16 = tdr_cdiv(d->Co, 16) * 16;
+    a.n_tiles = tdr_cdiv(co16, 256);
+    a.BN = tdr_cdiv(tdr_cdiv(co16, a.n_tiles), 16) * 16;
+  }
   a.kchunks = tdr_cdiv(d->Ci, kChunkK);
   a.total_tiles = d->B * a.tiles_y * a.tiles_x * a.n_tiles;
   uint32_t cols = 32;
@@ -394,7 +520,18 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   }
 
   TDR_CHECK_ARG(a.TW * d->stride <= 256 && a.TH * d->stride <= 256, "tdr_conv_gemm: TMA box too large");
-  TdrTensorMap map_a, map_w;
+  TdrTensorMap map_a, map_w, map_o;
+  memset(&map_o, 0, sizeof(map_o));
+  if (a.epi_mode == 1) {
+    const int box_w = a.TW < 32 ? a.TW : 32;
+    const uint64_t dims[4] = {(uint64_t)d->Co, (uint64_t)OW, (uint64_t)OH, (uint64_t)d->B};
+    const uint64_t strides[3] = {(uint64_t)d->out_bf16_ld * 2, (uint64_t)d->out_bf16_ld * 2 * OW,
+                                 (uint64_t)d->out_bf16_ld * 2 * OW * OH};
+    const uint32_t box[4] = {64, (uint32_t)box_w, (uint32_t)(32 / box_w), 1};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    int rc = tdr_make_tensor_map_bf16(&map_o, d->out_bf16, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
   {
     const uint64_t dims[4] = {(uint64_t)d->Ci, (uint64_t)img_w, (uint64_t)img_h, (uint64_t)n_img};
     const uint64_t strides[3] = {(uint64_t)d->in_ld * 2, (uint64_t)d->in_ld * 2 * img_w,
@@ -413,14 +550,14 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     int rc = tdr_make_tensor_map_bf16(&map_w, d->weight, 3, dims, strides, box, es);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + (size_t)kStages * (kABytes + a.BN * kChunkK * 2) + 256;
+  const size_t smem = 1024 + (size_t)kStages * (kABytes + a.BN * kChunkK * 2) + kEpiWarps * kEpiStageBytes + 256;
   static bool attr_set = false;
   if (!attr_set) {
     TDR_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   const int grid = a.total_tiles < tdr_num_sms() ? a.total_tiles : tdr_num_sms();
-  conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_w, a);
+  conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_w, map_o, a);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -81,50 +81,80 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
 // immediately scattered into the three pending output rows it contributes to, so nothing but 3 accumulator rows and the
 // 9 x VEC fp32 weights live in registers.  x-neighbours are served by L1 (adjacent threads = adjacent channel groups of
 // the same pixel, so every warp load is a contiguous 512 B run); rows are re-used from registers, never re-read.
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// Packed fp32x2 arithmetic (FFMA2 on sm_100): halves the FMA issue slots of this issue-bound stencil.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk2(float a, float b) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// two bf16 packed in a 32-bit word -> fp32 pair (exact)
+__device__ __forceinline__ f2 bf2_to_f2(uint32_t u) { return pk2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+
+// Exact-erf GELU (F.gelu default, R:239) on a pair.  erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below
+// the bf16 rounding of the stored result); the x < 0 branch is evaluated as a product so there is no cancellation.
+__device__ __forceinline__ f2 gelu2(f2 x) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  const float z0 = fabsf(x0) * 0.70710678118654752f, z1 = fabsf(x1) * 0.70710678118654752f;
+  const f2 z = pk2(z0, z1);
+  float d0, d1;
+  upk2(fma2(pk2(0.3275911f, 0.3275911f), z, pk2(1.f, 1.f)), d0, d1);
+  const f2 t = pk2(__frcp_rn(d0), __frcp_rn(d1));
+  f2 p = fma2(t, pk2(1.061405429f, 1.061405429f), pk2(-1.453152027f, -1.453152027f));
+  p = fma2(p, t, pk2(1.421413741f, 1.421413741f));
+  p = fma2(p, t, pk2(-0.284496736f, -0.284496736f));
+  p = fma2(p, t, pk2(0.254829592f, 0.254829592f));
+  p = mul2(p, t);
+  float e0, e1;
+  upk2(mul2(z, mul2(z, pk2(-1.4426950408889634f, -1.4426950408889634f))), e0, e1);
+  float q0, q1;
+  upk2(mul2(p, pk2(exp2f(e0), exp2f(e1))), q0, q1);          // q = 1 - erf(|x|/sqrt2)
+  const float s0 = x0 >= 0.f ? 2.f - q0 : q0, s1 = x1 >= 0.f ? 2.f - q1 : q1;
+  return mul2(mul2(x, pk2(0.5f, 0.5f)), pk2(s0, s1));
+}
 
 template <int VEC>
-struct PackT;
+struct RawT;
 template <>
-struct PackT<8> {
+struct RawT<8> {
   typedef uint4 type;
 };
 template <>
-struct PackT<4> {
+struct RawT<4> {
   typedef uint2 type;
 };
 
 template <int VEC>
-__device__ __forceinline__ void load_vec(const bf16* p, bool ok, float* f) {
-  typename PackT<VEC>::type raw;
+__device__ __forceinline__ typename RawT<VEC>::type load_raw(const bf16* p, bool ok) {
+  typename RawT<VEC>::type raw;
   if (ok) {
-    raw = __ldg(reinterpret_cast<const typename PackT<VEC>::type*>(p));
+    raw = __ldg(reinterpret_cast<const typename RawT<VEC>::type*>(p));
   } else {
     memset(&raw, 0, sizeof(raw));
   }
-  const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw);
-#pragma unroll
-  for (int i = 0; i < VEC / 2; ++i) {
-    f[2 * i] = __uint_as_float(u[i] << 16);
-    f[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u);
-  }
-}
-
-template <int VEC>
-__device__ __forceinline__ void store_vec(bf16* p, const float* f) {
-  typename PackT<VEC>::type raw;
-  uint32_t* u = reinterpret_cast<uint32_t*>(&raw);
-#pragma unroll
-  for (int i = 0; i < VEC / 2; ++i) u[i] = pack2(f[2 * i], f[2 * i + 1]);
-  *reinterpret_cast<typename PackT<VEC>::type*>(p) = raw;
+  return raw;
 }
 
 // NH = number of channel halves handled per thread (1 ungated, 2 gated); VEC channels per half.
 template <int NH, int VEC, int R>
-__global__ void __launch_bounds__(256) dwconv3x3_strip_kernel(const bf16* __restrict__ in, long long in_ld, int H, int W,
+__global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const bf16* __restrict__ in, long long in_ld, int H, int W,
                                                               int C, const float* __restrict__ wt,
                                                               const float* __restrict__ bias, int gate,
                                                               bf16* __restrict__ out, long long out_ld) {
+  typedef typename RawT<VEC>::type raw_t;
+  constexpr int NP = VEC / 2;                  // fp32 pairs per vector
   const int Cout = NH == 2 ? (C >> 1) : C;
   const int ncg = Cout / VEC;
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
@@ -134,71 +164,93 @@ __global__ void __launch_bounds__(256) dwconv3x3_strip_kernel(const bf16* __rest
   const int b = blockIdx.z;
   const int c0 = cg * VEC;
 
-  float w[NH][9][VEC];
-  float bv[NH][VEC];
+  f2 w[NH][9][NP];
+  f2 bv[NH][NP];
 #pragma unroll
   for (int h = 0; h < NH; ++h) {
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int e = 0; e < VEC; e += 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * C + h * Cout + c0 + e));
-        w[h][t][e] = v.x; w[h][t][e + 1] = v.y; w[h][t][e + 2] = v.z; w[h][t][e + 3] = v.w;
+      for (int e = 0; e < NP; e += 2) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wt + (size_t)t * C + h * Cout + c0 + 2 * e));
+        w[h][t][e] = pk2(v.x, v.y);
+        w[h][t][e + 1] = pk2(v.z, v.w);
       }
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) bv[h][e] = bias ? bias[h * Cout + c0 + e] : 0.f;
+    for (int e = 0; e < NP; ++e)
+      bv[h][e] = bias ? pk2(bias[h * Cout + c0 + 2 * e], bias[h * Cout + c0 + 2 * e + 1]) : pk2(0.f, 0.f);
   }
-  // acc[k] = pending output row (r - 1 + k) while consuming input row r
-  float acc[3][NH][VEC];
+  // Three pending output rows live in acc[]; the row loop is fully unrolled (R + 2 static iterations) so the slot
+  // rotation and the double-buffered raw rows are pure register renaming -- no MOVs are issued for them.
+  f2 acc[3][NH][NP];
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll
     for (int h = 0; h < NH; ++h)
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) acc[k][h][e] = bv[h][e];
+      for (int e = 0; e < NP; ++e) acc[k][h][e] = bv[h][e];
 
   const bool xl_ok = x > 0, xr_ok = x + 1 < W;
-  const bf16* base = in + ((size_t)b * H * W) * in_ld + c0;
+  const long long row_stride = (long long)W * in_ld;
+  const bf16* rowp = in + ((long long)b * H * W + x) * in_ld + c0 + (long long)(y0 - 1) * row_stride;   // input row y0-1
+  bf16* outp = out + (((long long)b * H + y0) * W + x) * out_ld + c0;                                   // output row y0
   const int r_end = min(y0 + R, H);
-  for (int r = y0 - 1; r <= r_end; ++r) {
-    if (r >= 0 && r < H) {
-      const bf16* rowp = base + ((size_t)r * W + x) * in_ld;
+  raw_t buf[2][NH][3];
+  {
+    const bool ok = y0 - 1 >= 0;
+#pragma unroll
+    for (int h = 0; h < NH; ++h) {
+      buf[0][h][0] = load_raw<VEC>(rowp + h * Cout - in_ld, ok && xl_ok);
+      buf[0][h][1] = load_raw<VEC>(rowp + h * Cout, ok);
+      buf[0][h][2] = load_raw<VEC>(rowp + h * Cout + in_ld, ok && xr_ok);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < R + 2; ++i) {
+    const int r = y0 - 1 + i;                   // input row consumed in this iteration
+    if (i + 1 < R + 2) {                        // prefetch input row r + 1
+      rowp += row_stride;
+      const bool ok = r + 1 <= r_end && r + 1 < H;
 #pragma unroll
       for (int h = 0; h < NH; ++h) {
-        float v[3][VEC];
-        load_vec<VEC>(rowp + h * Cout - in_ld, xl_ok, v[0]);
-        load_vec<VEC>(rowp + h * Cout, true, v[1]);
-        load_vec<VEC>(rowp + h * Cout + in_ld, xr_ok, v[2]);
-        // input row r is tap ky = 2 of output row r-1, ky = 1 of row r, ky = 0 of row r+1
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) acc[k][h][e] = fmaf(w[h][(2 - k) * 3 + kx][e], v[kx][e], acc[k][h][e]);
+        buf[(i + 1) & 1][h][0] = load_raw<VEC>(rowp + h * Cout - in_ld, ok && xl_ok);
+        buf[(i + 1) & 1][h][1] = load_raw<VEC>(rowp + h * Cout, ok);
+        buf[(i + 1) & 1][h][2] = load_raw<VEC>(rowp + h * Cout + in_ld, ok && xr_ok);
       }
     }
-    // output row r-1 is complete
-    const int ro = r - 1;
-    if (ro >= y0 && ro < r_end) {
-      float o[VEC];
-      if (NH == 2) {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) o[e] = (gate == 1 ? gelu_erf(acc[0][0][e]) : acc[0][0][e]) * acc[0][NH - 1][e];
-      } else {
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) o[e] = acc[0][0][e];
-      }
-      store_vec<VEC>(out + (((size_t)b * H + ro) * W + x) * out_ld + c0, o);
-    }
+    // input row r is tap ky = 2 - k of output row r - 1 + k, which lives in slot (i + k) % 3
 #pragma unroll
     for (int h = 0; h < NH; ++h)
 #pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        acc[0][h][e] = acc[1][h][e];
-        acc[1][h][e] = acc[2][h][e];
-        acc[2][h][e] = bv[h][e];
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint32_t* u = reinterpret_cast<const uint32_t*>(&buf[i & 1][h][kx]);
+#pragma unroll
+        for (int e = 0; e < NP; ++e) {
+          const f2 v = bf2_to_f2(u[e]);
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            acc[(i + k) % 3][h][e] = fma2(w[h][(2 - k) * 3 + kx][e], v, acc[(i + k) % 3][h][e]);
+        }
       }
+    const int ro = r - 1;                       // output row r - 1 (slot i % 3) is complete
+    if (i >= 2 && ro < r_end) {
+      raw_t o;
+      uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int e = 0; e < NP; ++e) {
+        f2 val = acc[i % 3][0][e];
+        if (NH == 2) val = mul2(gate == 1 ? gelu2(val) : val, acc[i % 3][NH - 1][e]);
+        float a0, a1;
+        upk2(val, a0, a1);
+        ou[e] = pack2(a0, a1);
+      }
+      *reinterpret_cast<raw_t*>(outp) = o;
+    }
+    if (i >= 2) outp += (long long)W * out_ld;
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+#pragma unroll
+      for (int e = 0; e < NP; ++e) acc[i % 3][h][e] = bv[h][e];
   }
 }
 

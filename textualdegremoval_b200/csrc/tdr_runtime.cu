@@ -59,8 +59,20 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+static int make_map(TdrTensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+
 int tdr_make_tensor_map_bf16(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  return make_map(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, elem_strides);
+}
+int tdr_make_tensor_map_f32(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  return make_map(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, elem_strides);
+}
+
+static int make_map(TdrTensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   static_assert(sizeof(CUtensorMap) == sizeof(TdrTensorMap), "tensor map size");
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
@@ -75,7 +87,7 @@ int tdr_make_tensor_map_bf16(TdrTensorMap* out, const void* base, int rank, cons
     es[i] = elem_strides[i];
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
-  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), dt, (cuuint32_t)rank,
                    const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

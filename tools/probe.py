@@ -1,0 +1,95 @@
+"""Run single kernels at the benchmark's shapes (for ncu captures and quick CUDA-event timing).
+
+    python tools/probe.py [name ...]        names: see PROBES
+Prints per-probe average time (CUDA events, 20 iterations after 3 warm-ups, 256 MB L2 flush between iterations),
+algorithmic GB/s and TFLOP/s.  Under ncu use:  ncu --set full -k regex:<kernel> -s 3 -c 2 python tools/probe.py <name>
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from textualdegremoval_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def r16(*s):
+    return torch.randn(*s, device=DEV, dtype=F32).to(BF16)
+
+
+def conv(B, H, W, Ci, Co, k=1, want="bf16", res=False, **kw):
+    x = r16(B, H, W, Ci)
+    w = r16(k * k, Co, ops.round_up(Ci, 8))
+    r = torch.randn(B, H, W, Co, device=DEV) if res else None
+    o32 = torch.empty(B, H, W, Co, device=DEV) if want == "f32" else None
+    nbytes = B * H * W * (Ci * 2 + Co * (2 if want == "bf16" else 4) + (Co * 4 if res else 0))
+    flops = 2 * B * H * W * Ci * Co * k * k
+    return (lambda: ops.conv_gemm(x, w, Co, k=k, pad=k // 2, res2=r, out_f32=o32, want=want, **kw)), nbytes, flops
+
+
+def dw(B, H, W, C_, gate):
+    x = r16(B, H, W, C_)
+    w = torch.randn(9, C_, device=DEV)
+    co = C_ // 2 if gate else C_
+    o = torch.empty(B, H, W, co, device=DEV, dtype=BF16)
+    return (lambda: ops.dwconv3x3(x, w, None, gate, out=o)), B * H * W * (C_ + co) * 2, 18 * B * H * W * C_
+
+
+def ln(B, H, W, C_):
+    x = torch.randn(B, H, W, C_, device=DEV)
+    w = torch.ones(C_, device=DEV)
+    b = torch.zeros(C_, device=DEV)
+    o = torch.empty(B, H, W, C_, device=DEV, dtype=BF16)
+    return (lambda: ops.rownorm(x, 1, w, b, 1e-5, out=o)), B * H * W * C_ * 6, 0
+
+
+def gram(B, H, W, C_, heads):
+    qkv = r16(B, H, W, 3 * C_)
+    t = torch.ones(heads, device=DEV)
+    wo = torch.randn(C_, C_, device=DEV)
+    return (lambda: ops.mdta_weff(qkv, C_, heads, t, wo)), B * H * W * 2 * C_ * 2, 6 * B * H * W * C_ * (C_ // heads)
+
+
+PROBES = {
+    "pin96": lambda: conv(4, 512, 512, 96, 512),
+    "qkv96": lambda: conv(4, 512, 512, 96, 288),
+    "pout256": lambda: conv(4, 512, 512, 256, 96, want="f32", res=True),
+    "qkv48": lambda: conv(4, 512, 512, 48, 144),
+    "pin192": lambda: conv(4, 128, 128, 192, 1024),
+    "c3x3_48": lambda: conv(8, 512, 512, 48, 48, k=3, relu=True),
+    "c3x3_96": lambda: conv(8, 256, 256, 96, 96, k=3, relu=True),
+    "c3x3_384": lambda: conv(8, 64, 64, 384, 384, k=3, relu=True),
+    "dwg512": lambda: dw(4, 512, 512, 512, 1),
+    "dw288": lambda: dw(4, 512, 512, 288, 0),
+    "dwg2048": lambda: dw(4, 64, 64, 2048, 1),
+    "ln96": lambda: ln(4, 512, 512, 96),
+    "gram96": lambda: gram(4, 512, 512, 96, 1),
+}
+
+
+def main():
+    names = sys.argv[1:] or list(PROBES)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    for n in names:
+        fn, nbytes, flops = PROBES[n]()
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        tot = 0.0
+        iters = 20
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            tot += s.elapsed_time(e)
+        ms = tot / iters
+        print(f"{n:10s} {ms * 1e3:9.1f} us  {nbytes / ms / 1e6:8.1f} GB/s  {flops / ms / 1e9:8.1f} TFLOP/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
