@@ -19,13 +19,14 @@
 //               overlaps the main loop of tile i+1.  tcgen05.commit releases smem stages / publishes TMEM.
 //   warps 2..9  epilogue: tcgen05.ld (thread = pixel row) -> bias / ReLU / row-scale / alpha / two residuals
 //               -> 128-bit stores, fp32 and/or bf16, plain or pixel-(un)shuffled addressing.
+#include <stdlib.h>
 #include <string.h>
 
 #include "tdr_common.cuh"
 
 namespace {
 
-constexpr int kStages = 4;
+constexpr int kMaxStages = 4;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // bf16 elements = 128 B = one swizzle row
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB
@@ -54,25 +55,36 @@ struct ConvGemmArgs {
   float* out_f32;     long long out_f32_ld;
   bf16* out_bf16;     long long out_bf16_ld;
   int store_mode;               // 0 plain, 1 pixel-unshuffle(2), 2 pixel-shuffle(2)
-  int epi_mode;                 // 0 generic staged stores; 1 bf16-only output through TMA stores (map_o)
+  int epi_mode;                 // 0 generic staged stores; 1 TMA epilogue (single-dtype output, residuals via TMA)
+  int out_is_f32;               // epi_mode 1: output (and res2) element type
+  int stages;                   // smem pipeline depth (3 or 4)
+  int epi_bufs;                 // staging buffers per epilogue warp (1 or 2)
 };
 
+// V < 0: generic epilogue (any combination of outputs / residuals / pixel (un)shuffle).
+// V >= 0: TMA epilogue specialised at compile time: bit 0 = fp32 output, bit 1 = res2 tile, bit 2 = res1 tile.
+template <int V>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_constant__ TdrTensorMap map_w,
-                 const __grid_constant__ TdrTensorMap map_o, const ConvGemmArgs a) {
+                 const __grid_constant__ TdrTensorMap map_o, const __grid_constant__ TdrTensorMap map_r2,
+                 const __grid_constant__ TdrTensorMap map_r1, const ConvGemmArgs a) {
+  constexpr bool kTma = V >= 0;
+  constexpr bool kF32 = kTma && (V & 1), kR2 = kTma && (V & 2), kR1 = kTma && (V & 4);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages][barriers][tmem ptr]; base rounded up to 1024 B for SWIZZLE_128B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_bytes = a.BN * kChunkK * 2;
   uint8_t* smem_a = smem;
+  const int kStages = a.stages;
   uint8_t* smem_b = smem + kStages * kABytes;
-  uint8_t* smem_epi = smem_b + kStages * b_bytes;              // kEpiWarps x 4 KiB store-staging tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiWarps * kEpiStageBytes);
+  uint8_t* smem_epi = smem_b + kStages * b_bytes;              // kEpiWarps x epi_bufs x 4 KiB staging tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiWarps * a.epi_bufs * kEpiStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kStages;
-  uint64_t* tfull = bars + 2 * kStages;
-  uint64_t* tempty = bars + 2 * kStages + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* empty = bars + kMaxStages;
+  uint64_t* tfull = bars + 2 * kMaxStages;
+  uint64_t* tempty = bars + 2 * kMaxStages + 2;
+  uint64_t* rbar = bars + 2 * kMaxStages + 4;                  // [kEpiWarps][2] residual-tile barriers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + 2 * kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,11 +92,16 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_w);
-    if (a.epi_mode == 1) tma_prefetch_desc(&map_o);
+    if (kTma) {
+      tma_prefetch_desc(&map_o);
+      if (kR2) tma_prefetch_desc(&map_r2);
+      if (kR1) tma_prefetch_desc(&map_r1);
+    }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
+    for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&rbar[i], 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpiWarps);
@@ -171,6 +188,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     const float alpha = a.alpha * g, r1s = a.res1_scale * g;
     const int ncol16 = a.BN / 16;
     const int c_begin = (ncol16 * half) / 2, c_end = (ncol16 * (half + 1)) / 2;
+    uint32_t rphase[2] = {0, 0};             // parity of this warp's residual-tile barriers
+    int store_cnt = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -185,54 +204,111 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       const long long pix = ((long long)b * a.OH + oy) * a.OW + ox;
       const float rs = (valid && a.rowscale) ? a.rowscale[pix] : 1.f;
 
-      mbar_wait(&tfull[acc], acc_phase);
-      tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * a.BN;
-      if (a.epi_mode == 1) {
-        // bf16-only output: phase 1 (thread = pixel row) applies the column-wise epilogue and writes a SWIZZLE_128B
-        // [32 pixels x 64 channels] staging tile; one lane then hands the tile to the TMA engine, which clips it
-        // against Co / OW / OH and writes full 128 B lines.  64-column sub-blocks alternate between the two warps
-        // of a TMEM lane quadrant.
-        uint8_t* stg = smem_epi + ew * kEpiStageBytes;
+      if constexpr (kTma) {
+        // TMA epilogue.  Sub-blocks of 128 B per pixel row (64 bf16 / 32 fp32 columns) alternate between the two
+        // warps of a TMEM lane quadrant.  Residual tiles are TMA-loaded into the same SWIZZLE_128B staging tile
+        // (prefetched before the accumulator is even ready), updated in place by phase 1 (thread = pixel row), and
+        // the tile is handed back to the TMA engine, which clips against Co / OW / OH and writes full 128 B lines.
+        constexpr int sbc = kF32 ? 32 : 64;                      // columns per sub-block
+        const int nsb = a.BN / sbc;
+        uint8_t* const buf = smem_epi + ew * a.epi_bufs * kEpiStageBytes;
+        uint64_t* const rb = rbar + ew * 2;
+        constexpr bool has_r2 = kR2, has_r1 = kR1;
+        const bool dbuf = a.epi_bufs == 2 && !has_r1;
         const bool plain = !a.bias && !a.rowscale && !a.relu && alpha == 1.f;
         const int box_w = a.TW < 32 ? a.TW : 32;                 // pixels per staged image row
         const int tx0 = (r % a.tiles_x) * a.TW + (a.TW > 32 ? quad * 32 : 0);
         const int ty0 = (r / a.tiles_x) * a.TH + (a.TW > 32 ? 0 : quad * (32 / box_w));
-        for (int sb = half; sb * 64 < a.BN; sb += 2) {
-          const int cs = sb * 64;
-          if (nt * a.BN + cs >= a.Co) break;
+        int n_my = 0;
+        for (int sb = half; sb < nsb && nt * a.BN + sb * sbc < a.Co; sb += 2) ++n_my;
+        // lane 0 only: queue the residual tile(s) of my k-th sub-block
+        auto issue_res = [&](int k) {
+          const int j = dbuf ? (k & 1) : 0;
+          const int col = nt * a.BN + (half + 2 * k) * sbc;
+          tma_store_wait_read();                                 // earlier stores have finished reading the buffers
+          mbar_expect_tx(&rb[j], has_r1 ? 2 * kEpiStageBytes : kEpiStageBytes);
+          tma_load_4d(buf + j * kEpiStageBytes, &map_r2, &rb[j], col, tx0, ty0, b);
+          if (has_r1) tma_load_4d(buf + kEpiStageBytes, &map_r1, &rb[j], col, tx0, ty0, b);
+        };
+        if (has_r2 && lane == 0 && n_my > 0) {
+          issue_res(0);
+          if (dbuf && n_my > 1) issue_res(1);
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        for (int k = 0; k < n_my; ++k) {
+          // staging buffer: residual tiles were queued into (k & 1); without residuals consecutive stores simply
+          // alternate (across tiles too), so wait_group.read 1 always covers the buffer about to be overwritten
+          const int j = !dbuf ? 0 : (has_r2 ? (k & 1) : (store_cnt++ & 1));
+          const int cs = (half + 2 * k) * sbc;
+          uint8_t* const stg = buf + j * kEpiStageBytes;
           uint32_t raw[4][16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) tmem_ld16(t_base + cs + j * 16, raw[j]);
+          for (int q4 = 0; q4 < 4; ++q4)
+            if (q4 * 16 < sbc) tmem_ld16(t_base + cs + q4 * 16, raw[q4]);
           tmem_ld_wait();
-          if (lane == 0) tma_store_wait_read();                  // previous bulk store has finished reading stg
-          __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int col0 = nt * a.BN + cs + j * 16;
-            float v[16];
-            if (plain) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[j][i]);
-            } else {
-              float bb[16];
-#pragma unroll
-              for (int i4 = 0; i4 < 4; ++i4) {
-                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (a.bias && col0 + i4 * 4 < a.Co) t = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i4 * 4));
-                bb[i4 * 4] = t.x; bb[i4 * 4 + 1] = t.y; bb[i4 * 4 + 2] = t.z; bb[i4 * 4 + 3] = t.w;
-              }
-#pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                float x = fmaf(__uint_as_float(raw[j][i]), rs, bb[i]);
-                if (a.relu) x = fmaxf(x, 0.f);
-                v[i] = x * alpha;
-              }
+          if (has_r2) {
+            mbar_wait(&rb[j], rphase[j]);
+            rphase[j] ^= 1;
+          } else {
+            if (lane == 0) {
+              if (a.epi_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read();
             }
+            __syncwarp();
+          }
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int ch = j * 2 + hh;
-              *reinterpret_cast<bf16x8*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) = pack8(v + hh * 8);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (q4 * 16 < sbc) {
+              const int col0 = nt * a.BN + cs + q4 * 16;
+              float v[16];
+              if (plain) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[q4][i]);
+              } else {
+                float bb[16];
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (a.bias && col0 + i4 * 4 < a.Co) t = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i4 * 4));
+                  bb[i4 * 4] = t.x; bb[i4 * 4 + 1] = t.y; bb[i4 * 4 + 2] = t.z; bb[i4 * 4 + 3] = t.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  float x = fmaf(__uint_as_float(raw[q4][i]), rs, bb[i]);
+                  if (a.relu) x = fmaxf(x, 0.f);
+                  v[i] = x * alpha;
+                }
+              }
+              if constexpr (kF32) {
+#pragma unroll
+                for (int hh = 0; hh < 4; ++hh) {
+                  const int off = lane * 128 + ((((q4 * 4 + hh) & 7) ^ (lane & 7)) << 4);
+                  float4 o = make_float4(v[hh * 4], v[hh * 4 + 1], v[hh * 4 + 2], v[hh * 4 + 3]);
+                  if (has_r2) {
+                    const float4 t = *reinterpret_cast<const float4*>(stg + off);
+                    o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                  }
+                  if (has_r1) {
+                    const float4 t = *reinterpret_cast<const float4*>(buf + kEpiStageBytes + off);
+                    o.x = fmaf(r1s, t.x, o.x); o.y = fmaf(r1s, t.y, o.y);
+                    o.z = fmaf(r1s, t.z, o.z); o.w = fmaf(r1s, t.w, o.w);
+                  }
+                  *reinterpret_cast<float4*>(stg + off) = o;
+                }
+              } else {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const int off = lane * 128 + (((q4 * 2 + hh) ^ (lane & 7)) << 4);
+                  if (has_r2) {
+                    float t[8];
+                    unpack8(*reinterpret_cast<const bf16x8*>(stg + off), t);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[hh * 8 + i] += t[i];
+                  }
+                  *reinterpret_cast<bf16x8*>(stg + off) = pack8(v + hh * 8);
+                }
+              }
             }
           }
           fence_proxy_async();
@@ -240,9 +316,16 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
           if (lane == 0) {
             tma_store_4d(&map_o, stg, nt * a.BN + cs, tx0, ty0, b);
             tma_store_commit();
+            if (has_r2) {
+              if (dbuf) { if (k + 2 < n_my) issue_res(k + 2); }
+              else if (k + 1 < n_my) issue_res(k + 1);
+            }
           }
+          __syncwarp();
         }
       } else if (a.store_mode == 0) {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
         // Coalesced stores through a per-warp staging tile: phase 1 (thread = pixel row) applies the column-wise
         // epilogue and writes 16 B chunks, XOR-swizzled by (row & 7); phase 2 re-reads them with 8 lanes per row so
         // that every global access of the warp is 4 full 128 B lines (residual loads included).
@@ -330,6 +413,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
           __syncwarp();
         }
       } else {
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
         for (int c16 = c_begin; c16 < c_end; ++c16) {
           uint32_t raw[16];
           tmem_ld16(t_base + c16 * 16, raw);
@@ -382,7 +467,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
     }
-    if (a.epi_mode == 1 && lane == 0) tma_store_wait_all();
+    if (kTma && lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -487,22 +572,51 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   if (OH == 1) { a.TW = 128; a.TH = 1; }         // flat [rows, C] GEMM view
   a.tiles_x = tdr_cdiv(OW, a.TW);
   a.tiles_y = tdr_cdiv(OH, a.TH);
-  a.epi_mode = (d->impl == 0 && d->store_mode == 0 && d->out_bf16 && !d->out_f32 && !d->res1 && !d->res2 &&
-                ((uintptr_t)d->out_bf16 & 15) == 0 && d->out_bf16_ld % 8 == 0) ? 1 : 0;
+  {
+    // TMA epilogue: exactly one output dtype, res2 (if any) of that dtype, res1 only with fp32 output, 16 B aligned
+    // rows everywhere.  Everything else goes through the generic (slower) staged path.
+    const bool one_out = (d->out_bf16 != nullptr) != (d->out_f32 != nullptr);
+    const bool f32o = d->out_f32 != nullptr;
+    const long long old_ = f32o ? d->out_f32_ld : d->out_bf16_ld;
+    const void* optr = f32o ? (const void*)d->out_f32 : d->out_bf16;
+    const int per16 = f32o ? 4 : 8;
+    bool ok = d->impl == 0 && d->store_mode == 0 && one_out && ((uintptr_t)optr & 15) == 0 && old_ % per16 == 0;
+    if (ok && d->res2) ok = (d->res2_bf16 != 0) == !f32o && ((uintptr_t)d->res2 & 15) == 0 && d->res2_ld % per16 == 0;
+    if (ok && d->res1) ok = f32o && d->res2 && ((uintptr_t)d->res1 & 15) == 0 && d->res1_ld % 4 == 0;
+    a.epi_mode = ok ? 1 : 0;
+    a.out_is_f32 = f32o ? 1 : 0;
+  }
   if (a.epi_mode == 1) {
-    // TMA-store epilogue works on 64-column sub-blocks: N tiles are multiples of 64 (<= 256), minimising padding
+    // N tiles are multiples of the sub-block width (64 bf16 / 32 fp32 columns, <= 256), minimising padding
+    const int sbc = a.out_is_f32 ? 32 : 64;
     int best_bn = 256, best_tot = 1 << 30;
-    for (int bn = 64; bn <= 256; bn += 64) {
+    for (int bn = sbc; bn <= 256; bn += sbc) {
       const int tot = tdr_cdiv(d->Co, bn) * bn;
       if (tot < best_tot || (tot == best_tot && bn > best_bn)) { best_tot = tot; best_bn = bn; }
     }
     a.BN = best_bn;
     a.n_tiles = tdr_cdiv(d->Co, a.BN);
+    a.epi_bufs = 2;
+    a.stages = a.BN <= 192 ? 4 : 3;
+    if (!d->res2 && !d->res1 && a.BN > 192) { a.epi_bufs = 1; a.stages = 4; }   // no residual tiles: favour depth
+    if (const char* e = getenv("TDR_CONV_EPIBUFS")) {                            // tuning knobs (experiments only)
+      const int v = atoi(e);
+      if ((v == 1 && !d->res1) || v == 2) a.epi_bufs = v;
+    }
+    if (const char* e = getenv("TDR_CONV_STAGES")) {
+      const int v = atoi(e);
+      if (v >= 2 && v <= 4) a.stages = v;
+    }
+    while (a.stages > 2 && 1024 + (size_t)a.stages * (kABytes + a.BN * kChunkK * 2) +
+                                   (size_t)kEpiWarps * a.epi_bufs * kEpiStageBytes + 512 > 227 * 1024)
+      --a.stages;
   } else {
     // N tiling: equal tiles of at most 256 columns, multiples of 16
     const int co16 = tdr_cdiv(d->Co, 16) * 16;
     a.n_tiles = tdr_cdiv(co16, 256);
     a.BN = tdr_cdiv(tdr_cdiv(co16, a.n_tiles), 16) * 16;
+    a.epi_bufs = 1;
+    a.stages = 4;
   }
   a.kchunks = tdr_cdiv(d->Ci, kChunkK);
   a.total_tiles = d->B * a.tiles_y * a.tiles_x * a.n_tiles;
@@ -520,17 +634,25 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   }
 
   TDR_CHECK_ARG(a.TW * d->stride <= 256 && a.TH * d->stride <= 256, "tdr_conv_gemm: TMA box too large");
-  TdrTensorMap map_a, map_w, map_o;
+  TdrTensorMap map_a, map_w, map_o, map_r2, map_r1;
   memset(&map_o, 0, sizeof(map_o));
+  memset(&map_r2, 0, sizeof(map_r2));
+  memset(&map_r1, 0, sizeof(map_r1));
   if (a.epi_mode == 1) {
     const int box_w = a.TW < 32 ? a.TW : 32;
+    const int esz = a.out_is_f32 ? 4 : 2;
     const uint64_t dims[4] = {(uint64_t)d->Co, (uint64_t)OW, (uint64_t)OH, (uint64_t)d->B};
-    const uint64_t strides[3] = {(uint64_t)d->out_bf16_ld * 2, (uint64_t)d->out_bf16_ld * 2 * OW,
-                                 (uint64_t)d->out_bf16_ld * 2 * OW * OH};
-    const uint32_t box[4] = {64, (uint32_t)box_w, (uint32_t)(32 / box_w), 1};
+    const uint32_t box[4] = {(uint32_t)(128 / esz), (uint32_t)box_w, (uint32_t)(32 / box_w), 1};
     const uint32_t es[4] = {1, 1, 1, 1};
-    int rc = tdr_make_tensor_map_bf16(&map_o, d->out_bf16, 4, dims, strides, box, es);
+    auto mk = [&](TdrTensorMap* m, const void* ptr, long long ld) {
+      const uint64_t strides[3] = {(uint64_t)ld * esz, (uint64_t)ld * esz * OW, (uint64_t)ld * esz * OW * OH};
+      return a.out_is_f32 ? tdr_make_tensor_map_f32(m, ptr, 4, dims, strides, box, es)
+                          : tdr_make_tensor_map_bf16(m, ptr, 4, dims, strides, box, es);
+    };
+    int rc = a.out_is_f32 ? mk(&map_o, d->out_f32, d->out_f32_ld) : mk(&map_o, d->out_bf16, d->out_bf16_ld);
     if (rc) return rc;
+    if (d->res2 && (rc = mk(&map_r2, d->res2, d->res2_ld))) return rc;
+    if (d->res1 && (rc = mk(&map_r1, d->res1, d->res1_ld))) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)d->Ci, (uint64_t)img_w, (uint64_t)img_h, (uint64_t)n_img};
@@ -550,14 +672,29 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     int rc = tdr_make_tensor_map_bf16(&map_w, d->weight, 3, dims, strides, box, es);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + (size_t)kStages * (kABytes + a.BN * kChunkK * 2) + kEpiWarps * kEpiStageBytes + 256;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  const size_t smem = 1024 + (size_t)a.stages * (kABytes + a.BN * kChunkK * 2) +
+                      (size_t)kEpiWarps * a.epi_bufs * kEpiStageBytes + 512;
   const int grid = a.total_tiles < tdr_num_sms() ? a.total_tiles : tdr_num_sms();
-  conv_gemm_kernel<<<grid, kThreads, smem, stream>>>(map_a, map_w, map_o, a);
+  const int variant = a.epi_mode == 1 ? (a.out_is_f32 | (d->res2 ? 2 : 0) | (d->res1 ? 4 : 0)) : -1;
+#define TDR_LAUNCH_CONV(VV)                                                                                        \
+  do {                                                                                                             \
+    static bool attr_set = false;                                                                                  \
+    if (!attr_set) {                                                                                               \
+      TDR_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<VV>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                          227 * 1024));                                                            \
+      attr_set = true;                                                                                             \
+    }                                                                                                              \
+    conv_gemm_kernel<VV><<<grid, kThreads, smem, stream>>>(map_a, map_w, map_o, map_r2, map_r1, a);                \
+  } while (0)
+  switch (variant) {
+    case 0: TDR_LAUNCH_CONV(0); break;
+    case 1: TDR_LAUNCH_CONV(1); break;
+    case 2: TDR_LAUNCH_CONV(2); break;
+    case 3: TDR_LAUNCH_CONV(3); break;
+    case 7: TDR_LAUNCH_CONV(7); break;
+    default: TDR_LAUNCH_CONV(-1); break;
+  }
+#undef TDR_LAUNCH_CONV
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

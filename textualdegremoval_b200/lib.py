@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libtdr_sm100.so")
+LIB_PATH = os.environ.get("TDR_LIB_PATH") or os.path.join(_PKG, "libtdr_sm100.so")
 
 
 class TdrError(RuntimeError):

@@ -59,6 +59,8 @@ PROBES = {
     "qkv96": lambda: conv(4, 512, 512, 96, 288),
     "pout256": lambda: conv(4, 512, 512, 256, 96, want="f32", res=True),
     "qkv48": lambda: conv(4, 512, 512, 48, 144),
+    "pout96wb": lambda: conv(4, 512, 512, 96, 96, want="f32", res=True),
+    "pout128": lambda: conv(4, 512, 512, 128, 48, want="f32", res=True),
     "pin192": lambda: conv(4, 128, 128, 192, 1024),
     "c3x3_48": lambda: conv(8, 512, 512, 48, 48, k=3, relu=True),
     "c3x3_96": lambda: conv(8, 256, 256, 96, 96, k=3, relu=True),
@@ -74,6 +76,14 @@ PROBES = {
 def main():
     names = sys.argv[1:] or list(PROBES)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    # box calibration: plain device copy bandwidth (read + write bytes)
+    a = torch.empty(1 << 29, dtype=torch.bfloat16, device=DEV); b_ = torch.empty_like(a)
+    for _ in range(2):
+        b_.copy_(a)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(); b_.copy_(a); e.record(); torch.cuda.synchronize()
+    print(f"[box] copy bandwidth {2 * a.numel() * 2 / s.elapsed_time(e) / 1e6:.0f} GB/s", flush=True)
+    del a, b_
     for n in names:
         fn, nbytes, flops = PROBES[n]()
         for _ in range(3):
