@@ -126,8 +126,10 @@ int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, c
  * ------------------------------------------------------------------------------------------------------------- */
 int tdr_nchw_to_nhwc(const float* src, int B, int C, int H, int W, int pad_h, int pad_w /* zero-padded output size */,
                      float* dst_f32, long long dst_f32_ld, void* dst_bf16, long long dst_bf16_ld, cudaStream_t stream);
+/* dst[b,c,y,x] = src[b,y,x,c] (+ res[b,y,x,c], e.g. the `+ inp_img` of R:499,962), cropped to out_h x out_w. */
 int tdr_nhwc_to_nchw(const float* src, long long src_ld, int B, int C, int H, int W /* source size */, int out_h,
-                     int out_w /* crop */, float* dst, cudaStream_t stream);
+                     int out_w /* crop */, const float* res /* NHWC fp32 or NULL */, long long res_ld, float* dst,
+                     cudaStream_t stream);
 /* dst[r, 0:C] = src[r, 0:C] (fp32 rows with independent strides); optionally also writes a bf16 copy. */
 int tdr_copy_rows_f32(const float* src, long long src_ld, long long rows, int C, float* dst, long long dst_ld,
                       void* dst_bf16, long long dst_bf16_ld, cudaStream_t stream);

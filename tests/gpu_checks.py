@@ -72,6 +72,10 @@ def check_layout():
     out.append(result("nchw_to_nhwc_pad", y, ref, 0.0))
     z = ops.nhwc_to_nchw(y, 20, 28)
     out.append(result("nhwc_to_nchw_crop", z, x, 0.0))
+    wide = torch.zeros(2, 24, 32, 8, device=DEV)
+    wide[..., :3] = y
+    z = ops.nhwc_to_nchw(wide[..., :3], 20, 28, res=y)
+    out.append(result("nhwc_to_nchw_slice_res", z, 2 * x, 0.0))
     src = rnd(1, 6, 10, 48, seed=2).to(DEV)                      # NHWC
     dst = torch.zeros(1, 6, 10, 96, device=DEV)
     d16 = torch.zeros(1, 6, 10, 96, device=DEV, dtype=BF16)

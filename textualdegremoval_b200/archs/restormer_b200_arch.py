@@ -255,7 +255,12 @@ class _RestormerBase(nn.Module):
         for name in ["reduce_chan_level3", "reduce_chan_level2"]:
             P[name] = _prep_conv(getattr(self, name))
         P["patch_embed"] = dict(w=_f(self.patch_embed.proj.weight), b=_f(self.patch_embed.proj.bias))
-        P["output"] = dict(w=_f(self.output.weight), b=_f(self.output.bias))
+        # output conv (:640): 3 (or 1) output channels are zero-padded to 8 so that it runs on the tensor-core path
+        ow = self.output.weight
+        co = ow.shape[0]
+        w8 = torch.zeros(8, ow.shape[1], 3, 3, dtype=ow.dtype, device=ow.device)
+        w8[:co] = ow.detach()
+        P["output"] = dict(w=ops.pack_conv_weight(w8), b=ops.pad_vec(self.output.bias, 8), Co=co)
         if self.dual_pixel_task:
             P["skip_conv"] = _prep_conv(self.skip_conv)
         return P
@@ -271,7 +276,7 @@ class _RestormerBase(nn.Module):
         x16 = ops.rownorm(x32, 0)
         ops.conv_gemm(x16, pc["w"], pc["Co"], k=3, pad=1, out_f32=out32, store_mode=1)
 
-    def _decode(self, P, lat, e1, e2, e3, inp32, x_in1):
+    def _decode(self, P, lat, e1, e2, e3, x_in1):
         """Decoder half (:477-501).  e*: fp32 NHWC views of the encoder outputs."""
         d = self.dims
         B, H8, W8, _ = lat.shape
@@ -297,8 +302,8 @@ class _RestormerBase(nn.Module):
         run_stack(d1, P["refinement"])
         if self.dual_pixel_task:      # :494-496  out = output(d1 + skip_conv(inp_enc_level1))
             ops.conv_gemm(ops.rownorm(x_in1, 0), P["skip_conv"]["w"], d[1], bias=P["skip_conv"]["b"], res2=d1, out_f32=d1)
-            return ops.conv3x3_small_co(ops.rownorm(d1, 0), P["output"]["w"], P["output"]["b"], None)
-        return ops.conv3x3_small_co(ops.rownorm(d1, 0), P["output"]["w"], P["output"]["b"], inp32)
+        o8, _ = ops.conv_gemm(ops.rownorm(d1, 0), P["output"]["w"], 8, k=3, pad=1, bias=P["output"]["b"], want="f32")
+        return o8[..., :P["output"]["Co"]]
 
 
 class Restormer(_RestormerBase):
@@ -335,8 +340,8 @@ class Restormer(_RestormerBase):
         lat = torch.empty((B, H // 8, W // 8, d[3]), dtype=F32, device=dev)
         self._down(e3, P["down3_4"], lat)
         run_stack(lat, P["latent"])
-        out = self._decode(P, lat, e1, e2, e3, inp32 if not self.dual_pixel_task else None, x_in1)
-        return ops.nhwc_to_nchw(out, H, W)
+        out = self._decode(P, lat, e1, e2, e3, x_in1)
+        return ops.nhwc_to_nchw(out, H, W, res=None if self.dual_pixel_task else inp32)     # + inp_img (:499)
 
 
 class RestormerRefFusion(_RestormerBase):
@@ -462,6 +467,6 @@ class RestormerRefFusion(_RestormerBase):
             x = fbuf[i][..., :d[i]]
             run_stack(x, P[enc_names[i]])
             xs.append(x)
-        out = self._decode(P, xs[3], xs[0], xs[1], xs[2], lq32, None)
-        out = ops.nhwc_to_nchw(out, oh, ow)
+        out = self._decode(P, xs[3], xs[0], xs[1], xs[2], None)
+        out = ops.nhwc_to_nchw(out, oh, ow, res=lq32)                                       # + inp_img (:962)
         return (out, aux) if return_aux else out

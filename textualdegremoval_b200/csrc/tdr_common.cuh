@@ -218,6 +218,9 @@ struct TdrTensorMap {
 };
 int tdr_make_tensor_map_bf16(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+// bf16, SWIZZLE_NONE (plain row-major box in shared memory)
+int tdr_make_tensor_map_bf16_noswizzle(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 // same for fp32 data (box inner dim <= 32 elements = 128 B)
 int tdr_make_tensor_map_f32(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
                             const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);

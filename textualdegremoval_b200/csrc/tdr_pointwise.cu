@@ -1,6 +1,8 @@
 // HBM-bound row/stencil kernels on NHWC activations: channel LayerNorm / cast, depthwise 3x3 (+ GDFN / SimpleGate
 // gating), image-boundary layout changes, slice copies, and the two small-channel direct convolutions at the image
 // boundary.  All access is 128-bit vectorised along the channel (innermost) dimension; reductions use warp shuffles.
+#include <stdlib.h>
+
 #include "tdr_common.cuh"
 
 namespace {
@@ -254,6 +256,150 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_strip_kernel(const bf16* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------ depthwise 3x3, TMA
+// Persistent CTAs (2 per SM) stream haloed tiles [10 rows x 34 px x 64 ch] (ungated) or 2 x [10 x 34 x 32 ch] (the two
+// GDFN halves) through a double-buffered TMA pipeline: the bytes in flight no longer depend on registers or occupancy,
+// the conv padding is the TMA out-of-bounds zero fill, and each thread reads its 3-pixel neighbourhood from shared
+// memory with conflict-free 128-bit (64-bit) loads while walking down 8 output rows with the same register sliding
+// window as the strip kernel.
+constexpr int kDwRows = 8, kDwCols = 32;
+constexpr int kDwBoxBytes = (kDwRows + 2) * (kDwCols + 2) * 64 * 2;      // 43520
+constexpr int kDwStageBytes = 43776;                                      // rounded to 256 B
+
+struct DwArgs {
+  int B, H, W, C, Cout;
+  int tiles_x, tiles_y, chunks, total_tiles;
+  const float* wt;
+  const float* bias;
+  int gate;
+  bf16* out;
+  long long out_ld;
+};
+
+template <int GATE>
+__global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_constant__ TdrTensorMap map, const DwArgs a) {
+  constexpr int NH = GATE ? 2 : 1;
+  constexpr int VEC = GATE ? 4 : 8;
+  constexpr int NP = VEC / 2;
+  constexpr int CB = GATE ? 32 : 64;                       // channels per box (= output channels per tile)
+  constexpr int PIX_PITCH = CB * 2;                        // bytes per pixel in the staged tile
+  constexpr int BOX_BYTES = (kDwRows + 2) * (kDwCols + 2) * PIX_PITCH;
+  typedef typename RawT<VEC>::type raw_t;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ __align__(8) uint64_t full[2];
+  const int tid = threadIdx.x;
+  const int cgi = tid & 7, xl = tid >> 3;                  // channel vector within the chunk, x within the tile
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // CTA -> (channel chunk, spatial group): the chunk is fixed for the CTA's lifetime (taps stay in registers) and the
+  // CTAs running concurrently cover ALL chunks of neighbouring spatial tiles, so whole pixel rows are touched together.
+  const int cc = blockIdx.x % a.chunks;
+  const int grp = blockIdx.x / a.chunks, ngrp = gridDim.x / a.chunks;
+  const int n_spatial = a.B * a.tiles_y * a.tiles_x;
+  auto issue = [&](int sp, int stage) {                    // thread 0 only
+    int r = sp;
+    const int b = r / (a.tiles_y * a.tiles_x);
+    r %= a.tiles_y * a.tiles_x;
+    const int y0 = (r / a.tiles_x) * kDwRows, x0 = (r % a.tiles_x) * kDwCols;
+    uint8_t* dst = dsm + stage * kDwStageBytes;
+    mbar_expect_tx(&full[stage], NH * BOX_BYTES);
+#pragma unroll
+    for (int h = 0; h < NH; ++h)
+      tma_load_4d(dst + h * BOX_BYTES, &map, &full[stage], h * a.Cout + cc * CB, x0 - 1, y0 - 1, b);
+  };
+
+  f2 w[NH][9][NP];
+  f2 bv[NH][NP];
+  const int c0 = cc * CB + cgi * VEC;                      // channel within a half
+  const bool c_ok = c0 < a.Cout;
+  {
+#pragma unroll
+      for (int h = 0; h < NH; ++h) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+          for (int e = 0; e < NP; e += 2) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c_ok) v = __ldg(reinterpret_cast<const float4*>(a.wt + (size_t)t * a.C + h * a.Cout + c0 + 2 * e));
+            w[h][t][e] = pk2(v.x, v.y);
+            w[h][t][e + 1] = pk2(v.z, v.w);
+          }
+#pragma unroll
+        for (int e = 0; e < NP; ++e)
+          bv[h][e] = (a.bias && c_ok) ? pk2(a.bias[h * a.Cout + c0 + 2 * e], a.bias[h * a.Cout + c0 + 2 * e + 1])
+                                      : pk2(0.f, 0.f);
+      }
+  }
+  int it = 0;
+  if (tid == 0 && grp < n_spatial) issue(grp, 0);
+  for (int sp = grp; sp < n_spatial; sp += ngrp, ++it) {
+    const int stage = it & 1;
+    if (tid == 0 && sp + ngrp < n_spatial) issue(sp + ngrp, stage ^ 1);
+    int r = sp;
+    const int b = r / (a.tiles_y * a.tiles_x);
+    r %= a.tiles_y * a.tiles_x;
+    const int y0 = (r / a.tiles_x) * kDwRows, x0 = (r % a.tiles_x) * kDwCols;
+    mbar_wait(&full[stage], (it >> 1) & 1);
+    const uint8_t* tile_s = dsm + stage * kDwStageBytes + xl * PIX_PITCH + cgi * (VEC * 2);
+    f2 acc[3][NH][NP];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+#pragma unroll
+        for (int e = 0; e < NP; ++e) acc[k][h][e] = bv[h][e];
+    const int x = x0 + xl;
+    bf16* outp = a.out + (((long long)b * a.H + y0) * a.W + x) * a.out_ld + c0;
+    const bool st_ok = c_ok && x < a.W;
+#pragma unroll
+    for (int i = 0; i < kDwRows + 2; ++i) {                // staged row i = input row y0 - 1 + i
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const raw_t rv = *reinterpret_cast<const raw_t*>(tile_s + h * BOX_BYTES +
+                                                           (i * (kDwCols + 2) + kx) * PIX_PITCH);
+          const uint32_t* u = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+          for (int e = 0; e < NP; ++e) {
+            const f2 v = bf2_to_f2(u[e]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              acc[(i + k) % 3][h][e] = fma2(w[h][(2 - k) * 3 + kx][e], v, acc[(i + k) % 3][h][e]);
+          }
+        }
+      if (i >= 2) {                                        // output row y0 + i - 2 (slot i % 3) is complete
+        if (st_ok && y0 + i - 2 < a.H) {
+          raw_t o;
+          uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+          for (int e = 0; e < NP; ++e) {
+            f2 val = acc[i % 3][0][e];
+            if (GATE) val = mul2(a.gate == 1 ? gelu2(val) : val, acc[i % 3][NH - 1][e]);
+            float a0, a1;
+            upk2(val, a0, a1);
+            ou[e] = pack2(a0, a1);
+          }
+          *reinterpret_cast<raw_t*>(outp) = o;
+        }
+        outp += (long long)a.W * a.out_ld;
+      }
+#pragma unroll
+      for (int h = 0; h < NH; ++h)
+#pragma unroll
+        for (int e = 0; e < NP; ++e) acc[i % 3][h][e] = bv[h][e];
+    }
+    __syncthreads();                                       // everyone is done with this stage before it is refilled
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ layout
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int B, int C, int H, int W, int PH, int PW,
                                     float* __restrict__ d32, long long ld32, bf16* __restrict__ d16, long long ld16) {
@@ -272,7 +418,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int B, int C,
 }
 
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, long long ld, int B, int C, int H, int W, int OH,
-                                    int OW, float* __restrict__ dst) {
+                                    int OW, const float* __restrict__ res, long long res_ld,
+                                    float* __restrict__ dst) {
   const long long total = (long long)B * C * OH * OW;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -280,7 +427,8 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, long long ld,
     const int y = (int)((i / OW) % OH);
     const int c = (int)((i / ((long long)OW * OH)) % C);
     const int b = (int)(i / ((long long)OW * OH * C));
-    dst[i] = src[(((long long)b * H + y) * W + x) * ld + c];
+    const long long p = ((long long)b * H + y) * W + x;
+    dst[i] = src[p * ld + c] + (res ? res[p * res_ld + c] : 0.f);
   }
 }
 
@@ -451,19 +599,52 @@ extern "C" int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H,
   TDR_CHECK_ARG(C % 8 == 0, "tdr_dwconv3x3: C must be a multiple of 8");
   TDR_CHECK_ARG(in_ld % 8 == 0 && out_ld % 4 == 0, "tdr_dwconv3x3: bad strides");
   TDR_CHECK_ARG(((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)out_bf16 & 7) == 0, "tdr_dwconv3x3: alignment");
-  constexpr int R = 16;
+  if (!gate) TDR_CHECK_ARG(out_ld % 8 == 0 && ((uintptr_t)out_bf16 & 15) == 0, "tdr_dwconv3x3: output alignment");
   const bf16* in = reinterpret_cast<const bf16*>(in_bf16);
   bf16* out = reinterpret_cast<bf16*>(out_bf16);
-  if (gate) {
-    const int items = W * (C / 2 / 4);
-    dim3 grid((items + 255) / 256, (H + R - 1) / R, B);
-    dwconv3x3_strip_kernel<2, 4, R><<<grid, 256, 0, stream>>>(in, in_ld, H, W, C, weight, bias, gate, out, out_ld);
-  } else {
-    TDR_CHECK_ARG(out_ld % 8 == 0 && ((uintptr_t)out_bf16 & 15) == 0, "tdr_dwconv3x3: output alignment");
-    const int items = W * (C / 8);
-    dim3 grid((items + 255) / 256, (H + R - 1) / R, B);
-    dwconv3x3_strip_kernel<1, 8, R><<<grid, 256, 0, stream>>>(in, in_ld, H, W, C, weight, bias, gate, out, out_ld);
+  static const bool use_strip = getenv("TDR_DWCONV_STRIP") != nullptr;     // previous (non-TMA) kernel, experiments only
+  if (use_strip) {
+    constexpr int R = 16;
+    if (gate) {
+      const int items = W * (C / 2 / 4);
+      dim3 grid((items + 255) / 256, (H + R - 1) / R, B);
+      dwconv3x3_strip_kernel<2, 4, R><<<grid, 256, 0, stream>>>(in, in_ld, H, W, C, weight, bias, gate, out, out_ld);
+    } else {
+      const int items = W * (C / 8);
+      dim3 grid((items + 255) / 256, (H + R - 1) / R, B);
+      dwconv3x3_strip_kernel<1, 8, R><<<grid, 256, 0, stream>>>(in, in_ld, H, W, C, weight, bias, gate, out, out_ld);
+    }
+    TDR_CHECK_LAUNCH();
+    return TDR_OK;
   }
+  DwArgs a;
+  a.B = B; a.H = H; a.W = W; a.C = C; a.Cout = gate ? C / 2 : C;
+  a.tiles_x = tdr_cdiv(W, kDwCols); a.tiles_y = tdr_cdiv(H, kDwRows);
+  const int cb = gate ? 32 : 64;
+  a.chunks = tdr_cdiv(a.Cout, cb);
+  a.total_tiles = B * a.tiles_x * a.tiles_y * a.chunks;
+  a.wt = weight; a.bias = bias; a.gate = gate; a.out = out; a.out_ld = out_ld;
+  TdrTensorMap map;
+  const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  const uint64_t strides[3] = {(uint64_t)in_ld * 2, (uint64_t)in_ld * 2 * W, (uint64_t)in_ld * 2 * W * H};
+  const uint32_t box[4] = {(uint32_t)cb, (uint32_t)(kDwCols + 2), (uint32_t)(kDwRows + 2), 1};
+  const uint32_t es[4] = {1, 1, 1, 1};
+  int rc = tdr_make_tensor_map_bf16_noswizzle(&map, in, 4, dims, strides, box, es);   // L2 promotion 128 B
+  if (rc) return rc;
+  const int n_spatial = B * a.tiles_x * a.tiles_y;
+  int groups = (2 * tdr_num_sms()) / a.chunks;
+  if (groups < 1) groups = 1;
+  if (groups > n_spatial) groups = n_spatial;
+  const int grid = groups * a.chunks;
+  const size_t smem = 2 * kDwStageBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  if (gate) dwconv3x3_tma_kernel<1><<<grid, 256, smem, stream>>>(map, a);
+  else dwconv3x3_tma_kernel<0><<<grid, 256, smem, stream>>>(map, a);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
@@ -480,10 +661,11 @@ extern "C" int tdr_nchw_to_nhwc(const float* src, int B, int C, int H, int W, in
 }
 
 extern "C" int tdr_nhwc_to_nchw(const float* src, long long src_ld, int B, int C, int H, int W, int out_h, int out_w,
-                                float* dst, cudaStream_t stream) {
+                                const float* res, long long res_ld, float* dst, cudaStream_t stream) {
   TDR_CHECK_ARG(src && dst && out_h <= H && out_w <= W && out_h > 0 && out_w > 0, "tdr_nhwc_to_nchw: bad arguments");
   const long long total = (long long)B * C * out_h * out_w;
-  nhwc_to_nchw_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(src, src_ld, B, C, H, W, out_h, out_w, dst);
+  nhwc_to_nchw_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(src, src_ld, B, C, H, W, out_h, out_w, res, res_ld,
+                                                                    dst);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

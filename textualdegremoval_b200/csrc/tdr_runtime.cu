@@ -60,7 +60,14 @@ static PFN_encodeTiled get_encode() {
 }
 
 static int make_map(TdrTensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B);
+
+int tdr_make_tensor_map_bf16_noswizzle(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                       const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  return make_map(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, elem_strides,
+                  CU_TENSOR_MAP_SWIZZLE_NONE);
+}
 
 int tdr_make_tensor_map_bf16(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
@@ -72,7 +79,8 @@ int tdr_make_tensor_map_f32(TdrTensorMap* out, const void* base, int rank, const
 }
 
 static int make_map(TdrTensorMap* out, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+                    const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides,
+                    CUtensorMapSwizzle sw) {
   static_assert(sizeof(CUtensorMap) == sizeof(TdrTensorMap), "tensor map size");
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
@@ -89,7 +97,8 @@ static int make_map(TdrTensorMap* out, CUtensorMapDataType dt, const void* base,
   }
   CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), dt, (cuuint32_t)rank,
                    const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   sw, sw == CU_TENSOR_MAP_SWIZZLE_NONE ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     tdr_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] stride0 %llu box [%u %u %u %u]",
                   (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),

@@ -53,7 +53,7 @@ SIGNATURES = {
     "tdr_mdta_gram": (_i, [_vp, _ll, _i, _ll, _i, _i, _vp, _vp]),
     "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp]),
     "tdr_nchw_to_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),
-    "tdr_nhwc_to_nchw": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tdr_nhwc_to_nchw": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _vp]),
     "tdr_copy_rows_f32": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_sqnorm_rows": (_i, [_vp, _ll, _ll, _i, _vp, _vp]),
     "tdr_masa_ref_invnorm": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _i, _vp, _vp]),

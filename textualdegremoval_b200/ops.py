@@ -237,10 +237,14 @@ def nchw_to_nhwc(x, pad_h, pad_w, want_bf16=False):
     return (o32, o16) if want_bf16 else o32
 
 
-def nhwc_to_nchw(x32, out_h, out_w):
+def nhwc_to_nchw(x32, out_h, out_w, res=None):
+    """NHWC fp32 view -> dense NCHW (cropped); optionally adds an NHWC fp32 residual with the same channel count."""
     B, H, W, Cc = x32.shape
     out = torch.empty((B, Cc, out_h, out_w), dtype=F32, device=x32.device)
-    _call("tdr_nhwc_to_nchw", _p(x32), _ld(x32), B, Cc, H, W, out_h, out_w, _p(out), _stream())
+    if res is not None:
+        assert res.shape == x32.shape and res.dtype == F32
+    _call("tdr_nhwc_to_nchw", _p(x32), _ld(x32), B, Cc, H, W, out_h, out_w, _p(res), _ld(res) if res is not None else 0,
+          _p(out), _stream())
     return out
 
 
