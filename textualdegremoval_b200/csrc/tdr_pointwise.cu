@@ -573,8 +573,10 @@ extern "C" int tdr_rownorm(const float* in, long long in_ld, long long rows, int
   TDR_CHECK_ARG(C <= 4096, "tdr_rownorm: C too large (%d)", C);
   if (rows == 0) return TDR_OK;
   const int nvec = C / 4;
+  // G lanes per row: the smallest power of two that keeps <= 4 float4 per lane (all lanes busy, short shuffle trees,
+  // 32/G rows per warp); very wide rows fall back to a full warp per row.
   int G = 1;
-  while (G < 32 && G < nvec) G <<= 1;
+  while (G < 32 && (nvec + G - 1) / G > 4) G <<= 1;
   const int nv = (nvec + G - 1) / G;
   const long long warps = (rows + (32 / G) - 1) / (32 / G);
   const int blocks = (int)((warps + 7) / 8);
@@ -582,6 +584,7 @@ extern "C" int tdr_rownorm(const float* in, long long in_ld, long long rows, int
 #define TDR_RN(NV) rownorm_kernel<NV><<<blocks, 256, 0, stream>>>(in, in_ld, rows, C, mode, weight, bias, eps, o, out_ld, G)
   if (nv <= 1) TDR_RN(1);
   else if (nv <= 2) TDR_RN(2);
+  else if (nv <= 3) TDR_RN(3);
   else if (nv <= 4) TDR_RN(4);
   else if (nv <= 8) TDR_RN(8);
   else if (nv <= 16) TDR_RN(16);
