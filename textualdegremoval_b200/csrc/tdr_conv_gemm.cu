@@ -57,7 +57,11 @@ struct ConvGemmArgs {
   int store_mode;               // 0 plain, 1 pixel-unshuffle(2), 2 pixel-shuffle(2)
   int epi_mode;                 // 0 generic staged stores; 1 TMA epilogue (single-dtype output, residuals via TMA)
   int out_is_f32;               // epi_mode 1: output (and res2) element type
-  int stages;                   // smem pipeline depth (3 or 4)
+  int halo;                     // 1: stride-1 KxK conv whose weights fit in shared memory: they are loaded ONCE per CTA,
+                                //    and ONE haloed A tile per channel chunk is streamed; taps are descriptor offsets
+                                //    into it (A is fetched once instead of KH*KW times, B never again)
+  int halo_bytes;               // bytes of one haloed A tile: (TH + (KH-1)*dil) rows x 16 px x 128 B
+  int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
   int epi_bufs;                 // staging buffers per epilogue warp (1 or 2)
 };
 
@@ -76,15 +80,18 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
   const int b_bytes = a.BN * kChunkK * 2;
   uint8_t* smem_a = smem;
   const int kStages = a.stages;
-  uint8_t* smem_b = smem + kStages * kABytes;
-  uint8_t* smem_epi = smem_b + kStages * b_bytes;              // kEpiWarps x epi_bufs x 4 KiB staging tiles
+  const int a_ring_bytes = a.halo ? kStages * a.halo_bytes : kStages * kABytes;
+  uint8_t* smem_b = smem + a_ring_bytes;
+  const int b_ring_bytes = a.halo ? a.KH * a.KW * a.kchunks * b_bytes : kStages * b_bytes;
+  uint8_t* smem_epi = smem_b + b_ring_bytes;                   // kEpiWarps x epi_bufs x 4 KiB staging tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiWarps * a.epi_bufs * kEpiStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
   uint64_t* tfull = bars + 2 * kMaxStages;
   uint64_t* tempty = bars + 2 * kMaxStages + 2;
   uint64_t* rbar = bars + 2 * kMaxStages + 4;                  // [kEpiWarps][2] residual-tile barriers
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4 + 2 * kEpiWarps);
+  uint64_t* wfull = rbar + 2 * kEpiWarps;                      // halo mode: resident weights have landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,6 +109,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&rbar[i], 1);
+    mbar_init(wfull, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpiWarps);
@@ -123,6 +131,12 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (a.halo) {                            // resident weights: every (chunk, tap) slice once, one barrier
+        mbar_expect_tx(wfull, (uint32_t)(taps * a.kchunks * b_bytes));
+        for (int kc = 0; kc < a.kchunks; ++kc)
+          for (int tap = 0; tap < taps; ++tap)
+            tma_load_3d(smem_b + (kc * taps + tap) * b_bytes, &map_w, wfull, kc * kChunkK, 0, tap);
+      }
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int nt = tile % a.n_tiles;
         const int mt = tile / a.n_tiles;
@@ -132,6 +146,16 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         const int ox0 = (r % a.tiles_x) * a.TW;
         int img = b, org_y = 0, org_x = 0;
         if (a.origin) { img = a.origin[3 * b]; org_y = a.origin[3 * b + 1]; org_x = a.origin[3 * b + 2]; }
+        if (a.halo) {
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], a.halo_bytes);
+            tma_load_4d(smem_a + stage * a.halo_bytes, &map_a, &full[stage], kc * kChunkK, org_x + ox0 - a.pad,
+                        org_y + oy0 - a.pad, img);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int ks = 0; ks < ksteps; ++ks) {
           const int tap = ks / a.kchunks;
           const int kc = ks % a.kchunks;
@@ -158,6 +182,35 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       mbar_wait(&tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * a.BN;
+      if (a.halo) {
+        if (it == 0) mbar_wait(wfull, 0);
+        for (int kc = 0; kc < a.kchunks; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (lane == 0) {
+            for (int tap = 0; tap < taps; ++tap) {
+              // tap (ky, kx) = the same haloed tile shifted by (ky*dil) rows of 16 px and (kx*dil) px; every 8-pixel
+              // UMMA row group is one image-row segment, groups are 2048 B apart (16-px row pitch).  The 128 B
+              // swizzle is a function of the absolute smem address, so 128 B-aligned shifted starts need no fix-up
+              // (verified on device: descriptor base-offset must stay 0).
+              const uint32_t sa_addr = smem_u32(smem_a + stage * a.halo_bytes) +
+                                       (((tap / a.KW) * a.dil * 16 + (tap % a.KW) * a.dil) << 7);
+              const uint32_t sb = smem_u32(smem_b + (kc * taps + tap) * b_bytes);
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k) {
+                const uint64_t da = umma_desc_sw128(sa_addr + k * 32, 0, 2048);
+                const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
+                umma_bf16(d_tmem, da, db, idesc, (kc | tap | k) != 0);
+              }
+            }
+            umma_commit(&empty[stage]);
+            if (kc == a.kchunks - 1) umma_commit(&tfull[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
@@ -570,6 +623,9 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   a.TW = OW >= 16 ? 16 : 8;
   a.TH = kTileM / a.TW;
   if (OH == 1) { a.TW = 128; a.TH = 1; }         // flat [rows, C] GEMM view
+  // halo mode: stride-1 multi-tap convs fetch one haloed [TH+(KH-1)dil] x 16 px tile per channel chunk
+  a.halo = 0;                                    // decided below, once the N tiling is known
+  a.halo_bytes = 0;
   a.tiles_x = tdr_cdiv(OW, a.TW);
   a.tiles_y = tdr_cdiv(OH, a.TH);
   {
@@ -607,9 +663,6 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
       const int v = atoi(e);
       if (v >= 2 && v <= 4) a.stages = v;
     }
-    while (a.stages > 2 && 1024 + (size_t)a.stages * (kABytes + a.BN * kChunkK * 2) +
-                                   (size_t)kEpiWarps * a.epi_bufs * kEpiStageBytes + 512 > 227 * 1024)
-      --a.stages;
   } else {
     // N tiling: equal tiles of at most 256 columns, multiples of 16
     const int co16 = tdr_cdiv(d->Co, 16) * 16;
@@ -619,6 +672,34 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     a.stages = 4;
   }
   a.kchunks = tdr_cdiv(d->Ci, kChunkK);
+  auto smem_need = [&]() {
+    const size_t ring = a.halo ? (size_t)a.stages * a.halo_bytes + (size_t)d->KH * d->KW * a.kchunks * a.BN * kChunkK * 2
+                               : (size_t)a.stages * (kABytes + a.BN * kChunkK * 2);
+    return 1024 + ring + (size_t)kEpiWarps * a.epi_bufs * kEpiStageBytes + 512;
+  };
+  // Halo mode: stride-1 multi-tap conv, shared (not per-sample) weights that fit in shared memory next to a 3-deep
+  // ring of haloed [TH + (KH-1)dil] x 16 px A tiles, a single N tile.  TW = 8 so that every 8-row UMMA group is one
+  // image-row segment of the haloed tile.
+  if (d->impl == 0 && d->stride == 1 && d->KH * d->KW > 1 && (d->KW - 1) * d->dil <= 8 && OH > 1 && !d->w_batched &&
+      a.n_tiles == 1 && getenv("TDR_CONV_NO_HALO") == nullptr) {
+    const int halo_bytes = (16 + (d->KH - 1) * d->dil) * 16 * 128;
+    const size_t need = 1024 + (size_t)3 * halo_bytes + (size_t)d->KH * d->KW * a.kchunks * a.BN * kChunkK * 2 +
+                        (size_t)kEpiWarps * kEpiStageBytes + 512;
+    if (need <= 227 * 1024) {
+      a.halo = 1;
+      a.halo_bytes = halo_bytes;
+      a.TW = 8; a.TH = 16;
+      a.tiles_x = tdr_cdiv(OW, a.TW); a.tiles_y = tdr_cdiv(OH, a.TH);
+      a.stages = 3;
+      a.epi_bufs = d->res1 ? 2 : 1;
+    }
+  }
+  while (smem_need() > 227 * 1024) {
+    if (a.epi_bufs == 2 && !d->res1) a.epi_bufs = 1;
+    else if (a.stages > 2) --a.stages;
+    else break;
+  }
+  TDR_CHECK_ARG(smem_need() <= 227 * 1024, "tdr_conv_gemm: shared-memory plan does not fit");
   a.total_tiles = d->B * a.tiles_y * a.tiles_x * a.n_tiles;
   uint32_t cols = 32;
   while (cols < (uint32_t)(2 * a.BN)) cols <<= 1;
@@ -658,7 +739,8 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     const uint64_t dims[4] = {(uint64_t)d->Ci, (uint64_t)img_w, (uint64_t)img_h, (uint64_t)n_img};
     const uint64_t strides[3] = {(uint64_t)d->in_ld * 2, (uint64_t)d->in_ld * 2 * img_w,
                                  (uint64_t)d->in_ld * 2 * img_w * img_h};
-    const uint32_t box[4] = {(uint32_t)kChunkK, (uint32_t)(a.TW * d->stride), (uint32_t)(a.TH * d->stride), 1};
+    uint32_t box[4] = {(uint32_t)kChunkK, (uint32_t)(a.TW * d->stride), (uint32_t)(a.TH * d->stride), 1};
+    if (a.halo) { box[1] = 16; box[2] = (uint32_t)(a.TH + (d->KH - 1) * d->dil); }
     const uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
     int rc = tdr_make_tensor_map_bf16(&map_a, d->in, 4, dims, strides, box, es);
     if (rc) return rc;
@@ -672,8 +754,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     int rc = tdr_make_tensor_map_bf16(&map_w, d->weight, 3, dims, strides, box, es);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + (size_t)a.stages * (kABytes + a.BN * kChunkK * 2) +
-                      (size_t)kEpiWarps * a.epi_bufs * kEpiStageBytes + 512;
+  const size_t smem = smem_need();
   const int grid = a.total_tiles < tdr_num_sms() ? a.total_tiles : tdr_num_sms();
   const int variant = a.epi_mode == 1 ? (a.out_is_f32 | (d->res2 ? 2 : 0) | (d->res1 ? 4 : 0)) : -1;
 #define TDR_LAUNCH_CONV(VV)                                                                                        \

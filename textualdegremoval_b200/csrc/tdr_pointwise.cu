@@ -102,6 +102,16 @@ __device__ __forceinline__ f2 mul2(f2 a, f2 b) {
   return d;
 }
 // two bf16 packed in a 32-bit word -> fp32 pair (exact)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ f2 bf2_to_f2(uint32_t u) { return pk2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
 
 // Exact-erf GELU (F.gelu default, R:239) on a pair.  erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below
@@ -113,7 +123,7 @@ __device__ __forceinline__ f2 gelu2(f2 x) {
   const f2 z = pk2(z0, z1);
   float d0, d1;
   upk2(fma2(pk2(0.3275911f, 0.3275911f), z, pk2(1.f, 1.f)), d0, d1);
-  const f2 t = pk2(__frcp_rn(d0), __frcp_rn(d1));
+  const f2 t = pk2(rcp_approx(d0), rcp_approx(d1));        // MUFU.RCP: 1 ulp, inputs in [1, 1 + 0.33|x|]
   f2 p = fma2(t, pk2(1.061405429f, 1.061405429f), pk2(-1.453152027f, -1.453152027f));
   p = fma2(p, t, pk2(1.421413741f, 1.421413741f));
   p = fma2(p, t, pk2(-0.284496736f, -0.284496736f));
@@ -122,7 +132,7 @@ __device__ __forceinline__ f2 gelu2(f2 x) {
   float e0, e1;
   upk2(mul2(z, mul2(z, pk2(-1.4426950408889634f, -1.4426950408889634f))), e0, e1);
   float q0, q1;
-  upk2(mul2(p, pk2(exp2f(e0), exp2f(e1))), q0, q1);          // q = 1 - erf(|x|/sqrt2)
+  upk2(mul2(p, pk2(ex2_approx(e0), ex2_approx(e1))), q0, q1);  // q = 1 - erf(|x|/sqrt2)
   const float s0 = x0 >= 0.f ? 2.f - q0 : q0, s1 = x1 >= 0.f ? 2.f - q1 : q1;
   return mul2(mul2(x, pk2(0.5f, 0.5f)), pk2(s0, s1));
 }
