@@ -105,6 +105,18 @@ int tdr_rownorm(const float* in, long long in_ld, long long rows, int C, int mod
 int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
                   const float* bias, int gate, void* out_bf16, long long out_ld, cudaStream_t stream);
 
+/* NAFNet pieces (network_nafnet_guided_arch.py, "N:").
+ *   tdr_gate_mul     : SimpleGate N:170-175 on bf16 rows, out[r, c] = x[r, c] * x[r, C + c].
+ *   tdr_naf_sca_fold : Simplified channel attention N:192-196 folded into conv3 N:229: s = W_sca * avgpool(g) + b_sca,
+ *                      Weff[b][co][ci] = rowscale[co] * W3[co][ci] * s[b][ci]  (bf16 [B][Co][weff_ld]); then
+ *                      `x * sca(x)` -> conv3 -> `* beta` is one tdr_conv_gemm(g, Weff, w_batched=1). */
+int tdr_gate_mul(const void* x_bf16, long long ld, long long rows, int C /* output channels */, void* out_bf16,
+                 long long out_ld, cudaStream_t stream);
+size_t tdr_naf_sca_workspace_bytes(int B, long long P, int C);
+int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long long P, int C, const float* w_sca /* [C][C] */,
+                     const float* b_sca, const float* w3 /* fp32 [Co][C] */, int Co, const float* rowscale /* [Co] */,
+                     void* weff_bf16, long long weff_ld, float* workspace, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * MDTA channel attention R:262-276.
  *   tdr_mdta_gram : per (sample, head) Gram q^T k plus sum-of-squares of q and k over all pixels (tcgen05, split over

@@ -40,6 +40,30 @@ GUIDED_CASES = {
 }
 
 
+NAFNET_CASES = {
+    # BASELINE.json configs[0]: NAFNet-tiny Gaussian gray denoise sigma=15, one 64x64 tile
+    "nafnet_tiny_gray64": dict(cfg=dict(img_channel=1, width=16, middle_blk_num=1, enc_blk_nums=[1, 1, 1, 1],
+                                        dec_blk_nums=[1, 1, 1, 1]), seed=31, shape=(1, 1, 64, 64), sigma=15),
+    "nafnet_rgb_ragged": dict(cfg=dict(img_channel=3, width=16, middle_blk_num=2, enc_blk_nums=[1, 2],
+                                       dec_blk_nums=[1, 1]), seed=32, shape=(2, 3, 50, 70), sigma=25),
+}
+NAF_GUIDED_CASES = {
+    "guided_nafnet_256": dict(cfg=dict(img_channel=3, width=16, middle_blk_num=1, enc_blk_nums=[1, 1, 1, 2],
+                                       dec_blk_nums=[1, 1, 1, 1], nf=16, ext_n_blocks=[1, 1, 1, 1],
+                                       reffusion_n_blocks=[1, 1, 1, 1, 1]),
+                              seed=41, lq=(1, 3, 256, 256), ref=(1, 3, 256, 256)),
+}
+
+
+def denoise_inputs(case):
+    """The reference's deterministic test-noise recipe (data/restoration_dataset.py:479-480): np.random.seed(0) then
+    N(0, (sigma/255)^2) added to a seeded clean tile."""
+    gt = W.seeded_image("gt", case["shape"], case["seed"])
+    np.random.seed(0)
+    noise = np.random.normal(0, case["sigma"] / 255.0, tuple(case["shape"])).astype(np.float32)
+    return gt + torch.from_numpy(noise), gt
+
+
 def guided_inputs(case):
     """lq = seeded image; ref = a shifted/noised copy when shapes agree (so matching is non-degenerate)."""
     lq = W.seeded_image("lq", case["lq"], case["seed"])
@@ -69,5 +93,24 @@ def main():
         print(name, tuple(y.shape), float(y.abs().max()))
 
 
+def main_nafnet():
+    torch.set_grad_enabled(False)
+    for name, case in NAFNET_CASES.items():
+        net = R.nafnet(**case["cfg"])
+        W.load_seeded(net, case["seed"])
+        lq, _ = denoise_inputs(case)
+        y = net(lq)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(case), out=y.numpy())
+        print(name, tuple(y.shape), float(y.abs().max()))
+    for name, case in NAF_GUIDED_CASES.items():
+        net = R.nafnet_ref_fusion(**case["cfg"])
+        W.load_seeded(net, case["seed"])
+        lq, ref = guided_inputs(case)
+        y = net(lq, ref)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(case), out=y.numpy())
+        print(name, tuple(y.shape), float(y.abs().max()))
+
+
 if __name__ == "__main__":
     main()
+    main_nafnet()

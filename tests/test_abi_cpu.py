@@ -82,6 +82,31 @@ def test_state_dict_keys_match_reference():
     assert all(a[k].shape == b[k].shape for k in b)
 
 
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="/root/reference not present")
+def test_nafnet_state_dict_keys_match_reference():
+    from oracle import ref_loader as R
+    from textualdegremoval_b200 import define_network
+    cfg = dict(img_channel=3, width=16, middle_blk_num=1, enc_blk_nums=[1, 1, 2, 1], dec_blk_nums=[1, 1, 1, 1], nf=16,
+               ext_n_blocks=[1, 2, 1, 1], reffusion_n_blocks=[1, 1, 2, 1, 1])
+    a = define_network(dict(type="NAFNetRefFusion", **cfg)).state_dict()
+    b = R.nafnet_ref_fusion(**cfg).state_dict()
+    assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in b)
+    cfg = dict(img_channel=1, width=16, middle_blk_num=1, enc_blk_nums=[1, 1, 1, 1], dec_blk_nums=[1, 1, 1, 1])
+    a = define_network(dict(type="NAFNet", **cfg)).state_dict()
+    b = R.nafnet(**cfg).state_dict()
+    assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in b)
+
+
+def test_nafnet_option_002_param_count():
+    """Option 002 kwargs (with the 5-entry fusion list the reference actually needs): 253,219,395."""
+    from textualdegremoval_b200 import define_network
+    net = define_network(dict(type="NAFNetRefFusion", img_channel=3, width=64, enc_blk_nums=[1, 1, 1, 28],
+                              middle_blk_num=1, dec_blk_nums=[1, 1, 1, 1], nf=64, ext_n_blocks=[4, 4, 4, 4],
+                              reffusion_n_blocks=[2, 2, 2, 2], reffusion_n_blocks_middle=1, scale=1, num_nbr=1, psize=3,
+                              lr_block_size=8, ref_down_block_size=1.5, dilations=[1, 2, 3]))
+    assert sum(p.numel() for p in net.parameters()) == 253219395
+
+
 def test_cpu_tensors_are_refused():
     from textualdegremoval_b200 import TdrError, define_network
     net = define_network(dict(type="Restormer", dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1))

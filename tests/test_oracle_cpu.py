@@ -8,7 +8,9 @@ import pytest
 import torch
 
 from oracle import ref_loader, restormer as O, weights as W
-from oracle.make_golden import GUIDED_CASES, RESTORMER_CASES, guided_inputs
+from oracle import nafnet as ON
+from oracle.make_golden import (GUIDED_CASES, NAF_GUIDED_CASES, NAFNET_CASES, RESTORMER_CASES, denoise_inputs,
+                                guided_inputs)
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -43,6 +45,42 @@ def test_guided_oracle_matches_golden(name):
     with torch.no_grad():
         y = O.restormer_ref_fusion_forward(sd, lq, rf, meta["cfg"]["heads"])
     assert (y - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("name", list(NAFNET_CASES))
+def test_nafnet_oracle_matches_golden(name):
+    from textualdegremoval_b200.archs.nafnet_b200_arch import NAFNet
+    meta, ref = _load(name)
+    sd = W.seeded_state_dict(_shapes(NAFNet, meta["cfg"]), meta["seed"])
+    lq, _ = denoise_inputs(meta)
+    with torch.no_grad():
+        y = ON.nafnet_forward(sd, lq)
+    assert (y - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("name", list(NAF_GUIDED_CASES))
+def test_guided_nafnet_oracle_matches_golden(name):
+    from textualdegremoval_b200.archs.nafnet_b200_arch import NAFNetRefFusion
+    meta, ref = _load(name)
+    sd = W.seeded_state_dict(_shapes(NAFNetRefFusion, meta["cfg"]), meta["seed"])
+    lq, rf = guided_inputs(meta)
+    with torch.no_grad():
+        y = ON.nafnet_ref_fusion_forward(sd, lq, rf)
+    assert (y - ref).abs().max().item() < 2e-5
+
+
+def test_config1_nafnet_tiny_plumbing():
+    """BASELINE.json configs[0] (CPU plumbing): registry -> NAFNet-tiny, structural checksum 1,136,625 params
+    (SURVEY 8c iii), oracle forward on the sigma=15 gray tile, L1 loss against the clean tile is finite."""
+    from textualdegremoval_b200 import define_network
+    meta = NAFNET_CASES["nafnet_tiny_gray64"]
+    net = define_network(dict(type="NAFNet", **meta["cfg"]))
+    assert sum(p.numel() for p in net.parameters()) == 1136625
+    sd = W.load_seeded(net, meta["seed"])
+    lq, gt = denoise_inputs(meta)
+    with torch.no_grad():
+        loss = (ON.nafnet_forward(sd, lq) - gt).abs().mean().item()
+    assert 0 < loss < 10
 
 
 def test_identity_at_zero_alpha():

@@ -20,6 +20,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..lib import TdrError
+from .masa import Encoder, MasaMixin, ResidualBlock, prep_conv as _prep_conv, conv3x3, _f  # noqa: F401
 
 F32, BF16 = torch.float32, torch.bfloat16
 
@@ -95,37 +96,11 @@ class Upsample(nn.Module):
         self.body = nn.Sequential(nn.Conv2d(n_feat, n_feat * 2, 3, 1, 1, bias=False), nn.PixelShuffle(2))
 
 
-class ResidualBlock(nn.Module):
-    def __init__(self, nf):
-        super().__init__()
-        self.conv1 = nn.Conv2d(nf, nf, 3, 1, 1)
-        self.conv2 = nn.Conv2d(nf, nf, 3, 1, 1)
-
-
-class Encoder(nn.Module):
-    """MASA feature extractor (:100-134): four levels nf, 2nf, 4nf, 8nf; n_blks[2] is reused for level 4."""
-
-    def __init__(self, in_chl, nf, n_blks=(1, 1, 1)):
-        super().__init__()
-        nb = [n_blks[0], n_blks[1], n_blks[2], n_blks[2]]
-        chans = [nf, nf * 2, nf * 4, nf * 8]
-        prev = in_chl
-        for i, (c, n) in enumerate(zip(chans, nb), start=1):
-            setattr(self, f"conv_L{i}", nn.Conv2d(prev, c, 3, 1 if i == 1 else 2, 1, bias=True))
-            setattr(self, f"blk_L{i}", nn.Sequential(*[ResidualBlock(c) for _ in range(n)]))
-            prev = c
-        self.levels = 4
-
-
 def _blocks(n, cls, **kw):
     return nn.Sequential(*[cls(**kw) for _ in range(n)])
 
 
 # ----------------------------------------------------------------------------------------------- weight preparation
-def _f(t):
-    return None if t is None else t.detach().float().contiguous()
-
-
 def _prep_block(blk: TransformerBlock):
     """Pack one transformer block's parameters for the kernels (bf16 GEMM weights, padded GDFN halves)."""
     a, f = blk.attn, blk.ffn
@@ -153,11 +128,6 @@ def _prep_block(blk: TransformerBlock):
     p["b_out"] = _f(f.project_out.bias)
     p["alpha"] = _f(blk.alpha) if hasattr(blk, "alpha") else None
     return p
-
-
-def _prep_conv(conv: nn.Conv2d):
-    return dict(w=ops.pack_conv_weight(conv.weight), b=_f(conv.bias), Co=conv.out_channels, Ci=conv.in_channels,
-                stride=conv.stride[0], raw_w=_f(conv.weight))
 
 
 # ----------------------------------------------------------------------------------------------- kernel schedules
@@ -194,10 +164,6 @@ def run_stack(x32, preps):
     for p in preps:
         run_block(x32, p)
     return x32
-
-
-def conv3x3(x16, pc, **kw):
-    return ops.conv_gemm(x16, pc["w"], pc["Co"], k=3, stride=pc["stride"], pad=1, bias=pc["b"], **kw)
 
 
 class _RestormerBase(nn.Module):
@@ -344,7 +310,7 @@ class Restormer(_RestormerBase):
         return ops.nhwc_to_nchw(out, H, W, res=None if self.dual_pixel_task else inp32)     # + inp_img (:499)
 
 
-class RestormerRefFusion(_RestormerBase):
+class RestormerRefFusion(MasaMixin, _RestormerBase):
     def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4,
                  heads=[1, 2, 4, 8], ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias",
                  dual_pixel_task=False, nf=64, ext_n_blocks=[4, 4, 4, 4], reffusion_n_blocks=[1, 1, 1, 1],
@@ -358,7 +324,7 @@ class RestormerRefFusion(_RestormerBase):
         self.scale, self.num_nbr, self.psize = scale, num_nbr, psize
         self.lr_block_size, self.ref_down_block_size, self.dilations = lr_block_size, ref_down_block_size, list(dilations)
         self.padder_size = 2 ** 3
-        self.masa_enc = Encoder(inp_channels, nf, ext_n_blocks)
+        self.masa_enc = Encoder(inp_channels, nf, ext_n_blocks, levels=4)
         # empty lists kept for key/structure parity with the reference (:547-549)
         self.masa_blk_enc = nn.ModuleList()
         self.masa_blk_middle = nn.ModuleList()
@@ -372,64 +338,9 @@ class RestormerRefFusion(_RestormerBase):
 
     def _prepare(self):
         P = self._prepare_body()
-        enc = {}
-        for i in range(1, 5):
-            c = getattr(self.masa_enc, f"conv_L{i}")
-            enc[f"conv_L{i}"] = dict(w=_f(c.weight), b=_f(c.bias)) if i == 1 else _prep_conv(c)
-            enc[f"blk_L{i}"] = [(_prep_conv(b.conv1), _prep_conv(b.conv2)) for b in getattr(self.masa_enc, f"blk_L{i}")]
+        enc = self.prepare_masa_enc()
         P["masa_enc"] = enc
         return P
-
-    # ---- MASA encoder (:100-134) on a batch of images ---------------------------------------------
-    def _masa_encode(self, E, img32):
-        feats = []
-        B, H, W, _ = img32.shape
-        x = torch.empty((B, H, W, self.nf), dtype=BF16, device=img32.device)
-        ops.conv3x3_small_ci(img32, E["conv_L1"]["w"], E["conv_L1"]["b"], relu=True, out_bf16=x)
-        for lvl in range(1, 5):
-            if lvl > 1:
-                _, x = conv3x3(x, E[f"conv_L{lvl}"], relu=True)
-            for c1, c2 in E[f"blk_L{lvl}"]:
-                _, t = conv3x3(x, c1, relu=True)
-                _, x = conv3x3(t, c2, res2=x)
-            feats.append(x)
-        return feats
-
-    # ---- MASA search + transfer (:753-900) ----------------------------------------------------------
-    def _masa_warp(self, f_lq_deep, f_ref, h, w, hr, wr, targets):
-        """targets[lev] = fp32 NHWC view receiving warp at level lev (0 = finest).  Returns aux tensors."""
-        ps, lb = self.padder_size, self.lr_block_size
-        px, py = w // ps // lb, h // ps // lb
-        k_x, k_y = w // ps // px, h // ps // py
-        d_x = 2 * int(wr // ps // (2 * px) * self.ref_down_block_size) + 1
-        d_y = 2 * int(hr // ps // (2 * py) * self.ref_down_block_size) + 1
-        fr = f_ref[-1]
-        B, Hr, Wr, Cd = fr.shape
-        if Wr < d_x + 2 or Hr < d_y + 2:
-            raise ValueError(f"reference image too small for the MASA search window ({d_y + 2}x{d_x + 2} at 1/8 scale)")
-        nblk = py * px
-        co_pad = ops.round_up(nblk, 8)
-        dils = self.dilations
-        # coarse search: 3 dilated 3x3 "convs" of the ref feature with the normalised lq block descriptors
-        n2 = ops.sqnorm_rows(fr)
-        inv = ops.masa_ref_invnorm(n2, dils)
-        wc = ops.masa_coarse_filters(f_lq_deep, k_y, k_x, dils, co_pad)
-        score = torch.empty((B, Hr, Wr, co_pad), dtype=F32, device=fr.device)
-        for i, dl in enumerate(dils):
-            ops.conv_gemm(fr, wc[i], co_pad, k=3, pad=dl, dil=dl, rowscale=inv[i], res2=score if i else None,
-                          out_f32=score, w_batched=True)
-        idx, origin = ops.masa_coarse_argmax(score, nblk, d_y, d_x)
-        # fine search inside each (d+2)^2 window
-        wf = ops.masa_fine_filters(f_lq_deep, k_y, k_x)
-        winv = ops.masa_win_invnorm(n2, origin, d_y, d_x)
-        corr, _ = ops.conv_gemm(fr, wf, k_y * k_x, k=3, pad=0, rowscale=winv, want="f32", w_batched=True,
-                                origin=origin, window=(d_y + 2, d_x + 2))
-        index, att = ops.masa_fine_argmax(corr)
-        nlev = len(f_ref)
-        for lev in range(nlev):
-            s = 2 ** (nlev - 1 - lev)
-            ops.masa_transfer(f_ref[lev], origin, index, att, py, px, k_y, k_x, d_x, s, out32=targets[lev])
-        return dict(idx=idx, origin=origin, index=index, att=att, score=score, corr=corr)
 
     def forward(self, inp_img, ref_img, return_aux=False):
         """:747-964 (with the B1 index shift).  NCHW in, NCHW out, arbitrary H, W (zero-padded to x64, cropped)."""

@@ -501,13 +501,17 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                 const long long row = ((long long)b * (a.OH * 2) + (oy * 2 + (sub >> 1))) * (a.OW * 2) + ox * 2 + (sub & 1);
                 const int cq = col0 >> 2;        // 4 consecutive output channels
                 if (col0 < a.Co) {
-                  if (a.out_f32)
-                    *reinterpret_cast<float4*>(a.out_f32 + row * a.out_f32_ld + cq) =
-                        make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
+                  float4 o = make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
+                  if (a.res2) {               // fp32 skip connection added at the shuffled location (N:372-373)
+                    const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.res2) +
+                                                                      row * a.res2_ld + cq);
+                    o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                  }
+                  if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + row * a.out_f32_ld + cq) = o;
                   if (a.out_bf16) {
                     uint2 pk;
-                    pk.x = pack2(v[sub], v[4 + sub]);
-                    pk.y = pack2(v[8 + sub], v[12 + sub]);
+                    pk.x = pack2(o.x, o.y);
+                    pk.y = pack2(o.z, o.w);
                     *reinterpret_cast<uint2*>(a.out_bf16 + row * a.out_bf16_ld + cq) = pk;
                   }
                 }
@@ -607,7 +611,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     TDR_CHECK_ARG(!d->res1 && !d->res2, "tdr_conv_gemm: residuals unsupported with pixel (un)shuffle");
   } else {
     TDR_CHECK_ARG(d->Co % 16 == 0, "tdr_conv_gemm: pixel-shuffle needs Co %% 16 == 0");
-    TDR_CHECK_ARG(!d->res1 && !d->res2, "tdr_conv_gemm: residuals unsupported with pixel (un)shuffle");
+    TDR_CHECK_ARG(!d->res1 && (!d->res2 || !d->res2_bf16), "tdr_conv_gemm: pixel-shuffle supports an fp32 res2 only");
   }
 
   ConvGemmArgs a;
@@ -649,6 +653,10 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     for (int bn = sbc; bn <= 256; bn += sbc) {
       const int tot = tdr_cdiv(d->Co, bn) * bn;
       if (tot < best_tot || (tot == best_tot && bn > best_bn)) { best_tot = tot; best_bn = bn; }
+    }
+    if (const char* e = getenv("TDR_CONV_BN")) {                                 // tuning knob (experiments only)
+      const int v = atoi(e);
+      if (v >= sbc && v <= 256 && v % sbc == 0) best_bn = v;
     }
     a.BN = best_bn;
     a.n_tiles = tdr_cdiv(d->Co, a.BN);

@@ -720,3 +720,137 @@ extern "C" int tdr_conv3x3_small_co(const void* in_bf16, long long in_ld, int B,
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ NAFNet helpers
+// SimpleGate (network_nafnet_guided_arch.py:170-175) on bf16 rows: out[r, c] = x[r, c] * x[r, C + c]
+namespace {
+__global__ void __launch_bounds__(256) gate_mul_kernel(const bf16* __restrict__ x, long long ld, long long rows, int C,
+                                                       bf16* __restrict__ out, long long out_ld) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int c = (int)(i % nvec) * 8;
+    float a[8], b[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(x + r * ld + c), a);
+    unpack8(*reinterpret_cast<const bf16x8*>(x + r * ld + C + c), b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] *= b[e];
+    *reinterpret_cast<bf16x8*>(out + r * out_ld + c) = pack8(a);
+  }
+}
+
+// Global average pool, stage 1: grid (chunks, B); partial[b][chunk][c] = sum over the chunk's pixels of x[b, p, c]
+__global__ void __launch_bounds__(256) pool_partial_kernel(const bf16* __restrict__ x, long long ld, long long P, int C,
+                                                           int chunks, float* __restrict__ partial) {
+  const int nvec = C >> 3;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const long long per = (P + chunks - 1) / chunks;
+  const long long p0 = chunk * per, p1 = p0 + per < P ? p0 + per : P;
+  // thread -> (channel vector, pixel lane): all threads sharing a vector are reduced through shared memory
+  const int lanes = blockDim.x / nvec > 0 ? blockDim.x / nvec : 1;
+  __shared__ float red[256 * 8];
+  for (int v0 = 0; v0 < nvec; v0 += blockDim.x) {          // nvec > 256 only for C > 2048
+    const int v = v0 + (int)(threadIdx.x % (nvec < (int)blockDim.x ? nvec : (int)blockDim.x));
+    const int pl = threadIdx.x / (nvec < (int)blockDim.x ? nvec : (int)blockDim.x);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (v < nvec && pl < lanes) {
+      for (long long p = p0 + pl; p < p1; p += lanes) {
+        float f[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(x + ((long long)b * P + p) * ld + v * 8), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[threadIdx.x * 8 + e] = acc[e];
+    __syncthreads();
+    const int nv_here = nvec - v0 < (int)blockDim.x ? nvec - v0 : (int)blockDim.x;
+    if ((int)threadIdx.x < nv_here) {
+      float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int l = 0; l < lanes && l * nv_here + (int)threadIdx.x < (int)blockDim.x; ++l)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s[e] += red[(l * nv_here + threadIdx.x) * 8 + e];
+      float* dst = partial + ((size_t)b * chunks + chunk) * C + (v0 + threadIdx.x) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dst[e] = s[e];
+    }
+    __syncthreads();
+  }
+}
+
+// Stage 2 + SCA + fold (N:192-196,225-229): s = W_sca * mean + b_sca;  Weff[b][co][ci] = rowscale[co] * W3[co][ci] * s[b][ci]
+// grid (ceil(Co/16), B), block 256
+__global__ void __launch_bounds__(256) sca_fold_kernel(const float* __restrict__ partial, int chunks, long long P, int C,
+                                                       const float* __restrict__ w_sca, const float* __restrict__ b_sca,
+                                                       const float* __restrict__ w3, int Co,
+                                                       const float* __restrict__ rowscale, bf16* __restrict__ weff,
+                                                       long long weff_ld) {
+  extern __shared__ float sm[];       // mean[C], s[C]
+  float* mean = sm;
+  float* s = sm + C;
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int ch = 0; ch < chunks; ++ch) t += partial[((size_t)b * chunks + ch) * C + c];
+    mean[c] = t / (float)P;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int c = warp; c < C; c += blockDim.x >> 5) {
+    float t = 0.f;
+    for (int k = lane; k < C; k += 32) t = fmaf(w_sca[(size_t)c * C + k], mean[k], t);
+    t = warp_sum(t);
+    if (lane == 0) s[c] = t + (b_sca ? b_sca[c] : 0.f);
+  }
+  __syncthreads();
+  const int co0 = blockIdx.x * 16;
+  for (int i = threadIdx.x; i < 16 * C; i += blockDim.x) {
+    const int co = co0 + i / C, ci = i % C;
+    if (co < Co)
+      weff[((size_t)b * Co + co) * weff_ld + ci] =
+          __float2bfloat16(w3[(size_t)co * C + ci] * s[ci] * (rowscale ? rowscale[co] : 1.f));
+  }
+}
+}  // namespace
+
+extern "C" int tdr_gate_mul(const void* x_bf16, long long ld, long long rows, int C, void* out_bf16, long long out_ld,
+                            cudaStream_t stream) {
+  TDR_CHECK_ARG(x_bf16 && out_bf16 && rows > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0 && out_ld % 8 == 0,
+                "tdr_gate_mul: bad arguments");
+  gate_mul_kernel<<<grid_for(rows * (C / 8), 256, 16), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x_bf16), ld, rows,
+                                                                        C, reinterpret_cast<bf16*>(out_bf16), out_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+static int naf_pool_chunks(long long P) {
+  long long c = (P + 1023) / 1024;
+  if (c > 128) c = 128;
+  if (c < 1) c = 1;
+  return (int)c;
+}
+
+extern "C" size_t tdr_naf_sca_workspace_bytes(int B, long long P, int C) {
+  if (B <= 0 || P <= 0 || C <= 0) return 0;
+  return (size_t)B * naf_pool_chunks(P) * C * sizeof(float);
+}
+
+extern "C" int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long long P, int C, const float* w_sca,
+                                const float* b_sca, const float* w3, int Co, const float* rowscale, void* weff_bf16,
+                                long long weff_ld, float* workspace, cudaStream_t stream) {
+  TDR_CHECK_ARG(g_bf16 && w_sca && w3 && weff_bf16 && workspace, "tdr_naf_sca_fold: null pointer");
+  TDR_CHECK_ARG(B > 0 && P > 0 && C % 8 == 0 && ld % 8 == 0 && weff_ld >= C && weff_ld % 8 == 0 && Co > 0,
+                "tdr_naf_sca_fold: bad dims");
+  TDR_CHECK_ARG(C <= 6144, "tdr_naf_sca_fold: C too large");
+  const int chunks = naf_pool_chunks(P);
+  dim3 g1(chunks, B);
+  pool_partial_kernel<<<g1, 256, 0, stream>>>(reinterpret_cast<const bf16*>(g_bf16), ld, P, C, chunks, workspace);
+  TDR_CHECK_LAUNCH();
+  dim3 g2((Co + 15) / 16, B);
+  sca_fold_kernel<<<g2, 256, 2 * C * sizeof(float), stream>>>(workspace, chunks, P, C, w_sca, b_sca, w3, Co, rowscale,
+                                                              reinterpret_cast<bf16*>(weff_bf16), weff_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}

@@ -49,6 +49,9 @@ SIGNATURES = {
     "tdr_conv3x3_small_co": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "tdr_rownorm": (_i, [_vp, _ll, _ll, _i, _i, _vp, _vp, _f, _vp, _ll, _vp]),
     "tdr_dwconv3x3": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _vp]),
+    "tdr_gate_mul": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp]),
+    "tdr_naf_sca_workspace_bytes": (_sz, [_i, _ll, _i]),
+    "tdr_naf_sca_fold": (_i, [_vp, _ll, _i, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp]),
     "tdr_mdta_partials_bytes": (_sz, [_i, _ll, _i, _i]),
     "tdr_mdta_gram": (_i, [_vp, _ll, _i, _ll, _i, _i, _vp, _vp]),
     "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp]),

@@ -228,6 +228,30 @@ def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False):
     return (weff, attn) if want_attn else weff
 
 
+def gate_mul(x16, out=None):
+    """SimpleGate: bf16 [B,H,W,2C] -> [B,H,W,C]."""
+    B, H, W, C2 = x16.shape
+    Cc = C2 // 2
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=BF16, device=x16.device)
+    _call("tdr_gate_mul", _p(x16), _ld(x16), B * H * W, Cc, _p(out), _ld(out), _stream(), tag=f"C{Cc}",
+          nbytes=B * H * W * Cc * 6)
+    return out
+
+
+def naf_sca_fold(g16, w_sca, b_sca, w3, rowscale=None):
+    """g16: bf16 [B,H,W,C] (gated features).  Returns per-sample folded conv3 weights bf16 [B, Co, C_p]."""
+    B, H, W, Cc = g16.shape
+    Co = w3.shape[0]
+    nbytes = lib.load().tdr_naf_sca_workspace_bytes(B, H * W, Cc)
+    ws = torch.empty(nbytes // 4, dtype=F32, device=g16.device)
+    cp = round_up(Cc, 8)
+    weff = torch.empty((B, Co, cp), dtype=BF16, device=g16.device)
+    _call("tdr_naf_sca_fold", _p(g16), _ld(g16), B, H * W, Cc, _p(w_sca), _p(b_sca), _p(w3), Co, _p(rowscale), _p(weff),
+          cp, _p(ws), _stream(), tag=f"C{Cc}", nbytes=B * H * W * Cc * 2)
+    return weff
+
+
 def nchw_to_nhwc(x, pad_h, pad_w, want_bf16=False):
     x = x.contiguous().float()
     B, Cc, H, W = x.shape
