@@ -45,6 +45,7 @@ int tdr_check_device(void);
  * `attn @ v` + project_out R:272-276 (per-sample weights); MASA correlations R:683-692, R:661-669 (per-sample
  * filters, dilation, per-pixel scale, window origins).
  *   out = g * alpha * act( acc * rowscale[pixel] + bias[co] ) + g * res1_scale * res1 + res2,   g = scale_ptr ? *scale_ptr : 1
+ * With H == 1 the op is a plain row-major GEMM over [W rows, Ci] (ViT / mapper linears, q.k^T, p.v).
  * ------------------------------------------------------------------------------------------------------------- */
 typedef struct tdr_conv_gemm_desc {
   const void* in; /* bf16 [B_img, H, W, in_ld], channels [0, Ci) used */
@@ -54,6 +55,7 @@ typedef struct tdr_conv_gemm_desc {
   long long w_ld;
   int Co, KH, KW, stride, pad, dil;
   int w_batched;
+  long long w_batch_stride; /* elements between per-sample weight sets; 0 = taps * Co * w_ld (packed) */
   const int* origin; /* optional int32 [B][3] = (image, y0, x0): sample b reads image `image` shifted by (y0, x0);
                         H, W then describe the per-sample window used to size the output */
   int n_images;      /* number of images in `in` when origin != NULL (else ignored) */
@@ -62,7 +64,7 @@ typedef struct tdr_conv_gemm_desc {
   const float* rowscale; /* fp32 [B*OH*OW] or NULL */
   float alpha;
   const float* scale_ptr; /* optional DEVICE scalar g (e.g. TransformerResFusionBlock.alpha R:343,353) */
-  int relu;
+  int act;                /* 0 none, 1 ReLU, 2 exact (erf) GELU */
   const float* res1; /* fp32, same addressing as the output, or NULL */
   long long res1_ld;
   float res1_scale;
@@ -96,8 +98,11 @@ int tdr_conv3x3_small_co(const void* in_bf16, long long in_ld, int B, int H, int
  *   mode 0: cast only.  mode 1: WithBias LN R:189-205 (also LayerNorm2d nafnet_arch_utils.py:264-300 with eps 1e-6).
  *   mode 2: BiasFree LN R:172-186 (x / sqrt(var + eps) * w, mean not subtracted).
  * ------------------------------------------------------------------------------------------------------------- */
+/* act: 0 none, 3 LeakyReLU(0.01) applied after the affine (mapper MLPs, main_train_tr_mapping.py:52-60).
+ * Either or both of out_bf16 / out_f32 (e.g. the final DINO norm, models/dino/vision_transformers.py:262). */
 int tdr_rownorm(const float* in, long long in_ld, long long rows, int C, int mode, const float* weight,
-                const float* bias, float eps, void* out_bf16, long long out_ld, cudaStream_t stream);
+                const float* bias, float eps, int act, void* out_bf16, long long out_ld, float* out_f32,
+                long long out_f32_ld, cudaStream_t stream);
 
 /* Depthwise 3x3, pad 1 (R:231, R:253; N:conv2) on bf16 NHWC.  weight fp32 [9][C] (tap-major), bias fp32 [C] or NULL.
  * gate = 0: out[.., C].  gate = 1 (GDFN R:238-239): C = 2*Ch, out[.., Ch] = gelu(dw(x)[:Ch]) * dw(x)[Ch:].
@@ -132,6 +137,33 @@ int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long long P, int C,
 int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature /* [heads] */,
                   const float* w_out /* fp32 [C][C] */, void* weff_bf16, long long weff_ld, float* attn_ws,
                   cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * ViT encoder / mapper glue (DINOv2 ViT-B/14 models/dino/*.py "D:", CLIP ViT-H/14 via transformers, mappers "M:" =
+ * scripts/train/main_train_tr_mapping.py:40-122).  Dense contractions go through tdr_conv_gemm (H == 1 view).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* NCHW fp32 images -> bf16 patches [B, (H/p)*(W/p), ld], K index = (c*p + ky)*p + kx  (D: patch_embed.py:76) */
+int tdr_vit_patchify(const float* img, int B, int C, int H, int W, int patch, void* out_bf16, long long ld,
+                     cudaStream_t stream);
+/* x[b,0] = cls + pos[0]; x[b,1+t] = patch_tokens[b,t] + pos[1+t]  (D: vision_transformers.py:215-216) */
+int tdr_vit_assemble_tokens(const float* patch_tokens, const float* cls, const float* pos, int B, int N, int D, float* x,
+                            cudaStream_t stream);
+/* p = softmax(scale * s[row, 0:n]) as bf16, pad columns zeroed (D: attention.py:61-64) */
+int tdr_softmax_rows(const float* s, long long ld, long long rows, int n, float scale, void* out_bf16, long long ld_out,
+                     cudaStream_t stream);
+/* vt[b, h, d, t] = qkv[b, t, voff + h*hd + d], t padded with zeros to n_pad (K-major operand of p.v) */
+int tdr_vit_transpose_v(const void* qkv_bf16, long long ld, int B, int N, int heads, int hd, int voff, void* vt_bf16,
+                        int n_pad, cudaStream_t stream);
+/* Reference-crop selection (models/image_restoration_ref_model.py:215-247): crop (origin[k] = (image, y0, x0), size
+ * crop_h x crop_w) + bilinear resize (align_corners=False) of NCHW fp32 images in one pass, and the cosine similarity
+ * between one query feature row per sample and n candidate rows. */
+int tdr_crop_resize(const float* img, int C, int H, int W, const int* origin, int ncrops, int crop_h, int crop_w,
+                    int out_h, int out_w, float* out, cudaStream_t stream);
+int tdr_cosine_rows(const float* fl /* [B, F] */, const float* fr /* [B*n, F] */, int B, int n, long long F,
+                    float* cosv /* [B, n] */, cudaStream_t stream);
+/* out[b, c] (+)= mean_t x[b, t0 + t, c], t < n  (M: `.mean(dim=1, keepdim=True)` :77) */
+int tdr_mean_tokens(const float* x, long long ld, int B, int tokens_per_b, int t0, int n, int C, float* out,
+                    long long out_ld, int accumulate, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Layout / copies.

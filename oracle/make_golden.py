@@ -93,6 +93,59 @@ def main():
         print(name, tuple(y.shape), float(y.abs().max()))
 
 
+VIT_CASES = {
+    "dino_vit_tiny": dict(cfg=dict(img_size=70, patch_size=14, embed_dim=64, depth=2, num_heads=4, mlp_ratio=4,
+                                   init_values=1.0, ffn_layer="mlp", block_chunks=0), seed=51, shape=(2, 3, 56, 84)),
+    "clip_vit_tiny": dict(cfg=dict(hidden_size=80, intermediate_size=160, num_hidden_layers=2, num_attention_heads=1,
+                                   patch_size=14, image_size=56, hidden_act="gelu"), seed=52, shape=(2, 3, 56, 56)),
+    "mappers_tiny": dict(cfg=dict(input_dim=80, mid_dim=48, num_words=3), seed=53, shape=(2, 17, 80)),
+}
+
+
+def load_mapper_classes():
+    """Mapper / CleanMapper live in a training script that imports accelerate/diffusers (absent): extract the two
+    ClassDef nodes with ast and exec them unchanged (SURVEY 8c recipe)."""
+    import ast
+    src = open(os.path.join(R.REF_ROOT, "scripts", "train", "main_train_tr_mapping.py")).read()
+    ns = {"nn": torch.nn, "torch": torch}
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name in ("Mapper", "CleanMapper"):
+            exec(compile(ast.Module([node], []), "main_train_tr_mapping.py", "exec"), ns)
+    return ns["Mapper"], ns["CleanMapper"]
+
+
+def main_vit():
+    from functools import partial
+    torch.set_grad_enabled(False)
+    R._stub_packages()
+    from models.dino.attention import MemEffAttention
+    from models.dino.block import Block
+    from models.dino.vision_transformers import DinoVisionTransformer
+    case = VIT_CASES["dino_vit_tiny"]
+    net = DinoVisionTransformer(block_fn=partial(Block, attn_class=MemEffAttention), **case["cfg"]).eval()
+    W.load_seeded(net, case["seed"])
+    y = net(W.seeded_image("x", case["shape"], case["seed"]))
+    np.savez_compressed(os.path.join(OUT, "dino_vit_tiny.npz"), meta=json.dumps(case), out=y.numpy())
+    print("dino_vit_tiny", tuple(y.shape))
+    # CLIP: arithmetic lives in third-party transformers (reference pins 4.31.0; installed here: see fixture meta)
+    import transformers
+    case = dict(VIT_CASES["clip_vit_tiny"], transformers=transformers.__version__)
+    net = transformers.CLIPVisionModel(transformers.CLIPVisionConfig(**case["cfg"])).eval()
+    W.load_seeded(net, case["seed"])
+    y = net(W.seeded_image("x", case["shape"], case["seed"]), output_hidden_states=True)[0]
+    np.savez_compressed(os.path.join(OUT, "clip_vit_tiny.npz"), meta=json.dumps(case), out=y.numpy())
+    print("clip_vit_tiny", tuple(y.shape), "transformers", transformers.__version__)
+    Mapper, CleanMapper = load_mapper_classes()
+    case = VIT_CASES["mappers_tiny"]
+    c = case["cfg"]
+    m, cm = Mapper(c["input_dim"], c["mid_dim"], c["num_words"]).eval(), CleanMapper(c["mid_dim"], c["mid_dim"], c["num_words"]).eval()
+    W.load_seeded(m, case["seed"]); W.load_seeded(cm, case["seed"] + 1)
+    emb = W.seeded_image("emb", case["shape"], case["seed"]) * 2 - 1
+    w1 = m([emb]); w2 = cm(w1)
+    np.savez_compressed(os.path.join(OUT, "mappers_tiny.npz"), meta=json.dumps(case), out=w1.numpy(), out2=w2.numpy())
+    print("mappers_tiny", tuple(w1.shape), tuple(w2.shape))
+
+
 def main_nafnet():
     torch.set_grad_enabled(False)
     for name, case in NAFNET_CASES.items():
@@ -114,3 +167,4 @@ def main_nafnet():
 if __name__ == "__main__":
     main()
     main_nafnet()
+    main_vit()

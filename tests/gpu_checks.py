@@ -156,7 +156,7 @@ def check_small_convs():
 # =============================================================================================== conv_gemm
 def _conv_case(name, impl, B=2, H=16, W=16, Ci=48, Co=144, k=1, stride=1, pad=0, dil=1, bias=False, relu=False,
                res2=None, res1=False, alpha=1.0, use_scale_ptr=False, store_mode=0, want="f32", batched=False,
-               rowscale=False, tol=2e-3):
+               rowscale=False, gelu=False, tol=2e-3):
     ops = _ops()
     x = q(rnd(B, Ci, H, W, seed=H * W + Ci))
     nb = B if batched else 1
@@ -175,6 +175,8 @@ def _conv_case(name, impl, B=2, H=16, W=16, Ci=48, Co=144, k=1, stride=1, pad=0,
         y = y + b.view(1, -1, 1, 1)
     if relu:
         y = F.relu(y)
+    if gelu:
+        y = F.gelu(y)
     g = 0.7 if use_scale_ptr else 1.0
     y = y * alpha * g
     if store_mode == 1:
@@ -193,7 +195,7 @@ def _conv_case(name, impl, B=2, H=16, W=16, Ci=48, Co=144, k=1, stride=1, pad=0,
     wp = torch.cat([ops.pack_conv_weight(w[i].to(DEV)) for i in range(nb)], 0)
     o32, o16 = ops.conv_gemm(
         nhwc(x.to(BF16)), wp, Co, k=k, stride=stride, pad=pad, dil=dil, bias=b.to(DEV) if bias else None, relu=relu,
-        rowscale=rs.to(DEV) if rowscale else None, alpha=alpha,
+        gelu=gelu, rowscale=rs.to(DEV) if rowscale else None, alpha=alpha,
         scale_ptr=torch.tensor([g], device=DEV) if use_scale_ptr else None,
         res1=nhwc(r1) if res1 else None, res1_scale=0.5,
         res2=(nhwc(r2.to(BF16)) if res2 == "bf16" else nhwc(r2)) if res2 is not None else None,
@@ -217,6 +219,8 @@ CONV_CASES = [
     dict(name="1x1_odd_spatial", Ci=48, Co=48, H=20, W=24, B=1),
     dict(name="1x1_w8", Ci=64, Co=64, H=16, W=8),
     dict(name="1x1_big_k", Ci=1024, Co=256, H=8, W=16, B=1),
+    dict(name="flat_gemm_gelu", Ci=768, Co=3072, H=1, W=300, B=2, bias=True, gelu=True, want="bf16"),
+    dict(name="flat_gemm_res", Ci=3072, Co=768, H=1, W=1370, B=1, bias=True, res2="f32"),
     dict(name="3x3_48to48_bias_relu", Ci=48, Co=48, k=3, pad=1, bias=True, relu=True, want="bf16"),
     dict(name="3x3_res_bf16", Ci=32, Co=32, k=3, pad=1, bias=True, res2="bf16", want="bf16"),
     dict(name="3x3_stride2", Ci=48, Co=96, k=3, pad=1, stride=2, bias=True, relu=True, H=32, W=32),
@@ -392,7 +396,7 @@ def guided_result(name, y, ref):
     r = result(name, y, ref, 1.0)
     mean = (y - ref).abs().mean().item()
     ps = psnr_u8(y, ref)
-    r["ok"] = bool(torch.isfinite(y).all()) and mean <= GUIDED_MEAN_TOL and ps >= GUIDED_PSNR_MIN
+    r["ok"] = bool(torch.isfinite(y).all() and mean <= GUIDED_MEAN_TOL and ps >= GUIDED_PSNR_MIN)
     r["tol"] = GUIDED_MEAN_TOL
     r["note"] = f"max|d|={r['max_err']:.2e} mean|d|={mean:.2e} (tol, on the mean) psnr_u8(ours,ref)={ps:.2f}dB"
     r["max_err"] = mean
@@ -475,6 +479,72 @@ def check_nafnet():
     return out
 
 
+def check_vit():
+    """ViT glue kernels, DINOv2 / CLIP towers, mappers and reference-crop selection against oracle / golden."""
+    from oracle import vit as OV, weights as Wt
+    from textualdegremoval_b200.archs import vit_b200 as VB
+    ops = _ops()
+    out = []
+    # softmax rows / crop-resize against torch
+    s = rnd(3, 5, 37, seed=1) * 4
+    sp = torch.zeros(3, 5, 40)
+    sp[..., :37] = s
+    o16 = torch.empty(3, 5, 40, dtype=BF16, device=DEV)
+    ops.softmax_rows(sp.to(DEV), 37, 0.25, o16)
+    out.append(result("softmax_rows", o16[..., :37], torch.softmax(s * 0.25, -1), 8e-3))
+    out.append(result("softmax_rows_pad", o16[..., 37:], torch.zeros(3, 5, 3), 0.0))
+    img = torch.rand(2, 3, 40, 52, generator=torch.Generator().manual_seed(2))
+    org = torch.tensor([[0, 0, 0], [1, 8, 12], [0, 3, 20]], dtype=torch.int32)
+    ref = torch.stack([F.interpolate(img[b:b + 1, :, y:y + 32, x:x + 32], size=(28, 42), mode="bilinear")[0]
+                       for b, y, x in org.tolist()])
+    out.append(result("crop_resize", ops.crop_resize(img.to(DEV), org.to(DEV), (32, 32), (28, 42)), ref, 1e-5))
+    # towers
+    meta, gold = _golden("dino_vit_tiny")
+    net = VB.DinoVisionTransformer(**meta["cfg"])
+    sd = Wt.load_seeded(net, meta["seed"])
+    net = net.to(DEV).eval()
+    x = Wt.seeded_image("x", meta["shape"], meta["seed"])
+    with torch.no_grad():
+        y = net(x.to(DEV)).cpu()
+    out.append(result("golden_dino_vit_tiny", y, gold, 2e-2))
+    meta, gold = _golden("clip_vit_tiny")
+    net = VB.CLIPVisionTower(**meta["cfg"])
+    Wt.load_seeded(net, meta["seed"])
+    net = net.to(DEV).eval()
+    with torch.no_grad():
+        y = net(Wt.seeded_image("x", meta["shape"], meta["seed"]).to(DEV), output_hidden_states=True)[0].cpu()
+    out.append(result("golden_clip_vit_tiny", y, gold, 2e-2))
+    z = np.load(os.path.join(ROOT, "tests", "golden", "mappers_tiny.npz"))
+    meta = json.loads(str(z["meta"]))
+    c = meta["cfg"]
+    m, cm = VB.Mapper(c["input_dim"], c["mid_dim"], c["num_words"]), VB.CleanMapper(c["mid_dim"], c["mid_dim"], c["num_words"])
+    Wt.load_seeded(m, meta["seed"]); Wt.load_seeded(cm, meta["seed"] + 1)
+    m, cm = m.to(DEV), cm.to(DEV)
+    emb = Wt.seeded_image("emb", meta["shape"], meta["seed"]) * 2 - 1
+    with torch.no_grad():
+        w1 = m([emb.to(DEV)])
+        w2 = cm(w1)
+    out.append(result("golden_mapper", w1.cpu(), torch.from_numpy(z["out"]), 2e-2))
+    out.append(result("golden_clean_mapper", w2.cpu(), torch.from_numpy(z["out2"]), 3e-2))
+    # reference-crop selection: lq is a blurred copy of one specific crop of ref -> that crop must win
+    net = VB.DinoVisionTransformer(img_size=70, patch_size=14, embed_dim=64, depth=2, num_heads=4)
+    sd = Wt.load_seeded(net, 61)
+    net = net.to(DEV).eval()
+    g = torch.Generator().manual_seed(5)
+    ref_img = F.avg_pool2d(torch.rand(2, 3, 84, 84, generator=g), 3, 1, 1)
+    lq = torch.stack([ref_img[0, :, 14:70, 0:56], ref_img[1, :, 28:84, 28:84]]) + 0.01 * torch.randn(2, 3, 56, 56, generator=g)
+    with torch.no_grad():
+        sel, idx, cos = VB.select_reference_crop(net, lq.to(DEV), ref_img.to(DEV))
+        sel_r, idx_r, cos_r = OV.dino_select_crop(sd, lq, ref_img, heads=4)
+    out.append(result("dino_select_cosine", cos, cos_r[:, 0], 2e-2))
+    same = bool((idx.cpu() == idx_r).all())
+    out.append(dict(name="dino_select_index", max_err=0.0 if same else 1.0, ref_scale=1, tol=0.0, ok=same,
+                    note=f"ours {idx.cpu().tolist()} oracle {idx_r.tolist()}"))
+    if same:
+        out.append(result("dino_select_crop", sel, sel_r, 1e-6))
+    return out
+
+
 def check_guided_stages():
     """Guided net stage by stage against the oracle (features, match indices, warps, output)."""
     from oracle import restormer as O, weights as Wt
@@ -523,6 +593,7 @@ CHECKS = {
     "guided_stages": check_guided_stages,
     "guided_golden": check_guided_golden,
     "nafnet": check_nafnet,
+    "vit": check_vit,
 }
 
 

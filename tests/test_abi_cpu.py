@@ -35,7 +35,7 @@ def test_argument_validation_without_gpu(tdr_lib):
     d = ConvGemmDesc()
     assert tdr_lib.tdr_conv_gemm(C.byref(d), None) == -1
     assert b"null" in tdr_lib.tdr_last_error()
-    assert tdr_lib.tdr_rownorm(None, 0, 1, 48, 1, None, None, 1e-5, None, 0, None) == -1
+    assert tdr_lib.tdr_rownorm(None, 0, 1, 48, 1, None, None, 1e-5, 0, None, 0, None, 0, None) == -1
     assert tdr_lib.tdr_mdta_partials_bytes(1, 4096, 50, 1) == 0        # head width not a multiple of 8
     assert tdr_lib.tdr_mdta_partials_bytes(4, 262144, 48, 1) > 0
 

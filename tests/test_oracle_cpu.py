@@ -9,6 +9,8 @@ import torch
 
 from oracle import ref_loader, restormer as O, weights as W
 from oracle import nafnet as ON
+from oracle import vit as OV
+from oracle.make_golden import VIT_CASES
 from oracle.make_golden import (GUIDED_CASES, NAF_GUIDED_CASES, NAFNET_CASES, RESTORMER_CASES, denoise_inputs,
                                 guided_inputs)
 
@@ -81,6 +83,46 @@ def test_config1_nafnet_tiny_plumbing():
     with torch.no_grad():
         loss = (ON.nafnet_forward(sd, lq) - gt).abs().mean().item()
     assert 0 < loss < 10
+
+
+def test_vit_oracles_match_golden():
+    """DINOv2 ViT (reference models/dino), CLIP tower (installed transformers; parity with 4.31.0 unpinned) and the
+    mapper MLPs (classes extracted from the reference script) against their fixtures."""
+    from textualdegremoval_b200.archs import vit_b200 as VB
+    meta, ref = _load("dino_vit_tiny")
+    sd = W.seeded_state_dict({k: v.shape for k, v in VB.DinoVisionTransformer(**meta["cfg"]).state_dict().items()}, meta["seed"])
+    with torch.no_grad():
+        y = OV.dino_vit_forward(sd, W.seeded_image("x", meta["shape"], meta["seed"]), heads=meta["cfg"]["num_heads"])
+    assert (y - ref).abs().max().item() < 2e-5
+    meta, ref = _load("clip_vit_tiny")
+    c = meta["cfg"]
+    sd = W.seeded_state_dict({k: v.shape for k, v in VB.CLIPVisionTower(**c).state_dict().items()}, meta["seed"])
+    with torch.no_grad():
+        y = OV.clip_vision_forward(sd, W.seeded_image("x", meta["shape"], meta["seed"]), c["num_attention_heads"], c["patch_size"])
+    assert (y - ref).abs().max().item() < 2e-5
+    z = np.load(os.path.join(GOLD, "mappers_tiny.npz"))
+    meta = json.loads(str(z["meta"]))
+    c = meta["cfg"]
+    m, cm = VB.Mapper(c["input_dim"], c["mid_dim"], c["num_words"]), VB.CleanMapper(c["mid_dim"], c["mid_dim"], c["num_words"])
+    sd1 = W.seeded_state_dict({k: v.shape for k, v in m.state_dict().items()}, meta["seed"])
+    sd2 = W.seeded_state_dict({k: v.shape for k, v in cm.state_dict().items()}, meta["seed"] + 1)
+    emb = W.seeded_image("emb", meta["shape"], meta["seed"]) * 2 - 1
+    with torch.no_grad():
+        w1 = OV.mapper_forward(sd1, emb, c["num_words"])
+        w2 = OV.clean_mapper_forward(sd2, w1, c["num_words"])
+    assert (w1 - torch.from_numpy(z["out"])).abs().max().item() < 2e-5
+    assert (w2 - torch.from_numpy(z["out2"])).abs().max().item() < 2e-5
+
+
+def test_vit_structural_checksums():
+    """Parameter counts of the full-size encoders / mappers (SURVEY 8c iii)."""
+    from textualdegremoval_b200.archs import vit_b200 as VB
+    n = lambda m: sum(p.numel() for p in m.parameters())
+    assert n(VB.vit_base(img_size=518, patch_size=14, init_values=1.0, ffn_layer="mlp", block_chunks=0)) == 86580480
+    with torch.device("meta"):
+        assert n(VB.CLIPVisionTower()) == 630766080 + 0
+        assert n(VB.Mapper(1280, 1024, 20)) == 249538560
+        assert n(VB.CleanMapper(1024, 1024, 20)) == 118215680
 
 
 def test_identity_at_zero_alpha():

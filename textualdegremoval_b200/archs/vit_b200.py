@@ -1,0 +1,402 @@
+"""B200-native frozen encoders and mapper MLPs (forward only):
+
+  * ``vit_base`` / ``DinoVisionTransformer`` -- DINOv2 ViT-B/14 as the reference builds it in
+    ``models/image_restoration_ref_model.py:75-90`` (``vit_base(img_size=518, patch_size=14, init_values=1.0,
+    ffn_layer='mlp', block_chunks=0)``); same ``state_dict`` keys as ``models/dino/vision_transformers.py`` so that
+    ``load_state_dict(torch.load(pretrain_dino), strict=True)`` works; ``net(x[B,3,14k,14k]) -> [B, k*k, 768]`` (normed
+    patch tokens).  ``select_reference_crop`` is the crop-selection step of ``optimize_parameters`` (:215-247).
+  * ``CLIPVisionTower`` -- CLIP ViT-H/14 vision tower with the ``transformers.CLIPVisionModel`` key names and call
+    convention (``tower(pixel_values, output_hidden_states=True)[0] -> [B, 257, 1280]``, the pre-post-LN hidden state
+    the reference consumes at ``scripts/train/main_train_tr_mapping.py:780``).
+  * ``Mapper`` / ``CleanMapper`` -- ``scripts/train/main_train_tr_mapping.py:40-122`` (keys ``mapping_{i}.{0,1,3,4,6,7,9}``).
+
+Every dense contraction (patch embedding, qkv/proj/fc1/fc2, q.k^T, p.v, mapper linears) is ``tdr_conv_gemm`` on the flat
+``[1 x tokens x channels]`` view (tcgen05); LayerNorm is ``tdr_rownorm``; softmax rows, V transposition, token assembly,
+crop/resize, cosine and token-mean are small dedicated kernels.  Attention materialises fp32 scores (first version; a
+fused flash-style kernel is the planned replacement).  This file is not ``*_arch.py``: the restoration arch registry
+does not scan it, exactly as the reference imports these classes directly.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+from ..lib import TdrError
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+def _f(t):
+    return None if t is None else t.detach().float().contiguous()
+
+
+def _pack_linear(w, row_scale=None):
+    """nn.Linear weight [out, in] -> packed bf16 [1, out, in_p]; optional per-output-row scale (LayerScale fold)."""
+    w = w.detach().float()
+    if row_scale is not None:
+        w = w * row_scale.view(-1, 1)
+    return ops.pack_conv_weight(w.view(w.shape[0], w.shape[1], 1, 1))
+
+
+# ----------------------------------------------------------------------------------------------- shared schedule
+def attention(qkv, heads, D):
+    """qkv: bf16 [B,1,N,3D] living in a buffer with >= 8 spare rows after it.  softmax(q k^T / sqrt(hd)) v -> bf16 [B,1,N,D]."""
+    B, _, N, _ = qkv.shape
+    hd = D // heads
+    n_pad = ops.round_up(N, 8)
+    dev = qkv.device
+    scores = torch.empty((heads, B, 1, N, n_pad), dtype=F32, device=dev)
+    for h in range(heads):
+        ops.conv_gemm(qkv[..., h * hd:(h + 1) * hd], None, n_pad, Ci=hd, w_batched=True, out_f32=scores[h],
+                      w_raw=(qkv.data_ptr() + (D + h * hd) * 2, qkv.stride(2), N * qkv.stride(2)))
+    probs = torch.empty((heads, B, 1, N, n_pad), dtype=BF16, device=dev)
+    ops.softmax_rows(scores, N, hd ** -0.5, probs)
+    vt = ops.vit_transpose_v(qkv, heads, hd, 2 * D, n_pad)
+    out = torch.empty((B, 1, N, D), dtype=BF16, device=dev)
+    for h in range(heads):
+        ops.conv_gemm(probs[h], None, hd, Ci=n_pad, w_batched=True, out_bf16=out[..., h * hd:(h + 1) * hd],
+                      w_raw=(vt.data_ptr() + h * hd * n_pad * 2, n_pad, heads * hd * n_pad))
+    return out
+
+
+def run_layer(x32, p, heads):
+    """Pre-LN transformer layer on the fp32 token stream x32 [B,1,N,D], in place."""
+    B, _, N, D = x32.shape
+    xn = ops.rownorm(x32, 1, p["ln1_w"], p["ln1_b"], p["eps"])
+    qkv_buf = torch.empty((B * N + 8, 3 * D), dtype=BF16, device=x32.device)       # spare rows: see attention()
+    qkv = qkv_buf[: B * N].view(B, 1, N, 3 * D)
+    ops.conv_gemm(xn, p["w_qkv"], 3 * D, bias=p["b_qkv"], out_bf16=qkv)
+    a = attention(qkv, heads, D)
+    ops.conv_gemm(a, p["w_o"], D, bias=p["b_o"], res2=x32, out_f32=x32)
+    xn = ops.rownorm(x32, 1, p["ln2_w"], p["ln2_b"], p["eps"])
+    _, h = ops.conv_gemm(xn, p["w_fc1"], p["hidden"], bias=p["b_fc1"], gelu=True)
+    ops.conv_gemm(h, p["w_fc2"], D, bias=p["b_fc2"], res2=x32, out_f32=x32)
+    return x32
+
+
+def embed_patches(img, w_pe, b_pe, patch, D):
+    """NCHW fp32 -> fp32 patch tokens [B,1,n,D] (Conv2d(k=patch, stride=patch) as a flat GEMM over extracted patches)."""
+    patches = ops.vit_patchify(img, patch)
+    tok, _ = ops.conv_gemm(patches, w_pe, D, bias=b_pe, want="f32")
+    return tok
+
+
+class _Cached(nn.Module):
+    def _key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def prepared(self):
+        key = self._key()
+        if getattr(self, "_prep_cache", None) is None or self._prep_cache[0] != key:
+            with torch.no_grad():
+                self._prep_cache = (key, self._prepare())
+        return self._prep_cache[1]
+
+    @staticmethod
+    def _check(*ts):
+        for t in ts:
+            if not t.is_cuda:
+                raise TdrError("textualdegremoval_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path")
+
+
+# ----------------------------------------------------------------------------------------------- DINOv2
+class _LayerScale(nn.Module):
+    def __init__(self, dim, init_values):
+        super().__init__()
+        self.gamma = nn.Parameter(init_values * torch.ones(dim))
+
+
+class _Attn(nn.Module):
+    def __init__(self, dim, heads):
+        super().__init__()
+        self.num_heads = heads
+        self.qkv = nn.Linear(dim, dim * 3)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class _DinoBlock(nn.Module):
+    def __init__(self, dim, heads, mlp_ratio, init_values):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = _Attn(dim, heads)
+        self.ls1 = _LayerScale(dim, init_values)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _Mlp(dim, int(dim * mlp_ratio))
+        self.ls2 = _LayerScale(dim, init_values)
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch, in_chans, dim):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, dim, patch, patch)
+
+
+class DinoVisionTransformer(_Cached):
+    def __init__(self, img_size=518, patch_size=14, in_chans=3, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4.0,
+                 init_values=1.0, ffn_layer="mlp", block_chunks=0, interpolate_offset=0.1, **unused):
+        super().__init__()
+        if ffn_layer != "mlp" or block_chunks != 0:
+            raise TdrError("DinoVisionTransformer (B200): only ffn_layer='mlp', block_chunks=0 (the reference's call)")
+        self.patch_size, self.embed_dim, self.num_heads = patch_size, embed_dim, num_heads
+        self.interpolate_offset = interpolate_offset
+        n = (img_size // patch_size) ** 2
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, n + 1, embed_dim))
+        self.mask_token = nn.Parameter(torch.zeros(1, embed_dim))
+        self.patch_embed = _PatchEmbed(patch_size, in_chans, embed_dim)
+        self.blocks = nn.ModuleList([_DinoBlock(embed_dim, num_heads, mlp_ratio, init_values) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        nn.init.normal_(self.cls_token, std=1e-6)
+        self._pos_cache = {}
+
+    def _prepare(self):
+        D = self.embed_dim
+        self._pos_cache = {}
+        P = dict(w_pe=_pack_linear(self.patch_embed.proj.weight.reshape(D, -1)), b_pe=_f(self.patch_embed.proj.bias),
+                 cls=_f(self.cls_token).reshape(-1), norm_w=_f(self.norm.weight), norm_b=_f(self.norm.bias), layers=[])
+        for b in self.blocks:
+            g1, g2 = _f(b.ls1.gamma), _f(b.ls2.gamma)
+            P["layers"].append(dict(
+                ln1_w=_f(b.norm1.weight), ln1_b=_f(b.norm1.bias), ln2_w=_f(b.norm2.weight), ln2_b=_f(b.norm2.bias),
+                eps=1e-6, w_qkv=_pack_linear(b.attn.qkv.weight), b_qkv=_f(b.attn.qkv.bias),
+                w_o=_pack_linear(b.attn.proj.weight, g1), b_o=_f(b.attn.proj.bias) * g1,          # LayerScale folded
+                w_fc1=_pack_linear(b.mlp.fc1.weight), b_fc1=_f(b.mlp.fc1.bias), hidden=b.mlp.fc1.out_features,
+                w_fc2=_pack_linear(b.mlp.fc2.weight, g2), b_fc2=_f(b.mlp.fc2.bias) * g2))
+        return P
+
+    def _pos(self, h, w):
+        """interpolate_pos_encoding (vision_transformers.py:179-207): bicubic resize of the learned grid, done once per
+        input size on the (tiny) parameter with torch and cached -- weight preparation, not per-step work."""
+        key = (h, w)
+        if key not in self._pos_cache:
+            with torch.no_grad():
+                pe = self.pos_embed.detach().float()
+                n = pe.shape[1] - 1
+                w0, h0 = w // self.patch_size, h // self.patch_size
+                if not (w0 * h0 == n and w == h):
+                    s = int(math.sqrt(n))
+                    sx = float(w0 + self.interpolate_offset) / math.sqrt(n)
+                    sy = float(h0 + self.interpolate_offset) / math.sqrt(n)
+                    pp = F.interpolate(pe[:, 1:].reshape(1, s, s, -1).permute(0, 3, 1, 2), scale_factor=(sx, sy),
+                                       mode="bicubic")
+                    pe = torch.cat([pe[:, :1], pp.permute(0, 2, 3, 1).reshape(1, w0 * h0, -1)], 1)
+                self._pos_cache[key] = pe.reshape(-1, pe.shape[-1]).contiguous()
+        return self._pos_cache[key]
+
+    def forward(self, x):
+        self._check(x)
+        B, _, H, W = x.shape
+        if H % self.patch_size or W % self.patch_size:       # the reference asserts (patch_embed.py:72-73)
+            raise AssertionError(f"Input image size {H}x{W} is not a multiple of patch size {self.patch_size}")
+        P = self.prepared()
+        tok = embed_patches(x, P["w_pe"], P["b_pe"], self.patch_size, self.embed_dim)
+        xs = ops.vit_assemble_tokens(tok, P["cls"], self._pos(W, H))     # (w, h) named as in the reference (:210)
+        for lp in P["layers"]:
+            run_layer(xs, lp, self.num_heads)
+        out = torch.empty_like(xs)
+        ops.rownorm(xs, 1, P["norm_w"], P["norm_b"], 1e-6, out_f32=out, want_bf16=False)
+        return out[:, 0, 1:, :]
+
+
+def vit_base(patch_size=16, num_register_tokens=0, **kwargs):
+    if num_register_tokens:
+        raise TdrError("vit_base (B200): register tokens are not implemented (unused by the reference)")
+    return DinoVisionTransformer(patch_size=patch_size, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, **kwargs)
+
+
+def select_reference_crop(net_ext, lq, ref):
+    """models/image_restoration_ref_model.py:215-247: among all h x h crops of ``ref`` at stride h//4 pick, per sample,
+    the one whose DINO patch tokens are most cosine-similar to those of ``lq``.  Returns (ref_in, index, cosine)."""
+    B, C, h, w = lq.shape
+    Hr, Wr = ref.shape[2:]
+    stride = h // 4
+    ny, nx = (Hr - h) // stride + 1, (Wr - h) // stride + 1
+    n = ny * nx
+    ps = net_ext.patch_size
+    size = (int(math.ceil(h / ps) * ps), int(math.ceil(w / ps) * ps))
+    dev = lq.device
+    bb, yy, xx = torch.meshgrid(torch.arange(B), torch.arange(ny) * stride, torch.arange(nx) * stride, indexing="ij")
+    origin = torch.stack([bb, yy, xx], -1).reshape(-1, 3).to(device=dev, dtype=torch.int32)
+    org_lq = torch.tensor([[b, 0, 0] for b in range(B)], device=dev, dtype=torch.int32)
+    f_l = net_ext(ops.crop_resize(lq, org_lq, (h, w), size))
+    f_r = net_ext(ops.crop_resize(ref, origin, (h, h), size))
+    # the token outputs are views that skip the CLS row: make the flattened features dense before the kernel
+    cos = ops.cosine_rows(f_l.reshape(B, -1).contiguous(), f_r.reshape(B * n, -1).contiguous(), n)
+    idx = cos.argmax(-1)                                   # device-side index math on a [B, n] tensor (plumbing)
+    sel = origin.view(B, n, 3)[torch.arange(B, device=dev), idx].contiguous()
+    return ops.crop_resize(ref, sel, (h, h), (h, h)), idx, cos
+
+
+# ----------------------------------------------------------------------------------------------- CLIP vision tower
+class _ClipAttn(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.k_proj = nn.Linear(dim, dim)
+        self.v_proj = nn.Linear(dim, dim)
+        self.q_proj = nn.Linear(dim, dim)
+        self.out_proj = nn.Linear(dim, dim)
+
+
+class _ClipLayer(nn.Module):
+    def __init__(self, dim, hidden, eps):
+        super().__init__()
+        self.self_attn = _ClipAttn(dim)
+        self.layer_norm1 = nn.LayerNorm(dim, eps=eps)
+        self.mlp = _Mlp(dim, hidden)
+        self.layer_norm2 = nn.LayerNorm(dim, eps=eps)
+
+
+class _ClipEmbeddings(nn.Module):
+    def __init__(self, dim, patch, image_size):
+        super().__init__()
+        self.class_embedding = nn.Parameter(torch.randn(dim))
+        self.patch_embedding = nn.Conv2d(3, dim, patch, patch, bias=False)
+        self.position_embedding = nn.Embedding((image_size // patch) ** 2 + 1, dim)
+
+
+class _ClipEncoder(nn.Module):
+    def __init__(self, dim, hidden, layers, eps):
+        super().__init__()
+        self.layers = nn.ModuleList([_ClipLayer(dim, hidden, eps) for _ in range(layers)])
+
+
+class _ClipVisionTransformer(nn.Module):
+    def __init__(self, dim, hidden, layers, patch, image_size, eps):
+        super().__init__()
+        self.embeddings = _ClipEmbeddings(dim, patch, image_size)
+        self.pre_layrnorm = nn.LayerNorm(dim, eps=eps)          # (sic) the transformers key name
+        self.encoder = _ClipEncoder(dim, hidden, layers, eps)
+        self.post_layernorm = nn.LayerNorm(dim, eps=eps)
+
+
+class CLIPVisionTower(_Cached):
+    """Defaults = CLIP ViT-H/14 (laion2b), the checkpoint the reference names (main_train_i2t_mapping.py:566)."""
+
+    def __init__(self, hidden_size=1280, intermediate_size=5120, num_hidden_layers=32, num_attention_heads=16,
+                 patch_size=14, image_size=224, layer_norm_eps=1e-5, hidden_act="gelu"):
+        super().__init__()
+        if hidden_act != "gelu":
+            raise TdrError("CLIPVisionTower (B200): only hidden_act='gelu' (ViT-H/14 laion2b) is implemented")
+        self.heads, self.patch, self.dim, self.eps = num_attention_heads, patch_size, hidden_size, layer_norm_eps
+        self.image_size = image_size
+        self.vision_model = _ClipVisionTransformer(hidden_size, intermediate_size, num_hidden_layers, patch_size,
+                                                   image_size, layer_norm_eps)
+
+    def _prepare(self):
+        vm, D = self.vision_model, self.dim
+        P = dict(w_pe=_pack_linear(vm.embeddings.patch_embedding.weight.reshape(D, -1)),
+                 cls=_f(vm.embeddings.class_embedding), pos=_f(vm.embeddings.position_embedding.weight),
+                 pre_w=_f(vm.pre_layrnorm.weight), pre_b=_f(vm.pre_layrnorm.bias), layers=[])
+        for l in vm.encoder.layers:
+            a = l.self_attn
+            P["layers"].append(dict(
+                ln1_w=_f(l.layer_norm1.weight), ln1_b=_f(l.layer_norm1.bias), ln2_w=_f(l.layer_norm2.weight),
+                ln2_b=_f(l.layer_norm2.bias), eps=self.eps,
+                w_qkv=_pack_linear(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)),
+                b_qkv=_f(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0)),
+                w_o=_pack_linear(a.out_proj.weight), b_o=_f(a.out_proj.bias),
+                w_fc1=_pack_linear(l.mlp.fc1.weight), b_fc1=_f(l.mlp.fc1.bias), hidden=l.mlp.fc1.out_features,
+                w_fc2=_pack_linear(l.mlp.fc2.weight), b_fc2=_f(l.mlp.fc2.bias)))
+        return P
+
+    def forward(self, pixel_values, output_hidden_states=False, **unused):
+        self._check(pixel_values)
+        B, _, H, W = pixel_values.shape
+        if H != self.image_size or W != self.image_size:
+            raise ValueError(f"CLIPVisionTower expects {self.image_size}x{self.image_size} inputs (got {H}x{W}); the "
+                             "reference resizes to 224 first (main_train_tr_mapping.py:777-779)")
+        P = self.prepared()
+        tok = embed_patches(pixel_values, P["w_pe"], None, self.patch, self.dim)
+        xs = ops.vit_assemble_tokens(tok, P["cls"], P["pos"])
+        pre = torch.empty_like(xs)
+        ops.rownorm(xs, 1, P["pre_w"], P["pre_b"], self.eps, out_f32=pre, want_bf16=False)
+        for lp in P["layers"]:
+            run_layer(pre, lp, self.heads)
+        last = pre[:, 0]
+        return (last,)            # [0] is last_hidden_state, as the reference indexes it
+
+
+# ----------------------------------------------------------------------------------------------- mappers
+def _mlp_module(inp, out):
+    return nn.Sequential(nn.Linear(inp, 1280), nn.LayerNorm(1280), nn.LeakyReLU(),
+                         nn.Linear(1280, 1280), nn.LayerNorm(1280), nn.LeakyReLU(),
+                         nn.Linear(1280, 1280), nn.LayerNorm(1280), nn.LeakyReLU(),
+                         nn.Linear(1280, out))
+
+
+def _prep_mlp(seq):
+    return [dict(w=_pack_linear(seq[j].weight), b=_f(seq[j].bias), n=seq[j].out_features,
+                 ln_w=_f(seq[j + 1].weight) if j < 9 else None, ln_b=_f(seq[j + 1].bias) if j < 9 else None)
+            for j in (0, 3, 6, 9)]
+
+
+def _run_mlp(x16, layers):
+    """bf16 rows [B,1,T,Cin] -> fp32 [B,1,T,Cout]: (Linear -> LayerNorm -> LeakyReLU) x3 -> Linear."""
+    for l in layers[:3]:
+        y32, _ = ops.conv_gemm(x16, l["w"], l["n"], bias=l["b"], want="f32")
+        x16 = ops.rownorm(y32, 1, l["ln_w"], l["ln_b"], 1e-5, leaky=True)
+    y32, _ = ops.conv_gemm(x16, layers[3]["w"], layers[3]["n"], bias=layers[3]["b"], want="f32")
+    return y32
+
+
+class Mapper(_Cached):
+    def __init__(self, input_dim, output_dim, num_words):
+        super().__init__()
+        self.num_words, self.output_dim = num_words, output_dim
+        for i in range(num_words):
+            setattr(self, f"mapping_{i}", _mlp_module(input_dim, output_dim))
+            setattr(self, f"mapping_patch_{i}", _mlp_module(input_dim, output_dim))
+
+    def _prepare(self):
+        return [(_prep_mlp(getattr(self, f"mapping_{i}")), _prep_mlp(getattr(self, f"mapping_patch_{i}")))
+                for i in range(self.num_words)]
+
+    def forward(self, embs):
+        emb = embs[0]                                          # (:75) the caller passes a tuple/list
+        self._check(emb)
+        P = self.prepared()
+        B, T, D = emb.shape
+        x32 = emb.contiguous().float().view(B, 1, T, D)
+        x16 = ops.rownorm(x32, 0)
+        cls16 = x16[:, 0, 0, :].contiguous().view(1, 1, B, D)  # dense copy of the CLS rows (B x D, plumbing)
+        out = torch.empty((B, self.num_words, self.output_dim), dtype=F32, device=emb.device)
+        x16 = x16.view(1, 1, B * T, D)                         # one flat row-major GEMM view over all tokens
+        for i, (p_cls, p_patch) in enumerate(P):
+            yp = _run_mlp(x16, p_patch).view(B, 1, T, self.output_dim)   # the CLS row is simply not averaged
+            ops.mean_tokens(yp, 1, T - 1, out[:, i, :])
+            yc = _run_mlp(cls16, p_cls).view(B, 1, 1, self.output_dim)
+            ops.mean_tokens(yc, 0, 1, out[:, i, :], accumulate=True)
+        return out
+
+
+class CleanMapper(_Cached):
+    def __init__(self, input_dim, output_dim, num_words):
+        super().__init__()
+        self.num_words, self.output_dim = num_words, output_dim
+        for i in range(num_words):
+            setattr(self, f"mapping_{i}", _mlp_module(input_dim, output_dim))
+
+    def _prepare(self):
+        return [_prep_mlp(getattr(self, f"mapping_{i}")) for i in range(self.num_words)]
+
+    def forward(self, embs):
+        self._check(embs)
+        P = self.prepared()
+        B, Wn, D = embs.shape
+        xw = embs.float().transpose(0, 1).contiguous()         # [words, B, D] (plumbing copy of a [B, 20, 1024] tensor)
+        out = torch.empty((B, self.num_words, self.output_dim), dtype=F32, device=embs.device)
+        for i, layers in enumerate(P):
+            x16 = ops.rownorm(xw[i].view(1, 1, B, D), 0)
+            y = _run_mlp(x16, layers).view(B, 1, 1, self.output_dim)
+            ops.mean_tokens(y, 0, 1, out[:, i, :])
+        return out

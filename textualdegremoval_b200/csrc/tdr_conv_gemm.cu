@@ -49,7 +49,7 @@ struct ConvGemmArgs {
   const float* rowscale;        // [B*OH*OW] or null
   float alpha, res1_scale;
   const float* scale_ptr;       // optional device scalar multiplying alpha and res1_scale
-  int relu;
+  int act;                      // 0 none, 1 ReLU, 2 exact GELU
   const float* res1;  long long res1_ld;
   const void* res2;   long long res2_ld;  int res2_bf16;
   float* out_f32;     long long out_f32_ld;
@@ -64,6 +64,12 @@ struct ConvGemmArgs {
   int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
   int epi_bufs;                 // staging buffers per epilogue warp (1 or 2)
 };
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == 1) return fmaxf(x, 0.f);
+  if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  return x;
+}
 
 // V < 0: generic epilogue (any combination of outputs / residuals / pixel (un)shuffle).
 // V >= 0: TMA epilogue specialised at compile time: bit 0 = fp32 output, bit 1 = res2 tile, bit 2 = res1 tile.
@@ -269,7 +275,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         uint64_t* const rb = rbar + ew * 2;
         constexpr bool has_r2 = kR2, has_r1 = kR1;
         const bool dbuf = a.epi_bufs == 2 && !has_r1;
-        const bool plain = !a.bias && !a.rowscale && !a.relu && alpha == 1.f;
+        const bool plain = !a.bias && !a.rowscale && !a.act && alpha == 1.f;
         const int box_w = a.TW < 32 ? a.TW : 32;                 // pixels per staged image row
         const int tx0 = (r % a.tiles_x) * a.TW + (a.TW > 32 ? quad * 32 : 0);
         const int ty0 = (r / a.tiles_x) * a.TH + (a.TW > 32 ? 0 : quad * (32 / box_w));
@@ -329,7 +335,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                   float x = fmaf(__uint_as_float(raw[q4][i]), rs, bb[i]);
-                  if (a.relu) x = fmaxf(x, 0.f);
+                  x = apply_act(x, a.act);
                   v[i] = x * alpha;
                 }
               }
@@ -403,7 +409,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
               for (int i = 0; i < 16; ++i) {
                 float x = __uint_as_float(raw[j][i]) * rs;
                 if (a.bias && col0 + i < a.Co) x += a.bias[col0 + i];
-                if (a.relu) x = fmaxf(x, 0.f);
+                x = apply_act(x, a.act);
                 v[i] = x * alpha;
               }
               if (direct16) {
@@ -479,7 +485,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
             for (int i = 0; i < 16; ++i) {
               float x = __uint_as_float(raw[i]) * rs;
               if (a.bias && col0 + i < a.Co) x += a.bias[col0 + i];
-              if (a.relu) x = fmaxf(x, 0.f);
+              x = apply_act(x, a.act);
               v[i] = x * alpha;
             }
             if (a.store_mode == 1) {
@@ -541,7 +547,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
 // implicitly.
 // ------------------------------------------------------------------------------------------------
 __global__ void conv_gemm_simt_kernel(const bf16* __restrict__ in, long long in_ld, int H, int W,
-                                      const bf16* __restrict__ w, long long w_ld, const ConvGemmArgs a) {
+                                      const bf16* __restrict__ w, long long w_ld, long long w_bstride,
+                                      const ConvGemmArgs a) {
   const long long total = (long long)a.B * a.OH * a.OW * a.Co;
   const int taps = a.KH * a.KW;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
@@ -559,12 +566,13 @@ __global__ void conv_gemm_simt_kernel(const bf16* __restrict__ in, long long in_
       const int ix = org_x + ox * a.stride - a.pad + (tap % a.KW) * a.dil;
       if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;     // H, W = full image extent (TMA zero-fill rule)
       const bf16* ip = in + (((long long)img * H + iy) * W + ix) * in_ld;
-      const bf16* wp = w + ((long long)((a.w_batched ? b * taps : 0) + tap) * a.Co + co) * w_ld;
+      const bf16* wp = w_bstride ? w + (long long)b * w_bstride + (long long)co * w_ld
+                                 : w + ((long long)((a.w_batched ? b * taps : 0) + tap) * a.Co + co) * w_ld;
       for (int ci = 0; ci < a.Ci; ++ci) acc += __bfloat162float(ip[ci]) * __bfloat162float(wp[ci]);
     }
     float x = acc * (a.rowscale ? a.rowscale[pix] : 1.f);
     if (a.bias) x += a.bias[co];
-    if (a.relu) x = fmaxf(x, 0.f);
+    x = apply_act(x, a.act);
     const float g = a.scale_ptr ? *a.scale_ptr : 1.f;
     x *= a.alpha * g;
     long long row = pix;
@@ -618,7 +626,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   a.B = d->B; a.OH = OH; a.OW = OW; a.Ci = d->Ci; a.Co = d->Co;
   a.KH = d->KH; a.KW = d->KW; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
   a.w_batched = d->w_batched; a.origin = d->origin;
-  a.bias = d->bias; a.rowscale = d->rowscale; a.alpha = d->alpha; a.res1_scale = d->res1_scale; a.scale_ptr = d->scale_ptr; a.relu = d->relu;
+  a.bias = d->bias; a.rowscale = d->rowscale; a.alpha = d->alpha; a.res1_scale = d->res1_scale; a.scale_ptr = d->scale_ptr; a.act = d->act;
   a.res1 = d->res1; a.res1_ld = d->res1_ld; a.res2 = d->res2; a.res2_ld = d->res2_ld; a.res2_bf16 = d->res2_bf16;
   a.out_f32 = d->out_f32; a.out_f32_ld = d->out_f32_ld;
   a.out_bf16 = reinterpret_cast<bf16*>(d->out_bf16); a.out_bf16_ld = d->out_bf16_ld;
@@ -647,12 +655,14 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     a.out_is_f32 = f32o ? 1 : 0;
   }
   if (a.epi_mode == 1) {
-    // N tiles are multiples of the sub-block width (64 bf16 / 32 fp32 columns, <= 256), minimising padding
+    // N tiles are multiples of the sub-block width (64 bf16 / 32 fp32 columns, <= 256).  Cost model: padded columns
+    // plus ~48 columns' worth of fixed work (A re-fetch, pipeline ramp) per extra N tile.
     const int sbc = a.out_is_f32 ? 32 : 64;
-    int best_bn = 256, best_tot = 1 << 30;
+    int best_bn = 256, best_cost = 1 << 30;
     for (int bn = sbc; bn <= 256; bn += sbc) {
-      const int tot = tdr_cdiv(d->Co, bn) * bn;
-      if (tot < best_tot || (tot == best_tot && bn > best_bn)) { best_tot = tot; best_bn = bn; }
+      const int nt = tdr_cdiv(d->Co, bn);
+      const int cost = nt * bn + 48 * nt;
+      if (cost < best_cost || (cost == best_cost && bn > best_bn)) { best_cost = cost; best_bn = bn; }
     }
     if (const char* e = getenv("TDR_CONV_BN")) {                                 // tuning knob (experiments only)
       const int v = atoi(e);
@@ -717,7 +727,8 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     const long long total = (long long)a.B * OH * OW * a.Co;
     const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
     conv_gemm_simt_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(d->in), d->in_ld, img_h, img_w,
-                                                      reinterpret_cast<const bf16*>(d->weight), d->w_ld, a);
+                                                      reinterpret_cast<const bf16*>(d->weight), d->w_ld,
+                                                      d->w_batched ? d->w_batch_stride : 0, a);
     TDR_CHECK_LAUNCH();
     return TDR_OK;
   }
@@ -756,7 +767,12 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   {
     const int taps = d->KH * d->KW;
     const uint64_t dims[3] = {(uint64_t)d->Ci, (uint64_t)d->Co, (uint64_t)taps * (d->w_batched ? d->B : 1)};
-    const uint64_t strides[2] = {(uint64_t)d->w_ld * 2, (uint64_t)d->w_ld * 2 * d->Co};
+    uint64_t tap_stride = (uint64_t)d->w_ld * 2 * d->Co;
+    if (d->w_batched && d->w_batch_stride) {
+      TDR_CHECK_ARG(taps == 1 && d->w_batch_stride % 8 == 0, "tdr_conv_gemm: w_batch_stride needs a 1x1 op and 16 B rows");
+      tap_stride = (uint64_t)d->w_batch_stride * 2;
+    }
+    const uint64_t strides[2] = {(uint64_t)d->w_ld * 2, tap_stride};
     const uint32_t box[3] = {(uint32_t)kChunkK, (uint32_t)a.BN, 1};
     const uint32_t es[3] = {1, 1, 1};
     int rc = tdr_make_tensor_map_bf16(&map_w, d->weight, 3, dims, strides, box, es);

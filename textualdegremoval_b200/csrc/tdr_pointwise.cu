@@ -12,8 +12,9 @@ namespace {
 template <int NV>
 __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ in, long long in_ld, long long rows,
                                                       int C, int mode, const float* __restrict__ w,
-                                                      const float* __restrict__ bvec, float eps,
-                                                      bf16* __restrict__ out, long long out_ld, int G) {
+                                                      const float* __restrict__ bvec, float eps, int act,
+                                                      bf16* __restrict__ out, long long out_ld,
+                                                      float* __restrict__ out32, long long out32_ld, int G) {
   const int lane = threadIdx.x & 31;
   const long long warp_id = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int rpw = 32 / G;
@@ -69,10 +70,17 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
         x.z = x.z * rstd * ww.z;
         x.w = x.w * rstd * ww.w;
       }
-      uint2 pk;
-      pk.x = pack2(x.x, x.y);
-      pk.y = pack2(x.z, x.w);
-      *reinterpret_cast<uint2*>(out + row * out_ld + idx * 4) = pk;
+      if (act == 3) {                   // LeakyReLU(0.01)
+        x.x = x.x > 0.f ? x.x : 0.01f * x.x; x.y = x.y > 0.f ? x.y : 0.01f * x.y;
+        x.z = x.z > 0.f ? x.z : 0.01f * x.z; x.w = x.w > 0.f ? x.w : 0.01f * x.w;
+      }
+      if (out) {
+        uint2 pk;
+        pk.x = pack2(x.x, x.y);
+        pk.y = pack2(x.z, x.w);
+        *reinterpret_cast<uint2*>(out + row * out_ld + idx * 4) = pk;
+      }
+      if (out32) *reinterpret_cast<float4*>(out32 + row * out32_ld + idx * 4) = x;
     }
   }
 }
@@ -462,51 +470,83 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, long long src_ld
 }
 
 // ------------------------------------------------------------------------------------------------ small convs
-// Ci <= 8 input channels (fp32 NHWC), Co % 8 == 0 outputs; weights staged in smem as [ci*9+tap][Co].
+// Ci <= 8 input channels (fp32 NHWC image), Co % 8 == 0 outputs.  A thread owns TWO horizontally adjacent pixels and
+// 16 output channels: the 3x4 input window is loaded once into registers, every weight read from shared memory
+// ([ci*9+tap][Co], broadcast across the warp) feeds two pixels, and each pixel's 16 outputs are stored as 64 B runs.
+template <int CI, int CPT>
 __global__ void __launch_bounds__(256) conv3x3_small_ci_kernel(const float* __restrict__ in, int B, int H, int W,
-                                                               int Ci, const float* __restrict__ weight,
+                                                               const float* __restrict__ weight,
                                                                const float* __restrict__ bias, int Co, int relu,
                                                                float* __restrict__ o32, long long ld32,
                                                                bf16* __restrict__ o16, long long ld16) {
   extern __shared__ float ws[];
-  for (int i = threadIdx.x; i < Co * Ci * 9; i += blockDim.x) {
-    const int co = i / (Ci * 9), r = i % (Ci * 9);       // weight[co][ci][ky][kx] -> ws[(ci*9+tap)*Co + co]
+  for (int i = threadIdx.x; i < Co * CI * 9; i += blockDim.x) {
+    const int co = i / (CI * 9), r = i % (CI * 9);       // weight[co][ci][ky][kx] -> ws[(ci*9+tap)*Co + co]
     ws[r * Co + co] = weight[i];
   }
   __syncthreads();
-  const int ncg = Co >> 3;
-  const long long total = (long long)B * H * W * ncg;
+  const int ncg = Co / CPT;                               // CPT-channel groups (16, or 8 when Co % 16 != 0)
+  const int wp = (W + 1) >> 1;                            // pixel pairs per row
+  const long long total = (long long)B * H * wp * ncg;
   for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total;
        it += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(it % ncg);
-    const long long p = it / ncg;
-    const int x = (int)(p % W);
-    const int y = (int)((p / W) % H);
-    const int b = (int)(p / ((long long)W * H));
-    float acc[8];
+    long long p = it / ncg;
+    const int xp = (int)(p % wp);
+    const int y = (int)((p / wp) % H);
+    const int b = (int)(p / ((long long)wp * H));
+    const int x0 = xp * 2;
+    float win[3][4][CI];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = bias ? bias[cg * 8 + e] : 0.f;
-    for (int tap = 0; tap < 9; ++tap) {
-      const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
-      if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-      const float* ip = in + (((long long)b * H + iy) * W + ix) * Ci;
-      for (int ci = 0; ci < Ci; ++ci) {
-        const float v = ip[ci];
-        const float* wp = ws + (ci * 9 + tap) * Co + cg * 8;
+    for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(v, wp[e], acc[e]);
+      for (int dx = 0; dx < 4; ++dx) {
+        const int iy = y + dy - 1, ix = x0 + dx - 1;
+        const bool ok = iy >= 0 && iy < H && ix >= 0 && ix < W;
+        const float* ip = in + (((long long)b * H + (ok ? iy : 0)) * W + (ok ? ix : 0)) * CI;
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) win[dy][dx][ci] = ok ? __ldg(ip + ci) : 0.f;
+      }
+    float acc[2][CPT];
+#pragma unroll
+    for (int e = 0; e < CPT; ++e) acc[0][e] = acc[1][e] = bias ? bias[cg * CPT + e] : 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float4* wp4 = reinterpret_cast<const float4*>(ws + (ci * 9 + dy * 3 + dx) * Co + cg * CPT);
+          const float v0 = win[dy][dx][ci], v1 = win[dy][dx + 1][ci];
+#pragma unroll
+          for (int q4 = 0; q4 < CPT / 4; ++q4) {
+            const float4 w4 = wp4[q4];
+            acc[0][q4 * 4 + 0] = fmaf(v0, w4.x, acc[0][q4 * 4 + 0]); acc[1][q4 * 4 + 0] = fmaf(v1, w4.x, acc[1][q4 * 4 + 0]);
+            acc[0][q4 * 4 + 1] = fmaf(v0, w4.y, acc[0][q4 * 4 + 1]); acc[1][q4 * 4 + 1] = fmaf(v1, w4.y, acc[1][q4 * 4 + 1]);
+            acc[0][q4 * 4 + 2] = fmaf(v0, w4.z, acc[0][q4 * 4 + 2]); acc[1][q4 * 4 + 2] = fmaf(v1, w4.z, acc[1][q4 * 4 + 2]);
+            acc[0][q4 * 4 + 3] = fmaf(v0, w4.w, acc[0][q4 * 4 + 3]); acc[1][q4 * 4 + 3] = fmaf(v1, w4.w, acc[1][q4 * 4 + 3]);
+          }
+        }
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      if (x0 + px >= W) continue;
+      const long long pix = ((long long)b * H + y) * W + x0 + px;
+      if (relu) {
+#pragma unroll
+        for (int e = 0; e < CPT; ++e) acc[px][e] = fmaxf(acc[px][e], 0.f);
+      }
+      if (o32) {
+        float4* q = reinterpret_cast<float4*>(o32 + pix * ld32 + cg * CPT);
+#pragma unroll
+        for (int q4 = 0; q4 < CPT / 4; ++q4)
+          q[q4] = make_float4(acc[px][q4 * 4], acc[px][q4 * 4 + 1], acc[px][q4 * 4 + 2], acc[px][q4 * 4 + 3]);
+      }
+      if (o16) {
+#pragma unroll
+        for (int q8 = 0; q8 < CPT / 8; ++q8)
+          *reinterpret_cast<bf16x8*>(o16 + pix * ld16 + cg * CPT + q8 * 8) = pack8(acc[px] + q8 * 8);
       }
     }
-    if (relu) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f);
-    }
-    if (o32) {
-      float4* q = reinterpret_cast<float4*>(o32 + p * ld32 + cg * 8);
-      q[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      q[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    }
-    if (o16) *reinterpret_cast<bf16x8*>(o16 + p * ld16 + cg * 8) = pack8(acc);
   }
 }
 
@@ -575,9 +615,12 @@ inline int grid_for(long long items, int per_block, int max_waves = 8) {
 }  // namespace
 
 extern "C" int tdr_rownorm(const float* in, long long in_ld, long long rows, int C, int mode, const float* weight,
-                           const float* bias, float eps, void* out_bf16, long long out_ld, cudaStream_t stream) {
-  TDR_CHECK_ARG(in && out_bf16 && rows >= 0 && C > 0, "tdr_rownorm: bad arguments");
-  TDR_CHECK_ARG(C % 4 == 0 && in_ld % 4 == 0 && out_ld % 4 == 0, "tdr_rownorm: C and strides must be multiples of 4");
+                           const float* bias, float eps, int act, void* out_bf16, long long out_ld, float* out_f32,
+                           long long out_f32_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(in && (out_bf16 || out_f32) && rows >= 0 && C > 0, "tdr_rownorm: bad arguments");
+  TDR_CHECK_ARG(C % 4 == 0 && in_ld % 4 == 0 && out_ld % 4 == 0 && out_f32_ld % 4 == 0,
+                "tdr_rownorm: C and strides must be multiples of 4");
+  TDR_CHECK_ARG(act == 0 || act == 3, "tdr_rownorm: act must be 0 or 3 (LeakyReLU)");
   TDR_CHECK_ARG(mode >= 0 && mode <= 2, "tdr_rownorm: bad mode");
   TDR_CHECK_ARG(mode == 0 || weight, "tdr_rownorm: weight required");
   TDR_CHECK_ARG(C <= 4096, "tdr_rownorm: C too large (%d)", C);
@@ -591,7 +634,8 @@ extern "C" int tdr_rownorm(const float* in, long long in_ld, long long rows, int
   const long long warps = (rows + (32 / G) - 1) / (32 / G);
   const int blocks = (int)((warps + 7) / 8);
   bf16* o = reinterpret_cast<bf16*>(out_bf16);
-#define TDR_RN(NV) rownorm_kernel<NV><<<blocks, 256, 0, stream>>>(in, in_ld, rows, C, mode, weight, bias, eps, o, out_ld, G)
+#define TDR_RN(NV) \
+  rownorm_kernel<NV><<<blocks, 256, 0, stream>>>(in, in_ld, rows, C, mode, weight, bias, eps, act, o, out_ld, out_f32, out_f32_ld, G)
   if (nv <= 1) TDR_RN(1);
   else if (nv <= 2) TDR_RN(2);
   else if (nv <= 3) TDR_RN(3);
@@ -699,11 +743,26 @@ extern "C" int tdr_conv3x3_small_ci(const float* in, int B, int H, int W, int Ci
                                     const float* bias, int Co, int relu, float* out_f32, long long out_f32_ld,
                                     void* out_bf16, long long out_bf16_ld, cudaStream_t stream) {
   TDR_CHECK_ARG(in && weight && (out_f32 || out_bf16), "tdr_conv3x3_small_ci: null pointer");
-  TDR_CHECK_ARG(Ci >= 1 && Ci <= 8 && Co % 8 == 0 && Co * Ci * 9 * 4 <= 48 * 1024, "tdr_conv3x3_small_ci: bad channels");
+  TDR_CHECK_ARG(Ci >= 1 && Ci <= 8 && Co % 8 == 0 && Co * Ci * 9 * 4 <= 48 * 1024,
+                "tdr_conv3x3_small_ci: need 1 <= Ci <= 8 and Co %% 8 == 0 (got Ci=%d Co=%d)", Ci, Co);
   TDR_CHECK_ARG(out_f32_ld % 4 == 0 && out_bf16_ld % 8 == 0, "tdr_conv3x3_small_ci: bad strides");
-  const long long items = (long long)B * H * W * (Co / 8);
-  conv3x3_small_ci_kernel<<<grid_for(items, 256, 8), 256, Co * Ci * 9 * sizeof(float), stream>>>(
-      in, B, H, W, Ci, weight, bias, Co, relu, out_f32, out_f32_ld, reinterpret_cast<bf16*>(out_bf16), out_bf16_ld);
+  const int cpt = Co % 16 == 0 ? 16 : 8;
+  const long long items = (long long)B * H * ((W + 1) / 2) * (Co / cpt);
+  const size_t smem = (size_t)Co * Ci * 9 * sizeof(float);
+  bf16* o16 = reinterpret_cast<bf16*>(out_bf16);
+#define TDR_SCI(N)                                                                                                   \
+  case N:                                                                                                            \
+    if (cpt == 16)                                                                                                   \
+      conv3x3_small_ci_kernel<N, 16><<<grid_for(items, 256, 8), 256, smem, stream>>>(                                \
+          in, B, H, W, weight, bias, Co, relu, out_f32, out_f32_ld, o16, out_bf16_ld);                               \
+    else                                                                                                             \
+      conv3x3_small_ci_kernel<N, 8><<<grid_for(items, 256, 8), 256, smem, stream>>>(                                 \
+          in, B, H, W, weight, bias, Co, relu, out_f32, out_f32_ld, o16, out_bf16_ld);                               \
+    break
+  switch (Ci) {
+    TDR_SCI(1); TDR_SCI(2); TDR_SCI(3); TDR_SCI(4); TDR_SCI(5); TDR_SCI(6); TDR_SCI(7); TDR_SCI(8);
+  }
+#undef TDR_SCI
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -22,12 +22,13 @@ class ConvGemmDesc(C.Structure):
         ("weight", C.c_void_p), ("w_ld", C.c_longlong),
         ("Co", C.c_int), ("KH", C.c_int), ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("dil", C.c_int),
         ("w_batched", C.c_int),
+        ("w_batch_stride", C.c_longlong),
         ("origin", C.c_void_p),
         ("n_images", C.c_int), ("img_h", C.c_int), ("img_w", C.c_int),
         ("bias", C.c_void_p), ("rowscale", C.c_void_p),
         ("alpha", C.c_float),
         ("scale_ptr", C.c_void_p),
-        ("relu", C.c_int),
+        ("act", C.c_int),
         ("res1", C.c_void_p), ("res1_ld", C.c_longlong), ("res1_scale", C.c_float),
         ("res2", C.c_void_p), ("res2_ld", C.c_longlong), ("res2_bf16", C.c_int),
         ("out_f32", C.c_void_p), ("out_f32_ld", C.c_longlong),
@@ -47,7 +48,7 @@ SIGNATURES = {
     "tdr_conv_gemm_desc_layout": (None, [C.POINTER(_i)]),
     "tdr_conv3x3_small_ci": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_conv3x3_small_co": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
-    "tdr_rownorm": (_i, [_vp, _ll, _ll, _i, _i, _vp, _vp, _f, _vp, _ll, _vp]),
+    "tdr_rownorm": (_i, [_vp, _ll, _ll, _i, _i, _vp, _vp, _f, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_dwconv3x3": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _vp]),
     "tdr_gate_mul": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp]),
     "tdr_naf_sca_workspace_bytes": (_sz, [_i, _ll, _i]),
@@ -55,6 +56,13 @@ SIGNATURES = {
     "tdr_mdta_partials_bytes": (_sz, [_i, _ll, _i, _i]),
     "tdr_mdta_gram": (_i, [_vp, _ll, _i, _ll, _i, _i, _vp, _vp]),
     "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp]),
+    "tdr_vit_patchify": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
+    "tdr_vit_assemble_tokens": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tdr_softmax_rows": (_i, [_vp, _ll, _ll, _i, _f, _vp, _ll, _vp]),
+    "tdr_vit_transpose_v": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "tdr_crop_resize": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "tdr_cosine_rows": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp]),
+    "tdr_mean_tokens": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _ll, _i, _vp]),
     "tdr_nchw_to_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_nhwc_to_nchw": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _vp]),
     "tdr_copy_rows_f32": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp, _ll, _vp]),

@@ -123,12 +123,12 @@ def pack_dw_weight(w: torch.Tensor, n=None, idx=None) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------- ops
-def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, relu=False, rowscale=None,
+def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, relu=False, gelu=False, rowscale=None,
               alpha=1.0, scale_ptr=None, res1=None, res1_scale=1.0, res2=None, out_f32=None, out_bf16=None,
-              want="bf16", store_mode=0, w_batched=False, origin=None, window=None, impl=0):
+              want="bf16", store_mode=0, w_batched=False, w_raw=None, origin=None, window=None, impl=0):
     """x: bf16 NHWC view.  wpack: bf16 [T, Co_p, Ci_p].  Returns (out_f32, out_bf16) -- allocated if not given
     according to ``want`` in {"bf16", "f32", "both"}."""
-    assert x.dtype == BF16 and wpack.dtype == BF16
+    assert x.dtype == BF16 and (w_raw is not None or wpack.dtype == BF16)
     B, H, W, Cx = x.shape
     Ci = Cx if Ci is None else Ci
     d = lib.ConvGemmDesc()
@@ -140,17 +140,22 @@ def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, 
     else:
         d.B = B; d.H = H; d.W = W
     d.Ci = Ci
-    d.weight = wpack.data_ptr(); d.w_ld = wpack.shape[2]
-    assert wpack.shape[1] >= Co and wpack.shape[2] >= Ci and wpack.is_contiguous()
-    # the weight tensor map uses Co as the row extent and w_ld*Co as the tap stride
-    assert wpack.shape[1] == Co, f"packed weight rows {wpack.shape[1]} != Co {Co}"
+    if w_raw is not None:
+        # raw per-sample weights living inside another tensor: (data_ptr, row stride, batch stride) in elements
+        d.weight, d.w_ld, d.w_batch_stride = w_raw
+        assert w_batched and k == 1
+    else:
+        d.weight = wpack.data_ptr(); d.w_ld = wpack.shape[2]
+        assert wpack.shape[1] >= Co and wpack.shape[2] >= Ci and wpack.is_contiguous()
+        # the weight tensor map uses Co as the row extent and w_ld*Co as the tap stride
+        assert wpack.shape[1] == Co, f"packed weight rows {wpack.shape[1]} != Co {Co}"
     d.Co = Co; d.KH = k; d.KW = k; d.stride = stride; d.pad = pad; d.dil = dil
     d.w_batched = int(w_batched)
     d.bias = bias.data_ptr() if bias is not None else None
     d.rowscale = rowscale.data_ptr() if rowscale is not None else None
     d.alpha = alpha
     d.scale_ptr = scale_ptr.data_ptr() if scale_ptr is not None else None
-    d.relu = int(relu)
+    d.act = 2 if gelu else int(relu)
     nB, nH, nW = d.B, d.H, d.W
     OH = (nH + 2 * pad - dil * (k - 1) - 1) // stride + 1
     OW = (nW + 2 * pad - dil * (k - 1) - 1) // stride + 1
@@ -188,15 +193,16 @@ def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, 
     return out_f32, out_bf16
 
 
-def rownorm(x32, mode, weight=None, bias=None, eps=1e-5, out=None):
-    """fp32 NHWC view -> bf16 NHWC.  mode 0 cast, 1 WithBias LN, 2 BiasFree LN."""
+def rownorm(x32, mode, weight=None, bias=None, eps=1e-5, out=None, leaky=False, out_f32=None, want_bf16=True):
+    """fp32 NHWC view -> bf16 NHWC (and/or fp32).  mode 0 cast, 1 WithBias LN, 2 BiasFree LN; leaky: LeakyReLU(0.01)."""
     assert x32.dtype == F32
     B, H, W, Cc = x32.shape
-    if out is None:
+    if out is None and want_bf16:
         out = torch.empty((B, H, W, Cc), dtype=BF16, device=x32.device)
-    _call("tdr_rownorm", _p(x32), _ld(x32), B * H * W, Cc, mode, _p(weight), _p(bias), eps, _p(out), _ld(out),
-          _stream(), tag=f"m{mode}_C{Cc}", nbytes=B * H * W * Cc * 6)
-    return out
+    _call("tdr_rownorm", _p(x32), _ld(x32), B * H * W, Cc, mode, _p(weight), _p(bias), eps, 3 if leaky else 0, _p(out),
+          _ld(out) if out is not None else 0, _p(out_f32), _ld(out_f32) if out_f32 is not None else 0, _stream(),
+          tag=f"m{mode}_C{Cc}", nbytes=B * H * W * Cc * (4 + (2 if out is not None else 0) + (4 if out_f32 is not None else 0)))
+    return out if out is not None else out_f32
 
 
 def dwconv3x3(x, w9, bias=None, gate=0, out=None):
@@ -368,3 +374,62 @@ def masa_transfer(f_ref, origin, index, att, py, px, k_y, k_x, d_x, s, out32=Non
           _p(out32), _ld(out32) if out32 is not None else 0, _p(out16), _ld(out16) if out16 is not None else 0,
           _stream(), tag=f"s{s}_C{Cc}",
           nbytes=npx * Cc * (2 + (4 if out32 is not None else 0) + (2 if out16 is not None else 0)))
+
+
+# ---------------------------------------------------------------------------------------------- ViT glue
+def vit_patchify(img, patch):
+    img = img.contiguous().float()
+    B, Cc, H, W = img.shape
+    K = Cc * patch * patch
+    n = (H // patch) * (W // patch)
+    out = torch.zeros((B, 1, n, round_up(K, 8)), dtype=BF16, device=img.device)
+    _call("tdr_vit_patchify", _p(img), B, Cc, H, W, patch, _p(out), out.shape[3], _stream())
+    return out
+
+
+def vit_assemble_tokens(patch_tokens, cls, pos):
+    B, _, N, D = patch_tokens.shape
+    x = torch.empty((B, 1, N + 1, D), dtype=F32, device=patch_tokens.device)
+    _call("tdr_vit_assemble_tokens", _p(patch_tokens), _p(cls), _p(pos), B, N, D, _p(x), _stream())
+    return x
+
+
+def softmax_rows(s32, n, scale, out16):
+    rows = s32.numel() // s32.shape[-1]
+    _call("tdr_softmax_rows", _p(s32), s32.shape[-1], rows, n, scale, _p(out16), out16.shape[-1], _stream(),
+          nbytes=rows * n * 6)
+    return out16
+
+
+def vit_transpose_v(qkv, heads, hd, voff, n_pad):
+    B, _, N, _ = qkv.shape
+    vt = torch.empty((B, heads, hd, n_pad), dtype=BF16, device=qkv.device)
+    _call("tdr_vit_transpose_v", _p(qkv), _ld(qkv), B, N, heads, hd, voff, _p(vt), n_pad, _stream())
+    return vt
+
+
+def mean_tokens(x32, t0, n, out, accumulate=False):
+    """x32 fp32 [B,1,T,C]; out fp32 [B, C] view (row stride out.stride(0))."""
+    B, _, T, Cc = x32.shape
+    _call("tdr_mean_tokens", _p(x32), _ld(x32), B, T, t0, n, Cc, _p(out), out.stride(0), int(accumulate), _stream())
+    return out
+
+
+def crop_resize(img, origin, crop_hw, out_hw):
+    """img NCHW fp32; origin int32 [n, 3] = (image, y0, x0) on device -> [n, C, oh, ow] fp32 (bilinear)."""
+    img = img.contiguous().float()
+    _, Cc, H, W = img.shape
+    n = origin.shape[0]
+    out = torch.empty((n, Cc, out_hw[0], out_hw[1]), dtype=F32, device=img.device)
+    _call("tdr_crop_resize", _p(img), Cc, H, W, _p(origin), n, crop_hw[0], crop_hw[1], out_hw[0], out_hw[1], _p(out),
+          _stream())
+    return out
+
+
+def cosine_rows(fl, fr, n):
+    """fl fp32 [B, F], fr fp32 [B*n, F] (both dense) -> cos fp32 [B, n]."""
+    assert fl.is_contiguous() and fr.is_contiguous() and fl.dtype == F32 and fr.dtype == F32
+    B, Fdim = fl.shape[0], fl.numel() // fl.shape[0]
+    out = torch.empty((B, n), dtype=F32, device=fl.device)
+    _call("tdr_cosine_rows", _p(fl), _p(fr), B, n, Fdim, _p(out), _stream())
+    return out
