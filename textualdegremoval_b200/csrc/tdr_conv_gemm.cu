@@ -333,10 +333,19 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                   bb[i4 * 4] = t.x; bb[i4 * 4 + 1] = t.y; bb[i4 * 4 + 2] = t.z; bb[i4 * 4 + 3] = t.w;
                 }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                  float x = fmaf(__uint_as_float(raw[q4][i]), rs, bb[i]);
-                  x = apply_act(x, a.act);
-                  v[i] = x * alpha;
+                for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(raw[q4][i]), rs, bb[i]);
+                // activation switch hoisted out of the element loop (GELU's erf must not be if-converted into
+                // every element of the ReLU / linear paths)
+                if (a.act == 1) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                } else if (a.act == 2) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], 2);
+                }
+                if (alpha != 1.f) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] *= alpha;
                 }
               }
               if constexpr (kF32) {
@@ -409,9 +418,17 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
               for (int i = 0; i < 16; ++i) {
                 float x = __uint_as_float(raw[j][i]) * rs;
                 if (a.bias && col0 + i < a.Co) x += a.bias[col0 + i];
-                x = apply_act(x, a.act);
-                v[i] = x * alpha;
+                v[i] = x;
               }
+              if (a.act == 1) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+              } else if (a.act == 2) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], 2);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= alpha;
               if (direct16) {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
@@ -485,9 +502,17 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
             for (int i = 0; i < 16; ++i) {
               float x = __uint_as_float(raw[i]) * rs;
               if (a.bias && col0 + i < a.Co) x += a.bias[col0 + i];
-              x = apply_act(x, a.act);
-              v[i] = x * alpha;
+              v[i] = x;
             }
+            if (a.act == 1) {
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            } else if (a.act == 2) {
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], 2);
+            }
+  #pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= alpha;
             if (a.store_mode == 1) {
               // PixelUnshuffle(2): out[b, oy/2, ox/2, co*4 + (oy&1)*2 + (ox&1)]
               const long long row = ((long long)b * (a.OH >> 1) + (oy >> 1)) * (a.OW >> 1) + (ox >> 1);
