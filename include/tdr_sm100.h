@@ -166,6 +166,20 @@ int tdr_mean_tokens(const float* x, long long ld, int B, int tokens_per_b, int t
                     long long out_ld, int accumulate, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Optimizer tail of the DDP step on flat fp32 buffers (models/image_restoration_ref_model.py:276-284,
+ * models/base_model.py:54-62).  No host synchronisation: the clip coefficient stays on the device.
+ * ------------------------------------------------------------------------------------------------------------- */
+int tdr_sumsq_partial_count(void); /* number of floats tdr_sumsq_partial writes */
+int tdr_sumsq_partial(const float* g, long long n, float* partial, cudaStream_t stream);
+/* out2[0] = min(1, max_norm / (grad_scale * sqrt(sum partial) + 1e-6)), out2[1] = total norm (clip_grad_norm_) */
+int tdr_clip_coef(const float* partial, int n, float max_norm, float grad_scale, float* out2, cudaStream_t stream);
+/* torch.optim.AdamW semantics on grad_scale * clip_coef[0] * g (clip_coef may be NULL); step >= 1 */
+int tdr_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, float grad_scale, const float* clip_coef,
+                   cudaStream_t stream);
+int tdr_ema_update(float* ema, const float* p, long long n, float decay, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Layout / copies.
  * ------------------------------------------------------------------------------------------------------------- */
 int tdr_nchw_to_nhwc(const float* src, int B, int C, int H, int W, int pad_h, int pad_w /* zero-padded output size */,

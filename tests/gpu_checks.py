@@ -545,6 +545,38 @@ def check_vit():
     return out
 
 
+def check_optim():
+    """Fused clip + AdamW (+EMA) tail on flat buffers vs torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW."""
+    from textualdegremoval_b200.ddp import DDPStep
+    out = []
+    torch.manual_seed(3)
+    shapes = {"a.weight": (33, 17), "masa_x.weight": (65,), "b.bias": (129, 3), "masa_y.weight": (7, 7, 3)}
+    ps = {k: torch.nn.Parameter(torch.randn(*s, device=DEV)) for k, s in shapes.items()}
+    ref = {k: torch.nn.Parameter(p.detach().clone()) for k, p in ps.items()}
+    opt = torch.optim.AdamW([dict(params=[ref[k] for k in shapes if "masa" not in k], lr=2e-4),
+                             dict(params=[ref[k] for k in shapes if "masa" in k], lr=1e-4)],
+                            lr=2e-4, weight_decay=1e-4, betas=(0.9, 0.999))
+    eng = DDPStep(ps.items(), lr=2e-4, ref_lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), max_grad_norm=0.01,
+                  ema_decay=0.999)
+    ema_ref = {k: p.detach().clone() for k, p in ref.items()}
+    for step in range(4):
+        for k in shapes:
+            g = torch.randn(*shapes[k], device=DEV) * (0.5 if step % 2 else 1e-4)     # clipped and unclipped steps
+            ps[k].grad.copy_(g)
+            ref[k].grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(list(ref.values()), 0.01)
+        opt.step()
+        eng.step()
+        for k in shapes:
+            ema_ref[k].mul_(0.999).add_(ref[k].detach(), alpha=0.001)
+    for k in shapes:
+        out.append(result(f"adamw_{k}", ps[k].detach(), ref[k].detach(), 2e-6))
+    ema = torch.cat([e[:g.n] for e, g in zip(eng.ema, eng.groups)])
+    order = [k for k in shapes if "masa" not in k] + [k for k in shapes if "masa" in k]
+    out.append(result("ema", ema, torch.cat([ema_ref[k].reshape(-1) for k in order]), 2e-6))
+    return out
+
+
 def check_guided_stages():
     """Guided net stage by stage against the oracle (features, match indices, warps, output)."""
     from oracle import restormer as O, weights as Wt
@@ -594,6 +626,7 @@ CHECKS = {
     "guided_golden": check_guided_golden,
     "nafnet": check_nafnet,
     "vit": check_vit,
+    "optim": check_optim,
 }
 
 

@@ -1,0 +1,148 @@
+"""DDP training-step tail: flat gradient buffers, bucketed all-reduce, global-norm clip, AdamW over
+the reference's two LR groups, EMA, asynchronous loss reduction.
+
+Reference behaviour being replaced (all in /root/reference):
+  * ``models/base_model.py:76-82``  -- ``DistributedDataParallel`` (c10d 25 MB buckets, mean all-reduce of fp32 grads);
+  * ``models/image_restoration_ref_model.py:149-181`` -- two optimizer groups split on the substring ``"masa"`` in the
+    parameter name (``lr`` / ``ref_lr``), AdamW with ``weight_decay`` and ``betas``;
+  * ``:276-281`` -- ``clip_grad_norm_(net_g.parameters(), 0.01)`` when ``use_grad_clip``, ``optimizer.step()``,
+    ``reduce_loss_dict`` (``base_model.py:353-378``: ``dist.reduce`` to rank 0 + ``.item()`` EVERY step);
+  * ``base_model.py:54-62`` -- EMA of the parameters.
+
+Here: every parameter (and its ``.grad``) of a group is a view into ONE contiguous fp32 buffer, so
+  - the gradient exchange is ``torch.distributed.all_reduce`` (NCCL over NVLink on the B200 box, gloo in the CPU tests)
+    over fixed 25 MB slices of that buffer, issued asynchronously on the process group's stream;
+  - clip + AdamW (+ EMA) are three flat CUDA kernels (csrc/tdr_optim.cu) that read the clip coefficient from device
+    memory -- the step never synchronises with the host; the loss is reduced with an async ``dist.reduce`` and only
+    read when the caller asks (``print_freq``).
+The 1/world averaging is folded into the optimizer kernel (``grad_scale``) instead of a separate pass.
+"""
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from . import lib
+
+F32 = torch.float32
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class FlatGroup:
+    """One optimizer group whose parameters / gradients are views into flat buffers."""
+
+    def __init__(self, params, lr):
+        self.params = list(params)
+        self.lr = lr
+        n = sum(p.numel() for p in self.params)
+        n_pad = (n + 3) // 4 * 4
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.n = n
+        self.flat = torch.zeros(n_pad, dtype=F32, device=dev)
+        self.grad = torch.zeros(n_pad, dtype=F32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+
+
+def split_param_groups(named_params, lr, ref_lr):
+    """The reference's grouping rule (image_restoration_ref_model.py:149-158): names containing ``masa`` -> ref_lr."""
+    normal, ref = [], []
+    for name, p in named_params:
+        (ref if "masa" in name else normal).append(p)
+    return [g for g in (FlatGroup(normal, lr) if normal else None, FlatGroup(ref, ref_lr) if ref else None) if g]
+
+
+class DDPStep:
+    """all-reduce -> clip -> AdamW -> (EMA).  ``process_group=None`` and world size 1 make it a single-GPU step."""
+
+    def __init__(self, named_params, lr, ref_lr, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=0.01,
+                 use_grad_clip=True, bucket_bytes=25 * 1024 * 1024, ema_decay=0.0, process_group=None):
+        self.groups = split_param_groups(list(named_params), lr, ref_lr)
+        self.weight_decay, self.betas, self.eps = weight_decay, betas, eps
+        self.max_grad_norm, self.use_grad_clip = max_grad_norm, use_grad_clip
+        self.bucket_elems = max(1, bucket_bytes // 4)
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.step_count = 0
+        self.ema_decay = ema_decay
+        self.ema = [g.flat.clone() for g in self.groups] if ema_decay > 0 else None
+        self._loss_work = None
+        dev = self.groups[0].flat.device
+        self._on_cuda = dev.type == "cuda"
+        if self._on_cuda:
+            nb = lib.load().tdr_sumsq_partial_count()
+            self._partials = torch.zeros(nb * len(self.groups), dtype=F32, device=dev)
+            self._clip = torch.ones(2, dtype=F32, device=dev)
+
+    # ---- gradient exchange ---------------------------------------------------------------------------------------
+    def buckets(self):
+        """(group index, start, end) slices of the flat gradient buffers, <= bucket_bytes each, in REVERSE order (the
+        last layers' gradients are produced first by backward)."""
+        out = []
+        for gi, g in enumerate(self.groups):
+            for s in range(0, g.n, self.bucket_elems):
+                out.append((gi, s, min(g.n, s + self.bucket_elems)))
+        return out[::-1]
+
+    def all_reduce_gradients(self):
+        """SUM all-reduce of every bucket (async); averaging is folded into the optimizer kernel."""
+        if self.world == 1:
+            return []
+        works = []
+        for gi, s, e in self.buckets():
+            works.append(dist.all_reduce(self.groups[gi].grad[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        return works
+
+    # ---- optimizer tail ------------------------------------------------------------------------------------------
+    def step(self, works=()):
+        for w in works:
+            w.wait()                      # stream-level wait on NCCL; does not block the host for CUDA tensors
+        self.step_count += 1
+        scale = 1.0 / self.world
+        if not self._on_cuda:
+            raise lib.TdrError("DDPStep.step: the fused clip/AdamW kernels run on CUDA tensors only")
+        clip_ptr = None
+        if self.use_grad_clip:
+            nb = lib.load().tdr_sumsq_partial_count()
+            for gi, g in enumerate(self.groups):
+                lib.call("tdr_sumsq_partial", C.c_void_p(g.grad.data_ptr()), g.n,
+                         C.c_void_p(self._partials.data_ptr() + gi * nb * 4), _stream())
+            lib.call("tdr_clip_coef", C.c_void_p(self._partials.data_ptr()), nb * len(self.groups), self.max_grad_norm,
+                     scale, C.c_void_p(self._clip.data_ptr()), _stream())
+            clip_ptr = C.c_void_p(self._clip.data_ptr())
+        for g in self.groups:
+            lib.call("tdr_adamw_step", C.c_void_p(g.flat.data_ptr()), C.c_void_p(g.grad.data_ptr()),
+                     C.c_void_p(g.m.data_ptr()), C.c_void_p(g.v.data_ptr()), g.n, g.lr, self.betas[0], self.betas[1],
+                     self.eps, self.weight_decay, self.step_count, scale, clip_ptr, _stream())
+        if self.ema is not None:
+            for g, e in zip(self.groups, self.ema):
+                lib.call("tdr_ema_update", C.c_void_p(e.data_ptr()), C.c_void_p(g.flat.data_ptr()), g.n, self.ema_decay,
+                         _stream())
+
+    def zero_grad(self):
+        for g in self.groups:
+            g.grad.zero_()
+
+    # ---- loss logging (base_model.py:353-378 without the per-step .item()) ------------------------------------------
+    def reduce_loss_async(self, loss):
+        self._loss = loss.detach().clone().reshape(1)
+        self._loss_work = dist.reduce(self._loss, dst=0, group=self.pg, async_op=True) if self.world > 1 else None
+
+    def read_loss(self):
+        """Host read (synchronises): call every print_freq iterations, not every step."""
+        if self._loss_work is not None:
+            self._loss_work.wait()
+        return float(self._loss.item()) / self.world
+
+    def grad_norm(self):
+        return float(self._clip[1].item())
