@@ -136,6 +136,7 @@ int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long long P, int C,
                   cudaStream_t stream);
 int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature /* [heads] */,
                   const float* w_out /* fp32 [C][C] */, void* weff_bf16, long long weff_ld, float* attn_ws,
+                  void* weff_t_bf16 /* optional: Weff[b]^T, same ld (the dgrad operand of the training step) */,
                   cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -178,6 +179,75 @@ int tdr_adamw_step(float* p, const float* g, float* m, float* v, long long n, fl
                    float eps, float weight_decay, int step, float grad_scale, const float* clip_coef,
                    cudaStream_t stream);
 int tdr_ema_update(float* ema, const float* p, long long n, float decay, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Backward kernels (training step).  The reference obtains every gradient from autograd over stock PyTorch ops
+ * (`l_total.backward()` models/image_restoration_ref_model.py:268-275); the data gradients of convolutions are
+ * tdr_conv_gemm / tdr_dwconv3x3 calls with transposed + flipped weights, everything else is below.
+ * Reductions are two-stage and deterministic; `accumulate` != 0 adds into the destination (gradient accumulation).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* Weight gradient of a dense convolution (tcgen05, contraction over pixels):
+ *   dW[co][ci][ky][kx] = sum_{b,y,x} dy[b,y,x,co] * x[b, y*stride + ky*dil - pad, x*stride + kx*dil - pad, ci]
+ * out[b*out_stride_b + map(co)*out_stride_co + map(ci)*out_stride_ci + tap*out_stride_tap] (+)= scale * dW; with
+ * per_sample != 0 one result per batch sample (the per-sample Weff of MDTA R:272-276), else summed over the batch.
+ * co_map / ci_map: optional DEVICE int32 maps from the (padded) kernel channel to the parameter channel, -1 = skip. */
+typedef struct tdr_wgrad_desc {
+  const void* dy; /* bf16 [B, OH, OW, dy_ld], channels [0, Co) */
+  long long dy_ld;
+  const void* x; /* bf16 [B, H, W, x_ld], channels [0, Ci) */
+  long long x_ld;
+  int B, H, W, Ci, Co, KH, KW, stride, pad, dil;
+  int per_sample;
+  float* out;
+  long long out_stride_b, out_stride_co, out_stride_ci, out_stride_tap;
+  const int* co_map;
+  const int* ci_map;
+  int accumulate;
+  float scale;
+  float* workspace; /* tdr_wgrad_workspace_bytes(d) */
+  size_t workspace_bytes;
+} tdr_wgrad_desc;
+size_t tdr_wgrad_workspace_bytes(const tdr_wgrad_desc* d);
+int tdr_wgrad(const tdr_wgrad_desc* d, cudaStream_t stream);
+/* workspace (bytes) large enough for tdr_colsum / tdr_dwconv3x3_wgrad / tdr_rownorm_bwd / tdr_dot_f32 on C channels */
+size_t tdr_reduce_workspace_bytes(int C);
+/* out[map(c) * out_stride] (+)= sum_rows x[r, c]   (bias gradients) */
+int tdr_colsum(const void* x_bf16, long long ld, long long rows, int C, float* out, long long out_stride,
+               const int* c_map, int accumulate, float* workspace, cudaStream_t stream);
+/* depthwise 3x3 (pad 1) weight and bias gradient: dw fp32 [C_param][9] (= nn.Conv2d weight [C,1,3,3]), db [C_param] or NULL */
+int tdr_dwconv3x3_wgrad(const void* dy_bf16, long long dy_ld, const void* x_bf16, long long x_ld, int B, int H, int W,
+                        int C, float* dw, float* db, const int* c_map, int accumulate, float* workspace,
+                        cudaStream_t stream);
+/* Backward of tdr_rownorm (same modes): dx[r,:] = (add ? add[r,:] : 0) + d/dx( norm(x)[r,:] . dy[r,:] ), fp32;
+ * dweight / dbias (+)= column sums (either may be NULL; workspace needed when dweight != NULL).  dx may alias add. */
+int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf16, long long dy_ld, long long rows, int C, int mode,
+                    const float* weight, float eps, const float* add, long long add_ld, float* dx, long long dx_ld,
+                    float* dweight, float* dbias, int accumulate, float* workspace, cudaStream_t stream);
+/* Gate backward.  y = pre-gate depthwise output [rows, 2*Ch] (a | b), dg = gradient of the gated product [rows, Ch]:
+ * gate 1 (GDFN, gelu(a)*b R:238-239): dy = [dg*b*gelu'(a) | dg*gelu(a)];  gate 2 (SimpleGate): dy = [dg*b | dg*a].
+ * dy may alias y. */
+int tdr_gate_bwd(const void* y_bf16, long long y_ld, const void* dg_bf16, long long dg_ld, long long rows, int Ch,
+                 int gate, void* dy_bf16, long long dy_ld, cudaStream_t stream);
+/* Backward of the MDTA score path R:266-276 given dWeff (per-sample tdr_wgrad of the attn.v.project_out product):
+ * dW_out (+)=, dtemperature (+)=, and mqk[b] = the [2C x 2C] matrix with [dq; dk] = mqk[b] . [q; k] per pixel (softmax,
+ * temperature and F.normalize backward folded; bf16 [B][2C][mqk_ld], rows beyond 2C / pad columns untouched). */
+size_t tdr_mdta_bwd_workspace_bytes(int B, int C, int heads);
+int tdr_mdta_bwd(const float* partials, const float* attn, int B, long long P, int C, int heads,
+                 const float* temperature, const float* w_out, const float* dweff /* fp32 [B][C][C] */, void* mqk_bf16,
+                 long long mqk_ld, float* dw_out, float* dtemperature, int accumulate, float* workspace,
+                 cudaStream_t stream);
+/* out = (scale_ptr ? *scale_ptr : 1) * scale * x + y   (fp32 rows; y may be NULL; R:353 and its backward) */
+int tdr_scale_add_f32(const float* x, long long x_ld, const float* y, long long y_ld, long long rows, int C,
+                      const float* scale_ptr, float scale, float* out, long long out_ld, cudaStream_t stream);
+/* out[0] (+)= sum x*y over [rows, C] fp32 (gradient of the fusion gate alpha R:343) */
+int tdr_dot_f32(const float* x, long long x_ld, const float* y, long long y_ld, long long rows, int C, float* out,
+                int accumulate, float* workspace, cudaStream_t stream);
+/* bf16 NHWC PixelUnshuffle(2) (mode 1) / PixelShuffle(2) (mode 2): the adjoints of store_mode 2 / 1 of tdr_conv_gemm */
+int tdr_pixel_shuffle_nhwc(const void* in_bf16, long long in_ld, int B, int H, int W, int C, int mode, void* out_bf16,
+                           long long out_ld, cudaStream_t stream);
+/* out = y > 0 ? dy : 0 (ReLU backward from the stored activation, R:38-49,106-116) */
+int tdr_relu_mask(const void* y_bf16, long long y_ld, const void* dy_bf16, long long dy_ld, long long rows, int C,
+                  void* out_bf16, long long out_ld, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Layout / copies.

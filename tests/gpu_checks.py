@@ -609,6 +609,226 @@ def check_guided_stages():
     return out
 
 
+
+# =============================================================================================== backward kernels
+def grad_result(name, got, ref, rel=3e-2):
+    """Gradient comparison: relative L2 error of the whole tensor (bf16 operands, fp32 accumulation)."""
+    got = got.detach().float().cpu().reshape(-1)
+    ref = ref.detach().float().cpu().reshape(-1)
+    assert got.shape == ref.shape, f"{name}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
+    nr = ref.norm().item()
+    err = (got - ref).norm().item() / max(nr, 1e-20)
+    ok = bool(torch.isfinite(got).all()) and (err <= rel or (got - ref).abs().max().item() < 1e-9)
+    return dict(name=name, max_err=err, ref_scale=nr, tol=rel, ok=ok, note="rel-L2")
+
+
+def check_wgrad():
+    """tdr_wgrad (tcgen05 pixel-contraction GEMM) vs autograd of F.conv2d on the same bf16-rounded operands."""
+    ops = _ops()
+    out = []
+    cases = [  # B, H, W, Ci, Co, k, stride, pad, dil
+        (2, 16, 16, 48, 144, 1, 1, 0, 1), (1, 8, 24, 96, 96, 1, 1, 0, 1), (2, 16, 16, 256, 96, 1, 1, 0, 1),
+        (1, 16, 32, 96, 512, 1, 1, 0, 1), (2, 8, 8, 384, 40, 1, 1, 0, 1), (1, 8, 8, 520, 136, 1, 1, 0, 1),
+        (2, 16, 16, 48, 48, 3, 1, 1, 1), (1, 12, 20, 96, 24, 3, 1, 1, 1), (2, 16, 16, 16, 32, 3, 2, 1, 1),
+        (1, 9, 13, 32, 64, 3, 1, 1, 1), (1, 16, 16, 8, 48, 3, 1, 1, 1), (1, 16, 16, 96, 8, 3, 1, 1, 1),
+        (1, 1, 300, 80, 160, 1, 1, 0, 1),
+    ]
+    for (B, H, W, Ci, Co, k, st, pad, dil) in cases:
+        x = q(rnd(B, Ci, H, W, seed=Ci + H))
+        wt = torch.zeros(Co, Ci, k, k, requires_grad=True)
+        y = F.conv2d(x, wt, None, stride=st, padding=pad, dilation=dil)
+        dy = q(rnd(*y.shape, seed=Co + W))
+        (ref,) = torch.autograd.grad(y, wt, dy)
+        dw = torch.full((Co, Ci, k, k), 0.5, device=DEV)
+        ops.wgrad(nhwc(dy.to(BF16)), nhwc(x.to(BF16)), dw, k=k, stride=st, pad=pad, dil=dil, accumulate=True)
+        out.append(grad_result(f"wgrad_B{B}_{H}x{W}_Ci{Ci}_Co{Co}_k{k}s{st}", dw - 0.5, ref, 1e-2))
+    # per-sample (MDTA Weff gradient), strided channel-slice operands
+    B, H, W, C_ = 2, 16, 16, 96
+    buf = q(rnd(B, H, W, 3 * C_, seed=5))
+    dyv = q(rnd(B, H, W, C_, seed=6))
+    ref = torch.einsum("bhwo,bhwi->boi", dyv, buf[..., 2 * C_:])
+    dwe = torch.empty(B, C_, C_, device=DEV)
+    ops.wgrad(dyv.to(BF16).to(DEV), buf.to(BF16).to(DEV)[..., 2 * C_:], dwe, Co=C_, Ci=C_, per_sample=True,
+              strides=(C_ * C_, C_, 1, 0), accumulate=False)
+    out.append(grad_result("wgrad_per_sample_slice", dwe, ref, 1e-2))
+    # channel maps (GDFN padded halves): padded 2*hp = 272 kernel rows -> 2*h = 254 parameter rows
+    h, hp = 127, 136
+    idx2 = torch.cat([torch.arange(h), hp + torch.arange(h)])
+    m2 = torch.full((2 * hp,), -1, dtype=torch.int32)
+    m2[idx2] = torch.arange(2 * h, dtype=torch.int32)
+    dyp = torch.zeros(1, 8, 8, 2 * hp)
+    dyl = q(rnd(1, 8, 8, 2 * h, seed=7))
+    dyp[..., idx2] = dyl
+    xx = q(rnd(1, 8, 8, 48, seed=8))
+    ref = torch.einsum("bhwo,bhwi->oi", dyl, xx).reshape(2 * h, 48, 1, 1)
+    dw = torch.zeros(2 * h, 48, 1, 1, device=DEV)
+    ops.wgrad(dyp.to(BF16).to(DEV), xx.to(BF16).to(DEV), dw, co_map=m2.to(DEV))
+    out.append(grad_result("wgrad_co_map", dw, ref, 1e-2))
+    return out
+
+
+def check_bwd_pointwise():
+    ops = _ops()
+    out = []
+    # colsum
+    for C_ in (48, 288, 1024, 2560):
+        x = q(rnd(2, 7, 9, C_, seed=C_))
+        o = torch.ones(C_, device=DEV)
+        ops.colsum(x.to(BF16).to(DEV), o)
+        out.append(grad_result(f"colsum_C{C_}", o - 1, x.sum((0, 1, 2)), 1e-4))
+    # depthwise wgrad
+    for (C_, H, W, bias) in ((48, 9, 13, True), (144, 16, 16, False), (288, 8, 12, True), (2048, 4, 4, True)):
+        x = q(rnd(2, C_, H, W, seed=C_ + 1))
+        wt = torch.zeros(C_, 1, 3, 3, requires_grad=True)
+        bb = torch.zeros(C_, requires_grad=True)
+        y = F.conv2d(x, wt, bb, padding=1, groups=C_)
+        dy = q(rnd(*y.shape, seed=C_ + 2))
+        rw, rb = torch.autograd.grad(y, (wt, bb), dy)
+        dw = torch.zeros(C_, 1, 3, 3, device=DEV)
+        db = torch.zeros(C_, device=DEV) if bias else None
+        ops.dwconv3x3_wgrad(nhwc(dy.to(BF16)), nhwc(x.to(BF16)), dw, db)
+        out.append(grad_result(f"dw_wgrad_C{C_}_{H}x{W}", dw, rw, 1e-4))
+        if bias:
+            out.append(grad_result(f"dw_bgrad_C{C_}", db, rb, 1e-4))
+    # dwconv data gradient = dwconv with flipped taps
+    x = q(rnd(1, 64, 10, 12, seed=3)).requires_grad_(True)
+    wt = rnd(64, 1, 3, 3, seed=4) * 0.3
+    y = F.conv2d(x, wt, None, padding=1, groups=64)
+    dy = q(rnd(*y.shape, seed=5))
+    (rx,) = torch.autograd.grad(y, x, dy)
+    dx = ops.dwconv3x3(nhwc(dy.to(BF16)), ops.pack_dw_weight(wt.flip(2, 3).to(DEV)), None)
+    out.append(result("dwconv_dgrad_flipped", nchw(dx), rx, 1e-2))
+    # rownorm backward
+    for C_ in (48, 96, 192, 768):
+        for mode in (0, 1, 2):
+            x = (rnd(2, 5, 7, C_, seed=C_) * 2 + 0.3).requires_grad_(True)
+            w = (1 + 0.2 * rnd(C_, seed=C_ + 1)).requires_grad_(True)
+            b = (0.1 * rnd(C_, seed=C_ + 2)).requires_grad_(True)
+            mu = x.mean(-1, keepdim=True)
+            var = ((x - mu) ** 2).mean(-1, keepdim=True)
+            y = {0: x * 1.0, 1: (x - mu) / torch.sqrt(var + 1e-5) * w + b, 2: x / torch.sqrt(var + 1e-5) * w}[mode]
+            dy = q(rnd(*y.shape, seed=C_ + 3))
+            add = rnd(*y.shape, seed=C_ + 4)
+            gs = torch.autograd.grad(y, (x, w, b)[: (1, 3, 2)[mode]], dy)
+            dwt = torch.zeros(C_, device=DEV) if mode else None
+            dbt = torch.zeros(C_, device=DEV) if mode == 1 else None
+            dx = ops.rownorm_bwd(x.detach().to(DEV) if mode else None, dy.to(BF16).to(DEV), mode,
+                                 w.detach().to(DEV) if mode else None, 1e-5, add=add.to(DEV), dweight=dwt, dbias=dbt)
+            out.append(grad_result(f"rownorm_bwd_dx_m{mode}_C{C_}", dx - add.to(DEV), gs[0], 1e-4))
+            if mode:
+                out.append(grad_result(f"rownorm_bwd_dw_m{mode}_C{C_}", dwt, gs[1], 1e-4))
+            if mode == 1:
+                out.append(grad_result(f"rownorm_bwd_db_m{mode}_C{C_}", dbt, gs[2], 1e-4))
+    # gate backward
+    for gate in (1, 2):
+        yv = q(rnd(2, 6, 5, 272, seed=9)).requires_grad_(True)
+        a, b = yv.chunk(2, -1)
+        gv = (F.gelu(a) if gate == 1 else a) * b
+        dg = q(rnd(*gv.shape, seed=10))
+        (ry,) = torch.autograd.grad(gv, yv, dg)
+        dyo = torch.empty(2, 6, 5, 272, device=DEV, dtype=BF16)
+        ops.gate_bwd(yv.detach().to(BF16).to(DEV), dg.to(BF16).to(DEV), gate, out=dyo)
+        out.append(grad_result(f"gate_bwd_g{gate}", dyo, ry, 8e-3))
+    # scale_add / dot / pixel shuffle / relu mask
+    xs, ys = rnd(2, 4, 4, 96, seed=11), rnd(2, 4, 4, 96, seed=12)
+    al = torch.tensor([0.37], device=DEV)
+    out.append(result("scale_add", ops.scale_add(xs.to(DEV), ys.to(DEV), scale_ptr=al), 0.37 * xs + ys, 1e-6))
+    o = torch.ones(1, device=DEV)
+    ops.dot_f32(xs.to(DEV), ys.to(DEV), o)
+    out.append(result("dot_f32", o - 1, (xs * ys).sum().reshape(1), 1e-5))
+    t = q(rnd(2, 16, 6, 10, seed=13))                                       # NCHW
+    out.append(result("pixel_unshuffle", nchw(ops.pixel_shuffle(nhwc(t.to(BF16)), 1)), F.pixel_unshuffle(t, 2), 0.0))
+    out.append(result("pixel_shuffle", nchw(ops.pixel_shuffle(nhwc(t.to(BF16)), 2)), F.pixel_shuffle(t, 2), 0.0))
+    yy, dd = q(rnd(1, 5, 5, 64, seed=14)), q(rnd(1, 5, 5, 64, seed=15))
+    out.append(result("relu_mask", ops.relu_mask(yy.to(BF16).to(DEV), dd.to(BF16).to(DEV)), dd * (yy > 0), 0.0))
+    return out
+
+
+def check_block_bwd():
+    """One TransformerBlock / ResFusionBlock: training forward + explicit backward vs autograd through the oracle."""
+    from oracle import restormer as O, weights as Wt
+    from textualdegremoval_b200.archs import restormer_b200_arch as A
+    from textualdegremoval_b200.archs import restormer_train as TR
+    out = []
+    for (dim, heads, ln, bias, fusion, H, W) in ((48, 1, "WithBias", False, False, 16, 16),
+                                                (96, 2, "BiasFree", True, False, 8, 24),
+                                                (96, 1, "WithBias", False, True, 16, 16),
+                                                (32, 2, "WithBias", True, True, 8, 8)):
+        cls = A.TransformerResFusionBlock if fusion else A.TransformerBlock
+        blk = cls(dim, heads, 2.66, bias, ln)
+        sd = Wt.load_seeded(blk, seed=dim + heads)
+        x = rnd(2, dim, H, W, seed=dim).requires_grad_(True)
+        psd = {"b." + k_: v.clone().requires_grad_(True) for k_, v in sd.items()}
+        ref = (O.res_fusion_block if fusion else O.transformer_block)(psd, "b", x, heads)
+        dout = rnd(*ref.shape, seed=dim + 7)
+        names = list(psd)
+        gref = torch.autograd.grad(ref, [x] + [psd[n] for n in names], dout)
+        blk = blk.to(DEV)
+        p = TR.prep_block_train(blk, A._prep_block(blk))
+        tape = []
+        y = TR.run_block_train(nhwc(x.detach()), p, tape)
+        tag = f"d{dim}_h{heads}_{ln}_b{int(bias)}_f{int(fusion)}"
+        out.append(result(f"block_train_fwd_{tag}", nchw(y), ref, 1.5e-2))
+        G = TR.Grads()
+        dx = TR.run_block_bwd(nhwc(dout), tape[0], G)
+        out.append(grad_result(f"block_bwd_dx_{tag}", nchw(dx), gref[0], 3e-2))
+        params = dict(blk.named_parameters())
+        for n, gr in zip(names, gref[1:]):
+            g = G.get(params[n[2:]])
+            if g is None:
+                out.append(dict(name=f"block_bwd_{tag}_{n[2:]}", ok=False, max_err=None, note="no gradient produced"))
+            else:
+                out.append(grad_result(f"block_bwd_{tag}_{n[2:]}", g, gr, 4e-2))
+    return out
+
+
+def _net_grads(net, names_ref):
+    return {n: p.grad for n, p in net.named_parameters()}
+
+
+def check_restormer_grad():
+    """End-to-end: L1 loss -> loss.backward() through the explicit backward schedule vs autograd through the oracle."""
+    from oracle import restormer as O, weights as Wt
+    from textualdegremoval_b200.archs import define_network
+    out = []
+    for name in ("restormer_withbias", "restormer_gray_bias"):
+        meta, _ = _golden(name)
+        net = define_network(dict(type="Restormer", **meta["cfg"]))
+        sd = Wt.load_seeded(net, meta["seed"])
+        x = Wt.seeded_image("x", meta["shape"], meta["seed"])
+        gt = Wt.seeded_image("gt", meta["shape"], meta["seed"])
+        sdg = {k_: v.clone().requires_grad_(True) for k_, v in sd.items()}
+        yr = O.restormer_forward(sdg, x, meta["cfg"]["heads"])
+        lr = (yr - gt).abs().mean()
+        lr.backward()
+        net = net.to(DEV).train()
+        y = net(x.to(DEV))
+        loss = (y - gt.to(DEV)).abs().mean()
+        loss.backward()
+        out.append(result(f"train_fwd_{name}", y.detach().cpu(), yr.detach(), E2E_TOL / max(yr.abs().max().item(), 1e-6)))
+        out.append(result(f"train_loss_{name}", loss.detach().reshape(1), lr.detach().reshape(1), 1e-2))
+        num = den = 0.0
+        worst = ("", 0.0)
+        for n, p in net.named_parameters():
+            gr = sdg[n].grad
+            if p.grad is None:
+                out.append(dict(name=f"grad_{name}_{n}", ok=False, max_err=None, note="no gradient"))
+                continue
+            g = p.grad.float().cpu()
+            e = (g - gr).norm().item()
+            num += e * e
+            den += gr.norm().item() ** 2
+            rel = e / max(gr.norm().item(), 1e-12)
+            if rel > worst[1]:
+                worst = (n, rel)
+        tot = (num / max(den, 1e-30)) ** 0.5
+        r = dict(name=f"grad_global_{name}", max_err=tot, tol=5e-2, ok=bool(tot <= 5e-2), ref_scale=den ** 0.5,
+                 note=f"global rel-L2 over all parameters; worst tensor {worst[0]} rel {worst[1]:.3f}")
+        out.append(r)
+        out.append(dict(name=f"grad_worst_{name}", max_err=worst[1], tol=0.25, ok=bool(worst[1] <= 0.25),
+                        note=f"worst per-tensor rel-L2: {worst[0]}"))
+    return out
+
 CHECKS = {
     "layout": check_layout,
     "rownorm": check_rownorm,
@@ -627,6 +847,10 @@ CHECKS = {
     "nafnet": check_nafnet,
     "vit": check_vit,
     "optim": check_optim,
+    "wgrad": check_wgrad,
+    "bwd_pointwise": check_bwd_pointwise,
+    "block_bwd": check_block_bwd,
+    "restormer_grad": check_restormer_grad,
 }
 
 

@@ -21,6 +21,7 @@ import torch.nn as nn
 from .. import ops
 from ..lib import TdrError
 from .masa import Encoder, MasaMixin, ResidualBlock, prep_conv as _prep_conv, conv3x3, _f  # noqa: F401
+from .restormer_train import RestormerTrainMixin, train_call
 
 F32, BF16 = torch.float32, torch.bfloat16
 
@@ -231,6 +232,9 @@ class _RestormerBase(nn.Module):
             P["skip_conv"] = _prep_conv(self.skip_conv)
         return P
 
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     # ---- schedules ----------------------------------------------------------------------------
     def _check(self, *ts):
         for t in ts:
@@ -272,7 +276,7 @@ class _RestormerBase(nn.Module):
         return o8[..., :P["output"]["Co"]]
 
 
-class Restormer(_RestormerBase):
+class Restormer(RestormerTrainMixin, _RestormerBase):
     def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4,
                  heads=[1, 2, 4, 8], ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias",
                  dual_pixel_task=False):
@@ -284,8 +288,12 @@ class Restormer(_RestormerBase):
         return self._prepare_body()
 
     def forward(self, inp_img):
-        """:463-501.  inp_img NCHW; H and W must be multiples of 8 (as in the reference, which fails otherwise)."""
+        """:463-501.  inp_img NCHW; H and W must be multiples of 8 (as in the reference, which fails otherwise).
+        Under autograd (grad mode on and trainable parameters) the call records the training tape and is
+        differentiable w.r.t. the parameters (restormer_train.NetFunction)."""
         self._check(inp_img)
+        if self._wants_grad():
+            return train_call(self, inp_img)
         B, Cin, H, W = inp_img.shape
         if H % 8 or W % 8:
             raise ValueError(f"Restormer needs H, W multiples of 8 (got {H}x{W})")

@@ -1,0 +1,376 @@
+"""Training-step schedules (forward with a tape + explicit backward) for ``Restormer`` / ``RestormerRefFusion``.
+
+The reference trains through autograd over stock PyTorch ops (``l_total.backward()``,
+/root/reference/models/image_restoration_ref_model.py:251-284).  Here the backward pass is an explicit kernel schedule
+over the tensors the training forward keeps on a tape:
+
+  * data gradients of every conv are ``tdr_conv_gemm`` / ``tdr_dwconv3x3`` calls with transposed + flipped weights;
+  * weight gradients are ``tdr_wgrad`` (tcgen05, contraction over pixels) / ``tdr_dwconv3x3_wgrad`` / ``tdr_colsum``;
+  * LayerNorm, GELU gate, MDTA softmax/normalise and the fusion gate ``alpha`` have their own backward kernels.
+
+The residual-stream gradient is fp32; gradients of GEMM operands are bf16 (as the activations are).  LayerNorm outputs
+and the pre-gate depthwise output are recomputed in the backward pass instead of being stored.
+
+``NetFunction`` exposes the pair to ``torch.autograd`` so that ``loss.backward()`` and an unmodified optimizer /
+``DistributedDataParallel`` wrapper keep working; parameter gradients come back in the reference's parameter layout.
+"""
+import torch
+
+from .. import ops
+from .masa import _f
+
+F32, BF16 = torch.float32, torch.bfloat16
+
+
+# ----------------------------------------------------------------------------------------------- gradient sink
+class Grads:
+    """fp32 gradient buffers, one per parameter, in the parameter's own layout (allocated zeroed on first touch)."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def __call__(self, param):
+        if param is None:
+            return None
+        t = self.buf.get(id(param))
+        if t is None:
+            t = torch.zeros(param.shape, dtype=F32, device=param.device)
+            self.buf[id(param)] = t
+        return t
+
+    def get(self, param):
+        return self.buf.get(id(param))
+
+
+def _flip_T(w):
+    """[Co, Ci, k, k] -> weight of the data-gradient conv: [Ci, Co, k, k] with taps flipped."""
+    return w.detach().permute(1, 0, 2, 3).flip(2, 3)
+
+
+def prep_conv_train(conv, pc):
+    """Adds the dgrad pack to a ``prep_conv`` dict (stride-1 convs)."""
+    if "wT" not in pc:
+        pc["wT"] = ops.pack_conv_weight(_flip_T(conv.weight))
+        pc["mod"] = conv
+    return pc
+
+
+def prep_block_train(blk, p):
+    """Transposed / flipped packs and channel maps for one transformer block (cached next to the forward packs)."""
+    if "w_qkv_T" in p:
+        return p
+    a, f = blk.attn, blk.ffn
+    h, hp = p["h"], p["hp"]
+    dev = a.qkv.weight.device
+    idx2 = torch.cat([torch.arange(h, device=dev), hp + torch.arange(h, device=dev)])
+    p["mod"] = blk
+    p["w_qkv_T"] = ops.pack_conv_weight(_flip_T(a.qkv.weight))
+    p["w_qkv_dw_f"] = ops.pack_dw_weight(a.qkv_dwconv.weight.detach().flip(2, 3))
+    p["w_in_T"] = ops.pack_conv_weight(_flip_T(f.project_in.weight), ci_map=(2 * hp, idx2))
+    p["w_dw_f"] = ops.pack_dw_weight(f.dwconv.weight.detach().flip(2, 3), 2 * hp, idx2)
+    p["w_out_T"] = ops.pack_conv_weight(_flip_T(f.project_out.weight), co_map=(hp, torch.arange(h, device=dev)))
+    m2 = torch.full((2 * hp,), -1, dtype=torch.int32, device=dev)
+    m2[idx2] = torch.arange(2 * h, dtype=torch.int32, device=dev)
+    m1 = torch.full((hp,), -1, dtype=torch.int32, device=dev)
+    m1[:h] = torch.arange(h, dtype=torch.int32, device=dev)
+    p["map_2h"], p["map_h"] = m2, m1
+    return p
+
+
+# ----------------------------------------------------------------------------------------------- one block
+def run_block_train(x32, p, tape):
+    """Training forward of one (Res-fusion) transformer block: NOT in place, returns the new residual stream."""
+    C_, heads, hp = p["C"], p["heads"], p["hp"]
+    fusion = p["alpha"] is not None
+    sv = dict(p=p, x0=x32)
+    xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5)
+    _, qkv0 = ops.conv_gemm(xn, p["w_qkv"], 3 * C_, bias=p["b_qkv"])
+    qkv = ops.dwconv3x3(qkv0, p["w_qkv_dw"], p["b_qkv_dw"])
+    weff = ops.mdta_weff(qkv, C_, heads, p["temp"], p["w_po"], save=sv)
+    x1, _ = ops.conv_gemm(qkv[..., 2 * C_:], weff, C_, Ci=C_, bias=p["b_po"], res2=x32, want="f32", w_batched=True)
+    xn = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5)
+    _, hid = ops.conv_gemm(xn, p["w_in"], 2 * hp, bias=p["b_in"])
+    g = ops.dwconv3x3(hid, p["w_dw"], p["b_dw"], gate=1)
+    out, _ = ops.conv_gemm(g, p["w_out"], C_, bias=p["b_out"], res2=x1, want="f32")
+    if fusion:          # out = alpha * block(x0) + x0   (R:353)
+        sv["t"] = out
+        out = ops.scale_add(out, x32, scale_ptr=p["alpha"])
+    sv.update(qkv0=qkv0, qkv=qkv, x1=x1, hid=hid, g=g)
+    tape.append(sv)
+    return out
+
+
+def run_block_bwd(dout, sv, G):
+    """Backward of run_block_train.  dout: fp32 NHWC gradient wrt the block output (overwritten).  Returns the
+    gradient wrt the block input (fp32 NHWC)."""
+    p = sv["p"]
+    blk = p["mod"]
+    a, f = blk.attn, blk.ffn
+    C_, heads, hp = p["C"], p["heads"], p["hp"]
+    fusion = p["alpha"] is not None
+    x0, x1, qkv0, qkv, hid, g = sv["x0"], sv["x1"], sv["qkv0"], sv["qkv"], sv["hid"], sv["g"]
+    B, H, W, _ = x0.shape
+    mode = p["ln_mode"]
+    if fusion:
+        ops.dot_f32(dout, sv["t"], G(blk.alpha))
+        d2 = ops.scale_add(dout, None, scale_ptr=p["alpha"])
+    else:
+        d2 = dout
+    # ---- GDFN: x2 = x1 + project_out(gelu(a) * b), [a | b] = dw(project_in(LN2(x1)))
+    d2_16 = ops.rownorm(d2, 0)
+    _, dg = ops.conv_gemm(d2_16, p["w_out_T"], hp, Ci=C_)
+    ops.wgrad(d2_16, g, G(f.project_out.weight), ci_map=p["map_h"])
+    if f.project_out.bias is not None:
+        ops.colsum(d2_16, G(f.project_out.bias))
+    y = ops.dwconv3x3(hid, p["w_dw"], p["b_dw"], gate=0)
+    dy = ops.gate_bwd(y, dg, 1)
+    ops.dwconv3x3_wgrad(dy, hid, G(f.dwconv.weight), G(f.dwconv.bias), c_map=p["map_2h"])
+    dhid = ops.dwconv3x3(dy, p["w_dw_f"], None)
+    xn2 = ops.rownorm(x1, mode, p["ln2_w"], p["ln2_b"], 1e-5)
+    _, dxn2 = ops.conv_gemm(dhid, p["w_in_T"], C_, Ci=2 * hp)
+    ops.wgrad(dhid, xn2, G(f.project_in.weight), co_map=p["map_2h"])
+    if f.project_in.bias is not None:
+        ops.colsum(dhid, G(f.project_in.bias), c_map=p["map_2h"])
+    d1 = ops.rownorm_bwd(x1, dxn2, mode, p["ln2_w"], 1e-5, add=d2, out=d2, dweight=G(blk.norm2.body.weight),
+                         dbias=G(blk.norm2.body.bias))
+    # ---- MDTA: x1 = x0 + project_out(softmax(norm(q) norm(k)^T * temperature) v)
+    d1_16 = ops.rownorm(d1, 0)
+    dqkv = torch.empty_like(qkv)
+    ops.conv_gemm(d1_16, sv["weff_t"], C_, Ci=C_, w_batched=True, out_bf16=dqkv[..., 2 * C_:])
+    dweff = torch.empty((B, C_, C_), dtype=F32, device=dout.device)
+    ops.wgrad(d1_16, qkv[..., 2 * C_:], dweff, Co=C_, Ci=C_, per_sample=True, strides=(C_ * C_, C_, 1, 0), accumulate=False)
+    if a.project_out.bias is not None:
+        ops.colsum(d1_16, G(a.project_out.bias))
+    mqk = ops.mdta_bwd(sv, B, H * W, C_, heads, p["temp"], p["w_po"], dweff, G(a.project_out.weight), G(a.temperature))
+    ops.conv_gemm(qkv[..., :2 * C_], mqk, 2 * C_, Ci=2 * C_, w_batched=True, out_bf16=dqkv[..., :2 * C_])
+    ops.dwconv3x3_wgrad(dqkv, qkv0, G(a.qkv_dwconv.weight), G(a.qkv_dwconv.bias))
+    dqkv0 = ops.dwconv3x3(dqkv, p["w_qkv_dw_f"], None)
+    xn1 = ops.rownorm(x0, mode, p["ln1_w"], p["ln1_b"], 1e-5)
+    _, dxn1 = ops.conv_gemm(dqkv0, p["w_qkv_T"], C_, Ci=3 * C_)
+    ops.wgrad(dqkv0, xn1, G(a.qkv.weight))
+    if a.qkv.bias is not None:
+        ops.colsum(dqkv0, G(a.qkv.bias))
+    d0 = ops.rownorm_bwd(x0, dxn1, mode, p["ln1_w"], 1e-5, add=d1, out=d1, dweight=G(blk.norm1.body.weight),
+                         dbias=G(blk.norm1.body.bias))
+    if fusion:
+        ops.scale_add(dout, d0, out=d0)            # + dout through the shortcut
+    return d0
+
+
+def run_stack_train(x32, preps, mods, tape):
+    n0 = len(tape)
+    for p, m in zip(preps, mods):
+        x32 = run_block_train(x32, prep_block_train(m, p), tape)
+    return x32, (n0, len(tape))
+
+
+def run_stack_bwd(d, tape, span, G):
+    for i in range(span[1] - 1, span[0] - 1, -1):
+        d = run_block_bwd(d, tape[i], G)
+        tape[i] = None                              # free the block's activations as soon as they are consumed
+    return d
+
+
+# ----------------------------------------------------------------------------------------------- U-Net wiring
+def down_train(x32, pc, out32, sv):
+    """Downsample R:372-380: conv3x3 C -> C/2 + PixelUnshuffle(2)."""
+    sv["x"] = x32
+    ops.conv_gemm(ops.rownorm(x32, 0), pc["w"], pc["Co"], k=3, pad=1, out_f32=out32, store_mode=1)
+
+
+def down_bwd(dy32, pc, sv, G, add=None):
+    """dy32: fp32 gradient wrt the unshuffled output [B,H/2,W/2,2C].  Returns fp32 gradient wrt x (+ add)."""
+    conv = pc["mod"]
+    dconv = ops.pixel_shuffle(ops.rownorm(dy32, 0), 2)                 # adjoint of the unshuffle store
+    x16 = ops.rownorm(sv["x"], 0)
+    ops.wgrad(dconv, x16, G(conv.weight), k=3, pad=1)
+    dx, _ = ops.conv_gemm(dconv, pc["wT"], conv.in_channels, k=3, pad=1, want="f32", res2=add)
+    return dx
+
+
+def up_bwd(dy16, pc, x32, G):
+    """Upsample R:383-391 (conv3x3 C -> 2C + PixelShuffle(2)).  dy16: bf16 gradient wrt the shuffled output (dense or a
+    channel slice).  Returns fp32 gradient wrt x32."""
+    conv = pc["mod"]
+    dconv = ops.pixel_shuffle(dy16, 1)                                  # adjoint of the shuffle store
+    ops.wgrad(dconv, ops.rownorm(x32, 0), G(conv.weight), k=3, pad=1)
+    dx, _ = ops.conv_gemm(dconv, pc["wT"], conv.in_channels, k=3, pad=1, want="f32")
+    return dx
+
+
+def _head_map(n, valid, dev):
+    """int32 channel map for zero-padded image-boundary buffers: the first ``valid`` of ``n`` channels are real."""
+    m = torch.full((n,), -1, dtype=torch.int32, device=dev)
+    m[:valid] = torch.arange(valid, dtype=torch.int32, device=dev)
+    return m
+
+
+class RestormerTrainMixin:
+    """Training forward / backward for the shared U-Net body (``_RestormerBase``)."""
+
+    @staticmethod
+    def _image16(img, pad_h, pad_w):
+        """NCHW image -> zero-padded bf16 NHWC with 8 channels (16 B rows for TMA): the wgrad operand of the first conv."""
+        t = torch.zeros((img.shape[0], pad_h, pad_w, 8), dtype=BF16, device=img.device)
+        ops.nchw_to_nhwc_into(img, pad_h, pad_w, dst16=t)
+        return t
+
+    def _prep_train(self, P):
+        if P.get("_train"):
+            return P
+        for name in ["down1_2", "down2_3", "down3_4", "up4_3", "up3_2", "up2_1"]:
+            prep_conv_train(getattr(self, name).body[0], P[name])
+        for name in ["reduce_chan_level3", "reduce_chan_level2"]:
+            prep_conv_train(getattr(self, name), P[name])
+        ow = self.output.weight                                          # [co, 2*dim, 3, 3] -> dgrad pack with Ci = 8
+        w8 = torch.zeros(8, ow.shape[1], 3, 3, dtype=ow.dtype, device=ow.device)
+        w8[:ow.shape[0]] = ow.detach()
+        P["output"]["wT"] = ops.pack_conv_weight(_flip_T(w8))
+        P["_train"] = True
+        return P
+
+    # ---- decoder half (R:477-501) ------------------------------------------------------------------------------
+    def _decode_train(self, P, lat, e1, e2, e3, tape, T):
+        d = self.dims
+        dev = lat.device
+
+        def up_cat_reduce(x32, enc, up, red, Cn, key):
+            b, hh, ww, _ = x32.shape
+            cat16 = torch.empty((b, hh * 2, ww * 2, 2 * Cn), dtype=BF16, device=dev)
+            ops.conv_gemm(ops.rownorm(x32, 0), P[up]["w"], P[up]["Co"], k=3, pad=1, out_bf16=cat16[..., :Cn], store_mode=2)
+            ops.copy_rows(enc, dst16=cat16[..., Cn:])
+            y32, _ = ops.conv_gemm(cat16, P[red]["w"], Cn, bias=P[red]["b"], want="f32")
+            T[key] = dict(x=x32, cat16=cat16)
+            return y32
+
+        d3, T["s_dec3"] = run_stack_train(up_cat_reduce(lat, e3, "up4_3", "reduce_chan_level3", d[2], "cat3"),
+                                          P["decoder_level3"], self.decoder_level3, tape)
+        d2, T["s_dec2"] = run_stack_train(up_cat_reduce(d3, e2, "up3_2", "reduce_chan_level2", d[1], "cat2"),
+                                          P["decoder_level2"], self.decoder_level2, tape)
+        b, hh, ww, _ = d2.shape
+        d1 = torch.empty((b, hh * 2, ww * 2, d[1]), dtype=F32, device=dev)
+        ops.conv_gemm(ops.rownorm(d2, 0), P["up2_1"]["w"], P["up2_1"]["Co"], k=3, pad=1, out_f32=d1[..., :d[0]], store_mode=2)
+        ops.copy_rows(e1, dst32=d1[..., d[0]:])
+        T["d2"] = d2
+        d1, T["s_dec1"] = run_stack_train(d1, P["decoder_level1"], self.decoder_level1, tape)
+        d1, T["s_ref"] = run_stack_train(d1, P["refinement"], self.refinement, tape)
+        T["d1"] = d1
+        o8, _ = ops.conv_gemm(ops.rownorm(d1, 0), P["output"]["w"], 8, k=3, pad=1, bias=P["output"]["b"], want="f32")
+        return o8[..., :P["output"]["Co"]]
+
+    def _decode_bwd(self, P, dout_nchw, h, w, tape, T, G):
+        """dout_nchw: fp32 NCHW gradient of the network output.  Returns (dlat, de1_skip, de2_skip16, de3_skip16):
+        the latent gradient (fp32) and the skip-connection gradients (level 1 fp32 view, levels 2/3 bf16 views)."""
+        d = self.dims
+        B = dout_nchw.shape[0]
+        dev = dout_nchw.device
+        co = P["output"]["Co"]
+        do8 = torch.zeros((B, h, w, 8), dtype=BF16, device=dev)
+        ops.nchw_to_nhwc_into(dout_nchw, h, w, dst16=do8)
+        d1_16 = ops.rownorm(T["d1"], 0)
+        m = _head_map(8, co, dev)
+        ops.wgrad(do8, d1_16, G(self.output.weight), k=3, pad=1, co_map=m)
+        if self.output.bias is not None:
+            ops.colsum(do8, G(self.output.bias), c_map=m)
+        dd1, _ = ops.conv_gemm(do8, P["output"]["wT"], d[1], Ci=8, k=3, pad=1, want="f32")
+        dd1 = run_stack_bwd(dd1, tape, T["s_ref"], G)
+        dd1 = run_stack_bwd(dd1, tape, T["s_dec1"], G)
+        de1_skip = dd1[..., d[0]:]
+        dd2 = up_bwd(ops.rownorm(dd1[..., :d[0]], 0), P["up2_1"], T["d2"], G)
+
+        def up_cat_reduce_bwd(dy32, up, red, Cn, key):
+            conv = P[red]["mod"]
+            dy16 = ops.rownorm(dy32, 0)
+            cat16 = T[key]["cat16"]
+            ops.wgrad(dy16, cat16, G(conv.weight))
+            if conv.bias is not None:
+                ops.colsum(dy16, G(conv.bias))
+            _, dcat = ops.conv_gemm(dy16, P[red]["wT"], 2 * Cn, Ci=Cn)
+            dx = up_bwd(dcat[..., :Cn], P[up], T[key]["x"], G)
+            return dx, dcat[..., Cn:]
+
+        dd2 = run_stack_bwd(dd2, tape, T["s_dec2"], G)
+        dd3, de2_skip = up_cat_reduce_bwd(dd2, "up3_2", "reduce_chan_level2", d[1], "cat2")
+        dd3 = run_stack_bwd(dd3, tape, T["s_dec3"], G)
+        dlat, de3_skip = up_cat_reduce_bwd(dd3, "up4_3", "reduce_chan_level3", d[2], "cat3")
+        return dlat, de1_skip, de2_skip, de3_skip
+
+    # ---- plain Restormer (R:463-501) -----------------------------------------------------------------------------
+    def _forward_train(self, inp_img):
+        self._check(inp_img)
+        B, Cin, H, W = inp_img.shape
+        if H % 8 or W % 8:
+            raise ValueError(f"Restormer needs H, W multiples of 8 (got {H}x{W})")
+        if self.dual_pixel_task:
+            raise ops.lib.TdrError("Restormer (B200): training with dual_pixel_task is not implemented")
+        P = self._prep_train(self.prepared())
+        d = self.dims
+        dev = inp_img.device
+        tape, T = [], dict(hw=(H, W))
+        inp32 = ops.nchw_to_nhwc(inp_img, H, W)
+        T["inp16"] = self._image16(inp_img, H, W)
+        x = torch.empty((B, H, W, d[0]), dtype=F32, device=dev)
+        ops.conv3x3_small_ci(inp32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=x)
+        names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
+        downs = [None, "down1_2", "down2_3", "down3_4"]
+        es = []
+        for i in range(4):
+            if i:
+                nxt = torch.empty((B, H >> i, W >> i, d[i]), dtype=F32, device=dev)
+                T[downs[i]] = {}
+                down_train(x, P[downs[i]], nxt, T[downs[i]])
+                x = nxt
+            x, T["s_" + names[i]] = run_stack_train(x, P[names[i]], getattr(self, names[i]), tape)
+            es.append(x)
+        out = self._decode_train(P, es[3], es[0], es[1], es[2], tape, T)
+        y = ops.nhwc_to_nchw(out, H, W, res=inp32)
+        return y, (P, tape, T)
+
+    def _backward(self, state, dout):
+        P, tape, T = state
+        G = Grads()
+        H, W = T["hw"]
+        dlat, de1_skip, de2_skip, de3_skip = self._decode_bwd(P, dout.contiguous().float(), H, W, tape, T, G)
+        names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
+        downs = [None, "down1_2", "down2_3", "down3_4"]
+        dx = run_stack_bwd(dlat, tape, T["s_latent"], G)
+        dx = down_bwd(dx, P["down3_4"], T["down3_4"], G)
+        dx = ops.rownorm_bwd(None, de3_skip, 0, add=dx, out=dx)
+        dx = run_stack_bwd(dx, tape, T["s_encoder_level3"], G)
+        dx = down_bwd(dx, P["down2_3"], T["down2_3"], G)
+        dx = ops.rownorm_bwd(None, de2_skip, 0, add=dx, out=dx)
+        dx = run_stack_bwd(dx, tape, T["s_encoder_level2"], G)
+        dx = down_bwd(dx, P["down1_2"], T["down1_2"], G, add=de1_skip)
+        dx = run_stack_bwd(dx, tape, T["s_encoder_level1"], G)
+        pe = self.patch_embed.proj
+        dx16 = ops.rownorm(dx, 0)
+        ops.wgrad(dx16, T["inp16"], G(pe.weight), k=3, pad=1, ci_map=_head_map(8, pe.in_channels, dx.device))
+        if pe.bias is not None:
+            ops.colsum(dx16, G(pe.bias))
+        return G
+
+
+class NetFunction(torch.autograd.Function):
+    """autograd bridge: forward = training schedule (tape kept on ctx), backward = explicit kernel schedule."""
+
+    @staticmethod
+    def forward(ctx, net, n_inputs, *args):
+        inputs, params = args[:n_inputs], args[n_inputs:]
+        out, state = net._forward_train(*[t.detach() for t in inputs])
+        ctx.net, ctx.state, ctx.params, ctx.n_inputs = net, state, params, n_inputs
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        G = ctx.net._backward(ctx.state, dout)
+        ctx.state = None
+        grads = []
+        for p in ctx.params:
+            g = G.get(p)
+            grads.append(g.to(p.dtype) if g is not None else (torch.zeros_like(p) if p.requires_grad else None))
+        return (None, None) + (None,) * ctx.n_inputs + tuple(grads)
+
+
+def train_call(net, *inputs):
+    params = [p for p in net.parameters()]
+    return NetFunction.apply(net, len(inputs), *inputs, *params)

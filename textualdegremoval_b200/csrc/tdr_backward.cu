@@ -1,0 +1,1007 @@
+// Backward kernels of the restoration-network hot path (training step, SURVEY.md 8(a) a21 and the "bwd" half of a1-a16).
+// The reference gets these from autograd over stock PyTorch ops (loss.backward() in
+// /root/reference/models/image_restoration_ref_model.py:268-275); here every gradient is an explicit kernel:
+//
+//   tdr_wgrad            weight gradient of any dense conv / 1x1 / per-sample product: a tcgen05 GEMM whose contraction
+//                        runs over PIXELS (both operands MN-major straight from NHWC TMA boxes, like tdr_mdta_gram)
+//   tdr_dwconv3x3_wgrad  depthwise 3x3 weight + bias gradient (per-channel 9-tap correlation, HBM-bound)
+//   tdr_colsum           bias gradients (column sums of a bf16 activation-gradient)
+//   tdr_rownorm_bwd      LayerNorm (WithBias / BiasFree / LayerNorm2d) backward fused with the residual-stream add
+//   tdr_gate_bwd         GELU-gate (GDFN) / SimpleGate (NAF) backward
+//   tdr_mdta_bwd         softmax / normalise / temperature backward of the MDTA score path, emitted as the per-sample
+//                        [2C x 2C] matrix that maps [q;k] to [dq;dk] (so the pixel-sized part is one tdr_conv_gemm)
+//   tdr_scale_add_f32, tdr_dot_f32, tdr_pixel_shuffle_nhwc, tdr_relu_mask: small glue of the fusion blocks / U-Net wiring
+//
+// Data gradients (dgrad) of convolutions are tdr_conv_gemm / tdr_dwconv3x3 calls with transposed + flipped weights.
+// Reductions are two-stage and deterministic (no atomics).
+#include <stdlib.h>
+#include <string.h>
+
+#include "tdr_common.cuh"
+
+namespace {
+
+constexpr int kPixTile = 128;                 // pixels (K) per pipeline stage = TH x TW
+constexpr int kBoxBytes = 64 * kPixTile * 2;  // one [64 ch x 128 px] bf16 box
+
+// ------------------------------------------------------------------------------------------------ wgrad (tcgen05)
+struct WgradPlan {
+  int OH, OW, T;
+  int TW, TH, tiles_x, tiles_y;
+  int BM, BN, m_tiles, n_tiles, boxes_m, boxes_n, stages;
+  int nb, nchunks, tiles_per_chunk, tiles_total;
+  uint32_t tmem_cols;
+};
+
+struct WgradArgs {
+  int Co, Ci, KW, stride, pad, dil, per_sample;
+  WgradPlan plan;
+  float* partials;
+};
+
+static int wgrad_plan(const tdr_wgrad_desc* d, WgradPlan* p) {
+  p->OH = (d->H + 2 * d->pad - d->dil * (d->KH - 1) - 1) / d->stride + 1;
+  p->OW = (d->W + 2 * d->pad - d->dil * (d->KW - 1) - 1) / d->stride + 1;
+  if (p->OH <= 0 || p->OW <= 0) return -1;
+  p->T = d->KH * d->KW;
+  if (p->OH == 1) { p->TW = 128; p->TH = 1; }          // flat [rows, C] view (ViT / mapper linears)
+  else if (p->OW >= 16) { p->TW = 16; p->TH = 8; }
+  else { p->TW = 8; p->TH = 16; }
+  p->tiles_x = tdr_cdiv(p->OW, p->TW);
+  p->tiles_y = tdr_cdiv(p->OH, p->TH);
+  p->BM = d->Co <= 64 ? 64 : 128;
+  p->m_tiles = tdr_cdiv(d->Co, p->BM);
+  p->boxes_m = p->BM / 64;
+  const int ci16 = tdr_cdiv(d->Ci, 16) * 16;
+  p->n_tiles = tdr_cdiv(ci16, 256);
+  p->BN = tdr_cdiv(tdr_cdiv(ci16, p->n_tiles), 16) * 16;
+  p->boxes_n = tdr_cdiv(p->BN, 64);
+  const int stage_bytes = (p->boxes_m + p->boxes_n) * kBoxBytes;
+  p->stages = (220 * 1024) / stage_bytes;
+  if (p->stages > 4) p->stages = 4;
+  if (p->stages < 2) return -1;
+  p->nb = d->per_sample ? d->B : 1;
+  p->tiles_total = (d->per_sample ? 1 : d->B) * p->tiles_y * p->tiles_x;
+  const int outer = p->T * p->m_tiles * p->n_tiles * p->nb;
+  int want = (2 * tdr_num_sms() + outer - 1) / outer;
+  if (want < 1) want = 1;
+  if (want > p->tiles_total) want = p->tiles_total;
+  p->tiles_per_chunk = tdr_cdiv(p->tiles_total, want);
+  p->nchunks = tdr_cdiv(p->tiles_total, p->tiles_per_chunk);
+  uint32_t cols = 32;
+  while (cols < (uint32_t)p->BN) cols <<= 1;
+  p->tmem_cols = cols;
+  return 0;
+}
+
+// grid (chunk, (tap * m_tiles + mt) * n_tiles + nt, sample-or-1); 6 warps: TMA producer, MMA issuer, 4 epilogue.
+__global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ TdrTensorMap map_dy,
+                                                       const __grid_constant__ TdrTensorMap map_x, const WgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const WgradPlan& pl = a.plan;
+  const int stage_bytes = (pl.boxes_m + pl.boxes_n) * kBoxBytes;   // dy boxes then x boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + pl.stages;
+  uint64_t* tfull = bars + 2 * pl.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * pl.stages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x, bz = blockIdx.z;
+  int yy = blockIdx.y;
+  const int nt = yy % pl.n_tiles; yy /= pl.n_tiles;
+  const int mt = yy % pl.m_tiles;
+  const int tap = yy / pl.m_tiles;
+  const int ky = tap / a.KW, kx = tap % a.KW;
+  const int tile0 = chunk * pl.tiles_per_chunk;
+  int ntiles = pl.tiles_total - tile0;
+  if (ntiles > pl.tiles_per_chunk) ntiles = pl.tiles_per_chunk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_dy);
+    tma_prefetch_desc(&map_x);
+    for (int s = 0; s < pl.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, pl.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < ntiles; ++t) {
+        int tile = tile0 + t;
+        const int tx = tile % pl.tiles_x; tile /= pl.tiles_x;
+        const int ty = tile % pl.tiles_y;
+        const int b = a.per_sample ? bz : tile / pl.tiles_y;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], stage_bytes);
+        uint8_t* base = smem + stage * stage_bytes;
+        for (int j = 0; j < pl.boxes_m; ++j)
+          tma_load_4d(base + j * kBoxBytes, &map_dy, &full[stage], mt * pl.BM + 64 * j, tx * pl.TW, ty * pl.TH, b);
+        const int x0 = tx * pl.TW * a.stride + kx * a.dil - a.pad;
+        const int y0 = ty * pl.TH * a.stride + ky * a.dil - a.pad;
+        for (int j = 0; j < pl.boxes_n; ++j)
+          tma_load_4d(base + (pl.boxes_m + j) * kBoxBytes, &map_x, &full[stage], nt * pl.BN + 64 * j, x0, y0, b);
+        if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_bf16(pl.BM, pl.BN, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = 0; t < ntiles; ++t) {
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint32_t sb = sa + pl.boxes_m * kBoxBytes;
+#pragma unroll
+        for (int ks = 0; ks < kPixTile / 16; ++ks) {
+          // 16 pixels (K) = two 8-row swizzle atoms of 1024 B; 64-channel chunks are kBoxBytes apart (LBO)
+          const uint64_t da = umma_desc_sw128(sa + ks * 2048, kBoxBytes, 1024);
+          const uint64_t db = umma_desc_sw128(sb + ks * 2048, kBoxBytes, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (t | ks) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (t == ntiles - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+      if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // epilogue warps 2..5: TMEM lane quadrant = warp % 4
+    const int quad = warp & 3;
+    // M = 128: row r lives in lane r.  M = 64: row r lives in lane (r/16)*32 + r%16 (16 rows per quadrant).
+    const int row = pl.BM == 128 ? quad * 32 + lane : quad * 16 + lane;
+    const int co = mt * pl.BM + row;
+    const bool row_ok = (pl.BM == 128 || lane < 16) && co < a.Co;
+    float* out = a.partials + ((((size_t)bz * pl.nchunks + chunk) * pl.T + tap) * a.Co + co) * (size_t)a.Ci;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
+    for (int c16 = 0; c16 < pl.BN / 16; ++c16) {
+      uint32_t g[16];
+      tmem_ld16(t_lane + c16 * 16, g);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int ci = nt * pl.BN + c16 * 16 + i;
+          if (ci < a.Ci) out[ci] = __uint_as_float(g[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, pl.tmem_cols);
+  }
+}
+
+// out[b*s_b + map(co)*s_co + map(ci)*s_ci + t*s_t] (+)= scale * sum_chunk partials[b][chunk][t][co][ci]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partials, int nb, int nchunks, int T,
+                                                           int Co, int Ci, float* __restrict__ out, long long s_b,
+                                                           long long s_co, long long s_ci, long long s_t,
+                                                           const int* __restrict__ co_map, const int* __restrict__ ci_map,
+                                                           int accumulate, float scale) {
+  const long long per = (long long)T * Co * Ci;
+  const long long total = (long long)nb * per;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per);
+    long long r = i % per;
+    const int ci = (int)(r % Ci); r /= Ci;
+    const int co = (int)(r % Co);
+    const int t = (int)(r / Co);
+    const int lco = co_map ? co_map[co] : co;
+    const int lci = ci_map ? ci_map[ci] : ci;
+    if (lco < 0 || lci < 0) continue;
+    const float* p = partials + (size_t)b * nchunks * per + (i % per);
+    float s = 0.f;
+    for (int c = 0; c < nchunks; ++c) s += p[(size_t)c * per];
+    float* o = out + b * s_b + lco * s_co + lci * s_ci + t * s_t;
+    *o = (accumulate ? *o : 0.f) + scale * s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ generic helpers
+inline int grid_for(long long items, int per_block, int max_waves = 8) {
+  long long g = (items + per_block - 1) / per_block;
+  const long long cap = (long long)tdr_num_sms() * max_waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// out[map(c)*stride] (+)= scale * sum_{p < nparts} partials[p][c]
+__global__ void __launch_bounds__(256) reduce_parts_kernel(const float* __restrict__ partials, int nparts, int n,
+                                                           float* __restrict__ out, long long stride,
+                                                           const int* __restrict__ map, int accumulate, float scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  const int lc = map ? map[c] : c;
+  if (lc < 0) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * n + c];
+  float* o = out + lc * stride;
+  *o = (accumulate ? *o : 0.f) + scale * s;
+}
+
+constexpr int kRedBlocks = 296;   // partial rows written by the first stage of the column reductions
+
+// ------------------------------------------------------------------------------------------------ colsum / dw wgrad
+// Thread mapping shared by the two column reductions: CG = C/8 channel groups; a block of 256 threads covers
+// cgb = min(CG, 256) groups x (256 / cgb) pixel slots (thread = slot * cgb + group), so narrow tensors still use every
+// lane and a warp's loads are contiguous runs.  grid (blocks over pixels, ceil(CG / 256)).
+struct ColMap {
+  int cgb, slots, slot, c0;
+  bool active;
+};
+__device__ __forceinline__ ColMap col_map(int C) {
+  ColMap m;
+  const int CG = C >> 3;
+  m.cgb = CG < 256 ? CG : 256;
+  m.slots = 256 / m.cgb;
+  m.slot = threadIdx.x / m.cgb;
+  const int cg = blockIdx.y * 256 + (int)(threadIdx.x % m.cgb);
+  m.c0 = cg * 8;
+  m.active = m.slot < m.slots && cg < CG;
+  return m;
+}
+// sums sm[slot][g][i] over slots and writes dst[c] for the block's channel range
+__device__ __forceinline__ void col_reduce_store(const float (*sm)[8], const ColMap& m, int C, float* dst) {
+  for (int e = threadIdx.x; e < m.cgb * 8; e += 256) {
+    const int g = e >> 3, i = e & 7;
+    float s = 0.f;
+    for (int k = 0; k < m.slots; ++k) s += sm[k * m.cgb + g][i];
+    const int c = (blockIdx.y * 256 + g) * 8 + i;
+    if (c < C) dst[c] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x, long long ld, long long rows, int C,
+                                                     float* __restrict__ partials) {
+  __shared__ float sm[256][8];
+  const ColMap m = col_map(C);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (m.active) {
+    for (long long r = (long long)blockIdx.x * m.slots + m.slot; r < rows; r += (long long)gridDim.x * m.slots) {
+      float f[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + r * ld + m.c0), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  col_reduce_store(sm, m, C, partials + (size_t)blockIdx.x * C);
+}
+
+// dW[tap][c] = sum_p dy[p, c] * x[p + off(tap), c];  db[c] = sum_p dy[p, c].  partials [blk][10][C] (tap 9 = bias).
+__global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld,
+                                                       const bf16* __restrict__ x, long long x_ld, int B, int H, int W,
+                                                       int C, float* __restrict__ partials) {
+  __shared__ float sm[256][8];
+  const ColMap m = col_map(C);
+  float acc[10][8];
+#pragma unroll
+  for (int t = 0; t < 10; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  const long long npix = (long long)B * H * W;
+  // contiguous pixel range per block (keeps the 3-row neighbourhood in L1/L2)
+  const long long per = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = blockIdx.x * per, p1 = p0 + per < npix ? p0 + per : npix;
+  if (m.active) {
+    for (long long p = p0 + m.slot; p < p1; p += m.slots) {
+      const int xx = (int)(p % W);
+      const int yy = (int)((p / W) % H);
+      float g[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + p * dy_ld + m.c0), g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[9][i] += g[i];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const int dyy = t / 3 - 1, dxx = t % 3 - 1;
+        if ((unsigned)(yy + dyy) < (unsigned)H && (unsigned)(xx + dxx) < (unsigned)W) {
+          float f[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(x + (p + dyy * W + dxx) * x_ld + m.c0), f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(g[i], f[i], acc[t][i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 10; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[threadIdx.x][i] = acc[t][i];
+    __syncthreads();
+    col_reduce_store(sm, m, C, partials + ((size_t)blockIdx.x * 10 + t) * C);
+  }
+}
+
+// dw[map(c)*9 + tap] (+)= sum_blk partials[blk][tap][c];  db[map(c)] (+)= sum_blk partials[blk][9][c]
+__global__ void __launch_bounds__(256) dw_wgrad_reduce_kernel(const float* __restrict__ partials, int nparts, int C,
+                                                              float* __restrict__ dw, float* __restrict__ db,
+                                                              const int* __restrict__ map, int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 10 * C) return;
+  const int t = idx / C, c = idx % C;
+  const int lc = map ? map[c] : c;
+  if (lc < 0) return;
+  if (t == 9 && !db) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partials[((size_t)p * 10 + t) * C + c];
+  float* o = t == 9 ? db + lc : dw + lc * 9 + t;
+  *o = (accumulate ? *o : 0.f) + s;
+}
+
+// ------------------------------------------------------------------------------------------------ rownorm backward
+// G lanes per row, NV float4 per lane (same mapping as the forward kernel).  dx = add + LN_bwd(dy) ; per-block partial
+// sums of dweight / dbias are reduced through shared memory in a fixed order.
+template <int NV>
+__global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restrict__ x, long long x_ld,
+                                                          const bf16* __restrict__ dy, long long dy_ld, long long rows,
+                                                          int C, int mode, const float* __restrict__ w, float eps,
+                                                          const float* __restrict__ add, long long add_ld,
+                                                          float* __restrict__ dx, long long dx_ld,
+                                                          float* __restrict__ partials, int G) {
+  extern __shared__ float sm[];                // [2][256/G][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rpw = 32 / G;
+  const int sub = lane / G, l = lane % G;
+  const int nvec = C >> 2;
+  const int slot = warp * rpw + sub;           // row slot inside the block
+  const int slots = 8 * rpw;
+  float4 aw[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) aw[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row0 = (long long)blockIdx.x * slots; row0 < rows; row0 += (long long)gridDim.x * slots) {
+    const long long row = row0 + slot;
+    const bool row_ok = row < rows;
+    float4 v[NV], g[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = l + i * G;
+      if (row_ok && idx < nvec) {
+        v[i] = mode ? *reinterpret_cast<const float4*>(x + row * x_ld + idx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint2 pk = *reinterpret_cast<const uint2*>(dy + row * dy_ld + idx * 4);
+        g[i] = make_float4(__uint_as_float(pk.x << 16), __uint_as_float(pk.x & 0xffff0000u),
+                           __uint_as_float(pk.y << 16), __uint_as_float(pk.y & 0xffff0000u));
+      } else {
+        v[i] = g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      s += v[i].x + v[i].y + v[i].z + v[i].w;
+    }
+    float mean = 0.f, rstd = 1.f, m1 = 0.f, m2 = 0.f;
+    if (mode != 0) {
+      for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      mean = s / (float)C;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int idx = l + i * G;
+        if (idx < nvec) {
+          const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+          q += a * a + b * b + c * c + d * d;
+        }
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      rstd = rsqrtf(q / (float)C + eps);
+      // xh = normalised value the forward multiplied by w: (x - mean) * rstd [mode 1] or x * rstd [mode 2]
+      // gw = dy * w;  m1 = mean(gw);  m2 = mean(gw * (x - mean) * rstd) [mode 1] / mean(gw * x) [mode 2]
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int idx = l + i * G;
+        if (idx < nvec) {
+          const float4 ww = *reinterpret_cast<const float4*>(w + idx * 4);
+          const float4 gw = make_float4(g[i].x * ww.x, g[i].y * ww.y, g[i].z * ww.z, g[i].w * ww.w);
+          float4 xh;
+          if (mode == 1) xh = make_float4((v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd);
+          else xh = make_float4(v[i].x * rstd, v[i].y * rstd, v[i].z * rstd, v[i].w * rstd);
+          if (row_ok) {
+            aw[i].x += g[i].x * xh.x; aw[i].y += g[i].y * xh.y; aw[i].z += g[i].z * xh.z; aw[i].w += g[i].w * xh.w;
+            ab[i].x += g[i].x; ab[i].y += g[i].y; ab[i].z += g[i].z; ab[i].w += g[i].w;
+          }
+          m1 += gw.x + gw.y + gw.z + gw.w;
+          if (mode == 1) m2 += gw.x * xh.x + gw.y * xh.y + gw.z * xh.z + gw.w * xh.w;
+          else m2 += gw.x * v[i].x + gw.y * v[i].y + gw.z * v[i].z + gw.w * v[i].w;
+          g[i] = gw;
+        }
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) {
+        m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+      }
+      m1 /= (float)C;
+      m2 /= (float)C;
+    }
+    if (row_ok) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int idx = l + i * G;
+        if (idx < nvec) {
+          float4 r;
+          if (mode == 1) {          // dx = rstd * (gw - mean(gw) - xh * mean(gw * xh))
+            r.x = rstd * (g[i].x - m1 - (v[i].x - mean) * rstd * m2);
+            r.y = rstd * (g[i].y - m1 - (v[i].y - mean) * rstd * m2);
+            r.z = rstd * (g[i].z - m1 - (v[i].z - mean) * rstd * m2);
+            r.w = rstd * (g[i].w - m1 - (v[i].w - mean) * rstd * m2);
+          } else if (mode == 2) {   // y = x * rstd * w : dx = rstd * gw - rstd^3 * (x - mean) * mean(gw * x)
+            const float r3 = rstd * rstd * rstd * m2;
+            r.x = rstd * g[i].x - r3 * (v[i].x - mean);
+            r.y = rstd * g[i].y - r3 * (v[i].y - mean);
+            r.z = rstd * g[i].z - r3 * (v[i].z - mean);
+            r.w = rstd * g[i].w - r3 * (v[i].w - mean);
+          } else {
+            r = g[i];
+          }
+          if (add) {
+            const float4 a4 = *reinterpret_cast<const float4*>(add + row * add_ld + idx * 4);
+            r.x += a4.x; r.y += a4.y; r.z += a4.z; r.w += a4.w;
+          }
+          *reinterpret_cast<float4*>(dx + row * dx_ld + idx * 4) = r;
+        }
+      }
+    }
+  }
+  if (!partials) return;
+  // block reduction of dweight / dbias in slot order
+  float* sw = sm;
+  float* sb = sm + (size_t)slots * C;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = l + i * G;
+    if (idx < nvec) {
+      *reinterpret_cast<float4*>(sw + (size_t)slot * C + idx * 4) = aw[i];
+      *reinterpret_cast<float4*>(sb + (size_t)slot * C + idx * 4) = ab[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    const float* src = c < C ? sw + c : sb + (c - C);
+    float s = 0.f;
+    for (int k = 0; k < slots; ++k) s += src[(size_t)k * C];
+    partials[(size_t)blockIdx.x * 2 * C + c] = s;
+  }
+}
+
+// dweight[c] (+)= sum_blk partials[blk][c];  dbias[c] (+)= sum_blk partials[blk][C + c]
+__global__ void __launch_bounds__(256) rownorm_bwd_reduce_kernel(const float* __restrict__ partials, int nblk, int C,
+                                                                 float* __restrict__ dweight, float* __restrict__ dbias,
+                                                                 int accumulate) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * C) return;
+  float* o = idx < C ? dweight + idx : (dbias ? dbias + (idx - C) : nullptr);
+  if (!o) return;
+  float s = 0.f;
+  for (int p = 0; p < nblk; ++p) s += partials[(size_t)p * 2 * C + idx];
+  *o = (accumulate ? *o : 0.f) + s;
+}
+
+// ------------------------------------------------------------------------------------------------ gate backward
+__device__ __forceinline__ void gelu_and_grad(float a, float& g, float& dg) {
+  const float cdf = 0.5f * (1.f + erff(a * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * a * a);
+  g = a * cdf;
+  dg = cdf + a * pdf;
+}
+
+// y: [rows, 2*Ch] pre-gate (a | b halves), dg: [rows, Ch].  dyo[:, :Ch] = dg * b * act'(a), dyo[:, Ch:] = dg * act(a)
+// with act = GELU (gate 1) or identity (gate 2: SimpleGate, dyo = [dg*b | dg*a]).  dyo may alias y.
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const bf16* __restrict__ y, long long y_ld,
+                                                       const bf16* __restrict__ dg, long long dg_ld, long long rows,
+                                                       int Ch, int gate, bf16* __restrict__ dyo, long long dyo_ld) {
+  const int nv = Ch >> 3;
+  const long long total = rows * nv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nv;
+    const int c = (int)(i % nv) * 8;
+    float a[8], b[8], g[8], oa[8], ob[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(y + r * y_ld + c), a);
+    unpack8(*reinterpret_cast<const bf16x8*>(y + r * y_ld + Ch + c), b);
+    unpack8(*reinterpret_cast<const bf16x8*>(dg + r * dg_ld + c), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (gate == 1) {
+        float ga, dga;
+        gelu_and_grad(a[k], ga, dga);
+        oa[k] = g[k] * b[k] * dga;
+        ob[k] = g[k] * ga;
+      } else {
+        oa[k] = g[k] * b[k];
+        ob[k] = g[k] * a[k];
+      }
+    }
+    *reinterpret_cast<bf16x8*>(dyo + r * dyo_ld + c) = pack8(oa);
+    *reinterpret_cast<bf16x8*>(dyo + r * dyo_ld + Ch + c) = pack8(ob);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ MDTA backward (small)
+// One CTA per (head, sample).  c <= 128 channels per head.  Shared: attn[c][c], dattn[c][c] (-> dS_hat), shat[c][c],
+// a [32][c] staging tile for W / dWeff rows, nq[c], nk[c], r[c], s[c].
+struct MdtaBwdArgs {
+  int C, heads, nchunks;
+  const float* partials;   // forward Gram partials (tdr_mdta_gram)
+  const float* attn;       // [B, heads, c, c]
+  const float* temperature;
+  const float* w_out;      // [C][C]
+  const float* dweff;      // [B][C][C] fp32 (per-sample wgrad of the attn.v.project_out product)
+  bf16* mqk;               // [B][2C][mqk_ld]
+  long long mqk_ld;
+  float* dwout_part;       // [B][C][C]
+  float* dtemp_part;       // [B][heads]
+};
+
+__global__ void __launch_bounds__(256) mdta_bwd_kernel(const MdtaBwdArgs a) {
+  extern __shared__ float sm[];
+  const int C = a.C, c = C / a.heads;
+  const int h = blockIdx.x, b = blockIdx.y;
+  float* attn = sm;
+  float* dat = attn + c * c;
+  float* shat = dat + c * c;
+  float* tw = shat + c * c;        // [32][c]
+  float* td = tw + 32 * c;         // [32][c]
+  float* nq = td + 32 * c;
+  float* nk = nq + c;
+  float* rr = nk + c;
+  float* ss = rr + c;
+  __shared__ float red[256];
+  const int tid = threadIdx.x;
+  const size_t psz = (size_t)c * c + 2 * c;
+  const float* pbase = a.partials + (size_t)(b * a.heads + h) * a.nchunks * psz;
+  const float* asrc = a.attn + (size_t)(b * a.heads + h) * c * c;
+  const float temp = a.temperature[h];
+  // norms
+  for (int i = tid; i < 2 * c; i += 256) {
+    float s = 0.f;
+    for (int ch = 0; ch < a.nchunks; ++ch) s += pbase[(size_t)ch * psz + c * c + i];
+    nq[i] = fmaxf(sqrtf(fmaxf(s, 0.f)), 1e-12f);        // nq then nk (contiguous)
+  }
+  __syncthreads();
+  for (int t = tid; t < c * c; t += 256) {
+    float s = 0.f;
+    for (int ch = 0; ch < a.nchunks; ++ch) s += pbase[(size_t)ch * psz + t];
+    shat[t] = s / (nq[t / c] * nk[t % c]);
+    attn[t] = asrc[t];
+    dat[t] = 0.f;
+  }
+  __syncthreads();
+  // dattn[i][j] = sum_co W[co][hc+i] * dWeff[b][co][hc+j];  thread (ti, tj) of a 16x16 grid owns i = ti + 16a, j = tj + 16b
+  const int ti = tid >> 4, tj = tid & 15;
+  float acc[8][8];
+#pragma unroll
+  for (int x = 0; x < 8; ++x)
+#pragma unroll
+    for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
+  const float* dweff = a.dweff + (size_t)b * C * C;
+  for (int co0 = 0; co0 < C; co0 += 32) {
+    __syncthreads();
+    for (int t = tid; t < 32 * c; t += 256) {
+      const int r = t / c, k = t % c;
+      const int co = co0 + r;
+      tw[t] = co < C ? a.w_out[(size_t)co * C + h * c + k] : 0.f;
+      td[t] = co < C ? dweff[(size_t)co * C + h * c + k] : 0.f;
+    }
+    __syncthreads();
+    for (int r = 0; r < 32; ++r) {
+      float wv[8], dv[8];
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        wv[x] = ti + 16 * x < c ? tw[r * c + ti + 16 * x] : 0.f;
+        dv[x] = tj + 16 * x < c ? td[r * c + tj + 16 * x] : 0.f;
+      }
+#pragma unroll
+      for (int x = 0; x < 8; ++x)
+#pragma unroll
+        for (int y = 0; y < 8; ++y) acc[x][y] = fmaf(wv[x], dv[y], acc[x][y]);
+    }
+    // dW_out[b][co][hc+i] = sum_j dWeff[co][hc+j] * attn[i][j]  for the 32 rows staged in td
+    for (int t = tid; t < 32 * c; t += 256) {
+      const int r = t / c, i = t % c;
+      const int co = co0 + r;
+      if (co < C) {
+        float s = 0.f;
+        for (int j = 0; j < c; ++j) s = fmaf(td[r * c + j], attn[i * c + j], s);
+        a.dwout_part[((size_t)b * C + co) * C + h * c + i] = s;
+      }
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 8; ++x)
+#pragma unroll
+    for (int y = 0; y < 8; ++y) {
+      const int i = ti + 16 * x, j = tj + 16 * y;
+      if (i < c && j < c) dat[i * c + j] = acc[x][y];
+    }
+  __syncthreads();
+  // softmax backward per row i: dS = attn * (dattn - sum_j dattn*attn); logits = shat * temp
+  float dtemp = 0.f;
+  for (int i = tid >> 5; i < c; i += 8) {
+    const int lane = tid & 31;
+    float s = 0.f;
+    for (int j = lane; j < c; j += 32) s += dat[i * c + j] * attn[i * c + j];
+    s = warp_sum(s);
+    float r = 0.f;
+    for (int j = lane; j < c; j += 32) {
+      const float ds = attn[i * c + j] * (dat[i * c + j] - s);
+      dtemp += ds * shat[i * c + j];
+      const float dsh = ds * temp;
+      dat[i * c + j] = dsh;                         // dat now holds dS_hat
+      r += dsh * shat[i * c + j];
+    }
+    r = warp_sum(r);
+    if (lane == 0) rr[i] = r;
+  }
+  red[tid] = dtemp;
+  __syncthreads();
+  if (tid < 32) {
+    float s = 0.f;
+    for (int k = tid; k < 256; k += 32) s += red[k];
+    s = warp_sum(s);
+    if (tid == 0) a.dtemp_part[b * a.heads + h] = s;
+  }
+  for (int j = tid; j < c; j += 256) {
+    float s = 0.f;
+    for (int i = 0; i < c; ++i) s += dat[i * c + j] * shat[i * c + j];
+    ss[j] = s;
+  }
+  __syncthreads();
+  // rows of M (zero outside this head's blocks):
+  //   dq_i = sum_j dS_hat[i][j] / (nq_i nk_j) * k_j - r_i / nq_i^2 * q_i
+  //   dk_j = sum_i dS_hat[i][j] / (nq_i nk_j) * q_i - s_j / nk_j^2 * k_j
+  bf16* mq = a.mqk + (size_t)b * 2 * C * a.mqk_ld;
+  for (int t = tid; t < c * 2 * C; t += 256) {
+    const int i = t / (2 * C), col = t % (2 * C);
+    float vq = 0.f, vk = 0.f;
+    if (col >= C + h * c && col < C + h * c + c) {          // k columns
+      const int j = col - C - h * c;
+      vq = dat[i * c + j] / (nq[i] * nk[j]);
+      if (j == i) vk = -ss[i] / (nk[i] * nk[i]);
+    } else if (col >= h * c && col < h * c + c) {           // q columns
+      const int j = col - h * c;
+      vk = dat[j * c + i] / (nq[j] * nk[i]);
+      if (j == i) vq = -rr[i] / (nq[i] * nq[i]);
+    }
+    mq[(size_t)(h * c + i) * a.mqk_ld + col] = __float2bfloat16(vq);
+    mq[(size_t)(C + h * c + i) * a.mqk_ld + col] = __float2bfloat16(vk);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small glue
+// out[r, c] = s * x[r, c] + y[r, c]   (s = *scale_ptr * scale; y optional) -- TransformerResFusionBlock R:353
+__global__ void __launch_bounds__(256) scale_add_kernel(const float* __restrict__ x, long long x_ld,
+                                                        const float* __restrict__ y, long long y_ld, long long rows,
+                                                        int C, const float* __restrict__ scale_ptr, float scale,
+                                                        float* __restrict__ out, long long out_ld) {
+  const int nv = C >> 2;
+  const float s = (scale_ptr ? *scale_ptr : 1.f) * scale;
+  const long long total = rows * nv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nv;
+    const int c = (int)(i % nv) * 4;
+    float4 v = *reinterpret_cast<const float4*>(x + r * x_ld + c);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    if (y) {
+      const float4 w = *reinterpret_cast<const float4*>(y + r * y_ld + c);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    *reinterpret_cast<float4*>(out + r * out_ld + c) = v;
+  }
+}
+
+// partial[blk] = sum over this block's elements of x * y
+__global__ void __launch_bounds__(256) dot_kernel(const float* __restrict__ x, long long x_ld, const float* __restrict__ y,
+                                                  long long y_ld, long long rows, int C, float* __restrict__ partials) {
+  __shared__ float red[8];
+  const int nv = C >> 2;
+  const long long total = rows * nv;
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nv;
+    const int c = (int)(i % nv) * 4;
+    const float4 a = *reinterpret_cast<const float4*>(x + r * x_ld + c);
+    const float4 b = *reinterpret_cast<const float4*>(y + r * y_ld + c);
+    s += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < 8; ++k) t += red[k];
+    partials[blockIdx.x] = t;
+  }
+}
+
+// mode 1 (PixelUnshuffle(2)): out[b, y/2, x/2, c*4 + (y&1)*2 + (x&1)] = in[b, y, x, c]
+// mode 2 (PixelShuffle(2))  : out[b, 2y + s/2, 2x + s%2, c/4] = in[b, y, x, c], s = c & 3      (bf16 -> bf16)
+__global__ void __launch_bounds__(256) pixel_shuffle_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H,
+                                                            int W, int C, int mode, bf16* __restrict__ out,
+                                                            long long out_ld) {
+  const long long total = (long long)B * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int x = (int)(p % W); p /= W;
+    const int y = (int)(p % H);
+    const int b = (int)(p / H);
+    const bf16 v = in[((((long long)b * H + y) * W) + x) * in_ld + c];
+    if (mode == 1) {
+      out[((((long long)b * (H >> 1) + (y >> 1)) * (W >> 1)) + (x >> 1)) * out_ld + c * 4 + ((y & 1) << 1) + (x & 1)] = v;
+    } else {
+      const int s = c & 3;
+      out[((((long long)b * (H * 2) + y * 2 + (s >> 1)) * (W * 2)) + x * 2 + (s & 1)) * out_ld + (c >> 2)] = v;
+    }
+  }
+}
+
+// dy_out = y > 0 ? dy : 0   (ReLU backward from the stored post-activation y), bf16 rows
+__global__ void __launch_bounds__(256) relu_mask_kernel(const bf16* __restrict__ y, long long y_ld,
+                                                        const bf16* __restrict__ dy, long long dy_ld, long long rows,
+                                                        int C, bf16* __restrict__ out, long long out_ld) {
+  const int nv = C >> 3;
+  const long long total = rows * nv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nv;
+    const int c = (int)(i % nv) * 8;
+    float a[8], g[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(y + r * y_ld + c), a);
+    unpack8(*reinterpret_cast<const bf16x8*>(dy + r * dy_ld + c), g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] = a[k] > 0.f ? g[k] : 0.f;
+    *reinterpret_cast<bf16x8*>(out + r * out_ld + c) = pack8(g);
+  }
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" size_t tdr_wgrad_workspace_bytes(const tdr_wgrad_desc* d) {
+  WgradPlan p;
+  if (!d || d->B <= 0 || d->H <= 0 || d->W <= 0 || d->Ci <= 0 || d->Co <= 0 || d->KH < 1 || d->KW < 1 ||
+      d->stride < 1 || d->dil < 1 || wgrad_plan(d, &p))
+    return 0;
+  return (size_t)p.nb * p.nchunks * p.T * d->Co * d->Ci * sizeof(float);
+}
+
+extern "C" int tdr_wgrad(const tdr_wgrad_desc* d, cudaStream_t stream) {
+  TDR_CHECK_ARG(d != nullptr, "tdr_wgrad: null descriptor");
+  TDR_CHECK_ARG(d->dy && d->x && d->out && d->workspace, "tdr_wgrad: null pointer");
+  TDR_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0 && d->Ci > 0 && d->Co > 0, "tdr_wgrad: bad dims");
+  TDR_CHECK_ARG(d->KH >= 1 && d->KW >= 1 && d->stride >= 1 && d->stride <= 2 && d->dil >= 1, "tdr_wgrad: bad filter geometry");
+  TDR_CHECK_ARG(d->dy_ld % 8 == 0 && d->x_ld % 8 == 0, "tdr_wgrad: row strides must be multiples of 8 (16 B rows)");
+  TDR_CHECK_ARG(((uintptr_t)d->dy & 15) == 0 && ((uintptr_t)d->x & 15) == 0, "tdr_wgrad: 16 B alignment");
+  WgradArgs a;
+  TDR_CHECK_ARG(wgrad_plan(d, &a.plan) == 0, "tdr_wgrad: unsupported shape (Co=%d Ci=%d)", d->Co, d->Ci);
+  const WgradPlan& p = a.plan;
+  const size_t need = (size_t)p.nb * p.nchunks * p.T * d->Co * d->Ci * sizeof(float);
+  TDR_CHECK_ARG(d->workspace_bytes >= need, "tdr_wgrad: workspace too small (%zu < %zu)", d->workspace_bytes, need);
+  a.Co = d->Co; a.Ci = d->Ci; a.KW = d->KW; a.stride = d->stride; a.pad = d->pad; a.dil = d->dil;
+  a.per_sample = d->per_sample; a.partials = d->workspace;
+  TdrTensorMap map_dy, map_x;
+  {
+    const uint64_t dims[4] = {(uint64_t)d->Co, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)d->B};
+    const uint64_t strides[3] = {(uint64_t)d->dy_ld * 2, (uint64_t)d->dy_ld * 2 * p.OW, (uint64_t)d->dy_ld * 2 * p.OW * p.OH};
+    const uint32_t box[4] = {64, (uint32_t)p.TW, (uint32_t)p.TH, 1};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    int rc = tdr_make_tensor_map_bf16(&map_dy, d->dy, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)d->Ci, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    const uint64_t strides[3] = {(uint64_t)d->x_ld * 2, (uint64_t)d->x_ld * 2 * d->W, (uint64_t)d->x_ld * 2 * d->W * d->H};
+    const uint32_t box[4] = {64, (uint32_t)(p.TW * d->stride), (uint32_t)(p.TH * d->stride), 1};
+    const uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
+    TDR_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "tdr_wgrad: TMA box too large");
+    int rc = tdr_make_tensor_map_bf16(&map_x, d->x, 4, dims, strides, box, es);
+    if (rc) return rc;
+  }
+  const size_t smem = 1024 + (size_t)p.stages * (p.boxes_m + p.boxes_n) * kBoxBytes + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  dim3 grid(p.nchunks, p.T * p.m_tiles * p.n_tiles, p.nb);
+  wgrad_kernel<<<grid, 192, smem, stream>>>(map_dy, map_x, a);
+  TDR_CHECK_LAUNCH();
+  const long long total = (long long)p.nb * p.T * d->Co * d->Ci;
+  wgrad_reduce_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
+      d->workspace, p.nb, p.nchunks, p.T, d->Co, d->Ci, d->out, d->out_stride_b, d->out_stride_co, d->out_stride_ci,
+      d->out_stride_tap, d->co_map, d->ci_map, d->accumulate, d->scale);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" size_t tdr_reduce_workspace_bytes(int C) { return (size_t)kRedBlocks * 10 * (size_t)(C > 0 ? C : 0) * sizeof(float); }
+
+extern "C" int tdr_colsum(const void* x_bf16, long long ld, long long rows, int C, float* out, long long out_stride,
+                          const int* c_map, int accumulate, float* workspace, cudaStream_t stream) {
+  TDR_CHECK_ARG(x_bf16 && out && workspace && rows > 0 && C > 0, "tdr_colsum: bad arguments");
+  TDR_CHECK_ARG(C % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x_bf16 & 15) == 0, "tdr_colsum: C, ld multiples of 8, 16 B aligned");
+  int nblk = (int)((rows + 7) / 8 < kRedBlocks ? (rows + 7) / 8 : kRedBlocks);
+  dim3 grid(nblk, tdr_cdiv(C / 8, 256));
+  colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x_bf16), ld, rows, C, workspace);
+  TDR_CHECK_LAUNCH();
+  reduce_parts_kernel<<<tdr_cdiv(C, 256), 256, 0, stream>>>(workspace, nblk, C, out, out_stride, c_map, accumulate, 1.f);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_dwconv3x3_wgrad(const void* dy_bf16, long long dy_ld, const void* x_bf16, long long x_ld, int B, int H,
+                                   int W, int C, float* dw, float* db, const int* c_map, int accumulate,
+                                   float* workspace, cudaStream_t stream) {
+  TDR_CHECK_ARG(dy_bf16 && x_bf16 && dw && workspace, "tdr_dwconv3x3_wgrad: null pointer");
+  TDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "tdr_dwconv3x3_wgrad: bad dims");
+  TDR_CHECK_ARG(dy_ld % 8 == 0 && x_ld % 8 == 0 && ((uintptr_t)dy_bf16 & 15) == 0 && ((uintptr_t)x_bf16 & 15) == 0,
+                "tdr_dwconv3x3_wgrad: alignment");
+  const long long npix = (long long)B * H * W;
+  int nblk = (int)((npix + 63) / 64 < kRedBlocks ? (npix + 63) / 64 : kRedBlocks);
+  dim3 grid(nblk, tdr_cdiv(C / 8, 256));
+  dw_wgrad_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy_bf16), dy_ld,
+                                            reinterpret_cast<const bf16*>(x_bf16), x_ld, B, H, W, C, workspace);
+  TDR_CHECK_LAUNCH();
+  dw_wgrad_reduce_kernel<<<tdr_cdiv(10 * C, 256), 256, 0, stream>>>(workspace, nblk, C, dw, db, c_map, accumulate);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf16, long long dy_ld, long long rows, int C,
+                               int mode, const float* weight, float eps, const float* add, long long add_ld, float* dx,
+                               long long dx_ld, float* dweight, float* dbias, int accumulate, float* workspace,
+                               cudaStream_t stream) {
+  TDR_CHECK_ARG(dy_bf16 && dx && rows > 0 && C > 0, "tdr_rownorm_bwd: bad arguments");
+  TDR_CHECK_ARG(mode >= 0 && mode <= 2, "tdr_rownorm_bwd: bad mode");
+  TDR_CHECK_ARG(mode == 0 || (x && weight), "tdr_rownorm_bwd: x and weight required");
+  TDR_CHECK_ARG(C % 4 == 0 && x_ld % 4 == 0 && dy_ld % 4 == 0 && add_ld % 4 == 0 && dx_ld % 4 == 0,
+                "tdr_rownorm_bwd: C and strides must be multiples of 4");
+  TDR_CHECK_ARG(C <= 4096, "tdr_rownorm_bwd: C too large (%d)", C);
+  const bool want_w = mode != 0 && dweight != nullptr;
+  TDR_CHECK_ARG(!want_w || workspace, "tdr_rownorm_bwd: workspace required for the weight gradient");
+  const int nvec = C / 4;
+  int G = 1;
+  while (G < 32 && (nvec + G - 1) / G > 4) G <<= 1;
+  const int nv = (nvec + G - 1) / G;
+  const int slots = 8 * (32 / G);
+  long long nb = (rows + slots - 1) / slots;
+  const int blocks = (int)(nb < kRedBlocks ? nb : kRedBlocks);
+  const size_t smem = want_w ? (size_t)2 * slots * C * sizeof(float) : 0;
+  TDR_CHECK_ARG(smem <= 200 * 1024, "tdr_rownorm_bwd: C too large for the weight-gradient reduction");
+  const bf16* g = reinterpret_cast<const bf16*>(dy_bf16);
+  float* parts = want_w ? workspace : nullptr;
+#define TDR_RNB(NV)                                                                                                    \
+  do {                                                                                                                 \
+    static bool attr_set = false;                                                                                      \
+    if (!attr_set) {                                                                                                   \
+      TDR_CHECK_CUDA(cudaFuncSetAttribute(rownorm_bwd_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
+      attr_set = true;                                                                                                 \
+    }                                                                                                                  \
+    rownorm_bwd_kernel<NV><<<blocks, 256, smem, stream>>>(x, x_ld, g, dy_ld, rows, C, mode, weight, eps, add, add_ld, dx, \
+                                                          dx_ld, parts, G);                                            \
+  } while (0)
+  if (nv <= 1) TDR_RNB(1);
+  else if (nv <= 2) TDR_RNB(2);
+  else if (nv <= 3) TDR_RNB(3);
+  else if (nv <= 4) TDR_RNB(4);
+  else if (nv <= 8) TDR_RNB(8);
+  else if (nv <= 16) TDR_RNB(16);
+  else TDR_RNB(32);
+#undef TDR_RNB
+  TDR_CHECK_LAUNCH();
+  if (want_w) {
+    // partials rows are [dweight(C) | dbias(C)] per block
+    rownorm_bwd_reduce_kernel<<<tdr_cdiv(2 * C, 256), 256, 0, stream>>>(workspace, blocks, C, dweight, dbias, accumulate);
+    TDR_CHECK_LAUNCH();
+  }
+  return TDR_OK;
+}
+
+extern "C" int tdr_gate_bwd(const void* y_bf16, long long y_ld, const void* dg_bf16, long long dg_ld, long long rows,
+                            int Ch, int gate, void* dy_bf16, long long dy_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(y_bf16 && dg_bf16 && dy_bf16 && rows > 0 && Ch > 0, "tdr_gate_bwd: bad arguments");
+  TDR_CHECK_ARG(gate == 1 || gate == 2, "tdr_gate_bwd: gate must be 1 (GELU) or 2 (SimpleGate)");
+  TDR_CHECK_ARG(Ch % 8 == 0 && y_ld % 8 == 0 && dg_ld % 8 == 0 && dy_ld % 8 == 0, "tdr_gate_bwd: multiples of 8");
+  gate_bwd_kernel<<<grid_for(rows * (Ch / 8), 256, 16), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(y_bf16), y_ld, reinterpret_cast<const bf16*>(dg_bf16), dg_ld, rows, Ch, gate,
+      reinterpret_cast<bf16*>(dy_bf16), dy_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_mdta_bwd(const float* partials, const float* attn, int B, long long P, int C, int heads,
+                            const float* temperature, const float* w_out, const float* dweff, void* mqk_bf16,
+                            long long mqk_ld, float* dw_out, float* dtemperature, int accumulate, float* workspace,
+                            cudaStream_t stream) {
+  TDR_CHECK_ARG(partials && attn && temperature && w_out && dweff && mqk_bf16 && dw_out && dtemperature && workspace,
+                "tdr_mdta_bwd: null pointer");
+  TDR_CHECK_ARG(heads > 0 && C % heads == 0 && C / heads <= 128 && B > 0, "tdr_mdta_bwd: unsupported head width");
+  TDR_CHECK_ARG(mqk_ld >= 2 * C && mqk_ld % 8 == 0, "tdr_mdta_bwd: bad mqk_ld");
+  const size_t nbytes = tdr_mdta_partials_bytes(B, P, C, heads);
+  TDR_CHECK_ARG(nbytes != 0, "tdr_mdta_bwd: unsupported MDTA shape");
+  const int c = C / heads;
+  MdtaBwdArgs a;
+  a.C = C; a.heads = heads;
+  a.nchunks = (int)(nbytes / sizeof(float) / ((size_t)B * heads * ((size_t)c * c + 2 * c)));
+  a.partials = partials; a.attn = attn; a.temperature = temperature; a.w_out = w_out; a.dweff = dweff;
+  a.mqk = reinterpret_cast<bf16*>(mqk_bf16); a.mqk_ld = mqk_ld;
+  a.dwout_part = workspace;                       // [B][C][C]
+  a.dtemp_part = workspace + (size_t)B * C * C;   // [B][heads]
+  const size_t smem = ((size_t)3 * c * c + 64 * c + 4 * c) * sizeof(float);
+  TDR_CHECK_ARG(smem <= 220 * 1024, "tdr_mdta_bwd: head too wide for shared memory");
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(mdta_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  mdta_bwd_kernel<<<dim3(heads, B), 256, smem, stream>>>(a);
+  TDR_CHECK_LAUNCH();
+  reduce_parts_kernel<<<tdr_cdiv(C * C, 256), 256, 0, stream>>>(a.dwout_part, B, C * C, dw_out, 1, nullptr, accumulate, 1.f);
+  TDR_CHECK_LAUNCH();
+  reduce_parts_kernel<<<1, 256, 0, stream>>>(a.dtemp_part, B, heads, dtemperature, 1, nullptr, accumulate, 1.f);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" size_t tdr_mdta_bwd_workspace_bytes(int B, int C, int heads) {
+  return ((size_t)B * C * C + (size_t)B * heads) * sizeof(float);
+}
+
+extern "C" int tdr_scale_add_f32(const float* x, long long x_ld, const float* y, long long y_ld, long long rows, int C,
+                                 const float* scale_ptr, float scale, float* out, long long out_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(x && out && rows > 0 && C > 0 && C % 4 == 0 && x_ld % 4 == 0 && y_ld % 4 == 0 && out_ld % 4 == 0,
+                "tdr_scale_add_f32: bad arguments");
+  scale_add_kernel<<<grid_for(rows * (C / 4), 256, 16), 256, 0, stream>>>(x, x_ld, y, y_ld, rows, C, scale_ptr, scale, out, out_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_dot_f32(const float* x, long long x_ld, const float* y, long long y_ld, long long rows, int C,
+                           float* out, int accumulate, float* workspace, cudaStream_t stream) {
+  TDR_CHECK_ARG(x && y && out && workspace && rows > 0 && C > 0 && C % 4 == 0 && x_ld % 4 == 0 && y_ld % 4 == 0,
+                "tdr_dot_f32: bad arguments");
+  const int nblk = grid_for(rows * (C / 4), 256, 2);
+  dot_kernel<<<nblk, 256, 0, stream>>>(x, x_ld, y, y_ld, rows, C, workspace);
+  TDR_CHECK_LAUNCH();
+  reduce_parts_kernel<<<1, 32, 0, stream>>>(workspace, nblk, 1, out, 1, nullptr, accumulate, 1.f);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_pixel_shuffle_nhwc(const void* in_bf16, long long in_ld, int B, int H, int W, int C, int mode,
+                                      void* out_bf16, long long out_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(in_bf16 && out_bf16 && B > 0 && H > 0 && W > 0 && C > 0, "tdr_pixel_shuffle_nhwc: bad arguments");
+  TDR_CHECK_ARG(mode == 1 ? (H % 2 == 0 && W % 2 == 0) : (mode == 2 && C % 4 == 0), "tdr_pixel_shuffle_nhwc: bad mode/shape");
+  pixel_shuffle_kernel<<<grid_for((long long)B * H * W * C, 256, 16), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(in_bf16), in_ld, B, H, W, C, mode, reinterpret_cast<bf16*>(out_bf16), out_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_relu_mask(const void* y_bf16, long long y_ld, const void* dy_bf16, long long dy_ld, long long rows,
+                             int C, void* out_bf16, long long out_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(y_bf16 && dy_bf16 && out_bf16 && rows > 0 && C > 0 && C % 8 == 0 && y_ld % 8 == 0 && dy_ld % 8 == 0 &&
+                    out_ld % 8 == 0,
+                "tdr_relu_mask: bad arguments");
+  relu_mask_kernel<<<grid_for(rows * (C / 8), 256, 16), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(y_bf16), y_ld, reinterpret_cast<const bf16*>(dy_bf16), dy_ld, rows, C,
+      reinterpret_cast<bf16*>(out_bf16), out_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}

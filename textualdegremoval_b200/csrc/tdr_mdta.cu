@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
 // Stage 2: grid (ceil(C/32), heads, B).  Weff[b][co][h*c + j] = sum_i W_out[co][h*c + i] * attn[b,h,i,j]
 __global__ void __launch_bounds__(256) mdta_fold_kernel(const float* __restrict__ attn, int C, int heads,
                                                         const float* __restrict__ w_out, bf16* __restrict__ weff,
-                                                        long long weff_ld) {
+                                                        long long weff_ld, bf16* __restrict__ weff_t) {
   extern __shared__ float sm[];
   const int c = C / heads;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(256) mdta_fold_kernel(const float* __restrict_
 #pragma unroll 4
     for (int i = 0; i < c; ++i) s = fmaf(wr[i], a[i * c + j], s);
     weff[((size_t)b * C + co0 + r) * weff_ld + h * c + j] = __float2bfloat16(s);
+    if (weff_t) weff_t[((size_t)b * C + h * c + j) * weff_ld + co0 + r] = __float2bfloat16(s);   // transposed (dgrad)
   }
 }
 
@@ -289,7 +290,7 @@ extern "C" int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long lon
 
 extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature,
                              const float* w_out, void* weff_bf16, long long weff_ld, float* attn_ws,
-                             cudaStream_t stream) {
+                             void* weff_t_bf16, cudaStream_t stream) {
   TDR_CHECK_ARG(partials && temperature && w_out && weff_bf16 && attn_ws, "tdr_mdta_weff: null pointer");
   GramPlan p;
   TDR_CHECK_ARG(make_plan(B, P, C, heads, &p) == 0, "tdr_mdta_weff: unsupported head width");
@@ -306,7 +307,8 @@ extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, i
     attr_set = true;
   }
   dim3 grid((C + 31) / 32, heads, B);
-  mdta_fold_kernel<<<grid, 256, smem, stream>>>(attn_ws, C, heads, w_out, reinterpret_cast<bf16*>(weff_bf16), weff_ld);
+  mdta_fold_kernel<<<grid, 256, smem, stream>>>(attn_ws, C, heads, w_out, reinterpret_cast<bf16*>(weff_bf16), weff_ld,
+                                            reinterpret_cast<bf16*>(weff_t_bf16));
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -55,7 +55,7 @@ SIGNATURES = {
     "tdr_naf_sca_fold": (_i, [_vp, _ll, _i, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp]),
     "tdr_mdta_partials_bytes": (_sz, [_i, _ll, _i, _i]),
     "tdr_mdta_gram": (_i, [_vp, _ll, _i, _ll, _i, _i, _vp, _vp]),
-    "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp]),
+    "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp]),
     "tdr_vit_patchify": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
     "tdr_vit_assemble_tokens": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tdr_softmax_rows": (_i, [_vp, _ll, _ll, _i, _f, _vp, _ll, _vp]),
@@ -80,6 +80,41 @@ SIGNATURES = {
     "tdr_masa_fine_argmax": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "tdr_masa_transfer": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),
 }
+
+
+
+class WgradDesc(C.Structure):
+    """Mirror of ``tdr_wgrad_desc`` (include/tdr_sm100.h)."""
+    _fields_ = [
+        ("dy", C.c_void_p), ("dy_ld", C.c_longlong),
+        ("x", C.c_void_p), ("x_ld", C.c_longlong),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Ci", C.c_int), ("Co", C.c_int), ("KH", C.c_int),
+        ("KW", C.c_int), ("stride", C.c_int), ("pad", C.c_int), ("dil", C.c_int),
+        ("per_sample", C.c_int),
+        ("out", C.c_void_p),
+        ("out_stride_b", C.c_longlong), ("out_stride_co", C.c_longlong), ("out_stride_ci", C.c_longlong),
+        ("out_stride_tap", C.c_longlong),
+        ("co_map", C.c_void_p), ("ci_map", C.c_void_p),
+        ("accumulate", C.c_int), ("scale", C.c_float),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+SIGNATURES.update({
+    "tdr_wgrad_workspace_bytes": (_sz, [C.POINTER(WgradDesc)]),
+    "tdr_wgrad": (_i, [C.POINTER(WgradDesc), _vp]),
+    "tdr_reduce_workspace_bytes": (_sz, [_i]),
+    "tdr_colsum": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp, _i, _vp, _vp]),
+    "tdr_dwconv3x3_wgrad": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
+    "tdr_rownorm_bwd": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _f, _vp, _ll, _vp, _ll, _vp, _vp, _i, _vp, _vp]),
+    "tdr_gate_bwd": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _ll, _vp]),
+    "tdr_mdta_bwd_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tdr_mdta_bwd": (_i, [_vp, _vp, _i, _ll, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _i, _vp, _vp]),
+    "tdr_scale_add_f32": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _f, _vp, _ll, _vp]),
+    "tdr_dot_f32": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _i, _vp, _vp]),
+    "tdr_pixel_shuffle_nhwc": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
+    "tdr_relu_mask": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _ll, _vp]),
+})
 
 _lib = None
 

@@ -216,8 +216,9 @@ def dwconv3x3(x, w9, bias=None, gate=0, out=None):
     return out
 
 
-def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False):
-    """qkv: bf16 NHWC [B,H,W,>=3C].  Returns Weff bf16 [B, C, C_p] (and attn fp32 [B,heads,c,c])."""
+def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False, save=None):
+    """qkv: bf16 NHWC [B,H,W,>=3C].  Returns Weff bf16 [B, C, C_p] (and attn fp32 [B,heads,c,c]).
+    save: optional dict that receives partials / attn / weff / weff_t (what the backward pass needs)."""
     B, H, W, _ = qkv.shape
     P = H * W
     nbytes = lib.load().tdr_mdta_partials_bytes(B, P, C_, heads)
@@ -229,8 +230,11 @@ def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False):
     cp = round_up(C_, 8)
     weff = torch.empty((B, C_, cp), dtype=BF16, device=qkv.device)
     attn = torch.empty((B, heads, C_ // heads, C_ // heads), dtype=F32, device=qkv.device)
+    weff_t = torch.zeros((B, C_, cp), dtype=BF16, device=qkv.device) if save is not None else None
     _call("tdr_mdta_weff", _p(partials), B, P, C_, heads, _p(temperature), _p(w_out), _p(weff), cp, _p(attn),
-          _stream(), tag=f"C{C_}_h{heads}", nbytes=nbytes + _nb(weff))
+          _p(weff_t), _stream(), tag=f"C{C_}_h{heads}", nbytes=nbytes + _nb(weff))
+    if save is not None:
+        save.update(partials=partials, attn=attn, weff=weff, weff_t=weff_t)
     return (weff, attn) if want_attn else weff
 
 
@@ -265,6 +269,14 @@ def nchw_to_nhwc(x, pad_h, pad_w, want_bf16=False):
     o16 = torch.empty((B, pad_h, pad_w, Cc), dtype=BF16, device=x.device) if want_bf16 else None
     _call("tdr_nchw_to_nhwc", _p(x), B, Cc, H, W, pad_h, pad_w, _p(o32), Cc, _p(o16), Cc, _stream())
     return (o32, o16) if want_bf16 else o32
+
+
+def nchw_to_nhwc_into(x, pad_h, pad_w, dst32=None, dst16=None):
+    """NCHW fp32 -> existing NHWC buffers (any channel width >= C; only the first C channels are written)."""
+    x = x.contiguous().float()
+    B, Cc, H, W = x.shape
+    _call("tdr_nchw_to_nhwc", _p(x), B, Cc, H, W, pad_h, pad_w, _p(dst32), _ld(dst32) if dst32 is not None else 0,
+          _p(dst16), _ld(dst16) if dst16 is not None else 0, _stream())
 
 
 def nhwc_to_nchw(x32, out_h, out_w, res=None):
@@ -432,4 +444,140 @@ def cosine_rows(fl, fr, n):
     B, Fdim = fl.shape[0], fl.numel() // fl.shape[0]
     out = torch.empty((B, n), dtype=F32, device=fl.device)
     _call("tdr_cosine_rows", _p(fl), _p(fr), B, n, Fdim, _p(out), _stream())
+    return out
+
+
+# ---------------------------------------------------------------------------------------------- backward (training)
+_WS = {}
+
+
+def workspace(nbytes, dev):
+    """Grow-only fp32 scratch buffer per device (stream-ordered reuse: every consumer runs on the current stream)."""
+    t = _WS.get(dev)
+    n = (int(nbytes) + 3) // 4
+    if t is None or t.numel() < n:
+        t = torch.empty(max(n, 1 << 20), dtype=F32, device=dev)
+        _WS[dev] = t
+    return t
+
+
+def wgrad(dy16, x16, out, *, Co=None, Ci=None, k=1, stride=1, pad=0, dil=1, per_sample=False, strides=None,
+          co_map=None, ci_map=None, accumulate=True, scale=1.0):
+    """Weight gradient of a dense conv.  dy16 bf16 NHWC [B,OH,OW,>=Co], x16 bf16 NHWC [B,H,W,>=Ci]; ``out`` fp32 in
+    the PARAMETER layout [Co, Ci, k, k] (default strides) or any layout given by strides=(s_b, s_co, s_ci, s_tap)."""
+    assert dy16.dtype == BF16 and x16.dtype == BF16 and out.dtype == F32
+    B, H, W, Cx = x16.shape
+    Co = dy16.shape[3] if Co is None else Co
+    Ci = Cx if Ci is None else Ci
+    d = lib.WgradDesc()
+    d.dy = dy16.data_ptr(); d.dy_ld = _ld(dy16)
+    d.x = x16.data_ptr(); d.x_ld = _ld(x16)
+    d.B = B; d.H = H; d.W = W; d.Ci = Ci; d.Co = Co; d.KH = k; d.KW = k; d.stride = stride; d.pad = pad; d.dil = dil
+    d.per_sample = int(per_sample)
+    OH = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    OW = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    assert dy16.shape[0] == B and dy16.shape[1] == OH and dy16.shape[2] == OW, \
+        f"wgrad: dy {tuple(dy16.shape)} does not match conv output {(B, OH, OW)}"
+    if strides is None:
+        ci_l = out.shape[1]
+        strides = (0, ci_l * k * k, k * k, 1)
+    d.out = out.data_ptr()
+    d.out_stride_b, d.out_stride_co, d.out_stride_ci, d.out_stride_tap = strides
+    d.co_map = co_map.data_ptr() if co_map is not None else None
+    d.ci_map = ci_map.data_ptr() if ci_map is not None else None
+    d.accumulate = int(accumulate); d.scale = scale
+    nbytes = lib.load().tdr_wgrad_workspace_bytes(C.byref(d))
+    if nbytes == 0:
+        raise lib.TdrError(f"tdr_wgrad: unsupported shape Co={Co} Ci={Ci} k={k}")
+    ws = workspace(nbytes, x16.device)
+    d.workspace = ws.data_ptr(); d.workspace_bytes = ws.numel() * 4
+    _call("tdr_wgrad", C.byref(d), _stream(), tag=f"k{k}s{stride}_Ci{Ci}_Co{Co}_{OH}x{OW}" + ("_ps" if per_sample else ""),
+          nbytes=B * H * W * Ci * 2 * (1 if k == 1 else 1) + B * OH * OW * Co * 2, flops=2 * B * OH * OW * Co * Ci * k * k)
+    return out
+
+
+def _red_ws(Cc, dev):
+    return workspace(lib.load().tdr_reduce_workspace_bytes(Cc), dev)
+
+
+def colsum(x16, out, c_map=None, accumulate=True, Cc=None):
+    B, H, W, Cx = x16.shape
+    Cc = Cx if Cc is None else Cc
+    _call("tdr_colsum", _p(x16), _ld(x16), B * H * W, Cc, _p(out), 1, _p(c_map), int(accumulate), _p(_red_ws(Cc, x16.device)),
+          _stream(), tag=f"C{Cc}", nbytes=B * H * W * Cc * 2)
+    return out
+
+
+def dwconv3x3_wgrad(dy16, x16, dw, db=None, c_map=None, accumulate=True):
+    B, H, W, Cc = x16.shape
+    assert dy16.shape == x16.shape
+    _call("tdr_dwconv3x3_wgrad", _p(dy16), _ld(dy16), _p(x16), _ld(x16), B, H, W, Cc, _p(dw), _p(db), _p(c_map),
+          int(accumulate), _p(_red_ws(Cc, x16.device)), _stream(), tag=f"C{Cc}_{H}x{W}", nbytes=B * H * W * Cc * 4,
+          flops=2 * 9 * B * H * W * Cc)
+
+
+def rownorm_bwd(x32, dy16, mode, weight=None, eps=1e-5, add=None, out=None, dweight=None, dbias=None, accumulate=True):
+    """dx = add + LN_bwd(dy) (fp32).  mode 0: dx = add + float(dy).  out may alias add."""
+    B, H, W, Cc = dy16.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=F32, device=dy16.device)
+    _call("tdr_rownorm_bwd", _p(x32), _ld(x32) if x32 is not None else 0, _p(dy16), _ld(dy16), B * H * W, Cc, mode,
+          _p(weight), eps, _p(add), _ld(add) if add is not None else 0, _p(out), _ld(out), _p(dweight), _p(dbias),
+          int(accumulate), _p(_red_ws(Cc, dy16.device)) if dweight is not None else None, _stream(), tag=f"m{mode}_C{Cc}",
+          nbytes=B * H * W * Cc * (2 + 4 + (4 if mode else 0) + (4 if add is not None else 0)))
+    return out
+
+
+def gate_bwd(y16, dg16, gate, out=None):
+    B, H, W, C2 = y16.shape
+    if out is None:
+        out = y16
+    _call("tdr_gate_bwd", _p(y16), _ld(y16), _p(dg16), _ld(dg16), B * H * W, C2 // 2, gate, _p(out), _ld(out), _stream(),
+          tag=f"g{gate}_C{C2}", nbytes=B * H * W * C2 * 5)
+    return out
+
+
+def mdta_bwd(saved, B, P, C_, heads, temperature, w_out, dweff, dw_out, dtemp):
+    """Returns mqk bf16 [B, 2C, 2C_p]: [dq; dk] = mqk[b] . [q; k].  Accumulates dw_out [C,C] and dtemp [heads]."""
+    cp2 = round_up(2 * C_, 8)
+    mqk = torch.zeros((B, 2 * C_, cp2), dtype=BF16, device=dweff.device)
+    ws = workspace(lib.load().tdr_mdta_bwd_workspace_bytes(B, C_, heads), dweff.device)
+    _call("tdr_mdta_bwd", _p(saved["partials"]), _p(saved["attn"]), B, P, C_, heads, _p(temperature), _p(w_out), _p(dweff),
+          _p(mqk), cp2, _p(dw_out), _p(dtemp), 1, _p(ws), _stream(), tag=f"C{C_}_h{heads}")
+    return mqk
+
+
+def scale_add(x32, y32=None, scale_ptr=None, scale=1.0, out=None):
+    B, H, W, Cc = x32.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=F32, device=x32.device)
+    _call("tdr_scale_add_f32", _p(x32), _ld(x32), _p(y32), _ld(y32) if y32 is not None else 0, B * H * W, Cc,
+          _p(scale_ptr), scale, _p(out), _ld(out), _stream(), tag=f"C{Cc}",
+          nbytes=B * H * W * Cc * (8 + (4 if y32 is not None else 0)))
+    return out
+
+
+def dot_f32(x32, y32, out, accumulate=True):
+    B, H, W, Cc = x32.shape
+    _call("tdr_dot_f32", _p(x32), _ld(x32), _p(y32), _ld(y32), B * H * W, Cc, _p(out), int(accumulate),
+          _p(workspace(1 << 16, x32.device)), _stream(), tag=f"C{Cc}", nbytes=B * H * W * Cc * 8)
+    return out
+
+
+def pixel_shuffle(x16, mode):
+    """mode 1: PixelUnshuffle(2) [B,H,W,C] -> [B,H/2,W/2,4C]; mode 2: PixelShuffle(2) [B,H,W,C] -> [B,2H,2W,C/4]."""
+    B, H, W, Cc = x16.shape
+    oshape = (B, H // 2, W // 2, Cc * 4) if mode == 1 else (B, H * 2, W * 2, Cc // 4)
+    out = torch.empty(oshape, dtype=BF16, device=x16.device)
+    _call("tdr_pixel_shuffle_nhwc", _p(x16), _ld(x16), B, H, W, Cc, mode, _p(out), _ld(out), _stream(),
+          tag=f"m{mode}_C{Cc}", nbytes=B * H * W * Cc * 4)
+    return out
+
+
+def relu_mask(y16, dy16, out=None):
+    B, H, W, Cc = y16.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=BF16, device=y16.device)
+    _call("tdr_relu_mask", _p(y16), _ld(y16), _p(dy16), _ld(dy16), B * H * W, Cc, _p(out), _ld(out), _stream(),
+          tag=f"C{Cc}", nbytes=B * H * W * Cc * 6)
     return out
