@@ -249,6 +249,22 @@ int tdr_pixel_shuffle_nhwc(const void* in_bf16, long long in_ld, int B, int H, i
 int tdr_relu_mask(const void* y_bf16, long long y_ld, const void* dy_bf16, long long dy_ld, long long rows, int C,
                   void* out_bf16, long long out_ld, cudaStream_t stream);
 
+/* Backward of the MASA transfer / confidence path (the matches themselves are arg-max constants).
+ *   tdr_masa_transfer_bwd: dref[gathered ref pixel] += dout * a / cnt  and  datt[win, q] += bilinear^T(sum_c dout * mean)
+ *                          (dref fp32 [B, Hr_s, Wr_s, C] and datt fp32 [nwin, k_y*k_x] are accumulated with fp32 atomics
+ *                          and must be zero-initialised by the caller; the only non-deterministic reductions here).
+ *   tdr_masa_fine_bwd    : gradient of att = max cosine (R:661-670) w.r.t. the deepest lq and ref features.
+ *   tdr_dilate2_nhwc     : zero insertion out[b,2y,2x,:] = in[b,y,x,:] (adjoint of stride 2; out pre-zeroed), so the
+ *                          data gradient of the stride-2 convs R:109-116 is a stride-1 tdr_conv_gemm. */
+int tdr_masa_transfer_bwd(const float* dout, long long dout_ld, const void* f_ref_bf16, int B, int Hr_s, int Wr_s, int C,
+                          const int* origin, const int* index, const float* att, int py, int px, int k_y, int k_x,
+                          int d_x, int s, float* dref, float* datt, cudaStream_t stream);
+int tdr_masa_fine_bwd(const void* f_lq_bf16, int B, int H, int W, const void* f_ref_bf16, int Hr, int Wr, int C, int k_y,
+                      int k_x, int d_x, const int* origin, const int* index, const float* datt, float* dlq, float* dref,
+                      cudaStream_t stream);
+int tdr_dilate2_nhwc(const void* in_bf16, long long in_ld, int B, int H, int W, int C, void* out_bf16, long long out_ld,
+                     int OH, int OW, cudaStream_t stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Layout / copies.
  * ------------------------------------------------------------------------------------------------------------- */

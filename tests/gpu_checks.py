@@ -829,6 +829,70 @@ def check_restormer_grad():
                         note=f"worst per-tensor rel-L2: {worst[0]}"))
     return out
 
+
+def _grad_compare(tag, net, sdg, out, groups=None):
+    """Appends global / worst / per-group rel-L2 between net.parameters().grad and the oracle's autograd grads."""
+    num = den = 0.0
+    worst = ("", 0.0)
+    gsum = {}
+    for n, p in net.named_parameters():
+        gr = sdg[n].grad
+        if gr is None:
+            gr = torch.zeros_like(sdg[n])
+        if p.grad is None:
+            out.append(dict(name=f"grad_{tag}_{n}", ok=False, max_err=None, note="no gradient"))
+            continue
+        g = p.grad.float().cpu()
+        e2 = (g - gr).pow(2).sum().item()
+        r2 = gr.pow(2).sum().item()
+        num += e2
+        den += r2
+        rel = (e2 / max(r2, 1e-30)) ** 0.5
+        if rel > worst[1] and r2 > 0:
+            worst = (n, rel)
+        key = n.split(".")[0]
+        a = gsum.setdefault(key, [0.0, 0.0])
+        a[0] += e2
+        a[1] += r2
+    tot = (num / max(den, 1e-30)) ** 0.5
+    return tot, worst, {k_: (v[0] / max(v[1], 1e-30)) ** 0.5 for k_, v in gsum.items()}
+
+
+def check_guided_grad():
+    """RestormerRefFusion end-to-end: L1 loss backward through fusion blocks, MASA transfer / confidence and the shared
+    feature encoder vs autograd through the oracle (the arg-max matches are constants on both sides; a few near-tied
+    fine matches flip with bf16 features, which perturbs the guidance gradients inside the affected 8x8 patches)."""
+    from oracle import restormer as O, weights as Wt
+    from oracle.make_golden import guided_inputs
+    from textualdegremoval_b200.archs import define_network
+    out = []
+    for name in ("guided_restormer_128", "guided_restormer_ragged"):
+        meta, _ = _golden(name)
+        net = define_network(dict(type="RestormerRefFusion", **meta["cfg"]))
+        sd = Wt.load_seeded(net, meta["seed"])
+        lq, rf = guided_inputs(meta)
+        gt = Wt.seeded_image("gt", meta["lq"], meta["seed"])
+        sdg = {k_: v.clone().requires_grad_(True) for k_, v in sd.items()}
+        yr = O.restormer_ref_fusion_forward(sdg, lq, rf, meta["cfg"]["heads"])
+        lr = (yr - gt).abs().mean()
+        lr.backward()
+        net = net.to(DEV).train()
+        y = net(lq.to(DEV), rf.to(DEV))
+        loss = (y - gt.to(DEV)).abs().mean()
+        loss.backward()
+        out.append(guided_result(f"train_fwd_{name}", y.detach().cpu(), yr.detach()))
+        tot, worst, groups = _grad_compare(name, net, sdg, out)
+        body = {k_: v for k_, v in groups.items() if "masa" not in k_}
+        masa = {k_: v for k_, v in groups.items() if "masa" in k_}
+        note = "per-module rel-L2: " + ", ".join(f"{k_}={v:.3f}" for k_, v in sorted(groups.items(), key=lambda kv: -kv[1])[:6])
+        out.append(dict(name=f"grad_global_{name}", max_err=tot, tol=0.02, ok=bool(tot <= 0.02), note=note))
+        wb = max(body.values())
+        out.append(dict(name=f"grad_body_{name}", max_err=wb, tol=0.05, ok=bool(wb <= 0.05), note="worst non-masa module"))
+        wm = max(masa.values())
+        out.append(dict(name=f"grad_masa_{name}", max_err=wm, tol=0.06, ok=bool(wm <= 0.06),
+                        note=f"worst masa module (match flips perturb these); worst tensor {worst[0]} {worst[1]:.3f}"))
+    return out
+
 CHECKS = {
     "layout": check_layout,
     "rownorm": check_rownorm,
@@ -851,6 +915,7 @@ CHECKS = {
     "bwd_pointwise": check_bwd_pointwise,
     "block_bwd": check_block_bwd,
     "restormer_grad": check_restormer_grad,
+    "guided_grad": check_guided_grad,
 }
 
 

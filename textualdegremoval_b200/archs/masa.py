@@ -107,5 +107,98 @@ class MasaMixin:
         for lev in range(nlev):
             s = 2 ** (nlev - 1 - lev)
             ops.masa_transfer(f_ref[lev], origin, index, att, py, px, k_y, k_x, d_x, s, out32=targets[lev])
-        return dict(idx=idx, origin=origin, index=index, att=att, score=score, corr=corr)
+        return dict(idx=idx, origin=origin, index=index, att=att, score=score, corr=corr,
+                    geom=dict(py=py, px=px, k_y=k_y, k_x=k_x, d_x=d_x, d_y=d_y))
 
+
+
+# =============================================================================================== training (tape + backward)
+def _flip_T(w):
+    return w.detach().permute(1, 0, 2, 3).flip(2, 3)
+
+
+class MasaTrainMixin:
+    """Training forward (keeps every activation of the feature encoder and the match aux tensors) and explicit backward
+    of the MASA guidance path.  The matches (coarse / fine arg-max) are constants; gradients flow through the gathered
+    reference features (R:698-715) and through the confidence map ``soft_att`` (R:661-670)."""
+
+    def _prep_masa_train(self, E):
+        if E.get("_train"):
+            return E
+        for i in range(1, self.masa_enc.levels + 1):
+            c = getattr(self.masa_enc, f"conv_L{i}")
+            if i > 1:
+                E[f"conv_L{i}"]["wT"] = ops.pack_conv_weight(_flip_T(c.weight))
+            for (c1, c2), b in zip(E[f"blk_L{i}"], getattr(self.masa_enc, f"blk_L{i}")):
+                c1["wT"] = ops.pack_conv_weight(_flip_T(b.conv1.weight))
+                c2["wT"] = ops.pack_conv_weight(_flip_T(b.conv2.weight))
+        E["_train"] = True
+        return E
+
+    def _masa_encode_train(self, E, img32, img16):
+        """Like _masa_encode, keeping every intermediate activation.  Returns (feats, tape)."""
+        B, H, W, _ = img32.shape
+        x = torch.empty((B, H, W, self.masa_enc.nf), dtype=BF16, device=img32.device)
+        ops.conv3x3_small_ci(img32, E["conv_L1"]["w"], E["conv_L1"]["b"], relu=True, out_bf16=x)
+        tape = dict(img16=img16, levels=[])
+        feats = []
+        for lvl in range(1, self.masa_enc.levels + 1):
+            x_prev = x
+            if lvl > 1:
+                _, x = conv3x3(x, E[f"conv_L{lvl}"], relu=True)
+            blocks = []
+            y0 = x
+            for c1, c2 in E[f"blk_L{lvl}"]:
+                _, t = conv3x3(x, c1, relu=True)
+                _, xn = conv3x3(t, c2, res2=x)
+                blocks.append((x, t))
+                x = xn
+            tape["levels"].append(dict(x_prev=x_prev, y0=y0, blocks=blocks))
+            feats.append(x)
+        return feats, tape
+
+    def _masa_encode_bwd(self, E, tape, dfeats, G):
+        """dfeats[lev]: fp32 NHWC gradient w.r.t. the level-lev feature (same batch as the forward).  Consumed in place."""
+        enc = self.masa_enc
+        d = None
+        for lvl in range(enc.levels, 0, -1):
+            T = tape["levels"][lvl - 1]
+            d = dfeats[lvl - 1] if d is None else d          # deeper levels already added their part (res2 below)
+            mods = getattr(enc, f"blk_L{lvl}")
+            for (c1, c2), m, (x_in, t) in reversed(list(zip(E[f"blk_L{lvl}"], mods, T["blocks"]))):
+                d16 = ops.rownorm(d, 0)
+                ops.wgrad(d16, t, G(m.conv2.weight), k=3, pad=1)
+                ops.colsum(d16, G(m.conv2.bias))
+                _, dt = ops.conv_gemm(d16, c2["wT"], c2["Ci"], k=3, pad=1)
+                dt = ops.relu_mask(t, dt, out=dt)
+                ops.wgrad(dt, x_in, G(m.conv1.weight), k=3, pad=1)
+                ops.colsum(dt, G(m.conv1.bias))
+                ops.conv_gemm(dt, c1["wT"], c1["Ci"], k=3, pad=1, res2=d, out_f32=d)
+            conv = getattr(enc, f"conv_L{lvl}")
+            dy = ops.relu_mask(T["y0"], ops.rownorm(d, 0))
+            ops.colsum(dy, G(conv.bias))
+            if lvl > 1:
+                xp = T["x_prev"]
+                ops.wgrad(dy, xp, G(conv.weight), k=3, stride=2, pad=1)
+                dyd = ops.dilate2(dy, xp.shape[1], xp.shape[2])
+                nxt = dfeats[lvl - 2]
+                ops.conv_gemm(dyd, E[f"conv_L{lvl}"]["wT"], conv.in_channels, k=3, pad=1, res2=nxt, out_f32=nxt)
+                d = nxt
+            else:
+                cin = conv.in_channels
+                m = torch.full((8,), -1, dtype=torch.int32, device=dy.device)
+                m[:cin] = torch.arange(cin, dtype=torch.int32, device=dy.device)
+                ops.wgrad(dy, tape["img16"], G(conv.weight), k=3, pad=1, ci_map=m)
+
+    def _masa_warp_bwd(self, aux, f_lq_deep, f_ref, dwarps, dfeat_lq_deep, dfeat_ref):
+        """dwarps[lev]: fp32 NHWC gradient w.r.t. the warped features at level lev (views allowed).  Accumulates into
+        dfeat_ref[lev] (fp32, zero-initialised, same shapes as f_ref[lev]) and dfeat_lq_deep."""
+        g = aux["geom"]
+        nlev = len(f_ref)
+        datt = torch.zeros_like(aux["att"])
+        for lev in range(nlev):
+            s = 2 ** (nlev - 1 - lev)
+            ops.masa_transfer_bwd(dwarps[lev], f_ref[lev], aux["origin"], aux["index"], aux["att"], g["py"], g["px"],
+                                  g["k_y"], g["k_x"], g["d_x"], s, dfeat_ref[lev], datt)
+        ops.masa_fine_bwd(f_lq_deep, f_ref[-1], aux["origin"], aux["index"], datt, g["k_y"], g["k_x"], g["d_x"],
+                          dfeat_lq_deep, dfeat_ref[-1])

@@ -20,8 +20,8 @@ import torch.nn as nn
 
 from .. import ops
 from ..lib import TdrError
-from .masa import Encoder, MasaMixin, ResidualBlock, prep_conv as _prep_conv, conv3x3, _f  # noqa: F401
-from .restormer_train import RestormerTrainMixin, train_call
+from .masa import Encoder, MasaMixin, MasaTrainMixin, ResidualBlock, prep_conv as _prep_conv, conv3x3, _f  # noqa: F401
+from .restormer_train import GuidedRestormerTrainMixin, RestormerTrainMixin, train_call
 
 F32, BF16 = torch.float32, torch.bfloat16
 
@@ -318,7 +318,7 @@ class Restormer(RestormerTrainMixin, _RestormerBase):
         return ops.nhwc_to_nchw(out, H, W, res=None if self.dual_pixel_task else inp32)     # + inp_img (:499)
 
 
-class RestormerRefFusion(MasaMixin, _RestormerBase):
+class RestormerRefFusion(GuidedRestormerTrainMixin, MasaTrainMixin, MasaMixin, _RestormerBase):
     def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4,
                  heads=[1, 2, 4, 8], ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias",
                  dual_pixel_task=False, nf=64, ext_n_blocks=[4, 4, 4, 4], reffusion_n_blocks=[1, 1, 1, 1],
@@ -355,6 +355,8 @@ class RestormerRefFusion(MasaMixin, _RestormerBase):
         self._check(inp_img, ref_img)
         if self.dual_pixel_task:
             raise TdrError("RestormerRefFusion (B200): dual_pixel_task is not implemented")
+        if self._wants_grad() and not return_aux:
+            return train_call(self, inp_img, ref_img)
         P = self.prepared()
         d = self.dims
         dev = inp_img.device

@@ -350,6 +350,100 @@ class RestormerTrainMixin:
         return G
 
 
+class GuidedRestormerTrainMixin(RestormerTrainMixin):
+    """Training forward / backward of ``RestormerRefFusion`` (R:747-964): MASA feature encoder, match + transfer, the
+    fusion blocks on [x || warp] before every encoder level, then the shared U-Net body."""
+
+    def _forward_train(self, inp_img, ref_img):
+        self._check(inp_img, ref_img)
+        if self.dual_pixel_task:
+            raise ops.lib.TdrError("RestormerRefFusion (B200): dual_pixel_task is not implemented")
+        P = self._prep_train(self.prepared())
+        E = self._prep_masa_train(P["masa_enc"])
+        d = self.dims
+        dev = inp_img.device
+        B, _, oh, ow = inp_img.shape
+        mult = self.padder_size * self.lr_block_size
+        h, w = ops.round_up(oh, mult), ops.round_up(ow, mult)
+        hr, wr = ops.round_up(ref_img.shape[2], mult), ops.round_up(ref_img.shape[3], mult)
+        lq32, ref32 = ops.nchw_to_nhwc(inp_img, h, w), ops.nchw_to_nhwc(ref_img, hr, wr)
+        lq16, ref16 = self._image16(inp_img, h, w), self._image16(ref_img, hr, wr)
+        tape, T = [], dict(hw=(h, w), B=B, inp16=lq16)
+        if (h, w) == (hr, wr):           # shared weights: lq and ref as one batch
+            fb, et = self._masa_encode_train(E, torch.cat([lq32, ref32], 0), torch.cat([lq16, ref16], 0))
+            f_lq, f_ref = [t[:B] for t in fb], [t[B:] for t in fb]
+            T["enc"] = [(et, fb)]
+        else:
+            f_lq, et_l = self._masa_encode_train(E, lq32, lq16)
+            f_ref, et_r = self._masa_encode_train(E, ref32, ref16)
+            T["enc"] = [(et_l, f_lq), (et_r, f_ref)]
+        fbuf = [torch.empty((B, h >> i, w >> i, 2 * d[i]), dtype=F32, device=dev) for i in range(4)]
+        aux = self._masa_warp(f_lq[-1], f_ref, h, w, hr, wr, [fbuf[i][..., d[i]:] for i in range(4)])
+        T["aux"], T["f_lq_deep"], T["f_ref"] = aux, f_lq[-1], f_ref
+        ops.conv3x3_small_ci(lq32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=fbuf[0][..., :d[0]])
+        names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
+        downs = [None, "down1_2", "down2_3", "down3_4"]
+        xs = []
+        for i in range(4):
+            if i:
+                T[downs[i]] = {}
+                down_train(xs[-1], P[downs[i]], fbuf[i][..., :d[i]], T[downs[i]])
+            fuse = f"masa_blk_enc_level{i + 1}"
+            y, T["s_" + fuse] = run_stack_train(fbuf[i], P[fuse], getattr(self, fuse), tape)
+            x, T["s_" + names[i]] = run_stack_train(y[..., :d[i]], P[names[i]], getattr(self, names[i]), tape)
+            xs.append(x)
+        out = self._decode_train(P, xs[3], xs[0], xs[1], xs[2], tape, T)
+        y = ops.nhwc_to_nchw(out, oh, ow, res=lq32)
+        return y, (P, tape, T)
+
+    def _backward(self, state, dout):
+        P, tape, T = state
+        E = P["masa_enc"]
+        G = Grads()
+        h, w = T["hw"]
+        B = T["B"]
+        d = self.dims
+        dev = dout.device
+        dlat, de1_skip, de2_skip, de3_skip = self._decode_bwd(P, dout.contiguous().float(), h, w, tape, T, G)
+        names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
+        downs = [None, "down1_2", "down2_3", "down3_4"]
+        skips16 = [None, de2_skip, de3_skip]
+        dwarps = [None] * 4
+        dx = dlat
+        for i in (3, 2, 1, 0):
+            dx = run_stack_bwd(dx, tape, T["s_" + names[i]], G)
+            dfo = torch.zeros((B, h >> i, w >> i, 2 * d[i]), dtype=F32, device=dev)     # [dx || 0]: the slice R:907-909
+            ops.copy_rows(dx, dst32=dfo[..., :d[i]])
+            dfb = run_stack_bwd(dfo, tape, T[f"s_masa_blk_enc_level{i + 1}"], G)
+            dwarps[i] = dfb[..., d[i]:]
+            dxi = dfb[..., :d[i]]
+            if i:
+                dx = down_bwd(dxi, P[downs[i]], T[downs[i]], G, add=de1_skip if i == 1 else None)
+                if skips16[i - 1] is not None:
+                    dx = ops.rownorm_bwd(None, skips16[i - 1], 0, add=dx, out=dx)
+            else:
+                pe = self.patch_embed.proj
+                dx16 = ops.rownorm(dxi, 0)
+                ops.wgrad(dx16, T["inp16"], G(pe.weight), k=3, pad=1, ci_map=_head_map(8, pe.in_channels, dev))
+                if pe.bias is not None:
+                    ops.colsum(dx16, G(pe.bias))
+        # MASA: transfer + confidence backward, then the shared feature encoder
+        f_ref = T["f_ref"]
+        if len(T["enc"]) == 1:
+            et, fb = T["enc"][0]
+            dfeat = [torch.zeros(t.shape, dtype=F32, device=dev) for t in fb]
+            self._masa_warp_bwd(T["aux"], T["f_lq_deep"], f_ref, dwarps, dfeat[-1][:B], [t[B:] for t in dfeat])
+            self._masa_encode_bwd(E, et, dfeat, G)
+        else:
+            (et_l, f_lq), (et_r, _) = T["enc"]
+            dlq = [torch.zeros(t.shape, dtype=F32, device=dev) for t in f_lq]
+            dref = [torch.zeros(t.shape, dtype=F32, device=dev) for t in f_ref]
+            self._masa_warp_bwd(T["aux"], T["f_lq_deep"], f_ref, dwarps, dlq[-1], dref)
+            self._masa_encode_bwd(E, et_l, dlq, G)
+            self._masa_encode_bwd(E, et_r, dref, G)
+        return G
+
+
 class NetFunction(torch.autograd.Function):
     """autograd bridge: forward = training schedule (tape kept on ctx), backward = explicit kernel schedule."""
 

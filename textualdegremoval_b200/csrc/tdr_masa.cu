@@ -275,6 +275,177 @@ __global__ void __launch_bounds__(256) transfer_kernel(const bf16* __restrict__ 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ backward
+__device__ __forceinline__ void atomic_add8(float* dst, const float* v) {
+  atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));       // red.global.add.v4.f32
+  atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4], v[5], v[6], v[7]));
+}
+
+// Backward of transfer_kernel.  G lanes (power of two) cooperate on one output pixel, each lane owning 8-channel
+// vectors v = l, l+G, ...:  out = mean_gathered(f) * a(p)  =>  dref[gathered] += dout * a / cnt  (vector fp32 atomics),
+// da = sum_c dout * mean_gathered(f), distributed to the 4 bilinear taps of the per-window confidence map (atomics).
+__global__ void __launch_bounds__(256) transfer_bwd_kernel(const float* __restrict__ dout, long long dld,
+                                                           const bf16* __restrict__ f, int B, int Hs, int Ws, int C,
+                                                           const int* __restrict__ origin, const int* __restrict__ index,
+                                                           const float* __restrict__ att, int py, int px, int k_y,
+                                                           int k_x, int d_x, int s, float* __restrict__ dref,
+                                                           float* __restrict__ datt, int G) {
+  const int OH = py * k_y * s, OW = px * k_x * s;
+  const int nvec = C >> 3;
+  const int nq = k_y * k_x, nblk = py * px;
+  const long long npix = (long long)B * OH * OW;
+  const float inv_s = 1.f / (float)s;
+  const int ppb = 256 / G;                              // pixels per block iteration
+  const int slot = threadIdx.x / G, l = threadIdx.x % G;
+  for (long long p0 = (long long)blockIdx.x * ppb; p0 < npix; p0 += (long long)gridDim.x * ppb) {
+    const long long p = p0 + slot;
+    const bool ok = p < npix;
+    float da = 0.f;
+    int win = 0, y0 = 0, x0 = 0, y1i = 0, x1i = 0;
+    float ly = 0.f, lx = 0.f;
+    if (ok) {
+      const int X = (int)(p % OW), Y = (int)((p / OW) % OH), b = (int)(p / ((long long)OW * OH));
+      const int tby = Y / (k_y * s), Yl = Y % (k_y * s);
+      const int tbx = X / (k_x * s), Xl = X % (k_x * s);
+      win = b * nblk + tby * px + tbx;
+      const int y1 = origin[3 * win + 1] * s, x1 = origin[3 * win + 2] * s;
+      const int* idx = index + (size_t)win * nq;
+      int sy[9], sx[9];
+      int cnt = 0, nval = 0;
+#pragma unroll
+      for (int oy = -1; oy <= 1; ++oy) {
+        const int qy = Yl / s + oy;
+        if (qy < 0 || qy >= k_y) continue;
+#pragma unroll
+        for (int ox = -1; ox <= 1; ++ox) {
+          const int qx = Xl / s + ox;
+          if (qx < 0 || qx >= k_x) continue;
+          const int j = idx[qy * k_x + qx];
+          const int yy = y1 + (j / d_x) * s + (Yl - qy * s + s);
+          const int xx = x1 + (j % d_x) * s + (Xl - qx * s + s);
+          ++cnt;
+          if (yy >= 0 && yy < Hs && xx >= 0 && xx < Ws) { sy[nval] = yy; sx[nval] = xx; ++nval; }
+        }
+      }
+      float fy = ((float)Yl + 0.5f) * inv_s - 0.5f, fx = ((float)Xl + 0.5f) * inv_s - 0.5f;
+      fy = fy < 0.f ? 0.f : fy;
+      fx = fx < 0.f ? 0.f : fx;
+      y0 = (int)fy; x0 = (int)fx;
+      y1i = y0 + 1 < k_y ? y0 + 1 : k_y - 1; x1i = x0 + 1 < k_x ? x0 + 1 : k_x - 1;
+      ly = fy - (float)y0; lx = fx - (float)x0;
+      const float* aw = att + (size_t)win * nq;
+      const float a = (1.f - ly) * ((1.f - lx) * aw[y0 * k_x + x0] + lx * aw[y0 * k_x + x1i]) +
+                      ly * ((1.f - lx) * aw[y1i * k_x + x0] + lx * aw[y1i * k_x + x1i]);
+      const float inv_cnt = 1.f / (float)cnt;
+      for (int v = l; v < nvec; v += G) {
+        const float4* g4 = reinterpret_cast<const float4*>(dout + p * dld + v * 8);
+        const float4 ga = g4[0], gb = g4[1];
+        const float g[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+        float acc[8], sc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { acc[e] = 0.f; sc[e] = g[e] * a * inv_cnt; }
+        for (int k = 0; k < nval; ++k) {
+          const size_t off = (((size_t)b * Hs + sy[k]) * Ws + sx[k]) * C + v * 8;
+          float e8[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(f + off), e8);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += e8[e];
+          atomic_add8(dref + off, sc);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) da = fmaf(g[e], acc[e] * inv_cnt, da);
+      }
+    }
+    for (int o = G >> 1; o > 0; o >>= 1) da += __shfl_xor_sync(0xffffffffu, da, o);      // G-lane groups are aligned
+    if (ok && l == 0) {
+      float* dw = datt + (size_t)win * nq;
+      atomicAdd(dw + y0 * k_x + x0, (1.f - ly) * (1.f - lx) * da);
+      atomicAdd(dw + y0 * k_x + x1i, (1.f - ly) * lx * da);
+      atomicAdd(dw + y1i * k_x + x0, ly * (1.f - lx) * da);
+      atomicAdd(dw + y1i * k_x + x1i, ly * lx * da);
+    }
+  }
+}
+
+// Backward of the fine-search confidence R:661-670: att[win, q] = cos(a, r), a = 3x3xC lq patch at interior position q
+// (replicate-padded halo), r = 3x3xC ref-window patch at the arg-max position.  grid (nq, nwin), block 128.
+//   da = datt / |a| * (r/|r| - cos * a/|a|),   dr = datt / |r| * (a/|a| - cos * r/|r|)   (scattered with fp32 atomics)
+__global__ void __launch_bounds__(128) fine_bwd_kernel(const bf16* __restrict__ flq, int H, int W,
+                                                       const bf16* __restrict__ fref, int Hr, int Wr, int C, int k_y,
+                                                       int k_x, int d_x, const int* __restrict__ origin,
+                                                       const int* __restrict__ index, const float* __restrict__ datt,
+                                                       float* __restrict__ dlq, float* __restrict__ dref) {
+  __shared__ float red[4];
+  const int q = blockIdx.x, win = blockIdx.y;
+  const int px = W / k_x, py = H / k_y;
+  const int nblk = py * px, nq = k_y * k_x;
+  const float g = datt[(size_t)win * nq + q];
+  if (g == 0.f) return;
+  const int b = win / nblk, blk = win % nblk;
+  const int by = blk / px, bx = blk % px;
+  const int qy = q / k_x, qx = q % k_x;
+  const int j = index[(size_t)win * nq + q];
+  const int ry = origin[3 * win + 1] + j / d_x, rx = origin[3 * win + 2] + j % d_x;
+  const int nvec = C >> 3;
+  float saa = 0.f, srr = 0.f, sar = 0.f;
+  for (int i = threadIdx.x; i < 9 * nvec; i += blockDim.x) {
+    const int tap = i / nvec, v = i % nvec;
+    const int yy = clampi(by * k_y - 1 + qy + tap / 3, 0, H - 1);
+    const int xx = clampi(bx * k_x - 1 + qx + tap % 3, 0, W - 1);
+    float a8[8], r8[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(flq + (((size_t)b * H + yy) * W + xx) * C + v * 8), a8);
+    unpack8(*reinterpret_cast<const bf16x8*>(fref + (((size_t)b * Hr + ry + tap / 3) * Wr + rx + tap % 3) * C + v * 8), r8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      saa = fmaf(a8[e], a8[e], saa);
+      srr = fmaf(r8[e], r8[e], srr);
+      sar = fmaf(a8[e], r8[e], sar);
+    }
+  }
+  saa = block_sum(saa, red);
+  srr = block_sum(srr, red);
+  sar = block_sum(sar, red);
+  const float na = fmaxf(sqrtf(saa), 1e-12f), nr = fmaxf(sqrtf(srr), 1e-12f);
+  const float cosv = sar / (na * nr);
+  const float ca_r = g / (na * nr), ca_a = -g * cosv / (na * na);      // da = ca_r * r + ca_a * a
+  const float cr_a = g / (na * nr), cr_r = -g * cosv / (nr * nr);      // dr = cr_a * a + cr_r * r
+  for (int i = threadIdx.x; i < 9 * nvec; i += blockDim.x) {
+    const int tap = i / nvec, v = i % nvec;
+    const int yy = clampi(by * k_y - 1 + qy + tap / 3, 0, H - 1);
+    const int xx = clampi(bx * k_x - 1 + qx + tap % 3, 0, W - 1);
+    const size_t oa = (((size_t)b * H + yy) * W + xx) * C + v * 8;
+    const size_t orr = (((size_t)b * Hr + ry + tap / 3) * Wr + rx + tap % 3) * C + v * 8;
+    float a8[8], r8[8], da[8], dr[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(flq + oa), a8);
+    unpack8(*reinterpret_cast<const bf16x8*>(fref + orr), r8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      da[e] = ca_r * r8[e] + ca_a * a8[e];
+      dr[e] = cr_a * a8[e] + cr_r * r8[e];
+    }
+    atomic_add8(dlq + oa, da);
+    atomic_add8(dref + orr, dr);
+  }
+}
+
+// zero insertion (adjoint of a stride-2 subsampling): out[b, 2y, 2x, c] = in[b, y, x, c]; out is pre-zeroed
+__global__ void __launch_bounds__(256) dilate2_kernel(const bf16* __restrict__ in, long long in_ld, int B, int H, int W,
+                                                      int C, bf16* __restrict__ out, long long out_ld, int OH, int OW) {
+  const int nvec = C >> 3;
+  const long long total = (long long)B * H * W * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    long long p = i / nvec;
+    const int x = (int)(p % W); p /= W;
+    const int y = (int)(p % H);
+    const int b = (int)(p / H);
+    if (2 * y < OH && 2 * x < OW)
+      *reinterpret_cast<uint4*>(out + ((((long long)b * OH + 2 * y) * OW) + 2 * x) * out_ld + v * 8) =
+          *reinterpret_cast<const uint4*>(in + ((((long long)b * H + y) * W) + x) * in_ld + v * 8);
+  }
+}
+
 inline int grid1d(long long items, int per_block) {
   long long g = (items + per_block - 1) / per_block;
   const long long cap = (long long)tdr_num_sms() * 16;
@@ -361,6 +532,48 @@ extern "C" int tdr_masa_transfer(const void* f_ref_bf16, int B, int Hr_s, int Wr
   transfer_kernel<<<grid1d(items, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(f_ref_bf16), B, Hr_s, Wr_s, C,
                                                           origin, index, att, py, px, k_y, k_x, d_x, s, out, out_ld,
                                                           reinterpret_cast<bf16*>(out_bf16), out_bf16_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_masa_transfer_bwd(const float* dout, long long dout_ld, const void* f_ref_bf16, int B, int Hr_s,
+                                     int Wr_s, int C, const int* origin, const int* index, const float* att, int py,
+                                     int px, int k_y, int k_x, int d_x, int s, float* dref, float* datt,
+                                     cudaStream_t stream) {
+  TDR_CHECK_ARG(dout && f_ref_bf16 && origin && index && att && dref && datt, "tdr_masa_transfer_bwd: null pointer");
+  TDR_CHECK_ARG(C % 8 == 0 && s >= 1 && dout_ld % 4 == 0 && ((uintptr_t)dref & 15) == 0 && ((uintptr_t)dout & 15) == 0,
+                "tdr_masa_transfer_bwd: bad arguments");
+  const int nvec = C / 8;
+  int G = 1;
+  while (G < 32 && G < nvec) G <<= 1;
+  const long long npix = (long long)B * py * k_y * s * px * k_x * s;
+  transfer_bwd_kernel<<<grid1d(npix, 256 / G), 256, 0, stream>>>(dout, dout_ld, reinterpret_cast<const bf16*>(f_ref_bf16),
+                                                                 B, Hr_s, Wr_s, C, origin, index, att, py, px, k_y, k_x,
+                                                                 d_x, s, dref, datt, G);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_masa_fine_bwd(const void* f_lq_bf16, int B, int H, int W, const void* f_ref_bf16, int Hr, int Wr, int C,
+                                 int k_y, int k_x, int d_x, const int* origin, const int* index, const float* datt,
+                                 float* dlq, float* dref, cudaStream_t stream) {
+  TDR_CHECK_ARG(f_lq_bf16 && f_ref_bf16 && origin && index && datt && dlq && dref, "tdr_masa_fine_bwd: null pointer");
+  TDR_CHECK_ARG(C % 8 == 0 && H % k_y == 0 && W % k_x == 0 && B > 0, "tdr_masa_fine_bwd: bad geometry");
+  dim3 grid(k_y * k_x, B * (H / k_y) * (W / k_x));
+  fine_bwd_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(f_lq_bf16), H, W,
+                                            reinterpret_cast<const bf16*>(f_ref_bf16), Hr, Wr, C, k_y, k_x, d_x, origin,
+                                            index, datt, dlq, dref);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_dilate2_nhwc(const void* in_bf16, long long in_ld, int B, int H, int W, int C, void* out_bf16,
+                                long long out_ld, int OH, int OW, cudaStream_t stream) {
+  TDR_CHECK_ARG(in_bf16 && out_bf16 && B > 0 && H > 0 && W > 0 && C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0,
+                "tdr_dilate2_nhwc: bad arguments");
+  TDR_CHECK_ARG(OH >= 2 * H - 1 && OW >= 2 * W - 1, "tdr_dilate2_nhwc: output too small");
+  dilate2_kernel<<<grid1d((long long)B * H * W * (C / 8), 256), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(in_bf16), in_ld, B, H, W, C, reinterpret_cast<bf16*>(out_bf16), out_ld, OH, OW);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

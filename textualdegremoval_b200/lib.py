@@ -114,6 +114,9 @@ SIGNATURES.update({
     "tdr_dot_f32": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _i, _vp, _vp]),
     "tdr_pixel_shuffle_nhwc": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
     "tdr_relu_mask": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _ll, _vp]),
+    "tdr_masa_transfer_bwd": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "tdr_masa_fine_bwd": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tdr_dilate2_nhwc": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _ll, _i, _i, _vp]),
 })
 
 _lib = None

@@ -581,3 +581,29 @@ def relu_mask(y16, dy16, out=None):
     _call("tdr_relu_mask", _p(y16), _ld(y16), _p(dy16), _ld(dy16), B * H * W, Cc, _p(out), _ld(out), _stream(),
           tag=f"C{Cc}", nbytes=B * H * W * Cc * 6)
     return out
+
+
+def masa_transfer_bwd(dout32, f_ref, origin, index, att, py, px, k_y, k_x, d_x, s, dref32, datt):
+    B, Hs, Ws, Cc = f_ref.shape
+    assert f_ref.is_contiguous() and dref32.is_contiguous() and dref32.shape == f_ref.shape and dref32.dtype == F32
+    assert tuple(dout32.shape) == (B, py * k_y * s, px * k_x * s, Cc) and dout32.dtype == F32
+    _call("tdr_masa_transfer_bwd", _p(dout32), _ld(dout32), _p(f_ref), B, Hs, Ws, Cc, _p(origin), _p(index), _p(att),
+          py, px, k_y, k_x, d_x, s, _p(dref32), _p(datt), _stream(), tag=f"s{s}_C{Cc}",
+          nbytes=dout32.shape[0] * dout32.shape[1] * dout32.shape[2] * Cc * (4 + 2 + 8))
+
+
+def masa_fine_bwd(f_lq, f_ref, origin, index, datt, k_y, k_x, d_x, dlq32, dref32):
+    B, H, W, Cc = f_lq.shape
+    _, Hr, Wr, _ = f_ref.shape
+    assert f_lq.is_contiguous() and f_ref.is_contiguous() and dlq32.is_contiguous() and dref32.is_contiguous()
+    _call("tdr_masa_fine_bwd", _p(f_lq), B, H, W, _p(f_ref), Hr, Wr, Cc, k_y, k_x, d_x, _p(origin), _p(index), _p(datt),
+          _p(dlq32), _p(dref32), _stream(), tag=f"C{Cc}")
+
+
+def dilate2(x16, OH, OW):
+    """Zero insertion: [B,H,W,C] -> [B,OH,OW,C] with out[:, 2y, 2x] = x[:, y, x] (adjoint of a stride-2 conv's subsampling)."""
+    B, H, W, Cc = x16.shape
+    out = torch.zeros((B, OH, OW, Cc), dtype=BF16, device=x16.device)
+    _call("tdr_dilate2_nhwc", _p(x16), _ld(x16), B, H, W, Cc, _p(out), _ld(out), OH, OW, _stream(), tag=f"C{Cc}",
+          nbytes=B * H * W * Cc * 4)
+    return out
