@@ -244,10 +244,41 @@ def run_b200(args):
             step_resident()
             prof = ops.PROF.stop()
 
+    # ---- training step: forward + L1 + backward + gradient all-reduce + clip + AdamW, same batch ----
+    train = None
+    if args.train_steps > 0:
+        from textualdegremoval_b200.ddp import RefGuidedTrainer
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats()
+        net.train()
+        tr = RefGuidedTrainer(net, dict(optim_g=dict(type="AdamW", lr=3e-4, ref_lr=1e-4, weight_decay=1e-4,
+                                                     betas=[0.9, 0.999]), use_grad_clip=True,
+                                        pixel_opt=dict(type="L1Loss", loss_weight=1.0)),
+                              process_group=None)
+        _, _, gt_h = synth_inputs(B, S, 100 + rank)
+        tr.feed_train_data(dict(lq=lq_h, gt=gt_h, ref_in=ref_h))
+        for _ in range(2):
+            tr.optimize_parameters()
+        barrier()
+        l0 = ops.PROF.launches
+        ms_train = timed(lambda: tr.optimize_parameters(), args.train_steps)
+        train_launches = ops.PROF.launches - l0
+        barrier()
+        loss_val = tr.current_loss()
+        tprof = None
+        if rank == 0 and args.dump_prof_train:
+            ops.PROF.start()
+            tr.optimize_parameters()
+            tprof = ops.PROF.stop()
+        train = dict(ms=ms_train, launches=train_launches, loss=loss_val,
+                     peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
+
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, train["ms"] if train else 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = t.tolist()
+        ms, ms_e2e, ms_tr = t.tolist()
+        if train:
+            train["ms"] = ms_tr
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -303,6 +334,25 @@ def run_b200(args):
         "clocks": clocks,
         "roofline": roof,
     }
+    if train is not None:
+        tsteps = args.train_steps
+        line["train_step"] = {
+            "what": "RefGuidedTrainer.optimize_parameters: forward + L1 + explicit backward + gradient all-reduce (NCCL, "
+                    "world > 1) + clip 0.01 + AdamW (lr / ref_lr groups), same batch and shapes as the forward metric",
+            "value": B * world * tsteps / (train["ms"] * 1e-3), "unit": "img/s", "ms_per_step": train["ms"] / tsteps,
+            "steps": tsteps, "gpu_launches": train["launches"], "loss": train["loss"],
+            "peak_mem_gb": round(train["peak_mem_gb"], 2),
+            "model_tflops_achieved": 3 * FWD_GFLOP_PER_IMG * B * tsteps / (train["ms"] * 1e-3) / 1e3}
+        if tprof is not None:
+            tags = {}
+            for name, tag, nb, fl, t in tprof:
+                d_ = tags.setdefault(f"{name}:{tag}", dict(ms=0.0, n=0, bytes=0, flops=0))
+                d_["ms"] += t; d_["n"] += 1; d_["bytes"] += nb; d_["flops"] += fl
+            rows = sorted(tags.items(), key=lambda kv: -kv[1]["ms"])
+            with open(args.dump_prof_train, "w") as fh:
+                json.dump([dict(key=k, ms=round(v["ms"], 4), n=v["n"], us_per=round(1e3 * v["ms"] / v["n"], 1),
+                                GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                                TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)) for k, v in rows], fh, indent=0)
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
@@ -321,6 +371,8 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-prof", default="", help="write the per-(kernel, shape) event-timed profile to this json")
+    ap.add_argument("--train-steps", type=int, default=3, help="timed training steps reported under train_step (0 = skip)")
+    ap.add_argument("--dump-prof-train", default="", help="per-(kernel, shape) profile of one training step")
     ap.add_argument("--ncu", action="store_true", help="profiling mode: 1 warm-up + --steps forwards, nothing else "
                                                        "(numbers printed under a profiler are never bench values)")
     args = ap.parse_args()

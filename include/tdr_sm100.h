@@ -179,6 +179,11 @@ int tdr_adamw_step(float* p, const float* g, float* m, float* v, long long n, fl
                    float eps, float weight_decay, int step, float grad_scale, const float* clip_coef,
                    cudaStream_t stream);
 int tdr_ema_update(float* ema, const float* p, long long n, float decay, cudaStream_t stream);
+/* L1 pixel loss (reference losses L1Loss, reduction 'mean', image_restoration_ref_model.py:268-274) and its gradient in
+ * one pass: loss[0] = w * mean|x - gt| (device scalar), dx = w / n * sign(x - gt).  partial: scratch of
+ * tdr_sumsq_partial_count() floats. */
+int tdr_l1_loss_grad(const float* x, const float* gt, long long n, float loss_weight, float* dx, float* loss,
+                     float* partial, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Backward kernels (training step).  The reference obtains every gradient from autograd over stock PyTorch ops

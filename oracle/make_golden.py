@@ -164,7 +164,49 @@ def main_nafnet():
         print(name, tuple(y.shape), float(y.abs().max()))
 
 
+
+GRAD_CASES = {"restormer_withbias": "restormer", "guided_restormer_128": "guided"}
+
+
+def grad_probe(name, g):
+    """Small fingerprint of a gradient tensor: (L2 norm, dot with a key-seeded N(0,1) vector)."""
+    r = torch.randn(g.shape, generator=W._gen("probe:" + name, 0))
+    return float(g.double().norm()), float((g.double() * r.double()).sum())
+
+
+def main_grads():
+    """Parameter gradients of the UNMODIFIED reference modules (autograd, L1 loss against a seeded target): pins the
+    oracle's autograd -- the checker of the explicit backward schedule -- to the reference.  Fixture = per-parameter
+    (norm, probe) fingerprints, not the full tensors."""
+    torch.set_grad_enabled(True)
+    for name, kind in GRAD_CASES.items():
+        case = (RESTORMER_CASES if kind == "restormer" else GUIDED_CASES)[name]
+        if kind == "restormer":
+            net = R.restormer(**case["cfg"])
+            W.load_seeded(net, case["seed"])
+            x = W.seeded_image("x", case["shape"], case["seed"])
+            gt = W.seeded_image("gt", case["shape"], case["seed"])
+            y = net(x)
+        else:
+            net = R.restormer_ref_fusion(**case["cfg"])
+            W.load_seeded(net, case["seed"])
+            lq, ref = guided_inputs(case)
+            gt = W.seeded_image("gt", case["lq"], case["seed"])
+            y = net(lq, ref)
+        loss = (y - gt).abs().mean()
+        loss.backward()
+        names, norms, probes = [], [], []
+        for n, p in net.named_parameters():
+            g = p.grad if p.grad is not None else torch.zeros_like(p)
+            a, b = grad_probe(n, g)
+            names.append(n); norms.append(a); probes.append(b)
+        np.savez_compressed(os.path.join(OUT, name + "_grad.npz"), meta=json.dumps(case), loss=float(loss),
+                            names=np.array(names), norms=np.array(norms), probes=np.array(probes))
+        print(name + "_grad", len(names), float(loss), float(np.sqrt((np.array(norms) ** 2).sum())))
+    torch.set_grad_enabled(False)
+
 if __name__ == "__main__":
     main()
+    main_grads()
     main_nafnet()
     main_vit()

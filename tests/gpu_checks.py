@@ -893,6 +893,59 @@ def check_guided_grad():
                         note=f"worst masa module (match flips perturb these); worst tensor {worst[0]} {worst[1]:.3f}"))
     return out
 
+
+def check_train_step():
+    """RefGuidedTrainer.optimize_parameters (forward, L1, backward, clip 0.01, AdamW with lr / ref_lr groups) for three
+    iterations vs the same loop in PyTorch over the oracle (autograd + clip_grad_norm_ + torch.optim.AdamW)."""
+    from oracle import restormer as O, weights as Wt
+    from oracle.make_golden import guided_inputs
+    from textualdegremoval_b200.archs import define_network
+    from textualdegremoval_b200.ddp import RefGuidedTrainer
+    out = []
+    meta, _ = _golden("guided_restormer_128")
+    net = define_network(dict(type="RestormerRefFusion", **meta["cfg"]))
+    sd = Wt.load_seeded(net, meta["seed"])
+    lq, rf = guided_inputs(meta)
+    gt = Wt.seeded_image("gt", meta["lq"], meta["seed"])
+    lr, ref_lr, wd = 2e-3, 1e-3, 1e-4
+    sdg = {k_: v.clone().requires_grad_(True) for k_, v in sd.items()}
+    opt = torch.optim.AdamW([dict(params=[v for k_, v in sdg.items() if "masa" not in k_], lr=lr),
+                             dict(params=[v for k_, v in sdg.items() if "masa" in k_], lr=ref_lr)],
+                            lr=lr, weight_decay=wd, betas=(0.9, 0.999))
+    ref_losses = []
+    for _ in range(3):
+        opt.zero_grad()
+        l = (O.restormer_ref_fusion_forward(sdg, lq, rf, meta["cfg"]["heads"]) - gt).abs().mean()
+        l.backward()
+        torch.nn.utils.clip_grad_norm_(list(sdg.values()), 0.01)
+        opt.step()
+        ref_losses.append(l.item())
+    net = net.to(DEV).train()
+    tr = RefGuidedTrainer(net, dict(optim_g=dict(type="AdamW", lr=lr, ref_lr=ref_lr, weight_decay=wd, betas=[0.9, 0.999]),
+                                    use_grad_clip=True, pixel_opt=dict(type="L1Loss", loss_weight=1.0)))
+    tr.feed_train_data(dict(lq=lq, gt=gt, ref_in=rf))
+    losses = []
+    for it in range(3):
+        tr.optimize_parameters(it)
+        losses.append(tr.current_loss())
+    out.append(result("train_step_losses", torch.tensor(losses), torch.tensor(ref_losses), 5e-3,
+                      note=f"ours {losses} ref {ref_losses}"))
+    out.append(dict(name="train_step_loss_decreases", ok=bool(losses[2] < losses[0]), max_err=losses[2] - losses[0], tol=0.0))
+    # parameter updates after 3 steps: cosine similarity with the reference trajectory, per LR group
+    for grp, sel in (("normal", lambda n: "masa" not in n), ("masa", lambda n: "masa" in n)):
+        a = torch.cat([(p.detach().cpu() - sd[n]).reshape(-1) for n, p in net.named_parameters() if sel(n)])
+        b = torch.cat([(sdg[n].detach() - sd[n]).reshape(-1) for n, _ in net.named_parameters() if sel(n)])
+        cos = (a @ b / (a.norm() * b.norm())).item()
+        out.append(dict(name=f"train_step_update_cos_{grp}", max_err=1 - cos, tol=0.05, ok=bool(cos > 0.95),
+                        note=f"|dp| ours {a.norm().item():.4e} ref {b.norm().item():.4e}"))
+    # plain autograd route (loss.backward() on the module output) still works with the flat grads in place
+    y = net(lq.to(DEV), rf.to(DEV))
+    tr.engine.zero_grad()
+    (y - gt.to(DEV)).abs().mean().backward()
+    gn = torch.cat([g.grad[:g.n] for g in tr.engine.groups]).norm().item()
+    out.append(dict(name="autograd_into_flat_buffers", ok=bool(gn > 0 and np.isfinite(gn)), max_err=gn, tol=None))
+    return out
+
 CHECKS = {
     "layout": check_layout,
     "rownorm": check_rownorm,
@@ -916,6 +969,7 @@ CHECKS = {
     "block_bwd": check_block_bwd,
     "restormer_grad": check_restormer_grad,
     "guided_grad": check_guided_grad,
+    "train_step": check_train_step,
 }
 
 

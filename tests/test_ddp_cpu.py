@@ -37,7 +37,8 @@ def _worker(rank, world, port, out):
     net = _Tiny()
     eng = DDPStep(net.named_parameters(), lr=2e-4, ref_lr=1e-4, bucket_bytes=256)      # tiny buckets -> many of them
     assert len(eng.groups) == 2 and eng.groups[1].lr == 1e-4
-    assert sum(g.n for g in eng.groups) == sum(p.numel() for p in net.parameters())
+    assert sum(g.n_params for g in eng.groups) == sum(p.numel() for p in net.parameters())
+    assert all(p.data_ptr() % 64 == 0 and p.grad.data_ptr() % 64 == 0 for p in net.parameters())
     assert len(eng.buckets()) > 4
     g = torch.Generator().manual_seed(1)
     x, y = torch.rand(4, 3, 8, 8, generator=g), torch.rand(4, 3, 8, 8, generator=g)
@@ -50,7 +51,7 @@ def _worker(rank, world, port, out):
     for w in eng.all_reduce_gradients():
         w.wait()
     eng.reduce_loss_async(loss)
-    avg = torch.cat([gr.grad[:gr.n] for gr in eng.groups]) / world
+    avg = torch.cat([p.grad.reshape(-1) for gr in eng.groups for p in gr.params]) / world
     if rank == 0:
         torch.manual_seed(0)
         ref = _Tiny()

@@ -169,3 +169,34 @@ def test_oracle_vs_live_reference():
     rf = W.seeded_image("b", (1, 3, 192, 128), 5)
     with torch.no_grad():
         assert (net(lq, rf) - O.restormer_ref_fusion_forward(sd, lq, rf)).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("name", ["restormer_withbias", "guided_restormer_128"])
+def test_oracle_autograd_matches_reference_gradients(name):
+    """The oracle's autograd (the checker of the CUDA backward schedule) against per-parameter gradient fingerprints of
+    the unmodified reference modules (oracle/make_golden.py main_grads)."""
+    from oracle.make_golden import GRAD_CASES, grad_probe
+    from textualdegremoval_b200.archs.restormer_b200_arch import Restormer, RestormerRefFusion
+    z = np.load(os.path.join(GOLD, name + "_grad.npz"))
+    meta = json.loads(str(z["meta"]))
+    guided = GRAD_CASES[name] == "guided"
+    sd = W.seeded_state_dict(_shapes(RestormerRefFusion if guided else Restormer, meta["cfg"]), meta["seed"])
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    if guided:
+        lq, rf = guided_inputs(meta)
+        gt = W.seeded_image("gt", meta["lq"], meta["seed"])
+        y = O.restormer_ref_fusion_forward(sdg, lq, rf, meta["cfg"]["heads"])
+    else:
+        x = W.seeded_image("x", meta["shape"], meta["seed"])
+        gt = W.seeded_image("gt", meta["shape"], meta["seed"])
+        y = O.restormer_forward(sdg, x, meta["cfg"]["heads"])
+    loss = (y - gt).abs().mean()
+    loss.backward()
+    assert abs(float(loss) - float(z["loss"])) < 1e-6
+    total = float(np.sqrt((z["norms"] ** 2).sum()))
+    for n, norm, probe in zip(z["names"].tolist(), z["norms"].tolist(), z["probes"].tolist()):
+        g = sdg[n].grad if sdg[n].grad is not None else torch.zeros_like(sdg[n])
+        a, b = grad_probe(n, g)
+        tol = 2e-4 * max(norm, 1e-3 * total)
+        assert abs(a - norm) < tol, (n, a, norm)
+        assert abs(b - probe) < tol * max(1.0, float(g.numel()) ** 0.5), (n, b, probe)

@@ -24,17 +24,27 @@ F32, BF16 = torch.float32, torch.bfloat16
 
 # ----------------------------------------------------------------------------------------------- gradient sink
 class Grads:
-    """fp32 gradient buffers, one per parameter, in the parameter's own layout (allocated zeroed on first touch)."""
+    """fp32 gradient buffers, one per parameter, in the parameter's own layout (allocated zeroed on first touch).
 
-    def __init__(self):
+    ``direct=True``: a parameter that already owns a contiguous fp32 ``.grad`` (the flat DDP buffers of
+    ``ddp.FlatGroup``) is accumulated into in place -- no per-step allocation and no extra add pass."""
+
+    def __init__(self, direct=False):
         self.buf = {}
+        self.direct = direct
+        self.in_place = set()
 
     def __call__(self, param):
         if param is None:
             return None
         t = self.buf.get(id(param))
         if t is None:
-            t = torch.zeros(param.shape, dtype=F32, device=param.device)
+            g = param.grad
+            if self.direct and g is not None and g.dtype == F32 and g.is_contiguous() and g.device == param.device:
+                t = g
+                self.in_place.add(id(param))
+            else:
+                t = torch.zeros(param.shape, dtype=F32, device=param.device)
             self.buf[id(param)] = t
         return t
 
@@ -326,9 +336,9 @@ class RestormerTrainMixin:
         y = ops.nhwc_to_nchw(out, H, W, res=inp32)
         return y, (P, tape, T)
 
-    def _backward(self, state, dout):
+    def _backward(self, state, dout, G=None):
         P, tape, T = state
-        G = Grads()
+        G = Grads() if G is None else G
         H, W = T["hw"]
         dlat, de1_skip, de2_skip, de3_skip = self._decode_bwd(P, dout.contiguous().float(), H, W, tape, T, G)
         names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
@@ -396,10 +406,10 @@ class GuidedRestormerTrainMixin(RestormerTrainMixin):
         y = ops.nhwc_to_nchw(out, oh, ow, res=lq32)
         return y, (P, tape, T)
 
-    def _backward(self, state, dout):
+    def _backward(self, state, dout, G=None):
         P, tape, T = state
         E = P["masa_enc"]
-        G = Grads()
+        G = Grads() if G is None else G
         h, w = T["hw"]
         B = T["B"]
         d = self.dims
@@ -456,12 +466,15 @@ class NetFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        G = ctx.net._backward(ctx.state, dout)
+        G = ctx.net._backward(ctx.state, dout, Grads(direct=getattr(ctx.net, "grad_direct", False)))
         ctx.state = None
         grads = []
         for p in ctx.params:
             g = G.get(p)
-            grads.append(g.to(p.dtype) if g is not None else (torch.zeros_like(p) if p.requires_grad else None))
+            if id(p) in G.in_place:
+                grads.append(None)                   # already accumulated into p.grad (flat DDP buffer)
+            else:
+                grads.append(g.to(p.dtype) if g is not None else (torch.zeros_like(p) if p.requires_grad else None))
         return (None, None) + (None,) * ctx.n_inputs + tuple(grads)
 
 

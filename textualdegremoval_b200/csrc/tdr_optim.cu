@@ -73,6 +73,42 @@ __global__ void ema_kernel(float* __restrict__ ema, const float* __restrict__ p,
     ema[i] = decay * ema[i] + (1.f - decay) * p[i];
 }
 
+// L1 pixel loss (losses L1Loss 'mean', loss_weight w): partial[blk] = sum |x - gt| over the block's elements,
+// dx = w / n * sign(x - gt)   (the gradient autograd would hand to the network output)
+__global__ void __launch_bounds__(256) l1_loss_grad_kernel(const float* __restrict__ x, const float* __restrict__ gt,
+                                                           long long n, float gscale, float* __restrict__ dx,
+                                                           float* __restrict__ partial) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = x[i] - gt[i];
+    s += fabsf(d);
+    dx[i] = d > 0.f ? gscale : (d < 0.f ? -gscale : 0.f);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+
+__global__ void l1_loss_final_kernel(const float* __restrict__ partial, int n, float scale, float* __restrict__ loss) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)partial[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    loss[0] = (float)(t * scale);
+  }
+}
+
 inline int grid_flat(long long n) {
   long long g = (n + 1023) / 1024;
   const long long cap = (long long)tdr_num_sms() * 8;
@@ -113,6 +149,17 @@ extern "C" int tdr_adamw_step(float* p, const float* g, float* m, float* v, long
 extern "C" int tdr_ema_update(float* ema, const float* p, long long n, float decay, cudaStream_t stream) {
   TDR_CHECK_ARG(ema && p && n > 0, "tdr_ema_update: bad arguments");
   ema_kernel<<<grid_flat(n), 256, 0, stream>>>(ema, p, n, decay);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_l1_loss_grad(const float* x, const float* gt, long long n, float loss_weight, float* dx, float* loss,
+                                float* partial /* tdr_sumsq_partial_count() floats */, cudaStream_t stream) {
+  TDR_CHECK_ARG(x && gt && dx && loss && partial && n > 0, "tdr_l1_loss_grad: bad arguments");
+  const int blocks = grid_flat(n) < kSumsqBlocks ? grid_flat(n) : kSumsqBlocks;
+  l1_loss_grad_kernel<<<blocks, 256, 0, stream>>>(x, gt, n, loss_weight / (float)n, dx, partial);
+  TDR_CHECK_LAUNCH();
+  l1_loss_final_kernel<<<1, 256, 0, stream>>>(partial, blocks, (double)loss_weight / (double)n, loss);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

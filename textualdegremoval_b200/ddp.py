@@ -34,22 +34,25 @@ def _stream():
 class FlatGroup:
     """One optimizer group whose parameters / gradients are views into flat buffers."""
 
+    ALIGN = 16     # floats: every parameter starts on a 64 B boundary (the kernels read weights / biases as float4)
+
     def __init__(self, params, lr):
         self.params = list(params)
         self.lr = lr
-        n = sum(p.numel() for p in self.params)
-        n_pad = (n + 3) // 4 * 4
-        dev = self.params[0].device if self.params else torch.device("cpu")
-        self.n = n
-        self.flat = torch.zeros(n_pad, dtype=F32, device=dev)
-        self.grad = torch.zeros(n_pad, dtype=F32, device=dev)
-        off = 0
+        offs, n = [], 0
         for p in self.params:
+            offs.append(n)
+            n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.n = n                                       # padded length (padding stays zero: p = g = m = v = 0)
+        self.n_params = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(max(n, 4), dtype=F32, device=dev)
+        self.grad = torch.zeros(max(n, 4), dtype=F32, device=dev)
+        for p, off in zip(self.params, offs):
             k = p.numel()
             self.flat[off:off + k].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + k].view_as(p)
             p.grad = self.grad[off:off + k].view_as(p)
-            off += k
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
 
@@ -128,6 +131,11 @@ class DDPStep:
             for g, e in zip(self.groups, self.ema):
                 lib.call("tdr_ema_update", C.c_void_p(e.data_ptr()), C.c_void_p(g.flat.data_ptr()), g.n, self.ema_decay,
                          _stream())
+        # the kernels wrote the parameters behind autograd's back: bump the version counters so that weight caches
+        # keyed on (data_ptr, _version) -- the packed bf16 GEMM operands of the arch modules -- are rebuilt
+        for g in self.groups:
+            for p in g.params:
+                torch.autograd.graph.increment_version(p)
 
     def zero_grad(self):
         for g in self.groups:
@@ -146,3 +154,68 @@ class DDPStep:
 
     def grad_norm(self):
         return float(self._clip[1].item())
+
+
+class RefGuidedTrainer:
+    """The training half of the reference's ``RefGuidedImageCleanModel`` (models/image_restoration_ref_model.py) for one
+    process per GPU: ``feed_train_data`` :185-213 (without the dataset / DINO crop selection, which the caller does) and
+    ``optimize_parameters`` :248-284 -- zero_grad, ``net_g(lq, ref_in)``, L1 ``cri_pix``, backward, DDP gradient
+    all-reduce (``base_model.py:76-82``), ``clip_grad_norm_(…, 0.01)``, AdamW over the ``masa`` / non-``masa`` LR groups,
+    loss reduction, EMA.
+
+    ``train_opt`` takes the reference's option keys: ``optim_g: {type: AdamW, lr, ref_lr, weight_decay, betas}``,
+    ``use_grad_clip``, ``pixel_opt: {type: L1Loss, loss_weight}``, ``ema_decay``.  The network runs its explicit
+    forward-with-tape / backward schedule (archs/restormer_train.py) and accumulates gradients straight into the flat
+    buffers the all-reduce and the fused optimizer kernels work on; nothing in the step synchronises with the host.
+    """
+
+    def __init__(self, net_g, train_opt, process_group=None):
+        og = dict(train_opt.get("optim_g", {}))
+        if og.get("type", "AdamW") != "AdamW":
+            raise lib.TdrError(f"RefGuidedTrainer: optimizer {og.get('type')} not implemented (AdamW only, as in the "
+                               "shipped option files)")
+        pix = dict(train_opt.get("pixel_opt", {}))
+        if pix.get("type", "L1Loss") != "L1Loss" or pix.get("reduction", "mean") != "mean":
+            raise lib.TdrError("RefGuidedTrainer: only the L1Loss(mean) pixel criterion is implemented")
+        self.loss_weight = float(pix.get("loss_weight", 1.0))
+        self.net_g = net_g
+        self.engine = DDPStep(net_g.named_parameters(), lr=og.get("lr", 3e-4), ref_lr=og.get("ref_lr", og.get("lr", 3e-4)),
+                              weight_decay=og.get("weight_decay", 1e-4), betas=tuple(og.get("betas", (0.9, 0.999))),
+                              use_grad_clip=bool(train_opt.get("use_grad_clip", True)),
+                              ema_decay=float(train_opt.get("ema_decay", 0.0)), process_group=process_group)
+        net_g.grad_direct = True
+        dev = self.engine.groups[0].flat.device
+        self._loss = torch.zeros(1, dtype=F32, device=dev)
+        self._partial = torch.zeros(lib.load().tdr_sumsq_partial_count(), dtype=F32, device=dev)
+        self.lq = self.gt = self.ref_in = self.output = None
+        self.log_dict = {}
+
+    def feed_train_data(self, data):
+        dev = self.engine.groups[0].flat.device
+        self.lq = data["lq"].to(dev, non_blocking=True)
+        self.gt = data["gt"].to(dev, non_blocking=True) if "gt" in data else None
+        ref = data.get("ref_in", data.get("ref"))
+        self.ref_in = ref.to(dev, non_blocking=True) if ref is not None else None
+
+    def optimize_parameters(self, current_iter=0):
+        from .archs.restormer_train import Grads
+        net = self.net_g
+        self.engine.zero_grad()
+        inputs = (self.lq,) if self.ref_in is None else (self.lq, self.ref_in)
+        out, state = net._forward_train(*inputs)
+        self.output = out
+        dout = torch.empty_like(out)
+        gt = self.gt.contiguous().float()
+        lib.call("tdr_l1_loss_grad", C.c_void_p(out.data_ptr()), C.c_void_p(gt.data_ptr()), out.numel(), self.loss_weight,
+                 C.c_void_p(dout.data_ptr()), C.c_void_p(self._loss.data_ptr()), C.c_void_p(self._partial.data_ptr()),
+                 _stream())
+        net._backward(state, dout, Grads(direct=True))
+        works = self.engine.all_reduce_gradients()
+        self.engine.step(works)
+        self.engine.reduce_loss_async(self._loss)
+        return self._loss
+
+    def current_loss(self):
+        """Host read of the (rank-averaged) pixel loss: call every print_freq iterations (base_model.py:353-378)."""
+        self.log_dict = {"l_pix": self.engine.read_loss()}
+        return self.log_dict["l_pix"]
