@@ -289,48 +289,142 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ x,
   col_reduce_store(sm, m, C, partials + (size_t)blockIdx.x * C);
 }
 
+// ---- depthwise 3x3 weight gradient ----------------------------------------------------------------------------------
 // dW[tap][c] = sum_p dy[p, c] * x[p + off(tap), c];  db[c] = sum_p dy[p, c].  partials [blk][10][C] (tap 9 = bias).
-__global__ void __launch_bounds__(256) dw_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld,
-                                                       const bf16* __restrict__ x, long long x_ld, int B, int H, int W,
-                                                       int C, float* __restrict__ partials) {
-  __shared__ float sm[256][8];
-  const ColMap m = col_map(C);
-  float acc[10][8];
-#pragma unroll
-  for (int t = 0; t < 10; ++t)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
-  const long long npix = (long long)B * H * W;
-  // contiguous pixel range per block (keeps the 3-row neighbourhood in L1/L2)
-  const long long per = (npix + gridDim.x - 1) / gridDim.x;
-  const long long p0 = blockIdx.x * per, p1 = p0 + per < npix ? p0 + per : npix;
-  if (m.active) {
-    for (long long p = p0 + m.slot; p < p1; p += m.slots) {
-      const int xx = (int)(p % W);
-      const int yy = (int)((p / W) % H);
-      float g[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(dy + p * dy_ld + m.c0), g);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[9][i] += g[i];
-#pragma unroll
-      for (int t = 0; t < 9; ++t) {
-        const int dyy = t / 3 - 1, dxx = t % 3 - 1;
-        if ((unsigned)(yy + dyy) < (unsigned)H && (unsigned)(xx + dxx) < (unsigned)W) {
-          float f[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(x + (p + dyy * W + dxx) * x_ld + m.c0), f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[t][i] = fmaf(g[i], f[i], acc[t][i]);
-        }
-      }
-    }
+// blockIdx.y = block of 128 channels.  A lane owns 4 channels (8 B loads; a warp row = up to 256 B contiguous) and walks
+// a 32-pixel segment of one image row with a 3x3 register window: per pixel 3 new x vectors + 1 dy vector are loaded and
+// 9 taps x 4 channels accumulate in packed fp32x2 FMAs.  Narrow channel blocks (< 32 quads) put several x sub-segments
+// in one warp.  The 8 warps of a block take 8 consecutive rows, so the rows above / below are L1 hits.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk2(float a, float b) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f2 r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2 bf2_to_f2(uint32_t u) { return pk2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+
+struct Q4 {   // 4 channels as two packed pairs
+  f2 a, b;
+};
+__device__ __forceinline__ Q4 ldq(const bf16* p, bool ok) {
+  Q4 q;
+  if (ok) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    q.a = bf2_to_f2(u.x);
+    q.b = bf2_to_f2(u.y);
+  } else {
+    q.a = q.b = 0ull;
   }
+  return q;
+}
+
+constexpr int kDwgSeg = 32;
+
+__global__ void __launch_bounds__(256, 2) dw_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld,
+                                                          const bf16* __restrict__ x, long long x_ld, int B, int H, int W,
+                                                          int C, float* __restrict__ partials) {
+  __shared__ float sm[8][32][4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c_lo = blockIdx.y * 128;
+  const int nq = (C - c_lo < 128 ? C - c_lo : 128) >> 2;
+  int LQ = 1;
+  while (LQ < nq) LQ <<= 1;
+  const int XS = 32 / LQ;
+  const int cq = lane % LQ, xs = lane / LQ;
+  const bool active = cq < nq;
+  const int c0 = c_lo + cq * 4;
+  const int span = XS * kDwgSeg;
+  const int nxseg = (W + span - 1) / span;
+  const long long total = (long long)B * H * nxseg;
+  Q4 acc[10];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) acc[t].a = acc[t].b = 0ull;
+  for (long long t = (long long)blockIdx.x * 8 + warp; t < total; t += (long long)gridDim.x * 8) {
+    const int y = (int)(t % H);
+    const long long r = t / H;
+    const int xseg = (int)(r % nxseg), b = (int)(r / nxseg);
+    const int xb = xseg * span + xs * kDwgSeg;
+    int xe = xb + kDwgSeg;
+    if (xe > W) xe = W;
+    if (!active || xb >= W) continue;
+    const long long row = ((long long)b * H + y) * W;
+    const bool up = y > 0, dn = y + 1 < H;
+    const bf16* xr0 = x + (row - W) * x_ld + c0;
+    const bf16* xr1 = x + row * x_ld + c0;
+    const bf16* xr2 = x + (row + W) * x_ld + c0;
+    const bf16* gr = dy + row * dy_ld + c0;
+    Q4 w0[3], w1[3], w2[3];     // columns (x-1, x, x+1), rows (y-1, y, y+1)
+#define TDR_LDCOL(col, xx)                                        \
+  do {                                                            \
+    const bool in = (xx) >= 0 && (xx) < W;                        \
+    col[0] = ldq(xr0 + (long long)(xx) * x_ld, in && up);         \
+    col[1] = ldq(xr1 + (long long)(xx) * x_ld, in);               \
+    col[2] = ldq(xr2 + (long long)(xx) * x_ld, in && dn);         \
+  } while (0)
+#define TDR_STEP(cl, cm, cr, xx)                                  \
+  do {                                                            \
+    TDR_LDCOL(cr, (xx) + 1);                                      \
+    const Q4 g = ldq(gr + (long long)(xx) * dy_ld, true);         \
+    acc[9].a = add2(acc[9].a, g.a);                               \
+    acc[9].b = add2(acc[9].b, g.b);                               \
+    _Pragma("unroll") for (int rr = 0; rr < 3; ++rr) {            \
+      acc[rr * 3 + 0].a = fma2(g.a, cl[rr].a, acc[rr * 3 + 0].a); \
+      acc[rr * 3 + 0].b = fma2(g.b, cl[rr].b, acc[rr * 3 + 0].b); \
+      acc[rr * 3 + 1].a = fma2(g.a, cm[rr].a, acc[rr * 3 + 1].a); \
+      acc[rr * 3 + 1].b = fma2(g.b, cm[rr].b, acc[rr * 3 + 1].b); \
+      acc[rr * 3 + 2].a = fma2(g.a, cr[rr].a, acc[rr * 3 + 2].a); \
+      acc[rr * 3 + 2].b = fma2(g.b, cr[rr].b, acc[rr * 3 + 2].b); \
+    }                                                             \
+  } while (0)
+    TDR_LDCOL(w0, xb - 1);
+    TDR_LDCOL(w1, xb);
+    int xx = xb;
+    for (; xx + 2 < xe; xx += 3) {
+      TDR_STEP(w0, w1, w2, xx);
+      TDR_STEP(w1, w2, w0, xx + 1);
+      TDR_STEP(w2, w0, w1, xx + 2);
+    }
+    if (xx < xe) {
+      TDR_STEP(w0, w1, w2, xx);
+      if (xx + 1 < xe) TDR_STEP(w1, w2, w0, xx + 1);
+    }
+#undef TDR_STEP
+#undef TDR_LDCOL
+  }
+  // lanes holding the same channel quad at different x sub-segments, then the 8 warps
 #pragma unroll
   for (int t = 0; t < 10; ++t) {
+    float v[4];
+    upk2(acc[t].a, v[0], v[1]);
+    upk2(acc[t].b, v[2], v[3]);
+    for (int o = 16; o >= LQ; o >>= 1) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+    }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sm[threadIdx.x][i] = acc[t][i];
+    for (int i = 0; i < 4; ++i) sm[warp][lane][i] = v[i];
     __syncthreads();
-    col_reduce_store(sm, m, C, partials + ((size_t)blockIdx.x * 10 + t) * C);
+    if (threadIdx.x < 128) {
+      const int q = threadIdx.x >> 2, i = threadIdx.x & 3;
+      if (q < nq) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sm[w][q][i];      // lane q (< LQ) holds the xs-reduced sum of quad q
+        partials[((size_t)blockIdx.x * 10 + t) * C + c_lo + q * 4 + i] = s;
+      }
+    }
   }
 }
 
@@ -534,31 +628,87 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const bf16* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ MDTA backward (small)
-// One CTA per (head, sample).  c <= 128 channels per head.  Shared: attn[c][c], dattn[c][c] (-> dS_hat), shat[c][c],
-// a [32][c] staging tile for W / dWeff rows, nq[c], nk[c], r[c], s[c].
+// Strided, two-level batched fp32 SGEMM (SIMT, 64x64 tiles, 4x4 per thread): C(m,n) = sum_k A(m,k) * B(k,n).
+// Used for the per-(sample, head) products of the MDTA backward, which are far too small for a tensor-core launch.
+struct SgemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  int M, N, K, nb2;
+  long long sam, sak, sbk, sbn, scm, scn;
+  long long a_b1, a_b2, b_b1, b_b2, c_b1, c_b2;
+};
+
+__global__ void __launch_bounds__(256) sgemm_batched_kernel(const SgemmArgs a) {
+  __shared__ float As[16][65];
+  __shared__ float Bs[16][65];
+  const int b1 = blockIdx.z / a.nb2, b2 = blockIdx.z % a.nb2;
+  const float* A = a.A + b1 * a.a_b1 + b2 * a.a_b2;
+  const float* Bm = a.B + b1 * a.b_b1 + b2 * a.b_b2;
+  float* Cm = a.C + b1 * a.c_b1 + b2 * a.c_b2;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < a.K; k0 += 16) {
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      int kk, mm;
+      if (a.sam == 1) { mm = e & 63; kk = e >> 6; } else { kk = e & 15; mm = e >> 4; }     // coalesce along the unit stride
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < a.M && k < a.K) ? A[m * a.sam + k * a.sak] : 0.f;
+    }
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      int kk, nn;
+      if (a.sbn == 1) { nn = e & 63; kk = e >> 6; } else { kk = e & 15; nn = e >> 4; }
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < a.N && k < a.K) ? Bm[k * a.sbk + n * a.sbn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = As[kk][ty + 16 * i]; bv[i] = Bs[kk][tx + 16 * i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * j;
+      if (m < a.M && n < a.N) Cm[m * a.scm + n * a.scn] = acc[i][j];
+    }
+}
+
+// One CTA per (head, sample): softmax / temperature / normalise backward and the rows of the [2C x 2C] matrix.
+// Shared: attn, dattn (-> dS_hat), shat as [c][c+1] (padded against bank conflicts), nq, nk, r, s.
 struct MdtaBwdArgs {
   int C, heads, nchunks;
   const float* partials;   // forward Gram partials (tdr_mdta_gram)
   const float* attn;       // [B, heads, c, c]
+  const float* dattn;      // [B, heads, c, c] = W_out[:, head]^T . dWeff[b][:, head]
   const float* temperature;
-  const float* w_out;      // [C][C]
-  const float* dweff;      // [B][C][C] fp32 (per-sample wgrad of the attn.v.project_out product)
   bf16* mqk;               // [B][2C][mqk_ld]
   long long mqk_ld;
-  float* dwout_part;       // [B][C][C]
   float* dtemp_part;       // [B][heads]
 };
 
 __global__ void __launch_bounds__(256) mdta_bwd_kernel(const MdtaBwdArgs a) {
   extern __shared__ float sm[];
-  const int C = a.C, c = C / a.heads;
+  const int C = a.C, c = C / a.heads, ld = c + 1;
   const int h = blockIdx.x, b = blockIdx.y;
   float* attn = sm;
-  float* dat = attn + c * c;
-  float* shat = dat + c * c;
-  float* tw = shat + c * c;        // [32][c]
-  float* td = tw + 32 * c;         // [32][c]
-  float* nq = td + 32 * c;
+  float* dat = attn + c * ld;
+  float* shat = dat + c * ld;
+  float* nq = shat + c * ld;
   float* nk = nq + c;
   float* rr = nk + c;
   float* ss = rr + c;
@@ -567,8 +717,8 @@ __global__ void __launch_bounds__(256) mdta_bwd_kernel(const MdtaBwdArgs a) {
   const size_t psz = (size_t)c * c + 2 * c;
   const float* pbase = a.partials + (size_t)(b * a.heads + h) * a.nchunks * psz;
   const float* asrc = a.attn + (size_t)(b * a.heads + h) * c * c;
+  const float* dsrc = a.dattn + (size_t)(b * a.heads + h) * c * c;
   const float temp = a.temperature[h];
-  // norms
   for (int i = tid; i < 2 * c; i += 256) {
     float s = 0.f;
     for (int ch = 0; ch < a.nchunks; ++ch) s += pbase[(size_t)ch * psz + c * c + i];
@@ -578,73 +728,26 @@ __global__ void __launch_bounds__(256) mdta_bwd_kernel(const MdtaBwdArgs a) {
   for (int t = tid; t < c * c; t += 256) {
     float s = 0.f;
     for (int ch = 0; ch < a.nchunks; ++ch) s += pbase[(size_t)ch * psz + t];
-    shat[t] = s / (nq[t / c] * nk[t % c]);
-    attn[t] = asrc[t];
-    dat[t] = 0.f;
+    const int i = t / c, j = t % c;
+    shat[i * ld + j] = s / (nq[i] * nk[j]);
+    attn[i * ld + j] = asrc[t];
+    dat[i * ld + j] = dsrc[t];
   }
-  __syncthreads();
-  // dattn[i][j] = sum_co W[co][hc+i] * dWeff[b][co][hc+j];  thread (ti, tj) of a 16x16 grid owns i = ti + 16a, j = tj + 16b
-  const int ti = tid >> 4, tj = tid & 15;
-  float acc[8][8];
-#pragma unroll
-  for (int x = 0; x < 8; ++x)
-#pragma unroll
-    for (int y = 0; y < 8; ++y) acc[x][y] = 0.f;
-  const float* dweff = a.dweff + (size_t)b * C * C;
-  for (int co0 = 0; co0 < C; co0 += 32) {
-    __syncthreads();
-    for (int t = tid; t < 32 * c; t += 256) {
-      const int r = t / c, k = t % c;
-      const int co = co0 + r;
-      tw[t] = co < C ? a.w_out[(size_t)co * C + h * c + k] : 0.f;
-      td[t] = co < C ? dweff[(size_t)co * C + h * c + k] : 0.f;
-    }
-    __syncthreads();
-    for (int r = 0; r < 32; ++r) {
-      float wv[8], dv[8];
-#pragma unroll
-      for (int x = 0; x < 8; ++x) {
-        wv[x] = ti + 16 * x < c ? tw[r * c + ti + 16 * x] : 0.f;
-        dv[x] = tj + 16 * x < c ? td[r * c + tj + 16 * x] : 0.f;
-      }
-#pragma unroll
-      for (int x = 0; x < 8; ++x)
-#pragma unroll
-        for (int y = 0; y < 8; ++y) acc[x][y] = fmaf(wv[x], dv[y], acc[x][y]);
-    }
-    // dW_out[b][co][hc+i] = sum_j dWeff[co][hc+j] * attn[i][j]  for the 32 rows staged in td
-    for (int t = tid; t < 32 * c; t += 256) {
-      const int r = t / c, i = t % c;
-      const int co = co0 + r;
-      if (co < C) {
-        float s = 0.f;
-        for (int j = 0; j < c; ++j) s = fmaf(td[r * c + j], attn[i * c + j], s);
-        a.dwout_part[((size_t)b * C + co) * C + h * c + i] = s;
-      }
-    }
-  }
-#pragma unroll
-  for (int x = 0; x < 8; ++x)
-#pragma unroll
-    for (int y = 0; y < 8; ++y) {
-      const int i = ti + 16 * x, j = tj + 16 * y;
-      if (i < c && j < c) dat[i * c + j] = acc[x][y];
-    }
   __syncthreads();
   // softmax backward per row i: dS = attn * (dattn - sum_j dattn*attn); logits = shat * temp
   float dtemp = 0.f;
   for (int i = tid >> 5; i < c; i += 8) {
     const int lane = tid & 31;
     float s = 0.f;
-    for (int j = lane; j < c; j += 32) s += dat[i * c + j] * attn[i * c + j];
+    for (int j = lane; j < c; j += 32) s += dat[i * ld + j] * attn[i * ld + j];
     s = warp_sum(s);
     float r = 0.f;
     for (int j = lane; j < c; j += 32) {
-      const float ds = attn[i * c + j] * (dat[i * c + j] - s);
-      dtemp += ds * shat[i * c + j];
+      const float ds = attn[i * ld + j] * (dat[i * ld + j] - s);
+      dtemp += ds * shat[i * ld + j];
       const float dsh = ds * temp;
-      dat[i * c + j] = dsh;                         // dat now holds dS_hat
-      r += dsh * shat[i * c + j];
+      dat[i * ld + j] = dsh;                         // dat now holds dS_hat
+      r += dsh * shat[i * ld + j];
     }
     r = warp_sum(r);
     if (lane == 0) rr[i] = r;
@@ -659,7 +762,7 @@ __global__ void __launch_bounds__(256) mdta_bwd_kernel(const MdtaBwdArgs a) {
   }
   for (int j = tid; j < c; j += 256) {
     float s = 0.f;
-    for (int i = 0; i < c; ++i) s += dat[i * c + j] * shat[i * c + j];
+    for (int i = 0; i < c; ++i) s += dat[i * ld + j] * shat[i * ld + j];
     ss[j] = s;
   }
   __syncthreads();
@@ -672,11 +775,11 @@ __global__ void __launch_bounds__(256) mdta_bwd_kernel(const MdtaBwdArgs a) {
     float vq = 0.f, vk = 0.f;
     if (col >= C + h * c && col < C + h * c + c) {          // k columns
       const int j = col - C - h * c;
-      vq = dat[i * c + j] / (nq[i] * nk[j]);
+      vq = dat[i * ld + j] / (nq[i] * nk[j]);
       if (j == i) vk = -ss[i] / (nk[i] * nk[i]);
     } else if (col >= h * c && col < h * c + c) {           // q columns
       const int j = col - h * c;
-      vk = dat[j * c + i] / (nq[j] * nk[i]);
+      vk = dat[j * ld + i] / (nq[j] * nk[i]);
       if (j == i) vq = -rr[i] / (nq[i] * nq[i]);
     }
     mq[(size_t)(h * c + i) * a.mqk_ld + col] = __float2bfloat16(vq);
@@ -830,7 +933,7 @@ extern "C" int tdr_wgrad(const tdr_wgrad_desc* d, cudaStream_t stream) {
   return TDR_OK;
 }
 
-extern "C" size_t tdr_reduce_workspace_bytes(int C) { return (size_t)kRedBlocks * 10 * (size_t)(C > 0 ? C : 0) * sizeof(float); }
+extern "C" size_t tdr_reduce_workspace_bytes(int C) { return (size_t)kRedBlocks * 10 * (size_t)(C > 0 ? C : 0) * sizeof(float); }   // >= 3 * kRedBlocks * 2 * C (rownorm_bwd)
 
 extern "C" int tdr_colsum(const void* x_bf16, long long ld, long long rows, int C, float* out, long long out_stride,
                           const int* c_map, int accumulate, float* workspace, cudaStream_t stream) {
@@ -852,9 +955,9 @@ extern "C" int tdr_dwconv3x3_wgrad(const void* dy_bf16, long long dy_ld, const v
   TDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "tdr_dwconv3x3_wgrad: bad dims");
   TDR_CHECK_ARG(dy_ld % 8 == 0 && x_ld % 8 == 0 && ((uintptr_t)dy_bf16 & 15) == 0 && ((uintptr_t)x_bf16 & 15) == 0,
                 "tdr_dwconv3x3_wgrad: alignment");
-  const long long npix = (long long)B * H * W;
-  int nblk = (int)((npix + 63) / 64 < kRedBlocks ? (npix + 63) / 64 : kRedBlocks);
-  dim3 grid(nblk, tdr_cdiv(C / 8, 256));
+  const long long rows = (long long)B * H;
+  int nblk = (int)((rows + 7) / 8 < kRedBlocks ? (rows + 7) / 8 : kRedBlocks);
+  dim3 grid(nblk, tdr_cdiv(C, 128));
   dw_wgrad_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy_bf16), dy_ld,
                                             reinterpret_cast<const bf16*>(x_bf16), x_ld, B, H, W, C, workspace);
   TDR_CHECK_LAUNCH();
@@ -881,7 +984,7 @@ extern "C" int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf
   const int nv = (nvec + G - 1) / G;
   const int slots = 8 * (32 / G);
   long long nb = (rows + slots - 1) / slots;
-  const int blocks = (int)(nb < kRedBlocks ? nb : kRedBlocks);
+  const int blocks = (int)(nb < 3 * kRedBlocks ? nb : 3 * kRedBlocks);
   const size_t smem = want_w ? (size_t)2 * slots * C * sizeof(float) : 0;
   TDR_CHECK_ARG(smem <= 200 * 1024, "tdr_rownorm_bwd: C too large for the weight-gradient reduction");
   const bf16* g = reinterpret_cast<const bf16*>(dy_bf16);
@@ -936,14 +1039,32 @@ extern "C" int tdr_mdta_bwd(const float* partials, const float* attn, int B, lon
   const size_t nbytes = tdr_mdta_partials_bytes(B, P, C, heads);
   TDR_CHECK_ARG(nbytes != 0, "tdr_mdta_bwd: unsupported MDTA shape");
   const int c = C / heads;
+  float* dwout_part = workspace;                              // [B][C][C]
+  float* dattn = workspace + (size_t)B * C * C;               // [B][heads][c][c]
+  float* dtemp_part = dattn + (size_t)B * heads * c * c;      // [B][heads]
+  {
+    // dattn[b,h][i][j] = sum_co W_out[co][hc+i] * dWeff[b][co][hc+j]
+    SgemmArgs g;
+    g.A = w_out; g.B = dweff; g.C = dattn; g.M = c; g.N = c; g.K = C; g.nb2 = heads;
+    g.sam = 1; g.sak = C; g.sbk = C; g.sbn = 1; g.scm = c; g.scn = 1;
+    g.a_b1 = 0; g.a_b2 = c; g.b_b1 = (long long)C * C; g.b_b2 = c; g.c_b1 = (long long)heads * c * c; g.c_b2 = (long long)c * c;
+    sgemm_batched_kernel<<<dim3(tdr_cdiv(c, 64), tdr_cdiv(c, 64), B * heads), 256, 0, stream>>>(g);
+    TDR_CHECK_LAUNCH();
+    // dW_out[b][co][hc+i] = sum_j dWeff[b][co][hc+j] * attn[b,h][i][j]
+    g.A = dweff; g.B = attn; g.C = dwout_part; g.M = C; g.N = c; g.K = c;
+    g.sam = C; g.sak = 1; g.sbk = 1; g.sbn = c; g.scm = C; g.scn = 1;
+    g.a_b1 = (long long)C * C; g.a_b2 = c; g.b_b1 = (long long)heads * c * c; g.b_b2 = (long long)c * c;
+    g.c_b1 = (long long)C * C; g.c_b2 = c;
+    sgemm_batched_kernel<<<dim3(tdr_cdiv(c, 64), tdr_cdiv(C, 64), B * heads), 256, 0, stream>>>(g);
+    TDR_CHECK_LAUNCH();
+  }
   MdtaBwdArgs a;
   a.C = C; a.heads = heads;
   a.nchunks = (int)(nbytes / sizeof(float) / ((size_t)B * heads * ((size_t)c * c + 2 * c)));
-  a.partials = partials; a.attn = attn; a.temperature = temperature; a.w_out = w_out; a.dweff = dweff;
+  a.partials = partials; a.attn = attn; a.dattn = dattn; a.temperature = temperature;
   a.mqk = reinterpret_cast<bf16*>(mqk_bf16); a.mqk_ld = mqk_ld;
-  a.dwout_part = workspace;                       // [B][C][C]
-  a.dtemp_part = workspace + (size_t)B * C * C;   // [B][heads]
-  const size_t smem = ((size_t)3 * c * c + 64 * c + 4 * c) * sizeof(float);
+  a.dtemp_part = dtemp_part;
+  const size_t smem = ((size_t)3 * c * (c + 1) + 4 * c) * sizeof(float);
   TDR_CHECK_ARG(smem <= 220 * 1024, "tdr_mdta_bwd: head too wide for shared memory");
   static bool attr_set = false;
   if (!attr_set) {
@@ -952,15 +1073,16 @@ extern "C" int tdr_mdta_bwd(const float* partials, const float* attn, int B, lon
   }
   mdta_bwd_kernel<<<dim3(heads, B), 256, smem, stream>>>(a);
   TDR_CHECK_LAUNCH();
-  reduce_parts_kernel<<<tdr_cdiv(C * C, 256), 256, 0, stream>>>(a.dwout_part, B, C * C, dw_out, 1, nullptr, accumulate, 1.f);
+  reduce_parts_kernel<<<tdr_cdiv(C * C, 256), 256, 0, stream>>>(dwout_part, B, C * C, dw_out, 1, nullptr, accumulate, 1.f);
   TDR_CHECK_LAUNCH();
-  reduce_parts_kernel<<<1, 256, 0, stream>>>(a.dtemp_part, B, heads, dtemperature, 1, nullptr, accumulate, 1.f);
+  reduce_parts_kernel<<<1, 256, 0, stream>>>(dtemp_part, B, heads, dtemperature, 1, nullptr, accumulate, 1.f);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
 
 extern "C" size_t tdr_mdta_bwd_workspace_bytes(int B, int C, int heads) {
-  return ((size_t)B * C * C + (size_t)B * heads) * sizeof(float);
+  const size_t c = heads > 0 ? (size_t)(C / heads) : 0;
+  return ((size_t)B * C * C + (size_t)B * heads * c * c + (size_t)B * heads) * sizeof(float);
 }
 
 extern "C" int tdr_scale_add_f32(const float* x, long long x_ld, const float* y, long long y_ld, long long rows, int C,
