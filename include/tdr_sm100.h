@@ -120,7 +120,10 @@ int tdr_gate_mul(const void* x_bf16, long long ld, long long rows, int C /* outp
 size_t tdr_naf_sca_workspace_bytes(int B, long long P, int C);
 int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long long P, int C, const float* w_sca /* [C][C] */,
                      const float* b_sca, const float* w3 /* fp32 [Co][C] */, int Co, const float* rowscale /* [Co] */,
-                     void* weff_bf16, long long weff_ld, float* workspace, cudaStream_t stream);
+                     void* weff_bf16, long long weff_ld, float* workspace,
+                     float* mean_out /* optional [B][C]: avgpool(g) */, float* s_out /* optional [B][C]: sca vector */,
+                     void* weff_t_bf16 /* optional Weff[b]^T [B][C][weff_t_ld] (dgrad operand) */, long long weff_t_ld,
+                     cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * MDTA channel attention R:262-276.
@@ -232,7 +235,20 @@ int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf16, long lo
  * gate 1 (GDFN, gelu(a)*b R:238-239): dy = [dg*b*gelu'(a) | dg*gelu(a)];  gate 2 (SimpleGate): dy = [dg*b | dg*a].
  * dy may alias y. */
 int tdr_gate_bwd(const void* y_bf16, long long y_ld, const void* dg_bf16, long long dg_ld, long long rows, int Ch,
-                 int gate, void* dy_bf16, long long dy_ld, cudaStream_t stream);
+                 int gate, void* dy_bf16, long long dy_ld,
+                 const float* dg_add /* optional fp32 [rows / rows_per_sample][Ch] added to dg (SCA pool gradient) */,
+                 long long rows_per_sample, cudaStream_t stream);
+/* NAFBlock scaled convs N:225-237, y = x + scale[co] * (W (g * s_b) + bias) with scale = beta (conv3, s_b = SCA vector)
+ * or gamma (conv5, s = NULL).  raw = tdr_wgrad(dy, g) [nb][Co][C] (per sample when s != NULL), colsum_dy = tdr_colsum(dy):
+ *   dW += scale * sum_b s_b raw_b,  dscale += sum W s_b raw_b + bias * colsum_dy,  dbias += scale * colsum_dy.
+ * tdr_naf_sca_bwd continues through the SCA branch N:192-196: dW_sca, db_sca (+=) and dg_add[b][c] = the per-sample
+ * constant that the average pool adds to every pixel's dg (pass it to tdr_gate_bwd). */
+int tdr_naf_scaled_conv_bwd(const float* raw, int nb, int Co, int C, const float* W /* fp32 [Co][C] */, const float* bias,
+                            const float* scale, const float* colsum_dy, const float* s /* [nb][C] or NULL */, float* dW,
+                            float* dbias, float* dscale, cudaStream_t stream);
+int tdr_naf_sca_bwd(const float* raw, int B, int Co, int C, const float* w3, const float* scale, const float* mean,
+                    const float* w_sca, long long P, float* dw_sca, float* db_sca, float* dg_add,
+                    float* workspace /* B*C floats */, cudaStream_t stream);
 /* Backward of the MDTA score path R:266-276 given dWeff (per-sample tdr_wgrad of the attn.v.project_out product):
  * dW_out (+)=, dtemperature (+)=, and mqk[b] = the [2C x 2C] matrix with [dq; dk] = mqk[b] . [q; k] per pixel (softmax,
  * temperature and F.normalize backward folded; bf16 [B][2C][mqk_ld], rows beyond 2C / pad columns untouched). */

@@ -946,6 +946,49 @@ def check_train_step():
     out.append(dict(name="autograd_into_flat_buffers", ok=bool(gn > 0 and np.isfinite(gn)), max_err=gn, tol=None))
     return out
 
+
+def check_nafnet_grad():
+    """NAFNet / NAFNetRefFusion: L1 loss backward through the explicit schedule vs autograd through the oracle."""
+    from oracle import nafnet as ON, weights as Wt
+    from oracle.make_golden import denoise_inputs, guided_inputs
+    from textualdegremoval_b200.archs import define_network
+    out = []
+    for name in ("nafnet_tiny_gray64", "nafnet_rgb_ragged"):
+        meta, _ = _golden(name)
+        net = define_network(dict(type="NAFNet", **meta["cfg"]))
+        sd = Wt.load_seeded(net, meta["seed"])
+        lq, gt = denoise_inputs(meta)
+        sdg = {k_: v.clone().requires_grad_(True) for k_, v in sd.items()}
+        yr = ON.nafnet_forward(sdg, lq)
+        (yr - gt).abs().mean().backward()
+        net = net.to(DEV).train()
+        y = net(lq.to(DEV))
+        (y - gt.to(DEV)).abs().mean().backward()
+        out.append(result(f"train_fwd_{name}", y.detach().cpu(), yr.detach(), E2E_TOL / max(yr.abs().max().item(), 1e-6)))
+        tot, worst, groups = _grad_compare(name, net, sdg, out)
+        note = f"worst tensor {worst[0]} {worst[1]:.3f}; " + ", ".join(f"{k_}={v:.3f}" for k_, v in sorted(groups.items(), key=lambda kv: -kv[1])[:4])
+        out.append(dict(name=f"grad_global_{name}", max_err=tot, tol=0.02, ok=bool(tot <= 0.02), note=note))
+        wm = max(groups.values())
+        out.append(dict(name=f"grad_modules_{name}", max_err=wm, tol=0.06, ok=bool(wm <= 0.06), note="worst module"))
+    meta, _ = _golden("guided_nafnet_256")
+    net = define_network(dict(type="NAFNetRefFusion", **meta["cfg"]))
+    sd = Wt.load_seeded(net, meta["seed"])
+    lq, rf = guided_inputs(meta)
+    gt = Wt.seeded_image("gt", meta["lq"], meta["seed"])
+    sdg = {k_: v.clone().requires_grad_(True) for k_, v in sd.items()}
+    yr = ON.nafnet_ref_fusion_forward(sdg, lq, rf)
+    (yr - gt).abs().mean().backward()
+    net = net.to(DEV).train()
+    y = net(lq.to(DEV), rf.to(DEV))
+    (y - gt.to(DEV)).abs().mean().backward()
+    out.append(guided_result("train_fwd_guided_nafnet_256", y.detach().cpu(), yr.detach()))
+    tot, worst, groups = _grad_compare("guided_nafnet_256", net, sdg, out)
+    note = f"worst tensor {worst[0]} {worst[1]:.3f}; " + ", ".join(f"{k_}={v:.3f}" for k_, v in sorted(groups.items(), key=lambda kv: -kv[1])[:5])
+    out.append(dict(name="grad_global_guided_nafnet_256", max_err=tot, tol=0.03, ok=bool(tot <= 0.03), note=note))
+    wm = max(groups.values())
+    out.append(dict(name="grad_modules_guided_nafnet_256", max_err=wm, tol=0.1, ok=bool(wm <= 0.1), note="worst module"))
+    return out
+
 CHECKS = {
     "layout": check_layout,
     "rownorm": check_rownorm,
@@ -970,6 +1013,7 @@ CHECKS = {
     "restormer_grad": check_restormer_grad,
     "guided_grad": check_guided_grad,
     "train_step": check_train_step,
+    "nafnet_grad": check_nafnet_grad,
 }
 
 

@@ -19,7 +19,9 @@ import torch.nn as nn
 
 from .. import ops
 from ..lib import TdrError
-from .masa import Encoder, MasaMixin, _f
+from .masa import Encoder, MasaMixin, MasaTrainMixin, _f
+from .nafnet_train import GuidedNAFTrainMixin, NAFTrainMixin
+from .restormer_train import train_call
 
 F32, BF16 = torch.float32, torch.bfloat16
 
@@ -130,6 +132,9 @@ class _NAFBase(nn.Module):
     def _prep_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
     def prepared(self):
         key = self._prep_key()
         if self._prep_cache is None or self._prep_cache[0] != key:
@@ -188,7 +193,7 @@ class _NAFBase(nn.Module):
         return torch.empty((B, H, W, c), dtype=F32, device=dev)
 
 
-class NAFNet(_NAFBase):
+class NAFNet(NAFTrainMixin, _NAFBase):
     def __init__(self, img_channel=3, width=16, middle_blk_num=1, enc_blk_nums=[], dec_blk_nums=[]):
         super().__init__()
         self._build_unet(img_channel, width, middle_blk_num, enc_blk_nums, dec_blk_nums)
@@ -198,8 +203,11 @@ class NAFNet(_NAFBase):
         return self._prepare_unet()
 
     def forward(self, inp):
-        """:356-379.  NCHW in/out, zero-padded to a multiple of 2**stages and cropped back."""
+        """:356-379.  NCHW in/out, zero-padded to a multiple of 2**stages and cropped back.  Differentiable w.r.t. the
+        parameters under autograd (nafnet_train / restormer_train.NetFunction)."""
         self._check(inp)
+        if self._wants_grad():
+            return train_call(self, inp)
         P = self.prepared()
         B, _, H, W = inp.shape
         h, w = ops.round_up(H, self.padder_size), ops.round_up(W, self.padder_size)
@@ -210,7 +218,7 @@ class NAFNet(_NAFBase):
         return ops.nhwc_to_nchw(out, H, W, res=inp32)
 
 
-class NAFNetRefFusion(MasaMixin, _NAFBase):
+class NAFNetRefFusion(GuidedNAFTrainMixin, MasaTrainMixin, MasaMixin, _NAFBase):
     def __init__(self, img_channel=3, width=16, middle_blk_num=1, enc_blk_nums=[], dec_blk_nums=[], nf=64,
                  ext_n_blocks=[4, 4, 4, 4], reffusion_n_blocks=[1, 1, 1, 1], reffusion_n_blocks_middle=1, scale=1,
                  num_nbr=1, psize=3, lr_block_size=8, ref_down_block_size=1.5, dilations=[1, 2, 3]):
@@ -243,6 +251,8 @@ class NAFNetRefFusion(MasaMixin, _NAFBase):
     def forward(self, inp, ref, return_aux=False):
         """:587-740.  NCHW in/out, arbitrary H, W (zero-padded to 2**stages * lr_block_size, cropped back)."""
         self._check(inp, ref)
+        if self._wants_grad() and not return_aux:
+            return train_call(self, inp, ref)
         P = self.prepared()
         dev = inp.device
         B, _, oh, ow = inp.shape

@@ -600,7 +600,8 @@ __device__ __forceinline__ void gelu_and_grad(float a, float& g, float& dg) {
 // with act = GELU (gate 1) or identity (gate 2: SimpleGate, dyo = [dg*b | dg*a]).  dyo may alias y.
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const bf16* __restrict__ y, long long y_ld,
                                                        const bf16* __restrict__ dg, long long dg_ld, long long rows,
-                                                       int Ch, int gate, bf16* __restrict__ dyo, long long dyo_ld) {
+                                                       int Ch, int gate, bf16* __restrict__ dyo, long long dyo_ld,
+                                                       const float* __restrict__ dg_add, long long rows_per_sample) {
   const int nv = Ch >> 3;
   const long long total = rows * nv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -610,6 +611,11 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const bf16* __restrict__ 
     unpack8(*reinterpret_cast<const bf16x8*>(y + r * y_ld + c), a);
     unpack8(*reinterpret_cast<const bf16x8*>(y + r * y_ld + Ch + c), b);
     unpack8(*reinterpret_cast<const bf16x8*>(dg + r * dg_ld + c), g);
+    if (dg_add) {                     // per-sample channel term (gradient through the SCA average pool N:192-196)
+      const float* ad = dg_add + (r / rows_per_sample) * Ch + c;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] += ad[k];
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       if (gate == 1) {
@@ -873,6 +879,81 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(const bf16* __restrict__
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ NAFBlock scaled convs
+// y = x + scale[co] * (W (g * s_b) + bias)  (N:225-237: conv3 with beta and the SCA vector s_b, conv5 with gamma, s = 1).
+// Given raw[b][co][ci] = sum_p dy[b,p,co] g[b,p,ci] (tdr_wgrad) and cs[co] = sum_p dy[p,co]:
+//   dW[co][ci] += scale[co] * sum_b s_b[ci] raw_b[co][ci];   dscale[co] += sum_{b,ci} W[co][ci] s_b[ci] raw_b[co][ci] + bias[co] cs[co]
+//   dbias[co] += scale[co] * cs[co].     grid (Co), block 256.
+__global__ void __launch_bounds__(256) naf_scaled_conv_bwd_kernel(const float* __restrict__ raw, int nb, int Co, int C,
+                                                                  const float* __restrict__ W,
+                                                                  const float* __restrict__ bias,
+                                                                  const float* __restrict__ scale,
+                                                                  const float* __restrict__ cs,
+                                                                  const float* __restrict__ s, float* __restrict__ dW,
+                                                                  float* __restrict__ dbias, float* __restrict__ dscale) {
+  __shared__ float red[8];
+  const int co = blockIdx.x;
+  const float sc = scale[co];
+  float acc = 0.f;
+  for (int ci = threadIdx.x; ci < C; ci += blockDim.x) {
+    float t = 0.f;
+    for (int b = 0; b < nb; ++b) t = fmaf(s ? s[(size_t)b * C + ci] : 1.f, raw[((size_t)b * Co + co) * C + ci], t);
+    dW[(size_t)co * C + ci] += sc * t;
+    acc = fmaf(W[(size_t)co * C + ci], t, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const float b0 = bias ? bias[co] : 0.f;
+    dscale[co] += t + b0 * cs[co];
+    if (dbias) dbias[co] += sc * cs[co];
+  }
+}
+
+// ds[b][ci] = sum_co scale[co] W3[co][ci] raw_b[co][ci]     (thread per (b, ci); coalesced over ci)
+__global__ void __launch_bounds__(256) naf_sca_ds_kernel(const float* __restrict__ raw, int B, int Co, int C,
+                                                         const float* __restrict__ W3, const float* __restrict__ scale,
+                                                         float* __restrict__ ds) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * C) return;
+  const int b = idx / C, ci = idx % C;
+  float t = 0.f;
+  for (int co = 0; co < Co; ++co) t = fmaf(scale[co] * W3[(size_t)co * C + ci], raw[((size_t)b * Co + co) * C + ci], t);
+  ds[idx] = t;
+}
+
+// SCA 1x1 conv backward: dWsca[i][j] += sum_b ds_b[i] mean_b[j]; dbsca[i] += sum_b ds_b[i]; dgadd[b][j] = sum_i Wsca[i][j] ds_b[i] / P
+// grid (C + B): blocks [0, C) handle row i of dWsca, blocks [C, C + B) handle sample b of dgadd.
+__global__ void __launch_bounds__(256) naf_sca_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ mean,
+                                                          const float* __restrict__ w_sca, int B, int C, float inv_p,
+                                                          float* __restrict__ dwsca, float* __restrict__ dbsca,
+                                                          float* __restrict__ dgadd) {
+  if ((int)blockIdx.x < C) {
+    const int i = blockIdx.x;
+    for (int j = threadIdx.x; j < C; j += blockDim.x) {
+      float t = 0.f;
+      for (int b = 0; b < B; ++b) t = fmaf(ds[(size_t)b * C + i], mean[(size_t)b * C + j], t);
+      dwsca[(size_t)i * C + j] += t;
+    }
+    if (threadIdx.x == 0 && dbsca) {
+      float t = 0.f;
+      for (int b = 0; b < B; ++b) t += ds[(size_t)b * C + i];
+      dbsca[i] += t;
+    }
+  } else {
+    const int b = blockIdx.x - C;
+    for (int j = threadIdx.x; j < C; j += blockDim.x) {
+      float t = 0.f;
+      for (int i = 0; i < C; ++i) t = fmaf(w_sca[(size_t)i * C + j], ds[(size_t)b * C + i], t);
+      dgadd[(size_t)b * C + j] = t * inv_p;
+    }
+  }
+}
+
 }  // namespace
 
 // ================================================================================================ C ABI
@@ -1017,13 +1098,15 @@ extern "C" int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf
 }
 
 extern "C" int tdr_gate_bwd(const void* y_bf16, long long y_ld, const void* dg_bf16, long long dg_ld, long long rows,
-                            int Ch, int gate, void* dy_bf16, long long dy_ld, cudaStream_t stream) {
+                            int Ch, int gate, void* dy_bf16, long long dy_ld, const float* dg_add,
+                            long long rows_per_sample, cudaStream_t stream) {
+  TDR_CHECK_ARG(!dg_add || rows_per_sample > 0, "tdr_gate_bwd: rows_per_sample required with dg_add");
   TDR_CHECK_ARG(y_bf16 && dg_bf16 && dy_bf16 && rows > 0 && Ch > 0, "tdr_gate_bwd: bad arguments");
   TDR_CHECK_ARG(gate == 1 || gate == 2, "tdr_gate_bwd: gate must be 1 (GELU) or 2 (SimpleGate)");
   TDR_CHECK_ARG(Ch % 8 == 0 && y_ld % 8 == 0 && dg_ld % 8 == 0 && dy_ld % 8 == 0, "tdr_gate_bwd: multiples of 8");
   gate_bwd_kernel<<<grid_for(rows * (Ch / 8), 256, 16), 256, 0, stream>>>(
       reinterpret_cast<const bf16*>(y_bf16), y_ld, reinterpret_cast<const bf16*>(dg_bf16), dg_ld, rows, Ch, gate,
-      reinterpret_cast<bf16*>(dy_bf16), dy_ld);
+      reinterpret_cast<bf16*>(dy_bf16), dy_ld, dg_add, rows_per_sample);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
@@ -1124,6 +1207,28 @@ extern "C" int tdr_relu_mask(const void* y_bf16, long long y_ld, const void* dy_
   relu_mask_kernel<<<grid_for(rows * (C / 8), 256, 16), 256, 0, stream>>>(
       reinterpret_cast<const bf16*>(y_bf16), y_ld, reinterpret_cast<const bf16*>(dy_bf16), dy_ld, rows, C,
       reinterpret_cast<bf16*>(out_bf16), out_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_naf_scaled_conv_bwd(const float* raw, int nb, int Co, int C, const float* W, const float* bias,
+                                       const float* scale, const float* colsum_dy, const float* s, float* dW,
+                                       float* dbias, float* dscale, cudaStream_t stream) {
+  TDR_CHECK_ARG(raw && W && scale && colsum_dy && dW && dscale && nb > 0 && Co > 0 && C > 0,
+                "tdr_naf_scaled_conv_bwd: bad arguments");
+  naf_scaled_conv_bwd_kernel<<<Co, 256, 0, stream>>>(raw, nb, Co, C, W, bias, scale, colsum_dy, s, dW, dbias, dscale);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_naf_sca_bwd(const float* raw, int B, int Co, int C, const float* w3, const float* scale,
+                               const float* mean, const float* w_sca, long long P, float* dw_sca, float* db_sca,
+                               float* dg_add, float* workspace /* B*C floats */, cudaStream_t stream) {
+  TDR_CHECK_ARG(raw && w3 && scale && mean && w_sca && dw_sca && dg_add && workspace && B > 0 && Co > 0 && C > 0 && P > 0,
+                "tdr_naf_sca_bwd: bad arguments");
+  naf_sca_ds_kernel<<<tdr_cdiv((long long)B * C, 256), 256, 0, stream>>>(raw, B, Co, C, w3, scale, workspace);
+  TDR_CHECK_LAUNCH();
+  naf_sca_bwd_kernel<<<C + B, 256, 0, stream>>>(workspace, mean, w_sca, B, C, 1.f / (float)P, dw_sca, db_sca, dg_add);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -845,7 +845,9 @@ __global__ void __launch_bounds__(256) sca_fold_kernel(const float* __restrict__
                                                        const float* __restrict__ w_sca, const float* __restrict__ b_sca,
                                                        const float* __restrict__ w3, int Co,
                                                        const float* __restrict__ rowscale, bf16* __restrict__ weff,
-                                                       long long weff_ld) {
+                                                       long long weff_ld, float* __restrict__ mean_out,
+                                                       float* __restrict__ s_out, bf16* __restrict__ weff_t,
+                                                       long long weff_t_ld) {
   extern __shared__ float sm[];       // mean[C], s[C]
   float* mean = sm;
   float* s = sm + C;
@@ -864,12 +866,20 @@ __global__ void __launch_bounds__(256) sca_fold_kernel(const float* __restrict__
     if (lane == 0) s[c] = t + (b_sca ? b_sca[c] : 0.f);
   }
   __syncthreads();
+  if (blockIdx.x == 0 && mean_out) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      mean_out[(size_t)b * C + c] = mean[c];
+      s_out[(size_t)b * C + c] = s[c];
+    }
+  }
   const int co0 = blockIdx.x * 16;
   for (int i = threadIdx.x; i < 16 * C; i += blockDim.x) {
     const int co = co0 + i / C, ci = i % C;
-    if (co < Co)
-      weff[((size_t)b * Co + co) * weff_ld + ci] =
-          __float2bfloat16(w3[(size_t)co * C + ci] * s[ci] * (rowscale ? rowscale[co] : 1.f));
+    if (co < Co) {
+      const bf16 v = __float2bfloat16(w3[(size_t)co * C + ci] * s[ci] * (rowscale ? rowscale[co] : 1.f));
+      weff[((size_t)b * Co + co) * weff_ld + ci] = v;
+      if (weff_t) weff_t[((size_t)b * C + ci) * weff_t_ld + co] = v;      // transposed copy: dgrad operand
+    }
   }
 }
 }  // namespace
@@ -898,7 +908,10 @@ extern "C" size_t tdr_naf_sca_workspace_bytes(int B, long long P, int C) {
 
 extern "C" int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long long P, int C, const float* w_sca,
                                 const float* b_sca, const float* w3, int Co, const float* rowscale, void* weff_bf16,
-                                long long weff_ld, float* workspace, cudaStream_t stream) {
+                                long long weff_ld, float* workspace, float* mean_out, float* s_out, void* weff_t_bf16,
+                                long long weff_t_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG((mean_out == nullptr) == (s_out == nullptr), "tdr_naf_sca_fold: mean_out and s_out go together");
+  TDR_CHECK_ARG(!weff_t_bf16 || (weff_t_ld >= Co && weff_t_ld % 8 == 0), "tdr_naf_sca_fold: bad weff_t_ld");
   TDR_CHECK_ARG(g_bf16 && w_sca && w3 && weff_bf16 && workspace, "tdr_naf_sca_fold: null pointer");
   TDR_CHECK_ARG(B > 0 && P > 0 && C % 8 == 0 && ld % 8 == 0 && weff_ld >= C && weff_ld % 8 == 0 && Co > 0,
                 "tdr_naf_sca_fold: bad dims");
@@ -909,7 +922,8 @@ extern "C" int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long lo
   TDR_CHECK_LAUNCH();
   dim3 g2((Co + 15) / 16, B);
   sca_fold_kernel<<<g2, 256, 2 * C * sizeof(float), stream>>>(workspace, chunks, P, C, w_sca, b_sca, w3, Co, rowscale,
-                                                              reinterpret_cast<bf16*>(weff_bf16), weff_ld);
+                                                              reinterpret_cast<bf16*>(weff_bf16), weff_ld, mean_out, s_out,
+                                                              reinterpret_cast<bf16*>(weff_t_bf16), weff_t_ld);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

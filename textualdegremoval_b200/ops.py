@@ -249,16 +249,24 @@ def gate_mul(x16, out=None):
     return out
 
 
-def naf_sca_fold(g16, w_sca, b_sca, w3, rowscale=None):
-    """g16: bf16 [B,H,W,C] (gated features).  Returns per-sample folded conv3 weights bf16 [B, Co, C_p]."""
+def naf_sca_fold(g16, w_sca, b_sca, w3, rowscale=None, save=None):
+    """g16: bf16 [B,H,W,C] (gated features).  Returns per-sample folded conv3 weights bf16 [B, Co, C_p].
+    save: optional dict receiving mean / s / weff_t (training)."""
     B, H, W, Cc = g16.shape
     Co = w3.shape[0]
     nbytes = lib.load().tdr_naf_sca_workspace_bytes(B, H * W, Cc)
     ws = torch.empty(nbytes // 4, dtype=F32, device=g16.device)
     cp = round_up(Cc, 8)
     weff = torch.empty((B, Co, cp), dtype=BF16, device=g16.device)
+    mean = s_vec = weff_t = None
+    cop = round_up(Co, 8)
+    if save is not None:
+        mean = torch.empty((B, Cc), dtype=F32, device=g16.device)
+        s_vec = torch.empty((B, Cc), dtype=F32, device=g16.device)
+        weff_t = torch.zeros((B, Cc, cop), dtype=BF16, device=g16.device)
+        save.update(mean=mean, s=s_vec, weff_t=weff_t)
     _call("tdr_naf_sca_fold", _p(g16), _ld(g16), B, H * W, Cc, _p(w_sca), _p(b_sca), _p(w3), Co, _p(rowscale), _p(weff),
-          cp, _p(ws), _stream(), tag=f"C{Cc}", nbytes=B * H * W * Cc * 2)
+          cp, _p(ws), _p(mean), _p(s_vec), _p(weff_t), cop, _stream(), tag=f"C{Cc}", nbytes=B * H * W * Cc * 2)
     return weff
 
 
@@ -528,13 +536,31 @@ def rownorm_bwd(x32, dy16, mode, weight=None, eps=1e-5, add=None, out=None, dwei
     return out
 
 
-def gate_bwd(y16, dg16, gate, out=None):
+def gate_bwd(y16, dg16, gate, out=None, dg_add=None):
+    """dg_add: optional fp32 [B, C2/2] added to dg of every pixel of sample b (SCA pool gradient)."""
     B, H, W, C2 = y16.shape
     if out is None:
         out = y16
-    _call("tdr_gate_bwd", _p(y16), _ld(y16), _p(dg16), _ld(dg16), B * H * W, C2 // 2, gate, _p(out), _ld(out), _stream(),
-          tag=f"g{gate}_C{C2}", nbytes=B * H * W * C2 * 5)
+    _call("tdr_gate_bwd", _p(y16), _ld(y16), _p(dg16), _ld(dg16), B * H * W, C2 // 2, gate, _p(out), _ld(out), _p(dg_add),
+          H * W, _stream(), tag=f"g{gate}_C{C2}", nbytes=B * H * W * C2 * 5)
     return out
+
+
+def naf_scaled_conv_bwd(raw, W, bias, scale, cs, s, dW, dbias, dscale):
+    """raw fp32 [nb, Co, C]; accumulates dW [Co, C], dbias [Co], dscale [Co] (see include/tdr_sm100.h)."""
+    nb, Co, Cc = raw.shape
+    _call("tdr_naf_scaled_conv_bwd", _p(raw), nb, Co, Cc, _p(W), _p(bias), _p(scale), _p(cs), _p(s), _p(dW), _p(dbias),
+          _p(dscale), _stream(), tag=f"Co{Co}_C{Cc}")
+
+
+def naf_sca_bwd(raw, w3, scale, mean, w_sca, P, dw_sca, db_sca):
+    """Returns dg_add fp32 [B, C] (to be passed to gate_bwd); accumulates dw_sca [C, C] and db_sca [C]."""
+    B, Co, Cc = raw.shape
+    dg_add = torch.empty((B, Cc), dtype=F32, device=raw.device)
+    ws = torch.empty(B * Cc, dtype=F32, device=raw.device)
+    _call("tdr_naf_sca_bwd", _p(raw), B, Co, Cc, _p(w3), _p(scale), _p(mean), _p(w_sca), P, _p(dw_sca), _p(db_sca),
+          _p(dg_add), _p(ws), _stream(), tag=f"C{Cc}")
+    return dg_add
 
 
 def mdta_bwd(saved, B, P, C_, heads, temperature, w_out, dweff, dw_out, dtemp):
