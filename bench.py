@@ -154,7 +154,33 @@ def run_reference(args):
     return 0
 
 
+class _StdoutToStderr:
+    """fd-level redirect of stdout to stderr while the benchmark runs: libraries (NCCL's version banner) must not
+    pollute the single JSON line the driver parses.  ``emit`` writes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self._saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        return False
+
+
 def run_b200(args):
+    with _StdoutToStderr() as out:
+        return _run_b200(args, out)
+
+
+def _run_b200(args, out):
     import torch
     import torch.distributed as dist
     from textualdegremoval_b200 import define_network, lib, ops
@@ -212,13 +238,16 @@ def run_b200(args):
         return sum(s.elapsed_time(e) for s, e in evs)
 
     if args.ncu:
+        # profiling mode: run under `ncu --profile-from-start off ...` to capture exactly the steady-state step(s)
         with torch.no_grad():
             step_resident()
             torch.cuda.synchronize()
+            torch.cuda.profiler.start()
             for _ in range(args.steps):
                 step_resident()
             torch.cuda.synchronize()
-        print(json.dumps({"ncu_mode": True, "launches_per_step": ops.PROF.launches // (1 + args.steps)}))
+            torch.cuda.profiler.stop()
+        out.emit(json.dumps({"ncu_mode": True, "launches_per_step": ops.PROF.launches // (1 + args.steps)}))
         return 0
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
@@ -355,7 +384,7 @@ def run_b200(args):
                                 TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)) for k, v in rows], fh, indent=0)
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+    out.emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -140,6 +140,7 @@ int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long long P, int C,
 int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature /* [heads] */,
                   const float* w_out /* fp32 [C][C] */, void* weff_bf16, long long weff_ld, float* attn_ws,
                   void* weff_t_bf16 /* optional: Weff[b]^T, same ld (the dgrad operand of the training step) */,
+                  float* shat_out /* optional fp32 [B][heads][c*c + 2c]: normalised Gram | |q| | |k| (for tdr_mdta_bwd) */,
                   cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -230,6 +231,7 @@ int tdr_dwconv3x3_wgrad(const void* dy_bf16, long long dy_ld, const void* x_bf16
  * dweight / dbias (+)= column sums (either may be NULL; workspace needed when dweight != NULL).  dx may alias add. */
 int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf16, long long dy_ld, long long rows, int C, int mode,
                     const float* weight, float eps, const float* add, long long add_ld, float* dx, long long dx_ld,
+                    void* dx_bf16 /* optional bf16 copy of dx (operand of the next dgrad / wgrad) */, long long dx_bf16_ld,
                     float* dweight, float* dbias, int accumulate, float* workspace, cudaStream_t stream);
 /* Gate backward.  y = pre-gate depthwise output [rows, 2*Ch] (a | b), dg = gradient of the gated product [rows, Ch]:
  * gate 1 (GDFN, gelu(a)*b R:238-239): dy = [dg*b*gelu'(a) | dg*gelu(a)];  gate 2 (SimpleGate): dy = [dg*b | dg*a].
@@ -238,6 +240,12 @@ int tdr_gate_bwd(const void* y_bf16, long long y_ld, const void* dg_bf16, long l
                  int gate, void* dy_bf16, long long dy_ld,
                  const float* dg_add /* optional fp32 [rows / rows_per_sample][Ch] added to dg (SCA pool gradient) */,
                  long long rows_per_sample, cudaStream_t stream);
+/* Fused recompute + gate backward: dy = tdr_gate_bwd(tdr_dwconv3x3(in, gate 0), dg) without writing the pre-gate tensor:
+ * in = the depthwise conv's INPUT [B,H,W,C] (C = 2*Ch), dy bf16 [B,H,W,>=C] receives [d a | d b]. */
+int tdr_dwconv3x3_gate_bwd(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
+                           const float* bias, int gate /* 1 GELU gate, 2 SimpleGate */, const void* dg_bf16,
+                           long long dg_ld, const float* dg_add /* optional [B][C/2] */, void* dy_bf16, long long dy_ld,
+                           cudaStream_t stream);
 /* NAFBlock scaled convs N:225-237, y = x + scale[co] * (W (g * s_b) + bias) with scale = beta (conv3, s_b = SCA vector)
  * or gamma (conv5, s = NULL).  raw = tdr_wgrad(dy, g) [nb][Co][C] (per sample when s != NULL), colsum_dy = tdr_colsum(dy):
  *   dW += scale * sum_b s_b raw_b,  dscale += sum W s_b raw_b + bias * colsum_dy,  dbias += scale * colsum_dy.
@@ -253,7 +261,7 @@ int tdr_naf_sca_bwd(const float* raw, int B, int Co, int C, const float* w3, con
  * dW_out (+)=, dtemperature (+)=, and mqk[b] = the [2C x 2C] matrix with [dq; dk] = mqk[b] . [q; k] per pixel (softmax,
  * temperature and F.normalize backward folded; bf16 [B][2C][mqk_ld], rows beyond 2C / pad columns untouched). */
 size_t tdr_mdta_bwd_workspace_bytes(int B, int C, int heads);
-int tdr_mdta_bwd(const float* partials, const float* attn, int B, long long P, int C, int heads,
+int tdr_mdta_bwd(const float* shat /* tdr_mdta_weff shat_out */, const float* attn, int B, long long P, int C, int heads,
                  const float* temperature, const float* w_out, const float* dweff /* fp32 [B][C][C] */, void* mqk_bf16,
                  long long mqk_ld, float* dw_out, float* dtemperature, int accumulate, float* workspace,
                  cudaStream_t stream);

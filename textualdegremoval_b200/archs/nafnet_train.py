@@ -74,10 +74,9 @@ def run_naf_block_bwd(dout, sv, G):
     ops.wgrad(dt2, xn2, G(blk.conv4.weight))
     ops.colsum(dt2, G(blk.conv4.bias))
     _, dxn2 = ops.conv_gemm(dt2, p["w4_T"], c, Ci=ffn)
-    dy = ops.rownorm_bwd(y, dxn2, 1, p["n2_w"], p["eps"], add=dout, out=dout, dweight=G(blk.norm2.weight),
-                         dbias=G(blk.norm2.bias))
+    dy, dy16 = ops.rownorm_bwd(y, dxn2, 1, p["n2_w"], p["eps"], add=dout, out=dout, dweight=G(blk.norm2.weight),
+                               dbias=G(blk.norm2.bias), want16=True)
     # ---- y = x + beta * (conv3(g * sca(g)) + b3),  g = SG(dw3x3(conv1(LN1(x))))
-    dy16 = ops.rownorm(dy, 0)
     raw3 = torch.empty((B, c, dw // 2), dtype=F32, device=dev)
     ops.wgrad(dy16, g, raw3, Co=c, Ci=dw // 2, per_sample=True, strides=(c * (dw // 2), dw // 2, 1, 0), accumulate=False)
     ops.colsum(dy16, cs, accumulate=False)
@@ -86,8 +85,7 @@ def run_naf_block_bwd(dout, sv, G):
     dg_add = ops.naf_sca_bwd(raw3, p["w3"], p["beta"], sv["mean"], p["w_sca"], H * W, G(blk.sca[1].weight),
                              G(blk.sca[1].bias))
     _, dg = ops.conv_gemm(dy16, sv["weff_t"], dw // 2, Ci=c, w_batched=True)
-    ydw = ops.dwconv3x3(t1, p["w2"], p["b2"], gate=0)
-    dyd = ops.gate_bwd(ydw, dg, 2, dg_add=dg_add)
+    dyd = ops.dwconv3x3_gate_bwd(t1, p["w2"], p["b2"], 2, dg, dg_add=dg_add)
     ops.dwconv3x3_wgrad(dyd, t1, G(blk.conv2.weight), G(blk.conv2.bias))
     dt1 = ops.dwconv3x3(dyd, p["w2_f"], None)
     xn1 = ops.rownorm(x0, 1, p["n1_w"], p["n1_b"], p["eps"])

@@ -110,9 +110,10 @@ def run_block_train(x32, p, tape):
     return out
 
 
-def run_block_bwd(dout, sv, G):
-    """Backward of run_block_train.  dout: fp32 NHWC gradient wrt the block output (overwritten).  Returns the
-    gradient wrt the block input (fp32 NHWC)."""
+def run_block_bwd(dout, sv, G, dout16=None, want16=False):
+    """Backward of run_block_train.  dout: fp32 NHWC gradient wrt the block output (overwritten); dout16: its bf16 copy
+    when the producer already made one.  Returns the gradient wrt the block input (fp32 NHWC), or (d, d16) with
+    want16 (the LayerNorm backward emits the bf16 copy the next block's GEMMs need)."""
     p = sv["p"]
     blk = p["mod"]
     a, f = blk.attn, blk.ffn
@@ -124,16 +125,16 @@ def run_block_bwd(dout, sv, G):
     if fusion:
         ops.dot_f32(dout, sv["t"], G(blk.alpha))
         d2 = ops.scale_add(dout, None, scale_ptr=p["alpha"])
+        dout16 = None
     else:
         d2 = dout
     # ---- GDFN: x2 = x1 + project_out(gelu(a) * b), [a | b] = dw(project_in(LN2(x1)))
-    d2_16 = ops.rownorm(d2, 0)
+    d2_16 = dout16 if dout16 is not None else ops.rownorm(d2, 0)
     _, dg = ops.conv_gemm(d2_16, p["w_out_T"], hp, Ci=C_)
     ops.wgrad(d2_16, g, G(f.project_out.weight), ci_map=p["map_h"])
     if f.project_out.bias is not None:
         ops.colsum(d2_16, G(f.project_out.bias))
-    y = ops.dwconv3x3(hid, p["w_dw"], p["b_dw"], gate=0)
-    dy = ops.gate_bwd(y, dg, 1)
+    dy = ops.dwconv3x3_gate_bwd(hid, p["w_dw"], p["b_dw"], 1, dg)
     ops.dwconv3x3_wgrad(dy, hid, G(f.dwconv.weight), G(f.dwconv.bias), c_map=p["map_2h"])
     dhid = ops.dwconv3x3(dy, p["w_dw_f"], None)
     xn2 = ops.rownorm(x1, mode, p["ln2_w"], p["ln2_b"], 1e-5)
@@ -141,10 +142,9 @@ def run_block_bwd(dout, sv, G):
     ops.wgrad(dhid, xn2, G(f.project_in.weight), co_map=p["map_2h"])
     if f.project_in.bias is not None:
         ops.colsum(dhid, G(f.project_in.bias), c_map=p["map_2h"])
-    d1 = ops.rownorm_bwd(x1, dxn2, mode, p["ln2_w"], 1e-5, add=d2, out=d2, dweight=G(blk.norm2.body.weight),
-                         dbias=G(blk.norm2.body.bias))
+    d1, d1_16 = ops.rownorm_bwd(x1, dxn2, mode, p["ln2_w"], 1e-5, add=d2, out=d2, dweight=G(blk.norm2.body.weight),
+                                dbias=G(blk.norm2.body.bias), want16=True)
     # ---- MDTA: x1 = x0 + project_out(softmax(norm(q) norm(k)^T * temperature) v)
-    d1_16 = ops.rownorm(d1, 0)
     dqkv = torch.empty_like(qkv)
     ops.conv_gemm(d1_16, sv["weff_t"], C_, Ci=C_, w_batched=True, out_bf16=dqkv[..., 2 * C_:])
     dweff = torch.empty((B, C_, C_), dtype=F32, device=dout.device)
@@ -160,11 +160,13 @@ def run_block_bwd(dout, sv, G):
     ops.wgrad(dqkv0, xn1, G(a.qkv.weight))
     if a.qkv.bias is not None:
         ops.colsum(dqkv0, G(a.qkv.bias))
+    emit16 = want16 and not fusion
     d0 = ops.rownorm_bwd(x0, dxn1, mode, p["ln1_w"], 1e-5, add=d1, out=d1, dweight=G(blk.norm1.body.weight),
-                         dbias=G(blk.norm1.body.bias))
+                         dbias=G(blk.norm1.body.bias), want16=emit16)
+    d0, d0_16 = d0 if emit16 else (d0, None)
     if fusion:
         ops.scale_add(dout, d0, out=d0)            # + dout through the shortcut
-    return d0
+    return (d0, d0_16) if want16 else d0
 
 
 def run_stack_train(x32, preps, mods, tape):
@@ -175,8 +177,11 @@ def run_stack_train(x32, preps, mods, tape):
 
 
 def run_stack_bwd(d, tape, span, G):
+    d16 = None
     for i in range(span[1] - 1, span[0] - 1, -1):
-        d = run_block_bwd(d, tape[i], G)
+        want = i > span[0]
+        res = run_block_bwd(d, tape[i], G, dout16=d16, want16=want)
+        d, d16 = res if want else (res, None)
         tape[i] = None                              # free the block's activations as soon as they are consumed
     return d
 

@@ -63,7 +63,7 @@ static int wgrad_plan(const tdr_wgrad_desc* d, WgradPlan* p) {
   p->nb = d->per_sample ? d->B : 1;
   p->tiles_total = (d->per_sample ? 1 : d->B) * p->tiles_y * p->tiles_x;
   const int outer = p->T * p->m_tiles * p->n_tiles * p->nb;
-  int want = (2 * tdr_num_sms() + outer - 1) / outer;
+  int want = tdr_num_sms() / outer;          // one wave of CTAs (1 CTA / SM: the smem ring fills the SM)
   if (want < 1) want = 1;
   if (want > p->tiles_total) want = p->tiles_total;
   p->tiles_per_chunk = tdr_cdiv(p->tiles_total, want);
@@ -74,7 +74,7 @@ static int wgrad_plan(const tdr_wgrad_desc* d, WgradPlan* p) {
   return 0;
 }
 
-// grid (chunk, (tap * m_tiles + mt) * n_tiles + nt, sample-or-1); 6 warps: TMA producer, MMA issuer, 4 epilogue.
+// grid ((tap * m_tiles + mt) * n_tiles + nt, chunk, sample-or-1); 6 warps: TMA producer, MMA issuer, 4 epilogue.
 __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ TdrTensorMap map_dy,
                                                        const __grid_constant__ TdrTensorMap map_x, const WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -88,8 +88,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * pl.stages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunk = blockIdx.x, bz = blockIdx.z;
-  int yy = blockIdx.y;
+  // blockIdx.x = (tap, m tile, n tile) is the fastest-varying launch coordinate, so the CTAs that share a pixel chunk
+  // (and therefore re-read the same dy / x tiles) run concurrently and hit in L2
+  const int chunk = blockIdx.y, bz = blockIdx.z;
+  int yy = blockIdx.x;
   const int nt = yy % pl.n_tiles; yy /= pl.n_tiles;
   const int mt = yy % pl.m_tiles;
   const int tap = yy / pl.m_tiles;
@@ -329,102 +331,116 @@ __device__ __forceinline__ Q4 ldq(const bf16* p, bool ok) {
   return q;
 }
 
-constexpr int kDwgSeg = 32;
+// TMA version: a persistent CTA owns one 64-channel chunk and streams [8 x 32]-pixel tiles: the haloed x tile
+// [10 x 34 x 64ch] and the dy tile [8 x 32 x 64ch] land in shared memory through a 2-stage mbarrier ring (76 KB per
+// stage in flight per SM, independent of occupancy); out-of-image pixels are zero-filled by TMA, which is exactly the
+// conv's zero padding (x) and "no contribution" (dy), so the inner loop has no boundary logic.  A thread owns 4 channels
+// and 2 pixel columns and walks down the 10 staged rows keeping 3 dy rows in registers: 4 LDS.64 per 18 packed FMAs.
+constexpr int kDgRows = 8, kDgCols = 32;
+constexpr int kDgXBytes = (kDgRows + 2) * (kDgCols + 2) * 128;     // 43520
+constexpr int kDgYBytes = kDgRows * kDgCols * 128;                 // 32768
+constexpr int kDgStageBytes = 76544;                               // x box + dy box, rounded to 256 B
 
-__global__ void __launch_bounds__(256, 2) dw_wgrad_kernel(const bf16* __restrict__ dy, long long dy_ld,
-                                                          const bf16* __restrict__ x, long long x_ld, int B, int H, int W,
-                                                          int C, float* __restrict__ partials) {
-  __shared__ float sm[8][32][4];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c_lo = blockIdx.y * 128;
-  const int nq = (C - c_lo < 128 ? C - c_lo : 128) >> 2;
-  int LQ = 1;
-  while (LQ < nq) LQ <<= 1;
-  const int XS = 32 / LQ;
-  const int cq = lane % LQ, xs = lane / LQ;
-  const bool active = cq < nq;
-  const int c0 = c_lo + cq * 4;
-  const int span = XS * kDwgSeg;
-  const int nxseg = (W + span - 1) / span;
-  const long long total = (long long)B * H * nxseg;
+struct DwgArgs {
+  int B, H, W, C;
+  int tiles_x, tiles_y, chunks;
+  float* partials;
+};
+
+__device__ __forceinline__ Q4 ldsq(const uint8_t* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  Q4 q;
+  q.a = bf2_to_f2(u.x);
+  q.b = bf2_to_f2(u.y);
+  return q;
+}
+
+__global__ void __launch_bounds__(256, 1) dw_wgrad_tma_kernel(const __grid_constant__ TdrTensorMap map_x,
+                                                              const __grid_constant__ TdrTensorMap map_dy,
+                                                              const DwgArgs a) {
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ __align__(8) uint64_t full[2];
+  __shared__ float red[256][4];
+  const int tid = threadIdx.x;
+  const int cq = tid & 15, xl = tid >> 4;                  // channel quad within the chunk, pixel column (and +16)
+  if (tid == 0) {
+    tma_prefetch_desc(&map_x);
+    tma_prefetch_desc(&map_dy);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int cc = blockIdx.x % a.chunks;
+  const int grp = blockIdx.x / a.chunks, ngrp = gridDim.x / a.chunks;
+  const int n_spatial = a.B * a.tiles_y * a.tiles_x;
+  auto issue = [&](int sp, int stage) {                    // thread 0 only
+    int r = sp;
+    const int b = r / (a.tiles_y * a.tiles_x);
+    r %= a.tiles_y * a.tiles_x;
+    const int y0 = (r / a.tiles_x) * kDgRows, x0 = (r % a.tiles_x) * kDgCols;
+    uint8_t* dst = dsm + stage * kDgStageBytes;
+    mbar_expect_tx(&full[stage], kDgXBytes + kDgYBytes);
+    tma_load_4d(dst, &map_x, &full[stage], cc * 64, x0 - 1, y0 - 1, b);
+    tma_load_4d(dst + kDgXBytes, &map_dy, &full[stage], cc * 64, x0, y0, b);
+  };
   Q4 acc[10];
 #pragma unroll
   for (int t = 0; t < 10; ++t) acc[t].a = acc[t].b = 0ull;
-  for (long long t = (long long)blockIdx.x * 8 + warp; t < total; t += (long long)gridDim.x * 8) {
-    const int y = (int)(t % H);
-    const long long r = t / H;
-    const int xseg = (int)(r % nxseg), b = (int)(r / nxseg);
-    const int xb = xseg * span + xs * kDwgSeg;
-    int xe = xb + kDwgSeg;
-    if (xe > W) xe = W;
-    if (!active || xb >= W) continue;
-    const long long row = ((long long)b * H + y) * W;
-    const bool up = y > 0, dn = y + 1 < H;
-    const bf16* xr0 = x + (row - W) * x_ld + c0;
-    const bf16* xr1 = x + row * x_ld + c0;
-    const bf16* xr2 = x + (row + W) * x_ld + c0;
-    const bf16* gr = dy + row * dy_ld + c0;
-    Q4 w0[3], w1[3], w2[3];     // columns (x-1, x, x+1), rows (y-1, y, y+1)
-#define TDR_LDCOL(col, xx)                                        \
-  do {                                                            \
-    const bool in = (xx) >= 0 && (xx) < W;                        \
-    col[0] = ldq(xr0 + (long long)(xx) * x_ld, in && up);         \
-    col[1] = ldq(xr1 + (long long)(xx) * x_ld, in);               \
-    col[2] = ldq(xr2 + (long long)(xx) * x_ld, in && dn);         \
-  } while (0)
-#define TDR_STEP(cl, cm, cr, xx)                                  \
-  do {                                                            \
-    TDR_LDCOL(cr, (xx) + 1);                                      \
-    const Q4 g = ldq(gr + (long long)(xx) * dy_ld, true);         \
-    acc[9].a = add2(acc[9].a, g.a);                               \
-    acc[9].b = add2(acc[9].b, g.b);                               \
-    _Pragma("unroll") for (int rr = 0; rr < 3; ++rr) {            \
-      acc[rr * 3 + 0].a = fma2(g.a, cl[rr].a, acc[rr * 3 + 0].a); \
-      acc[rr * 3 + 0].b = fma2(g.b, cl[rr].b, acc[rr * 3 + 0].b); \
-      acc[rr * 3 + 1].a = fma2(g.a, cm[rr].a, acc[rr * 3 + 1].a); \
-      acc[rr * 3 + 1].b = fma2(g.b, cm[rr].b, acc[rr * 3 + 1].b); \
-      acc[rr * 3 + 2].a = fma2(g.a, cr[rr].a, acc[rr * 3 + 2].a); \
-      acc[rr * 3 + 2].b = fma2(g.b, cr[rr].b, acc[rr * 3 + 2].b); \
-    }                                                             \
-  } while (0)
-    TDR_LDCOL(w0, xb - 1);
-    TDR_LDCOL(w1, xb);
-    int xx = xb;
-    for (; xx + 2 < xe; xx += 3) {
-      TDR_STEP(w0, w1, w2, xx);
-      TDR_STEP(w1, w2, w0, xx + 1);
-      TDR_STEP(w2, w0, w1, xx + 2);
-    }
-    if (xx < xe) {
-      TDR_STEP(w0, w1, w2, xx);
-      if (xx + 1 < xe) TDR_STEP(w1, w2, w0, xx + 1);
-    }
-#undef TDR_STEP
-#undef TDR_LDCOL
-  }
-  // lanes holding the same channel quad at different x sub-segments, then the 8 warps
+  int it = 0;
+  if (tid == 0 && grp < n_spatial) issue(grp, 0);
+  for (int sp = grp; sp < n_spatial; sp += ngrp, ++it) {
+    const int stage = it & 1;
+    if (tid == 0 && sp + ngrp < n_spatial) issue(sp + ngrp, stage ^ 1);
+    mbar_wait(&full[stage], (it >> 1) & 1);
+    const uint8_t* xs = dsm + stage * kDgStageBytes + cq * 8;
+    const uint8_t* ys = xs + kDgXBytes;
 #pragma unroll
-  for (int t = 0; t < 10; ++t) {
-    float v[4];
-    upk2(acc[t].a, v[0], v[1]);
-    upk2(acc[t].b, v[2], v[3]);
-    for (int o = 16; o >= LQ; o >>= 1) {
+    for (int half = 0; half < 2; ++half) {
+      const int col = xl + 16 * half;                      // output column within the tile; x columns col .. col+2
+      Q4 g0, g1, g2;                                       // dy rows i-2, i-1, i  (taps ky = 2, 1, 0 of staged row i)
+      g0.a = g0.b = g1.a = g1.b = g2.a = g2.b = 0ull;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
-    }
-    __syncthreads();
+      for (int i = 0; i < kDgRows + 2; ++i) {              // staged x row i = image row y0 - 1 + i
+        g0 = g1;
+        g1 = g2;
+        if (i < kDgRows) {
+          g2 = ldsq(ys + (i * kDgCols + col) * 128);
+          acc[9].a = add2(acc[9].a, g2.a);
+          acc[9].b = add2(acc[9].b, g2.b);
+        } else {
+          g2.a = g2.b = 0ull;
+        }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) sm[warp][lane][i] = v[i];
-    __syncthreads();
-    if (threadIdx.x < 128) {
-      const int q = threadIdx.x >> 2, i = threadIdx.x & 3;
-      if (q < nq) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) s += sm[w][q][i];      // lane q (< LQ) holds the xs-reduced sum of quad q
-        partials[((size_t)blockIdx.x * 10 + t) * C + c_lo + q * 4 + i] = s;
+        for (int kx = 0; kx < 3; ++kx) {
+          const Q4 v = ldsq(xs + (i * (kDgCols + 2) + col + kx) * 128);
+          // x row i is tap ky of output row (i - ky): dy rows i (ky 0) = g2, i-1 (ky 1) = g1, i-2 (ky 2) = g0
+          acc[0 * 3 + kx].a = fma2(g2.a, v.a, acc[0 * 3 + kx].a);
+          acc[0 * 3 + kx].b = fma2(g2.b, v.b, acc[0 * 3 + kx].b);
+          acc[1 * 3 + kx].a = fma2(g1.a, v.a, acc[1 * 3 + kx].a);
+          acc[1 * 3 + kx].b = fma2(g1.b, v.b, acc[1 * 3 + kx].b);
+          acc[2 * 3 + kx].a = fma2(g0.a, v.a, acc[2 * 3 + kx].a);
+          acc[2 * 3 + kx].b = fma2(g0.b, v.b, acc[2 * 3 + kx].b);
+        }
       }
     }
+    __syncthreads();                                       // everyone is done with this stage before it is refilled
+  }
+  // reduce the 16 column-threads of every channel quad
+#pragma unroll
+  for (int t = 0; t < 10; ++t) {
+    upk2(acc[t].a, red[tid][0], red[tid][1]);
+    upk2(acc[t].b, red[tid][2], red[tid][3]);
+    __syncthreads();
+    if (tid < 64) {
+      const int q = tid >> 2, i = tid & 3;
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) sum += red[k * 16 + q][i];
+      const int c = cc * 64 + q * 4 + i;
+      if (c < a.C) a.partials[((size_t)grp * 10 + t) * a.C + c] = sum;
+    }
+    __syncthreads();
   }
 }
 
@@ -448,11 +464,12 @@ __global__ void __launch_bounds__(256) dw_wgrad_reduce_kernel(const float* __res
 // G lanes per row, NV float4 per lane (same mapping as the forward kernel).  dx = add + LN_bwd(dy) ; per-block partial
 // sums of dweight / dbias are reduced through shared memory in a fixed order.
 template <int NV>
-__global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restrict__ x, long long x_ld,
+__global__ void __launch_bounds__(256, 3) rownorm_bwd_kernel(const float* __restrict__ x, long long x_ld,
                                                           const bf16* __restrict__ dy, long long dy_ld, long long rows,
                                                           int C, int mode, const float* __restrict__ w, float eps,
                                                           const float* __restrict__ add, long long add_ld,
                                                           float* __restrict__ dx, long long dx_ld,
+                                                          bf16* __restrict__ dx16, long long dx16_ld,
                                                           float* __restrict__ partials, int G) {
   extern __shared__ float sm[];                // [2][256/G][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -467,11 +484,13 @@ __global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restric
   for (long long row0 = (long long)blockIdx.x * slots; row0 < rows; row0 += (long long)gridDim.x * slots) {
     const long long row = row0 + slot;
     const bool row_ok = row < rows;
-    float4 v[NV], g[NV];
+    float4 v[NV], g[NV], ad[NV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int idx = l + i * G;
+      ad[i] = (add && row_ok && idx < nvec) ? *reinterpret_cast<const float4*>(add + row * add_ld + idx * 4)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
       if (row_ok && idx < nvec) {
         v[i] = mode ? *reinterpret_cast<const float4*>(x + row * x_ld + idx * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         const uint2 pk = *reinterpret_cast<const uint2*>(dy + row * dy_ld + idx * 4);
@@ -545,11 +564,14 @@ __global__ void __launch_bounds__(256) rownorm_bwd_kernel(const float* __restric
           } else {
             r = g[i];
           }
-          if (add) {
-            const float4 a4 = *reinterpret_cast<const float4*>(add + row * add_ld + idx * 4);
-            r.x += a4.x; r.y += a4.y; r.z += a4.z; r.w += a4.w;
-          }
+          r.x += ad[i].x; r.y += ad[i].y; r.z += ad[i].z; r.w += ad[i].w;
           *reinterpret_cast<float4*>(dx + row * dx_ld + idx * 4) = r;
+          if (dx16) {                 // bf16 copy: the operand of the next dgrad / wgrad GEMMs
+            uint2 pk;
+            pk.x = pack2(r.x, r.y);
+            pk.y = pack2(r.z, r.w);
+            *reinterpret_cast<uint2*>(dx16 + row * dx16_ld + idx * 4) = pk;
+          }
         }
       }
     }
@@ -697,8 +719,8 @@ __global__ void __launch_bounds__(256) sgemm_batched_kernel(const SgemmArgs a) {
 // One CTA per (head, sample): softmax / temperature / normalise backward and the rows of the [2C x 2C] matrix.
 // Shared: attn, dattn (-> dS_hat), shat as [c][c+1] (padded against bank conflicts), nq, nk, r, s.
 struct MdtaBwdArgs {
-  int C, heads, nchunks;
-  const float* partials;   // forward Gram partials (tdr_mdta_gram)
+  int C, heads;
+  const float* shat;       // forward: normalised Gram | |q| | |k| per (sample, head) (tdr_mdta_weff shat_out)
   const float* attn;       // [B, heads, c, c]
   const float* dattn;      // [B, heads, c, c] = W_out[:, head]^T . dWeff[b][:, head]
   const float* temperature;
@@ -721,21 +743,14 @@ __global__ void __launch_bounds__(256) mdta_bwd_kernel(const MdtaBwdArgs a) {
   __shared__ float red[256];
   const int tid = threadIdx.x;
   const size_t psz = (size_t)c * c + 2 * c;
-  const float* pbase = a.partials + (size_t)(b * a.heads + h) * a.nchunks * psz;
+  const float* ssrc = a.shat + (size_t)(b * a.heads + h) * psz;
   const float* asrc = a.attn + (size_t)(b * a.heads + h) * c * c;
   const float* dsrc = a.dattn + (size_t)(b * a.heads + h) * c * c;
   const float temp = a.temperature[h];
-  for (int i = tid; i < 2 * c; i += 256) {
-    float s = 0.f;
-    for (int ch = 0; ch < a.nchunks; ++ch) s += pbase[(size_t)ch * psz + c * c + i];
-    nq[i] = fmaxf(sqrtf(fmaxf(s, 0.f)), 1e-12f);        // nq then nk (contiguous)
-  }
-  __syncthreads();
+  for (int i = tid; i < 2 * c; i += 256) nq[i] = ssrc[(size_t)c * c + i];      // nq then nk (contiguous)
   for (int t = tid; t < c * c; t += 256) {
-    float s = 0.f;
-    for (int ch = 0; ch < a.nchunks; ++ch) s += pbase[(size_t)ch * psz + t];
     const int i = t / c, j = t % c;
-    shat[i * ld + j] = s / (nq[i] * nk[j]);
+    shat[i * ld + j] = ssrc[t];
     attn[i * ld + j] = asrc[t];
     dat[i * ld + j] = dsrc[t];
   }
@@ -1003,7 +1018,7 @@ extern "C" int tdr_wgrad(const tdr_wgrad_desc* d, cudaStream_t stream) {
     TDR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid(p.nchunks, p.T * p.m_tiles * p.n_tiles, p.nb);
+  dim3 grid(p.T * p.m_tiles * p.n_tiles, p.nchunks, p.nb);
   wgrad_kernel<<<grid, 192, smem, stream>>>(map_dy, map_x, a);
   TDR_CHECK_LAUNCH();
   const long long total = (long long)p.nb * p.T * d->Co * d->Ci;
@@ -1036,11 +1051,37 @@ extern "C" int tdr_dwconv3x3_wgrad(const void* dy_bf16, long long dy_ld, const v
   TDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "tdr_dwconv3x3_wgrad: bad dims");
   TDR_CHECK_ARG(dy_ld % 8 == 0 && x_ld % 8 == 0 && ((uintptr_t)dy_bf16 & 15) == 0 && ((uintptr_t)x_bf16 & 15) == 0,
                 "tdr_dwconv3x3_wgrad: alignment");
-  const long long rows = (long long)B * H;
-  int nblk = (int)((rows + 7) / 8 < kRedBlocks ? (rows + 7) / 8 : kRedBlocks);
-  dim3 grid(nblk, tdr_cdiv(C, 128));
-  dw_wgrad_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(dy_bf16), dy_ld,
-                                            reinterpret_cast<const bf16*>(x_bf16), x_ld, B, H, W, C, workspace);
+  DwgArgs a;
+  a.B = B; a.H = H; a.W = W; a.C = C;
+  a.tiles_x = tdr_cdiv(W, kDgCols); a.tiles_y = tdr_cdiv(H, kDgRows);
+  a.chunks = tdr_cdiv(C, 64);
+  a.partials = workspace;
+  const int n_spatial = B * a.tiles_x * a.tiles_y;
+  int groups = tdr_num_sms() / a.chunks;
+  if (groups < 1) groups = 1;
+  if (groups > n_spatial) groups = n_spatial;
+  if (groups > kRedBlocks) groups = kRedBlocks;
+  const int nblk = groups;
+  TdrTensorMap map_x, map_dy;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint32_t es[4] = {1, 1, 1, 1};
+    const uint64_t sx[3] = {(uint64_t)x_ld * 2, (uint64_t)x_ld * 2 * W, (uint64_t)x_ld * 2 * W * H};
+    const uint32_t bx[4] = {64, (uint32_t)(kDgCols + 2), (uint32_t)(kDgRows + 2), 1};
+    int rc = tdr_make_tensor_map_bf16_noswizzle(&map_x, x_bf16, 4, dims, sx, bx, es);
+    if (rc) return rc;
+    const uint64_t sy[3] = {(uint64_t)dy_ld * 2, (uint64_t)dy_ld * 2 * W, (uint64_t)dy_ld * 2 * W * H};
+    const uint32_t by[4] = {64, (uint32_t)kDgCols, (uint32_t)kDgRows, 1};
+    rc = tdr_make_tensor_map_bf16_noswizzle(&map_dy, dy_bf16, 4, dims, sy, by, es);
+    if (rc) return rc;
+  }
+  const size_t smem = 2 * kDgStageBytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dw_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dw_wgrad_tma_kernel<<<groups * a.chunks, 256, smem, stream>>>(map_x, map_dy, a);
   TDR_CHECK_LAUNCH();
   dw_wgrad_reduce_kernel<<<tdr_cdiv(10 * C, 256), 256, 0, stream>>>(workspace, nblk, C, dw, db, c_map, accumulate);
   TDR_CHECK_LAUNCH();
@@ -1049,9 +1090,10 @@ extern "C" int tdr_dwconv3x3_wgrad(const void* dy_bf16, long long dy_ld, const v
 
 extern "C" int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf16, long long dy_ld, long long rows, int C,
                                int mode, const float* weight, float eps, const float* add, long long add_ld, float* dx,
-                               long long dx_ld, float* dweight, float* dbias, int accumulate, float* workspace,
-                               cudaStream_t stream) {
+                               long long dx_ld, void* dx_bf16, long long dx_bf16_ld, float* dweight, float* dbias,
+                               int accumulate, float* workspace, cudaStream_t stream) {
   TDR_CHECK_ARG(dy_bf16 && dx && rows > 0 && C > 0, "tdr_rownorm_bwd: bad arguments");
+  TDR_CHECK_ARG(dx_bf16_ld % 4 == 0, "tdr_rownorm_bwd: dx_bf16_ld must be a multiple of 4");
   TDR_CHECK_ARG(mode >= 0 && mode <= 2, "tdr_rownorm_bwd: bad mode");
   TDR_CHECK_ARG(mode == 0 || (x && weight), "tdr_rownorm_bwd: x and weight required");
   TDR_CHECK_ARG(C % 4 == 0 && x_ld % 4 == 0 && dy_ld % 4 == 0 && add_ld % 4 == 0 && dx_ld % 4 == 0,
@@ -1065,7 +1107,8 @@ extern "C" int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf
   const int nv = (nvec + G - 1) / G;
   const int slots = 8 * (32 / G);
   long long nb = (rows + slots - 1) / slots;
-  const int blocks = (int)(nb < 3 * kRedBlocks ? nb : 3 * kRedBlocks);
+  const long long cap = 3LL * tdr_num_sms() < 3 * kRedBlocks ? 3LL * tdr_num_sms() : 3 * kRedBlocks;   // one full wave at 3 CTAs / SM
+  const int blocks = (int)(nb < cap ? nb : cap);
   const size_t smem = want_w ? (size_t)2 * slots * C * sizeof(float) : 0;
   TDR_CHECK_ARG(smem <= 200 * 1024, "tdr_rownorm_bwd: C too large for the weight-gradient reduction");
   const bf16* g = reinterpret_cast<const bf16*>(dy_bf16);
@@ -1078,7 +1121,7 @@ extern "C" int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf
       attr_set = true;                                                                                                 \
     }                                                                                                                  \
     rownorm_bwd_kernel<NV><<<blocks, 256, smem, stream>>>(x, x_ld, g, dy_ld, rows, C, mode, weight, eps, add, add_ld, dx, \
-                                                          dx_ld, parts, G);                                            \
+                                                          dx_ld, reinterpret_cast<bf16*>(dx_bf16), dx_bf16_ld, parts, G); \
   } while (0)
   if (nv <= 1) TDR_RNB(1);
   else if (nv <= 2) TDR_RNB(2);
@@ -1111,16 +1154,15 @@ extern "C" int tdr_gate_bwd(const void* y_bf16, long long y_ld, const void* dg_b
   return TDR_OK;
 }
 
-extern "C" int tdr_mdta_bwd(const float* partials, const float* attn, int B, long long P, int C, int heads,
+extern "C" int tdr_mdta_bwd(const float* shat, const float* attn, int B, long long P, int C, int heads,
                             const float* temperature, const float* w_out, const float* dweff, void* mqk_bf16,
                             long long mqk_ld, float* dw_out, float* dtemperature, int accumulate, float* workspace,
                             cudaStream_t stream) {
-  TDR_CHECK_ARG(partials && attn && temperature && w_out && dweff && mqk_bf16 && dw_out && dtemperature && workspace,
+  TDR_CHECK_ARG(shat && attn && temperature && w_out && dweff && mqk_bf16 && dw_out && dtemperature && workspace,
                 "tdr_mdta_bwd: null pointer");
+  (void)P;
   TDR_CHECK_ARG(heads > 0 && C % heads == 0 && C / heads <= 128 && B > 0, "tdr_mdta_bwd: unsupported head width");
   TDR_CHECK_ARG(mqk_ld >= 2 * C && mqk_ld % 8 == 0, "tdr_mdta_bwd: bad mqk_ld");
-  const size_t nbytes = tdr_mdta_partials_bytes(B, P, C, heads);
-  TDR_CHECK_ARG(nbytes != 0, "tdr_mdta_bwd: unsupported MDTA shape");
   const int c = C / heads;
   float* dwout_part = workspace;                              // [B][C][C]
   float* dattn = workspace + (size_t)B * C * C;               // [B][heads][c][c]
@@ -1143,8 +1185,7 @@ extern "C" int tdr_mdta_bwd(const float* partials, const float* attn, int B, lon
   }
   MdtaBwdArgs a;
   a.C = C; a.heads = heads;
-  a.nchunks = (int)(nbytes / sizeof(float) / ((size_t)B * heads * ((size_t)c * c + 2 * c)));
-  a.partials = partials; a.attn = attn; a.dattn = dattn; a.temperature = temperature;
+  a.shat = shat; a.attn = attn; a.dattn = dattn; a.temperature = temperature;
   a.mqk = reinterpret_cast<bf16*>(mqk_bf16); a.mqk_ld = mqk_ld;
   a.dtemp_part = dtemp_part;
   const size_t smem = ((size_t)3 * c * (c + 1) + 4 * c) * sizeof(float);

@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
 // Grams (deterministic order), applies the F.normalize denominators, temperature and the row softmax.
 __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restrict__ partials, int C, int heads,
                                                            int nchunks, const float* __restrict__ temperature,
-                                                           float* __restrict__ attn) {
+                                                           float* __restrict__ attn, float* __restrict__ shat_out) {
   const int c = C / heads;
   const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,11 +196,20 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
   const float nqi = fmaxf(sqrtf(fmaxf(nq, 0.f)), 1e-12f);
   const float temp = temperature[h];
   float mx = -INFINITY;
+  // training: keep the normalised Gram and the norms ([c*c | nq(c) | nk(c)] per (sample, head)) for tdr_mdta_bwd
+  float* so = shat_out ? shat_out + (size_t)(b * heads + h) * psz : nullptr;
+  if (so && lane == 0) so[(size_t)c * c + i] = nqi;
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
     const int j = lane + 32 * t;
     if (j < c) {
-      g[t] = g[t] / (nqi * fmaxf(sqrtf(fmaxf(nk[t], 0.f)), 1e-12f)) * temp;
+      const float nkj = fmaxf(sqrtf(fmaxf(nk[t], 0.f)), 1e-12f);
+      const float sh = g[t] / (nqi * nkj);
+      if (so) {
+        so[(size_t)i * c + j] = sh;
+        if (i == 0) so[(size_t)c * c + c + j] = nkj;
+      }
+      g[t] = sh * temp;
       mx = fmaxf(mx, g[t]);
     }
   }
@@ -290,14 +299,14 @@ extern "C" int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long lon
 
 extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature,
                              const float* w_out, void* weff_bf16, long long weff_ld, float* attn_ws,
-                             void* weff_t_bf16, cudaStream_t stream) {
+                             void* weff_t_bf16, float* shat_out, cudaStream_t stream) {
   TDR_CHECK_ARG(partials && temperature && w_out && weff_bf16 && attn_ws, "tdr_mdta_weff: null pointer");
   GramPlan p;
   TDR_CHECK_ARG(make_plan(B, P, C, heads, &p) == 0, "tdr_mdta_weff: unsupported head width");
   TDR_CHECK_ARG(weff_ld >= C && weff_ld % 8 == 0, "tdr_mdta_weff: bad weff_ld");
   {
     dim3 grid((p.c + 7) / 8, heads, B);
-    mdta_softmax_kernel<<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws);
+    mdta_softmax_kernel<<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out);
     TDR_CHECK_LAUNCH();
   }
   const size_t smem = ((size_t)p.c * p.c + 32 * p.c) * sizeof(float);

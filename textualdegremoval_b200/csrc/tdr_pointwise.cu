@@ -292,8 +292,21 @@ struct DwArgs {
   int gate;
   bf16* out;
   long long out_ld;
+  const bf16* dg;          // GATE == 2 (gate backward): gradient of the gated product [B,H,W,Cout]
+  long long dg_ld;
+  const float* dg_add;     // optional per-sample term [B][Cout] added to dg (SCA pool gradient)
 };
 
+__device__ __forceinline__ void gelu_and_grad_pw(float a, float& g, float& dg) {
+  const float cdf = 0.5f * (1.f + erff(a * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * a * a);
+  g = a * cdf;
+  dg = cdf + a * pdf;
+}
+
+// GATE: 0 plain, 1 gated forward (a.gate 1 = GELU gate, 2 = SimpleGate), 2 gate BACKWARD: recomputes the two depthwise
+// halves (a | b) exactly as the forward does and writes d[a | b] = [dg * b * act'(a) | dg * act(a)] (2 * Cout channels),
+// i.e. tdr_dwconv3x3(gate 0) + tdr_gate_bwd without the round trip of the pre-gate tensor through HBM.
 template <int GATE>
 __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_constant__ TdrTensorMap map, const DwArgs a) {
   constexpr int NH = GATE ? 2 : 1;
@@ -375,6 +388,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
         for (int e = 0; e < NP; ++e) acc[k][h][e] = bv[h][e];
     const int x = x0 + xl;
     bf16* outp = a.out + (((long long)b * a.H + y0) * a.W + x) * a.out_ld + c0;
+    const bf16* dgp = GATE == 2 ? a.dg + (((long long)b * a.H + y0) * a.W + x) * a.dg_ld + c0 : nullptr;
     const bool st_ok = c_ok && x < a.W;
 #pragma unroll
     for (int i = 0; i < kDwRows + 2; ++i) {                // staged row i = input row y0 - 1 + i
@@ -395,19 +409,55 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
         }
       if (i >= 2) {                                        // output row y0 + i - 2 (slot i % 3) is complete
         if (st_ok && y0 + i - 2 < a.H) {
-          raw_t o;
-          uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+          if constexpr (GATE == 2) {
+            const raw_t gr = *reinterpret_cast<const raw_t*>(dgp);
+            const uint32_t* gu = reinterpret_cast<const uint32_t*>(&gr);
+            raw_t oa, ob;
+            uint32_t* oau = reinterpret_cast<uint32_t*>(&oa);
+            uint32_t* obu = reinterpret_cast<uint32_t*>(&ob);
 #pragma unroll
-          for (int e = 0; e < NP; ++e) {
-            f2 val = acc[i % 3][0][e];
-            if (GATE) val = mul2(a.gate == 1 ? gelu2(val) : val, acc[i % 3][NH - 1][e]);
-            float a0, a1;
-            upk2(val, a0, a1);
-            ou[e] = pack2(a0, a1);
+            for (int e = 0; e < NP; ++e) {
+              float av[2], bv2[2], gv[2], da[2], db[2];
+              upk2(acc[i % 3][0][e], av[0], av[1]);
+              upk2(acc[i % 3][1][e], bv2[0], bv2[1]);
+              upk2(bf2_to_f2(gu[e]), gv[0], gv[1]);
+              if (a.dg_add) {
+                gv[0] += a.dg_add[(long long)b * a.Cout + c0 + 2 * e];
+                gv[1] += a.dg_add[(long long)b * a.Cout + c0 + 2 * e + 1];
+              }
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                if (a.gate == 1) {
+                  float ga, dga;
+                  gelu_and_grad_pw(av[k], ga, dga);
+                  da[k] = gv[k] * bv2[k] * dga;
+                  db[k] = gv[k] * ga;
+                } else {
+                  da[k] = gv[k] * bv2[k];
+                  db[k] = gv[k] * av[k];
+                }
+              }
+              oau[e] = pack2(da[0], da[1]);
+              obu[e] = pack2(db[0], db[1]);
+            }
+            *reinterpret_cast<raw_t*>(outp) = oa;
+            *reinterpret_cast<raw_t*>(outp + a.Cout) = ob;
+          } else {
+            raw_t o;
+            uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+            for (int e = 0; e < NP; ++e) {
+              f2 val = acc[i % 3][0][e];
+              if (GATE) val = mul2(a.gate == 1 ? gelu2(val) : val, acc[i % 3][NH - 1][e]);
+              float a0, a1;
+              upk2(val, a0, a1);
+              ou[e] = pack2(a0, a1);
+            }
+            *reinterpret_cast<raw_t*>(outp) = o;
           }
-          *reinterpret_cast<raw_t*>(outp) = o;
         }
         outp += (long long)a.W * a.out_ld;
+        if (GATE == 2) dgp += (long long)a.W * a.dg_ld;
       }
 #pragma unroll
       for (int h = 0; h < NH; ++h)
@@ -648,8 +698,10 @@ extern "C" int tdr_rownorm(const float* in, long long in_ld, long long rows, int
   return TDR_OK;
 }
 
-extern "C" int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
-                             const float* bias, int gate, void* out_bf16, long long out_ld, cudaStream_t stream) {
+static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
+                         const float* bias, int gate, void* out_bf16, long long out_ld, const void* dg_bf16,
+                         long long dg_ld, const float* dg_add, cudaStream_t stream) {
+  const bool bwd = dg_bf16 != nullptr;
   TDR_CHECK_ARG(in_bf16 && out_bf16 && weight, "tdr_dwconv3x3: null pointer");
   TDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "tdr_dwconv3x3: bad dims");
   TDR_CHECK_ARG(gate >= 0 && gate <= 2, "tdr_dwconv3x3: bad gate");
@@ -657,10 +709,12 @@ extern "C" int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H,
   TDR_CHECK_ARG(in_ld % 8 == 0 && out_ld % 4 == 0, "tdr_dwconv3x3: bad strides");
   TDR_CHECK_ARG(((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)out_bf16 & 7) == 0, "tdr_dwconv3x3: alignment");
   if (!gate) TDR_CHECK_ARG(out_ld % 8 == 0 && ((uintptr_t)out_bf16 & 15) == 0, "tdr_dwconv3x3: output alignment");
+  if (bwd) TDR_CHECK_ARG(gate >= 1 && (C / 2) % 4 == 0 && dg_ld % 4 == 0 && ((uintptr_t)dg_bf16 & 7) == 0,
+                         "tdr_dwconv3x3_gate_bwd: bad gate / alignment");
   const bf16* in = reinterpret_cast<const bf16*>(in_bf16);
   bf16* out = reinterpret_cast<bf16*>(out_bf16);
   static const bool use_strip = getenv("TDR_DWCONV_STRIP") != nullptr;     // previous (non-TMA) kernel, experiments only
-  if (use_strip) {
+  if (use_strip && !bwd) {
     constexpr int R = 16;
     if (gate) {
       const int items = W * (C / 2 / 4);
@@ -681,6 +735,7 @@ extern "C" int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H,
   a.chunks = tdr_cdiv(a.Cout, cb);
   a.total_tiles = B * a.tiles_x * a.tiles_y * a.chunks;
   a.wt = weight; a.bias = bias; a.gate = gate; a.out = out; a.out_ld = out_ld;
+  a.dg = reinterpret_cast<const bf16*>(dg_bf16); a.dg_ld = dg_ld; a.dg_add = dg_add;
   TdrTensorMap map;
   const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)in_ld * 2, (uint64_t)in_ld * 2 * W, (uint64_t)in_ld * 2 * W * H};
@@ -698,12 +753,28 @@ extern "C" int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H,
   if (!attr_set) {
     TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  if (gate) dwconv3x3_tma_kernel<1><<<grid, 256, smem, stream>>>(map, a);
+  if (bwd) dwconv3x3_tma_kernel<2><<<grid, 256, smem, stream>>>(map, a);
+  else if (gate) dwconv3x3_tma_kernel<1><<<grid, 256, smem, stream>>>(map, a);
   else dwconv3x3_tma_kernel<0><<<grid, 256, smem, stream>>>(map, a);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
+}
+
+extern "C" int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
+                             const float* bias, int gate, void* out_bf16, long long out_ld, cudaStream_t stream) {
+  return dwconv_launch(in_bf16, in_ld, B, H, W, C, weight, bias, gate, out_bf16, out_ld, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int tdr_dwconv3x3_gate_bwd(const void* in_bf16, long long in_ld, int B, int H, int W, int C,
+                                      const float* weight, const float* bias, int gate, const void* dg_bf16,
+                                      long long dg_ld, const float* dg_add, void* dy_bf16, long long dy_ld,
+                                      cudaStream_t stream) {
+  TDR_CHECK_ARG(dg_bf16 != nullptr && (gate == 1 || gate == 2), "tdr_dwconv3x3_gate_bwd: dg and gate 1|2 required");
+  TDR_CHECK_ARG(dy_ld >= C && dy_ld % 4 == 0, "tdr_dwconv3x3_gate_bwd: dy must hold 2 * (C/2) channels");
+  return dwconv_launch(in_bf16, in_ld, B, H, W, C, weight, bias, gate, dy_bf16, dy_ld, dg_bf16, dg_ld, dg_add, stream);
 }
 
 extern "C" int tdr_nchw_to_nhwc(const float* src, int B, int C, int H, int W, int pad_h, int pad_w, float* dst_f32,

@@ -55,7 +55,7 @@ SIGNATURES = {
     "tdr_naf_sca_fold": (_i, [_vp, _ll, _i, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp]),
     "tdr_mdta_partials_bytes": (_sz, [_i, _ll, _i, _i]),
     "tdr_mdta_gram": (_i, [_vp, _ll, _i, _ll, _i, _i, _vp, _vp]),
-    "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp]),
+    "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp]),
     "tdr_vit_patchify": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
     "tdr_vit_assemble_tokens": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tdr_softmax_rows": (_i, [_vp, _ll, _ll, _i, _f, _vp, _ll, _vp]),
@@ -107,8 +107,9 @@ SIGNATURES.update({
     "tdr_reduce_workspace_bytes": (_sz, [_i]),
     "tdr_colsum": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp, _i, _vp, _vp]),
     "tdr_dwconv3x3_wgrad": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
-    "tdr_rownorm_bwd": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _f, _vp, _ll, _vp, _ll, _vp, _vp, _i, _vp, _vp]),
+    "tdr_rownorm_bwd": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _f, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _vp, _vp]),
     "tdr_gate_bwd": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _ll, _vp, _ll, _vp]),
+    "tdr_dwconv3x3_gate_bwd": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _vp, _vp, _ll, _vp]),
     "tdr_naf_scaled_conv_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tdr_naf_sca_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp]),
     "tdr_mdta_bwd_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -230,11 +230,15 @@ def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False, save=None):
     cp = round_up(C_, 8)
     weff = torch.empty((B, C_, cp), dtype=BF16, device=qkv.device)
     attn = torch.empty((B, heads, C_ // heads, C_ // heads), dtype=F32, device=qkv.device)
-    weff_t = torch.zeros((B, C_, cp), dtype=BF16, device=qkv.device) if save is not None else None
-    _call("tdr_mdta_weff", _p(partials), B, P, C_, heads, _p(temperature), _p(w_out), _p(weff), cp, _p(attn),
-          _p(weff_t), _stream(), tag=f"C{C_}_h{heads}", nbytes=nbytes + _nb(weff))
+    weff_t = shat = None
     if save is not None:
-        save.update(partials=partials, attn=attn, weff=weff, weff_t=weff_t)
+        c = C_ // heads
+        weff_t = torch.zeros((B, C_, cp), dtype=BF16, device=qkv.device)
+        shat = torch.empty((B, heads, c * c + 2 * c), dtype=F32, device=qkv.device)
+    _call("tdr_mdta_weff", _p(partials), B, P, C_, heads, _p(temperature), _p(w_out), _p(weff), cp, _p(attn),
+          _p(weff_t), _p(shat), _stream(), tag=f"C{C_}_h{heads}", nbytes=nbytes + _nb(weff))
+    if save is not None:
+        save.update(shat=shat, attn=attn, weff=weff, weff_t=weff_t)
     return (weff, attn) if want_attn else weff
 
 
@@ -524,16 +528,20 @@ def dwconv3x3_wgrad(dy16, x16, dw, db=None, c_map=None, accumulate=True):
           flops=2 * 9 * B * H * W * Cc)
 
 
-def rownorm_bwd(x32, dy16, mode, weight=None, eps=1e-5, add=None, out=None, dweight=None, dbias=None, accumulate=True):
-    """dx = add + LN_bwd(dy) (fp32).  mode 0: dx = add + float(dy).  out may alias add."""
+def rownorm_bwd(x32, dy16, mode, weight=None, eps=1e-5, add=None, out=None, dweight=None, dbias=None, accumulate=True,
+                want16=False):
+    """dx = add + LN_bwd(dy) (fp32).  mode 0: dx = add + float(dy).  out may alias add.  want16: also return a bf16
+    copy of dx (what the next dgrad / wgrad GEMMs consume) -> (dx, dx16)."""
     B, H, W, Cc = dy16.shape
     if out is None:
         out = torch.empty((B, H, W, Cc), dtype=F32, device=dy16.device)
+    out16 = torch.empty((B, H, W, Cc), dtype=BF16, device=dy16.device) if want16 else None
     _call("tdr_rownorm_bwd", _p(x32), _ld(x32) if x32 is not None else 0, _p(dy16), _ld(dy16), B * H * W, Cc, mode,
-          _p(weight), eps, _p(add), _ld(add) if add is not None else 0, _p(out), _ld(out), _p(dweight), _p(dbias),
-          int(accumulate), _p(_red_ws(Cc, dy16.device)) if dweight is not None else None, _stream(), tag=f"m{mode}_C{Cc}",
-          nbytes=B * H * W * Cc * (2 + 4 + (4 if mode else 0) + (4 if add is not None else 0)))
-    return out
+          _p(weight), eps, _p(add), _ld(add) if add is not None else 0, _p(out), _ld(out), _p(out16),
+          _ld(out16) if out16 is not None else 0, _p(dweight), _p(dbias), int(accumulate),
+          _p(_red_ws(Cc, dy16.device)) if dweight is not None else None, _stream(), tag=f"m{mode}_C{Cc}_{H}x{W}",
+          nbytes=B * H * W * Cc * (2 + 4 + (4 if mode else 0) + (4 if add is not None else 0) + (2 if want16 else 0)))
+    return (out, out16) if want16 else out
 
 
 def gate_bwd(y16, dg16, gate, out=None, dg_add=None):
@@ -543,6 +551,16 @@ def gate_bwd(y16, dg16, gate, out=None, dg_add=None):
         out = y16
     _call("tdr_gate_bwd", _p(y16), _ld(y16), _p(dg16), _ld(dg16), B * H * W, C2 // 2, gate, _p(out), _ld(out), _p(dg_add),
           H * W, _stream(), tag=f"g{gate}_C{C2}", nbytes=B * H * W * C2 * 5)
+    return out
+
+
+def dwconv3x3_gate_bwd(x16, w9, bias, gate, dg16, dg_add=None):
+    """Fused recompute of the gated depthwise conv + gate backward: returns d(pre-gate) bf16 [B,H,W,C]."""
+    B, H, W, Cc = x16.shape
+    out = torch.empty((B, H, W, Cc), dtype=BF16, device=x16.device)
+    _call("tdr_dwconv3x3_gate_bwd", _p(x16), _ld(x16), B, H, W, Cc, _p(w9), _p(bias), gate, _p(dg16), _ld(dg16),
+          _p(dg_add), _p(out), _ld(out), _stream(), tag=f"g{gate}_C{Cc}_{H}x{W}", nbytes=B * H * W * Cc * 5,
+          flops=2 * 9 * B * H * W * Cc)
     return out
 
 
@@ -568,7 +586,7 @@ def mdta_bwd(saved, B, P, C_, heads, temperature, w_out, dweff, dw_out, dtemp):
     cp2 = round_up(2 * C_, 8)
     mqk = torch.zeros((B, 2 * C_, cp2), dtype=BF16, device=dweff.device)
     ws = workspace(lib.load().tdr_mdta_bwd_workspace_bytes(B, C_, heads), dweff.device)
-    _call("tdr_mdta_bwd", _p(saved["partials"]), _p(saved["attn"]), B, P, C_, heads, _p(temperature), _p(w_out), _p(dweff),
+    _call("tdr_mdta_bwd", _p(saved["shat"]), _p(saved["attn"]), B, P, C_, heads, _p(temperature), _p(w_out), _p(dweff),
           _p(mqk), cp2, _p(dw_out), _p(dtemp), 1, _p(ws), _stream(), tag=f"C{C_}_h{heads}")
     return mqk
 

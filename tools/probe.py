@@ -54,7 +54,43 @@ def gram(B, H, W, C_, heads):
     return (lambda: ops.mdta_weff(qkv, C_, heads, t, wo)), B * H * W * 2 * C_ * 2, 6 * B * H * W * C_ * (C_ // heads)
 
 
+def wg(B, H, W, Ci, Co, k=1):
+    dy, x = r16(B, H, W, Co), r16(B, H, W, Ci)
+    out = torch.zeros(Co, Ci, k, k, device=DEV)
+    return (lambda: ops.wgrad(dy, x, out, k=k, pad=k // 2)), B * H * W * (Ci + Co) * 2, 2 * B * H * W * Ci * Co * k * k
+
+
+def dwwg(B, H, W, C_):
+    dy, x = r16(B, H, W, C_), r16(B, H, W, C_)
+    dw_, db = torch.zeros(C_, 1, 3, 3, device=DEV), torch.zeros(C_, device=DEV)
+    return (lambda: ops.dwconv3x3_wgrad(dy, x, dw_, db)), B * H * W * C_ * 4, 18 * B * H * W * C_
+
+
+def lnb(B, H, W, C_):
+    x, add = torch.randn(B, H, W, C_, device=DEV), torch.randn(B, H, W, C_, device=DEV)
+    dy = r16(B, H, W, C_)
+    w = torch.ones(C_, device=DEV)
+    dwt, dbt = torch.zeros(C_, device=DEV), torch.zeros(C_, device=DEV)
+    return (lambda: ops.rownorm_bwd(x, dy, 1, w, 1e-5, add=add, out=add, dweight=dwt, dbias=dbt)), B * H * W * C_ * 14, 0
+
+
+def gateb(B, H, W, C2):
+    y, dg = r16(B, H, W, C2), r16(B, H, W, C2 // 2)
+    return (lambda: ops.gate_bwd(y, dg, 1)), B * H * W * C2 * 5, 0
+
+
 PROBES = {
+    "wg_pin96": lambda: wg(4, 512, 512, 96, 512),
+    "wg_qkv96": lambda: wg(4, 512, 512, 96, 288),
+    "wg_pout256": lambda: wg(4, 512, 512, 256, 96),
+    "wg_3x3_48": lambda: wg(8, 512, 512, 48, 48, k=3),
+    "wg_3x3_96": lambda: wg(8, 256, 256, 96, 96, k=3),
+    "wg_3x3_384": lambda: wg(8, 64, 64, 384, 384, k=3),
+    "dwwg512": lambda: dwwg(4, 512, 512, 512),
+    "dwwg288": lambda: dwwg(4, 512, 512, 288),
+    "dwwg1024": lambda: dwwg(4, 128, 128, 1024),
+    "lnb96": lambda: lnb(4, 512, 512, 96),
+    "gateb512": lambda: gateb(4, 512, 512, 512),
     "pin96": lambda: conv(4, 512, 512, 96, 512),
     "qkv96": lambda: conv(4, 512, 512, 96, 288),
     "pout256": lambda: conv(4, 512, 512, 256, 96, want="f32", res=True),
