@@ -295,6 +295,22 @@ int tdr_dilate2_nhwc(const void* in_bf16, long long in_ld, int B, int H, int W, 
                      int OH, int OW, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Weight packing (host-side `prepared()` of the arch modules; re-run after every optimizer step in training).
+ *   tdr_pack_conv_weight: nn.Conv2d weight fp32 [Co][Ci][KH][KW] -> bf16 [T][Co_p][ld] (the tdr_conv_gemm operand) and/or
+ *                         its transposed, tap-flipped twin [T][Ci_p][ld_t] (the data-gradient operand).  co_map / ci_map:
+ *                         optional DEVICE int32 padded->logical channel maps (-1 = zero row / column); scale: optional
+ *                         fp32 [Co] multiplied into output channel co.
+ *   tdr_pack_dw_weight  : depthwise weight [C][1][3][3] -> fp32 [9][C_p], its flipped twin, and the padded bias.
+ *   tdr_gather_vec      : out[i] = map[i] >= 0 ? v[map[i]] : 0.
+ * ------------------------------------------------------------------------------------------------------------- */
+int tdr_pack_conv_weight(const float* w, int Co, int Ci, int KH, int KW, const int* co_map, int Co_p, const int* ci_map,
+                         int Ci_p, const float* scale, void* out_bf16, long long ld, void* out_t_bf16, long long ld_t,
+                         cudaStream_t stream);
+int tdr_pack_dw_weight(const float* w, const float* bias, int C, const int* c_map, int C_p, float* out, float* out_flip,
+                       float* out_bias, cudaStream_t stream);
+int tdr_gather_vec(const float* v, const int* map, int n, int n_src, float* out, cudaStream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Layout / copies.
  * ------------------------------------------------------------------------------------------------------------- */
 int tdr_nchw_to_nhwc(const float* src, int B, int C, int H, int W, int pad_h, int pad_w /* zero-padded output size */,

@@ -571,7 +571,7 @@ def check_optim():
             ema_ref[k].mul_(0.999).add_(ref[k].detach(), alpha=0.001)
     for k in shapes:
         out.append(result(f"adamw_{k}", ps[k].detach(), ref[k].detach(), 2e-6))
-    ema = torch.cat([e[:g.n] for e, g in zip(eng.ema, eng.groups)])
+    ema = torch.cat([v.reshape(-1) for e, g in zip(eng.ema, eng.groups) for v in g.views(e)])
     order = [k for k in shapes if "masa" not in k] + [k for k in shapes if "masa" in k]
     out.append(result("ema", ema, torch.cat([ema_ref[k].reshape(-1) for k in order]), 2e-6))
     return out

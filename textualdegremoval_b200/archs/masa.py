@@ -128,10 +128,10 @@ class MasaTrainMixin:
         for i in range(1, self.masa_enc.levels + 1):
             c = getattr(self.masa_enc, f"conv_L{i}")
             if i > 1:
-                E[f"conv_L{i}"]["wT"] = ops.pack_conv_weight(_flip_T(c.weight))
+                E[f"conv_L{i}"]["wT"] = ops.pack_conv(c.weight, fwd=False, dgrad=True)[1]
             for (c1, c2), b in zip(E[f"blk_L{i}"], getattr(self.masa_enc, f"blk_L{i}")):
-                c1["wT"] = ops.pack_conv_weight(_flip_T(b.conv1.weight))
-                c2["wT"] = ops.pack_conv_weight(_flip_T(b.conv2.weight))
+                c1["wT"] = ops.pack_conv(b.conv1.weight, fwd=False, dgrad=True)[1]
+                c2["wT"] = ops.pack_conv(b.conv2.weight, fwd=False, dgrad=True)[1]
         E["_train"] = True
         return E
 

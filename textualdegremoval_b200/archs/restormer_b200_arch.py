@@ -102,32 +102,46 @@ def _blocks(n, cls, **kw):
 
 
 # ----------------------------------------------------------------------------------------------- weight preparation
-def _prep_block(blk: TransformerBlock):
-    """Pack one transformer block's parameters for the kernels (bf16 GEMM weights, padded GDFN halves)."""
+def _block_maps(blk, h, hp, dev):
+    """int32 padded->logical channel maps of the GDFN halves (static per block, cached on the module)."""
+    m = getattr(blk, "_tdr_maps", None)
+    if m is None or m[0].device != dev:
+        idx2 = torch.cat([torch.arange(h, device=dev), hp + torch.arange(h, device=dev)])
+        m2 = torch.full((2 * hp,), -1, dtype=torch.int32, device=dev)
+        m2[idx2] = torch.arange(2 * h, dtype=torch.int32, device=dev)
+        m1 = torch.full((hp,), -1, dtype=torch.int32, device=dev)
+        m1[:h] = torch.arange(h, dtype=torch.int32, device=dev)
+        m = (m2, m1)
+        blk._tdr_maps = m
+    return m
+
+
+def _prep_block(blk: TransformerBlock, train=False):
+    """Pack one transformer block's parameters for the kernels (bf16 GEMM weights, padded GDFN halves): one launch per
+    parameter.  train=True also emits the transposed / flipped twins the data-gradient kernels consume."""
     a, f = blk.attn, blk.ffn
     C_ = a.qkv.in_channels
     h = f.project_out.in_channels
     hp = ops.round_up(h, 8)
     dev = a.qkv.weight.device
-    idx2 = torch.cat([torch.arange(h, device=dev), hp + torch.arange(h, device=dev)])
-    p = dict(C=C_, heads=a.num_heads, h=h, hp=hp)
+    m2, m1 = _block_maps(blk, h, hp, dev)
+    p = dict(C=C_, heads=a.num_heads, h=h, hp=hp, map_2h=m2, map_h=m1, mod=blk)
     p["ln1_w"], p["ln1_b"] = _f(blk.norm1.body.weight), _f(blk.norm1.body.bias)
     p["ln2_w"], p["ln2_b"] = _f(blk.norm2.body.weight), _f(blk.norm2.body.bias)
     p["ln_mode"] = 1 if blk.norm1.body.bias is not None else 2
-    p["w_qkv"] = ops.pack_conv_weight(a.qkv.weight)
+    p["w_qkv"], p["w_qkv_T"] = ops.pack_conv(a.qkv.weight, dgrad=train)
     p["b_qkv"] = _f(a.qkv.bias)
-    p["w_qkv_dw"] = ops.pack_dw_weight(a.qkv_dwconv.weight)
-    p["b_qkv_dw"] = _f(a.qkv_dwconv.bias)
+    p["w_qkv_dw"], p["w_qkv_dw_f"], p["b_qkv_dw"] = ops.pack_dw(a.qkv_dwconv.weight, a.qkv_dwconv.bias, flip=train)
     p["temp"] = _f(a.temperature).reshape(-1)
     p["w_po"] = _f(a.project_out.weight).reshape(C_, C_)
     p["b_po"] = _f(a.project_out.bias)
-    p["w_in"] = ops.pack_conv_weight(f.project_in.weight, co_map=(2 * hp, idx2))
-    p["b_in"] = ops.pad_vec(f.project_in.bias, 2 * hp, idx2)
-    p["w_dw"] = ops.pack_dw_weight(f.dwconv.weight, 2 * hp, idx2)
-    p["b_dw"] = ops.pad_vec(f.dwconv.bias, 2 * hp, idx2)
-    p["w_out"] = ops.pack_conv_weight(f.project_out.weight, ci_map=(hp, torch.arange(h, device=dev)))
+    p["w_in"], p["w_in_T"] = ops.pack_conv(f.project_in.weight, co_map=m2, Co_p=2 * hp, dgrad=train)
+    p["b_in"] = ops.gather_vec(f.project_in.bias, m2, 2 * hp)
+    p["w_dw"], p["w_dw_f"], p["b_dw"] = ops.pack_dw(f.dwconv.weight, f.dwconv.bias, c_map=m2, C_p=2 * hp, flip=train)
+    p["w_out"], p["w_out_T"] = ops.pack_conv(f.project_out.weight, ci_map=m1, Ci_p=hp, dgrad=train)
     p["b_out"] = _f(f.project_out.bias)
     p["alpha"] = _f(blk.alpha) if hasattr(blk, "alpha") else None
+    p["train"] = train
     return p
 
 
@@ -204,19 +218,24 @@ class _RestormerBase(nn.Module):
     def _prep_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def prepared(self):
+    def prepared(self, train=False):
+        """Packed kernel operands, rebuilt when a parameter changed.  train=True also builds the data-gradient packs
+        (a cache built for training serves inference too)."""
         key = self._prep_key()
-        if self._prep_cache is None or self._prep_cache[0] != key:
+        c = self._prep_cache
+        if c is None or c[0] != key or (train and not c[2]):
             with torch.no_grad():
-                self._prep_cache = (key, self._prepare())
+                self._prep_train_flag = train
+                self._prep_cache = (key, self._prepare(), train)
         return self._prep_cache[1]
 
     def _prepare_body(self):
         P = {}
+        train = getattr(self, "_prep_train_flag", False)
         for name in ["encoder_level1", "encoder_level2", "encoder_level3", "latent", "decoder_level3",
                      "decoder_level2", "decoder_level1", "refinement"] + \
                     [f"masa_blk_enc_level{i}" for i in range(1, 5) if hasattr(self, f"masa_blk_enc_level{i}")]:
-            P[name] = [_prep_block(b) for b in getattr(self, name)]
+            P[name] = [_prep_block(b, train) for b in getattr(self, name)]
         for name in ["down1_2", "down2_3", "down3_4", "up4_3", "up3_2", "up2_1"]:
             P[name] = _prep_conv(getattr(self, name).body[0])
         for name in ["reduce_chan_level3", "reduce_chan_level2"]:

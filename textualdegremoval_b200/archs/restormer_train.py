@@ -60,30 +60,18 @@ def _flip_T(w):
 def prep_conv_train(conv, pc):
     """Adds the dgrad pack to a ``prep_conv`` dict (stride-1 convs)."""
     if "wT" not in pc:
-        pc["wT"] = ops.pack_conv_weight(_flip_T(conv.weight))
+        pc["wT"] = ops.pack_conv(conv.weight, fwd=False, dgrad=True)[1]
         pc["mod"] = conv
     return pc
 
 
 def prep_block_train(blk, p):
-    """Transposed / flipped packs and channel maps for one transformer block (cached next to the forward packs)."""
-    if "w_qkv_T" in p:
+    """The transposed / flipped packs and channel maps are built by ``_prep_block(blk, train=True)``; blocks prepared for
+    inference only are re-packed here."""
+    if p.get("train"):
         return p
-    a, f = blk.attn, blk.ffn
-    h, hp = p["h"], p["hp"]
-    dev = a.qkv.weight.device
-    idx2 = torch.cat([torch.arange(h, device=dev), hp + torch.arange(h, device=dev)])
-    p["mod"] = blk
-    p["w_qkv_T"] = ops.pack_conv_weight(_flip_T(a.qkv.weight))
-    p["w_qkv_dw_f"] = ops.pack_dw_weight(a.qkv_dwconv.weight.detach().flip(2, 3))
-    p["w_in_T"] = ops.pack_conv_weight(_flip_T(f.project_in.weight), ci_map=(2 * hp, idx2))
-    p["w_dw_f"] = ops.pack_dw_weight(f.dwconv.weight.detach().flip(2, 3), 2 * hp, idx2)
-    p["w_out_T"] = ops.pack_conv_weight(_flip_T(f.project_out.weight), co_map=(hp, torch.arange(h, device=dev)))
-    m2 = torch.full((2 * hp,), -1, dtype=torch.int32, device=dev)
-    m2[idx2] = torch.arange(2 * h, dtype=torch.int32, device=dev)
-    m1 = torch.full((hp,), -1, dtype=torch.int32, device=dev)
-    m1[:h] = torch.arange(h, dtype=torch.int32, device=dev)
-    p["map_2h"], p["map_h"] = m2, m1
+    from .restormer_b200_arch import _prep_block
+    p.update(_prep_block(blk, train=True))
     return p
 
 
@@ -318,7 +306,7 @@ class RestormerTrainMixin:
             raise ValueError(f"Restormer needs H, W multiples of 8 (got {H}x{W})")
         if self.dual_pixel_task:
             raise ops.lib.TdrError("Restormer (B200): training with dual_pixel_task is not implemented")
-        P = self._prep_train(self.prepared())
+        P = self._prep_train(self.prepared(train=True))
         d = self.dims
         dev = inp_img.device
         tape, T = [], dict(hw=(H, W))
@@ -373,7 +361,7 @@ class GuidedRestormerTrainMixin(RestormerTrainMixin):
         self._check(inp_img, ref_img)
         if self.dual_pixel_task:
             raise ops.lib.TdrError("RestormerRefFusion (B200): dual_pixel_task is not implemented")
-        P = self._prep_train(self.prepared())
+        P = self._prep_train(self.prepared(train=True))
         E = self._prep_masa_train(P["masa_enc"])
         d = self.dims
         dev = inp_img.device

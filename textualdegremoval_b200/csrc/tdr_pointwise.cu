@@ -145,6 +145,31 @@ __device__ __forceinline__ f2 gelu2(f2 x) {
   return mul2(mul2(x, pk2(0.5f, 0.5f)), pk2(s0, s1));
 }
 
+// GELU and its derivative on a pair, sharing one erf evaluation: with z = |x|/sqrt2, e = exp(-z^2) = exp(-x^2/2) is both
+// the A&S tail factor and (times 1/sqrt(2 pi)) the normal pdf, so gelu'(x) = Phi(x) + x pdf(x) costs two more FMAs.
+__device__ __forceinline__ void gelu2_grad(f2 x, f2& gelu, f2& dgelu) {
+  float x0, x1;
+  upk2(x, x0, x1);
+  const float z0 = fabsf(x0) * 0.70710678118654752f, z1 = fabsf(x1) * 0.70710678118654752f;
+  const f2 z = pk2(z0, z1);
+  float d0, d1;
+  upk2(fma2(pk2(0.3275911f, 0.3275911f), z, pk2(1.f, 1.f)), d0, d1);
+  const f2 t = pk2(rcp_approx(d0), rcp_approx(d1));
+  f2 p = fma2(t, pk2(1.061405429f, 1.061405429f), pk2(-1.453152027f, -1.453152027f));
+  p = fma2(p, t, pk2(1.421413741f, 1.421413741f));
+  p = fma2(p, t, pk2(-0.284496736f, -0.284496736f));
+  p = fma2(p, t, pk2(0.254829592f, 0.254829592f));
+  p = mul2(p, t);
+  float e0, e1;
+  upk2(mul2(z, mul2(z, pk2(-1.4426950408889634f, -1.4426950408889634f))), e0, e1);
+  const f2 ex = pk2(ex2_approx(e0), ex2_approx(e1));                 // exp(-x^2 / 2)
+  float q0, q1;
+  upk2(mul2(p, ex), q0, q1);                                          // q = 1 - erf(|x|/sqrt2)
+  const f2 cdf = pk2(x0 >= 0.f ? 1.f - 0.5f * q0 : 0.5f * q0, x1 >= 0.f ? 1.f - 0.5f * q1 : 0.5f * q1);
+  gelu = mul2(x, cdf);
+  dgelu = fma2(mul2(x, pk2(0.3989422804014327f, 0.3989422804014327f)), ex, cdf);
+}
+
 template <int VEC>
 struct RawT;
 template <>
@@ -417,28 +442,26 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
             uint32_t* obu = reinterpret_cast<uint32_t*>(&ob);
 #pragma unroll
             for (int e = 0; e < NP; ++e) {
-              float av[2], bv2[2], gv[2], da[2], db[2];
-              upk2(acc[i % 3][0][e], av[0], av[1]);
-              upk2(acc[i % 3][1][e], bv2[0], bv2[1]);
-              upk2(bf2_to_f2(gu[e]), gv[0], gv[1]);
-              if (a.dg_add) {
-                gv[0] += a.dg_add[(long long)b * a.Cout + c0 + 2 * e];
-                gv[1] += a.dg_add[(long long)b * a.Cout + c0 + 2 * e + 1];
+              const f2 av = acc[i % 3][0][e], bvv = acc[i % 3][1][e];
+              f2 gv = bf2_to_f2(gu[e]);
+              if (a.dg_add)
+                gv = fma2(pk2(1.f, 1.f), gv, pk2(a.dg_add[(long long)b * a.Cout + c0 + 2 * e],
+                                                  a.dg_add[(long long)b * a.Cout + c0 + 2 * e + 1]));
+              f2 da, db;
+              if (a.gate == 1) {
+                f2 ga, dga;
+                gelu2_grad(av, ga, dga);
+                da = mul2(mul2(gv, bvv), dga);
+                db = mul2(gv, ga);
+              } else {
+                da = mul2(gv, bvv);
+                db = mul2(gv, av);
               }
-#pragma unroll
-              for (int k = 0; k < 2; ++k) {
-                if (a.gate == 1) {
-                  float ga, dga;
-                  gelu_and_grad_pw(av[k], ga, dga);
-                  da[k] = gv[k] * bv2[k] * dga;
-                  db[k] = gv[k] * ga;
-                } else {
-                  da[k] = gv[k] * bv2[k];
-                  db[k] = gv[k] * av[k];
-                }
-              }
-              oau[e] = pack2(da[0], da[1]);
-              obu[e] = pack2(db[0], db[1]);
+              float t0, t1;
+              upk2(da, t0, t1);
+              oau[e] = pack2(t0, t1);
+              upk2(db, t0, t1);
+              obu[e] = pack2(t0, t1);
             }
             *reinterpret_cast<raw_t*>(outp) = oa;
             *reinterpret_cast<raw_t*>(outp + a.Cout) = ob;
@@ -466,6 +489,70 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
     }
     __syncthreads();                                       // everyone is done with this stage before it is refilled
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------ weight packing
+// nn.Conv2d weight fp32 [Co][Ci][KH][KW] -> bf16 GEMM operand [T][rows][ld] (K contiguous, zero padded), optionally
+// through padded->logical channel maps (GDFN halves) and a per-output-channel scale (NAF gamma fold):
+//   fwd  : out[t][co_p][ci_p]   = scale[co] * w[co][ci][t]
+//   dgrad: out_t[t][ci_p][co_p] = scale[co] * w[co][ci][T-1-t]     (transposed, taps flipped)
+// One launch per parameter replaces the chain of small torch ops that re-packed the weights after every optimizer step.
+__global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ w, int Co, int Ci, int T,
+                                                               const int* __restrict__ co_map, int Co_p,
+                                                               const int* __restrict__ ci_map, int Ci_p,
+                                                               const float* __restrict__ scale, bf16* __restrict__ out,
+                                                               long long ld, bf16* __restrict__ out_t, long long ld_t) {
+  const long long n_f = out ? (long long)T * Co_p * ld : 0;
+  const long long n_t = out_t ? (long long)T * Ci_p * ld_t : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_f + n_t; i += (long long)gridDim.x * blockDim.x) {
+    const bool tr = i >= n_f;
+    long long r = tr ? i - n_f : i;
+    const long long l = tr ? ld_t : ld;
+    const int col = (int)(r % l); r /= l;
+    const int rows = tr ? Ci_p : Co_p;
+    const int row = (int)(r % rows);
+    const int t = (int)(r / rows);
+    const int co_p = tr ? col : row, ci_p = tr ? row : col;
+    float v = 0.f;
+    if (co_p < Co_p && ci_p < Ci_p) {
+      const int co = co_map ? co_map[co_p] : co_p;
+      const int ci = ci_map ? ci_map[ci_p] : ci_p;
+      if (co >= 0 && co < Co && ci >= 0 && ci < Ci) {
+        v = w[((long long)co * Ci + ci) * T + (tr ? T - 1 - t : t)];
+        if (scale) v *= scale[co];
+      }
+    }
+    (tr ? out_t : out)[i - (tr ? n_f : 0)] = __float2bfloat16(v);
+  }
+}
+
+// depthwise weight [C][1][3][3] (+ bias [C]) -> fp32 tap-major [9][C_p] (+ flipped copy for the data gradient, + padded bias)
+__global__ void __launch_bounds__(256) pack_dw_weight_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                             int C, const int* __restrict__ c_map, int C_p,
+                                                             float* __restrict__ out, float* __restrict__ out_flip,
+                                                             float* __restrict__ out_bias) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 10 * C_p) return;
+  const int t = i / C_p, cp = i % C_p;
+  const int c = c_map ? c_map[cp] : cp;
+  const bool ok = c >= 0 && c < C;
+  if (t == 9) {
+    if (out_bias) out_bias[cp] = (ok && bias) ? bias[c] : 0.f;
+    return;
+  }
+  const float v = ok ? w[(long long)c * 9 + t] : 0.f;
+  if (out) out[(long long)t * C_p + cp] = v;
+  if (out_flip) out_flip[(long long)(8 - t) * C_p + cp] = v;
+}
+
+// out[i] = map[i] >= 0 ? v[map[i]] : 0   (padded bias vectors)
+__global__ void gather_vec_kernel(const float* __restrict__ v, const int* __restrict__ map, int n, int n_src,
+                                  float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int j = map ? map[i] : i;
+  out[i] = (j >= 0 && j < n_src) ? v[j] : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ layout
@@ -995,6 +1082,36 @@ extern "C" int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long lo
   sca_fold_kernel<<<g2, 256, 2 * C * sizeof(float), stream>>>(workspace, chunks, P, C, w_sca, b_sca, w3, Co, rowscale,
                                                               reinterpret_cast<bf16*>(weff_bf16), weff_ld, mean_out, s_out,
                                                               reinterpret_cast<bf16*>(weff_t_bf16), weff_t_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_pack_conv_weight(const float* w, int Co, int Ci, int KH, int KW, const int* co_map, int Co_p,
+                                    const int* ci_map, int Ci_p, const float* scale, void* out_bf16, long long ld,
+                                    void* out_t_bf16, long long ld_t, cudaStream_t stream) {
+  TDR_CHECK_ARG(w && (out_bf16 || out_t_bf16) && Co > 0 && Ci > 0 && KH > 0 && KW > 0 && Co_p > 0 && Ci_p > 0,
+                "tdr_pack_conv_weight: bad arguments");
+  TDR_CHECK_ARG((!out_bf16 || ld >= Ci_p) && (!out_t_bf16 || ld_t >= Co_p), "tdr_pack_conv_weight: row stride too small");
+  const int T = KH * KW;
+  const long long n = (out_bf16 ? (long long)T * Co_p * ld : 0) + (out_t_bf16 ? (long long)T * Ci_p * ld_t : 0);
+  pack_conv_weight_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(w, Co, Ci, T, co_map, Co_p, ci_map, Ci_p, scale,
+                                                                    reinterpret_cast<bf16*>(out_bf16), ld,
+                                                                    reinterpret_cast<bf16*>(out_t_bf16), ld_t);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_pack_dw_weight(const float* w, const float* bias, int C, const int* c_map, int C_p, float* out,
+                                  float* out_flip, float* out_bias, cudaStream_t stream) {
+  TDR_CHECK_ARG(w && C > 0 && C_p > 0 && (out || out_flip || out_bias), "tdr_pack_dw_weight: bad arguments");
+  pack_dw_weight_kernel<<<tdr_cdiv(10 * C_p, 256), 256, 0, stream>>>(w, bias, C, c_map, C_p, out, out_flip, out_bias);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_gather_vec(const float* v, const int* map, int n, int n_src, float* out, cudaStream_t stream) {
+  TDR_CHECK_ARG(v && out && n > 0 && n_src > 0, "tdr_gather_vec: bad arguments");
+  gather_vec_kernel<<<tdr_cdiv(n, 256), 256, 0, stream>>>(v, map, n, n_src, out);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -48,6 +48,7 @@ class FlatGroup:
         self.n_params = sum(p.numel() for p in self.params)
         self.flat = torch.zeros(max(n, 4), dtype=F32, device=dev)
         self.grad = torch.zeros(max(n, 4), dtype=F32, device=dev)
+        self.offsets = offs
         for p, off in zip(self.params, offs):
             k = p.numel()
             self.flat[off:off + k].copy_(p.detach().reshape(-1))
@@ -55,6 +56,10 @@ class FlatGroup:
             p.grad = self.grad[off:off + k].view_as(p)
         self.m = torch.zeros_like(self.flat)
         self.v = torch.zeros_like(self.flat)
+
+    def views(self, flat):
+        """Per-parameter views of a flat buffer laid out like ``self.flat`` (e.g. the EMA copy)."""
+        return [flat[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)]
 
 
 def split_param_groups(named_params, lr, ref_lr):

@@ -117,6 +117,9 @@ SIGNATURES.update({
     "tdr_scale_add_f32": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _f, _vp, _ll, _vp]),
     "tdr_dot_f32": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _i, _vp, _vp]),
     "tdr_pixel_shuffle_nhwc": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
+    "tdr_pack_conv_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _ll, _vp, _ll, _vp]),
+    "tdr_pack_dw_weight": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
+    "tdr_gather_vec": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "tdr_relu_mask": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _ll, _vp]),
     "tdr_masa_transfer_bwd": (_i, [_vp, _ll, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "tdr_masa_fine_bwd": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),

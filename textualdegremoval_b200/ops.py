@@ -76,12 +76,35 @@ def round_up(x: int, m: int) -> int:
 
 
 # ---------------------------------------------------------------------------------------------- weight packing
+def _f32c(t):
+    t = t.detach()
+    return t if (t.dtype == F32 and t.is_contiguous()) else t.float().contiguous()
+
+
+def pack_conv(w, co_map=None, Co_p=None, ci_map=None, Ci_p=None, scale=None, fwd=True, dgrad=False):
+    """nn.Conv2d weight [Co, Ci, kh, kw] -> (bf16 [T, Co_p, ld], bf16 [T, Ci_p, ld_t]): the tdr_conv_gemm operand and its
+    transposed, tap-flipped twin (data gradient), each in ONE kernel launch.  co_map / ci_map: int32 DEVICE tensors mapping
+    padded channel -> logical channel (-1 = zero); scale: fp32 [Co] folded into the output channels."""
+    w = _f32c(w)
+    co, ci, kh, kw = w.shape
+    Co_p = co if Co_p is None else Co_p
+    Ci_p = ci if Ci_p is None else Ci_p
+    ld, ld_t = round_up(Ci_p, 8), round_up(Co_p, 8)
+    out = torch.empty((kh * kw, Co_p, ld), dtype=BF16, device=w.device) if fwd else None
+    out_t = torch.empty((kh * kw, Ci_p, ld_t), dtype=BF16, device=w.device) if dgrad else None
+    lib.call("tdr_pack_conv_weight", _p(w), co, ci, kh, kw, _p(co_map), Co_p, _p(ci_map), Ci_p, _p(scale), _p(out), ld,
+             _p(out_t), ld_t, _stream())
+    return out, out_t
+
+
 def pack_conv_weight(w: torch.Tensor, ci_map=None, co_map=None) -> torch.Tensor:
     """[Co, Ci, kh, kw] fp32 -> bf16 [kh*kw, Co, Ci_p] (tap-major, K contiguous, Ci padded to 8) for tdr_conv_gemm.
     Rows are NOT padded: the kernel's TMA box zero-fills beyond Co.
 
     ci_map / co_map: optional (n_padded, index tensor) placing logical channels at padded positions (GDFN halves).
     """
+    if ci_map is None and co_map is None and w.dim() == 4 and w.is_cuda:
+        return pack_conv(w)[0]
     co, ci, kh, kw = w.shape
     wt = w.detach().permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
     if ci_map is not None:
@@ -97,6 +120,29 @@ def pack_conv_weight(w: torch.Tensor, ci_map=None, co_map=None) -> torch.Tensor:
     cip = round_up(wt.shape[2], 8)
     out = torch.zeros(kh * kw, wt.shape[1], cip, dtype=BF16, device=w.device)
     out[:, :, : wt.shape[2]] = wt.to(BF16)
+    return out
+
+
+def pack_dw(w, bias=None, c_map=None, C_p=None, flip=False):
+    """Depthwise weight [C,1,3,3] (+bias) -> (fp32 [9, C_p], flipped twin or None, padded bias or None), one launch."""
+    w = _f32c(w)
+    c = w.shape[0]
+    C_p = c if C_p is None else C_p
+    out = torch.empty((9, C_p), dtype=F32, device=w.device)
+    out_f = torch.empty((9, C_p), dtype=F32, device=w.device) if flip else None
+    out_b = torch.empty(C_p, dtype=F32, device=w.device) if bias is not None else None
+    lib.call("tdr_pack_dw_weight", _p(w), _p(_f32c(bias)) if bias is not None else None, c, _p(c_map), C_p, _p(out),
+             _p(out_f), _p(out_b), _stream())
+    return out, out_f, out_b
+
+
+def gather_vec(v, cmap, n):
+    """out[i] = v[cmap[i]] (0 where cmap[i] < 0): padded bias vectors."""
+    if v is None:
+        return None
+    v = _f32c(v).reshape(-1)
+    out = torch.empty(n, dtype=F32, device=v.device)
+    lib.call("tdr_gather_vec", _p(v), _p(cmap), n, v.numel(), _p(out), _stream())
     return out
 
 
