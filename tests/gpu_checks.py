@@ -729,6 +729,18 @@ def check_bwd_pointwise():
         dyo = torch.empty(2, 6, 5, 272, device=DEV, dtype=BF16)
         ops.gate_bwd(yv.detach().to(BF16).to(DEV), dg.to(BF16).to(DEV), gate, out=dyo)
         out.append(grad_result(f"gate_bwd_g{gate}", dyo, ry, 8e-3))
+    # fused recompute + gate backward (tdr_dwconv3x3_gate_bwd) == dwconv(gate 0) followed by gate_bwd
+    for gate in (1, 2):
+        hx = q(rnd(2, 6, 9, 272, seed=21))
+        w9 = (rnd(9, 272, seed=22) * 0.3).to(DEV)
+        b9 = (rnd(272, seed=23) * 0.1).to(DEV)
+        dgv = q(rnd(2, 6, 9, 136, seed=24))
+        add = rnd(2, 136, seed=25).to(DEV) if gate == 2 else None
+        hx_d, dg_d = hx.to(BF16).to(DEV), dgv.to(BF16).to(DEV)
+        ysep = ops.dwconv3x3(hx_d, w9, b9, gate=0)
+        ref_dy = ops.gate_bwd(ysep.clone(), dg_d, gate, dg_add=add)
+        fused = ops.dwconv3x3_gate_bwd(hx_d, w9, b9, gate, dg_d, dg_add=add)
+        out.append(grad_result(f"dwconv_gate_bwd_fused_g{gate}", fused, ref_dy, 1e-2))
     # scale_add / dot / pixel shuffle / relu mask
     xs, ys = rnd(2, 4, 4, 96, seed=11), rnd(2, 4, 4, 96, seed=12)
     al = torch.tensor([0.37], device=DEV)

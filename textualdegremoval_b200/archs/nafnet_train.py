@@ -85,7 +85,8 @@ def run_naf_block_bwd(dout, sv, G):
     dg_add = ops.naf_sca_bwd(raw3, p["w3"], p["beta"], sv["mean"], p["w_sca"], H * W, G(blk.sca[1].weight),
                              G(blk.sca[1].bias))
     _, dg = ops.conv_gemm(dy16, sv["weff_t"], dw // 2, Ci=c, w_batched=True)
-    dyd = ops.dwconv3x3_gate_bwd(t1, p["w2"], p["b2"], 2, dg, dg_add=dg_add)
+    ydw = ops.dwconv3x3(t1, p["w2"], p["b2"], gate=0)
+    dyd = ops.gate_bwd(ydw, dg, 2, dg_add=dg_add)
     ops.dwconv3x3_wgrad(dyd, t1, G(blk.conv2.weight), G(blk.conv2.bias))
     dt1 = ops.dwconv3x3(dyd, p["w2_f"], None)
     xn1 = ops.rownorm(x0, 1, p["n1_w"], p["n1_b"], p["eps"])

@@ -122,7 +122,10 @@ def run_block_bwd(dout, sv, G, dout16=None, want16=False):
     ops.wgrad(d2_16, g, G(f.project_out.weight), ci_map=p["map_h"])
     if f.project_out.bias is not None:
         ops.colsum(d2_16, G(f.project_out.bias))
-    dy = ops.dwconv3x3_gate_bwd(hid, p["w_dw"], p["b_dw"], 1, dg)
+    # recompute the pre-gate tensor with the (85 % of HBM) ungated kernel, then the pointwise gate backward: measured
+    # faster than the fused tdr_dwconv3x3_gate_bwd, which inherits the gated kernel's 32-channel tiling (52 % of HBM)
+    y = ops.dwconv3x3(hid, p["w_dw"], p["b_dw"], gate=0)
+    dy = ops.gate_bwd(y, dg, 1)
     ops.dwconv3x3_wgrad(dy, hid, G(f.dwconv.weight), G(f.dwconv.bias), c_map=p["map_2h"])
     dhid = ops.dwconv3x3(dy, p["w_dw_f"], None)
     xn2 = ops.rownorm(x1, mode, p["ln2_w"], p["ln2_b"], 1e-5)
