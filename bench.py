@@ -340,8 +340,20 @@ def _run_b200(args, out):
         roof = dict(bound="hbm", achieved=hbm_gbs, peak=pk["hbm"], unit="GB/s", frac=hbm_frac)
     else:
         roof = dict(bound="tensor", achieved=tflops, peak=pk["tf_sust"], unit="TFLOP/s", frac=tc_frac)
+    # measured DRAM traffic per launch of that kernel family: one ncu pass over a steady-state step of this same
+    # workload (dram__bytes_read.sum + dram__bytes_write.sum), committed under profiles/ -- not re-measured here
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as fh:
+            tj = json.load(fh)
+        if tj.get("workload") == f"{S}x{S}_b{B}" and top in tj["families"]:
+            traffic = tj["families"][top]["dram_bytes_per_launch"]
+            traffic_src = tj["source"]
+    except Exception:  # noqa: BLE001
+        pass
     roof.update(kernel=top, launches_per_step=ft["n"], avg_launch_ms=ft["ms"] / ft["n"],
-                share_of_step=ft["ms"] / total_prof, traffic=None, peak_source=pk["src"],
+                share_of_step=ft["ms"] / total_prof, traffic=traffic, traffic_unit="bytes/launch (DRAM read+write, ncu)",
+                traffic_source=traffic_src, algorithmic_bytes_per_launch=ft["bytes"] / ft["n"], peak_source=pk["src"],
                 families={k: dict(ms=round(v["ms"], 3), n=v["n"], GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
                                   TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)) for k, v in fam.items()})
     imgs = B * world * args.steps
