@@ -192,7 +192,7 @@ def test_oracle_autograd_matches_reference_gradients(name):
         y = O.restormer_forward(sdg, x, meta["cfg"]["heads"])
     loss = (y - gt).abs().mean()
     loss.backward()
-    assert abs(float(loss) - float(z["loss"])) < 1e-6
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-6
     total = float(np.sqrt((z["norms"] ** 2).sum()))
     for n, norm, probe in zip(z["names"].tolist(), z["norms"].tolist(), z["probes"].tolist()):
         g = sdg[n].grad if sdg[n].grad is not None else torch.zeros_like(sdg[n])

@@ -113,10 +113,6 @@ class MasaMixin:
 
 
 # =============================================================================================== training (tape + backward)
-def _flip_T(w):
-    return w.detach().permute(1, 0, 2, 3).flip(2, 3)
-
-
 class MasaTrainMixin:
     """Training forward (keeps every activation of the feature encoder and the match aux tensors) and explicit backward
     of the MASA guidance path.  The matches (coarse / fine arg-max) are constants; gradients flow through the gathered

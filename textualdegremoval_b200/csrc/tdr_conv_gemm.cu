@@ -676,6 +676,9 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     bool ok = d->impl == 0 && d->store_mode == 0 && one_out && ((uintptr_t)optr & 15) == 0 && old_ % per16 == 0;
     if (ok && d->res2) ok = (d->res2_bf16 != 0) == !f32o && ((uintptr_t)d->res2 & 15) == 0 && d->res2_ld % per16 == 0;
     if (ok && d->res1) ok = f32o && d->res2 && ((uintptr_t)d->res1 & 15) == 0 && d->res1_ld % 4 == 0;
+    if (const char* e = getenv("TDR_CONV_EPI")) {                                // tuning knob (experiments only)
+      if (atoi(e) == 0) ok = false;
+    }
     a.epi_mode = ok ? 1 : 0;
     a.out_is_f32 = f32o ? 1 : 0;
   }

@@ -322,13 +322,6 @@ struct DwArgs {
   const float* dg_add;     // optional per-sample term [B][Cout] added to dg (SCA pool gradient)
 };
 
-__device__ __forceinline__ void gelu_and_grad_pw(float a, float& g, float& dg) {
-  const float cdf = 0.5f * (1.f + erff(a * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * a * a);
-  g = a * cdf;
-  dg = cdf + a * pdf;
-}
-
 // GATE: 0 plain, 1 gated forward (a.gate 1 = GELU gate, 2 = SimpleGate), 2 gate BACKWARD: recomputes the two depthwise
 // halves (a | b) exactly as the forward does and writes d[a | b] = [dg * b * act'(a) | dg * act(a)] (2 * Cout channels),
 // i.e. tdr_dwconv3x3(gate 0) + tdr_gate_bwd without the round trip of the pre-gate tensor through HBM.

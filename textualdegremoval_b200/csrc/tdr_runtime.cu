@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <stdarg.h>
 #include <stddef.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "tdr_common.cuh"
@@ -95,10 +96,18 @@ static int make_map(TdrTensorMap* out, CUtensorMapDataType dt, const void* base,
     es[i] = elem_strides[i];
     if (i + 1 < rank) gstr[i] = strides_bytes[i];
   }
+  CUtensorMapL2promotion promo =
+      sw == CU_TENSOR_MAP_SWIZZLE_NONE ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  static const char* promo_env = getenv("TDR_TMA_L2PROMO");                    // tuning knob (experiments only)
+  if (promo_env && sw != CU_TENSOR_MAP_SWIZZLE_NONE) {
+    const int v = atoi(promo_env);
+    promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                   : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                              : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+  }
   CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), dt, (cuuint32_t)rank,
                    const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   sw, sw == CU_TENSOR_MAP_SWIZZLE_NONE ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   sw, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     tdr_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu] stride0 %llu box [%u %u %u %u]",
                   (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
