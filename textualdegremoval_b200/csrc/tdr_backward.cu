@@ -31,7 +31,13 @@ struct WgradPlan {
   int BM, BN, m_tiles, n_tiles, boxes_m, boxes_n, stages;
   int nb, nchunks, tiles_per_chunk, tiles_total;
   uint32_t tmem_cols;
+  int fused;          // 1: 3x3 stride-1 conv with Ci <= 48: ONE CTA accumulates all 9 taps (9 x BN TMEM columns) from
+                      //    one dy tile and three kx-shifted haloed x tiles [18 rows x 8 px]; a ky shift is 1024 B = one
+                      //    swizzle atom, so the taps are descriptor offsets (dy / x are fetched 1 + 3.4 times, not 9 + 9)
+  int stage_bytes;
 };
+
+constexpr int kHaloXBytes = 18 * 8 * 128;      // fused mode: one kx-shifted x tile, [18 rows][8 px][64 ch]
 
 struct WgradArgs {
   int Co, Ci, KW, stride, pad, dil, per_sample;
@@ -56,20 +62,28 @@ static int wgrad_plan(const tdr_wgrad_desc* d, WgradPlan* p) {
   p->n_tiles = tdr_cdiv(ci16, 256);
   p->BN = tdr_cdiv(tdr_cdiv(ci16, p->n_tiles), 16) * 16;
   p->boxes_n = tdr_cdiv(p->BN, 64);
-  const int stage_bytes = (p->boxes_m + p->boxes_n) * kBoxBytes;
-  p->stages = (220 * 1024) / stage_bytes;
+  p->fused = (d->KH == 3 && d->KW == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && !d->per_sample && p->OH > 1 &&
+              9 * p->BN <= 512 && p->n_tiles == 1 && getenv("TDR_WGRAD_NO_FUSE") == nullptr)
+                 ? 1 : 0;
+  if (p->fused) {
+    p->TW = 8; p->TH = 16;
+    p->tiles_x = tdr_cdiv(p->OW, p->TW);
+    p->tiles_y = tdr_cdiv(p->OH, p->TH);
+  }
+  p->stage_bytes = p->fused ? p->boxes_m * kBoxBytes + 3 * kHaloXBytes : (p->boxes_m + p->boxes_n) * kBoxBytes;
+  p->stages = (220 * 1024) / p->stage_bytes;
   if (p->stages > 4) p->stages = 4;
   if (p->stages < 2) return -1;
   p->nb = d->per_sample ? d->B : 1;
   p->tiles_total = (d->per_sample ? 1 : d->B) * p->tiles_y * p->tiles_x;
-  const int outer = p->T * p->m_tiles * p->n_tiles * p->nb;
+  const int outer = (p->fused ? 1 : p->T) * p->m_tiles * p->n_tiles * p->nb;
   int want = tdr_num_sms() / outer;          // one wave of CTAs (1 CTA / SM: the smem ring fills the SM)
   if (want < 1) want = 1;
   if (want > p->tiles_total) want = p->tiles_total;
   p->tiles_per_chunk = tdr_cdiv(p->tiles_total, want);
   p->nchunks = tdr_cdiv(p->tiles_total, p->tiles_per_chunk);
   uint32_t cols = 32;
-  while (cols < (uint32_t)p->BN) cols <<= 1;
+  while (cols < (uint32_t)(p->fused ? 9 * p->BN : p->BN)) cols <<= 1;
   p->tmem_cols = cols;
   return 0;
 }
@@ -80,7 +94,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const WgradPlan& pl = a.plan;
-  const int stage_bytes = (pl.boxes_m + pl.boxes_n) * kBoxBytes;   // dy boxes then x boxes
+  const int stage_bytes = pl.stage_bytes;                          // dy boxes then x boxes
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + pl.stages;
@@ -94,7 +108,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
   int yy = blockIdx.x;
   const int nt = yy % pl.n_tiles; yy /= pl.n_tiles;
   const int mt = yy % pl.m_tiles;
-  const int tap = yy / pl.m_tiles;
+  const int tap = yy / pl.m_tiles;                                 // 0 in fused mode (all taps in this CTA)
   const int ky = tap / a.KW, kx = tap % a.KW;
   const int tile0 = chunk * pl.tiles_per_chunk;
   int ntiles = pl.tiles_total - tile0;
@@ -130,6 +144,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
         uint8_t* base = smem + stage * stage_bytes;
         for (int j = 0; j < pl.boxes_m; ++j)
           tma_load_4d(base + j * kBoxBytes, &map_dy, &full[stage], mt * pl.BM + 64 * j, tx * pl.TW, ty * pl.TH, b);
+        if (pl.fused) {                                            // three kx-shifted haloed x tiles (map_x box = 8 x 18)
+          for (int k3 = 0; k3 < 3; ++k3)
+            tma_load_4d(base + pl.boxes_m * kBoxBytes + k3 * kHaloXBytes, &map_x, &full[stage], 0, tx * pl.TW + k3 - 1,
+                        ty * pl.TH - 1, b);
+          if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+          continue;
+        }
         const int x0 = tx * pl.TW * a.stride + kx * a.dil - a.pad;
         const int y0 = ty * pl.TH * a.stride + ky * a.dil - a.pad;
         for (int j = 0; j < pl.boxes_n; ++j)
@@ -147,12 +168,25 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
       if (lane == 0) {
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint32_t sb = sa + pl.boxes_m * kBoxBytes;
+        if (pl.fused) {
+          for (int tp = 0; tp < 9; ++tp) {
+            // tap (ky, kx): x tile kx, shifted down by ky image rows = ky * 8 px * 128 B (one swizzle atom)
+            const uint32_t sx = sb + (tp % 3) * kHaloXBytes + (tp / 3) * 1024;
 #pragma unroll
-        for (int ks = 0; ks < kPixTile / 16; ++ks) {
-          // 16 pixels (K) = two 8-row swizzle atoms of 1024 B; 64-channel chunks are kBoxBytes apart (LBO)
-          const uint64_t da = umma_desc_sw128(sa + ks * 2048, kBoxBytes, 1024);
-          const uint64_t db = umma_desc_sw128(sb + ks * 2048, kBoxBytes, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (t | ks) != 0);
+            for (int ks = 0; ks < kPixTile / 16; ++ks) {
+              const uint64_t da = umma_desc_sw128(sa + ks * 2048, kBoxBytes, 1024);
+              const uint64_t db = umma_desc_sw128(sx + ks * 2048, kBoxBytes, 1024);
+              umma_bf16(tmem_base + tp * pl.BN, da, db, idesc, (t | ks) != 0);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < kPixTile / 16; ++ks) {
+            // 16 pixels (K) = two 8-row swizzle atoms of 1024 B; 64-channel chunks are kBoxBytes apart (LBO)
+            const uint64_t da = umma_desc_sw128(sa + ks * 2048, kBoxBytes, 1024);
+            const uint64_t db = umma_desc_sw128(sb + ks * 2048, kBoxBytes, 1024);
+            umma_bf16(tmem_base, da, db, idesc, (t | ks) != 0);
+          }
         }
         umma_commit(&empty[stage]);
         if (t == ntiles - 1) umma_commit(tfull);
@@ -167,19 +201,22 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
     const int row = pl.BM == 128 ? quad * 32 + lane : quad * 16 + lane;
     const int co = mt * pl.BM + row;
     const bool row_ok = (pl.BM == 128 || lane < 16) && co < a.Co;
-    float* out = a.partials + ((((size_t)bz * pl.nchunks + chunk) * pl.T + tap) * a.Co + co) * (size_t)a.Ci;
     mbar_wait(tfull, 0);
     tc_fence_after();
     const uint32_t t_lane = tmem_base + ((uint32_t)(quad * 32) << 16);
-    for (int c16 = 0; c16 < pl.BN / 16; ++c16) {
-      uint32_t g[16];
-      tmem_ld16(t_lane + c16 * 16, g);
-      tmem_ld_wait();
-      if (row_ok) {
+    const int ntap = pl.fused ? 9 : 1;
+    for (int tp = 0; tp < ntap; ++tp) {
+      float* out = a.partials + ((((size_t)bz * pl.nchunks + chunk) * pl.T + tap + tp) * a.Co + co) * (size_t)a.Ci;
+      for (int c16 = 0; c16 < pl.BN / 16; ++c16) {
+        uint32_t g[16];
+        tmem_ld16(t_lane + tp * pl.BN + c16 * 16, g);
+        tmem_ld_wait();
+        if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int ci = nt * pl.BN + c16 * 16 + i;
-          if (ci < a.Ci) out[ci] = __uint_as_float(g[i]);
+          for (int i = 0; i < 16; ++i) {
+            const int ci = nt * pl.BN + c16 * 16 + i;
+            if (ci < a.Ci) out[ci] = __uint_as_float(g[i]);
+          }
         }
       }
     }
@@ -1006,19 +1043,20 @@ extern "C" int tdr_wgrad(const tdr_wgrad_desc* d, cudaStream_t stream) {
   {
     const uint64_t dims[4] = {(uint64_t)d->Ci, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     const uint64_t strides[3] = {(uint64_t)d->x_ld * 2, (uint64_t)d->x_ld * 2 * d->W, (uint64_t)d->x_ld * 2 * d->W * d->H};
-    const uint32_t box[4] = {64, (uint32_t)(p.TW * d->stride), (uint32_t)(p.TH * d->stride), 1};
+    uint32_t box[4] = {64, (uint32_t)(p.TW * d->stride), (uint32_t)(p.TH * d->stride), 1};
+    if (p.fused) { box[1] = 8; box[2] = 18; }                  // haloed rows, one kx shift per load
     const uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
     TDR_CHECK_ARG(box[1] <= 256 && box[2] <= 256, "tdr_wgrad: TMA box too large");
     int rc = tdr_make_tensor_map_bf16(&map_x, d->x, 4, dims, strides, box, es);
     if (rc) return rc;
   }
-  const size_t smem = 1024 + (size_t)p.stages * (p.boxes_m + p.boxes_n) * kBoxBytes + 256;
+  const size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + 256;
   static bool attr_set = false;
   if (!attr_set) {
     TDR_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  dim3 grid(p.T * p.m_tiles * p.n_tiles, p.nchunks, p.nb);
+  dim3 grid((p.fused ? 1 : p.T) * p.m_tiles * p.n_tiles, p.nchunks, p.nb);
   wgrad_kernel<<<grid, 192, smem, stream>>>(map_dy, map_x, a);
   TDR_CHECK_LAUNCH();
   const long long total = (long long)p.nb * p.T * d->Co * d->Ci;

@@ -181,17 +181,32 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
   const float* base = partials + (size_t)(b * heads + h) * nchunks * psz;
   float g[4] = {0.f, 0.f, 0.f, 0.f}, nk[4] = {0.f, 0.f, 0.f, 0.f};
   float nq = 0.f;
-  for (int ch = 0; ch < nchunks; ++ch) {
-    const float* p = base + (size_t)ch * psz;
+  // the chunk loop is a chain of dependent L2 round trips unless several chunks are in flight: 8 at a time (the
+  // summation ORDER stays chunk 0, 1, 2, ... so the result is still deterministic)
+  for (int ch0 = 0; ch0 < nchunks; ch0 += 8) {
+    float tg[8][4], tk[8][4], tq[8];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int j = lane + 32 * t;
-      if (j < c) {
-        g[t] += p[i * c + j];
-        nk[t] += p[c * c + c + j];
+    for (int u = 0; u < 8; ++u) {
+      const bool in = ch0 + u < nchunks;
+      const float* p = base + (size_t)(in ? ch0 + u : 0) * psz;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = lane + 32 * t;
+        const bool ok = in && j < c;
+        tg[u][t] = ok ? p[i * c + j] : 0.f;
+        tk[u][t] = ok ? p[c * c + c + j] : 0.f;
       }
+      tq[u] = in ? p[c * c + i] : 0.f;
     }
-    nq += p[c * c + i];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        g[t] += tg[u][t];
+        nk[t] += tk[u][t];
+      }
+      nq += tq[u];
+    }
   }
   const float nqi = fmaxf(sqrtf(fmaxf(nq, 0.f)), 1e-12f);
   const float temp = temperature[h];
@@ -244,7 +259,8 @@ __global__ void __launch_bounds__(256) mdta_fold_kernel(const float* __restrict_
   float* a = sm;                   // [c][c]
   float* wsm = sm + c * c;         // [32][c]
   const float* src = attn + (size_t)(b * heads + h) * c * c;
-  for (int t = threadIdx.x; t < c * c; t += blockDim.x) a[t] = src[t];
+  for (int t = threadIdx.x; t < (c * c) >> 2; t += blockDim.x)          // c % 8 == 0: float4 staging
+    reinterpret_cast<float4*>(a)[t] = reinterpret_cast<const float4*>(src)[t];
   for (int t = threadIdx.x; t < 32 * c; t += blockDim.x) {
     const int co = co0 + t / c;
     wsm[t] = co < C ? w_out[(size_t)co * C + h * c + t % c] : 0.f;
