@@ -301,6 +301,21 @@ def _run_b200(args, out):
             tprof = ops.PROF.stop()
         train = dict(ms=ms_train, launches=train_launches, loss=loss_val,
                      peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
+        # the reference's step also selects the reference crop with a frozen DINOv2 ViT-B/14 every iteration
+        # (image_restoration_ref_model.py:215-247); with a 512x512 reference there is one candidate (N = 1), the two
+        # 518x518 ViT forwards per sample are executed all the same
+        try:
+            from textualdegremoval_b200.archs.vit_b200 import vit_base
+            ext = vit_base(img_size=518, patch_size=14, init_values=1.0, ffn_layer="mlp", block_chunks=0).to(dev).eval()
+            tr.net_ext = ext
+            tr.feed_train_data(dict(lq=lq_h, gt=gt_h, ref=ref_h))
+            tr.optimize_parameters()
+            barrier()
+            train["ms_dino"] = timed(lambda: tr.optimize_parameters(), 2) / 2
+            barrier()
+        except Exception as e:  # noqa: BLE001
+            train["ms_dino"] = None
+            train["dino_error"] = f"{type(e).__name__}: {e}"[:200]
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e, train["ms"] if train else 0.0], device=dev, dtype=torch.float64)
@@ -383,6 +398,7 @@ def _run_b200(args, out):
             "value": B * world * tsteps / (train["ms"] * 1e-3), "unit": "img/s", "ms_per_step": train["ms"] / tsteps,
             "steps": tsteps, "gpu_launches": train["launches"], "loss": train["loss"],
             "peak_mem_gb": round(train["peak_mem_gb"], 2),
+            "ms_per_step_with_dino_select": train.get("ms_dino"),
             "model_tflops_achieved": 3 * FWD_GFLOP_PER_IMG * B * tsteps / (train["ms"] * 1e-3) / 1e3}
         if tprof is not None:
             tags = {}

@@ -950,6 +950,31 @@ def check_train_step():
         cos = (a @ b / (a.norm() * b.norm())).item()
         out.append(dict(name=f"train_step_update_cos_{grp}", max_err=1 - cos, tol=0.05, ok=bool(cos > 0.95),
                         note=f"|dp| ours {a.norm().item():.4e} ref {b.norm().item():.4e}"))
+    # fix_iterations: the masa group is frozen (no update, excluded from the clipped norm)
+    before = {n: p.detach().clone() for n, p in net.named_parameters()}
+    tr.fix_iterations = 10
+    tr.optimize_parameters(3)
+    tr.fix_iterations = None
+    moved_masa = max((p.detach() - before[n]).abs().max().item() for n, p in net.named_parameters() if "masa" in n)
+    moved_body = max((p.detach() - before[n]).abs().max().item() for n, p in net.named_parameters() if "masa" not in n)
+    out.append(dict(name="fix_iterations_freezes_masa", ok=bool(moved_masa == 0.0 and moved_body > 0.0), max_err=moved_masa,
+                    tol=0.0, note=f"body moved {moved_body:.2e}"))
+    # DINO reference-crop selection inside the step (full reference image in the batch, image_restoration_ref_model.py:215-247)
+    from textualdegremoval_b200.archs import vit_b200 as VB
+    ext = VB.DinoVisionTransformer(img_size=70, patch_size=14, embed_dim=64, depth=2, num_heads=4, mlp_ratio=4,
+                                   init_values=1.0, ffn_layer="mlp", block_chunks=0)
+    Wt.load_seeded(ext, 7)
+    ext = ext.to(DEV).eval()
+    tr.net_ext = ext
+    big = torch.cat([rf, torch.roll(rf, 17, 3)], 3)                     # [B,3,128,256]: N = 1 x 5 candidate crops
+    tr.feed_train_data(dict(lq=lq, gt=gt, ref=big))
+    tr.optimize_parameters(4)
+    sel, idx, cos = VB.select_reference_crop(ext, lq.to(DEV), big.to(DEV))
+    out.append(result("dino_selected_ref_in", tr.ref_in, sel, 0.0, note=f"selected crops {idx.tolist()}"))
+    l_sel = tr.current_loss()
+    out.append(dict(name="train_step_with_dino_select_finite", ok=bool(np.isfinite(l_sel)), max_err=l_sel, tol=None))
+    tr.net_ext = None
+    tr.feed_train_data(dict(lq=lq, gt=gt, ref_in=rf))
     # plain autograd route (loss.backward() on the module output) still works with the flat grads in place
     y = net(lq.to(DEV), rf.to(DEV))
     tr.engine.zero_grad()

@@ -39,6 +39,7 @@ class FlatGroup:
     def __init__(self, params, lr):
         self.params = list(params)
         self.lr = lr
+        self.tag = "normal"
         offs, n = [], 0
         for p in self.params:
             offs.append(n)
@@ -67,7 +68,13 @@ def split_param_groups(named_params, lr, ref_lr):
     normal, ref = [], []
     for name, p in named_params:
         (ref if "masa" in name else normal).append(p)
-    return [g for g in (FlatGroup(normal, lr) if normal else None, FlatGroup(ref, ref_lr) if ref else None) if g]
+    groups = []
+    for tag, ps, rate in (("normal", normal, lr), ("ref", ref, ref_lr)):
+        if ps:
+            g = FlatGroup(ps, rate)
+            g.tag = tag
+            groups.append(g)
+    return groups
 
 
 class DDPStep:
@@ -112,7 +119,10 @@ class DDPStep:
         return works
 
     # ---- optimizer tail ------------------------------------------------------------------------------------------
-    def step(self, works=()):
+    def step(self, works=(), frozen=()):
+        """frozen: indices of groups whose parameters are not updated this step (the reference's ``fix_iterations``
+        warm-up sets requires_grad=False on the ``masa`` parameters, image_restoration_ref_model.py:203-209: they then
+        take no part in the clipped norm and receive no update)."""
         for w in works:
             w.wait()                      # stream-level wait on NCCL; does not block the host for CUDA tensors
         self.step_count += 1
@@ -122,13 +132,17 @@ class DDPStep:
         clip_ptr = None
         if self.use_grad_clip:
             nb = lib.load().tdr_sumsq_partial_count()
-            for gi, g in enumerate(self.groups):
+            active = [gi for gi in range(len(self.groups)) if gi not in frozen]
+            for k, gi in enumerate(active):
+                g = self.groups[gi]
                 lib.call("tdr_sumsq_partial", C.c_void_p(g.grad.data_ptr()), g.n,
-                         C.c_void_p(self._partials.data_ptr() + gi * nb * 4), _stream())
-            lib.call("tdr_clip_coef", C.c_void_p(self._partials.data_ptr()), nb * len(self.groups), self.max_grad_norm,
+                         C.c_void_p(self._partials.data_ptr() + k * nb * 4), _stream())
+            lib.call("tdr_clip_coef", C.c_void_p(self._partials.data_ptr()), nb * len(active), self.max_grad_norm,
                      scale, C.c_void_p(self._clip.data_ptr()), _stream())
             clip_ptr = C.c_void_p(self._clip.data_ptr())
-        for g in self.groups:
+        for gi, g in enumerate(self.groups):
+            if gi in frozen:
+                continue
             lib.call("tdr_adamw_step", C.c_void_p(g.flat.data_ptr()), C.c_void_p(g.grad.data_ptr()),
                      C.c_void_p(g.m.data_ptr()), C.c_void_p(g.v.data_ptr()), g.n, g.lr, self.betas[0], self.betas[1],
                      self.eps, self.weight_decay, self.step_count, scale, clip_ptr, _stream())
@@ -174,7 +188,10 @@ class RefGuidedTrainer:
     buffers the all-reduce and the fused optimizer kernels work on; nothing in the step synchronises with the host.
     """
 
-    def __init__(self, net_g, train_opt, process_group=None):
+    def __init__(self, net_g, train_opt, process_group=None, net_ext=None):
+        """net_ext: optional frozen DINOv2 ViT (``archs.vit_b200.vit_base``): when given and the batch carries the FULL
+        reference image under ``'ref'``, the h x h reference crop most similar to ``lq`` is selected on the device every
+        step (image_restoration_ref_model.py:215-247), exactly where the reference does it."""
         og = dict(train_opt.get("optim_g", {}))
         if og.get("type", "AdamW") != "AdamW":
             raise lib.TdrError(f"RefGuidedTrainer: optimizer {og.get('type')} not implemented (AdamW only, as in the "
@@ -189,22 +206,32 @@ class RefGuidedTrainer:
                               use_grad_clip=bool(train_opt.get("use_grad_clip", True)),
                               ema_decay=float(train_opt.get("ema_decay", 0.0)), process_group=process_group)
         net_g.grad_direct = True
+        self.net_ext = net_ext
+        self.fix_iterations = train_opt.get("fix_iterations")
+        self._ref_group = tuple(i for i, g in enumerate(self.engine.groups) if g.tag == "ref")
         dev = self.engine.groups[0].flat.device
         self._loss = torch.zeros(1, dtype=F32, device=dev)
         self._partial = torch.zeros(lib.load().tdr_sumsq_partial_count(), dtype=F32, device=dev)
-        self.lq = self.gt = self.ref_in = self.output = None
+        self.lq = self.gt = self.ref_in = self.ref = self.output = None
         self.log_dict = {}
 
     def feed_train_data(self, data):
         dev = self.engine.groups[0].flat.device
         self.lq = data["lq"].to(dev, non_blocking=True)
         self.gt = data["gt"].to(dev, non_blocking=True) if "gt" in data else None
-        ref = data.get("ref_in", data.get("ref"))
-        self.ref_in = ref.to(dev, non_blocking=True) if ref is not None else None
+        self.ref_in = data["ref_in"].to(dev, non_blocking=True) if "ref_in" in data else None
+        self.ref = data["ref"].to(dev, non_blocking=True) if "ref" in data else None
+        if self.ref_in is None and self.ref is not None and self.net_ext is None:
+            self.ref_in = self.ref             # no selector: the reference image is used as is
 
     def optimize_parameters(self, current_iter=0):
         from .archs.restormer_train import Grads
         net = self.net_g
+        if self.net_ext is not None and self.ref is not None:
+            from .archs.vit_b200 import select_reference_crop
+            with torch.no_grad():
+                self.ref_in, _, _ = select_reference_crop(self.net_ext, self.lq, self.ref)
+        frozen = self._ref_group if (self.fix_iterations is not None and current_iter < self.fix_iterations) else ()
         self.engine.zero_grad()
         inputs = (self.lq,) if self.ref_in is None else (self.lq, self.ref_in)
         out, state = net._forward_train(*inputs)
@@ -216,7 +243,7 @@ class RefGuidedTrainer:
                  _stream())
         net._backward(state, dout, Grads(direct=True))
         works = self.engine.all_reduce_gradients()
-        self.engine.step(works)
+        self.engine.step(works, frozen=frozen)
         self.engine.reduce_loss_async(self._loss)
         return self._loss
 
