@@ -240,6 +240,11 @@ int tdr_gate_bwd(const void* y_bf16, long long y_ld, const void* dg_bf16, long l
                  int gate, void* dy_bf16, long long dy_ld,
                  const float* dg_add /* optional fp32 [rows / rows_per_sample][Ch] added to dg (SCA pool gradient) */,
                  long long rows_per_sample, cudaStream_t stream);
+/* Training forward of the gated depthwise conv: as tdr_dwconv3x3(gate 1|2) and ALSO stores the pre-gate tensor
+ * y = [a | b] (bf16 [B,H,W,>=C]) that tdr_gate_bwd needs, so the backward pass does not recompute the convolution. */
+int tdr_dwconv3x3_gated_train(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
+                              const float* bias, int gate, void* out_bf16, long long out_ld, void* y_bf16, long long y_ld,
+                              cudaStream_t stream);
 /* Fused recompute + gate backward: dy = tdr_gate_bwd(tdr_dwconv3x3(in, gate 0), dg) without writing the pre-gate tensor:
  * in = the depthwise conv's INPUT [B,H,W,C] (C = 2*Ch), dy bf16 [B,H,W,>=C] receives [d a | d b]. */
 int tdr_dwconv3x3_gate_bwd(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,

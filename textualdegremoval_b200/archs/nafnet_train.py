@@ -39,11 +39,13 @@ def run_naf_block_train(x32, p, tape):
     c = p["C"]
     sv = dict(p=p, x0=x32)
     xn = ops.rownorm(x32, 1, p["n1_w"], p["n1_b"], p["eps"])
+    sv["xn1"] = xn
     _, t1 = ops.conv_gemm(xn, p["w1"], p["dw"], bias=p["b1"])
-    g = ops.dwconv3x3(t1, p["w2"], p["b2"], gate=2)
+    g, sv["ydw"] = ops.dwconv3x3_gated_train(t1, p["w2"], p["b2"], 2)
     w3eff = ops.naf_sca_fold(g, p["w_sca"], p["b_sca"], p["w3"], rowscale=p["beta"], save=sv)
     y, _ = ops.conv_gemm(g, w3eff, c, bias=p["b3_beta"], res2=x32, want="f32", w_batched=True)
     xn = ops.rownorm(y, 1, p["n2_w"], p["n2_b"], p["eps"])
+    sv["xn2"] = xn
     _, t2 = ops.conv_gemm(xn, p["w4"], p["ffn"], bias=p["b4"])
     g2 = ops.gate_mul(t2)
     out, _ = ops.conv_gemm(g2, p["w5"], c, bias=p["b5_gamma"], res2=y, want="f32")
@@ -70,8 +72,7 @@ def run_naf_block_bwd(dout, sv, G):
                             G(blk.gamma))
     _, dg2 = ops.conv_gemm(d16, p["w5_T"], ffn // 2, Ci=c)
     dt2 = ops.gate_bwd(t2, dg2, 2)
-    xn2 = ops.rownorm(y, 1, p["n2_w"], p["n2_b"], p["eps"])
-    ops.wgrad(dt2, xn2, G(blk.conv4.weight))
+    ops.wgrad(dt2, sv["xn2"], G(blk.conv4.weight))
     ops.colsum(dt2, G(blk.conv4.bias))
     _, dxn2 = ops.conv_gemm(dt2, p["w4_T"], c, Ci=ffn)
     dy, dy16 = ops.rownorm_bwd(y, dxn2, 1, p["n2_w"], p["eps"], add=dout, out=dout, dweight=G(blk.norm2.weight),
@@ -85,12 +86,10 @@ def run_naf_block_bwd(dout, sv, G):
     dg_add = ops.naf_sca_bwd(raw3, p["w3"], p["beta"], sv["mean"], p["w_sca"], H * W, G(blk.sca[1].weight),
                              G(blk.sca[1].bias))
     _, dg = ops.conv_gemm(dy16, sv["weff_t"], dw // 2, Ci=c, w_batched=True)
-    ydw = ops.dwconv3x3(t1, p["w2"], p["b2"], gate=0)
-    dyd = ops.gate_bwd(ydw, dg, 2, dg_add=dg_add)
+    dyd = ops.gate_bwd(sv["ydw"], dg, 2, dg_add=dg_add)
     ops.dwconv3x3_wgrad(dyd, t1, G(blk.conv2.weight), G(blk.conv2.bias))
     dt1 = ops.dwconv3x3(dyd, p["w2_f"], None)
-    xn1 = ops.rownorm(x0, 1, p["n1_w"], p["n1_b"], p["eps"])
-    ops.wgrad(dt1, xn1, G(blk.conv1.weight))
+    ops.wgrad(dt1, sv["xn1"], G(blk.conv1.weight))
     ops.colsum(dt1, G(blk.conv1.bias))
     _, dxn1 = ops.conv_gemm(dt1, p["w1_T"], c, Ci=dw)
     return ops.rownorm_bwd(x0, dxn1, 1, p["n1_w"], p["eps"], add=dy, out=dy, dweight=G(blk.norm1.weight),

@@ -8,8 +8,9 @@ over the tensors the training forward keeps on a tape:
   * weight gradients are ``tdr_wgrad`` (tcgen05, contraction over pixels) / ``tdr_dwconv3x3_wgrad`` / ``tdr_colsum``;
   * LayerNorm, GELU gate, MDTA softmax/normalise and the fusion gate ``alpha`` have their own backward kernels.
 
-The residual-stream gradient is fp32; gradients of GEMM operands are bf16 (as the activations are).  LayerNorm outputs
-and the pre-gate depthwise output are recomputed in the backward pass instead of being stored.
+The residual-stream gradient is fp32; gradients of GEMM operands are bf16 (as the activations are).  The training forward
+keeps the LayerNorm outputs and the pre-gate depthwise output (the gated kernel stores it on the side), so the backward
+pass recomputes nothing.
 
 ``NetFunction`` exposes the pair to ``torch.autograd`` so that ``loss.backward()`` and an unmodified optimizer /
 ``DistributedDataParallel`` wrapper keep working; parameter gradients come back in the reference's parameter layout.
@@ -82,13 +83,15 @@ def run_block_train(x32, p, tape):
     fusion = p["alpha"] is not None
     sv = dict(p=p, x0=x32)
     xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5)
+    sv["xn1"] = xn                     # kept: operand of the qkv weight gradient (cheaper than re-normalising)
     _, qkv0 = ops.conv_gemm(xn, p["w_qkv"], 3 * C_, bias=p["b_qkv"])
     qkv = ops.dwconv3x3(qkv0, p["w_qkv_dw"], p["b_qkv_dw"])
     weff = ops.mdta_weff(qkv, C_, heads, p["temp"], p["w_po"], save=sv)
     x1, _ = ops.conv_gemm(qkv[..., 2 * C_:], weff, C_, Ci=C_, bias=p["b_po"], res2=x32, want="f32", w_batched=True)
     xn = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5)
+    sv["xn2"] = xn
     _, hid = ops.conv_gemm(xn, p["w_in"], 2 * hp, bias=p["b_in"])
-    g = ops.dwconv3x3(hid, p["w_dw"], p["b_dw"], gate=1)
+    g, sv["y"] = ops.dwconv3x3_gated_train(hid, p["w_dw"], p["b_dw"], 1)      # also keeps the pre-gate [a | b]
     out, _ = ops.conv_gemm(g, p["w_out"], C_, bias=p["b_out"], res2=x1, want="f32")
     if fusion:          # out = alpha * block(x0) + x0   (R:353)
         sv["t"] = out
@@ -122,15 +125,11 @@ def run_block_bwd(dout, sv, G, dout16=None, want16=False):
     ops.wgrad(d2_16, g, G(f.project_out.weight), ci_map=p["map_h"])
     if f.project_out.bias is not None:
         ops.colsum(d2_16, G(f.project_out.bias))
-    # recompute the pre-gate tensor with the (85 % of HBM) ungated kernel, then the pointwise gate backward: measured
-    # faster than the fused tdr_dwconv3x3_gate_bwd, which inherits the gated kernel's 32-channel tiling (52 % of HBM)
-    y = ops.dwconv3x3(hid, p["w_dw"], p["b_dw"], gate=0)
-    dy = ops.gate_bwd(y, dg, 1)
+    dy = ops.gate_bwd(sv["y"], dg, 1)           # pre-gate tensor kept by the training forward; overwritten in place
     ops.dwconv3x3_wgrad(dy, hid, G(f.dwconv.weight), G(f.dwconv.bias), c_map=p["map_2h"])
     dhid = ops.dwconv3x3(dy, p["w_dw_f"], None)
-    xn2 = ops.rownorm(x1, mode, p["ln2_w"], p["ln2_b"], 1e-5)
     _, dxn2 = ops.conv_gemm(dhid, p["w_in_T"], C_, Ci=2 * hp)
-    ops.wgrad(dhid, xn2, G(f.project_in.weight), co_map=p["map_2h"])
+    ops.wgrad(dhid, sv["xn2"], G(f.project_in.weight), co_map=p["map_2h"])
     if f.project_in.bias is not None:
         ops.colsum(dhid, G(f.project_in.bias), c_map=p["map_2h"])
     d1, d1_16 = ops.rownorm_bwd(x1, dxn2, mode, p["ln2_w"], 1e-5, add=d2, out=d2, dweight=G(blk.norm2.body.weight),
@@ -146,9 +145,8 @@ def run_block_bwd(dout, sv, G, dout16=None, want16=False):
     ops.conv_gemm(qkv[..., :2 * C_], mqk, 2 * C_, Ci=2 * C_, w_batched=True, out_bf16=dqkv[..., :2 * C_])
     ops.dwconv3x3_wgrad(dqkv, qkv0, G(a.qkv_dwconv.weight), G(a.qkv_dwconv.bias))
     dqkv0 = ops.dwconv3x3(dqkv, p["w_qkv_dw_f"], None)
-    xn1 = ops.rownorm(x0, mode, p["ln1_w"], p["ln1_b"], 1e-5)
     _, dxn1 = ops.conv_gemm(dqkv0, p["w_qkv_T"], C_, Ci=3 * C_)
-    ops.wgrad(dqkv0, xn1, G(a.qkv.weight))
+    ops.wgrad(dqkv0, sv["xn1"], G(a.qkv.weight))
     if a.qkv.bias is not None:
         ops.colsum(dqkv0, G(a.qkv.bias))
     emit16 = want16 and not fusion

@@ -320,9 +320,12 @@ struct DwArgs {
   const bf16* dg;          // GATE == 2 (gate backward): gradient of the gated product [B,H,W,Cout]
   long long dg_ld;
   const float* dg_add;     // optional per-sample term [B][Cout] added to dg (SCA pool gradient)
+  bf16* y_out;             // GATE == 1, optional (training): also store the pre-gate halves [a | b] (2 * Cout channels)
+  long long y_ld;
 };
 
-// GATE: 0 plain, 1 gated forward (a.gate 1 = GELU gate, 2 = SimpleGate), 2 gate BACKWARD: recomputes the two depthwise
+// GATE: 0 plain, 1 gated forward (a.gate 1 = GELU gate, 2 = SimpleGate), 3 = 1 + the pre-gate tensor is stored too
+// (training forward; a separate instantiation so that the inference kernel is untouched), 2 gate BACKWARD: recomputes the two depthwise
 // halves (a | b) exactly as the forward does and writes d[a | b] = [dg * b * act'(a) | dg * act(a)] (2 * Cout channels),
 // i.e. tdr_dwconv3x3(gate 0) + tdr_gate_bwd without the round trip of the pre-gate tensor through HBM.
 template <int GATE>
@@ -407,6 +410,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
     const int x = x0 + xl;
     bf16* outp = a.out + (((long long)b * a.H + y0) * a.W + x) * a.out_ld + c0;
     const bf16* dgp = GATE == 2 ? a.dg + (((long long)b * a.H + y0) * a.W + x) * a.dg_ld + c0 : nullptr;
+    bf16* yp = GATE == 3 ? a.y_out + (((long long)b * a.H + y0) * a.W + x) * a.y_ld + c0 : nullptr;
     const bool st_ok = c_ok && x < a.W;
 #pragma unroll
     for (int i = 0; i < kDwRows + 2; ++i) {                // staged row i = input row y0 - 1 + i
@@ -461,6 +465,21 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
           } else {
             raw_t o;
             uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
+            if constexpr (GATE == 3) {                      // training: keep the pre-gate tensor for the gate backward
+              raw_t ya, yb;
+              uint32_t* yau = reinterpret_cast<uint32_t*>(&ya);
+              uint32_t* ybu = reinterpret_cast<uint32_t*>(&yb);
+#pragma unroll
+              for (int e = 0; e < NP; ++e) {
+                float t0, t1;
+                upk2(acc[i % 3][0][e], t0, t1);
+                yau[e] = pack2(t0, t1);
+                upk2(acc[i % 3][NH - 1][e], t0, t1);
+                ybu[e] = pack2(t0, t1);
+              }
+              *reinterpret_cast<raw_t*>(yp) = ya;
+              *reinterpret_cast<raw_t*>(yp + a.Cout) = yb;
+            }
 #pragma unroll
             for (int e = 0; e < NP; ++e) {
               f2 val = acc[i % 3][0][e];
@@ -474,6 +493,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
         }
         outp += (long long)a.W * a.out_ld;
         if (GATE == 2) dgp += (long long)a.W * a.dg_ld;
+        if (GATE == 3) yp += (long long)a.W * a.y_ld;
       }
 #pragma unroll
       for (int h = 0; h < NH; ++h)
@@ -780,7 +800,10 @@ extern "C" int tdr_rownorm(const float* in, long long in_ld, long long rows, int
 
 static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
                          const float* bias, int gate, void* out_bf16, long long out_ld, const void* dg_bf16,
-                         long long dg_ld, const float* dg_add, cudaStream_t stream) {
+                         long long dg_ld, const float* dg_add, cudaStream_t stream, void* y_out = nullptr,
+                         long long y_ld = 0) {
+  TDR_CHECK_ARG(!y_out || (gate >= 1 && !dg_bf16 && y_ld >= C && y_ld % 4 == 0 && ((uintptr_t)y_out & 7) == 0),
+                "tdr_dwconv3x3_gated_train: y_out needs a gated forward launch and room for C channels");
   const bool bwd = dg_bf16 != nullptr;
   TDR_CHECK_ARG(in_bf16 && out_bf16 && weight, "tdr_dwconv3x3: null pointer");
   TDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "tdr_dwconv3x3: bad dims");
@@ -816,6 +839,7 @@ static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int
   a.total_tiles = B * a.tiles_x * a.tiles_y * a.chunks;
   a.wt = weight; a.bias = bias; a.gate = gate; a.out = out; a.out_ld = out_ld;
   a.dg = reinterpret_cast<const bf16*>(dg_bf16); a.dg_ld = dg_ld; a.dg_add = dg_add;
+  a.y_out = reinterpret_cast<bf16*>(y_out); a.y_ld = y_ld;
   TdrTensorMap map;
   const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)in_ld * 2, (uint64_t)in_ld * 2 * W, (uint64_t)in_ld * 2 * W * H};
@@ -834,9 +858,11 @@ static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int
     TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   if (bwd) dwconv3x3_tma_kernel<2><<<grid, 256, smem, stream>>>(map, a);
+  else if (gate && y_out) dwconv3x3_tma_kernel<3><<<grid, 256, smem, stream>>>(map, a);
   else if (gate) dwconv3x3_tma_kernel<1><<<grid, 256, smem, stream>>>(map, a);
   else dwconv3x3_tma_kernel<0><<<grid, 256, smem, stream>>>(map, a);
   TDR_CHECK_LAUNCH();
@@ -846,6 +872,14 @@ static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int
 extern "C" int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
                              const float* bias, int gate, void* out_bf16, long long out_ld, cudaStream_t stream) {
   return dwconv_launch(in_bf16, in_ld, B, H, W, C, weight, bias, gate, out_bf16, out_ld, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int tdr_dwconv3x3_gated_train(const void* in_bf16, long long in_ld, int B, int H, int W, int C,
+                                         const float* weight, const float* bias, int gate, void* out_bf16,
+                                         long long out_ld, void* y_bf16, long long y_ld, cudaStream_t stream) {
+  TDR_CHECK_ARG(gate == 1 || gate == 2, "tdr_dwconv3x3_gated_train: gate must be 1 or 2");
+  return dwconv_launch(in_bf16, in_ld, B, H, W, C, weight, bias, gate, out_bf16, out_ld, nullptr, 0, nullptr, stream,
+                       y_bf16, y_ld);
 }
 
 extern "C" int tdr_dwconv3x3_gate_bwd(const void* in_bf16, long long in_ld, int B, int H, int W, int C,

@@ -109,6 +109,7 @@ SIGNATURES.update({
     "tdr_dwconv3x3_wgrad": (_i, [_vp, _ll, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp]),
     "tdr_rownorm_bwd": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _f, _vp, _ll, _vp, _ll, _vp, _ll, _vp, _vp, _i, _vp, _vp]),
     "tdr_gate_bwd": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _i, _vp, _ll, _vp, _ll, _vp]),
+    "tdr_dwconv3x3_gated_train": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_dwconv3x3_gate_bwd": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _vp, _vp, _ll, _vp]),
     "tdr_naf_scaled_conv_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tdr_naf_sca_bwd": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _vp]),

@@ -600,6 +600,16 @@ def gate_bwd(y16, dg16, gate, out=None, dg_add=None):
     return out
 
 
+def dwconv3x3_gated_train(x16, w9, bias, gate):
+    """Gated depthwise conv that also returns the pre-gate tensor: (g [B,H,W,C/2], y [B,H,W,C])."""
+    B, H, W, Cc = x16.shape
+    out = torch.empty((B, H, W, Cc // 2), dtype=BF16, device=x16.device)
+    y = torch.empty((B, H, W, Cc), dtype=BF16, device=x16.device)
+    _call("tdr_dwconv3x3_gated_train", _p(x16), _ld(x16), B, H, W, Cc, _p(w9), _p(bias), gate, _p(out), _ld(out), _p(y),
+          _ld(y), _stream(), tag=f"g{gate}_C{Cc}_{H}x{W}", nbytes=B * H * W * Cc * 5, flops=2 * 9 * B * H * W * Cc)
+    return out, y
+
+
 def dwconv3x3_gate_bwd(x16, w9, bias, gate, dg16, dg_add=None):
     """Fused recompute of the gated depthwise conv + gate backward: returns d(pre-gate) bf16 [B,H,W,C]."""
     B, H, W, Cc = x16.shape
