@@ -348,33 +348,39 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                   for (int i = 0; i < 16; ++i) v[i] *= alpha;
                 }
               }
+              const uint32_t stg_s = smem_u32(stg);
               if constexpr (kF32) {
 #pragma unroll
                 for (int hh = 0; hh < 4; ++hh) {
                   const int off = lane * 128 + ((((q4 * 4 + hh) & 7) ^ (lane & 7)) << 4);
                   float4 o = make_float4(v[hh * 4], v[hh * 4 + 1], v[hh * 4 + 2], v[hh * 4 + 3]);
                   if (has_r2) {
-                    const float4 t = *reinterpret_cast<const float4*>(stg + off);
-                    o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+                    const uint4 t = lds128(stg_s + off);
+                    o.x += __uint_as_float(t.x); o.y += __uint_as_float(t.y);
+                    o.z += __uint_as_float(t.z); o.w += __uint_as_float(t.w);
                   }
                   if (has_r1) {
-                    const float4 t = *reinterpret_cast<const float4*>(buf + kEpiStageBytes + off);
-                    o.x = fmaf(r1s, t.x, o.x); o.y = fmaf(r1s, t.y, o.y);
-                    o.z = fmaf(r1s, t.z, o.z); o.w = fmaf(r1s, t.w, o.w);
+                    const uint4 t = lds128(smem_u32(buf + kEpiStageBytes) + off);
+                    o.x = fmaf(r1s, __uint_as_float(t.x), o.x); o.y = fmaf(r1s, __uint_as_float(t.y), o.y);
+                    o.z = fmaf(r1s, __uint_as_float(t.z), o.z); o.w = fmaf(r1s, __uint_as_float(t.w), o.w);
                   }
-                  *reinterpret_cast<float4*>(stg + off) = o;
+                  sts128(stg_s + off, __float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w));
                 }
               } else {
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                   const int off = lane * 128 + (((q4 * 2 + hh) ^ (lane & 7)) << 4);
                   if (has_r2) {
-                    float t[8];
-                    unpack8(*reinterpret_cast<const bf16x8*>(stg + off), t);
+                    const uint4 t = lds128(stg_s + off);
+                    const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) v[hh * 8 + i] += t[i];
+                    for (int i = 0; i < 4; ++i) {
+                      v[hh * 8 + 2 * i] += __uint_as_float(tw[i] << 16);
+                      v[hh * 8 + 2 * i + 1] += __uint_as_float(tw[i] & 0xffff0000u);
+                    }
                   }
-                  *reinterpret_cast<bf16x8*>(stg + off) = pack8(v + hh * 8);
+                  sts128(stg_s + off, pack2(v[hh * 8], v[hh * 8 + 1]), pack2(v[hh * 8 + 2], v[hh * 8 + 3]),
+                         pack2(v[hh * 8 + 4], v[hh * 8 + 5]), pack2(v[hh * 8 + 6], v[hh * 8 + 7]));
                 }
               }
             }
