@@ -168,25 +168,26 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
       if (lane == 0) {
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint32_t sb = sa + pl.boxes_m * kBoxBytes;
+        // descriptors are built once per stage and advanced through their start-address field (16 B units): the
+        // single issuing thread is instruction-bound for these small-N MMAs
+        const uint64_t da0 = umma_desc_sw128(sa, kBoxBytes, 1024);
+        const uint64_t db0 = umma_desc_sw128(sb, kBoxBytes, 1024);
         if (pl.fused) {
-          for (int tp = 0; tp < 9; ++tp) {
-            // tap (ky, kx): x tile kx, shifted down by ky image rows = ky * 8 px * 128 B (one swizzle atom)
-            const uint32_t sx = sb + (tp % 3) * kHaloXBytes + (tp / 3) * 1024;
+          uint32_t d_tmem = tmem_base;
+          for (int ky = 0; ky < 3; ++ky) {
+            for (int kx = 0; kx < 3; ++kx) {
+              // tap (ky, kx): x tile kx, shifted down by ky image rows = ky * 8 px * 128 B (one swizzle atom)
+              const uint64_t db = db0 + (uint64_t)((kx * kHaloXBytes + ky * 1024) >> 4);
 #pragma unroll
-            for (int ks = 0; ks < kPixTile / 16; ++ks) {
-              const uint64_t da = umma_desc_sw128(sa + ks * 2048, kBoxBytes, 1024);
-              const uint64_t db = umma_desc_sw128(sx + ks * 2048, kBoxBytes, 1024);
-              umma_bf16(tmem_base + tp * pl.BN, da, db, idesc, (t | ks) != 0);
+              for (int ks = 0; ks < kPixTile / 16; ++ks)
+                umma_bf16(d_tmem, da0 + ks * 128, db + ks * 128, idesc, (t | ks) != 0);
+              d_tmem += pl.BN;
             }
           }
         } else {
 #pragma unroll
-          for (int ks = 0; ks < kPixTile / 16; ++ks) {
-            // 16 pixels (K) = two 8-row swizzle atoms of 1024 B; 64-channel chunks are kBoxBytes apart (LBO)
-            const uint64_t da = umma_desc_sw128(sa + ks * 2048, kBoxBytes, 1024);
-            const uint64_t db = umma_desc_sw128(sb + ks * 2048, kBoxBytes, 1024);
-            umma_bf16(tmem_base, da, db, idesc, (t | ks) != 0);
-          }
+          for (int ks = 0; ks < kPixTile / 16; ++ks)     // 16 pixels (K) = two 8-row swizzle atoms = 2048 B = 128 units
+            umma_bf16(tmem_base, da0 + ks * 128, db0 + ks * 128, idesc, (t | ks) != 0);
         }
         umma_commit(&empty[stage]);
         if (t == ntiles - 1) umma_commit(tfull);

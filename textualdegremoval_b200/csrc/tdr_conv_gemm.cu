@@ -194,19 +194,26 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (lane == 0) {
-            for (int tap = 0; tap < taps; ++tap) {
-              // tap (ky, kx) = the same haloed tile shifted by (ky*dil) rows of 16 px and (kx*dil) px; every 8-pixel
-              // UMMA row group is one image-row segment, groups are 2048 B apart (16-px row pitch).  The 128 B
-              // swizzle is a function of the absolute smem address, so 128 B-aligned shifted starts need no fix-up
-              // (verified on device: descriptor base-offset must stay 0).
-              const uint32_t sa_addr = smem_u32(smem_a + stage * a.halo_bytes) +
-                                       (((tap / a.KW) * a.dil * 16 + (tap % a.KW) * a.dil) << 7);
-              const uint32_t sb = smem_u32(smem_b + (kc * taps + tap) * b_bytes);
+            // tap (ky, kx) = the same haloed tile shifted by (ky*dil) rows of 16 px and (kx*dil) px; every 8-pixel
+            // UMMA row group is one image-row segment, groups are 2048 B apart (16-px row pitch).  The 128 B
+            // swizzle is a function of the absolute smem address, so 128 B-aligned shifted starts need no fix-up
+            // (verified on device: descriptor base-offset must stay 0).
+            // The single issuing thread is instruction-bound (ncu: tensor pipe 23 % busy at N = 64), so descriptors
+            // are built ONCE per stage and advanced by adding to their 14-bit start-address field (16 B units).
+            const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a + stage * a.halo_bytes), 0, 2048);
+            uint64_t db = umma_desc_sw128(smem_u32(smem_b + kc * taps * b_bytes), 0, 1024);
+            const uint32_t b_step = (uint32_t)b_bytes >> 4;
+            uint32_t accum = kc != 0;
+            for (int ky = 0; ky < a.KH; ++ky) {
+              uint64_t da = da0 + (uint64_t)((ky * a.dil * 16) << 3);
+              for (int kx = 0; kx < a.KW; ++kx) {
 #pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) {
-                const uint64_t da = umma_desc_sw128(sa_addr + k * 32, 0, 2048);
-                const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
-                umma_bf16(d_tmem, da, db, idesc, (kc | tap | k) != 0);
+                for (int k = 0; k < kChunkK / 16; ++k) {
+                  umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                  accum = 1;
+                }
+                da += (uint64_t)(a.dil << 3);
+                db += b_step;
               }
             }
             umma_commit(&empty[stage]);
@@ -221,14 +228,11 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(smem_a + stage * kABytes);
-          const uint32_t sb = smem_u32(smem_b + stage * b_bytes);
+          const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * kABytes), 0, 1024);
+          const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * b_bytes), 0, 1024);
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k) {
-            const uint64_t da = umma_desc_sw128(sa + k * 32, 0, 1024);
-            const uint64_t db = umma_desc_sw128(sb + k * 32, 0, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0);
-          }
+          for (int k = 0; k < kChunkK / 16; ++k)                  // K advance = 32 B = 2 units of the address field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
           umma_commit(&empty[stage]);                   // smem stage reusable once these MMAs retire
           if (ks == ksteps - 1) umma_commit(&tfull[acc]);
         }

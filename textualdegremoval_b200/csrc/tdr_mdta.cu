@@ -110,11 +110,12 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
       if (lane == 0) {
         const uint32_t sq = smem_u32(smem + stage * stage_bytes);
         const uint32_t sk = sq + pl.boxes * kBoxBytes;
+        const uint64_t dq0 = umma_desc_sw128(sq, kBoxBytes, 1024), dk0 = umma_desc_sw128(sk, kBoxBytes, 1024);
 #pragma unroll
         for (int ks = 0; ks < kPixTile / 16; ++ks) {
-          // 16 pixels (K) = two 8-row swizzle atoms of 1024 B; 64-channel chunks are kBoxBytes apart (LBO)
-          const uint64_t dq = umma_desc_sw128(sq + ks * 2048, kBoxBytes, 1024);
-          const uint64_t dk = umma_desc_sw128(sk + ks * 2048, kBoxBytes, 1024);
+          // 16 pixels (K) = two 8-row swizzle atoms of 1024 B = 128 units of the descriptor's start-address field;
+          // 64-channel chunks are kBoxBytes apart (LBO)
+          const uint64_t dq = dq0 + ks * 128, dk = dk0 + ks * 128;
           const uint32_t accum = (t | ks) != 0;
           umma_bf16(tmem_base + 0 * pl.N, dq, dk, idesc, accum);
           umma_bf16(tmem_base + 1 * pl.N, dq, dq, idesc, accum);
