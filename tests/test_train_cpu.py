@@ -62,3 +62,19 @@ def test_training_forward_refuses_cpu_tensors():
     naf = define_network(dict(type="NAFNet", img_channel=3, width=16, middle_blk_num=1, enc_blk_nums=[1], dec_blk_nums=[1])).train()
     with pytest.raises(TdrError):
         naf(torch.rand(1, 3, 32, 32))
+
+
+def test_ema_state_dict_views():
+    """EMA copies are exposed under the reference's parameter names (what `save_network(..., 'params_ema')` writes)."""
+    from textualdegremoval_b200.ddp import DDPStep
+    net = define_network(dict(type="Restormer", dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1))
+    tr = RefGuidedTrainer.__new__(RefGuidedTrainer)
+    tr.net_g = net
+    tr.engine = DDPStep.__new__(DDPStep)
+    tr.engine.groups = split_param_groups(list(net.named_parameters()), 1e-4, 1e-4)
+    tr.engine.ema = [g.flat.clone() for g in tr.engine.groups]
+    sd = tr.ema_state_dict()
+    assert set(sd) == set(net.state_dict()) and all(sd[n].shape == p.shape for n, p in net.named_parameters())
+    assert all(torch.equal(sd[n], p.detach()) for n, p in net.named_parameters())
+    tr.engine.ema = None
+    assert tr.ema_state_dict() is None

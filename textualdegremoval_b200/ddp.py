@@ -247,6 +247,20 @@ class RefGuidedTrainer:
         self.engine.reduce_loss_async(self._loss)
         return self._loss
 
+    def ema_state_dict(self):
+        """``net_g_ema`` parameters (models/base_model.py:54-62, saved under 'params_ema' :213-250) as a name -> tensor
+        dict of views into the flat EMA buffers; None when ema_decay == 0.  Buffers of the module are passed through."""
+        if self.engine.ema is None:
+            return None
+        by_id = {}
+        for g, e in zip(self.engine.groups, self.engine.ema):
+            for p, v in zip(g.params, g.views(e)):
+                by_id[id(p)] = v
+        sd = {n: by_id[id(p)] for n, p in self.net_g.named_parameters()}
+        for n, b in self.net_g.named_buffers():
+            sd[n] = b
+        return sd
+
     def current_loss(self):
         """Host read of the (rank-averaged) pixel loss: call every print_freq iterations (base_model.py:353-378)."""
         self.log_dict = {"l_pix": self.engine.read_loss()}
