@@ -803,7 +803,7 @@ def check_restormer_grad():
     from oracle import restormer as O, weights as Wt
     from textualdegremoval_b200.archs import define_network
     out = []
-    for name in ("restormer_withbias", "restormer_gray_bias"):
+    for name in ("restormer_withbias", "restormer_biasfree", "restormer_gray_bias"):
         meta, _ = _golden(name)
         net = define_network(dict(type="Restormer", **meta["cfg"]))
         sd = Wt.load_seeded(net, meta["seed"])
@@ -1026,6 +1026,67 @@ def check_nafnet_grad():
     out.append(dict(name="grad_modules_guided_nafnet_256", max_err=wm, tol=0.1, ok=bool(wm <= 0.1), note="worst module"))
     return out
 
+
+def check_fullsize_properties():
+    """BASELINE.json's full configuration (option 003, 512x512) has no CPU-oracle answer in test time; it is covered by
+    size-independent properties: (i) identity at alpha = 0 (SURVEY 8c i) -- the guided net equals the unguided Restormer
+    built from its non-masa weights; (ii) samples are independent units -- a batch equals its samples run one by one;
+    (iii) the backward pass is linear in the output gradient and the step is deterministic."""
+    from textualdegremoval_b200.archs import define_network
+    out = []
+    cfg = dict(inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4,
+               heads=[1, 2, 4, 8], ffn_expansion_factor=2.66, bias=False, LayerNorm_type="WithBias", nf=48,
+               ext_n_blocks=[4, 4, 4, 4], reffusion_n_blocks=[2, 2, 2, 2])
+    torch.manual_seed(0)
+    net = define_network(dict(type="RestormerRefFusion", **cfg))
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if n.endswith("temperature"):
+                p.uniform_(0.5, 1.5)
+    g = torch.Generator().manual_seed(5)
+    lq = torch.rand(2, 3, 512, 512, generator=g).to(DEV)
+    ref = torch.rand(2, 3, 512, 512, generator=g).to(DEV)
+    net = net.to(DEV).eval()
+    # (i) alpha = 0 (the reference's init): guided == unguided on the same non-masa weights
+    plain = define_network(dict(type="Restormer", **{k_: v for k_, v in cfg.items()
+                                                     if k_ not in ("nf", "ext_n_blocks", "reffusion_n_blocks")}))
+    plain.load_state_dict({k_: v for k_, v in net.state_dict().items() if "masa" not in k_}, strict=True)
+    plain = plain.to(DEV).eval()
+    with torch.no_grad():
+        y0 = net(lq[:1], ref[:1])
+        yp = plain(lq[:1])
+    out.append(result("fullsize_identity_at_zero_alpha", y0, yp, 1e-5))
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if n.endswith("alpha"):
+                p.uniform_(0.2, 1.0)
+        yb = net(lq, ref)
+        y1 = torch.cat([net(lq[i:i + 1], ref[i:i + 1]) for i in range(2)])
+    out.append(result("fullsize_batch_equals_samples", yb, y1, 2e-3,
+                      note="split-K Gram chunking depends on the batch size: summation order differs"))
+    out.append(dict(name="fullsize_guidance_changes_output", ok=bool((yb[:1] - y0).abs().max().item() > 1e-3),
+                    max_err=(yb[:1] - y0).abs().max().item(), tol=None))
+    # (iii) backward: deterministic and linear in dout
+    net.train()
+    gt = torch.rand(1, 3, 512, 512, generator=g).to(DEV)
+
+    def grads(scale):
+        for p in net.parameters():
+            p.grad = None
+        y = net(lq[:1], ref[:1])
+        ((y - gt).abs().mean() * scale).backward()
+        return torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+
+    g1, g1b, g4 = grads(1.0), grads(1.0), grads(4.0)
+    det = (g1 - g1b).abs().max().item()
+    out.append(dict(name="fullsize_backward_repeatable", ok=bool(det <= 1e-6 * g1.abs().max().item() + 1e-12), max_err=det, tol=None,
+                    note="only the MASA scatter-adds use fp32 atomics"))
+    out.append(grad_result("fullsize_backward_linear_in_dout", g4, 4.0 * g1, 2e-3))
+    out.append(dict(name="fullsize_all_params_get_gradients", ok=bool(all(p.grad is not None and torch.isfinite(p.grad).all()
+                                                                         and p.grad.abs().max() > 0 for p in net.parameters())),
+                    max_err=None, tol=None))
+    return out
+
 CHECKS = {
     "layout": check_layout,
     "rownorm": check_rownorm,
@@ -1051,6 +1112,7 @@ CHECKS = {
     "guided_grad": check_guided_grad,
     "train_step": check_train_step,
     "nafnet_grad": check_nafnet_grad,
+    "fullsize_properties": check_fullsize_properties,
 }
 
 

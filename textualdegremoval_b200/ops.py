@@ -668,7 +668,11 @@ def pixel_shuffle(x16, mode):
     """mode 1: PixelUnshuffle(2) [B,H,W,C] -> [B,H/2,W/2,4C]; mode 2: PixelShuffle(2) [B,H,W,C] -> [B,2H,2W,C/4]."""
     B, H, W, Cc = x16.shape
     oshape = (B, H // 2, W // 2, Cc * 4) if mode == 1 else (B, H * 2, W * 2, Cc // 4)
-    out = torch.empty(oshape, dtype=BF16, device=x16.device)
+    if oshape[3] % 8:            # keep 16 B rows for TMA: zero-padded channel stride, the view has the logical width
+        full = torch.zeros(oshape[:3] + (round_up(oshape[3], 8),), dtype=BF16, device=x16.device)
+        out = full[..., :oshape[3]]
+    else:
+        out = torch.empty(oshape, dtype=BF16, device=x16.device)
     _call("tdr_pixel_shuffle_nhwc", _p(x16), _ld(x16), B, H, W, Cc, mode, _p(out), _ld(out), _stream(),
           tag=f"m{mode}_C{Cc}", nbytes=B * H * W * Cc * 4)
     return out
