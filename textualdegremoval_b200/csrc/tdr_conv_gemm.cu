@@ -303,7 +303,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         for (int k = 0; k < n_my; ++k) {
           // staging buffer: residual tiles were queued into (k & 1); without residuals consecutive stores simply
           // alternate (across tiles too), so wait_group.read 1 always covers the buffer about to be overwritten
-          const int j = !dbuf ? 0 : (has_r2 ? (k & 1) : (store_cnt++ & 1));
+          const int j = has_r2 ? (dbuf ? (k & 1) : 0) : (a.epi_bufs > 1 ? (store_cnt++ % a.epi_bufs) : 0);
           const int cs = (half + 2 * k) * sbc;
           uint8_t* const stg = buf + j * kEpiStageBytes;
           uint32_t raw[4][16];
@@ -315,8 +315,11 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
             mbar_wait(&rb[j], rphase[j]);
             rphase[j] ^= 1;
           } else {
-            if (lane == 0) {
-              if (a.epi_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read();
+            if (lane == 0) {             // the staging buffer about to be overwritten was handed to TMA epi_bufs stores ago
+              if (a.epi_bufs >= 4) tma_store_wait_read3();
+              else if (a.epi_bufs == 3) tma_store_wait_read2();
+              else if (a.epi_bufs == 2) tma_store_wait_read1();
+              else tma_store_wait_read();
             }
             __syncwarp();
           }
@@ -713,7 +716,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     if (!d->res2 && !d->res1 && a.BN > 192) { a.epi_bufs = 1; a.stages = 4; }   // no residual tiles: favour depth
     if (const char* e = getenv("TDR_CONV_EPIBUFS")) {                            // tuning knobs (experiments only)
       const int v = atoi(e);
-      if ((v == 1 && !d->res1) || v == 2) a.epi_bufs = v;
+      if ((v == 1 && !d->res1) || v == 2 || ((v == 3 || v == 4) && !d->res1 && !d->res2)) a.epi_bufs = v;
     }
     if (const char* e = getenv("TDR_CONV_STAGES")) {
       const int v = atoi(e);
@@ -750,8 +753,10 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
       a.epi_bufs = d->res1 ? 2 : 1;
     }
   }
+  const bool bufs_forced = getenv("TDR_CONV_EPIBUFS") != nullptr;
   while (smem_need() > 227 * 1024) {
-    if (a.epi_bufs == 2 && !d->res1) a.epi_bufs = 1;
+    if (bufs_forced && a.stages > 2) --a.stages;
+    else if (a.epi_bufs >= 2 && !d->res1) --a.epi_bufs;
     else if (a.stages > 2) --a.stages;
     else break;
   }
