@@ -44,6 +44,7 @@ struct ConvGemmArgs {
   const int* origin;            // optional [B][3] = (image, y0, x0)
   int total_tiles;
   uint32_t tmem_cols;
+  int nacc;                     // TMEM accumulator buffers in flight (2..4): nacc * BN <= 512 columns
   // epilogue
   const float* bias;            // [Co] or null
   const float* rowscale;        // [B*OH*OW] or null
@@ -93,9 +94,9 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiWarps * a.epi_bufs * kEpiStageBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kMaxStages;
-  uint64_t* tfull = bars + 2 * kMaxStages;
-  uint64_t* tempty = bars + 2 * kMaxStages + 2;
-  uint64_t* rbar = bars + 2 * kMaxStages + 4;                  // [kEpiWarps][2] residual-tile barriers
+  uint64_t* tfull = bars + 2 * kMaxStages;                     // [4]
+  uint64_t* tempty = bars + 2 * kMaxStages + 4;                // [4]
+  uint64_t* rbar = bars + 2 * kMaxStages + 8;                  // [kEpiWarps][2] residual-tile barriers
   uint64_t* wfull = rbar + 2 * kEpiWarps;                      // halo mode: resident weights have landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
 
@@ -116,7 +117,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     }
     for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&rbar[i], 1);
     mbar_init(wfull, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpiWarps);
     }
@@ -183,8 +184,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % a.nacc;
+      const uint32_t acc_phase = (it / a.nacc) & 1;
       mbar_wait(&tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * a.BN;
@@ -255,8 +256,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     int store_cnt = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % a.nacc;
+      const uint32_t acc_phase = (it / a.nacc) & 1;
       const int nt = tile % a.n_tiles;
       const int mt = tile / a.n_tiles;
       const int b = mt / tiles_per_img;
@@ -762,8 +763,17 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   }
   TDR_CHECK_ARG(smem_need() <= 227 * 1024, "tdr_conv_gemm: shared-memory plan does not fit");
   a.total_tiles = d->B * a.tiles_y * a.tiles_x * a.n_tiles;
+  // accumulator ring: as many BN-column buffers as fit in the 512 TMEM columns (2..4) -- a deeper ring keeps more
+  // tiles between the MMA issuer and the epilogue in flight
+  a.nacc = 512 / a.BN;
+  if (a.nacc > 4) a.nacc = 4;
+  if (a.nacc < 2) a.nacc = 2;
+  if (const char* e = getenv("TDR_CONV_NACC")) {                                 // tuning knob (experiments only)
+    const int v = atoi(e);
+    if (v >= 2 && v <= 4 && v * a.BN <= 512) a.nacc = v;
+  }
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * a.BN)) cols <<= 1;
+  while (cols < (uint32_t)(a.nacc * a.BN)) cols <<= 1;
   a.tmem_cols = cols;
 
   if (d->impl == 1) {
