@@ -155,9 +155,12 @@ def run_block(x32, p):
     """
     C_, heads, hp = p["C"], p["heads"], p["hp"]
     fusion = p["alpha"] is not None
-    xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5)
-    _, qkv = ops.conv_gemm(xn, p["w_qkv"], 3 * C_, bias=p["b_qkv"])
-    qkv = ops.dwconv3x3(qkv, p["w_qkv_dw"], p["b_qkv_dw"])
+    B, H, W, _ = x32.shape
+    dev = x32.device
+    # bf16 operands with 128 B-aligned row pitch (ops.rows16): C = 48 / 96 rows would straddle lines otherwise
+    xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5, out=ops.rows16(B, H, W, C_, dev))
+    _, qkv = ops.conv_gemm(xn, p["w_qkv"], 3 * C_, bias=p["b_qkv"], out_bf16=ops.rows16(B, H, W, 3 * C_, dev))
+    qkv = ops.dwconv3x3(qkv, p["w_qkv_dw"], p["b_qkv_dw"], out=ops.rows16(B, H, W, 3 * C_, dev))
     weff = ops.mdta_weff(qkv, C_, heads, p["temp"], p["w_po"])
     v = qkv[..., 2 * C_:]
     if fusion:
@@ -165,7 +168,7 @@ def run_block(x32, p):
     else:
         ops.conv_gemm(v, weff, C_, Ci=C_, bias=p["b_po"], res2=x32, out_f32=x32, w_batched=True)
         x1 = x32
-    xn = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5)
+    xn = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5, out=xn)
     _, hid = ops.conv_gemm(xn, p["w_in"], 2 * hp, bias=p["b_in"])
     g = ops.dwconv3x3(hid, p["w_dw"], p["b_dw"], gate=1)
     if fusion:      # out = (x1 + ffn) * alpha + x0

@@ -45,6 +45,7 @@ struct ConvGemmArgs {
   int total_tiles;
   uint32_t tmem_cols;
   int nacc;                     // TMEM accumulator buffers in flight (2..4): nacc * BN <= 512 columns
+  int pf_dist;                  // L2 prefetch distance of the A operand, in this CTA's future tiles (0 = off)
   // epilogue
   const float* bias;            // [Co] or null
   const float* rowscale;        // [B*OH*OW] or null
@@ -153,6 +154,25 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         const int ox0 = (r % a.tiles_x) * a.TW;
         int img = b, org_y = 0, org_x = 0;
         if (a.origin) { img = a.origin[3 * b]; org_y = a.origin[3 * b + 1]; org_x = a.origin[3 * b + 2]; }
+        // The smem ring holds ~2 tiles of A: not enough bytes in flight to cover DRAM latency.  Pull the A
+        // boxes of a tile pf_dist iterations ahead into L2 now, so that its TMA loads later are L2 hits.
+        if (a.pf_dist > 0 && !a.origin && nt == 0) {
+          const long long ft = (long long)tile + (long long)a.pf_dist * gridDim.x;
+          if (ft < a.total_tiles) {
+            const int fmt = (int)(ft / a.n_tiles);
+            const int fb = fmt / tiles_per_img, fr = fmt % tiles_per_img;
+            const int foy = (fr / a.tiles_x) * a.TH, fox = (fr % a.tiles_x) * a.TW;
+            for (int kc = 0; kc < a.kchunks; ++kc) {
+              if (a.halo) {
+                tma_prefetch_4d(&map_a, kc * kChunkK, fox - a.pad, foy - a.pad, fb);
+              } else {
+                for (int tap = 0; tap < taps; ++tap)
+                  tma_prefetch_4d(&map_a, kc * kChunkK, fox * a.stride - a.pad + (tap % a.KW) * a.dil,
+                                  foy * a.stride - a.pad + (tap / a.KW) * a.dil, fb);
+              }
+            }
+          }
+        }
         if (a.halo) {
           for (int kc = 0; kc < a.kchunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -775,6 +795,8 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   uint32_t cols = 32;
   while (cols < (uint32_t)(a.nacc * a.BN)) cols <<= 1;
   a.tmem_cols = cols;
+  a.pf_dist = 0;
+  if (const char* e = getenv("TDR_CONV_PF")) a.pf_dist = atoi(e);                // tuning knob (experiments only)
 
   if (d->impl == 1) {
     const long long total = (long long)a.B * OH * OW * a.Co;

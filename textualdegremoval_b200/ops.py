@@ -168,6 +168,16 @@ def pack_dw_weight(w: torch.Tensor, n=None, idx=None) -> torch.Tensor:
     return out
 
 
+def rows16(B, H, W, Cc, dev):
+    """bf16 NHWC activation buffer whose row pitch is a multiple of 128 B (64 channels): a view [B,H,W,Cc] of a wider
+    allocation.  Rows that straddle 128 B lines (C = 48, 96, 144, 288 ...) cost the TMA loads / stores of the GEMMs up to
+    25 % of their bandwidth (tools/probe.py qkv48 vs qkv48_ld192); the pad columns are never read or written."""
+    ld = round_up(Cc, 64)
+    if ld == Cc:
+        return torch.empty((B, H, W, Cc), dtype=BF16, device=dev)
+    return torch.empty((B, H, W, ld), dtype=BF16, device=dev)[..., :Cc]
+
+
 # ---------------------------------------------------------------------------------------------- ops
 def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, relu=False, gelu=False, rowscale=None,
               alpha=1.0, scale_ptr=None, res1=None, res1_scale=1.0, res2=None, out_f32=None, out_bf16=None,

@@ -21,14 +21,15 @@ def r16(*s):
     return torch.randn(*s, device=DEV, dtype=F32).to(BF16)
 
 
-def conv(B, H, W, Ci, Co, k=1, want="bf16", res=False, **kw):
-    x = r16(B, H, W, Ci)
+def conv(B, H, W, Ci, Co, k=1, want="bf16", res=False, ld_out=None, ld_in=None, **kw):
+    x = r16(B, H, W, ld_in or Ci)[..., :Ci]
     w = r16(k * k, Co, ops.round_up(Ci, 8))
     r = torch.randn(B, H, W, Co, device=DEV) if res else None
-    o32 = torch.empty(B, H, W, Co, device=DEV) if want == "f32" else None
+    o32 = torch.empty(B, H, W, ld_out or Co, device=DEV)[..., :Co] if want == "f32" else None
+    o16 = torch.empty(B, H, W, ld_out or Co, device=DEV, dtype=BF16)[..., :Co] if want == "bf16" else None
     nbytes = B * H * W * (Ci * 2 + Co * (2 if want == "bf16" else 4) + (Co * 4 if res else 0))
     flops = 2 * B * H * W * Ci * Co * k * k
-    return (lambda: ops.conv_gemm(x, w, Co, k=k, pad=k // 2, res2=r, out_f32=o32, want=want, **kw)), nbytes, flops
+    return (lambda: ops.conv_gemm(x, w, Co, k=k, pad=k // 2, res2=r, out_f32=o32, out_bf16=o16, want=want, **kw)), nbytes, flops
 
 
 def dw(B, H, W, C_, gate):
@@ -91,6 +92,10 @@ PROBES = {
     "dwwg1024": lambda: dwwg(4, 128, 128, 1024),
     "lnb96": lambda: lnb(4, 512, 512, 96),
     "gateb512": lambda: gateb(4, 512, 512, 512),
+    "qkv96_ld320": lambda: conv(4, 512, 512, 96, 288, ld_out=320),
+    "qkv96_in128": lambda: conv(4, 512, 512, 96, 288, ld_in=128),
+    "qkv96_both": lambda: conv(4, 512, 512, 96, 288, ld_out=320, ld_in=128),
+    "qkv48_ld192": lambda: conv(4, 512, 512, 48, 144, ld_out=192, ld_in=64),
     "pin96": lambda: conv(4, 512, 512, 96, 512),
     "qkv96": lambda: conv(4, 512, 512, 96, 288),
     "pout256": lambda: conv(4, 512, 512, 256, 96, want="f32", res=True),
