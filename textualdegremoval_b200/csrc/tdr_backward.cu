@@ -272,10 +272,41 @@ __global__ void __launch_bounds__(256) reduce_parts_kernel(const float* __restri
   if (c >= n) return;
   const int lc = map ? map[c] : c;
   if (lc < 0) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * n + c];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;        // fixed association order: still deterministic
+  int p = 0;
+  for (; p + 3 < nparts; p += 4) {
+    s0 += partials[(size_t)p * n + c];
+    s1 += partials[(size_t)(p + 1) * n + c];
+    s2 += partials[(size_t)(p + 2) * n + c];
+    s3 += partials[(size_t)(p + 3) * n + c];
+  }
+  for (; p < nparts; ++p) s0 += partials[(size_t)p * n + c];
+  const float s = (s0 + s1) + (s2 + s3);
   float* o = out + lc * stride;
   *o = (accumulate ? *o : 0.f) + scale * s;
+}
+
+// out[map(c)*stride] (+)= sum_p partials[p][c] with the partial rows split over the 8 warps of a block (many partial rows,
+// few columns: colsum of small activations).  grid (ceil(n/32)), block (32, 8); fixed summation order.
+__global__ void __launch_bounds__(256) reduce_parts_wide_kernel(const float* __restrict__ partials, int nparts, int n,
+                                                                float* __restrict__ out, long long stride,
+                                                                const int* __restrict__ map, int accumulate) {
+  __shared__ float red[8][32];
+  const int c = blockIdx.x * 32 + threadIdx.x, ty = threadIdx.y;
+  float s = 0.f;
+  if (c < n)
+    for (int p = ty; p < nparts; p += 8) s += partials[(size_t)p * n + c];
+  red[ty][threadIdx.x] = s;
+  __syncthreads();
+  if (ty == 0 && c < n) {
+    const int lc = map ? map[c] : c;
+    if (lc < 0) return;
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    float* o = out + lc * stride;
+    *o = (accumulate ? *o : 0.f) + t;
+  }
 }
 
 constexpr int kRedBlocks = 296;   // partial rows written by the first stage of the column reductions
@@ -967,43 +998,59 @@ __global__ void __launch_bounds__(256) naf_scaled_conv_bwd_kernel(const float* _
   }
 }
 
-// ds[b][ci] = sum_co scale[co] W3[co][ci] raw_b[co][ci]     (thread per (b, ci); coalesced over ci)
+// ds[b][ci] = sum_co scale[co] W3[co][ci] raw_b[co][ci].  grid (ceil(C/32), B), block (32, 8): lanes over ci (coalesced),
+// the 8 warps split the co loop and are reduced through shared memory.
 __global__ void __launch_bounds__(256) naf_sca_ds_kernel(const float* __restrict__ raw, int B, int Co, int C,
                                                          const float* __restrict__ W3, const float* __restrict__ scale,
                                                          float* __restrict__ ds) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * C) return;
-  const int b = idx / C, ci = idx % C;
+  __shared__ float red[8][32];
+  const int ci = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y, ty = threadIdx.y;
   float t = 0.f;
-  for (int co = 0; co < Co; ++co) t = fmaf(scale[co] * W3[(size_t)co * C + ci], raw[((size_t)b * Co + co) * C + ci], t);
-  ds[idx] = t;
+  if (ci < C)
+    for (int co = ty; co < Co; co += 8)
+      t = fmaf(scale[co] * W3[(size_t)co * C + ci], raw[((size_t)b * Co + co) * C + ci], t);
+  red[ty][threadIdx.x] = t;
+  __syncthreads();
+  if (ty == 0 && ci < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    ds[(size_t)b * C + ci] = s;
+  }
 }
 
-// SCA 1x1 conv backward: dWsca[i][j] += sum_b ds_b[i] mean_b[j]; dbsca[i] += sum_b ds_b[i]; dgadd[b][j] = sum_i Wsca[i][j] ds_b[i] / P
-// grid (C + B): blocks [0, C) handle row i of dWsca, blocks [C, C + B) handle sample b of dgadd.
+// dgadd[b][j] = sum_i Wsca[i][j] ds_b[i] / P   (same mapping: lanes over j, warps over i)
+__global__ void __launch_bounds__(256) naf_sca_dgadd_kernel(const float* __restrict__ ds, const float* __restrict__ w_sca,
+                                                            int C, float inv_p, float* __restrict__ dgadd) {
+  __shared__ float red[8][32];
+  const int j = blockIdx.x * 32 + threadIdx.x, b = blockIdx.y, ty = threadIdx.y;
+  float t = 0.f;
+  if (j < C)
+    for (int i = ty; i < C; i += 8) t = fmaf(w_sca[(size_t)i * C + j], ds[(size_t)b * C + i], t);
+  red[ty][threadIdx.x] = t;
+  __syncthreads();
+  if (ty == 0 && j < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    dgadd[(size_t)b * C + j] = s * inv_p;
+  }
+}
+
+// dWsca[i][j] += sum_b ds_b[i] mean_b[j];  dbsca[i] += sum_b ds_b[i].   grid (C), block 256 over j.
 __global__ void __launch_bounds__(256) naf_sca_bwd_kernel(const float* __restrict__ ds, const float* __restrict__ mean,
-                                                          const float* __restrict__ w_sca, int B, int C, float inv_p,
-                                                          float* __restrict__ dwsca, float* __restrict__ dbsca,
-                                                          float* __restrict__ dgadd) {
-  if ((int)blockIdx.x < C) {
-    const int i = blockIdx.x;
-    for (int j = threadIdx.x; j < C; j += blockDim.x) {
-      float t = 0.f;
-      for (int b = 0; b < B; ++b) t = fmaf(ds[(size_t)b * C + i], mean[(size_t)b * C + j], t);
-      dwsca[(size_t)i * C + j] += t;
-    }
-    if (threadIdx.x == 0 && dbsca) {
-      float t = 0.f;
-      for (int b = 0; b < B; ++b) t += ds[(size_t)b * C + i];
-      dbsca[i] += t;
-    }
-  } else {
-    const int b = blockIdx.x - C;
-    for (int j = threadIdx.x; j < C; j += blockDim.x) {
-      float t = 0.f;
-      for (int i = 0; i < C; ++i) t = fmaf(w_sca[(size_t)i * C + j], ds[(size_t)b * C + i], t);
-      dgadd[(size_t)b * C + j] = t * inv_p;
-    }
+                                                          int B, int C, float* __restrict__ dwsca,
+                                                          float* __restrict__ dbsca) {
+  const int i = blockIdx.x;
+  for (int j = threadIdx.x; j < C; j += blockDim.x) {
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t = fmaf(ds[(size_t)b * C + i], mean[(size_t)b * C + j], t);
+    dwsca[(size_t)i * C + j] += t;
+  }
+  if (threadIdx.x == 0 && dbsca) {
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t += ds[(size_t)b * C + i];
+    dbsca[i] += t;
   }
 }
 
@@ -1074,11 +1121,11 @@ extern "C" int tdr_colsum(const void* x_bf16, long long ld, long long rows, int 
                           const int* c_map, int accumulate, float* workspace, cudaStream_t stream) {
   TDR_CHECK_ARG(x_bf16 && out && workspace && rows > 0 && C > 0, "tdr_colsum: bad arguments");
   TDR_CHECK_ARG(C % 8 == 0 && ld % 8 == 0 && ((uintptr_t)x_bf16 & 15) == 0, "tdr_colsum: C, ld multiples of 8, 16 B aligned");
-  int nblk = (int)((rows + 7) / 8 < kRedBlocks ? (rows + 7) / 8 : kRedBlocks);
+  int nblk = (int)((rows + 31) / 32 < kRedBlocks ? (rows + 31) / 32 : kRedBlocks);
   dim3 grid(nblk, tdr_cdiv(C / 8, 256));
   colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x_bf16), ld, rows, C, workspace);
   TDR_CHECK_LAUNCH();
-  reduce_parts_kernel<<<tdr_cdiv(C, 256), 256, 0, stream>>>(workspace, nblk, C, out, out_stride, c_map, accumulate, 1.f);
+  reduce_parts_wide_kernel<<<tdr_cdiv(C, 32), dim3(32, 8), 0, stream>>>(workspace, nblk, C, out, out_stride, c_map, accumulate);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
@@ -1306,9 +1353,11 @@ extern "C" int tdr_naf_sca_bwd(const float* raw, int B, int Co, int C, const flo
                                float* dg_add, float* workspace /* B*C floats */, cudaStream_t stream) {
   TDR_CHECK_ARG(raw && w3 && scale && mean && w_sca && dw_sca && dg_add && workspace && B > 0 && Co > 0 && C > 0 && P > 0,
                 "tdr_naf_sca_bwd: bad arguments");
-  naf_sca_ds_kernel<<<tdr_cdiv((long long)B * C, 256), 256, 0, stream>>>(raw, B, Co, C, w3, scale, workspace);
+  naf_sca_ds_kernel<<<dim3(tdr_cdiv(C, 32), B), dim3(32, 8), 0, stream>>>(raw, B, Co, C, w3, scale, workspace);
   TDR_CHECK_LAUNCH();
-  naf_sca_bwd_kernel<<<C + B, 256, 0, stream>>>(workspace, mean, w_sca, B, C, 1.f / (float)P, dw_sca, db_sca, dg_add);
+  naf_sca_dgadd_kernel<<<dim3(tdr_cdiv(C, 32), B), dim3(32, 8), 0, stream>>>(workspace, w_sca, C, 1.f / (float)P, dg_add);
+  TDR_CHECK_LAUNCH();
+  naf_sca_bwd_kernel<<<C, 256, 0, stream>>>(workspace, mean, B, C, dw_sca, db_sca);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -1024,47 +1024,46 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const bf16* __restric
   }
 }
 
-// Stage 2 + SCA + fold (N:192-196,225-229): s = W_sca * mean + b_sca;  Weff[b][co][ci] = rowscale[co] * W3[co][ci] * s[b][ci]
-// grid (ceil(Co/16), B), block 256
-__global__ void __launch_bounds__(256) sca_fold_kernel(const float* __restrict__ partial, int chunks, long long P, int C,
-                                                       const float* __restrict__ w_sca, const float* __restrict__ b_sca,
+// Stage 2 (N:192-196): mean[b][c] = sum_chunks partial / P, then s[b][c] = W_sca[c,:] . mean[b] + b_sca[c].
+// One warp per (b, c): the W_sca row is read coalesced, the mean vector comes from global (L1/L2 resident).
+__global__ void __launch_bounds__(256) sca_mean_kernel(const float* __restrict__ partial, int chunks, long long P, int C,
+                                                       int B, float* __restrict__ mean) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * C) return;
+  const int b = idx / C, c = idx % C;
+  float t = 0.f;
+  for (int ch = 0; ch < chunks; ++ch) t += partial[((size_t)b * chunks + ch) * C + c];
+  mean[idx] = t / (float)P;
+}
+
+__global__ void __launch_bounds__(256) sca_vec_kernel(const float* __restrict__ mean, const float* __restrict__ w_sca,
+                                                      const float* __restrict__ b_sca, int B, int C,
+                                                      float* __restrict__ s) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B * C) return;
+  const int b = warp / C, c = warp % C;
+  const float* wr = w_sca + (size_t)c * C;
+  const float* m = mean + (size_t)b * C;
+  float t = 0.f;
+  for (int k = lane; k < C; k += 32) t = fmaf(wr[k], m[k], t);
+  t = warp_sum(t);
+  if (lane == 0) s[warp] = t + (b_sca ? b_sca[c] : 0.f);
+}
+
+// Stage 3 (N:225-229 folded): Weff[b][co][ci] = rowscale[co] * W3[co][ci] * s[b][ci]  (+ transposed twin for the dgrad)
+__global__ void __launch_bounds__(256) sca_fold_kernel(const float* __restrict__ s, int B, int C,
                                                        const float* __restrict__ w3, int Co,
                                                        const float* __restrict__ rowscale, bf16* __restrict__ weff,
-                                                       long long weff_ld, float* __restrict__ mean_out,
-                                                       float* __restrict__ s_out, bf16* __restrict__ weff_t,
+                                                       long long weff_ld, bf16* __restrict__ weff_t,
                                                        long long weff_t_ld) {
-  extern __shared__ float sm[];       // mean[C], s[C]
-  float* mean = sm;
-  float* s = sm + C;
-  const int b = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float t = 0.f;
-    for (int ch = 0; ch < chunks; ++ch) t += partial[((size_t)b * chunks + ch) * C + c];
-    mean[c] = t / (float)P;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int c = warp; c < C; c += blockDim.x >> 5) {
-    float t = 0.f;
-    for (int k = lane; k < C; k += 32) t = fmaf(w_sca[(size_t)c * C + k], mean[k], t);
-    t = warp_sum(t);
-    if (lane == 0) s[c] = t + (b_sca ? b_sca[c] : 0.f);
-  }
-  __syncthreads();
-  if (blockIdx.x == 0 && mean_out) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      mean_out[(size_t)b * C + c] = mean[c];
-      s_out[(size_t)b * C + c] = s[c];
-    }
-  }
-  const int co0 = blockIdx.x * 16;
-  for (int i = threadIdx.x; i < 16 * C; i += blockDim.x) {
-    const int co = co0 + i / C, ci = i % C;
-    if (co < Co) {
-      const bf16 v = __float2bfloat16(w3[(size_t)co * C + ci] * s[ci] * (rowscale ? rowscale[co] : 1.f));
-      weff[((size_t)b * Co + co) * weff_ld + ci] = v;
-      if (weff_t) weff_t[((size_t)b * C + ci) * weff_t_ld + co] = v;      // transposed copy: dgrad operand
-    }
+  const long long total = (long long)B * Co * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % C);
+    const long long r = i / C;
+    const int co = (int)(r % Co), b = (int)(r / Co);
+    const bf16 v = __float2bfloat16(w3[(size_t)co * C + ci] * s[(size_t)b * C + ci] * (rowscale ? rowscale[co] : 1.f));
+    weff[((size_t)b * Co + co) * weff_ld + ci] = v;
+    if (weff_t) weff_t[((size_t)b * C + ci) * weff_t_ld + co] = v;      // transposed copy: dgrad operand
   }
 }
 }  // namespace
@@ -1088,7 +1087,7 @@ static int naf_pool_chunks(long long P) {
 
 extern "C" size_t tdr_naf_sca_workspace_bytes(int B, long long P, int C) {
   if (B <= 0 || P <= 0 || C <= 0) return 0;
-  return (size_t)B * naf_pool_chunks(P) * C * sizeof(float);
+  return ((size_t)B * naf_pool_chunks(P) * C + 2 * (size_t)B * C) * sizeof(float);   // pool partials + mean + s
 }
 
 extern "C" int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long long P, int C, const float* w_sca,
@@ -1102,13 +1101,18 @@ extern "C" int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long lo
                 "tdr_naf_sca_fold: bad dims");
   TDR_CHECK_ARG(C <= 6144, "tdr_naf_sca_fold: C too large");
   const int chunks = naf_pool_chunks(P);
+  float* mean = mean_out ? mean_out : workspace + (size_t)B * chunks * C;
+  float* svec = s_out ? s_out : workspace + (size_t)B * chunks * C + (size_t)B * C;
   dim3 g1(chunks, B);
   pool_partial_kernel<<<g1, 256, 0, stream>>>(reinterpret_cast<const bf16*>(g_bf16), ld, P, C, chunks, workspace);
   TDR_CHECK_LAUNCH();
-  dim3 g2((Co + 15) / 16, B);
-  sca_fold_kernel<<<g2, 256, 2 * C * sizeof(float), stream>>>(workspace, chunks, P, C, w_sca, b_sca, w3, Co, rowscale,
-                                                              reinterpret_cast<bf16*>(weff_bf16), weff_ld, mean_out, s_out,
-                                                              reinterpret_cast<bf16*>(weff_t_bf16), weff_t_ld);
+  sca_mean_kernel<<<tdr_cdiv((long long)B * C, 256), 256, 0, stream>>>(workspace, chunks, P, C, B, mean);
+  TDR_CHECK_LAUNCH();
+  sca_vec_kernel<<<tdr_cdiv((long long)B * C * 32, 256), 256, 0, stream>>>(mean, w_sca, b_sca, B, C, svec);
+  TDR_CHECK_LAUNCH();
+  sca_fold_kernel<<<grid_for((long long)B * Co * C, 256, 8), 256, 0, stream>>>(
+      svec, B, C, w3, Co, rowscale, reinterpret_cast<bf16*>(weff_bf16), weff_ld, reinterpret_cast<bf16*>(weff_t_bf16),
+      weff_t_ld);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
