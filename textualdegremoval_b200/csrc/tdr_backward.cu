@@ -248,8 +248,16 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     const int lci = ci_map ? ci_map[ci] : ci;
     if (lco < 0 || lci < 0) continue;
     const float* p = partials + (size_t)b * nchunks * per + (i % per);
-    float s = 0.f;
-    for (int c = 0; c < nchunks; ++c) s += p[(size_t)c * per];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // independent chains: the chunk loop is L2-latency bound
+    int c = 0;
+    for (; c + 3 < nchunks; c += 4) {
+      s0 += p[(size_t)c * per];
+      s1 += p[(size_t)(c + 1) * per];
+      s2 += p[(size_t)(c + 2) * per];
+      s3 += p[(size_t)(c + 3) * per];
+    }
+    for (; c < nchunks; ++c) s0 += p[(size_t)c * per];
+    const float s = (s0 + s1) + (s2 + s3);
     float* o = out + b * s_b + lco * s_co + lci * s_ci + t * s_t;
     *o = (accumulate ? *o : 0.f) + scale * s;
   }
@@ -523,8 +531,16 @@ __global__ void __launch_bounds__(256) dw_wgrad_reduce_kernel(const float* __res
   const int lc = map ? map[c] : c;
   if (lc < 0) return;
   if (t == 9 && !db) return;
-  float s = 0.f;
-  for (int p = 0; p < nparts; ++p) s += partials[((size_t)p * 10 + t) * C + c];
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int p = 0;
+  for (; p + 3 < nparts; p += 4) {
+    s0 += partials[((size_t)p * 10 + t) * C + c];
+    s1 += partials[((size_t)(p + 1) * 10 + t) * C + c];
+    s2 += partials[((size_t)(p + 2) * 10 + t) * C + c];
+    s3 += partials[((size_t)(p + 3) * 10 + t) * C + c];
+  }
+  for (; p < nparts; ++p) s0 += partials[((size_t)p * 10 + t) * C + c];
+  const float s = (s0 + s1) + (s2 + s3);
   float* o = t == 9 ? db + lc : dw + lc * 9 + t;
   *o = (accumulate ? *o : 0.f) + s;
 }
@@ -666,17 +682,25 @@ __global__ void __launch_bounds__(256, 3) rownorm_bwd_kernel(const float* __rest
   }
 }
 
-// dweight[c] (+)= sum_blk partials[blk][c];  dbias[c] (+)= sum_blk partials[blk][C + c]
+// dweight[c] (+)= sum_blk partials[blk][c];  dbias[c] (+)= sum_blk partials[blk][C + c].  grid (ceil(2C/32)), block (32, 8):
+// the partial rows (up to 444) are split over the 8 warps; fixed order.
 __global__ void __launch_bounds__(256) rownorm_bwd_reduce_kernel(const float* __restrict__ partials, int nblk, int C,
                                                                  float* __restrict__ dweight, float* __restrict__ dbias,
                                                                  int accumulate) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 2 * C) return;
+  __shared__ float red[8][32];
+  const int idx = blockIdx.x * 32 + threadIdx.x, ty = threadIdx.y;
+  float s = 0.f;
+  if (idx < 2 * C)
+    for (int p = ty; p < nblk; p += 8) s += partials[(size_t)p * 2 * C + idx];
+  red[ty][threadIdx.x] = s;
+  __syncthreads();
+  if (ty != 0 || idx >= 2 * C) return;
   float* o = idx < C ? dweight + idx : (dbias ? dbias + (idx - C) : nullptr);
   if (!o) return;
-  float s = 0.f;
-  for (int p = 0; p < nblk; ++p) s += partials[(size_t)p * 2 * C + idx];
-  *o = (accumulate ? *o : 0.f) + s;
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+  *o = (accumulate ? *o : 0.f) + t;
 }
 
 // ------------------------------------------------------------------------------------------------ gate backward
@@ -1220,7 +1244,7 @@ extern "C" int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf
   TDR_CHECK_LAUNCH();
   if (want_w) {
     // partials rows are [dweight(C) | dbias(C)] per block
-    rownorm_bwd_reduce_kernel<<<tdr_cdiv(2 * C, 256), 256, 0, stream>>>(workspace, blocks, C, dweight, dbias, accumulate);
+    rownorm_bwd_reduce_kernel<<<tdr_cdiv(2 * C, 32), dim3(32, 8), 0, stream>>>(workspace, blocks, C, dweight, dbias, accumulate);
     TDR_CHECK_LAUNCH();
   }
   return TDR_OK;
