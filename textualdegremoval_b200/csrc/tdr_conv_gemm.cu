@@ -42,10 +42,12 @@ struct ConvGemmArgs {
   int BN, n_tiles, kchunks;
   int w_batched;                // weights tensor map's 3rd coordinate = b*taps + tap
   const int* origin;            // optional [B][3] = (image, y0, x0)
-  int total_tiles;
+  int total_tiles;              // m_tiles * n_tiles
+  int m_tiles;                  // pixel tiles
+  int by_pixel;                 // item order, see conv_item(): unequal n tiles (Co = 288 -> 192 + 96) must not pile up on
+                                // half of the CTAs (148 is even)
   uint32_t tmem_cols;
   int nacc;                     // TMEM accumulator buffers in flight (2..4): nacc * BN <= 512 columns
-  int pf_dist;                  // L2 prefetch distance of the A operand, in this CTA's future tiles (0 = off)
   // epilogue
   const float* bias;            // [Co] or null
   const float* rowscale;        // [B*OH*OW] or null
@@ -66,6 +68,21 @@ struct ConvGemmArgs {
   int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
   int epi_bufs;                 // staging buffers per epilogue warp (1 or 2)
 };
+
+// it-th work item of this CTA -> (pixel tile, n tile).  by_pixel: CTA c owns pixel tiles c, c + grid, ... and walks ALL n tiles
+// of each in turn (balanced even when the n tiles are unequal, and the A tile is re-used from L2); otherwise (fewer pixel
+// tiles than SMs: ViT / mapper linears) items are dealt round-robin so that every SM gets work.
+__device__ __forceinline__ bool conv_item(const ConvGemmArgs& a, int it, int& mt, int& nt) {
+  if (a.by_pixel) {
+    mt = blockIdx.x + (it / a.n_tiles) * gridDim.x;
+    nt = it % a.n_tiles;
+    return mt < a.m_tiles;
+  }
+  const int tile = blockIdx.x + it * gridDim.x;
+  mt = tile / a.n_tiles;
+  nt = tile % a.n_tiles;
+  return tile < a.total_tiles;
+}
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == 1) return fmaxf(x, 0.f);
@@ -145,34 +162,15 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
           for (int tap = 0; tap < taps; ++tap)
             tma_load_3d(smem_b + (kc * taps + tap) * b_bytes, &map_w, wfull, kc * kChunkK, 0, tap);
       }
-      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-        const int nt = tile % a.n_tiles;
-        const int mt = tile / a.n_tiles;
+      for (int sq = 0;; ++sq) {
+        int mt, nt;
+        if (!conv_item(a, sq, mt, nt)) break;
         const int b = mt / tiles_per_img;
         const int r = mt % tiles_per_img;
         const int oy0 = (r / a.tiles_x) * a.TH;
         const int ox0 = (r % a.tiles_x) * a.TW;
         int img = b, org_y = 0, org_x = 0;
         if (a.origin) { img = a.origin[3 * b]; org_y = a.origin[3 * b + 1]; org_x = a.origin[3 * b + 2]; }
-        // The smem ring holds ~2 tiles of A: not enough bytes in flight to cover DRAM latency.  Pull the A
-        // boxes of a tile pf_dist iterations ahead into L2 now, so that its TMA loads later are L2 hits.
-        if (a.pf_dist > 0 && !a.origin && nt == 0) {
-          const long long ft = (long long)tile + (long long)a.pf_dist * gridDim.x;
-          if (ft < a.total_tiles) {
-            const int fmt = (int)(ft / a.n_tiles);
-            const int fb = fmt / tiles_per_img, fr = fmt % tiles_per_img;
-            const int foy = (fr / a.tiles_x) * a.TH, fox = (fr % a.tiles_x) * a.TW;
-            for (int kc = 0; kc < a.kchunks; ++kc) {
-              if (a.halo) {
-                tma_prefetch_4d(&map_a, kc * kChunkK, fox - a.pad, foy - a.pad, fb);
-              } else {
-                for (int tap = 0; tap < taps; ++tap)
-                  tma_prefetch_4d(&map_a, kc * kChunkK, fox * a.stride - a.pad + (tap % a.KW) * a.dil,
-                                  foy * a.stride - a.pad + (tap / a.KW) * a.dil, fb);
-              }
-            }
-          }
-        }
         if (a.halo) {
           for (int kc = 0; kc < a.kchunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -203,7 +201,9 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+    for (;; ++it) {
+      int mt_, nt_;
+      if (!conv_item(a, it, mt_, nt_)) break;
       const int acc = it % a.nacc;
       const uint32_t acc_phase = (it / a.nacc) & 1;
       mbar_wait(&tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
@@ -275,11 +275,11 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     uint32_t rphase[2] = {0, 0};             // parity of this warp's residual-tile barriers
     int store_cnt = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++it) {
+    for (;; ++it) {
+      int mt, nt;
+      if (!conv_item(a, it, mt, nt)) break;
       const int acc = it % a.nacc;
       const uint32_t acc_phase = (it / a.nacc) & 1;
-      const int nt = tile % a.n_tiles;
-      const int mt = tile / a.n_tiles;
       const int b = mt / tiles_per_img;
       const int r = mt % tiles_per_img;
       const int oy = (r / a.tiles_x) * a.TH + my;
@@ -782,7 +782,11 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     else break;
   }
   TDR_CHECK_ARG(smem_need() <= 227 * 1024, "tdr_conv_gemm: shared-memory plan does not fit");
-  a.total_tiles = d->B * a.tiles_y * a.tiles_x * a.n_tiles;
+  a.m_tiles = d->B * a.tiles_y * a.tiles_x;
+  a.total_tiles = a.m_tiles * a.n_tiles;
+  // by_pixel only pays when the n tiles are UNEQUAL (its scheduling granule is n_tiles items, so the tail gets coarser) and
+  // there are many pixel tiles per SM
+  a.by_pixel = (a.n_tiles > 1 && d->Co % a.BN != 0 && a.m_tiles >= 8 * tdr_num_sms()) ? 1 : 0;
   // accumulator ring: as many BN-column buffers as fit in the 512 TMEM columns (2..4) -- a deeper ring keeps more
   // tiles between the MMA issuer and the epilogue in flight
   a.nacc = 512 / a.BN;
@@ -795,8 +799,6 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   uint32_t cols = 32;
   while (cols < (uint32_t)(a.nacc * a.BN)) cols <<= 1;
   a.tmem_cols = cols;
-  a.pf_dist = 0;
-  if (const char* e = getenv("TDR_CONV_PF")) a.pf_dist = atoi(e);                // tuning knob (experiments only)
 
   if (d->impl == 1) {
     const long long total = (long long)a.B * OH * OW * a.Co;

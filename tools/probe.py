@@ -96,6 +96,13 @@ PROBES = {
     "qkv96_in128": lambda: conv(4, 512, 512, 96, 288, ld_in=128),
     "qkv96_both": lambda: conv(4, 512, 512, 96, 288, ld_out=320, ld_in=128),
     "qkv48_ld192": lambda: conv(4, 512, 512, 48, 144, ld_out=192, ld_in=64),
+    "co64": lambda: conv(4, 512, 512, 96, 64),
+    "co128": lambda: conv(4, 512, 512, 96, 128),
+    "co192": lambda: conv(4, 512, 512, 96, 192),
+    "co256": lambda: conv(4, 512, 512, 96, 256),
+    "co384": lambda: conv(4, 512, 512, 96, 384),
+    "co64k64": lambda: conv(4, 512, 512, 64, 64),
+    "co256k64": lambda: conv(4, 512, 512, 64, 256),
     "pin96": lambda: conv(4, 512, 512, 96, 512),
     "qkv96": lambda: conv(4, 512, 512, 96, 288),
     "pout256": lambda: conv(4, 512, 512, 256, 96, want="f32", res=True),
