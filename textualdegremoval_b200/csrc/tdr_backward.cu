@@ -1214,10 +1214,18 @@ extern "C" int tdr_rownorm_bwd(const float* x, long long x_ld, const void* dy_bf
   const int nvec = C / 4;
   int G = 1;
   while (G < 32 && (nvec + G - 1) / G > 4) G <<= 1;
+  if (const char* e = getenv("TDR_LNB_G")) {                                     // tuning knob (experiments only)
+    const int v = atoi(e);
+    if ((v == 2 || v == 4 || v == 8 || v == 16 || v == 32) && (nvec + v - 1) / v <= 32) G = v;
+  }
   const int nv = (nvec + G - 1) / G;
   const int slots = 8 * (32 / G);
   long long nb = (rows + slots - 1) / slots;
-  const long long cap = 3LL * tdr_num_sms() < 3 * kRedBlocks ? 3LL * tdr_num_sms() : 3 * kRedBlocks;   // one full wave at 3 CTAs / SM
+  long long cap = 3LL * tdr_num_sms() < 3 * kRedBlocks ? 3LL * tdr_num_sms() : 3 * kRedBlocks;   // one full wave at 3 CTAs / SM
+  if (const char* e = getenv("TDR_LNB_WAVES")) {
+    const long long v = atoll(e) * tdr_num_sms();
+    if (v >= tdr_num_sms() && v <= 3 * kRedBlocks) cap = v;
+  }
   const int blocks = (int)(nb < cap ? nb : cap);
   const size_t smem = want_w ? (size_t)2 * slots * C * sizeof(float) : 0;
   TDR_CHECK_ARG(smem <= 200 * 1024, "tdr_rownorm_bwd: C too large for the weight-gradient reduction");
