@@ -249,25 +249,26 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
   }
 }
 
-// Stage 2: grid (ceil(C/32), heads, B).  Weff[b][co][h*c + j] = sum_i W_out[co][h*c + i] * attn[b,h,i,j]
+// Stage 2: grid (ceil(C/kFoldRows), heads, B).  Weff[b][co][h*c + j] = sum_i W_out[co][h*c + i] * attn[b,h,i,j]
+constexpr int kFoldRows = 8;      // output rows per CTA: small, so that even one (sample, head) spreads over C/8 CTAs
 __global__ void __launch_bounds__(256) mdta_fold_kernel(const float* __restrict__ attn, int C, int heads,
                                                         const float* __restrict__ w_out, bf16* __restrict__ weff,
                                                         long long weff_ld, bf16* __restrict__ weff_t) {
   extern __shared__ float sm[];
   const int c = C / heads;
   const int h = blockIdx.y, b = blockIdx.z;
-  const int co0 = blockIdx.x * 32;
+  const int co0 = blockIdx.x * kFoldRows;
   float* a = sm;                   // [c][c]
-  float* wsm = sm + c * c;         // [32][c]
+  float* wsm = sm + c * c;         // [kFoldRows][c]
   const float* src = attn + (size_t)(b * heads + h) * c * c;
   for (int t = threadIdx.x; t < (c * c) >> 2; t += blockDim.x)          // c % 8 == 0: float4 staging
     reinterpret_cast<float4*>(a)[t] = reinterpret_cast<const float4*>(src)[t];
-  for (int t = threadIdx.x; t < 32 * c; t += blockDim.x) {
+  for (int t = threadIdx.x; t < kFoldRows * c; t += blockDim.x) {
     const int co = co0 + t / c;
     wsm[t] = co < C ? w_out[(size_t)co * C + h * c + t % c] : 0.f;
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < 32 * c; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < kFoldRows * c; idx += blockDim.x) {
     const int r = idx / c, j = idx % c;
     if (co0 + r >= C) break;
     const float* wr = wsm + r * c;
@@ -326,13 +327,13 @@ extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, i
     mdta_softmax_kernel<<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out);
     TDR_CHECK_LAUNCH();
   }
-  const size_t smem = ((size_t)p.c * p.c + 32 * p.c) * sizeof(float);
+  const size_t smem = ((size_t)p.c * p.c + kFoldRows * p.c) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     TDR_CHECK_CUDA(cudaFuncSetAttribute(mdta_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  dim3 grid((C + 31) / 32, heads, B);
+  dim3 grid((C + kFoldRows - 1) / kFoldRows, heads, B);
   mdta_fold_kernel<<<grid, 256, smem, stream>>>(attn_ws, C, heads, w_out, reinterpret_cast<bf16*>(weff_bf16), weff_ld,
                                             reinterpret_cast<bf16*>(weff_t_bf16));
   TDR_CHECK_LAUNCH();
