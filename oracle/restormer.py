@@ -180,9 +180,10 @@ def crop_windows(f, y1, x1, size_y, size_x, s):
     """W_s(b)[c,u,v] = f[n, c, y1*s+u, x1*s+v]  (:717-734, :835-852).  -> [N*p2, C, size_y*s, size_x*s]"""
     n, c = f.shape[:2]
     out = []
+    y1l, x1l = y1.tolist(), x1.tolist()            # one host read (the reference loops per block, :717-734)
     for i in range(n):
         for b in range(y1.shape[1]):
-            yy, xx = int(y1[i, b]) * s, int(x1[i, b]) * s
+            yy, xx = int(y1l[i][b]) * s, int(x1l[i][b]) * s
             out.append(f[i, :, yy: yy + size_y * s, xx: xx + size_x * s])
     return torch.stack(out, 0)
 
@@ -208,11 +209,12 @@ def transfer(win_s, index, att, s, d_x):
     m, c = win_s.shape[:2]
     k_y, k_x = index.shape[1:]
     jy, jx = index // d_x, index % d_x
-    ys = torch.arange(k_y * s)
-    xs = torch.arange(k_x * s)
-    acc = torch.zeros(m, c, k_y * s, k_x * s)
-    cnt = torch.zeros(1, 1, k_y * s, k_x * s)
-    mi = torch.arange(m).view(m, 1, 1)
+    dev = win_s.device
+    ys = torch.arange(k_y * s, device=dev)
+    xs = torch.arange(k_x * s, device=dev)
+    acc = torch.zeros(m, c, k_y * s, k_x * s, device=dev, dtype=win_s.dtype)
+    cnt = torch.zeros(1, 1, k_y * s, k_x * s, device=dev)
+    mi = torch.arange(m, device=dev).view(m, 1, 1)
     for oy in (-1, 0, 1):
         by = ys // s + oy
         vy = (by >= 0) & (by < k_y)

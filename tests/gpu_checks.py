@@ -126,6 +126,27 @@ def check_dwconv():
         ref = _dw_ref(x, w, b, gate)
         y = ops.dwconv3x3(nhwc(x.to(BF16)), ops.pack_dw_weight(w.to(DEV)), b.to(DEV) if bias else None, gate)
         out.append(result(f"dwconv_C{C_}_{H}x{W}_g{gate}", nchw(y), ref, 1e-2))
+    # GELU alone: identity stencil, x2 = 1, x1 sweeps every bf16 value in [-9, 9] -> the kernel's gate must equal the
+    # fp64 erf GELU (F.gelu default, R:239) to within one bf16 ulp of the result (rounding ties), tails included
+    bits = torch.arange(0, 1 << 16, dtype=torch.int32).to(torch.int16).view(torch.bfloat16).float()
+    vals = bits[torch.isfinite(bits) & (bits.abs() <= 9.0)]
+    n = vals.numel()
+    Hh = (n + 63) // 64
+    x1 = torch.zeros(Hh * 64)
+    x1[:n] = vals
+    x = torch.stack([x1.view(1, Hh, 64).expand(32, Hh, 64), torch.ones(32, Hh, 64)], 0).reshape(1, 64, Hh, 64)
+    w = torch.zeros(64, 1, 3, 3)
+    w[:, 0, 1, 1] = 1.0
+    y = ops.dwconv3x3(nhwc(x.to(BF16)), ops.pack_dw_weight(w.to(DEV)), None, 1)
+    got = nchw(y).float().cpu()[0, 0].reshape(-1)[:n].double()
+    exact = vals.double() * 0.5 * torch.special.erfc(-vals.double() / 2 ** 0.5)
+    ulp = torch.maximum(exact.abs(), torch.tensor(2.0 ** -126, dtype=torch.float64))
+    ulp = 2.0 ** (torch.floor(torch.log2(ulp)) - 7)
+    ulp = torch.clamp(ulp, min=2e-6)             # fp32 evaluations (torch's included) lose the far negative tail
+    worst = float(((got - exact).abs() / ulp).max())
+    abs_err = float((got - exact.to(BF16).double()).abs().max())
+    out.append(dict(name="dwconv_gelu_all_bf16_inputs_ulp", ok=worst <= 1.0, max_err=worst, ref_scale=1.0, tol=1.0,
+                    note=f"{n} inputs, worst error in units of max(bf16 ulp of the exact result, 2e-6); max |got - bf16(exact)| = {abs_err:.3e}"))
     return out
 
 
