@@ -77,10 +77,23 @@ typedef struct tdr_conv_gemm_desc {
   long long out_bf16_ld;
   int store_mode; /* 0 plain; 1 PixelUnshuffle(2) R:377; 2 PixelShuffle(2) R:388 */
   int impl;       /* 0 = tcgen05 (product path); 1 = SIMT restatement (tests/debug only) */
+  /* Optional fused LayerNorm of the OUTPUT rows: ln_out = LN(out) in bf16, i.e. the norm1 / norm2 that follows on the
+   * residual stream (TransformerBlock R:318-331) folded into the conv that produces it, saving the norm kernel's read
+   * of the fp32 stream.  ln_mode as tdr_rownorm (0 off, 1 WithBias R:189-205, 2 BiasFree R:172-186).  Supported with
+   * impl 0, store_mode 0, fp32 output only, an fp32 res2, no res1, Co <= 128, 16 B-aligned ln_out rows; anything else
+   * is rejected with TDR_EINVAL (tdr_conv_gemm_ln_supported tells beforehand). */
+  int ln_mode;
+  float ln_eps;
+  const float* ln_weight; /* fp32 [Co] */
+  const float* ln_bias;   /* fp32 [Co] (WithBias) or NULL */
+  void* ln_out_bf16;
+  long long ln_out_ld;
 } tdr_conv_gemm_desc;
 int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream);
+/* 1 when the fused output LayerNorm of the descriptor (see ln_mode) can run, 0 otherwise; no launch. */
+int tdr_conv_gemm_ln_supported(const tdr_conv_gemm_desc* d);
 /* ABI self-description for binding checks: writes sizeof(desc) and the offsets of weight, origin, bias, scale_ptr, res1,
- * res2, out_f32, out_bf16, impl into out[0..9]. */
+ * res2, out_f32, out_bf16, impl, ln_mode, ln_weight, ln_out_bf16 into out[0..12]. */
 void tdr_conv_gemm_desc_layout(int* out);
 
 /* Small-channel direct 3x3 convs (SIMT): Ci <= 8 inputs (patch_embed R:362, masa_enc.conv_L1 R:106) read fp32 NHWC;

@@ -257,6 +257,47 @@ CONV_CASES = [
 ]
 
 
+def check_conv_ln():
+    """1x1 conv + residual with the LayerNorm of the finished rows emitted by the same epilogue (norm1 / norm2 of
+    R:318-331 folded into the producing conv): fp32 rows must equal the plain epilogue's, the bf16 LN output must match
+    the fp32 LayerNorm of those rows, in place (out == res2) as the block schedule uses it, many tiles per CTA."""
+    from oracle import restormer as O
+    ops = _ops()
+    out = []
+    cases = [dict(Ci=96, Co=96, H=16, W=16, mode=1), dict(Ci=256, Co=96, H=20, W=24, mode=2, bias=True),
+             dict(Ci=128, Co=48, H=16, W=32, mode=1, bias=True), dict(Ci=48, Co=48, H=9, W=13, mode=2, B=3),
+             dict(Ci=96, Co=96, H=16, W=16, mode=1, batched=True, bias=True), dict(Ci=64, Co=128, H=8, W=40, mode=1),
+             dict(Ci=64, Co=64, H=16, W=16, mode=2), dict(Ci=32, Co=8, H=16, W=16, mode=1, B=1),
+             dict(Ci=256, Co=96, H=160, W=192, mode=1, bias=True, B=2, inplace=True),
+             dict(Ci=96, Co=48, H=128, W=256, mode=2, B=2, inplace=True, batched=True)]
+    for c in cases:
+        B, Ci, Co, H, W, mode = c.get("B", 2), c["Ci"], c["Co"], c["H"], c["W"], c["mode"]
+        batched = c.get("batched", False)
+        x = q(rnd(B, Ci, H, W, seed=H + Ci))
+        nb = B if batched else 1
+        w = q(rnd(nb, Co, Ci, 1, 1, seed=Co) * (1.0 / Ci ** 0.5))
+        b = rnd(Co, seed=11) * 0.2 if c.get("bias") else None
+        r2 = rnd(B, Co, H, W, seed=14) * 2.0 + 0.7                 # non-zero channel mean: WithBias must subtract it
+        y = torch.cat([F.conv2d(x[i:i + 1], w[i if batched else 0], b) for i in range(B)], 0) + r2
+        lw, lb = rnd(Co, seed=15) * 0.5 + 1.0, rnd(Co, seed=16) * 0.3
+        ref_ln = O.layernorm_c(y, lw, lb if mode == 1 else None)
+        wp = torch.cat([ops.pack_conv_weight(w[i].to(DEV)) for i in range(nb)], 0)
+        res = nhwc(r2)
+        ln_out = ops.rows16(B, H, W, Co, DEV)
+        ln_out.fill_(float("nan"))
+        o32 = res if c.get("inplace") else None
+        o32, _ = ops.conv_gemm(nhwc(x.to(BF16)), wp, Co, bias=b.to(DEV) if b is not None else None, res2=res,
+                               out_f32=o32, want="f32", w_batched=batched,
+                               ln=(mode, lw.to(DEV), lb.to(DEV), 1e-5, ln_out))
+        name = f"Ci{Ci}_Co{Co}_{H}x{W}_m{mode}" + ("_wb" if batched else "") + ("_inplace" if c.get("inplace") else "")
+        out.append(result(f"conv_ln_{name}_f32", nchw(o32), y, 2e-3))
+        out.append(result(f"conv_ln_{name}_ln", nchw(ln_out), ref_ln, 1e-2))
+        # against the standalone norm kernel on the same fp32 rows: same bf16 values up to rounding of the statistics
+        alone = ops.rownorm(o32, mode, lw.to(DEV), lb.to(DEV), 1e-5)
+        out.append(result(f"conv_ln_{name}_vs_rownorm", nchw(ln_out), nchw(alone).float(), 8e-3))
+    return out
+
+
 def check_conv_simt():
     out = []
     for c in CONV_CASES:
@@ -808,7 +849,7 @@ def check_block_bwd():
         blk = blk.to(DEV)
         p = TR.prep_block_train(blk, A._prep_block(blk))
         tape = []
-        y = TR.run_block_train(nhwc(x.detach()), p, tape)
+        y, _ = TR.run_block_train(nhwc(x.detach()), p, tape)
         tag = f"d{dim}_h{heads}_{ln}_b{int(bias)}_f{int(fusion)}"
         out.append(result(f"block_train_fwd_{tag}", nchw(y), ref, 1.5e-2))
         G = TR.Grads()
@@ -1126,6 +1167,7 @@ CHECKS = {
     "conv_tc_basic": check_conv_tc_basic,
     "conv_tc": check_conv_tc,
     "conv_origin": check_conv_origin,
+    "conv_ln": check_conv_ln,
     "mdta": check_mdta,
     "block": check_block,
     "masa": check_masa,

@@ -22,10 +22,11 @@ def test_header_symbols_exported(tdr_lib):
 
 def test_desc_layout_matches_ctypes(tdr_lib):
     from textualdegremoval_b200.lib import ConvGemmDesc as D
-    out = (C.c_int * 10)()
+    out = (C.c_int * 13)()
     tdr_lib.tdr_conv_gemm_desc_layout(out)
     mine = [C.sizeof(D)] + [getattr(D, f).offset for f in
-                            ("weight", "origin", "bias", "scale_ptr", "res1", "res2", "out_f32", "out_bf16", "impl")]
+                            ("weight", "origin", "bias", "scale_ptr", "res1", "res2", "out_f32", "out_bf16", "impl",
+                             "ln_mode", "ln_weight", "ln_out_bf16")]
     assert list(out) == mine
 
 

@@ -146,19 +146,29 @@ def _prep_block(blk: TransformerBlock, train=False):
 
 
 # ----------------------------------------------------------------------------------------------- kernel schedules
-def run_block(x32, p):
+def _ln_fusable(p):
+    """Plain (non Res-fusion) blocks whose width fits the conv epilogue's fused LayerNorm (ops.conv_ln_ok)."""
+    return p["alpha"] is None and ops.conv_ln_ok(p["C"])
+
+
+def run_block(x32, p, xn=None, nxt=None):
     """One (Res-fusion) transformer block on the fp32 residual stream x32 (NHWC view), updated IN PLACE.
 
     Reference :318-331 / :334-353.  Kernel sequence: LN -> qkv 1x1 (tcgen05) -> depthwise 3x3 -> Gram (tcgen05) ->
     softmax+fold -> attn.v.project_out + residual (tcgen05) -> LN -> project_in (tcgen05) -> depthwise 3x3 + GELU gate
-    -> project_out + residual (tcgen05).
+    -> project_out + residual (tcgen05).  For C <= 128 the two convs that finish a residual row also write the
+    LayerNorm that follows it (norm2 of this block; norm1 of ``nxt``, the next block of the stack), so the norm
+    kernels' re-read of the fp32 stream disappears: ``xn`` is that already-normalised input when the producer made it.
+    Returns the normalised input for ``nxt`` (or None when ``nxt`` has to run its own norm1).
     """
     C_, heads, hp = p["C"], p["heads"], p["hp"]
     fusion = p["alpha"] is not None
+    fuse_ln = _ln_fusable(p)
     B, H, W, _ = x32.shape
     dev = x32.device
     # bf16 operands with 128 B-aligned row pitch (ops.rows16): C = 48 / 96 rows would straddle lines otherwise
-    xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5, out=ops.rows16(B, H, W, C_, dev))
+    if xn is None:
+        xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5, out=ops.rows16(B, H, W, C_, dev))
     _, qkv = ops.conv_gemm(xn, p["w_qkv"], 3 * C_, bias=p["b_qkv"], out_bf16=ops.rows16(B, H, W, 3 * C_, dev))
     qkv = ops.dwconv3x3(qkv, p["w_qkv_dw"], p["b_qkv_dw"], out=ops.rows16(B, H, W, 3 * C_, dev))
     weff = ops.mdta_weff(qkv, C_, heads, p["temp"], p["w_po"])
@@ -166,21 +176,30 @@ def run_block(x32, p):
     if fusion:
         x1, _ = ops.conv_gemm(v, weff, C_, Ci=C_, bias=p["b_po"], res2=x32, want="f32", w_batched=True)
     else:
-        ops.conv_gemm(v, weff, C_, Ci=C_, bias=p["b_po"], res2=x32, out_f32=x32, w_batched=True)
+        ln2 = (p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5, xn) if fuse_ln else None     # xn1 is consumed: reuse it
+        ops.conv_gemm(v, weff, C_, Ci=C_, bias=p["b_po"], res2=x32, out_f32=x32, w_batched=True, ln=ln2)
         x1 = x32
-    xn = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5, out=xn)
+    if fusion or not fuse_ln:
+        xn = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5, out=xn)
     _, hid = ops.conv_gemm(xn, p["w_in"], 2 * hp, bias=p["b_in"])
     g = ops.dwconv3x3(hid, p["w_dw"], p["b_dw"], gate=1)
     if fusion:      # out = (x1 + ffn) * alpha + x0
         ops.conv_gemm(g, p["w_out"], C_, bias=p["b_out"], scale_ptr=p["alpha"], res1=x1, res2=x32, out_f32=x32)
-    else:
-        ops.conv_gemm(g, p["w_out"], C_, bias=p["b_out"], res2=x32, out_f32=x32)
-    return x32
+        return None
+    ln1 = None
+    if fuse_ln and nxt is not None and _ln_fusable(nxt) and nxt["C"] == C_:
+        ln1 = (nxt["ln_mode"], nxt["ln1_w"], nxt["ln1_b"], 1e-5, xn)                    # xn2 is consumed: reuse it
+    ops.conv_gemm(g, p["w_out"], C_, bias=p["b_out"], res2=x32, out_f32=x32, ln=ln1)
+    return xn if ln1 is not None else None
 
 
-def run_stack(x32, preps):
-    for p in preps:
-        run_block(x32, p)
+def run_stack(x32, preps, xn=None, nxt=None, tail=None):
+    """Blocks of one level, in place.  ``xn``: LayerNorm of x32 already made by the producer; ``nxt``: first block of the
+    stack that continues on the same stream (its norm1 is then emitted by this stack's last conv and appended to ``tail``)."""
+    for i, p in enumerate(preps):
+        xn = run_block(x32, p, xn, preps[i + 1] if i + 1 < len(preps) else nxt)
+    if tail is not None:
+        tail.append(xn)
     return x32
 
 
@@ -290,8 +309,9 @@ class _RestormerBase(nn.Module):
         ops.conv_gemm(ops.rownorm(d2, 0), P["up2_1"]["w"], P["up2_1"]["Co"], k=3, pad=1, out_f32=d1[..., :d[0]],
                       store_mode=2)
         ops.copy_rows(e1, dst32=d1[..., d[0]:])
-        run_stack(d1, P["decoder_level1"])
-        run_stack(d1, P["refinement"])
+        tail = []
+        run_stack(d1, P["decoder_level1"], nxt=P["refinement"][0] if P["refinement"] else None, tail=tail)
+        run_stack(d1, P["refinement"], xn=tail[0])
         if self.dual_pixel_task:      # :494-496  out = output(d1 + skip_conv(inp_enc_level1))
             ops.conv_gemm(ops.rownorm(x_in1, 0), P["skip_conv"]["w"], d[1], bias=P["skip_conv"]["b"], res2=d1, out_f32=d1)
         o8, _ = ops.conv_gemm(ops.rownorm(d1, 0), P["output"]["w"], 8, k=3, pad=1, bias=P["output"]["b"], want="f32")

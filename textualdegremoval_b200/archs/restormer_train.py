@@ -77,28 +77,40 @@ def prep_block_train(blk, p):
 
 
 # ----------------------------------------------------------------------------------------------- one block
-def run_block_train(x32, p, tape):
-    """Training forward of one (Res-fusion) transformer block: NOT in place, returns the new residual stream."""
+def run_block_train(x32, p, tape, xn=None, nxt=None):
+    """Training forward of one (Res-fusion) transformer block: NOT in place.  Returns (new residual stream, its
+    LayerNorm for ``nxt`` or None): as in ``run_block`` the convs that finish a residual row also emit the norm that
+    follows (C <= 128), here into the tape's own xn1 / xn2 tensors."""
+    from .restormer_b200_arch import _ln_fusable
     C_, heads, hp = p["C"], p["heads"], p["hp"]
     fusion = p["alpha"] is not None
+    fuse_ln = _ln_fusable(p)
     sv = dict(p=p, x0=x32)
-    xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5)
+    if xn is None:
+        xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5)
     sv["xn1"] = xn                     # kept: operand of the qkv weight gradient (cheaper than re-normalising)
     _, qkv0 = ops.conv_gemm(xn, p["w_qkv"], 3 * C_, bias=p["b_qkv"])
     qkv = ops.dwconv3x3(qkv0, p["w_qkv_dw"], p["b_qkv_dw"])
     weff = ops.mdta_weff(qkv, C_, heads, p["temp"], p["w_po"], save=sv)
-    x1, _ = ops.conv_gemm(qkv[..., 2 * C_:], weff, C_, Ci=C_, bias=p["b_po"], res2=x32, want="f32", w_batched=True)
-    xn = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5)
-    sv["xn2"] = xn
-    _, hid = ops.conv_gemm(xn, p["w_in"], 2 * hp, bias=p["b_in"])
+    xn2 = torch.empty_like(xn) if fuse_ln else None
+    x1, _ = ops.conv_gemm(qkv[..., 2 * C_:], weff, C_, Ci=C_, bias=p["b_po"], res2=x32, want="f32", w_batched=True,
+                          ln=(p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5, xn2) if fuse_ln else None)
+    if not fuse_ln:
+        xn2 = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5)
+    sv["xn2"] = xn2
+    _, hid = ops.conv_gemm(xn2, p["w_in"], 2 * hp, bias=p["b_in"])
     g, sv["y"] = ops.dwconv3x3_gated_train(hid, p["w_dw"], p["b_dw"], 1)      # also keeps the pre-gate [a | b]
-    out, _ = ops.conv_gemm(g, p["w_out"], C_, bias=p["b_out"], res2=x1, want="f32")
+    xn_next = None
+    if fuse_ln and nxt is not None and _ln_fusable(nxt) and nxt["C"] == C_:
+        xn_next = torch.empty_like(xn)
+    out, _ = ops.conv_gemm(g, p["w_out"], C_, bias=p["b_out"], res2=x1, want="f32",
+                           ln=(nxt["ln_mode"], nxt["ln1_w"], nxt["ln1_b"], 1e-5, xn_next) if xn_next is not None else None)
     if fusion:          # out = alpha * block(x0) + x0   (R:353)
         sv["t"] = out
         out = ops.scale_add(out, x32, scale_ptr=p["alpha"])
     sv.update(qkv0=qkv0, qkv=qkv, x1=x1, hid=hid, g=g)
     tape.append(sv)
-    return out
+    return out, xn_next
 
 
 def run_block_bwd(dout, sv, G, dout16=None, want16=False):
@@ -158,10 +170,12 @@ def run_block_bwd(dout, sv, G, dout16=None, want16=False):
     return (d0, d0_16) if want16 else d0
 
 
-def run_stack_train(x32, preps, mods, tape):
+def run_stack_train(x32, preps, mods, tape, xn=None, nxt=None, tail=None):
     n0 = len(tape)
-    for p, m in zip(preps, mods):
-        x32 = run_block_train(x32, prep_block_train(m, p), tape)
+    for i, (p, m) in enumerate(zip(preps, mods)):
+        x32, xn = run_block_train(x32, prep_block_train(m, p), tape, xn, preps[i + 1] if i + 1 < len(preps) else nxt)
+    if tail is not None:
+        tail.append(xn)
     return x32, (n0, len(tape))
 
 
@@ -256,8 +270,10 @@ class RestormerTrainMixin:
         ops.conv_gemm(ops.rownorm(d2, 0), P["up2_1"]["w"], P["up2_1"]["Co"], k=3, pad=1, out_f32=d1[..., :d[0]], store_mode=2)
         ops.copy_rows(e1, dst32=d1[..., d[0]:])
         T["d2"] = d2
-        d1, T["s_dec1"] = run_stack_train(d1, P["decoder_level1"], self.decoder_level1, tape)
-        d1, T["s_ref"] = run_stack_train(d1, P["refinement"], self.refinement, tape)
+        tail = []
+        d1, T["s_dec1"] = run_stack_train(d1, P["decoder_level1"], self.decoder_level1, tape,
+                                          nxt=P["refinement"][0] if P["refinement"] else None, tail=tail)
+        d1, T["s_ref"] = run_stack_train(d1, P["refinement"], self.refinement, tape, xn=tail[0])
         T["d1"] = d1
         o8, _ = ops.conv_gemm(ops.rownorm(d1, 0), P["output"]["w"], 8, k=3, pad=1, bias=P["output"]["b"], want="f32")
         return o8[..., :P["output"]["Co"]]

@@ -66,7 +66,12 @@ struct ConvGemmArgs {
                                 //    into it (A is fetched once instead of KH*KW times, B never again)
   int halo_bytes;               // bytes of one haloed A tile: (TH + (KH-1)*dil) rows x 16 px x 128 B
   int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
-  int epi_bufs;                 // staging buffers per epilogue warp (1 or 2)
+  int epi_bufs;                 // staging buffers per epilogue warp (1 or 2; 3 with the fused LayerNorm)
+  // fused LayerNorm of the output rows (variant bit 3): ln_out = LN(out) in bf16 through map_o2
+  int ln_mode;                  // 1 WithBias, 2 BiasFree (as tdr_rownorm)
+  float ln_eps;
+  const float* ln_w;
+  const float* ln_b;
 };
 
 // it-th work item of this CTA -> (pixel tile, n tile).  by_pixel: CTA c owns pixel tiles c, c + grid, ... and walks ALL n tiles
@@ -91,14 +96,16 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 }
 
 // V < 0: generic epilogue (any combination of outputs / residuals / pixel (un)shuffle).
-// V >= 0: TMA epilogue specialised at compile time: bit 0 = fp32 output, bit 1 = res2 tile, bit 2 = res1 tile.
+// V >= 0: TMA epilogue specialised at compile time: bit 0 = fp32 output, bit 1 = res2 tile, bit 2 = res1 tile,
+//         bit 3 = fused LayerNorm of the output rows (only with bits 0 and 1, Co <= 128).
 template <int V>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_constant__ TdrTensorMap map_w,
                  const __grid_constant__ TdrTensorMap map_o, const __grid_constant__ TdrTensorMap map_r2,
-                 const __grid_constant__ TdrTensorMap map_r1, const ConvGemmArgs a) {
+                 const __grid_constant__ TdrTensorMap map_r1, const __grid_constant__ TdrTensorMap map_o2,
+                 const ConvGemmArgs a) {
   constexpr bool kTma = V >= 0;
-  constexpr bool kF32 = kTma && (V & 1), kR2 = kTma && (V & 2), kR1 = kTma && (V & 4);
+  constexpr bool kF32 = kTma && (V & 1), kR2 = kTma && (V & 2), kR1 = kTma && (V & 4), kLN = kTma && (V & 8);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages][barriers][tmem ptr]; base rounded up to 1024 B for SWIZZLE_128B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -117,6 +124,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
   uint64_t* rbar = bars + 2 * kMaxStages + 8;                  // [kEpiWarps][2] residual-tile barriers
   uint64_t* wfull = rbar + 2 * kEpiWarps;                      // halo mode: resident weights have landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
+  float2* ln_xch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2][kEpiWarps][32] (kLN only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +136,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       tma_prefetch_desc(&map_o);
       if (kR2) tma_prefetch_desc(&map_r2);
       if (kR1) tma_prefetch_desc(&map_r1);
+      if (kLN) tma_prefetch_desc(&map_o2);
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
@@ -289,7 +298,141 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       const float rs = (valid && a.rowscale) ? a.rowscale[pix] : 1.f;
 
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * a.BN;
-      if constexpr (kTma) {
+      if constexpr (kLN) {
+        // TMA epilogue + LayerNorm of the finished rows (Co <= 128, one N tile, <= 4 fp32 sub-blocks of 32 columns).
+        // The two warps of a TMEM lane quadrant share a pool of staging tiles: one fp32 tile per sub-block (residual in,
+        // finished row out -- it stays in shared memory after its TMA store was issued) and one bf16 tile per 64 columns.
+        //   pass 1  sub-block sb belongs to warp half (sb & 1): residual add, per-row sum / sum of squares, fp32 store;
+        //   A       partial sums cross through shared memory, 64-thread named barrier (also publishes the fp32 tiles);
+        //   pass 2  re-read staged rows, normalise, write the bf16 tile; with an odd sub-block count the last one moves
+        //           to half 1 so that both warps carry the same number of passes;
+        //   B       second named barrier, then one lane per bf16 tile hands it to TMA.
+        uint8_t* const pool = smem_epi + quad * 6 * kEpiStageBytes;   // [0..3] fp32 sub-blocks, [4..5] bf16 tiles
+        uint64_t* const rb = rbar + quad * 4;                          // one residual barrier per sub-block
+        const bool plain = !a.bias && !a.rowscale && !a.act && alpha == 1.f;
+        const int box_w = a.TW < 32 ? a.TW : 32;
+        const int tx0 = (r % a.tiles_x) * a.TW + (a.TW > 32 ? quad * 32 : 0);
+        const int ty0 = (r / a.tiles_x) * a.TH + (a.TW > 32 ? 0 : quad * (32 / box_w));
+        const int n_sb = (a.Co + 31) >> 5;
+        if (lane == 0) {
+          tma_store_wait_read();                 // every store this lane issued has finished reading the pool
+          for (int sb = half; sb < n_sb; sb += 2) {
+            mbar_expect_tx(&rb[sb], kEpiStageBytes);
+            tma_load_4d(pool + sb * kEpiStageBytes, &map_r2, &rb[sb], sb * 32, tx0, ty0, b);
+          }
+        }
+        mbar_wait(&tfull[acc], acc_phase);
+        tc_fence_after();
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int sb = half + 2 * k;
+          if (sb < n_sb) {
+            const int cs = sb * 32;
+            const uint32_t stg_s = smem_u32(pool + sb * kEpiStageBytes);
+            uint32_t raw[2][16];
+            tmem_ld16(t_base + cs, raw[0]);
+            tmem_ld16(t_base + cs + 16, raw[1]);
+            tmem_ld_wait();
+            mbar_wait(&rb[sb], rphase[k]);
+            rphase[k] ^= 1;
+#pragma unroll
+            for (int q4 = 0; q4 < 2; ++q4) {
+              const int col0 = cs + q4 * 16;
+              float v[16];
+              if (plain) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(raw[q4][i]);
+              } else {
+                float bb[16];
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (a.bias && col0 + i4 * 4 < a.Co) t = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + i4 * 4));
+                  bb[i4 * 4] = t.x; bb[i4 * 4 + 1] = t.y; bb[i4 * 4 + 2] = t.z; bb[i4 * 4 + 3] = t.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaf(__uint_as_float(raw[q4][i]), rs, bb[i]);
+                if (a.act == 1) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (alpha != 1.f) {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] *= alpha;
+                }
+              }
+#pragma unroll
+              for (int hh = 0; hh < 4; ++hh) {
+                const int off = lane * 128 + ((((q4 * 4 + hh) & 7) ^ (lane & 7)) << 4);
+                const uint4 t = lds128(stg_s + off);
+                float4 o = make_float4(v[hh * 4] + __uint_as_float(t.x), v[hh * 4 + 1] + __uint_as_float(t.y),
+                                       v[hh * 4 + 2] + __uint_as_float(t.z), v[hh * 4 + 3] + __uint_as_float(t.w));
+                // columns >= Co are exact zeros (zero-filled weights and residual, bias skipped): no mask needed
+                s1 += (o.x + o.y) + (o.z + o.w);
+                s2 = fmaf(o.x, o.x, s2); s2 = fmaf(o.y, o.y, s2); s2 = fmaf(o.z, o.z, s2); s2 = fmaf(o.w, o.w, s2);
+                sts128(stg_s + off, __float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(o.w));
+              }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&map_o, pool + sb * kEpiStageBytes, cs, tx0, ty0, b);
+              tma_store_commit();
+            }
+          }
+        }
+        // A: row statistics, mine + the partner warp's (same quadrant, other sub-blocks)
+        float2* const xq = ln_xch + (it & 1) * (kEpiWarps * 32);
+        xq[ew * 32 + lane] = make_float2(s1, s2);
+        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        const float2 other = xq[(ew ^ 4) * 32 + lane];
+        s1 += other.x;
+        s2 += other.y;
+        const float inv_c = 1.f / (float)a.Co;
+        const float mean = s1 * inv_c;
+        const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, s2 * inv_c), 0.f) + a.ln_eps);
+        const float sub = a.ln_mode == 1 ? mean : 0.f;             // BiasFree divides x itself (R:184-186)
+        // pass 2: sub-block sb is normalised by warp half (sb & 1), except that the last of an odd count goes to half 1
+#pragma unroll
+        for (int sb = 0; sb < 4; ++sb) {
+          const int owner = (sb == n_sb - 1 && (n_sb & 1)) ? 1 : (sb & 1);
+          if (sb < n_sb && owner == half) {
+            const uint32_t stg_s = smem_u32(pool + sb * kEpiStageBytes);
+            const uint32_t stg16 = smem_u32(pool + (4 + (sb >> 1)) * kEpiStageBytes);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {                       // 8 columns = two fp32 chunks -> one bf16 chunk
+              const int col = sb * 32 + c8 * 8;
+              float y[8];
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const uint4 t = lds128(stg_s + lane * 128 + ((((c8 * 2 + h2) & 7) ^ (lane & 7)) << 4));
+                float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col + h2 * 4 < a.Co) {
+                  w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w + col + h2 * 4));
+                  if (a.ln_b) b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b + col + h2 * 4));
+                }
+                y[h2 * 4] = fmaf((__uint_as_float(t.x) - sub) * rstd, w4.x, b4.x);
+                y[h2 * 4 + 1] = fmaf((__uint_as_float(t.y) - sub) * rstd, w4.y, b4.y);
+                y[h2 * 4 + 2] = fmaf((__uint_as_float(t.z) - sub) * rstd, w4.z, b4.z);
+                y[h2 * 4 + 3] = fmaf((__uint_as_float(t.w) - sub) * rstd, w4.w, b4.w);
+              }
+              sts128(stg16 + lane * 128 + ((((sb & 1) * 4 + c8) ^ (lane & 7)) << 4), pack2(y[0], y[1]),
+                     pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
+            }
+          }
+        }
+        // B: both warps' bf16 chunks are in place (and visible to the async proxy) -> one lane per bf16 tile stores it
+        fence_proxy_async();
+        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
+        if (lane == 0 && half * 64 < a.Co) {
+          tma_store_4d(&map_o2, pool + (4 + half) * kEpiStageBytes, half * 64, tx0, ty0, b);
+          tma_store_commit();
+        }
+        __syncwarp();
+      } else if constexpr (kTma) {
         // TMA epilogue.  Sub-blocks of 128 B per pixel row (64 bf16 / 32 fp32 columns) alternate between the two
         // warps of a TMEM lane quadrant.  Residual tiles are TMA-loaded into the same SWIZZLE_128B staging tile
         // (prefetched before the accumulator is even ready), updated in place by phase 1 (thread = pixel row), and
@@ -655,6 +798,19 @@ __global__ void conv_gemm_simt_kernel(const bf16* __restrict__ in, long long in_
 
 }  // namespace
 
+// fused output LayerNorm: what the kLN epilogue covers (see include/tdr_sm100.h)
+static bool conv_ln_ok(const tdr_conv_gemm_desc* d) {
+  return d && (d->ln_mode == 1 || d->ln_mode == 2) && d->impl == 0 && d->store_mode == 0 && d->KH == 1 && d->KW == 1 &&
+         d->out_f32 && !d->out_bf16 && d->res2 && !d->res2_bf16 && !d->res1 && d->act != 2 && d->Co <= 128 &&
+         d->Co % 8 == 0 && d->ln_weight && d->ln_out_bf16 && ((uintptr_t)d->ln_out_bf16 & 15) == 0 &&
+         d->ln_out_ld % 8 == 0 && ((uintptr_t)d->out_f32 & 15) == 0 && d->out_f32_ld % 4 == 0 &&
+         ((uintptr_t)d->res2 & 15) == 0 && d->res2_ld % 4 == 0 && ((uintptr_t)d->ln_weight & 15) == 0 &&
+         (!d->ln_bias || ((uintptr_t)d->ln_bias & 15) == 0) && getenv("TDR_CONV_EPI") == nullptr &&
+         getenv("TDR_CONV_BN") == nullptr;
+}
+
+extern "C" int tdr_conv_gemm_ln_supported(const tdr_conv_gemm_desc* d) { return conv_ln_ok(d) ? 1 : 0; }
+
 extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   TDR_CHECK_ARG(d != nullptr, "tdr_conv_gemm: null descriptor");
   TDR_CHECK_ARG(d->in && d->weight, "tdr_conv_gemm: null input/weight");
@@ -690,6 +846,10 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   a.out_f32 = d->out_f32; a.out_f32_ld = d->out_f32_ld;
   a.out_bf16 = reinterpret_cast<bf16*>(d->out_bf16); a.out_bf16_ld = d->out_bf16_ld;
   a.store_mode = d->store_mode;
+  const bool want_ln = d->ln_mode != 0;
+  TDR_CHECK_ARG(!want_ln || conv_ln_ok(d), "tdr_conv_gemm: fused LayerNorm needs a 1x1 op with fp32 output + fp32 res2, "
+                "no res1, Co <= 128 and 16 B-aligned rows (ln_mode %d, Co %d)", d->ln_mode, d->Co);
+  a.ln_mode = d->ln_mode; a.ln_eps = d->ln_eps; a.ln_w = d->ln_weight; a.ln_b = d->ln_mode == 1 ? d->ln_bias : nullptr;
   // spatial tile: 128 output pixels as TH x TW
   a.TW = OW >= 16 ? 16 : 8;
   a.TH = kTileM / a.TW;
@@ -743,6 +903,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
       const int v = atoi(e);
       if (v >= 2 && v <= 4) a.stages = v;
     }
+    if (want_ln) a.epi_bufs = 3;                 // two fp32 sub-block tiles + the bf16 LayerNorm tile per warp
   } else {
     // N tiling: equal tiles of at most 256 columns, multiples of 16
     const int co16 = tdr_cdiv(d->Co, 16) * 16;
@@ -755,7 +916,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   auto smem_need = [&]() {
     const size_t ring = a.halo ? (size_t)a.stages * a.halo_bytes + (size_t)d->KH * d->KW * a.kchunks * a.BN * kChunkK * 2
                                : (size_t)a.stages * (kABytes + a.BN * kChunkK * 2);
-    return 1024 + ring + (size_t)kEpiWarps * a.epi_bufs * kEpiStageBytes + 512;
+    return 1024 + ring + (size_t)kEpiWarps * a.epi_bufs * kEpiStageBytes + 512 + (want_ln ? 2 * kEpiWarps * 32 * 8 : 0);
   };
   // Halo mode: stride-1 multi-tap conv, shared (not per-sample) weights that fit in shared memory next to a 3-deep
   // ring of haloed [TH + (KH-1)dil] x 16 px A tiles, a single N tile.  TW = 8 so that every 8-row UMMA group is one
@@ -776,12 +937,14 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   }
   const bool bufs_forced = getenv("TDR_CONV_EPIBUFS") != nullptr;
   while (smem_need() > 227 * 1024) {
-    if (bufs_forced && a.stages > 2) --a.stages;
-    else if (a.epi_bufs >= 2 && !d->res1) --a.epi_bufs;
+    if ((bufs_forced || want_ln) && a.stages > 2) --a.stages;
+    else if (a.epi_bufs >= 2 && !d->res1 && !want_ln) --a.epi_bufs;
     else if (a.stages > 2) --a.stages;
     else break;
   }
   TDR_CHECK_ARG(smem_need() <= 227 * 1024, "tdr_conv_gemm: shared-memory plan does not fit");
+  TDR_CHECK_ARG(!want_ln || (a.epi_mode == 1 && a.n_tiles == 1 && !a.halo && a.epi_bufs == 3),
+                "tdr_conv_gemm: fused LayerNorm plan not available for this shape");
   a.m_tiles = d->B * a.tiles_y * a.tiles_x;
   a.total_tiles = a.m_tiles * a.n_tiles;
   // by_pixel only pays when the n tiles are UNEQUAL (its scheduling granule is n_tiles items, so the tail gets coarser) and
@@ -811,7 +974,8 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   }
 
   TDR_CHECK_ARG(a.TW * d->stride <= 256 && a.TH * d->stride <= 256, "tdr_conv_gemm: TMA box too large");
-  TdrTensorMap map_a, map_w, map_o, map_r2, map_r1;
+  TdrTensorMap map_a, map_w, map_o, map_r2, map_r1, map_o2;
+  memset(&map_o2, 0, sizeof(map_o2));
   memset(&map_o, 0, sizeof(map_o));
   memset(&map_r2, 0, sizeof(map_r2));
   memset(&map_r1, 0, sizeof(map_r1));
@@ -830,6 +994,12 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     if (rc) return rc;
     if (d->res2 && (rc = mk(&map_r2, d->res2, d->res2_ld))) return rc;
     if (d->res1 && (rc = mk(&map_r1, d->res1, d->res1_ld))) return rc;
+    if (want_ln) {
+      const uint32_t box16[4] = {64, (uint32_t)box_w, (uint32_t)(32 / box_w), 1};
+      const uint64_t st16[3] = {(uint64_t)d->ln_out_ld * 2, (uint64_t)d->ln_out_ld * 2 * OW,
+                                (uint64_t)d->ln_out_ld * 2 * OW * OH};
+      if ((rc = tdr_make_tensor_map_bf16(&map_o2, d->ln_out_bf16, 4, dims, st16, box16, es))) return rc;
+    }
   }
   {
     const uint64_t dims[4] = {(uint64_t)d->Ci, (uint64_t)img_w, (uint64_t)img_h, (uint64_t)n_img};
@@ -857,7 +1027,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   }
   const size_t smem = smem_need();
   const int grid = a.total_tiles < tdr_num_sms() ? a.total_tiles : tdr_num_sms();
-  const int variant = a.epi_mode == 1 ? (a.out_is_f32 | (d->res2 ? 2 : 0) | (d->res1 ? 4 : 0)) : -1;
+  const int variant = a.epi_mode == 1 ? (a.out_is_f32 | (d->res2 ? 2 : 0) | (d->res1 ? 4 : 0) | (want_ln ? 8 : 0)) : -1;
 #define TDR_LAUNCH_CONV(VV)                                                                                        \
   do {                                                                                                             \
     static bool attr_set = false;                                                                                  \
@@ -866,7 +1036,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
                                           227 * 1024));                                                            \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    conv_gemm_kernel<VV><<<grid, kThreads, smem, stream>>>(map_a, map_w, map_o, map_r2, map_r1, a);                \
+    conv_gemm_kernel<VV><<<grid, kThreads, smem, stream>>>(map_a, map_w, map_o, map_r2, map_r1, map_o2, a);        \
   } while (0)
   switch (variant) {
     case 0: TDR_LAUNCH_CONV(0); break;
@@ -874,6 +1044,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     case 2: TDR_LAUNCH_CONV(2); break;
     case 3: TDR_LAUNCH_CONV(3); break;
     case 7: TDR_LAUNCH_CONV(7); break;
+    case 11: TDR_LAUNCH_CONV(11); break;
     default: TDR_LAUNCH_CONV(-1); break;
   }
 #undef TDR_LAUNCH_CONV

@@ -130,4 +130,7 @@ extern "C" void tdr_conv_gemm_desc_layout(int* out) {
   out[7] = (int)offsetof(tdr_conv_gemm_desc, out_f32);
   out[8] = (int)offsetof(tdr_conv_gemm_desc, out_bf16);
   out[9] = (int)offsetof(tdr_conv_gemm_desc, impl);
+  out[10] = (int)offsetof(tdr_conv_gemm_desc, ln_mode);
+  out[11] = (int)offsetof(tdr_conv_gemm_desc, ln_weight);
+  out[12] = (int)offsetof(tdr_conv_gemm_desc, ln_out_bf16);
 }

@@ -34,6 +34,8 @@ class ConvGemmDesc(C.Structure):
         ("out_f32", C.c_void_p), ("out_f32_ld", C.c_longlong),
         ("out_bf16", C.c_void_p), ("out_bf16_ld", C.c_longlong),
         ("store_mode", C.c_int), ("impl", C.c_int),
+        ("ln_mode", C.c_int), ("ln_eps", C.c_float), ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p),
+        ("ln_out_bf16", C.c_void_p), ("ln_out_ld", C.c_longlong),
     ]
 
 
@@ -45,6 +47,7 @@ SIGNATURES = {
     "tdr_version": (_i, []),
     "tdr_check_device": (_i, []),
     "tdr_conv_gemm": (_i, [C.POINTER(ConvGemmDesc), _vp]),
+    "tdr_conv_gemm_ln_supported": (_i, [C.POINTER(ConvGemmDesc)]),
     "tdr_conv_gemm_desc_layout": (None, [C.POINTER(_i)]),
     "tdr_conv3x3_small_ci": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_conv3x3_small_co": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),

@@ -5,6 +5,7 @@ buffer (``t[..., a:b]``) are passed as (pointer, row stride) without copies, whi
 (``torch.cat([x, warp], 1)`` in the reference) are expressed.  PyTorch is used for device memory and streams only.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -181,9 +182,12 @@ def rows16(B, H, W, Cc, dev):
 # ---------------------------------------------------------------------------------------------- ops
 def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, relu=False, gelu=False, rowscale=None,
               alpha=1.0, scale_ptr=None, res1=None, res1_scale=1.0, res2=None, out_f32=None, out_bf16=None,
-              want="bf16", store_mode=0, w_batched=False, w_raw=None, origin=None, window=None, impl=0):
+              want="bf16", store_mode=0, w_batched=False, w_raw=None, origin=None, window=None, impl=0, ln=None):
     """x: bf16 NHWC view.  wpack: bf16 [T, Co_p, Ci_p].  Returns (out_f32, out_bf16) -- allocated if not given
-    according to ``want`` in {"bf16", "f32", "both"}."""
+    according to ``want`` in {"bf16", "f32", "both"}.
+
+    ln = (mode, weight, bias, eps, out_bf16_view): also write LayerNorm(out) of the finished fp32 rows (the norm that
+    follows on the residual stream) from the same epilogue; see ``conv_ln_ok``."""
     assert x.dtype == BF16 and (w_raw is not None or wpack.dtype == BF16)
     B, H, W, Cx = x.shape
     Ci = Cx if Ci is None else Ci
@@ -241,12 +245,26 @@ def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, 
         d.out_bf16 = out_bf16.data_ptr(); d.out_bf16_ld = _ld(out_bf16)
     d.store_mode = store_mode
     d.impl = impl
+    ln_out = None
+    if ln is not None:
+        mode, lw, lb, eps, ln_out = ln
+        assert mode in (1, 2) and ln_out.dtype == BF16 and tuple(ln_out.shape) == oshape and lw.dtype == F32
+        d.ln_mode = mode; d.ln_eps = eps; d.ln_weight = lw.data_ptr()
+        d.ln_bias = lb.data_ptr() if (lb is not None and mode == 1) else None
+        d.ln_out_bf16 = ln_out.data_ptr(); d.ln_out_ld = _ld(ln_out)
     taps = k * k
     _call("tdr_conv_gemm", C.byref(d), _stream(),
-          tag=f"k{k}s{stride}_Ci{Ci}_Co{Co}_{OH}x{OW}" + ("_wb" if w_batched else ""),
-          nbytes=nB * nH * nW * Ci * 2 + Co * Ci * taps * 2 * (nB if w_batched else 1) + _nb(out_f32, out_bf16, res1, res2),
+          tag=f"k{k}s{stride}_Ci{Ci}_Co{Co}_{OH}x{OW}" + ("_wb" if w_batched else "") + ("_ln" if ln is not None else ""),
+          nbytes=nB * nH * nW * Ci * 2 + Co * Ci * taps * 2 * (nB if w_batched else 1) + _nb(out_f32, out_bf16, res1, res2, ln_out),
           flops=2 * nB * OH * OW * Co * Ci * taps)
     return out_f32, out_bf16
+
+
+def conv_ln_ok(Co):
+    """Can a 1x1 ``conv_gemm`` with fp32 output + fp32 res2 (no res1) also emit the LayerNorm of its output rows?  Mirrors
+    ``tdr_conv_gemm_ln_supported`` for the buffers this package allocates.  TDR_NO_LN_FUSION=1 turns the fusion off
+    (A/B measurements)."""
+    return Co <= 128 and Co % 8 == 0 and os.environ.get("TDR_NO_LN_FUSION", "0") in ("", "0")
 
 
 def rownorm(x32, mode, weight=None, bias=None, eps=1e-5, out=None, leaky=False, out_f32=None, want_bf16=True):
