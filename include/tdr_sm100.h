@@ -80,7 +80,7 @@ typedef struct tdr_conv_gemm_desc {
   /* Optional fused LayerNorm of the OUTPUT rows: ln_out = LN(out) in bf16, i.e. the norm1 / norm2 that follows on the
    * residual stream (TransformerBlock R:318-331) folded into the conv that produces it, saving the norm kernel's read
    * of the fp32 stream.  ln_mode as tdr_rownorm (0 off, 1 WithBias R:189-205, 2 BiasFree R:172-186).  Supported with
-   * impl 0, store_mode 0, fp32 output only, an fp32 res2, no res1, Co <= 128, 16 B-aligned ln_out rows; anything else
+   * impl 0, store_mode 0, fp32 output only, an fp32 res2, no res1, Co <= 96, 16 B-aligned ln_out rows; anything else
    * is rejected with TDR_EINVAL (tdr_conv_gemm_ln_supported tells beforehand). */
   int ln_mode;
   float ln_eps;

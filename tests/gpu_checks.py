@@ -266,7 +266,7 @@ def check_conv_ln():
     out = []
     cases = [dict(Ci=96, Co=96, H=16, W=16, mode=1), dict(Ci=256, Co=96, H=20, W=24, mode=2, bias=True),
              dict(Ci=128, Co=48, H=16, W=32, mode=1, bias=True), dict(Ci=48, Co=48, H=9, W=13, mode=2, B=3),
-             dict(Ci=96, Co=96, H=16, W=16, mode=1, batched=True, bias=True), dict(Ci=64, Co=128, H=8, W=40, mode=1),
+             dict(Ci=96, Co=96, H=16, W=16, mode=1, batched=True, bias=True), dict(Ci=64, Co=72, H=8, W=40, mode=1), dict(Ci=64, Co=96, H=64, W=96, mode=2, B=4, inplace=True),
              dict(Ci=64, Co=64, H=16, W=16, mode=2), dict(Ci=32, Co=8, H=16, W=16, mode=1, B=1),
              dict(Ci=256, Co=96, H=160, W=192, mode=1, bias=True, B=2, inplace=True),
              dict(Ci=96, Co=48, H=128, W=256, mode=2, B=2, inplace=True, batched=True)]

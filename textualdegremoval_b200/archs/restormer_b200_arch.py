@@ -156,7 +156,7 @@ def run_block(x32, p, xn=None, nxt=None):
 
     Reference :318-331 / :334-353.  Kernel sequence: LN -> qkv 1x1 (tcgen05) -> depthwise 3x3 -> Gram (tcgen05) ->
     softmax+fold -> attn.v.project_out + residual (tcgen05) -> LN -> project_in (tcgen05) -> depthwise 3x3 + GELU gate
-    -> project_out + residual (tcgen05).  For C <= 128 the two convs that finish a residual row also write the
+    -> project_out + residual (tcgen05).  For C <= 96 the two convs that finish a residual row also write the
     LayerNorm that follows it (norm2 of this block; norm1 of ``nxt``, the next block of the stack), so the norm
     kernels' re-read of the fp32 stream disappears: ``xn`` is that already-normalised input when the producer made it.
     Returns the normalised input for ``nxt`` (or None when ``nxt`` has to run its own norm1).

@@ -80,7 +80,7 @@ def prep_block_train(blk, p):
 def run_block_train(x32, p, tape, xn=None, nxt=None):
     """Training forward of one (Res-fusion) transformer block: NOT in place.  Returns (new residual stream, its
     LayerNorm for ``nxt`` or None): as in ``run_block`` the convs that finish a residual row also emit the norm that
-    follows (C <= 128), here into the tape's own xn1 / xn2 tensors."""
+    follows (C <= 96), here into the tape's own xn1 / xn2 tensors."""
     from .restormer_b200_arch import _ln_fusable
     C_, heads, hp = p["C"], p["heads"], p["hp"]
     fusion = p["alpha"] is not None

@@ -66,7 +66,7 @@ struct ConvGemmArgs {
                                 //    into it (A is fetched once instead of KH*KW times, B never again)
   int halo_bytes;               // bytes of one haloed A tile: (TH + (KH-1)*dil) rows x 16 px x 128 B
   int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
-  int epi_bufs;                 // staging buffers per epilogue warp (1 or 2; 3 with the fused LayerNorm)
+  int epi_bufs;                 // staging buffers per epilogue warp (1 or 2; 4 with the fused LayerNorm)
   // fused LayerNorm of the output rows (variant bit 3): ln_out = LN(out) in bf16 through map_o2
   int ln_mode;                  // 1 WithBias, 2 BiasFree (as tdr_rownorm)
   float ln_eps;
@@ -97,7 +97,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 
 // V < 0: generic epilogue (any combination of outputs / residuals / pixel (un)shuffle).
 // V >= 0: TMA epilogue specialised at compile time: bit 0 = fp32 output, bit 1 = res2 tile, bit 2 = res1 tile,
-//         bit 3 = fused LayerNorm of the output rows (only with bits 0 and 1, Co <= 128).
+//         bit 3 = fused LayerNorm of the output rows (only with bits 0 and 1, Co <= 96).
 template <int V>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_constant__ TdrTensorMap map_w,
@@ -124,6 +124,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
   uint64_t* rbar = bars + 2 * kMaxStages + 8;                  // [kEpiWarps][2] residual-tile barriers
   uint64_t* wfull = rbar + 2 * kEpiWarps;                      // halo mode: resident weights have landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
+  uint64_t* lnbar = bars + 40;                                 // kLN: [4 quadrants][2 sets][3 sub-blocks] residual tiles
   float2* ln_xch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2][kEpiWarps][32] (kLN only)
 
   const int warp = threadIdx.x >> 5;
@@ -144,6 +145,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     }
     for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(&rbar[i], 1);
     mbar_init(wfull, 1);
+    if (kLN)
+      for (int i = 0; i < 24; ++i) mbar_init(&lnbar[i], 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], kEpiWarps);
@@ -283,6 +286,22 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     const int c_begin = (ncol16 * half) / 2, c_end = (ncol16 * (half + 1)) / 2;
     uint32_t rphase[2] = {0, 0};             // parity of this warp's residual-tile barriers
     int store_cnt = 0;
+    // kLN: residual tiles of item `t` -> staging set (t & 1) of this quadrant's pool (lane 0 only)
+    auto ln_prefetch = [&](int t) {
+      int mt2, nt2;
+      if (!conv_item(a, t, mt2, nt2)) return;
+      const int b2 = mt2 / tiles_per_img, r2 = mt2 % tiles_per_img;
+      const int bw = a.TW < 32 ? a.TW : 32;
+      const int tx = (r2 % a.tiles_x) * a.TW + (a.TW > 32 ? quad * 32 : 0);
+      const int ty = (r2 / a.tiles_x) * a.TH + (a.TW > 32 ? 0 : quad * (32 / bw));
+      const int set = t & 1, n_sb2 = (a.Co + 31) >> 5;
+      for (int sb = half; sb < n_sb2; sb += 2) {
+        uint64_t* const bar = &lnbar[quad * 6 + set * 3 + sb];
+        mbar_expect_tx(bar, kEpiStageBytes);
+        tma_load_4d(smem_epi + (quad * 8 + set * 3 + sb) * kEpiStageBytes, &map_r2, bar, sb * 32, tx, ty, b2);
+      }
+    };
+    if (kLN && lane == 0) ln_prefetch(0);
     int it = 0;
     for (;; ++it) {
       int mt, nt;
@@ -299,43 +318,41 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
 
       const uint32_t t_base = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * a.BN;
       if constexpr (kLN) {
-        // TMA epilogue + LayerNorm of the finished rows (Co <= 128, one N tile, <= 4 fp32 sub-blocks of 32 columns).
-        // The two warps of a TMEM lane quadrant share a pool of staging tiles: one fp32 tile per sub-block (residual in,
-        // finished row out -- it stays in shared memory after its TMA store was issued) and one bf16 tile per 64 columns.
+        // TMA epilogue + LayerNorm of the finished rows (Co <= 96, one N tile, <= 3 fp32 sub-blocks of 32 columns).
+        // The two warps of a TMEM lane quadrant share a pool of staging tiles: two SETS of one fp32 tile per sub-block
+        // (residual in, finished row out -- it stays in shared memory after its TMA store was issued) and one bf16 tile
+        // per 64 columns.  The residual tiles of item t + 1 are fetched into the other set while item t is processed:
+        // with a single set the HBM latency of the residual sat on every item's critical path.
         //   pass 1  sub-block sb belongs to warp half (sb & 1): residual add, per-row sum / sum of squares, fp32 store;
         //   A       partial sums cross through shared memory, 64-thread named barrier (also publishes the fp32 tiles);
         //   pass 2  re-read staged rows, normalise, write the bf16 tile; with an odd sub-block count the last one moves
         //           to half 1 so that both warps carry the same number of passes;
         //   B       second named barrier, then one lane per bf16 tile hands it to TMA.
-        uint8_t* const pool = smem_epi + quad * 6 * kEpiStageBytes;   // [0..3] fp32 sub-blocks, [4..5] bf16 tiles
-        uint64_t* const rb = rbar + quad * 4;                          // one residual barrier per sub-block
+        const int set = it & 1;
+        uint8_t* const pool = smem_epi + quad * 8 * kEpiStageBytes;   // [set * 3 + sb] fp32 tiles, [6 + j] bf16 tiles
+        uint8_t* const fp = pool + set * 3 * kEpiStageBytes;
+        uint64_t* const rb = lnbar + quad * 6 + set * 3;
         const bool plain = !a.bias && !a.rowscale && !a.act && alpha == 1.f;
         const int box_w = a.TW < 32 ? a.TW : 32;
         const int tx0 = (r % a.tiles_x) * a.TW + (a.TW > 32 ? quad * 32 : 0);
         const int ty0 = (r / a.tiles_x) * a.TH + (a.TW > 32 ? 0 : quad * (32 / box_w));
         const int n_sb = (a.Co + 31) >> 5;
-        if (lane == 0) {
-          tma_store_wait_read();                 // every store this lane issued has finished reading the pool
-          for (int sb = half; sb < n_sb; sb += 2) {
-            mbar_expect_tx(&rb[sb], kEpiStageBytes);
-            tma_load_4d(pool + sb * kEpiStageBytes, &map_r2, &rb[sb], sb * 32, tx0, ty0, b);
-          }
-        }
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
         float s1 = 0.f, s2 = 0.f;
+        int n_p1 = 0;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const int sb = half + 2 * k;
           if (sb < n_sb) {
+            ++n_p1;
             const int cs = sb * 32;
-            const uint32_t stg_s = smem_u32(pool + sb * kEpiStageBytes);
+            const uint32_t stg_s = smem_u32(fp + sb * kEpiStageBytes);
             uint32_t raw[2][16];
             tmem_ld16(t_base + cs, raw[0]);
             tmem_ld16(t_base + cs + 16, raw[1]);
             tmem_ld_wait();
-            mbar_wait(&rb[sb], rphase[k]);
-            rphase[k] ^= 1;
+            mbar_wait(&rb[sb], (it >> 1) & 1);
 #pragma unroll
             for (int q4 = 0; q4 < 2; ++q4) {
               const int col0 = cs + q4 * 16;
@@ -377,13 +394,21 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) {
-              tma_store_4d(&map_o, pool + sb * kEpiStageBytes, cs, tx0, ty0, b);
+              tma_store_4d(&map_o, fp + sb * kEpiStageBytes, cs, tx0, ty0, b);
               tma_store_commit();
             }
           }
         }
+        if (lane == 0) {
+          // everything this lane stored before this item (the other set's fp32 tiles, its bf16 tile) has been read out;
+          // the partner finished reading the other set before barrier B of the previous item -> refill it for item + 1
+          if (n_p1 == 2) tma_store_wait_read2();
+          else if (n_p1 == 1) tma_store_wait_read1();
+          else tma_store_wait_read();
+          ln_prefetch(it + 1);
+        }
         // A: row statistics, mine + the partner warp's (same quadrant, other sub-blocks)
-        float2* const xq = ln_xch + (it & 1) * (kEpiWarps * 32);
+        float2* const xq = ln_xch + set * (kEpiWarps * 32);
         xq[ew * 32 + lane] = make_float2(s1, s2);
         __syncwarp();
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
@@ -396,11 +421,11 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         const float sub = a.ln_mode == 1 ? mean : 0.f;             // BiasFree divides x itself (R:184-186)
         // pass 2: sub-block sb is normalised by warp half (sb & 1), except that the last of an odd count goes to half 1
 #pragma unroll
-        for (int sb = 0; sb < 4; ++sb) {
+        for (int sb = 0; sb < 3; ++sb) {
           const int owner = (sb == n_sb - 1 && (n_sb & 1)) ? 1 : (sb & 1);
           if (sb < n_sb && owner == half) {
-            const uint32_t stg_s = smem_u32(pool + sb * kEpiStageBytes);
-            const uint32_t stg16 = smem_u32(pool + (4 + (sb >> 1)) * kEpiStageBytes);
+            const uint32_t stg_s = smem_u32(fp + sb * kEpiStageBytes);
+            const uint32_t stg16 = smem_u32(pool + (6 + (sb >> 1)) * kEpiStageBytes);
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {                       // 8 columns = two fp32 chunks -> one bf16 chunk
               const int col = sb * 32 + c8 * 8;
@@ -428,7 +453,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         __syncwarp();
         asm volatile("bar.sync %0, 64;" ::"r"(1 + quad) : "memory");
         if (lane == 0 && half * 64 < a.Co) {
-          tma_store_4d(&map_o2, pool + (4 + half) * kEpiStageBytes, half * 64, tx0, ty0, b);
+          tma_store_4d(&map_o2, pool + (6 + half) * kEpiStageBytes, half * 64, tx0, ty0, b);
           tma_store_commit();
         }
         __syncwarp();
@@ -801,7 +826,7 @@ __global__ void conv_gemm_simt_kernel(const bf16* __restrict__ in, long long in_
 // fused output LayerNorm: what the kLN epilogue covers (see include/tdr_sm100.h)
 static bool conv_ln_ok(const tdr_conv_gemm_desc* d) {
   return d && (d->ln_mode == 1 || d->ln_mode == 2) && d->impl == 0 && d->store_mode == 0 && d->KH == 1 && d->KW == 1 &&
-         d->out_f32 && !d->out_bf16 && d->res2 && !d->res2_bf16 && !d->res1 && d->act != 2 && d->Co <= 128 &&
+         d->out_f32 && !d->out_bf16 && d->res2 && !d->res2_bf16 && !d->res1 && d->act != 2 && d->Co <= 96 &&
          d->Co % 8 == 0 && d->ln_weight && d->ln_out_bf16 && ((uintptr_t)d->ln_out_bf16 & 15) == 0 &&
          d->ln_out_ld % 8 == 0 && ((uintptr_t)d->out_f32 & 15) == 0 && d->out_f32_ld % 4 == 0 &&
          ((uintptr_t)d->res2 & 15) == 0 && d->res2_ld % 4 == 0 && ((uintptr_t)d->ln_weight & 15) == 0 &&
@@ -848,7 +873,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   a.store_mode = d->store_mode;
   const bool want_ln = d->ln_mode != 0;
   TDR_CHECK_ARG(!want_ln || conv_ln_ok(d), "tdr_conv_gemm: fused LayerNorm needs a 1x1 op with fp32 output + fp32 res2, "
-                "no res1, Co <= 128 and 16 B-aligned rows (ln_mode %d, Co %d)", d->ln_mode, d->Co);
+                "no res1, Co <= 96 and 16 B-aligned rows (ln_mode %d, Co %d)", d->ln_mode, d->Co);
   a.ln_mode = d->ln_mode; a.ln_eps = d->ln_eps; a.ln_w = d->ln_weight; a.ln_b = d->ln_mode == 1 ? d->ln_bias : nullptr;
   // spatial tile: 128 output pixels as TH x TW
   a.TW = OW >= 16 ? 16 : 8;
@@ -903,7 +928,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
       const int v = atoi(e);
       if (v >= 2 && v <= 4) a.stages = v;
     }
-    if (want_ln) a.epi_bufs = 3;                 // two fp32 sub-block tiles + the bf16 LayerNorm tile per warp
+    if (want_ln) a.epi_bufs = 4;                 // per TMEM quadrant (2 warps): 2 sets x 3 fp32 tiles + 2 bf16 tiles
   } else {
     // N tiling: equal tiles of at most 256 columns, multiples of 16
     const int co16 = tdr_cdiv(d->Co, 16) * 16;
@@ -943,7 +968,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     else break;
   }
   TDR_CHECK_ARG(smem_need() <= 227 * 1024, "tdr_conv_gemm: shared-memory plan does not fit");
-  TDR_CHECK_ARG(!want_ln || (a.epi_mode == 1 && a.n_tiles == 1 && !a.halo && a.epi_bufs == 3),
+  TDR_CHECK_ARG(!want_ln || (a.epi_mode == 1 && a.n_tiles == 1 && !a.halo && a.epi_bufs == 4),
                 "tdr_conv_gemm: fused LayerNorm plan not available for this shape");
   a.m_tiles = d->B * a.tiles_y * a.tiles_x;
   a.total_tiles = a.m_tiles * a.n_tiles;

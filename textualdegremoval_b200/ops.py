@@ -264,7 +264,7 @@ def conv_ln_ok(Co):
     """Can a 1x1 ``conv_gemm`` with fp32 output + fp32 res2 (no res1) also emit the LayerNorm of its output rows?  Mirrors
     ``tdr_conv_gemm_ln_supported`` for the buffers this package allocates.  TDR_NO_LN_FUSION=1 turns the fusion off
     (A/B measurements)."""
-    return Co <= 128 and Co % 8 == 0 and os.environ.get("TDR_NO_LN_FUSION", "0") in ("", "0")
+    return Co <= 96 and Co % 8 == 0 and os.environ.get("TDR_NO_LN_FUSION", "0") in ("", "0")
 
 
 def rownorm(x32, mode, weight=None, bias=None, eps=1e-5, out=None, leaky=False, out_f32=None, want_bf16=True):
