@@ -32,6 +32,19 @@ def conv(B, H, W, Ci, Co, k=1, want="bf16", res=False, ld_out=None, ld_in=None, 
     return (lambda: ops.conv_gemm(x, w, Co, k=k, pad=k // 2, res2=r, out_f32=o32, out_bf16=o16, want=want, **kw)), nbytes, flops
 
 
+def conv_ln(B, H, W, Ci, Co, batched=False):
+    """1x1 conv + fp32 residual in place + fused LayerNorm of the finished rows (the block schedule's attn.v.proj / GDFN
+    project_out with norm2 / next norm1 folded in)."""
+    x = r16(B, H, W, Ci)
+    w = r16(B if batched else 1, Co, ops.round_up(Ci, 8))
+    res = torch.randn(B, H, W, Co, device=DEV)
+    lw, lb = torch.rand(Co, device=DEV) + 0.5, torch.randn(Co, device=DEV)
+    xn = ops.rows16(B, H, W, Co, DEV)
+    nbytes = B * H * W * (Ci * 2 + Co * 4 * 2 + Co * 2)
+    return (lambda: ops.conv_gemm(x, w, Co, res2=res, out_f32=res, w_batched=batched, ln=(1, lw, lb, 1e-5, xn))), nbytes, \
+        2 * B * H * W * Ci * Co
+
+
 def dw(B, H, W, C_, gate):
     x = r16(B, H, W, C_)
     w = torch.randn(9, C_, device=DEV)
@@ -107,6 +120,9 @@ PROBES = {
     "qkv96": lambda: conv(4, 512, 512, 96, 288),
     "pout256": lambda: conv(4, 512, 512, 256, 96, want="f32", res=True),
     "qkv48": lambda: conv(4, 512, 512, 48, 144),
+    "pout256_ln": lambda: conv_ln(4, 512, 512, 256, 96),
+    "pout96wb_ln": lambda: conv_ln(4, 512, 512, 96, 96, batched=True),
+    "pout128_ln48": lambda: conv_ln(4, 512, 512, 128, 48),
     "pout96wb": lambda: conv(4, 512, 512, 96, 96, want="f32", res=True),
     "pout128": lambda: conv(4, 512, 512, 128, 48, want="f32", res=True),
     "pin192": lambda: conv(4, 128, 128, 192, 1024),

@@ -1,7 +1,7 @@
 """Summarise `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` of
 `bench.py --ncu --steps 1` (profiler range = one steady-state forward step) into profiles/.
 
-    python tools/traffic_summary.py gpurun_out/traffic.csv 512x512_b4
+    python tools/traffic_summary.py gpurun_out/traffic.csv 512x512_b4 [r01f]      (last argument: round tag of the .txt)
 """
 import collections
 import csv
@@ -16,6 +16,9 @@ FAMILY = [("conv_gemm_kernel", "tdr_conv_gemm"), ("dwconv3x3", "tdr_dwconv3x3"),
           ("transfer_kernel", "tdr_masa_transfer"), ("conv3x3_small_ci", "tdr_conv3x3_small_ci")]
 BYTES = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 NS = {"ns": 1, "us": 1e3, "ms": 1e6, "nsecond": 1, "usecond": 1e3, "msecond": 1e6, "second": 1e9}
+
+
+TAG = sys.argv[3] if len(sys.argv) > 3 else "r01f"
 
 
 def main(path, workload):
@@ -34,7 +37,7 @@ def main(path, workload):
         v, u = d["dram__bytes_read.sum"]; a["rd"] += v * BYTES[u]
         v, u = d["dram__bytes_write.sum"]; a["wr"] += v * BYTES[u]
     out = {}
-    txt = os.path.join(ROOT, "profiles", "r01c_dram_traffic_forward_step.txt")
+    txt = os.path.join(ROOT, "profiles", f"{TAG}_dram_traffic_forward_step.txt")
     with open(txt, "w") as fh:
         fh.write("ncu --profile-from-start off --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
                  "--clock-control none  python bench.py --ncu --steps 1\n")
@@ -48,7 +51,7 @@ def main(path, workload):
                           ms=v["t"] / 1e6)
         tot = sum(v["rd"] + v["wr"] for v in fam.values())
         fh.write(f"total DRAM traffic of the step: {tot / 1e9:.2f} GB in {sum(v['n'] for v in fam.values())} launches\n")
-    json.dump(dict(source="profiles/r01c_dram_traffic_forward_step.txt (ncu metrics pass on B200)", workload=workload,
+    json.dump(dict(source=f"profiles/{TAG}_dram_traffic_forward_step.txt (ncu metrics pass on B200)", workload=workload,
                    families=out), open(os.path.join(ROOT, "profiles", "dram_traffic.json"), "w"), indent=1)
     print(open(txt).read())
 
