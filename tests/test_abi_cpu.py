@@ -41,6 +41,39 @@ def test_argument_validation_without_gpu(tdr_lib):
     assert tdr_lib.tdr_mdta_partials_bytes(4, 262144, 48, 1) > 0
 
 
+def test_fused_layernorm_eligibility(tdr_lib):
+    """tdr_conv_gemm_ln_supported (include/tdr_sm100.h): 1x1, fp32 out + fp32 res2, no res1, Co <= 96, aligned rows."""
+    from textualdegremoval_b200.lib import ConvGemmDesc
+
+    def desc(**kw):
+        d = ConvGemmDesc()
+        d.in_ = 4096; d.weight = 8192; d.B = 1; d.H = 16; d.W = 16; d.Ci = 96; d.Co = 96; d.KH = d.KW = 1; d.stride = 1; d.dil = 1
+        d.in_ld = 96; d.w_ld = 96
+        d.out_f32 = 1 << 20; d.out_f32_ld = 96; d.res2 = 1 << 20; d.res2_ld = 96
+        d.ln_mode = 1; d.ln_eps = 1e-5; d.ln_weight = 1 << 16; d.ln_bias = 1 << 17; d.ln_out_bf16 = 1 << 21; d.ln_out_ld = 128
+        for k, v in kw.items():
+            setattr(d, k, v)
+        return d
+
+    ok = lambda d: tdr_lib.tdr_conv_gemm_ln_supported(C.byref(d))
+    assert ok(desc()) == 1
+    assert ok(desc(ln_mode=2, ln_bias=None)) == 1
+    assert ok(desc(Co=48, out_f32_ld=48, res2_ld=48)) == 1
+    assert ok(desc(Co=128)) == 0                      # 4 sub-blocks do not fit the staging pool
+    assert ok(desc(KH=3, KW=3)) == 0
+    assert ok(desc(res1=1 << 22)) == 0                # Res-fusion epilogue keeps the standalone norm
+    assert ok(desc(res2=None)) == 0
+    assert ok(desc(res2_bf16=1)) == 0
+    assert ok(desc(out_bf16=1 << 23)) == 0
+    assert ok(desc(ln_out_ld=100)) == 0               # 16 B rows
+    assert ok(desc(ln_mode=0)) == 0
+    assert ok(desc(store_mode=1)) == 0
+    assert ok(desc(impl=1)) == 0
+    # asking for it where it cannot run is an error, not a silent fallback
+    assert tdr_lib.tdr_conv_gemm(C.byref(desc(Co=128)), None) == -1
+    assert b"LayerNorm" in tdr_lib.tdr_last_error()
+
+
 def test_registry_semantics():
     from textualdegremoval_b200 import define_network
     opt = dict(type="Restormer", dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1)

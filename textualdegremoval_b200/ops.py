@@ -169,11 +169,18 @@ def pack_dw_weight(w: torch.Tensor, n=None, idx=None) -> torch.Tensor:
     return out
 
 
+# widths kept dense by rows16 (TDR_ROWS16_DENSE="288,576": A/B knob for the pitch trade-off between the GEMM stores and
+# the depthwise conv that reads the same buffer)
+_ROWS16_DENSE = frozenset(int(v) for v in os.environ.get("TDR_ROWS16_DENSE", "").split(",") if v.strip())
+
+
 def rows16(B, H, W, Cc, dev):
     """bf16 NHWC activation buffer whose row pitch is a multiple of 128 B (64 channels): a view [B,H,W,Cc] of a wider
     allocation.  Rows that straddle 128 B lines (C = 48, 96, 144, 288 ...) cost the TMA loads / stores of the GEMMs up to
     25 % of their bandwidth (tools/probe.py qkv48 vs qkv48_ld192); the pad columns are never read or written."""
     ld = round_up(Cc, 64)
+    if Cc in _ROWS16_DENSE:
+        ld = Cc
     if ld == Cc:
         return torch.empty((B, H, W, Cc), dtype=BF16, device=dev)
     return torch.empty((B, H, W, ld), dtype=BF16, device=dev)[..., :Cc]

@@ -45,11 +45,11 @@ def conv_ln(B, H, W, Ci, Co, batched=False):
         2 * B * H * W * Ci * Co
 
 
-def dw(B, H, W, C_, gate):
-    x = r16(B, H, W, C_)
+def dw(B, H, W, C_, gate, pitched=False):
+    x = r16(B, H, W, ops.round_up(C_, 64) if pitched else C_)[..., :C_]
     w = torch.randn(9, C_, device=DEV)
     co = C_ // 2 if gate else C_
-    o = torch.empty(B, H, W, co, device=DEV, dtype=BF16)
+    o = ops.rows16(B, H, W, co, DEV) if pitched else torch.empty(B, H, W, co, device=DEV, dtype=BF16)
     return (lambda: ops.dwconv3x3(x, w, None, gate, out=o)), B * H * W * (C_ + co) * 2, 18 * B * H * W * C_
 
 
@@ -131,6 +131,7 @@ PROBES = {
     "c3x3_384": lambda: conv(8, 64, 64, 384, 384, k=3, relu=True),
     "dwg512": lambda: dw(4, 512, 512, 512, 1),
     "dw288": lambda: dw(4, 512, 512, 288, 0),
+    "dw288_ld320": lambda: dw(4, 512, 512, 288, 0, pitched=True),
     "dwg2048": lambda: dw(4, 64, 64, 2048, 1),
     "ln96": lambda: ln(4, 512, 512, 96),
     "gram96": lambda: gram(4, 512, 512, 96, 1),
