@@ -372,6 +372,26 @@ int tdr_masa_transfer(const void* f_ref_bf16, int B, int Hr_s, int Wr_s, int C, 
                       const float* att, int py, int px, int k_y, int k_x, int d_x, int s, float* out, long long out_ld,
                       void* out_bf16, long long out_bf16_ld, cudaStream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Input pipeline on the device: what Dataset_PairedImageWithRef.__getitem__ does to a decoded frame
+ * (data/restoration_dataset.py:194-253) -- imfrombytes float32 / 255 (utils/utils_image.py:216-217), `padding` =
+ * cv2.BORDER_REFLECT at the bottom / right up to the patch size (:243-254), paired_random_crop
+ * (data/transforms.py:24-83), random_augmentation mode 0..7 (data/transforms.py:223-275), img2tensor BGR->RGB + HWC->CHW
+ * (utils/utils_image.py:102-126), optional normalize (x - mean) / std (:240-244) -- for n samples in one launch.
+ * The random decisions (top, left, mode) are the caller's (the reference's `random.randint` calls); results are
+ * bit-identical to the reference's numpy / cv2 chain.  out = fp32 [n, channels, out_h, out_w].
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct tdr_patch_desc {
+  const void* image; /* DEVICE uint8 [h, w, channels], HWC, BGR when channels == 3 */
+  int h, w;
+  int top, left; /* crop origin in the (reflect-padded) frame */
+  int mode;      /* data_augmentation mode 0..7; modes 2, 3, 6, 7 (rot90 family) need out_h == out_w */
+  int reserved;
+} tdr_patch_desc;
+int tdr_prepare_patches(const tdr_patch_desc* descs_device, const tdr_patch_desc* descs_host /* same content, validated */,
+                        int n, int channels, int out_h, int out_w, int bgr2rgb, const float* mean /* host [channels] or NULL */,
+                        const float* stdv /* host [channels] or NULL */, float* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

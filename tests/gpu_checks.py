@@ -298,6 +298,41 @@ def check_conv_ln():
     return out
 
 
+def check_input_pipeline():
+    """tdr_prepare_patches vs tensors made by the unmodified reference dataset chain (tests/golden/input_pipeline.npz):
+    bit-exact (0 tolerance), all augmentation modes, reflect padding, normalisation, one launch for a whole batch."""
+    import numpy as np
+    from oracle import input_pipeline as IP
+    ops = _ops()
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "input_pipeline.npz"))
+    out = []
+    groups = {}
+    for k in range(int(z["n"])):
+        top, left, mode, size, norm = [int(v) for v in z[f"s{k}_dec"]]
+        groups.setdefault((size, norm), []).append((k, top, left, mode))
+    for (size, norm), items in groups.items():
+        frames, crops, refs = [], [], []
+        for k, top, left, mode in items:
+            for which in ("gt", "lq"):
+                frames.append(torch.from_numpy(z[f"s{k}_{which}_frame"]).to(DEV))
+                crops.append((top, left, mode))
+                refs.append(torch.from_numpy(z[f"s{k}_{which}"]))
+        mean, std = (z["mean"].tolist(), z["std"].tolist()) if norm else (None, None)
+        got = ops.prepare_patches(frames, crops, size, mean=mean, std=std)
+        out.append(result(f"prepare_patches_size{size}_norm{norm}_n{len(frames)}", got, torch.stack(refs), 0.0))
+    # the reference image of a sample is not cropped or augmented (restoration_dataset.py:236): rectangular, mode 0 / flips
+    rng = np.random.RandomState(3)
+    fr = [rng.randint(0, 256, (37, 53, 3)).astype(np.uint8) for _ in range(3)]
+    for mode in (0, 1, 4, 5):
+        got = ops.prepare_patches([torch.from_numpy(f).to(DEV) for f in fr], [(0, 0, mode)] * 3, (37, 53))
+        ref = torch.stack([torch.from_numpy(IP.prepare_patch(f, 0, 0, mode, (37, 53))) for f in fr])
+        out.append(result(f"prepare_patches_full_frame_mode{mode}", got, ref, 0.0))
+    gray = rng.randint(0, 256, (20, 20, 1)).astype(np.uint8)
+    got = ops.prepare_patches([torch.from_numpy(gray).to(DEV)], [(2, 3, 6)], 16)
+    out.append(result("prepare_patches_gray_rot270", got, torch.from_numpy(IP.prepare_patch(gray, 2, 3, 6, 16))[None], 0.0))
+    return out
+
+
 def check_conv_simt():
     out = []
     for c in CONV_CASES:
@@ -1168,6 +1203,7 @@ CHECKS = {
     "conv_tc": check_conv_tc,
     "conv_origin": check_conv_origin,
     "conv_ln": check_conv_ln,
+    "input_pipeline": check_input_pipeline,
     "mdta": check_mdta,
     "block": check_block,
     "masa": check_masa,

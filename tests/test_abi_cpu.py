@@ -74,6 +74,24 @@ def test_fused_layernorm_eligibility(tdr_lib):
     assert b"LayerNorm" in tdr_lib.tdr_last_error()
 
 
+def test_prepare_patches_argument_validation(tdr_lib):
+    """tdr_prepare_patches rejects what the reference's dataset code raises on (data/transforms.py:58-62) before launching."""
+    from textualdegremoval_b200.lib import PatchDesc
+
+    def call(h=20, w=30, top=0, left=0, mode=0, oh=16, ow=16, ch=3):
+        d = (PatchDesc * 1)()
+        d[0].image = 4096; d[0].h = h; d[0].w = w; d[0].top = top; d[0].left = left; d[0].mode = mode
+        return tdr_lib.tdr_prepare_patches(C.cast(d, C.c_void_p), C.cast(d, C.c_void_p), 1, ch, oh, ow, 1, None, None,
+                                           C.c_void_p(8192), None)
+
+    assert call(mode=8) == -1 and b"mode" in tdr_lib.tdr_last_error()
+    assert call(mode=2, oh=16, ow=20) == -1 and b"square" in tdr_lib.tdr_last_error()
+    assert call(top=5) == -1 and b"outside" in tdr_lib.tdr_last_error()          # 5 + 16 > max(20, 16)
+    assert call(h=10, top=1) == -1                                                # padded frame is exactly 16 rows
+    assert call(ch=2) == -1
+    assert call(top=-1) == -1
+
+
 def test_registry_semantics():
     from textualdegremoval_b200 import define_network
     opt = dict(type="Restormer", dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1)

@@ -200,3 +200,24 @@ def test_oracle_autograd_matches_reference_gradients(name):
         tol = 2e-4 * max(norm, 1e-3 * total)
         assert abs(a - norm) < tol, (n, a, norm)
         assert abs(b - probe) < tol * max(1.0, float(g.numel()) ** 0.5), (n, b, probe)
+
+
+def test_input_pipeline_oracle_matches_reference_fixture():
+    """oracle/input_pipeline.py vs tensors produced by the unmodified reference chain (padding, paired_random_crop,
+    random_augmentation, img2tensor, normalize; oracle/make_golden_input.py): bit-exact, all 8 augmentation modes,
+    frames smaller than the patch (single and multiple reflections)."""
+    import numpy as np
+    from oracle import input_pipeline as IP
+    z = np.load(os.path.join(GOLD, "input_pipeline.npz"))
+    modes, padded = set(), 0
+    for k in range(int(z["n"])):
+        top, left, mode, size, norm = [int(v) for v in z[f"s{k}_dec"]]
+        modes.add(mode)
+        padded += int(z[f"s{k}_gt_frame"].shape[0] < size or z[f"s{k}_gt_frame"].shape[1] < size)
+        mean, std = (z["mean"], z["std"]) if norm else (None, None)
+        for which in ("gt", "lq"):
+            got = IP.prepare_patch(z[f"s{k}_{which}_frame"], top, left, mode, size, mean=mean, std=std)
+            ref = z[f"s{k}_{which}"]
+            assert got.shape == ref.shape and got.dtype == ref.dtype
+            assert np.array_equal(got, ref), f"sample {k} {which}: max diff {np.abs(got - ref).max()}"
+    assert modes == set(range(8)) and padded >= 8

@@ -1,0 +1,96 @@
+// tdr_prepare_patches: the dataset's per-sample tensor preparation on the device (the caller side of
+// the path).  Reference, per sample of Dataset_PairedImageWithRef (data/restoration_dataset.py:194-253):
+//   imfrombytes(float32=True)      uint8 BGR HWC -> float32 / 255.            utils/utils_image.py:194-218
+//   padding                        cv2.copyMakeBorder(..., BORDER_REFLECT) bottom / right up to gt_size   :243-254
+//   paired_random_crop             [top : top + size, left : left + size]     data/transforms.py:24-83
+//   random_augmentation            one of 8 flip / rot90 modes                data/transforms.py:223-275
+//   img2tensor(bgr2rgb=True)       BGR -> RGB, HWC -> CHW                     utils/utils_image.py:102-126
+//   normalize(mean, std)           (x - mean) / std  (optional)               restoration_dataset.py:240-244
+// The random decisions (top, left, mode) stay on the host with the reference's own `random` calls; the kernel is pure
+// data movement plus two IEEE operations per element, so the result is bit-identical to the reference's.  One thread
+// per output pixel (all channels): reads are 3 B gathers from the decoded frame (L2-resident, frames are a few MB),
+// writes are coalesced along the output row of each channel plane.
+#include "tdr_common.cuh"
+
+namespace {
+
+inline int grid_for(long long items, int per_block, int max_waves) {
+  long long g = (items + per_block - 1) / per_block;
+  const long long cap = (long long)tdr_num_sms() * max_waves;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+__device__ __forceinline__ int reflect_index(int i, int n) {      // cv2.BORDER_REFLECT: fedcba|abcdefgh|hgfedcb
+  if (i < n) return i;
+  const int period = 2 * n;
+  i %= period;
+  return i < n ? i : period - 1 - i;
+}
+
+__global__ void __launch_bounds__(256) prepare_patches_kernel(const tdr_patch_desc* __restrict__ descs, int n, int channels,
+                                                              int out_h, int out_w, int bgr2rgb, float3 mean, float3 stdv,
+                                                              int normalize, float* __restrict__ out) {
+  const long long total = (long long)n * out_h * out_w;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % out_w);
+    const int i = (int)((idx / out_w) % out_h);
+    const int s = (int)(idx / ((long long)out_w * out_h));
+    const tdr_patch_desc d = descs[s];
+    // output (i, j) <- patch (y, x): inverse of data_augmentation (np.rot90 = counter-clockwise, then np.flipud)
+    int y, x;
+    switch (d.mode) {
+      case 1: y = out_h - 1 - i; x = j; break;                    // flipud
+      case 2: y = j; x = out_h - 1 - i; break;                    // rot90            (square patches)
+      case 3: y = j; x = i; break;                                // rot90 + flipud = transpose
+      case 4: y = out_h - 1 - i; x = out_w - 1 - j; break;        // rot180
+      case 5: y = i; x = out_w - 1 - j; break;                    // rot180 + flipud = fliplr
+      case 6: y = out_w - 1 - j; x = i; break;                    // rot270
+      case 7: y = out_w - 1 - j; x = out_h - 1 - i; break;        // rot270 + flipud = anti-transpose
+      default: y = i; x = j; break;
+    }
+    const int sy = reflect_index(d.top + y, d.h), sx = reflect_index(d.left + x, d.w);
+    const unsigned char* px = reinterpret_cast<const unsigned char*>(d.image) + ((long long)sy * d.w + sx) * channels;
+    const float m[3] = {mean.x, mean.y, mean.z}, sd[3] = {stdv.x, stdv.y, stdv.z};
+    for (int c = 0; c < channels; ++c) {
+      const int src_c = (channels == 3 && bgr2rgb) ? 2 - c : c;
+      float v = __fdiv_rn((float)px[src_c], 255.f);               // img.astype(np.float32) / 255.
+      if (normalize) v = __fdiv_rn(__fsub_rn(v, m[c]), sd[c]);    // tensor.sub_(mean).div_(std)
+      out[(((long long)s * channels + c) * out_h + i) * out_w + j] = v;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int tdr_prepare_patches(const tdr_patch_desc* descs_device, const tdr_patch_desc* descs_host, int n,
+                                   int channels, int out_h, int out_w, int bgr2rgb, const float* mean, const float* stdv,
+                                   float* out, cudaStream_t stream) {
+  TDR_CHECK_ARG(descs_device && descs_host && out, "tdr_prepare_patches: null pointer");
+  TDR_CHECK_ARG(n > 0 && out_h > 0 && out_w > 0 && (channels == 1 || channels == 3),
+                "tdr_prepare_patches: need n > 0, a non-empty patch and 1 or 3 channels");
+  TDR_CHECK_ARG((mean == nullptr) == (stdv == nullptr), "tdr_prepare_patches: mean and std go together");
+  for (int s = 0; s < n; ++s) {
+    const tdr_patch_desc& d = descs_host[s];
+    TDR_CHECK_ARG(d.image && d.h > 0 && d.w > 0, "tdr_prepare_patches: sample %d has no image", s);
+    TDR_CHECK_ARG(d.mode >= 0 && d.mode <= 7, "tdr_prepare_patches: sample %d: augmentation mode %d not in 0..7", s, d.mode);
+    TDR_CHECK_ARG(d.top >= 0 && d.left >= 0, "tdr_prepare_patches: sample %d: negative crop origin", s);
+    const bool transposing = d.mode == 2 || d.mode == 3 || d.mode == 6 || d.mode == 7;
+    TDR_CHECK_ARG(!transposing || out_h == out_w, "tdr_prepare_patches: rot90 modes need a square patch");
+    // the reference raises when the (reflect-padded) frame is smaller than the patch: padding only fills up to the
+    // patch size, so the crop must lie inside max(h, size) x max(w, size)  (data/transforms.py:58-62)
+    const int ph = d.h > out_h ? d.h : out_h, pw = d.w > out_w ? d.w : out_w;
+    TDR_CHECK_ARG(d.top + out_h <= ph && d.left + out_w <= pw, "tdr_prepare_patches: sample %d: crop outside the frame", s);
+  }
+  float3 m = make_float3(0.f, 0.f, 0.f), sd = make_float3(1.f, 1.f, 1.f);
+  if (mean) {
+    m = make_float3(mean[0], channels == 3 ? mean[1] : 0.f, channels == 3 ? mean[2] : 0.f);
+    sd = make_float3(stdv[0], channels == 3 ? stdv[1] : 1.f, channels == 3 ? stdv[2] : 1.f);
+  }
+  const long long total = (long long)n * out_h * out_w;
+  prepare_patches_kernel<<<grid_for(total, 256, 8), 256, 0, stream>>>(descs_device, n, channels, out_h, out_w, bgr2rgb, m,
+                                                                     sd, mean != nullptr, out);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}

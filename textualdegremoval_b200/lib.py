@@ -39,6 +39,12 @@ class ConvGemmDesc(C.Structure):
     ]
 
 
+class PatchDesc(C.Structure):
+    """Mirror of ``tdr_patch_desc`` (include/tdr_sm100.h)."""
+    _fields_ = [("image", C.c_void_p), ("h", C.c_int), ("w", C.c_int), ("top", C.c_int), ("left", C.c_int),
+                ("mode", C.c_int), ("reserved", C.c_int)]
+
+
 _vp, _ll, _i, _f, _sz = C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); every symbol include/tdr_sm100.h declares
@@ -72,6 +78,7 @@ SIGNATURES = {
     "tdr_adamw_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp, _vp]),
     "tdr_ema_update": (_i, [_vp, _vp, _ll, _f, _vp]),
     "tdr_l1_loss_grad": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _vp, _vp]),
+    "tdr_prepare_patches": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "tdr_nchw_to_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_nhwc_to_nchw": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _vp]),
     "tdr_copy_rows_f32": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp, _ll, _vp]),

@@ -746,3 +746,33 @@ def dilate2(x16, OH, OW):
     _call("tdr_dilate2_nhwc", _p(x16), _ld(x16), B, H, W, Cc, _p(out), _ld(out), OH, OW, _stream(), tag=f"C{Cc}",
           nbytes=B * H * W * Cc * 4)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ input pipeline
+def prepare_patches(frames, crops, size, bgr2rgb=True, mean=None, std=None, out=None):
+    """Device-side ``Dataset_PairedImageWithRef.__getitem__`` tensor preparation (data/restoration_dataset.py:194-253).
+
+    frames: list of uint8 CUDA tensors [h, w, c] (decoded BGR frames, HWC); crops: list of (top, left, mode) -- the
+    reference's ``random.randint`` decisions for paired_random_crop / random_augmentation; size: int or (out_h, out_w).
+    Returns fp32 [n, c, out_h, out_w] in [0, 1] (or normalised with mean / std), RGB, bit-identical to the reference's
+    numpy / cv2 chain (reflect padding of frames smaller than the patch included)."""
+    n = len(frames)
+    assert n > 0 and len(crops) == n
+    out_h, out_w = (size, size) if isinstance(size, int) else size
+    ch = frames[0].shape[2]
+    descs = (lib.PatchDesc * n)()
+    for i, (f, (top, left, mode)) in enumerate(zip(frames, crops)):
+        assert f.dtype == torch.uint8 and f.is_cuda and f.dim() == 3 and f.is_contiguous() and f.shape[2] == ch
+        descs[i].image = f.data_ptr(); descs[i].h = f.shape[0]; descs[i].w = f.shape[1]
+        descs[i].top = top; descs[i].left = left; descs[i].mode = mode
+    raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).pin_memory()
+    d_dev = raw.to(frames[0].device, non_blocking=True)
+    if out is None:
+        out = torch.empty((n, ch, out_h, out_w), dtype=F32, device=frames[0].device)
+    assert out.dtype == F32 and out.is_contiguous() and tuple(out.shape) == (n, ch, out_h, out_w)
+    m = (C.c_float * ch)(*mean) if mean is not None else None
+    sd = (C.c_float * ch)(*std) if std is not None else None
+    _call("tdr_prepare_patches", d_dev.data_ptr(), C.cast(descs, C.c_void_p), n, ch, out_h, out_w, int(bgr2rgb),
+          C.cast(m, C.c_void_p) if m is not None else None, C.cast(sd, C.c_void_p) if sd is not None else None,
+          out.data_ptr(), _stream(), tag=f"n{n}_{out_h}x{out_w}", nbytes=out.numel() * 4 + n * out_h * out_w * ch)
+    return out
