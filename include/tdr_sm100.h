@@ -392,6 +392,13 @@ int tdr_prepare_patches(const tdr_patch_desc* descs_device, const tdr_patch_desc
                         int n, int channels, int out_h, int out_w, int bgr2rgb, const float* mean /* host [channels] or NULL */,
                         const float* stdv /* host [channels] or NULL */, float* out, cudaStream_t stream);
 
+/* Validation PSNR (use_image: true) without a device->host image copy: per image the exact integer
+ * sum (q1 - q2)^2 over the crop_border-trimmed window and max(q1), q = tensor2img's uint8 quantisation
+ * (utils/utils_image.py:160-186: clamp [0, 1], * 255.0, round half-to-even).  The host finishes with calculate_psnr's
+ * float64 formula (metrics/psnr_ssim.py:55-59) and obtains the identical double.  img1 / img2: fp32 [B, C, H, W]. */
+int tdr_psnr_u8_sums(const float* img1, const float* img2, int B, int C, int H, int W, int crop_border,
+                     unsigned long long* sse /* [B] */, int* max1 /* [B] */, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

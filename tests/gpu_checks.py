@@ -333,6 +333,32 @@ def check_input_pipeline():
     return out
 
 
+def check_psnr():
+    """ops.psnr_u8 (device quantisation + exact integer sums, float64 tail on the host) vs the doubles the unmodified
+    reference tensor2img + calculate_psnr returned (tests/golden/psnr.npz): identical float64; integer sums vs oracle."""
+    import numpy as np
+    from oracle import metrics as M
+    from oracle.make_golden_metrics import CASES, make_pair
+    ops = _ops()
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "psnr.npz"))["psnr"]
+    out = []
+    for i, case in enumerate(CASES):
+        res, gt = make_pair(case, 500 + i)
+        got = ops.psnr_u8(res[None].to(DEV), gt[None].to(DEV), case["crop"])[0]
+        same = (got == ref[i]) or (np.isinf(got) and np.isinf(ref[i]))
+        out.append(dict(name=f"psnr_{case['kind']}_c{case['c']}_crop{case['crop']}", ok=bool(same), max_err=0.0 if same else
+                        abs(got - ref[i]), ref_scale=1.0, tol=0.0, note=f"{got!r} vs reference {ref[i]!r}"))
+    # a batch at validation size: per-image sums equal the oracle's integers
+    g = torch.Generator().manual_seed(9)
+    a = torch.rand(3, 3, 128, 160, generator=g) * 1.2 - 0.1
+    b = a + torch.randn(3, 3, 128, 160, generator=g) * 0.02
+    got = ops.psnr_u8(a.to(DEV), b.to(DEV), 3)
+    want = [M.psnr(a[k].numpy(), b[k].numpy(), 3) for k in range(3)]
+    out.append(dict(name="psnr_batch3_128x160_crop3", ok=got == want, max_err=max(abs(x - y) for x, y in zip(got, want)),
+                    ref_scale=1.0, tol=0.0, note=f"{got} vs {want}"))
+    return out
+
+
 def check_conv_simt():
     out = []
     for c in CONV_CASES:
@@ -1204,6 +1230,7 @@ CHECKS = {
     "conv_origin": check_conv_origin,
     "conv_ln": check_conv_ln,
     "input_pipeline": check_input_pipeline,
+    "psnr": check_psnr,
     "mdta": check_mdta,
     "block": check_block,
     "masa": check_masa,

@@ -221,3 +221,18 @@ def test_input_pipeline_oracle_matches_reference_fixture():
             assert got.shape == ref.shape and got.dtype == ref.dtype
             assert np.array_equal(got, ref), f"sample {k} {which}: max diff {np.abs(got - ref).max()}"
     assert modes == set(range(8)) and padded >= 8
+
+
+def test_psnr_oracle_matches_reference_fixture():
+    """oracle/metrics.py vs the doubles returned by the unmodified tensor2img + calculate_psnr (oracle/make_golden_metrics.py):
+    identical float64, incl. crop_border, clamping, round-half-to-even ties, the max_value = 1 branch and mse == 0."""
+    from oracle import metrics as M
+    from oracle.make_golden_metrics import CASES, make_pair
+    ref = np.load(os.path.join(GOLD, "psnr.npz"))["psnr"]
+    for i, case in enumerate(CASES):
+        res, gt = make_pair(case, 500 + i)
+        got = M.psnr(res.numpy(), gt.numpy(), case["crop"])
+        assert got == ref[i], (case, got, ref[i])
+        sse, mx, n = M.psnr_sums(res.numpy(), gt.numpy(), case["crop"])
+        if sse:
+            assert float(20. * np.log10((1. if mx <= 1 else 255.) / np.sqrt(np.float64(sse) / np.float64(n)))) == ref[i]

@@ -94,3 +94,63 @@ extern "C" int tdr_prepare_patches(const tdr_patch_desc* descs_device, const tdr
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ validation metric
+// tdr_psnr_u8_sums: the integer part of the reference's validation PSNR (use_image: true) without moving images to the
+// host.  Reference: tensor2img (utils/utils_image.py:129-191: clamp to [0, 1], * 255.0, numpy round = half-to-even,
+// uint8) on `result` and `gt`, then calculate_psnr (metrics/psnr_ssim.py:9-63: crop_border, float64 mean of squared
+// differences, max_value = 1 if img1.max() <= 1 else 255).  Squared differences of uint8 values are integers, so their
+// sum is exact in int64 whatever the order: the kernel returns, per image, sum (qa - qb)^2 over the cropped window and
+// max(qa); the host finishes with the reference's own float64 formula and gets the identical double.
+namespace {
+
+__device__ __forceinline__ int quant_u8(float x) {
+  x = fminf(fmaxf(x, 0.f), 1.f);                  // clamp_(0, 1); (x - 0) / (1 - 0) is exact
+  return (int)rintf(__fmul_rn(x, 255.f));         // (img_np * 255.0).round() on float32, half-to-even
+}
+
+__global__ void __launch_bounds__(256) psnr_u8_sums_kernel(const float* __restrict__ a, const float* __restrict__ b, int C,
+                                                           int H, int W, int crop, unsigned long long* __restrict__ sse,
+                                                           int* __restrict__ max_a) {
+  const int img = blockIdx.y;
+  const int h2 = H - 2 * crop, w2 = W - 2 * crop;
+  const long long n = (long long)C * h2 * w2;
+  const float* pa = a + (long long)img * C * H * W;
+  const float* pb = b + (long long)img * C * H * W;
+  unsigned long long acc = 0;
+  int mx = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w2);
+    const int y = (int)((i / w2) % h2);
+    const int c = (int)(i / ((long long)w2 * h2));
+    const long long off = ((long long)c * H + y + crop) * W + x + crop;
+    const int qa = quant_u8(pa[off]), qb = quant_u8(pb[off]);
+    const int d = qa - qb;
+    acc += (unsigned long long)(d * d);
+    mx = max(mx, qa);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {                  // integer atomics: order-independent, deterministic
+    atomicAdd(&sse[img], acc);
+    atomicMax(&max_a[img], mx);
+  }
+}
+
+}  // namespace
+
+extern "C" int tdr_psnr_u8_sums(const float* img1, const float* img2, int B, int C, int H, int W, int crop_border,
+                                unsigned long long* sse, int* max1, cudaStream_t stream) {
+  TDR_CHECK_ARG(img1 && img2 && sse && max1, "tdr_psnr_u8_sums: null pointer");
+  TDR_CHECK_ARG(B > 0 && C > 0 && crop_border >= 0 && H > 2 * crop_border && W > 2 * crop_border,
+                "tdr_psnr_u8_sums: empty window (B %d C %d H %d W %d crop %d)", B, C, H, W, crop_border);
+  TDR_CHECK_CUDA(cudaMemsetAsync(sse, 0, sizeof(unsigned long long) * B, stream));
+  TDR_CHECK_CUDA(cudaMemsetAsync(max1, 0, sizeof(int) * B, stream));
+  const long long n = (long long)C * (H - 2 * crop_border) * (W - 2 * crop_border);
+  int gx = grid_for(n, 256 * 8, 4);
+  psnr_u8_sums_kernel<<<dim3(gx, B), 256, 0, stream>>>(img1, img2, C, H, W, crop_border, sse, max1);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}

@@ -79,6 +79,7 @@ SIGNATURES = {
     "tdr_ema_update": (_i, [_vp, _vp, _ll, _f, _vp]),
     "tdr_l1_loss_grad": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _vp, _vp]),
     "tdr_prepare_patches": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "tdr_psnr_u8_sums": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "tdr_nchw_to_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_nhwc_to_nchw": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _vp]),
     "tdr_copy_rows_f32": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp, _ll, _vp]),

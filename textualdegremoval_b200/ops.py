@@ -776,3 +776,28 @@ def prepare_patches(frames, crops, size, bgr2rgb=True, mean=None, std=None, out=
           C.cast(m, C.c_void_p) if m is not None else None, C.cast(sd, C.c_void_p) if sd is not None else None,
           out.data_ptr(), _stream(), tag=f"n{n}_{out_h}x{out_w}", nbytes=out.numel() * 4 + n * out_h * out_w * ch)
     return out
+
+
+def psnr_u8(result, gt, crop_border=0):
+    """Validation PSNR of ``calculate_psnr(tensor2img(result), tensor2img(gt), crop_border)`` (metrics/psnr_ssim.py:9-63,
+    utils/utils_image.py:129-191; ``test_y_channel=False``) per image of fp32 NCHW CUDA batches: the uint8 quantisation
+    and the integer sums run on the device, 12 bytes per image come back, and the float64 tail is the reference's own
+    formula -- the returned doubles are identical to the reference's.  Returns a list of floats (``inf`` for equal images)."""
+    import numpy as np
+    assert result.dtype == F32 and gt.dtype == F32 and result.shape == gt.shape and result.dim() == 4
+    result, gt = result.contiguous(), gt.contiguous()
+    B, Cc, H, W = result.shape
+    sse = torch.empty(B, dtype=torch.int64, device=result.device)
+    mx = torch.empty(B, dtype=torch.int32, device=result.device)
+    _call("tdr_psnr_u8_sums", result.data_ptr(), gt.data_ptr(), B, Cc, H, W, crop_border, sse.data_ptr(), mx.data_ptr(),
+          _stream(), tag=f"{Cc}x{H}x{W}", nbytes=2 * result.numel() * 4)
+    n = Cc * (H - 2 * crop_border) * (W - 2 * crop_border)
+    out = []
+    for s_, m_ in zip(sse.tolist(), mx.tolist()):
+        mse = np.float64(s_) / np.float64(n)                       # np.mean of exact integers in float64
+        if mse == 0:
+            out.append(float("inf"))
+            continue
+        max_value = 1. if m_ <= 1 else 255.
+        out.append(float(20. * np.log10(max_value / np.sqrt(mse))))
+    return out
