@@ -103,3 +103,49 @@ def test_fusion_off_is_the_plain_schedule(monkeypatch):
     monkeypatch.setattr(A, "ops", r)
     A.run_stack(torch.zeros(1, 8, 8, 48), [_prep(48, 0), _prep(48, 1)])
     assert sum(c[0] == "rownorm" for c in r.calls) == 4 and not _ln_args(r.calls)
+
+
+# ------------------------------------------------------------------------------------------------ training forward
+class _TrainRecorder(_Recorder):
+    def conv_gemm(self, x, w, Co, **kw):
+        ln = kw.get("ln")
+        if ln is not None:
+            ln[4].fill_(float(len(self.calls)))            # mark the emitted norm tensor with its producer's position
+        return super().conv_gemm(x, w, Co, **kw)
+
+    def dwconv3x3_gated_train(self, x, w, b, gate):
+        self.calls.append(("dw_train", gate))
+        B, H, W, C = x.shape
+        return torch.zeros(B, H, W, C // 2, dtype=torch.bfloat16), torch.zeros(B, H, W, C, dtype=torch.bfloat16)
+
+    def mdta_weff(self, qkv, C, heads, temp, w_po, save=None, **kw):
+        if save is not None:
+            save.update(shat=None, attn=None, weff=None, weff_t=None)
+        return super().mdta_weff(qkv, C, heads, temp, w_po)
+
+    def scale_add(self, x, y, scale_ptr=None, **kw):
+        self.calls.append(("scale_add",))
+        return torch.zeros_like(x)
+
+
+def test_training_tape_keeps_the_norms_the_convs_emitted(monkeypatch):
+    from textualdegremoval_b200.archs import restormer_train as TR
+    r = _TrainRecorder()
+    monkeypatch.setattr(A, "ops", r)
+    monkeypatch.setattr(TR, "ops", r)
+    preps = [dict(_prep(96, i), train=True) for i in range(3)]
+    tape = []
+    out, span = TR.run_stack_train(torch.zeros(1, 8, 8, 96), preps, [None] * 3, tape)
+    assert span == (0, 3) and len(tape) == 3 and out.shape == (1, 8, 8, 96)
+    assert sum(c[0] == "rownorm" for c in r.calls) == 1                   # only the first norm1 is a launch
+    for i, sv in enumerate(tape):
+        assert sv["xn1"] is not sv["xn2"] and sv["xn1"].dtype == torch.bfloat16
+        if i:                                                              # block i's xn1 is what block i-1's last conv wrote
+            assert sv["xn1"] is not tape[i - 1]["xn2"]
+            assert float(sv["xn1"].flatten()[0]) > float(tape[i - 1]["xn2"].flatten()[0])
+    ln = _ln_args(r.calls)
+    assert [a[1] for a in ln] == [preps[0]["ln2_w"], preps[1]["ln1_w"], preps[1]["ln2_w"], preps[2]["ln1_w"],
+                                  preps[2]["ln2_w"]]
+    # every tape entry keeps its own tensors (the backward reads them after later blocks ran)
+    kept = [id(sv[k]) for sv in tape for k in ("xn1", "xn2")]
+    assert len(set(kept)) == len(kept)
