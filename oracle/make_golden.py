@@ -165,7 +165,8 @@ def main_nafnet():
 
 
 
-GRAD_CASES = {"restormer_withbias": "restormer", "guided_restormer_128": "guided"}
+GRAD_CASES = {"restormer_withbias": "restormer", "guided_restormer_128": "guided", "nafnet_rgb_ragged": "nafnet",
+              "guided_nafnet_256": "guided_nafnet"}
 
 
 def grad_probe(name, g):
@@ -180,8 +181,19 @@ def main_grads():
     (norm, probe) fingerprints, not the full tensors."""
     torch.set_grad_enabled(True)
     for name, kind in GRAD_CASES.items():
-        case = (RESTORMER_CASES if kind == "restormer" else GUIDED_CASES)[name]
-        if kind == "restormer":
+        case = dict(restormer=RESTORMER_CASES, guided=GUIDED_CASES, nafnet=NAFNET_CASES, guided_nafnet=NAF_GUIDED_CASES)[kind][name]
+        if kind == "nafnet":                       # LayerNormFunction's hand-written backward (nafnet_arch_utils.py:277-289)
+            net = R.nafnet(**case["cfg"])
+            W.load_seeded(net, case["seed"])
+            x, gt = denoise_inputs(case)
+            y = net(x)
+        elif kind == "guided_nafnet":
+            net = R.nafnet_ref_fusion(**case["cfg"])
+            W.load_seeded(net, case["seed"])
+            lq, ref = guided_inputs(case)
+            gt = W.seeded_image("gt", case["lq"], case["seed"])
+            y = net(lq, ref)
+        elif kind == "restormer":
             net = R.restormer(**case["cfg"])
             W.load_seeded(net, case["seed"])
             x = W.seeded_image("x", case["shape"], case["seed"])

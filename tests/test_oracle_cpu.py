@@ -171,6 +171,37 @@ def test_oracle_vs_live_reference():
         assert (net(lq, rf) - O.restormer_ref_fusion_forward(sd, lq, rf)).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize("name", ["nafnet_rgb_ragged", "guided_nafnet_256"])
+def test_nafnet_oracle_autograd_matches_reference_gradients(name):
+    """Same pin for the NAFNet family: the reference differentiates LayerNorm2d with its hand-written
+    LayerNormFunction.backward (nafnet_arch_utils.py:277-289); the oracle's plain autograd must agree with it."""
+    from oracle.make_golden import GRAD_CASES, grad_probe
+    from textualdegremoval_b200.archs.nafnet_b200_arch import NAFNet, NAFNetRefFusion
+    z = np.load(os.path.join(GOLD, name + "_grad.npz"))
+    meta = json.loads(str(z["meta"]))
+    guided = GRAD_CASES[name] == "guided_nafnet"
+    sd = W.seeded_state_dict(_shapes(NAFNetRefFusion if guided else NAFNet, meta["cfg"]), meta["seed"])
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    if guided:
+        lq, rf = guided_inputs(meta)
+        gt = W.seeded_image("gt", meta["lq"], meta["seed"])
+        y = ON.nafnet_ref_fusion_forward(sdg, lq, rf)
+    else:
+        x, gt = denoise_inputs(meta)
+        y = ON.nafnet_forward(sdg, x)
+    loss = (y - gt).abs().mean()
+    loss.backward()
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-6
+    total = float(np.sqrt((z["norms"] ** 2).sum()))
+    assert len(z["names"]) == len(sdg)
+    for n, norm, probe in zip(z["names"].tolist(), z["norms"].tolist(), z["probes"].tolist()):
+        g = sdg[n].grad if sdg[n].grad is not None else torch.zeros_like(sdg[n])
+        a, b = grad_probe(n, g)
+        tol = 2e-4 * max(norm, 1e-3 * total)
+        assert abs(a - norm) < tol, (n, a, norm)
+        assert abs(b - probe) < tol * max(1.0, float(g.numel()) ** 0.5), (n, b, probe)
+
+
 @pytest.mark.parametrize("name", ["restormer_withbias", "guided_restormer_128"])
 def test_oracle_autograd_matches_reference_gradients(name):
     """The oracle's autograd (the checker of the CUDA backward schedule) against per-parameter gradient fingerprints of
