@@ -164,3 +164,30 @@ def test_cpu_tensors_are_refused():
     net = define_network(dict(type="Restormer", dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1))
     with pytest.raises(TdrError):
         net(torch.rand(1, 3, 64, 64))
+
+
+def test_modules_are_deepcopyable_for_ema():
+    """Boundary contract: the nets must be deep-copy-able (EMA / checkpoint helpers of
+    models/base_model.py) -- copies own their parameters, and the cached weight packs of the original can never be
+    mistaken for the copy's (the cache key is (data_ptr, version) of every parameter)."""
+    import copy
+    from textualdegremoval_b200 import define_network
+    opts = [dict(type="Restormer", dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1, heads=[1, 2, 2, 4]),
+            dict(type="RestormerRefFusion", dim=16, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1, heads=[1, 2, 2, 4],
+                 nf=16, ext_n_blocks=[1, 1, 1, 1], reffusion_n_blocks=[1, 1, 1, 1]),
+            dict(type="NAFNet", img_channel=3, width=16, middle_blk_num=1, enc_blk_nums=[1, 1], dec_blk_nums=[1, 1])]
+    for opt in opts:
+        net = define_network(dict(opt))
+        twin = copy.deepcopy(net)
+        sd, sd2 = net.state_dict(), twin.state_dict()
+        assert list(sd) == list(sd2)
+        for k in sd:
+            assert torch.equal(sd[k], sd2[k]) and sd[k].data_ptr() != sd2[k].data_ptr()
+        assert [n for n, _ in net.named_parameters()] == [n for n, _ in twin.named_parameters()]
+        if hasattr(net, "_prep_key"):
+            assert net._prep_key() != twin._prep_key()
+        # EMA update in place (base_model.py:54-62): twin = decay * twin + (1 - decay) * net
+        with torch.no_grad():
+            for p, q in zip(net.parameters(), twin.parameters()):
+                q.mul_(0.999).add_(p, alpha=0.001)
+        assert all(torch.allclose(p, q, atol=1e-6) for p, q in zip(net.parameters(), twin.parameters()))
