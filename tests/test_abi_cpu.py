@@ -191,3 +191,19 @@ def test_modules_are_deepcopyable_for_ema():
             for p, q in zip(net.parameters(), twin.parameters()):
                 q.mul_(0.999).add_(p, alpha=0.001)
         assert all(torch.allclose(p, q, atol=1e-6) for p, q in zip(net.parameters(), twin.parameters()))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="/root/reference not present")
+def test_dino_state_dict_keys_match_reference():
+    """DINO boundary: `vit_base(img_size=518, patch_size=14, init_values=1.0, ffn_layer='mlp',
+    block_chunks=0)` must load the released checkpoint with strict=True -> identical key names and shapes as
+    models/dino/vision_transformers.py; H, W not multiples of 14 is an AssertionError (models/dino/patch_embed.py:72-73)."""
+    from oracle import ref_loader as R
+    R._stub_packages()
+    from models.dino.vision_transformers import vit_base as ref_vit_base
+    from textualdegremoval_b200.archs.vit_b200 import vit_base
+    kw = dict(img_size=518, patch_size=14, init_values=1.0, ffn_layer="mlp", block_chunks=0)
+    a = vit_base(**kw).state_dict()
+    b = ref_vit_base(**kw).state_dict()
+    assert list(a) == list(b)
+    assert all(a[k].shape == b[k].shape for k in b)
