@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(256) psnr_u8_sums_kernel(const float* __restri
 extern "C" int tdr_psnr_u8_sums(const float* img1, const float* img2, int B, int C, int H, int W, int crop_border,
                                 unsigned long long* sse, int* max1, cudaStream_t stream) {
   TDR_CHECK_ARG(img1 && img2 && sse && max1, "tdr_psnr_u8_sums: null pointer");
+  TDR_CHECK_ARG(B <= 65535, "tdr_psnr_u8_sums: at most 65535 images per call (got %d)", B);
   TDR_CHECK_ARG(B > 0 && C > 0 && crop_border >= 0 && H > 2 * crop_border && W > 2 * crop_border,
                 "tdr_psnr_u8_sums: empty window (B %d C %d H %d W %d crop %d)", B, C, H, W, crop_border);
   TDR_CHECK_CUDA(cudaMemsetAsync(sse, 0, sizeof(unsigned long long) * B, stream));
