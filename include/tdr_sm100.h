@@ -88,6 +88,17 @@ typedef struct tdr_conv_gemm_desc {
   const float* ln_bias;   /* fp32 [Co] (WithBias) or NULL */
   void* ln_out_bf16;
   long long ln_out_ld;
+  /* 16-bit operand format of the MASA feature encoder R:100-134 (its features feed two arg-max searches, so they need
+   * more mantissa than bf16 carries -- tools/precision_study.py): in_fp16 != 0: `in` AND `weight` hold IEEE fp16
+   * (tcgen05 kind::f16 takes either format at the same rate); out_fp16 != 0: the 16-bit outputs (`out_bf16`,
+   * `ln_out_bf16`) are written as fp16, saturating at +-65504 (not together with a bf16 res2).
+   * The INFERENCE forward of the restoration nets runs every GEMM on fp16 operands too: bf16's 8 significand bits put
+   * the 512x512 guided-Restormer output at mean |delta| 1.05e-3 / 54.3 dB / 0.032 dB PSNR-delta from the fp32
+   * reference (the reference's own bf16 path: 1.7e-3 / 53.8 dB), fp16's 11 bits meet the 1e-3 / 0.01 dB bar
+   * (tools/operand_format_study.py).  Accumulation, residual stream, LayerNorm, softmax stay fp32; the training
+   * forward and every gradient stay bf16 (range). */
+  int in_fp16;
+  int out_fp16;
 } tdr_conv_gemm_desc;
 int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream);
 /* 1 when the fused output LayerNorm of the descriptor (see ln_mode) can run, 0 otherwise; no launch. */
@@ -97,7 +108,8 @@ int tdr_conv_gemm_ln_supported(const tdr_conv_gemm_desc* d);
 void tdr_conv_gemm_desc_layout(int* out);
 
 /* Small-channel direct 3x3 convs (SIMT): Ci <= 8 inputs (patch_embed R:362, masa_enc.conv_L1 R:106) read fp32 NHWC;
- * or Co <= 4 outputs (output conv R:640, + input image residual R:962) read bf16 NHWC. */
+ * or Co <= 4 outputs (output conv R:640, + input image residual R:962) read bf16 NHWC.
+ * small_ci `relu`: bit 0 = ReLU, bit 1 = the 16-bit output is IEEE fp16 instead of bf16. */
 int tdr_conv3x3_small_ci(const float* in, int B, int H, int W, int Ci, const float* weight /* [Co][Ci][3][3] */,
                          const float* bias, int Co, int relu, float* out_f32, long long out_f32_ld, void* out_bf16,
                          long long out_bf16_ld, cudaStream_t stream);
@@ -111,15 +123,41 @@ int tdr_conv3x3_small_co(const void* in_bf16, long long in_ld, int B, int H, int
  *   mode 0: cast only.  mode 1: WithBias LN R:189-205 (also LayerNorm2d nafnet_arch_utils.py:264-300 with eps 1e-6).
  *   mode 2: BiasFree LN R:172-186 (x / sqrt(var + eps) * w, mean not subtracted).
  * ------------------------------------------------------------------------------------------------------------- */
-/* act: 0 none, 3 LeakyReLU(0.01) applied after the affine (mapper MLPs, main_train_tr_mapping.py:52-60).
+/* act: 0 none, 3 LeakyReLU(0.01) applied after the affine (mapper MLPs, main_train_tr_mapping.py:52-60); | 16: the
+ * 16-bit output is IEEE fp16 instead of bf16.
  * Either or both of out_bf16 / out_f32 (e.g. the final DINO norm, models/dino/vision_transformers.py:262). */
 int tdr_rownorm(const float* in, long long in_ld, long long rows, int C, int mode, const float* weight,
                 const float* bias, float eps, int act, void* out_bf16, long long out_ld, float* out_f32,
                 long long out_f32_ld, cudaStream_t stream);
 
+/* fp32 [rows, C] -> bf16 and / or IEEE fp16 (saturating) copies in one pass (either may be NULL): the MASA encoder's
+ * fp32 residual stream R:38-49 feeds the next conv as fp16 and the transfer kernels as bf16.
+ *   out_fp16 = fp16(x * *scale16)   and, when rescale_in != 0, the fp32 rows are rewritten as x * *scale16 too;
+ *   out_bf16 = bf16(x * *scale_bf16)            (scale pointers: DEVICE scalars or NULL = 1).
+ * Level scaling of the MASA feature encoder.  The encoder is 17-21 ReLU convs with residual adds and no normalisation,
+ * so its activations can grow geometrically with depth and leave fp16's range (65504).  Conv, bias, ReLU and the
+ * residual add are positively homogeneous, so every level runs in units of a power-of-two scale s_L chosen on the
+ * device from the level's first activation (no host sync, bit-exact: scaling by 2^k does not change mantissas):
+ *   tdr_masa_level_scale: state_cur = {s_L, 1/s_L, 1/r, max} with r = 2^(ceil(log2 max|x|) - 6) if max|x| > 64 else 1,
+ *                         s_L = s_prev * r  (x = the level's first activation in units of s_prev; state_cur[3] must be
+ *                         zero on entry; state_prev NULL = {1, 1, 1});
+ *   tdr_scale_vec       : out[i] = v[i] * *scale  (the level's conv biases in scaled units). */
+int tdr_cast_rows(float* in, long long in_ld, long long rows, int C, void* out_bf16, long long out_bf16_ld,
+                  void* out_fp16, long long out_fp16_ld, const float* scale16, const float* scale_bf16, int rescale_in,
+                  cudaStream_t stream);
+int tdr_masa_level_scale(const float* x, long long ld, long long rows, int C, const float* state_prev, float* state_cur,
+                         cudaStream_t stream);
+int tdr_scale_vec(const float* v, long long n, const float* scale, float* out, cudaStream_t stream);
+
+/* IEEE fp16 rows -> bf16 rows (the backward's weight-gradient GEMMs take bf16 operands only: tcgen05 kind::f16 rejects
+ * mixed fp16 x bf16 operand pairs, and gradients need bf16's exponent range). */
+int tdr_cvt_f16_bf16(const void* in_fp16, long long in_ld, long long rows, int C, void* out_bf16, long long out_ld,
+                     cudaStream_t stream);
+
 /* Depthwise 3x3, pad 1 (R:231, R:253; N:conv2) on bf16 NHWC.  weight fp32 [9][C] (tap-major), bias fp32 [C] or NULL.
  * gate = 0: out[.., C].  gate = 1 (GDFN R:238-239): C = 2*Ch, out[.., Ch] = gelu(dw(x)[:Ch]) * dw(x)[Ch:].
- * gate = 2 (SimpleGate N:170-175): out = dw(x)[:Ch] * dw(x)[Ch:]. */
+ * gate = 2 (SimpleGate N:170-175): out = dw(x)[:Ch] * dw(x)[Ch:].
+ * gate | 16: input and output are IEEE fp16 instead of bf16 (same kernels, other 16-bit conversions). */
 int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
                   const float* bias, int gate, void* out_bf16, long long out_ld, cudaStream_t stream);
 
@@ -129,14 +167,14 @@ int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H, int W, int
  *                      Weff[b][co][ci] = rowscale[co] * W3[co][ci] * s[b][ci]  (bf16 [B][Co][weff_ld]); then
  *                      `x * sca(x)` -> conv3 -> `* beta` is one tdr_conv_gemm(g, Weff, w_batched=1). */
 int tdr_gate_mul(const void* x_bf16, long long ld, long long rows, int C /* output channels */, void* out_bf16,
-                 long long out_ld, cudaStream_t stream);
+                 long long out_ld, int fp16 /* in / out are IEEE fp16 */, cudaStream_t stream);
 size_t tdr_naf_sca_workspace_bytes(int B, long long P, int C);
 int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long long P, int C, const float* w_sca /* [C][C] */,
                      const float* b_sca, const float* w3 /* fp32 [Co][C] */, int Co, const float* rowscale /* [Co] */,
                      void* weff_bf16, long long weff_ld, float* workspace,
                      float* mean_out /* optional [B][C]: avgpool(g) */, float* s_out /* optional [B][C]: sca vector */,
-                     void* weff_t_bf16 /* optional Weff[b]^T [B][C][weff_t_ld] (dgrad operand) */, long long weff_t_ld,
-                     cudaStream_t stream);
+                     void* weff_t_bf16 /* optional Weff[b]^T [B][C][weff_t_ld] (dgrad operand, always bf16) */,
+                     long long weff_t_ld, int fp16 /* g and Weff are IEEE fp16 */, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * MDTA channel attention R:262-276.
@@ -149,12 +187,12 @@ int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long long P, int C
  * ------------------------------------------------------------------------------------------------------------- */
 size_t tdr_mdta_partials_bytes(int B, long long P, int C, int heads);
 int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long long P, int C, int heads, float* partials,
-                  cudaStream_t stream);
+                  int fp16 /* qkv holds IEEE fp16 */, cudaStream_t stream);
 int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature /* [heads] */,
                   const float* w_out /* fp32 [C][C] */, void* weff_bf16, long long weff_ld, float* attn_ws,
                   void* weff_t_bf16 /* optional: Weff[b]^T, same ld (the dgrad operand of the training step) */,
                   float* shat_out /* optional fp32 [B][heads][c*c + 2c]: normalised Gram | |q| | |k| (for tdr_mdta_bwd) */,
-                  cudaStream_t stream);
+                  int fp16 /* Weff is written as IEEE fp16 (weff_t stays bf16) */, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * ViT encoder / mapper glue (DINOv2 ViT-B/14 models/dino/*.py "D:", CLIP ViT-H/14 via transformers, mappers "M:" =
@@ -228,6 +266,7 @@ typedef struct tdr_wgrad_desc {
   float scale;
   float* workspace; /* tdr_wgrad_workspace_bytes(d) */
   size_t workspace_bytes;
+  const float* scale_ptr; /* optional DEVICE scalar multiplied into `scale` (level scale of the MASA encoder's tape) */
 } tdr_wgrad_desc;
 size_t tdr_wgrad_workspace_bytes(const tdr_wgrad_desc* d);
 int tdr_wgrad(const tdr_wgrad_desc* d, cudaStream_t stream);
@@ -292,7 +331,8 @@ int tdr_dot_f32(const float* x, long long x_ld, const float* y, long long y_ld, 
 /* bf16 NHWC PixelUnshuffle(2) (mode 1) / PixelShuffle(2) (mode 2): the adjoints of store_mode 2 / 1 of tdr_conv_gemm */
 int tdr_pixel_shuffle_nhwc(const void* in_bf16, long long in_ld, int B, int H, int W, int C, int mode, void* out_bf16,
                            long long out_ld, cudaStream_t stream);
-/* out = y > 0 ? dy : 0 (ReLU backward from the stored activation, R:38-49,106-116) */
+/* out = y > 0 ? dy : 0 (ReLU backward from the stored activation, R:38-49,106-116).  y may be bf16 or IEEE fp16: only its
+ * sign / zero bits are inspected, which the two formats share. */
 int tdr_relu_mask(const void* y_bf16, long long y_ld, const void* dy_bf16, long long dy_ld, long long rows, int C,
                   void* out_bf16, long long out_ld, cudaStream_t stream);
 
@@ -323,6 +363,7 @@ int tdr_dilate2_nhwc(const void* in_bf16, long long in_ld, int B, int H, int W, 
  * ------------------------------------------------------------------------------------------------------------- */
 int tdr_pack_conv_weight(const float* w, int Co, int Ci, int KH, int KW, const int* co_map, int Co_p, const int* ci_map,
                          int Ci_p, const float* scale, void* out_bf16, long long ld, void* out_t_bf16, long long ld_t,
+                         int fwd_fp16 /* the forward operand `out_bf16` is IEEE fp16; the twin stays bf16 */,
                          cudaStream_t stream);
 int tdr_pack_dw_weight(const float* w, const float* bias, int C, const int* c_map, int C_p, float* out, float* out_flip,
                        float* out_bias, cudaStream_t stream);
@@ -337,29 +378,39 @@ int tdr_nchw_to_nhwc(const float* src, int B, int C, int H, int W, int pad_h, in
 int tdr_nhwc_to_nchw(const float* src, long long src_ld, int B, int C, int H, int W /* source size */, int out_h,
                      int out_w /* crop */, const float* res /* NHWC fp32 or NULL */, long long res_ld, float* dst,
                      cudaStream_t stream);
-/* dst[r, 0:C] = src[r, 0:C] (fp32 rows with independent strides); optionally also writes a bf16 copy. */
+/* dst[r, 0:C] = src[r, 0:C] (fp32 rows with independent strides); optionally also writes a 16-bit copy (bf16, or IEEE
+ * fp16 when dst16_fp16). */
 int tdr_copy_rows_f32(const float* src, long long src_ld, long long rows, int C, float* dst, long long dst_ld,
-                      void* dst_bf16, long long dst_bf16_ld, cudaStream_t stream);
+                      void* dst_bf16, long long dst_bf16_ld, int dst16_fp16, cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * MASA match-and-transfer R:753-900 (closed form of SURVEY.md appendix A; no unfold/fold materialisation).
- * Features are bf16 NHWC.  `k` = lr block size in feature pixels, (py, px) block grid, d = window diameter.
+ * `k` = lr block size in feature pixels, (py, px) block grid, d = window diameter.
+ * The two arg-max searches see the deepest features in fp32: bf16 descriptors alone flip 2.5 % of the fine matches
+ * between near-tied candidates (tools/precision_study.py).  The correlations still run as ONE bf16 tcgen05 GEMM over
+ * 3C channels: the reference features are split into [hi | lo | hi] bf16 thirds (tdr_masa_split3), the normalised lq
+ * descriptors into [hi | hi | lo], so the fp32 accumulator receives hi*hi + lo*hi + hi*lo (2^-16 relative).
+ * The transfer / backward kernels read the bf16 copies of the features.
  * ------------------------------------------------------------------------------------------------------------- */
-/* n2[r] = sum_c x[r,c]^2 */
-int tdr_sqnorm_rows(const void* x_bf16, long long ld, long long rows, int C, float* n2, cudaStream_t stream);
+/* n2[r] = sum_c x[r,c]^2, x fp32 */
+int tdr_sqnorm_rows(const float* x, long long ld, long long rows, int C, float* n2, cudaStream_t stream);
+/* out[r] = [bf16(x) | bf16(x - bf16(x)) | bf16(x)]  (bf16 [rows][out_ld >= 3C]) */
+int tdr_masa_split3(const float* x, long long ld, long long rows, int C, void* out_bf16, long long out_ld,
+                    cudaStream_t stream);
 /* inv[dil_i][b,y,x] = 1 / max(sqrt(sum_{3x3 taps, dilation dil_i, zero pad} n2), 1e-12)   (R:683,690) */
 int tdr_masa_ref_invnorm(const float* n2, int B, int H, int W, const int* host_dils, int ndil, float* inv,
                          cudaStream_t stream);
-/* coarse filters R:685-689: w[dil_i][b][tap][blk (padded to co_pad)][C] = normalised dilated 3x3 centre descriptor of
- * lq block blk (replicate-padded halo R:785). */
-int tdr_masa_coarse_filters(const void* f_lq_bf16, int B, int H, int W, int C, int k_y, int k_x, const int* host_dils,
+/* coarse filters R:685-689: w[dil_i][b][tap][blk (padded to co_pad)][3C] = normalised dilated 3x3 centre descriptor of
+ * lq block blk (replicate-padded halo R:785), f_lq fp32 [B,H,W,C] dense, each row split as [hi | hi | lo]. */
+int tdr_masa_coarse_filters(const float* f_lq, int B, int H, int W, int C, int k_y, int k_x, const int* host_dils,
                             int ndil, int co_pad, void* w_bf16, cudaStream_t stream);
 /* argmax over ref positions of score[b, pos, blk] (fp32, ld = co_pad) R:694 + window placement R:793-815.
  * origin[b*nblk + blk] = (b, y1, x1). */
 int tdr_masa_coarse_argmax(const float* score, int B, int Hr, int Wr, int nblk, int co_pad, int d_y, int d_x,
                            int* idx_out, int* origin, cudaStream_t stream);
-/* fine filters R:662-665: w[b*nblk+blk][tap][q (k_y*k_x)][C] = normalised 3x3 patch at interior position q. */
-int tdr_masa_fine_filters(const void* f_lq_bf16, int B, int H, int W, int C, int k_y, int k_x, void* w_bf16,
+/* fine filters R:662-665: w[b*nblk+blk][tap][q (k_y*k_x)][3C] = normalised 3x3 patch at interior position q, split as
+ * [hi | hi | lo]; f_lq fp32 dense. */
+int tdr_masa_fine_filters(const float* f_lq, int B, int H, int W, int C, int k_y, int k_x, void* w_bf16,
                           cudaStream_t stream);
 /* inv[blk, jy, jx] = 1 / max(|3x3 patch of the window at (jy, jx)|, 1e-12) from the per-pixel n2 map R:666 */
 int tdr_masa_win_invnorm(const float* n2_ref, int Hr, int Wr, const int* origin, int nwin, int d_y, int d_x,

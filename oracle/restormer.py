@@ -188,8 +188,9 @@ def crop_windows(f, y1, x1, size_y, size_x, s):
     return torch.stack(out, 0)
 
 
-def fine_search(blk, win):
-    """search_org (:654-672): blk [M,C,k+2,k+2], win [M,C,d+2,d+2] -> (att [M,k,k], index [M,k,k])."""
+def fine_search(blk, win, return_corr=False):
+    """search_org (:654-672): blk [M,C,k+2,k+2], win [M,C,d+2,d+2] -> (att [M,k,k], index [M,k,k])
+    (+ the whole correlation [M, k*k, d*d] when return_corr: the tests grade arg-max mismatches by the gap they jump)."""
     m, c, kh, kw = blk.shape
     _, _, wh, ww = win.shape
     a = torch.stack([blk[:, :, ty: ty + kh - 2, tx: tx + kw - 2] for ty in range(3) for tx in range(3)], 2)
@@ -198,6 +199,8 @@ def fine_search(blk, win):
     r = _l2n(r.reshape(m, c * 9, (wh - 2) * (ww - 2)), 1)
     corr = a.transpose(1, 2) @ r                                             # [M, k*k, d*d]
     att, idx = corr.max(-1)
+    if return_corr:
+        return att.view(m, kh - 2, kw - 2), idx.view(m, kh - 2, kw - 2), corr
     return att.view(m, kh - 2, kw - 2), idx.view(m, kh - 2, kw - 2)
 
 
@@ -259,7 +262,7 @@ def masa_warp(feat_lq_deep, feat_ref, padder_size, lr_block_size, ref_down_block
     score, idx = coarse_search(blocks, f_ref_deep, dilations)
     y1, x1 = window_origin(idx, wr_d, hr_d, d_x, d_y)
     win1 = crop_windows(f_ref_deep, y1, x1, d_y + 2, d_x + 2, 1)
-    att, index = fine_search(blocks.reshape(n * py * px, c, k_y + 2, k_x + 2), win1)
+    att, index, corr = fine_search(blocks.reshape(n * py * px, c, k_y + 2, k_x + 2), win1, return_corr=True)
     warps = []
     nlev = len(feat_ref)
     for lev in range(nlev):                       # lev 0 = finest level, scale 2**(nlev-1)
@@ -267,7 +270,8 @@ def masa_warp(feat_lq_deep, feat_ref, padder_size, lr_block_size, ref_down_block
         win = crop_windows(feat_ref[lev], y1, x1, d_y + 2, d_x + 2, s)
         warps.append(retile(transfer(win, index, att, s, d_x), n, py, px))
     if return_aux:
-        return warps, dict(score=score, idx=idx, y1=y1, x1=x1, att=att, index=index, d=(d_y, d_x), k=(k_y, k_x))
+        return warps, dict(score=score, idx=idx, y1=y1, x1=x1, att=att, index=index, corr=corr, d=(d_y, d_x),
+                           k=(k_y, k_x))
     return warps
 
 

@@ -257,6 +257,129 @@ CONV_CASES = [
 ]
 
 
+def check_fp16_path():
+    """The fp16-operand instantiations used by the MASA feature encoder (R:100-134): tdr_conv_gemm with in_fp16 / out_fp16
+    (TMA and generic epilogues), tdr_cast_rows, tdr_pack_conv_weight_f16, tdr_masa_split3, tdr_wgrad on an fp16 tape
+    (converted to bf16 first),
+    tdr_relu_mask on fp16 activations -- each against fp32 CPU math on the same fp16-rounded operands."""
+    ops = _ops()
+    F16 = torch.float16
+    qh = lambda t: t.to(F16).float()
+    out = []
+    for (name, B, H, W, Ci, Co, k, st, relu, res, o16) in (
+            ("3x3_48_relu_h", 2, 16, 16, 48, 48, 3, 1, True, False, True),
+            ("3x3_96_res32", 1, 16, 24, 96, 96, 3, 1, False, True, False),
+            ("3x3_s2_f32", 2, 32, 32, 48, 96, 3, 2, True, False, False),
+            ("3x3_192_relu_h", 1, 16, 16, 192, 192, 3, 1, True, False, True),
+            ("3x3_s2_h", 1, 16, 16, 16, 32, 3, 2, True, False, True)):
+        x = qh(rnd(B, Ci, H, W, seed=Ci + H))
+        w = rnd(Co, Ci, k, k, seed=Co) * (1.0 / (Ci * k * k) ** 0.5)
+        b = rnd(Co, seed=3) * 0.2
+        wp = ops.pack_conv_weight_f16(w.to(DEV))
+        y = F.conv2d(x, qh(w), b, stride=st, padding=1)
+        if relu:
+            y = F.relu(y)
+        r2 = None
+        if res:
+            r2 = rnd(*y.shape, seed=14)
+            y = y + r2
+        o32, oh = ops.conv_gemm(nhwc(x.to(F16)), wp, Co, k=k, stride=st, pad=1, bias=b.to(DEV), relu=relu,
+                                res2=nhwc(r2) if res else None, want="bf16" if o16 else "f32", out_fp16=o16)
+        if o16:
+            assert oh.dtype == F16
+            out.append(result(f"conv_fp16_{name}", nchw(oh), y, 1.5e-3))
+        else:
+            out.append(result(f"conv_fp16_{name}", nchw(o32), y, 2e-4))
+    # saturation instead of inf
+    x = torch.full((1, 16, 8, 8), 200.0)
+    w = torch.full((8, 16, 1, 1), 100.0)
+    _, oh = ops.conv_gemm(nhwc(x.to(F16)), ops.pack_conv_weight_f16(w.to(DEV)), 8, out_fp16=True)
+    out.append(dict(name="conv_fp16_saturates", max_err=float((oh.float() - 65504.0).abs().max()), ref_scale=65504.0,
+                    tol=0.0, ok=bool((oh.float() == 65504.0).all())))
+    # cast_rows / split3
+    xr = rnd(3, 5, 7, 48, seed=2) * 3
+    xb, xh = ops.cast_rows(xr.to(DEV), want_bf16=True, want_fp16=True)
+    out.append(result("cast_rows_bf16", xb.float().cpu(), q(xr), 0.0))
+    out.append(result("cast_rows_fp16", xh.float().cpu(), qh(xr), 0.0))
+    s3 = ops.masa_split3(xr.to(DEV)).float().cpu()
+    hi = q(xr)
+    out.append(result("split3_hi", s3[..., :48], hi, 0.0))
+    out.append(result("split3_lo", s3[..., 48:96], q(xr - hi), 0.0))
+    out.append(result("split3_hi2", s3[..., 96:], hi, 0.0))
+    out.append(result("split3_sum", s3[..., :48] + s3[..., 48:96], xr, 2.0 ** -16))
+    # wgrad with fp16 activations (ops.wgrad converts them to bf16: tolerance = bf16 rounding of x), bf16 dy
+    for (B, H, W, Ci, Co, k, st) in ((2, 16, 16, 48, 48, 3, 1), (1, 16, 16, 96, 192, 3, 2), (1, 8, 24, 96, 96, 1, 1)):
+        x = qh(rnd(B, Ci, H, W, seed=Ci + H))
+        wt = torch.zeros(Co, Ci, k, k, requires_grad=True)
+        y = F.conv2d(x, wt, None, stride=st, padding=k // 2)
+        dy = q(rnd(*y.shape, seed=Co + W))
+        (ref,) = torch.autograd.grad(y, wt, dy)
+        dw = torch.zeros((Co, Ci, k, k), device=DEV)
+        ops.wgrad(nhwc(dy.to(BF16)), nhwc(x.to(F16)), dw, k=k, stride=st, pad=k // 2, accumulate=False)
+        out.append(grad_result(f"wgrad_fp16x_Ci{Ci}_Co{Co}_k{k}s{st}", dw, ref, 5e-3))
+    # relu_mask reads only sign / zero bits: identical for bf16 and fp16 activations
+    yv = rnd(2, 4, 4, 32, seed=9)
+    yv[0, 0, 0, :4] = torch.tensor([0.0, -0.0, 1e-7, -1e-7])
+    dyv = q(rnd(2, 4, 4, 32, seed=10))
+    for dt, nm in ((F16, "fp16"), (BF16, "bf16")):
+        y16 = yv.to(dt)
+        got = ops.relu_mask(y16.to(DEV), dyv.to(BF16).to(DEV)).float().cpu()
+        out.append(result(f"relu_mask_{nm}", got, torch.where(y16.float() > 0, dyv, torch.zeros_like(dyv)), 0.0))
+    # ---- the inference forward's fp16 instantiations of the block kernels (ops.operand_dtype) --------------------------
+    for (C_, H, W, gate, bias) in ((48, 9, 13, 0, False), (144, 16, 16, 0, True), (256, 8, 21, 1, False),
+                                   (32, 5, 4, 2, True), (1024, 6, 8, 1, True)):
+        x = qh(rnd(2, C_, H, W, seed=C_ + H))
+        w = rnd(C_, 1, 3, 3, seed=3) * 0.3
+        b = rnd(C_, seed=4) * 0.1 if bias else None
+        y = ops.dwconv3x3(nhwc(x.to(F16)), ops.pack_dw_weight(w.to(DEV)), b.to(DEV) if bias else None, gate)
+        assert y.dtype == F16
+        out.append(result(f"dwconv_fp16_C{C_}_{H}x{W}_g{gate}", nchw(y), _dw_ref(x, w, b, gate), 1.5e-3))
+    from oracle import restormer as O
+    xr = rnd(2, 96, 7, 9, seed=21) * 2 + 0.5
+    lw, lb = rnd(96, seed=22) * 0.5 + 1.0, rnd(96, seed=23) * 0.3
+    for mode in (0, 1, 2):
+        got = ops.rownorm(nhwc(xr), mode, lw.to(DEV), lb.to(DEV) if mode == 1 else None, 1e-5, dt=F16)
+        ref = xr if mode == 0 else O.layernorm_c(xr, lw, lb if mode == 1 else None)
+        out.append(result(f"rownorm_fp16_m{mode}", nchw(got), ref, 6e-4))
+    xg = qh(rnd(2, 64, 9, 11, seed=5))
+    out.append(result("gate_mul_fp16", nchw(ops.gate_mul(nhwc(xg.to(F16)))), xg[:, :32] * xg[:, 32:], 1e-3))
+    # MDTA Gram + fold on fp16 q, k
+    for (C_, heads, H, W, B) in ((96, 2, 16, 16, 2), (48, 1, 16, 24, 1)):
+        c = C_ // heads
+        qkv = qh(rnd(B, 3 * C_, H, W, seed=C_ + heads))
+        temp = torch.rand(heads, generator=torch.Generator().manual_seed(1)) + 0.5
+        wpo = rnd(C_, C_, seed=2) / C_ ** 0.5
+        qq, kk, vv = qkv.view(B, 3, heads, c, H * W).unbind(1)
+        qn = qq / qq.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        kn = kk / kk.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        attn = torch.softmax(qn @ kn.transpose(-1, -2) * temp.view(1, heads, 1, 1), -1)
+        weff_ref = torch.zeros(B, C_, C_)
+        for h in range(heads):
+            weff_ref[:, :, h * c:(h + 1) * c] = wpo[:, h * c:(h + 1) * c] @ attn[:, h]
+        weff, attn_g = ops.mdta_weff(nhwc(qkv.to(F16)), C_, heads, temp.to(DEV), wpo.to(DEV), want_attn=True)
+        assert weff.dtype == F16
+        out.append(result(f"mdta_fp16_attn_C{C_}_h{heads}", attn_g, attn, 2e-4))
+        out.append(result(f"mdta_fp16_weff_C{C_}_h{heads}", weff[..., :C_], weff_ref, 1e-3))
+    # 1x1 conv + residual + fused LayerNorm with fp16 operands and fp16 LN output; PixelShuffle store of an fp16 output
+    B, Ci, Co, H, W = 2, 256, 96, 20, 24
+    x = qh(rnd(B, Ci, H, W, seed=H + Ci))
+    w = rnd(Co, Ci, 1, 1, seed=Co) * (1.0 / Ci ** 0.5)
+    r2 = rnd(B, Co, H, W, seed=14) * 2.0 + 0.7
+    y = F.conv2d(x, qh(w)) + r2
+    lw, lb = rnd(Co, seed=15) * 0.5 + 1.0, rnd(Co, seed=16) * 0.3
+    ln_out = ops.rows16(B, H, W, Co, DEV, F16)
+    o32, _ = ops.conv_gemm(nhwc(x.to(F16)), ops.pack_conv_weight(w.to(DEV), dt=F16), Co, res2=nhwc(r2), want="f32",
+                           ln=(1, lw.to(DEV), lb.to(DEV), 1e-5, ln_out))
+    out.append(result("conv_ln_fp16_f32", nchw(o32), y, 2e-4))
+    out.append(result("conv_ln_fp16_ln", nchw(ln_out), O.layernorm_c(y, lw, lb), 1.5e-3))
+    x = qh(rnd(1, 96, 8, 16, seed=31))
+    w = rnd(192, 96, 3, 3, seed=32) * (1.0 / (96 * 9) ** 0.5)
+    _, oh = ops.conv_gemm(nhwc(x.to(F16)), ops.pack_conv_weight(w.to(DEV), dt=F16), 192, k=3, pad=1, store_mode=2)
+    assert oh.dtype == F16
+    out.append(result("conv_fp16_pixel_shuffle", nchw(oh), F.pixel_shuffle(F.conv2d(x, qh(w), padding=1), 2), 1.5e-3))
+    return out
+
+
 def check_conv_ln():
     """1x1 conv + residual with the LayerNorm of the finished rows emitted by the same epilogue (norm1 / norm2 of
     R:318-331 folded into the producing conv): fp32 rows must equal the plain epilogue's, the bf16 LN output must match
@@ -444,31 +567,52 @@ def check_block():
         p = A._prep_block(blk)
         x32 = nhwc(x)
         A.run_block(x32, p)
-        out.append(result(f"block_d{dim}_h{heads}_{ln}_b{int(bias)}_f{int(fusion)}", nchw(x32), ref, 1.5e-2))
+        out.append(result(f"block_d{dim}_h{heads}_{ln}_b{int(bias)}_f{int(fusion)}", nchw(x32), ref, 2e-3,
+                          note="inference schedule: fp16 operands, fp32 stream"))
     return out
 
 
 # =============================================================================================== MASA
+def _tile_mask(index_g, index_r, same_win, B, py, px):
+    """[B, py, px] bool: windows whose coarse placement and all fine indices agree with the oracle."""
+    return ((index_g == index_r).all(dim=1) & same_win).view(B, py, px)
+
+
+def _warp_on_agreeing_tiles(name, got, ref, ok_tiles, rtol):
+    """Compare a warped-feature map only inside the windows whose matches agree (the others gather from a different
+    place by construction).  got / ref NCHW [B, C, py*t, px*t]."""
+    B, py, px = ok_tiles.shape
+    t_y, t_x = got.shape[2] // py, got.shape[3] // px
+    m = ok_tiles.repeat_interleave(t_y, 1).repeat_interleave(t_x, 2).unsqueeze(1).float()
+    r = result(name, got * m, ref * m, rtol)
+    r["note"] = f"compared on {int(ok_tiles.sum())}/{ok_tiles.numel()} windows with identical matches"
+    r["ok"] = r["ok"] and bool(ok_tiles.any())
+    return r
+
+
 def check_masa():
-    """MASA search/transfer kernels vs the oracle on identical (bf16-rounded) features."""
+    """MASA search/transfer kernels vs the oracle on identical features: the searches see the SAME fp32 deepest-level
+    features as the oracle (split-bf16 correlations, 2^-16 relative), the transfer gathers from bf16 copies."""
     from oracle import restormer as O
     from textualdegremoval_b200.archs import restormer_b200_arch as A
     ops = _ops()
     out = []
-    for (B, nf, h, w, hr, wr, seed) in ((2, 16, 128, 128, 128, 128, 1), (1, 8, 128, 192, 192, 128, 2)):
+    for (B, nf, h, w, hr, wr, seed) in ((2, 16, 128, 128, 128, 128, 1), (1, 8, 128, 192, 192, 128, 2),
+                                        (1, 16, 256, 256, 256, 256, 3)):
         net = A.RestormerRefFusion(dim=nf, nf=nf, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1,
                                    ext_n_blocks=[1, 1, 1, 1])
         g = torch.Generator().manual_seed(seed)
         smooth = lambda t: F.avg_pool2d(t, 3, 1, 1)
-        f_lq_deep = q(smooth(torch.randn(B, nf * 8, h // 8, w // 8, generator=g)))
-        f_ref = [q(smooth(torch.randn(B, nf * 2 ** i, hr >> i, wr >> i, generator=g))) for i in range(4)]
+        f_lq_deep = smooth(torch.randn(B, nf * 8, h // 8, w // 8, generator=g))          # NOT bf16-representable
+        f_ref = [q(smooth(torch.randn(B, nf * 2 ** i, hr >> i, wr >> i, generator=g))) for i in range(3)]
+        f_ref.append(smooth(torch.randn(B, nf * 8, hr >> 3, wr >> 3, generator=g)))
         warps_ref, aux = O.masa_warp(f_lq_deep, f_ref, 8, 8, 1.5, [1, 2, 3], h, w, hr, wr, return_aux=True)
         d = [nf, nf * 2, nf * 4, nf * 8]
         targets = [torch.zeros(B, h >> i, w >> i, d[i], device=DEV) for i in range(4)]
-        a = net._masa_warp(nhwc(f_lq_deep.to(BF16)), [nhwc(t.to(BF16)) for t in f_ref], h, w, hr, wr, targets)
+        a = net._masa_warp(nhwc(f_lq_deep), nhwc(f_ref[-1]), [nhwc(t.to(BF16)) for t in f_ref], h, w, hr, wr, targets)
         tag = f"{h}x{w}_{hr}x{wr}"
         score = a["score"][..., : aux["score"].shape[1]].reshape(B, -1, aux["score"].shape[1]).permute(0, 2, 1)
-        out.append(result(f"masa_coarse_score_{tag}", score, aux["score"], 2e-3))
+        out.append(result(f"masa_coarse_score_{tag}", score, aux["score"], 2e-5, note="split-bf16 (hi+lo) correlation"))
         agree = (a["idx"].cpu().long() == aux["idx"]).float().mean().item()
         out.append(dict(name=f"masa_coarse_idx_{tag}", max_err=1 - agree, ref_scale=1, tol=0.0, ok=agree == 1.0,
                         note="fraction of blocks whose arg-max differs"))
@@ -479,15 +623,14 @@ def check_masa():
         idx_g = a["index"].cpu().long().view(-1, nq)
         idx_r = aux["index"].view(-1, nq)
         agree_f = (idx_g == idx_r)[same_win].float().mean().item() if same_win.any() else 0.0
-        out.append(dict(name=f"masa_fine_idx_{tag}", max_err=1 - agree_f, ref_scale=1, tol=0.02, ok=agree_f >= 0.98,
-                        note="fraction of fine matches that differ (near-ties allowed <= 2%)"))
-        out.append(result(f"masa_att_{tag}", a["att"].view(-1, nq), aux["att"].view(-1, nq), 3e-3))
-        if agree == 1.0 and agree_f == 1.0:
-            for i in range(4):
-                out.append(result(f"masa_warp_l{i}_{tag}", nchw(targets[i]), warps_ref[i], 2e-3))
-        else:
-            out.append(dict(name=f"masa_warp_{tag}", max_err=0, ref_scale=1, tol=0, ok=True,
-                            note="skipped value check: indices differ"))
+        out.append(dict(name=f"masa_fine_idx_{tag}", max_err=1 - agree_f, ref_scale=1, tol=1e-3, ok=agree_f >= 0.999,
+                        note="fraction of fine matches that differ on identical fp32 features (bar: <= 0.1 %)"))
+        out.append(result(f"masa_att_{tag}", a["att"].view(-1, nq), aux["att"].view(-1, nq), 2e-5))
+        g_ = a["geom"]
+        ok_tiles = _tile_mask(idx_g, idx_r, same_win, B, g_["py"], g_["px"])
+        for i in range(4):      # deepest level: the transfer reads the bf16 copy of fp32 features (2^-9 relative)
+            out.append(_warp_on_agreeing_tiles(f"masa_warp_l{i}_{tag}", nchw(targets[i]), warps_ref[i], ok_tiles,
+                                               4e-3 if i == 3 else 2e-3))
     return out
 
 
@@ -505,25 +648,41 @@ def psnr_u8(a, b):
     return float("inf") if mse == 0 else 20 * np.log10(255.0 / np.sqrt(mse))
 
 
-# end-to-end forward tolerance (max |delta| vs the fp32 reference output, outputs are O(1) images)
-E2E_TOL = 2e-2
-# Guided nets contain two arg-max searches (MASA coarse/fine).  With bf16 features a few near-tied fine matches flip
-# (measured 95-98 % index agreement on random-weight features, coarse matches agree), which changes the output
-# discontinuously inside the affected 8x8 patches.  Their end-to-end criterion is therefore mean |delta| and PSNR on
-# uint8-rounded outputs (val.use_image semantics); the max is reported, and index agreement is measured separately.
-GUIDED_MEAN_TOL = 5e-3
-GUIDED_PSNR_MIN = 45.0
+# End-to-end forward parity against the fp32 reference output (outputs are O(1) images).  north_star: |delta| < 1e-3 and
+# PSNR within 0.01 dB.  Asserted here:
+#   mean |delta| <= 1e-3                    the north-star number, on the mean;
+#   max  |delta| <= 9.6e-3                  documented bf16 max tolerance: the reference's OWN bf16 forward differs from
+#                                           its fp32 forward by max 9.6e-3 / mean 1.7e-3 / 53.8 dB (SURVEY 8c calibration,
+#                                           random-init Restormer 128x128) -- GEMM operands here are bf16 by the metric's
+#                                           definition, everything else (residual stream, LN, softmax, Gram) is fp32;
+#   PSNR_u8(ours, reference) >= 55 dB       uint8-rounded outputs (val.use_image semantics);
+#   |PSNR(ours, gt) - PSNR(reference, gt)| <= 0.01 dB against a synthetic ground truth at ~38 dB.
+E2E_MEAN_TOL = 1e-3
+E2E_TOL = 9.6e-3
+E2E_PSNR_MIN = 55.0
+PSNR_DELTA_TOL = 0.01
+GUIDED_MEAN_TOL, GUIDED_PSNR_MIN = E2E_MEAN_TOL, E2E_PSNR_MIN
 
 
 def guided_result(name, y, ref):
     r = result(name, y, ref, 1.0)
+    mx = r["max_err"]
     mean = (y - ref).abs().mean().item()
     ps = psnr_u8(y, ref)
-    r["ok"] = bool(torch.isfinite(y).all() and mean <= GUIDED_MEAN_TOL and ps >= GUIDED_PSNR_MIN)
-    r["tol"] = GUIDED_MEAN_TOL
-    r["note"] = f"max|d|={r['max_err']:.2e} mean|d|={mean:.2e} (tol, on the mean) psnr_u8(ours,ref)={ps:.2f}dB"
-    r["max_err"] = mean
+    r["ok"] = bool(torch.isfinite(y).all() and mean <= E2E_MEAN_TOL and mx <= E2E_TOL and ps >= E2E_PSNR_MIN)
+    r["tol"] = E2E_TOL
+    r["note"] = (f"max|d|={mx:.2e} (<= {E2E_TOL:g}) mean|d|={mean:.2e} (<= {E2E_MEAN_TOL:g}) "
+                 f"psnr_u8(ours,ref)={ps:.2f}dB (>= {E2E_PSNR_MIN:g})")
     return r
+
+
+def psnr_delta_result(name, y, ref, seed):
+    """PSNR against a ground truth vs the reference's PSNR against it (val.use_image semantics: uint8)."""
+    from oracle import weights as Wt
+    gt = (ref + 0.05 * (Wt.seeded_image("gt_noise", ref.shape, seed) - 0.5)).clamp(0, 1)
+    dp = abs(psnr_u8(y, gt) - psnr_u8(ref, gt))
+    return dict(name=f"psnr_delta_{name}", max_err=dp, tol=PSNR_DELTA_TOL, ok=bool(dp <= PSNR_DELTA_TOL),
+                note=f"PSNR(ours, gt) {psnr_u8(y, gt):.4f} dB vs PSNR(reference, gt) {psnr_u8(ref, gt):.4f} dB (bar 0.01 dB)")
 
 
 def check_restormer_golden():
@@ -538,9 +697,8 @@ def check_restormer_golden():
         x = Wt.seeded_image("x", meta["shape"], meta["seed"])
         with torch.no_grad():
             y = net(x.to(DEV)).cpu()
-        r = result(f"golden_{name}", y, ref, E2E_TOL / max(ref.abs().max().item(), 1e-6))
-        r["note"] = f"mean|d|={(y - ref).abs().mean().item():.2e} psnr_u8(ours,ref)={psnr_u8(y, ref):.2f}dB"
-        out.append(r)
+        out.append(guided_result(f"golden_{name}", y, ref))
+        out.append(psnr_delta_result(name, y, ref, meta["seed"]))
     return out
 
 
@@ -558,16 +716,59 @@ def check_guided_golden():
         with torch.no_grad():
             y = net(lq.to(DEV), rf.to(DEV)).cpu()
         out.append(guided_result(f"golden_{name}", y, ref))
-        # PSNR against a ground truth vs the reference's PSNR against it (val.use_image semantics: uint8).  The
-        # north-star bar is 0.01 dB; with an rms deviation of 1.4e-3 between the two outputs (57-58 dB, heavy-tailed: the
-        # MASA arg-max flips) the difference is 10 log10(1 + e^2/sigma^2): 0.006-0.016 dB at a 37.8 dB ground truth, i.e.
-        # the bar is met for one fixture and missed for the other.  The test bounds it at 0.03 dB and reports the value.
-        gt = (ref + 0.05 * (Wt.seeded_image("gt_noise", ref.shape, meta["seed"]) - 0.5)).clamp(0, 1)
-        dp = abs(psnr_u8(y, gt) - psnr_u8(ref, gt))
-        out.append(dict(name=f"psnr_delta_{name}", max_err=dp, tol=0.03, ok=bool(dp < 0.03),
-                        note=f"PSNR(ours, gt) {psnr_u8(y, gt):.3f} dB vs PSNR(reference, gt) {psnr_u8(ref, gt):.3f} dB; "
-                             f"north-star bar 0.01 dB {'met' if dp < 0.01 else 'NOT met'}"))
+        out.append(psnr_delta_result(name, y, ref, meta["seed"]))
     return out
+
+
+class _ForcedMatches:
+    """Test hook: run a guided net with the ORACLE's coarse / fine matches instead of its own arg-max results (the
+    confidence is re-read from our own correlation at the forced index).  Around 1 % of the fine searches of a
+    random-weight fixture are decided by score gaps below 3e-6 -- the oracle's own fp32 summation noise -- and every
+    such tie that resolves the other way moves a 3s x 3s patch of warped reference features at every scale; the guided
+    NAFNet amplifies one flipped match to |delta| 7e-2.  End-to-end parity is therefore asserted in two parts: the
+    matches agree up to ties (_match_agreement / _book_agreement), and GIVEN identical matches the output meets the bar."""
+
+    def __init__(self, y1, x1, index):
+        self.y1, self.x1, self.index = y1.reshape(-1), x1.reshape(-1), index
+
+    def __enter__(self):
+        ops = _ops()
+        self.ops, self.c, self.f = ops, ops.masa_coarse_argmax, ops.masa_fine_argmax
+
+        def coarse(score, nblk, d_y, d_x):
+            idx, origin = self.c(score, nblk, d_y, d_x)
+            origin[:, 1] = self.y1.to(origin)
+            origin[:, 2] = self.x1.to(origin)
+            return idx, origin
+
+        def fine(corr):
+            index, att = self.f(corr)
+            forced = self.index.reshape(index.shape).to(index)
+            nwin, dy, dx, nq = corr.shape
+            att_f = corr.view(nwin, dy * dx, nq).gather(1, forced.long().unsqueeze(1)).squeeze(1).contiguous()
+            return forced.contiguous(), att_f
+
+        ops.masa_coarse_argmax, ops.masa_fine_argmax = coarse, fine
+        return self
+
+    def __exit__(self, *exc):
+        self.ops.masa_coarse_argmax, self.ops.masa_fine_argmax = self.c, self.f
+
+
+# Unconditional bound for the guided NAFNet (informational beside the conditional check above): a handful of tied matches
+# resolve differently and each one costs a visible patch.
+NAF_GUIDED_PSNR_MIN = 45.0
+
+
+def naf_unconditional_result(name, y, ref):
+    r = guided_result(name, y, ref)
+    ps = psnr_u8(y, ref)
+    mean = (y - ref).abs().mean().item()
+    r["ok"] = bool(torch.isfinite(y).all() and ps >= NAF_GUIDED_PSNR_MIN and mean <= 2e-3)
+    r["tol"] = None
+    r["note"] = ("own matches (tied searches may resolve differently, see _ForcedMatches): " + r["note"] +
+                 f"; asserted here: psnr >= {NAF_GUIDED_PSNR_MIN:g} dB, mean <= 2e-3")
+    return r
 
 
 def check_nafnet():
@@ -597,17 +798,24 @@ def check_nafnet():
         lq, _ = denoise_inputs(meta)
         with torch.no_grad():
             yy = net(lq.to(DEV)).cpu()
-        r = result(f"golden_{name}", yy, ref, E2E_TOL / max(ref.abs().max().item(), 1e-6))
-        r["note"] = f"mean|d|={(yy - ref).abs().mean().item():.2e} psnr_u8(ours,ref)={psnr_u8(yy, ref):.2f}dB"
-        out.append(r)
+        out.append(guided_result(f"golden_{name}", yy, ref))
+        out.append(psnr_delta_result(name, yy, ref, meta["seed"]))
     meta, ref = _golden("guided_nafnet_256")
     net = define_network(dict(type="NAFNetRefFusion", **meta["cfg"]))
     Wt.load_seeded(net, meta["seed"])
     net = net.to(DEV).eval()
     lq, rf = guided_inputs(meta)
     with torch.no_grad():
-        yy = net(lq.to(DEV), rf.to(DEV)).cpu()
-    out.append(guided_result("golden_guided_nafnet_256", yy, ref))
+        yy, aux = net(lq.to(DEV), rf.to(DEV), return_aux=True)
+        yy = yy.cpu()
+        _, aux_r = ON.nafnet_ref_fusion_forward(Wt.seeded_state_dict({k_: v.shape for k_, v in net.state_dict().items()},
+                                                                     meta["seed"]), lq, rf, return_aux=True)
+    out += _match_agreement("naf_stage", aux, aux_r)
+    out.append(naf_unconditional_result("golden_guided_nafnet_256_own_matches", yy, ref))
+    with _ForcedMatches(aux_r["y1"], aux_r["x1"], aux_r["index"]), torch.no_grad():
+        yf = net(lq.to(DEV), rf.to(DEV)).cpu()
+    out.append(guided_result("golden_guided_nafnet_256", yf, ref))
+    out.append(psnr_delta_result("guided_nafnet_256", yf, ref, meta["seed"]))
     return out
 
 
@@ -726,19 +934,57 @@ def check_guided_stages():
     for i in range(4):
         out.append(result(f"stage_feat_lq_l{i}", nchw(aux["feat_lq"][i]), aux_r["feat_lq"][i], 2e-2))
         out.append(result(f"stage_feat_ref_l{i}", nchw(aux["feat_ref"][i]), aux_r["feat_ref"][i], 2e-2))
-    agree = (aux["idx"].cpu().long() == aux_r["idx"]).float().mean().item()
-    out.append(dict(name="stage_coarse_idx", max_err=1 - agree, ref_scale=1, tol=0.0, ok=True,
-                    note=f"agreement {agree:.3f} (informational: bf16 features may flip near-ties)"))
+    ds = float(aux["deep_scale"][0])          # the deepest level runs in units of a power-of-two scale (masa._masa_encode)
+    out.append(result("stage_deep32_lq", nchw(aux["deep32_lq"]) * ds, aux_r["feat_lq"][3], 2e-3,
+                      note=f"fp32 stream of the deepest level (fp16 GEMM operands), level scale {ds:g}"))
+    out.append(result("stage_deep32_ref", nchw(aux["deep32_ref"]) * ds, aux_r["feat_ref"][3], 2e-3))
+    out += _match_agreement("stage", aux, aux_r)
+    B = lq.shape[0]
     nq = aux_r["index"].shape[1] * aux_r["index"].shape[2]
-    agree_f = (aux["index"].cpu().long().view(-1, nq) == aux_r["index"].view(-1, nq)).float().mean().item()
-    out.append(dict(name="stage_fine_idx", max_err=1 - agree_f, ref_scale=1, tol=0.0, ok=True,
-                    note=f"agreement {agree_f:.3f} (informational)"))
+    y1 = aux["origin"][:, 1].view(B, -1).cpu().long()
+    x1 = aux["origin"][:, 2].view(B, -1).cpu().long()
+    same_win = ((y1 == aux_r["y1"]) & (x1 == aux_r["x1"])).view(-1)
+    ok_tiles = _tile_mask(aux["index"].cpu().long().view(-1, nq), aux_r["index"].view(-1, nq), same_win, B,
+                          aux["geom"]["py"], aux["geom"]["px"])
     for i in range(4):
-        r = result(f"stage_warp_l{i}", nchw(aux["warps"][i]), aux_r["warps"][i], 1.0)
-        r["note"] = f"mean|d|={(nchw(aux['warps'][i]) - aux_r['warps'][i]).abs().mean().item():.2e} (informational)"
-        out.append(r)
+        out.append(_warp_on_agreeing_tiles(f"stage_warp_l{i}", nchw(aux["warps"][i]), aux_r["warps"][i], ok_tiles, 1e-2))
     out.append(guided_result("stage_output", y.cpu(), y_ref))
     return out
+
+
+FINE_AGREE_MIN = 0.999
+# Arg-max mismatches across a gap below TIE_TOL in the ORACLE's own fp32 score are ties, not errors: the oracle's fp32
+# dot products over 9C = 1296..9216 terms carry ~1e-6 of summation-order noise themselves (the 128x128 fixture has a
+# coarse top-2 gap of 1.19e-6 = one fp32 ulp, which the reference's own result depends on the BLAS build for).
+TIE_TOL = 1e-5
+
+
+def _match_agreement(tag, aux, aux_r):
+    """Coarse / fine arg-max agreement of an end-to-end run with the oracle's (same inputs, our features vs fp32).
+    A mismatch counts as agreement when the oracle's score of our candidate is within TIE_TOL of its maximum."""
+    sc = aux_r["score"]                                          # [B, nblk, Hr*Wr]
+    B, nblk, _ = sc.shape
+    ours = aux["idx"].cpu().long().view(B, nblk)
+    gap_c = sc.max(-1).values - sc.gather(2, ours.unsqueeze(-1)).squeeze(-1)
+    exact_c = (ours == aux_r["idx"]).float().mean().item()
+    agree_c = (gap_c <= TIE_TOL).float().mean().item()
+    nq = aux_r["index"].shape[1] * aux_r["index"].shape[2]
+    y1 = aux["origin"][:, 1].view(B, -1).cpu().long()
+    x1 = aux["origin"][:, 2].view(B, -1).cpu().long()
+    same_win = ((y1 == aux_r["y1"]) & (x1 == aux_r["x1"])).view(-1)
+    corr = aux_r["corr"]                                         # [M, nq, d*d] in the oracle's windows
+    mine = aux["index"].cpu().long().view(-1, nq)
+    gap_f = corr.max(-1).values - corr.gather(2, mine.unsqueeze(-1)).squeeze(-1)
+    exact_f = (mine == aux_r["index"].view(-1, nq))[same_win].float().mean().item() if same_win.any() else 0.0
+    agree_f = (gap_f <= TIE_TOL)[same_win].float().mean().item() if same_win.any() else 0.0
+    worst = gap_f[same_win].max().item() if same_win.any() else float("nan")
+    return [dict(name=f"{tag}_coarse_idx", max_err=1 - agree_c, ref_scale=1, tol=0.0, ok=agree_c == 1.0,
+                 note=f"coarse arg-max: identical {exact_c:.4f}, identical up to ties < {TIE_TOL:g} {agree_c:.4f}; "
+                      f"largest oracle-score gap jumped {gap_c.max().item():.2e}"),
+            dict(name=f"{tag}_fine_idx", max_err=1 - agree_f, ref_scale=1, tol=1 - FINE_AGREE_MIN,
+                 ok=agree_f >= FINE_AGREE_MIN,
+                 note=f"fine arg-max in {int(same_win.sum())}/{same_win.numel()} identically placed windows: identical "
+                      f"{exact_f:.4f}, up to ties {agree_f:.4f} (bar 99.9 %); largest gap jumped {worst:.2e}")]
 
 
 
@@ -1150,7 +1396,7 @@ def check_nafnet_grad():
     net = net.to(DEV).train()
     y = net(lq.to(DEV), rf.to(DEV))
     (y - gt.to(DEV)).abs().mean().backward()
-    out.append(guided_result("train_fwd_guided_nafnet_256", y.detach().cpu(), yr.detach()))
+    out.append(naf_unconditional_result("train_fwd_guided_nafnet_256", y.detach().cpu(), yr.detach()))
     tot, worst, groups = _grad_compare("guided_nafnet_256", net, sdg, out)
     note = f"worst tensor {worst[0]} {worst[1]:.3f}; " + ", ".join(f"{k_}={v:.3f}" for k_, v in sorted(groups.items(), key=lambda kv: -kv[1])[:5])
     out.append(dict(name="grad_global_guided_nafnet_256", max_err=tot, tol=0.03, ok=bool(tot <= 0.03), note=note))
@@ -1194,8 +1440,9 @@ def check_fullsize_properties():
                 p.uniform_(0.2, 1.0)
         yb = net(lq, ref)
         y1 = torch.cat([net(lq[i:i + 1], ref[i:i + 1]) for i in range(2)])
-    out.append(result("fullsize_batch_equals_samples", yb, y1, 2e-3,
-                      note="split-K Gram chunking depends on the batch size: summation order differs"))
+    out.append(result("fullsize_batch_equals_samples", yb, y1, 0.0,
+                      note="bit-identical: no reduction order depends on the batch size (the MDTA Gram split is a function "
+                           "of (P, heads) only)"))
     out.append(dict(name="fullsize_guidance_changes_output", ok=bool((yb[:1] - y0).abs().max().item() > 1e-3),
                     max_err=(yb[:1] - y0).abs().max().item(), tol=None))
     # (iii) backward: deterministic and linear in dout
@@ -1219,6 +1466,86 @@ def check_fullsize_properties():
                     max_err=None, tol=None))
     return out
 
+def _book_agreement(tag, aux, z):
+    """Arg-max agreement against a full-size fixture's match book (top-3 candidates + fp32 scores of every coarse /
+    fine arg-max, written by oracle/make_golden_fullsize.py): a mismatch is a tie when our candidate is one of the
+    oracle's top-3 within TIE_TOL of its maximum."""
+    cv, ci = torch.from_numpy(z["coarse_top_val"]), torch.from_numpy(z["coarse_top_idx"]).long()
+    fv, fi = torch.from_numpy(z["fine_top_val"]), torch.from_numpy(z["fine_top_idx"]).long()
+    B, nblk, _ = ci.shape
+
+    def grade(mine, top_i, top_v):
+        hit = (top_i == mine.unsqueeze(-1)) & ((top_v[..., :1] - top_v) <= TIE_TOL)
+        return (top_i[..., 0] == mine), hit.any(-1)
+
+    ex_c, ok_c = grade(aux["idx"].cpu().long().view(B, nblk), ci, cv)
+    y1 = aux["origin"][:, 1].view(B, -1).cpu().long()
+    x1 = aux["origin"][:, 2].view(B, -1).cpu().long()
+    same_win = ((y1 == torch.from_numpy(z["y1"]).long()) & (x1 == torch.from_numpy(z["x1"]).long())).view(-1)
+    nq = fi.shape[1]
+    ex_f, ok_f = grade(aux["index"].cpu().long().view(-1, nq), fi, fv)
+    a_c, a_f = ok_c.float().mean().item(), ok_f[same_win].float().mean().item()
+    return [dict(name=f"{tag}_coarse_idx", max_err=1 - a_c, ref_scale=1, tol=0.0, ok=a_c == 1.0,
+                 note=f"coarse arg-max over {B * nblk} blocks: identical {ex_c.float().mean().item():.4f}, up to ties "
+                      f"< {TIE_TOL:g} {a_c:.4f}"),
+            dict(name=f"{tag}_fine_idx", max_err=1 - a_f, ref_scale=1, tol=1 - FINE_AGREE_MIN, ok=a_f >= FINE_AGREE_MIN,
+                 note=f"fine arg-max over {int(same_win.sum()) * nq} positions: identical "
+                      f"{ex_f[same_win].float().mean().item():.4f}, up to ties {a_f:.4f} (bar 99.9 %)")]
+
+
+def check_fullsize_golden():
+    """The BASELINE.json configurations at FULL size against outputs of the unmodified reference modules
+    (tests/golden/full_*.npz, oracle/make_golden_fullsize.py): guided Restormer option 003 @512x512 (the headline
+    config), guided NAFNet option 002 @512x512, Restormer option 017 @256x256, DINOv2 ViT-B/14 @518x518, CLIP ViT-H/14
+    @224x224 (third-party transformers; version in the fixture)."""
+    from oracle import weights as Wt
+    from oracle.make_golden_fullsize import fullsize_inputs
+    from textualdegremoval_b200.archs import define_network, vit_b200 as VB
+    out = []
+    for name in ("full_guided_restormer_512", "full_guided_nafnet_512", "full_restormer_256", "full_dino_vitb_518",
+                 "full_clip_vith_224"):
+        z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+        meta, ref = json.loads(str(z["meta"])), torch.from_numpy(z["out"])
+        kind = meta["kind"]
+        lq, rf, _ = fullsize_inputs(meta)
+        if kind in ("guided_restormer", "guided_nafnet", "restormer"):
+            typ = dict(guided_restormer="RestormerRefFusion", guided_nafnet="NAFNetRefFusion", restormer="Restormer")[kind]
+            net = define_network(dict(type=typ, **meta["cfg"]))
+        elif kind == "dino":
+            net = VB.vit_base(**meta["cfg"])
+        else:
+            net = VB.CLIPVisionTower(**meta["cfg"])
+        Wt.load_seeded(net, meta["seed"])
+        net = net.to(DEV).eval()
+        with torch.no_grad():
+            if kind in ("guided_restormer", "guided_nafnet"):
+                y, aux = net(lq.to(DEV), rf.to(DEV), return_aux=True)
+                out += _book_agreement(name, aux, z)
+                if kind == "guided_nafnet":         # parity GIVEN the oracle's matches is the asserted one (see _ForcedMatches)
+                    out.append(naf_unconditional_result(f"golden_{name}_own_matches", y.cpu(), ref))
+                    with _ForcedMatches(torch.from_numpy(z["y1"]), torch.from_numpy(z["x1"]),
+                                        torch.from_numpy(z["fine_top_idx"][..., 0])):
+                        y = net(lq.to(DEV), rf.to(DEV))
+            elif kind == "clip":
+                y = net(lq.to(DEV), output_hidden_states=True)[0]
+            else:
+                y = net(lq.to(DEV))
+        y = y.cpu()
+        if kind in ("dino", "clip"):
+            # token features (O(1-5) values after the final / no final norm): relative to the fixture's scale
+            r = result(f"golden_{name}", y, ref, 2e-2)
+            rel = ((y - ref).norm() / ref.norm()).item()
+            r["note"] = f"max|d|={r['max_err']:.2e} of scale {r['ref_scale']:.2f}; rel-L2 {rel:.2e} (<= 5e-3)"
+            r["ok"] = r["ok"] and rel <= 5e-3
+            out.append(r)
+        else:
+            out.append(guided_result(f"golden_{name}", y, ref))
+            out.append(psnr_delta_result(name, y, ref, meta["seed"]))
+        del net
+        torch.cuda.empty_cache()
+    return out
+
+
 CHECKS = {
     "layout": check_layout,
     "rownorm": check_rownorm,
@@ -1229,6 +1556,7 @@ CHECKS = {
     "conv_tc": check_conv_tc,
     "conv_origin": check_conv_origin,
     "conv_ln": check_conv_ln,
+    "fp16_path": check_fp16_path,
     "input_pipeline": check_input_pipeline,
     "psnr": check_psnr,
     "mdta": check_mdta,
@@ -1248,6 +1576,7 @@ CHECKS = {
     "train_step": check_train_step,
     "nafnet_grad": check_nafnet_grad,
     "fullsize_properties": check_fullsize_properties,
+    "fullsize_golden": check_fullsize_golden,
 }
 
 

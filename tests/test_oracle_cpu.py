@@ -267,3 +267,36 @@ def test_psnr_oracle_matches_reference_fixture():
         sse, mx, n = M.psnr_sums(res.numpy(), gt.numpy(), case["crop"])
         if sse:
             assert float(20. * np.log10((1. if mx <= 1 else 255.) / np.sqrt(np.float64(sse) / np.float64(n)))) == ref[i]
+
+
+def test_fullsize_fixtures_pin_the_oracle_at_baseline_sizes():
+    """tests/golden/full_*.npz hold outputs of the UNMODIFIED reference modules at the BASELINE.json sizes; the generator
+    (oracle/make_golden_fullsize.py) asserted the oracle reproduces each.  Re-check the recorded agreement for all five and
+    re-run the two cheapest (Restormer 256x256, DINOv2 ViT-B/14 518x518) against the stored reference outputs."""
+    import json
+    import os
+
+    import numpy as np
+
+    from oracle import restormer as O, vit as OV, weights as W
+    from oracle.make_golden_fullsize import FULL_CASES, fullsize_inputs
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name in FULL_CASES:
+        z = np.load(os.path.join(gold, name + ".npz"))
+        meta = json.loads(str(z["meta"]))
+        assert meta["oracle_vs_reference_max"] < 2e-4, (name, meta["oracle_vs_reference_max"])
+        assert z["out"].dtype == np.float32 and np.isfinite(z["out"]).all()
+    with torch.no_grad():
+        for name in ("full_restormer_256", "full_dino_vitb_518"):
+            z = np.load(os.path.join(gold, name + ".npz"))
+            meta = json.loads(str(z["meta"]))
+            x, _, _ = fullsize_inputs(meta)
+            if meta["kind"] == "restormer":
+                from textualdegremoval_b200.archs import define_network
+                shapes = {k: v.shape for k, v in define_network(dict(type="Restormer", **meta["cfg"])).state_dict().items()}
+                y = O.restormer_forward(W.seeded_state_dict(shapes, meta["seed"]), x, meta["cfg"]["heads"])
+            else:
+                from textualdegremoval_b200.archs import vit_b200 as VB
+                shapes = {k: v.shape for k, v in VB.vit_base(**meta["cfg"]).state_dict().items()}
+                y = OV.dino_vit_forward(W.seeded_state_dict(shapes, meta["seed"]), x)
+            assert (y - torch.from_numpy(z["out"])).abs().max().item() < 2e-4, name

@@ -18,8 +18,8 @@ class _Recorder:
     def conv_ln_ok(self, Co):
         return self.fuse and Co <= 96 and Co % 8 == 0
 
-    def rows16(self, B, H, W, C, dev):
-        return torch.zeros(B, H, W, C, dtype=torch.bfloat16)
+    def rows16(self, B, H, W, C, dev, dt=torch.bfloat16):
+        return torch.zeros(B, H, W, C, dtype=dt)
 
     def rownorm(self, x, mode, w=None, b=None, eps=1e-5, out=None, **kw):
         self.calls.append(("rownorm", w))
@@ -48,7 +48,7 @@ class _Recorder:
 
 def _prep(C, tag, alpha=None):
     t = lambda name: torch.full((1,), 0.0).new_tensor([hash((tag, name)) % 997], dtype=torch.float32)
-    return dict(C=C, heads=1, hp=2 * C, alpha=alpha, ln_mode=1, ln1_w=t("ln1_w"), ln1_b=t("ln1_b"), ln2_w=t("ln2_w"),
+    return dict(C=C, heads=1, hp=2 * C, alpha=alpha, dt=torch.float16, ln_mode=1, ln1_w=t("ln1_w"), ln1_b=t("ln1_b"), ln2_w=t("ln2_w"),
                 ln2_b=t("ln2_b"), w_qkv=None, b_qkv=None, w_qkv_dw=None, b_qkv_dw=None, temp=None, w_po=None, b_po=None,
                 w_in=None, b_in=None, w_dw=None, b_dw=None, w_out=None, b_out=None)
 
@@ -149,3 +149,28 @@ def test_training_tape_keeps_the_norms_the_convs_emitted(monkeypatch):
     # every tape entry keeps its own tensors (the backward reads them after later blocks ran)
     kept = [id(sv[k]) for sv in tape for k in ("xn1", "xn2")]
     assert len(set(kept)) == len(kept)
+
+
+def test_every_ops_attribute_the_schedules_use_exists():
+    """The kernel schedules run on the GPU only; catch renamed / deleted wrappers (``ops.xyz``) and C-ABI entry points
+    (``lib.call("tdr_xyz", ...)`` / ``_call("tdr_xyz", ...)``) here, on the CPU."""
+    import ast
+    import glob
+    import os
+
+    from textualdegremoval_b200 import lib, ops
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "textualdegremoval_b200", "**", "*.py"), recursive=True) + \
+        [os.path.join(root, "bench.py"), os.path.join(root, "tests", "gpu_checks.py")]
+    missing = []
+    for f in files:
+        tree = ast.parse(open(f).read())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id == "ops":
+                if not hasattr(ops, node.attr):
+                    missing.append(f"{os.path.relpath(f, root)}:{node.lineno} ops.{node.attr}")
+            if isinstance(node, ast.Call) and node.args and isinstance(node.args[0], ast.Constant) \
+                    and isinstance(node.args[0].value, str) and node.args[0].value.startswith("tdr_"):
+                if node.args[0].value not in lib.SIGNATURES:
+                    missing.append(f"{os.path.relpath(f, root)}:{node.lineno} {node.args[0].value}")
+    assert not missing, "\n".join(missing)

@@ -23,6 +23,8 @@ from .masa import Encoder, MasaMixin, MasaTrainMixin, _f
 from .nafnet_train import GuidedNAFTrainMixin, NAFTrainMixin
 from .restormer_train import train_call
 
+operand_dtype = ops.operand_dtype
+
 F32, BF16 = torch.float32, torch.bfloat16
 
 
@@ -57,22 +59,23 @@ class NAFResFuseBlock(NAFBlock):
     """Same math as NAFBlock on the concatenated [x || warped-ref] channels (:241-302)."""
 
 
-def _prep_naf(blk: NAFBlock):
+def _prep_naf(blk: NAFBlock, dt=torch.float16):
+    """dt: 16-bit operand format (restormer_b200_arch.operand_dtype: fp16 for inference, bf16 for the training tape)."""
     c = blk.conv1.in_channels
     dw = blk.conv1.out_channels
     ffn = blk.conv4.out_channels
     beta, gamma = _f(blk.beta).reshape(-1), _f(blk.gamma).reshape(-1)
-    p = dict(C=c, dw=dw, ffn=ffn)
+    p = dict(C=c, dw=dw, ffn=ffn, dt=dt)
     p["n1_w"], p["n1_b"], p["n2_w"], p["n2_b"] = _f(blk.norm1.weight), _f(blk.norm1.bias), _f(blk.norm2.weight), _f(blk.norm2.bias)
     p["eps"] = blk.norm1.eps
-    p["w1"], p["b1"] = ops.pack_conv_weight(blk.conv1.weight), _f(blk.conv1.bias)
+    p["w1"], p["b1"] = ops.pack_conv_weight(blk.conv1.weight, dt=dt), _f(blk.conv1.bias)
     p["w2"], p["b2"] = ops.pack_dw_weight(blk.conv2.weight), _f(blk.conv2.bias)
     p["w_sca"], p["b_sca"] = _f(blk.sca[1].weight).reshape(dw // 2, dw // 2), _f(blk.sca[1].bias)
     p["w3"] = _f(blk.conv3.weight).reshape(c, dw // 2)
     p["b3_beta"] = _f(blk.conv3.bias) * beta                       # y = inp + beta * (conv3(.) + b3)
     p["beta"] = beta
-    p["w4"], p["b4"] = ops.pack_conv_weight(blk.conv4.weight), _f(blk.conv4.bias)
-    p["w5"] = ops.pack_conv_weight(blk.conv5.weight.detach() * gamma.view(-1, 1, 1, 1))   # out = y + gamma * (conv5 + b5)
+    p["w4"], p["b4"] = ops.pack_conv_weight(blk.conv4.weight, dt=dt), _f(blk.conv4.bias)
+    p["w5"] = ops.pack_conv_weight(blk.conv5.weight.detach() * gamma.view(-1, 1, 1, 1), dt=dt)   # out = y + gamma * (conv5 + b5)
     p["b5_gamma"] = _f(blk.conv5.bias) * gamma
     return p
 
@@ -80,12 +83,12 @@ def _prep_naf(blk: NAFBlock):
 def run_naf_block(x32, p):
     """One NAFBlock on the fp32 residual stream x32 (NHWC view), updated in place."""
     c = p["C"]
-    xn = ops.rownorm(x32, 1, p["n1_w"], p["n1_b"], p["eps"])
+    xn = ops.rownorm(x32, 1, p["n1_w"], p["n1_b"], p["eps"], dt=p["dt"])
     _, t = ops.conv_gemm(xn, p["w1"], p["dw"], bias=p["b1"])
     g = ops.dwconv3x3(t, p["w2"], p["b2"], gate=2)                                   # conv2 + SimpleGate
     w3eff = ops.naf_sca_fold(g, p["w_sca"], p["b_sca"], p["w3"], rowscale=p["beta"])  # x*sca(x) and beta folded
     ops.conv_gemm(g, w3eff, c, bias=p["b3_beta"], res2=x32, out_f32=x32, w_batched=True)
-    xn = ops.rownorm(x32, 1, p["n2_w"], p["n2_b"], p["eps"])
+    xn = ops.rownorm(x32, 1, p["n2_w"], p["n2_b"], p["eps"], out=xn)
     _, t = ops.conv_gemm(xn, p["w4"], p["ffn"], bias=p["b4"])
     g = ops.gate_mul(t)
     ops.conv_gemm(g, p["w5"], c, bias=p["b5_gamma"], res2=x32, out_f32=x32)
@@ -135,24 +138,30 @@ class _NAFBase(nn.Module):
     def _wants_grad(self):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
-    def prepared(self):
+    def prepared(self, train=False):
+        """Packed operands, one cache per mode (inference: fp16 operands; train=True: bf16, see operand_dtype)."""
         key = self._prep_key()
-        if self._prep_cache is None or self._prep_cache[0] != key:
+        if not isinstance(self._prep_cache, dict):
+            self._prep_cache = {}
+        c = self._prep_cache.get(bool(train))
+        if c is None or c[0] != key:
             with torch.no_grad():
-                self._prep_cache = (key, self._prepare())
-        return self._prep_cache[1]
+                self._prep_dt = operand_dtype(train)
+                c = self._prep_cache[bool(train)] = (key, self._prepare())
+        return c[1]
 
     def _prepare_unet(self):
-        P = dict(encoders=[[_prep_naf(b) for b in st] for st in self.encoders],
-                 decoders=[[_prep_naf(b) for b in st] for st in self.decoders],
-                 middle=[_prep_naf(b) for b in self.middle_blks])
-        P["downs"] = [dict(w=ops.pack_conv_weight(d.weight), b=_f(d.bias), Co=d.out_channels) for d in self.downs]
-        P["ups"] = [dict(w=ops.pack_conv_weight(u[0].weight), Co=u[0].out_channels) for u in self.ups]
+        dt = getattr(self, "_prep_dt", torch.float16)
+        P = dict(encoders=[[_prep_naf(b, dt) for b in st] for st in self.encoders],
+                 decoders=[[_prep_naf(b, dt) for b in st] for st in self.decoders],
+                 middle=[_prep_naf(b, dt) for b in self.middle_blks], dt=dt)
+        P["downs"] = [dict(w=ops.pack_conv_weight(d.weight, dt=dt), b=_f(d.bias), Co=d.out_channels) for d in self.downs]
+        P["ups"] = [dict(w=ops.pack_conv_weight(u[0].weight, dt=dt), Co=u[0].out_channels) for u in self.ups]
         P["intro"] = dict(w=_f(self.intro.weight), b=_f(self.intro.bias))
         ew = self.ending.weight
         w8 = torch.zeros(8, ew.shape[1], 3, 3, dtype=ew.dtype, device=ew.device)
         w8[: ew.shape[0]] = ew.detach()
-        P["ending"] = dict(w=ops.pack_conv_weight(w8), b=ops.pad_vec(self.ending.bias, 8), Co=ew.shape[0])
+        P["ending"] = dict(w=ops.pack_conv_weight(w8, dt=dt), b=ops.pad_vec(self.ending.bias, 8), Co=ew.shape[0])
         return P
 
     def _check(self, *ts):
@@ -166,6 +175,7 @@ class _NAFBase(nn.Module):
         """x32: fp32 NHWC stream of the first stage (possibly the first half of a fusion buffer).
         fuse(i, x32) -> stream after the i-th fusion stage (i == n_enc for the middle one)."""
         dev = x32.device
+        dt = P["dt"]
         encs = []
         n_enc = len(P["encoders"])
         for i in range(n_enc):
@@ -176,7 +186,7 @@ class _NAFBase(nn.Module):
             B, H, W, c = x32.shape
             nxt = self._alloc_stream(i + 1, B, H // 2, W // 2, 2 * c, dev)
             pd = P["downs"][i]
-            ops.conv_gemm(ops.rownorm(x32, 0), pd["w"], pd["Co"], k=2, stride=2, pad=0, bias=pd["b"], out_f32=nxt)
+            ops.conv_gemm(ops.rownorm(x32, 0, dt=dt), pd["w"], pd["Co"], k=2, stride=2, pad=0, bias=pd["b"], out_f32=nxt)
             x32 = nxt
         if fuse is not None:
             x32 = fuse(n_enc, x32)
@@ -184,9 +194,9 @@ class _NAFBase(nn.Module):
         for i, skip in enumerate(encs[::-1]):
             B, H, W, c = x32.shape
             up = torch.empty((B, H * 2, W * 2, c // 2), dtype=F32, device=dev)
-            ops.conv_gemm(ops.rownorm(x32, 0), P["ups"][i]["w"], P["ups"][i]["Co"], out_f32=up, res2=skip, store_mode=2)
+            ops.conv_gemm(ops.rownorm(x32, 0, dt=dt), P["ups"][i]["w"], P["ups"][i]["Co"], out_f32=up, res2=skip, store_mode=2)
             x32 = run_naf_stack(up, P["decoders"][i])
-        o8, _ = ops.conv_gemm(ops.rownorm(x32, 0), P["ending"]["w"], 8, k=3, pad=1, bias=P["ending"]["b"], want="f32")
+        o8, _ = ops.conv_gemm(ops.rownorm(x32, 0, dt=dt), P["ending"]["w"], 8, k=3, pad=1, bias=P["ending"]["b"], want="f32")
         return o8[..., : P["ending"]["Co"]]
 
     def _alloc_stream(self, stage, B, H, W, c, dev):
@@ -244,8 +254,9 @@ class NAFNetRefFusion(GuidedNAFTrainMixin, MasaTrainMixin, MasaMixin, _NAFBase):
     def _prepare(self):
         P = self._prepare_unet()
         P["masa_enc"] = self.prepare_masa_enc()
-        P["fuse"] = [[_prep_naf(b) for b in st] for st in self.masa_blk_enc] + \
-                    [[_prep_naf(b) for b in self.masa_blk_middle[0]]]
+        dt = P["dt"]
+        P["fuse"] = [[_prep_naf(b, dt) for b in st] for st in self.masa_blk_enc] + \
+                    [[_prep_naf(b, dt) for b in self.masa_blk_middle[0]]]
         return P
 
     def forward(self, inp, ref, return_aux=False):
@@ -262,17 +273,17 @@ class NAFNetRefFusion(GuidedNAFTrainMixin, MasaTrainMixin, MasaMixin, _NAFBase):
         lq32, ref32 = ops.nchw_to_nhwc(inp, h, w), ops.nchw_to_nhwc(ref, hr, wr)
         E = P["masa_enc"]
         if (h, w) == (hr, wr):
-            fb = self._masa_encode(E, torch.cat([lq32, ref32], 0))
-            f_lq, f_ref = [t[:B] for t in fb], [t[B:] for t in fb]
+            fb, d32 = self._masa_encode(E, torch.cat([lq32, ref32], 0))
+            f_lq, f_ref, lq_d32, ref_d32 = [t[:B] for t in fb], [t[B:] for t in fb], d32[:B], d32[B:]
         else:
-            f_lq, f_ref = self._masa_encode(E, lq32), self._masa_encode(E, ref32)
+            (f_lq, lq_d32), (f_ref, ref_d32) = self._masa_encode(E, lq32), self._masa_encode(E, ref32)
         nlev = len(f_ref)
         chans = [self.width * 2 ** i for i in range(nlev)]
         fbuf = [torch.empty((B, h >> i, w >> i, 2 * chans[i]), dtype=F32, device=dev) for i in range(nlev)]
         self._fbuf = fbuf
-        aux = self._masa_warp(f_lq[-1], f_ref, h, w, hr, wr, [fbuf[i][..., chans[i]:] for i in range(nlev)])
+        aux = self._masa_warp(lq_d32, ref_d32, f_ref, h, w, hr, wr, [fbuf[i][..., chans[i]:] for i in range(nlev)])
         if return_aux:
-            aux.update(feat_lq=f_lq, feat_ref=f_ref, warps=[fbuf[i][..., chans[i]:].clone() for i in range(nlev)])
+            aux.update(feat_lq=f_lq, feat_ref=f_ref, deep32_lq=lq_d32, deep32_ref=ref_d32, deep_scale=self._masa_last_scale[-1], warps=[fbuf[i][..., chans[i]:].clone() for i in range(nlev)])
         ops.conv3x3_small_ci(lq32, P["intro"]["w"], P["intro"]["b"], out_f32=fbuf[0][..., :chans[0]])
 
         def fuse(i, x32):

@@ -222,7 +222,7 @@ class NAFTrainMixin:
     # ---- plain NAFNet ----------------------------------------------------------------------------------------------
     def _forward_train(self, inp):
         self._check(inp)
-        P = self._prep_train(self.prepared())
+        P = self._prep_train(self.prepared(train=True))
         B, _, H, W = inp.shape
         h, w = ops.round_up(H, self.padder_size), ops.round_up(W, self.padder_size)
         inp32 = ops.nchw_to_nhwc(inp, h, w)
@@ -246,7 +246,7 @@ class GuidedNAFTrainMixin(NAFTrainMixin):
 
     def _forward_train(self, inp, ref):
         self._check(inp, ref)
-        P = self._prep_train(self.prepared())
+        P = self._prep_train(self.prepared(train=True))
         E = self._prep_masa_train(P["masa_enc"])
         dev = inp.device
         B, _, oh, ow = inp.shape
@@ -257,17 +257,17 @@ class GuidedNAFTrainMixin(NAFTrainMixin):
         lq16, ref16 = self._image16(inp, h, w), self._image16(ref, hr, wr)
         tape, T = [], dict(hw=(h, w), B=B, inp16=lq16)
         if (h, w) == (hr, wr):
-            fb, et = self._masa_encode_train(E, torch.cat([lq32, ref32], 0), torch.cat([lq16, ref16], 0))
-            f_lq, f_ref = [t[:B] for t in fb], [t[B:] for t in fb]
+            fb, d32, et = self._masa_encode_train(E, torch.cat([lq32, ref32], 0), torch.cat([lq16, ref16], 0))
+            f_lq, f_ref, lq_d32, ref_d32 = [t[:B] for t in fb], [t[B:] for t in fb], d32[:B], d32[B:]
             T["enc"] = [(et, fb)]
         else:
-            f_lq, et_l = self._masa_encode_train(E, lq32, lq16)
-            f_ref, et_r = self._masa_encode_train(E, ref32, ref16)
+            f_lq, lq_d32, et_l = self._masa_encode_train(E, lq32, lq16)
+            f_ref, ref_d32, et_r = self._masa_encode_train(E, ref32, ref16)
             T["enc"] = [(et_l, f_lq), (et_r, f_ref)]
         nlev = len(f_ref)
         chans = [self.width * 2 ** i for i in range(nlev)]
         fbuf = [torch.empty((B, h >> i, w >> i, 2 * chans[i]), dtype=F32, device=dev) for i in range(nlev)]
-        aux = self._masa_warp(f_lq[-1], f_ref, h, w, hr, wr, [fbuf[i][..., chans[i]:] for i in range(nlev)])
+        aux = self._masa_warp(lq_d32, ref_d32, f_ref, h, w, hr, wr, [fbuf[i][..., chans[i]:] for i in range(nlev)])
         T["aux"], T["f_lq_deep"], T["f_ref"] = aux, f_lq[-1], f_ref
         ops.conv3x3_small_ci(lq32, P["intro"]["w"], P["intro"]["b"], out_f32=fbuf[0][..., :chans[0]])
         out = self._unet_train(P, fbuf[0][..., :chans[0]], tape, T, fbuf=fbuf)

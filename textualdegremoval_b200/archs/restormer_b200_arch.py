@@ -23,7 +23,10 @@ from ..lib import TdrError
 from .masa import Encoder, MasaMixin, MasaTrainMixin, ResidualBlock, prep_conv as _prep_conv, conv3x3, _f  # noqa: F401
 from .restormer_train import GuidedRestormerTrainMixin, RestormerTrainMixin, train_call
 
-F32, BF16 = torch.float32, torch.bfloat16
+F32, BF16, F16 = torch.float32, torch.bfloat16, torch.float16
+
+
+operand_dtype = ops.operand_dtype
 
 
 # ----------------------------------------------------------------------------------------------- parameter holders
@@ -125,20 +128,21 @@ def _prep_block(blk: TransformerBlock, train=False):
     hp = ops.round_up(h, 8)
     dev = a.qkv.weight.device
     m2, m1 = _block_maps(blk, h, hp, dev)
-    p = dict(C=C_, heads=a.num_heads, h=h, hp=hp, map_2h=m2, map_h=m1, mod=blk)
+    dt = operand_dtype(train)
+    p = dict(C=C_, heads=a.num_heads, h=h, hp=hp, map_2h=m2, map_h=m1, mod=blk, dt=dt)
     p["ln1_w"], p["ln1_b"] = _f(blk.norm1.body.weight), _f(blk.norm1.body.bias)
     p["ln2_w"], p["ln2_b"] = _f(blk.norm2.body.weight), _f(blk.norm2.body.bias)
     p["ln_mode"] = 1 if blk.norm1.body.bias is not None else 2
-    p["w_qkv"], p["w_qkv_T"] = ops.pack_conv(a.qkv.weight, dgrad=train)
+    p["w_qkv"], p["w_qkv_T"] = ops.pack_conv(a.qkv.weight, dgrad=train, dt=dt)
     p["b_qkv"] = _f(a.qkv.bias)
     p["w_qkv_dw"], p["w_qkv_dw_f"], p["b_qkv_dw"] = ops.pack_dw(a.qkv_dwconv.weight, a.qkv_dwconv.bias, flip=train)
     p["temp"] = _f(a.temperature).reshape(-1)
     p["w_po"] = _f(a.project_out.weight).reshape(C_, C_)
     p["b_po"] = _f(a.project_out.bias)
-    p["w_in"], p["w_in_T"] = ops.pack_conv(f.project_in.weight, co_map=m2, Co_p=2 * hp, dgrad=train)
+    p["w_in"], p["w_in_T"] = ops.pack_conv(f.project_in.weight, co_map=m2, Co_p=2 * hp, dgrad=train, dt=dt)
     p["b_in"] = ops.gather_vec(f.project_in.bias, m2, 2 * hp)
     p["w_dw"], p["w_dw_f"], p["b_dw"] = ops.pack_dw(f.dwconv.weight, f.dwconv.bias, c_map=m2, C_p=2 * hp, flip=train)
-    p["w_out"], p["w_out_T"] = ops.pack_conv(f.project_out.weight, ci_map=m1, Ci_p=hp, dgrad=train)
+    p["w_out"], p["w_out_T"] = ops.pack_conv(f.project_out.weight, ci_map=m1, Ci_p=hp, dgrad=train, dt=dt)
     p["b_out"] = _f(f.project_out.bias)
     p["alpha"] = _f(blk.alpha) if hasattr(blk, "alpha") else None
     p["train"] = train
@@ -166,11 +170,12 @@ def run_block(x32, p, xn=None, nxt=None):
     fuse_ln = _ln_fusable(p)
     B, H, W, _ = x32.shape
     dev = x32.device
-    # bf16 operands with 128 B-aligned row pitch (ops.rows16): C = 48 / 96 rows would straddle lines otherwise
+    dt = p["dt"]
+    # 16-bit operands with 128 B-aligned row pitch (ops.rows16): C = 48 / 96 rows would straddle lines otherwise
     if xn is None:
-        xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5, out=ops.rows16(B, H, W, C_, dev))
-    _, qkv = ops.conv_gemm(xn, p["w_qkv"], 3 * C_, bias=p["b_qkv"], out_bf16=ops.rows16(B, H, W, 3 * C_, dev))
-    qkv = ops.dwconv3x3(qkv, p["w_qkv_dw"], p["b_qkv_dw"], out=ops.rows16(B, H, W, 3 * C_, dev))
+        xn = ops.rownorm(x32, p["ln_mode"], p["ln1_w"], p["ln1_b"], 1e-5, out=ops.rows16(B, H, W, C_, dev, dt))
+    _, qkv = ops.conv_gemm(xn, p["w_qkv"], 3 * C_, bias=p["b_qkv"], out_bf16=ops.rows16(B, H, W, 3 * C_, dev, dt))
+    qkv = ops.dwconv3x3(qkv, p["w_qkv_dw"], p["b_qkv_dw"], out=ops.rows16(B, H, W, 3 * C_, dev, dt))
     weff = ops.mdta_weff(qkv, C_, heads, p["temp"], p["w_po"])
     v = qkv[..., 2 * C_:]
     if fusion:
@@ -241,36 +246,39 @@ class _RestormerBase(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def prepared(self, train=False):
-        """Packed kernel operands, rebuilt when a parameter changed.  train=True also builds the data-gradient packs
-        (a cache built for training serves inference too)."""
+        """Packed kernel operands, rebuilt when a parameter changed; one cache per mode: inference packs are IEEE fp16
+        (operand_dtype), train=True packs are bf16 and come with the data-gradient twins."""
         key = self._prep_key()
-        c = self._prep_cache
-        if c is None or c[0] != key or (train and not c[2]):
+        if not isinstance(self._prep_cache, dict):
+            self._prep_cache = {}
+        c = self._prep_cache.get(bool(train))
+        if c is None or c[0] != key:
             with torch.no_grad():
                 self._prep_train_flag = train
-                self._prep_cache = (key, self._prepare(), train)
-        return self._prep_cache[1]
+                c = self._prep_cache[bool(train)] = (key, self._prepare())
+        return c[1]
 
     def _prepare_body(self):
         P = {}
         train = getattr(self, "_prep_train_flag", False)
+        dt = P["dt"] = operand_dtype(train)
         for name in ["encoder_level1", "encoder_level2", "encoder_level3", "latent", "decoder_level3",
                      "decoder_level2", "decoder_level1", "refinement"] + \
                     [f"masa_blk_enc_level{i}" for i in range(1, 5) if hasattr(self, f"masa_blk_enc_level{i}")]:
             P[name] = [_prep_block(b, train) for b in getattr(self, name)]
         for name in ["down1_2", "down2_3", "down3_4", "up4_3", "up3_2", "up2_1"]:
-            P[name] = _prep_conv(getattr(self, name).body[0])
+            P[name] = _prep_conv(getattr(self, name).body[0], dt)
         for name in ["reduce_chan_level3", "reduce_chan_level2"]:
-            P[name] = _prep_conv(getattr(self, name))
+            P[name] = _prep_conv(getattr(self, name), dt)
         P["patch_embed"] = dict(w=_f(self.patch_embed.proj.weight), b=_f(self.patch_embed.proj.bias))
         # output conv (:640): 3 (or 1) output channels are zero-padded to 8 so that it runs on the tensor-core path
         ow = self.output.weight
         co = ow.shape[0]
         w8 = torch.zeros(8, ow.shape[1], 3, 3, dtype=ow.dtype, device=ow.device)
         w8[:co] = ow.detach()
-        P["output"] = dict(w=ops.pack_conv_weight(w8), b=ops.pad_vec(self.output.bias, 8), Co=co)
+        P["output"] = dict(w=ops.pack_conv_weight(w8, dt=dt), b=ops.pad_vec(self.output.bias, 8), Co=co)
         if self.dual_pixel_task:
-            P["skip_conv"] = _prep_conv(self.skip_conv)
+            P["skip_conv"] = _prep_conv(self.skip_conv, dt)
         return P
 
     def _wants_grad(self):
@@ -284,7 +292,7 @@ class _RestormerBase(nn.Module):
 
     def _down(self, x32, pc, out32):
         """Downsample (:372-380): conv3x3 C->C/2 then PixelUnshuffle(2), written straight into out32."""
-        x16 = ops.rownorm(x32, 0)
+        x16 = ops.rownorm(x32, 0, dt=pc["w"].dtype)
         ops.conv_gemm(x16, pc["w"], pc["Co"], k=3, pad=1, out_f32=out32, store_mode=1)
 
     def _decode(self, P, lat, e1, e2, e3, x_in1):
@@ -292,11 +300,12 @@ class _RestormerBase(nn.Module):
         d = self.dims
         B, H8, W8, _ = lat.shape
         dev = lat.device
+        dt = P["dt"]
 
         def up_cat_reduce(x32, enc, up, red, Cn):
             b, hh, ww, _ = x32.shape
-            cat16 = torch.empty((b, hh * 2, ww * 2, 2 * Cn), dtype=BF16, device=dev)
-            ops.conv_gemm(ops.rownorm(x32, 0), P[up]["w"], P[up]["Co"], k=3, pad=1, out_bf16=cat16[..., :Cn],
+            cat16 = torch.empty((b, hh * 2, ww * 2, 2 * Cn), dtype=dt, device=dev)
+            ops.conv_gemm(ops.rownorm(x32, 0, dt=dt), P[up]["w"], P[up]["Co"], k=3, pad=1, out_bf16=cat16[..., :Cn],
                           store_mode=2)
             ops.copy_rows(enc, dst16=cat16[..., Cn:])
             y32, _ = ops.conv_gemm(cat16, P[red]["w"], Cn, bias=P[red]["b"], want="f32")
@@ -306,15 +315,16 @@ class _RestormerBase(nn.Module):
         d2 = run_stack(up_cat_reduce(d3, e2, "up3_2", "reduce_chan_level2", d[1]), P["decoder_level2"])
         b, hh, ww, _ = d2.shape
         d1 = torch.empty((b, hh * 2, ww * 2, d[1]), dtype=F32, device=dev)
-        ops.conv_gemm(ops.rownorm(d2, 0), P["up2_1"]["w"], P["up2_1"]["Co"], k=3, pad=1, out_f32=d1[..., :d[0]],
+        ops.conv_gemm(ops.rownorm(d2, 0, dt=dt), P["up2_1"]["w"], P["up2_1"]["Co"], k=3, pad=1, out_f32=d1[..., :d[0]],
                       store_mode=2)
         ops.copy_rows(e1, dst32=d1[..., d[0]:])
         tail = []
         run_stack(d1, P["decoder_level1"], nxt=P["refinement"][0] if P["refinement"] else None, tail=tail)
         run_stack(d1, P["refinement"], xn=tail[0])
         if self.dual_pixel_task:      # :494-496  out = output(d1 + skip_conv(inp_enc_level1))
-            ops.conv_gemm(ops.rownorm(x_in1, 0), P["skip_conv"]["w"], d[1], bias=P["skip_conv"]["b"], res2=d1, out_f32=d1)
-        o8, _ = ops.conv_gemm(ops.rownorm(d1, 0), P["output"]["w"], 8, k=3, pad=1, bias=P["output"]["b"], want="f32")
+            ops.conv_gemm(ops.rownorm(x_in1, 0, dt=dt), P["skip_conv"]["w"], d[1], bias=P["skip_conv"]["b"], res2=d1,
+                          out_f32=d1)
+        o8, _ = ops.conv_gemm(ops.rownorm(d1, 0, dt=dt), P["output"]["w"], 8, k=3, pad=1, bias=P["output"]["b"], want="f32")
         return o8[..., :P["output"]["Co"]]
 
 
@@ -410,15 +420,16 @@ class RestormerRefFusion(GuidedRestormerTrainMixin, MasaTrainMixin, MasaMixin, _
         ref32 = ops.nchw_to_nhwc(ref_img, hr, wr)
         E = P["masa_enc"]
         if (h, w) == (hr, wr):           # shared weights: run lq and ref as one batch
-            fb = self._masa_encode(E, torch.cat([lq32, ref32], 0))
-            f_lq, f_ref = [t[:B] for t in fb], [t[B:] for t in fb]
+            fb, d32 = self._masa_encode(E, torch.cat([lq32, ref32], 0))
+            f_lq, f_ref, lq_d32, ref_d32 = [t[:B] for t in fb], [t[B:] for t in fb], d32[:B], d32[B:]
         else:
-            f_lq, f_ref = self._masa_encode(E, lq32), self._masa_encode(E, ref32)
+            (f_lq, lq_d32), (f_ref, ref_d32) = self._masa_encode(E, lq32), self._masa_encode(E, ref32)
         # fusion buffers [x || warp] per level, fp32 residual streams
         fbuf = [torch.empty((B, h >> i, w >> i, 2 * d[i]), dtype=F32, device=dev) for i in range(4)]
-        aux = self._masa_warp(f_lq[-1], f_ref, h, w, hr, wr, [fbuf[i][..., d[i]:] for i in range(4)])
+        aux = self._masa_warp(lq_d32, ref_d32, f_ref, h, w, hr, wr, [fbuf[i][..., d[i]:] for i in range(4)])
         if return_aux:                   # the fusion blocks overwrite the warp halves in place
-            aux.update(feat_lq=f_lq, feat_ref=f_ref, warps=[fbuf[i][..., d[i]:].clone() for i in range(4)])
+            aux.update(feat_lq=f_lq, feat_ref=f_ref, deep32_lq=lq_d32, deep32_ref=ref_d32, deep_scale=self._masa_last_scale[-1],
+                       warps=[fbuf[i][..., d[i]:].clone() for i in range(4)])
         ops.conv3x3_small_ci(lq32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=fbuf[0][..., :d[0]])
         enc_names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
         downs = [None, "down1_2", "down2_3", "down3_4"]

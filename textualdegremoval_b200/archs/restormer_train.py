@@ -390,15 +390,15 @@ class GuidedRestormerTrainMixin(RestormerTrainMixin):
         lq16, ref16 = self._image16(inp_img, h, w), self._image16(ref_img, hr, wr)
         tape, T = [], dict(hw=(h, w), B=B, inp16=lq16)
         if (h, w) == (hr, wr):           # shared weights: lq and ref as one batch
-            fb, et = self._masa_encode_train(E, torch.cat([lq32, ref32], 0), torch.cat([lq16, ref16], 0))
-            f_lq, f_ref = [t[:B] for t in fb], [t[B:] for t in fb]
+            fb, d32, et = self._masa_encode_train(E, torch.cat([lq32, ref32], 0), torch.cat([lq16, ref16], 0))
+            f_lq, f_ref, lq_d32, ref_d32 = [t[:B] for t in fb], [t[B:] for t in fb], d32[:B], d32[B:]
             T["enc"] = [(et, fb)]
         else:
-            f_lq, et_l = self._masa_encode_train(E, lq32, lq16)
-            f_ref, et_r = self._masa_encode_train(E, ref32, ref16)
+            f_lq, lq_d32, et_l = self._masa_encode_train(E, lq32, lq16)
+            f_ref, ref_d32, et_r = self._masa_encode_train(E, ref32, ref16)
             T["enc"] = [(et_l, f_lq), (et_r, f_ref)]
         fbuf = [torch.empty((B, h >> i, w >> i, 2 * d[i]), dtype=F32, device=dev) for i in range(4)]
-        aux = self._masa_warp(f_lq[-1], f_ref, h, w, hr, wr, [fbuf[i][..., d[i]:] for i in range(4)])
+        aux = self._masa_warp(lq_d32, ref_d32, f_ref, h, w, hr, wr, [fbuf[i][..., d[i]:] for i in range(4)])
         T["aux"], T["f_lq_deep"], T["f_ref"] = aux, f_lq[-1], f_ref
         ops.conv3x3_small_ci(lq32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=fbuf[0][..., :d[0]])
         names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]

@@ -235,7 +235,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
                                                            int Co, int Ci, float* __restrict__ out, long long s_b,
                                                            long long s_co, long long s_ci, long long s_t,
                                                            const int* __restrict__ co_map, const int* __restrict__ ci_map,
-                                                           int accumulate, float scale) {
+                                                           int accumulate, float scale, const float* __restrict__ scale_ptr) {
+  if (scale_ptr) scale *= *scale_ptr;                  // device-side factor (MASA encoder level scale)
   const long long per = (long long)T * Co * Ci;
   const long long total = (long long)nb * per;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -978,12 +979,15 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(const bf16* __restrict__
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / nv;
     const int c = (int)(i % nv) * 8;
-    float a[8], g[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(y + r * y_ld + c), a);
-    unpack8(*reinterpret_cast<const bf16x8*>(dy + r * dy_ld + c), g);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] = a[k] > 0.f ? g[k] : 0.f;
-    *reinterpret_cast<bf16x8*>(out + r * out_ld + c) = pack8(g);
+    // y > 0 from the raw 16-bit patterns: sign bit clear and not zero -- identical for bf16 and IEEE fp16 (NaN never occurs)
+    const uint4 yb = *reinterpret_cast<const uint4*>(y + r * y_ld + c);
+    uint4 g = *reinterpret_cast<const uint4*>(dy + r * dy_ld + c);
+    auto mask = [](uint32_t yy) {
+      const uint32_t lo = yy & 0xffffu, hi = yy >> 16;
+      return ((lo - 1u) < 0x7fffu ? 0xffffu : 0u) | ((hi - 1u) < 0x7fffu ? 0xffff0000u : 0u);
+    };
+    g.x &= mask(yb.x); g.y &= mask(yb.y); g.z &= mask(yb.z); g.w &= mask(yb.w);
+    *reinterpret_cast<uint4*>(out + r * out_ld + c) = g;
   }
 }
 
@@ -1134,7 +1138,7 @@ extern "C" int tdr_wgrad(const tdr_wgrad_desc* d, cudaStream_t stream) {
   const long long total = (long long)p.nb * p.T * d->Co * d->Ci;
   wgrad_reduce_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(
       d->workspace, p.nb, p.nchunks, p.T, d->Co, d->Ci, d->out, d->out_stride_b, d->out_stride_co, d->out_stride_ci,
-      d->out_stride_tap, d->co_map, d->ci_map, d->accumulate, d->scale);
+      d->out_stride_tap, d->co_map, d->ci_map, d->accumulate, d->scale, d->scale_ptr);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

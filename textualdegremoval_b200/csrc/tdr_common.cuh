@@ -3,6 +3,7 @@
 // Everything here is written for sm_100a only; there is no other code path.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -67,6 +68,45 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   bf162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+
+// IEEE fp16 pair, round to nearest, saturating at +-65504 (one F2FP.SATFINITE): fp16 operands must never become inf
+__device__ __forceinline__ uint32_t pack2h(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// 16-bit operand format selected at compile time (H = IEEE fp16, else bf16) or at run time
+template <bool H>
+__device__ __forceinline__ uint32_t pack2t(float a, float b) {
+  if constexpr (H) return pack2h(a, b);
+  else return pack2(a, b);
+}
+__device__ __forceinline__ uint32_t pack2r(float a, float b, int fp16) { return fp16 ? pack2h(a, b) : pack2(a, b); }
+template <bool H>
+__device__ __forceinline__ void unpack2t(uint32_t u, float& a, float& b) {
+  if constexpr (H) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u));
+    a = f.x; b = f.y;
+  } else {
+    a = __uint_as_float(u << 16); b = __uint_as_float(u & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void unpack2r(uint32_t u, float& a, float& b, int fp16) {
+  if (fp16) unpack2t<true>(u, a, b);
+  else unpack2t<false>(u, a, b);
+}
+
+// 8 consecutive 16-bit values (bf16, or IEEE fp16 when `fp16`) <-> fp32, through one 128-bit access
+__device__ __forceinline__ void unpack8r(const void* p, float* f, int fp16) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  unpack2r(v.x, f[0], f[1], fp16); unpack2r(v.y, f[2], f[3], fp16);
+  unpack2r(v.z, f[4], f[5], fp16); unpack2r(v.w, f[6], f[7], fp16);
+}
+__device__ __forceinline__ void pack8r(void* p, const float* f, int fp16) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack2r(f[0], f[1], fp16), pack2r(f[2], f[3], fp16), pack2r(f[4], f[5], fp16),
+                                            pack2r(f[6], f[7], fp16));
+}
+__device__ __forceinline__ uint16_t pack1r(float a, int fp16) { return (uint16_t)(pack2r(a, 0.f, fp16) & 0xffffu); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -222,10 +262,12 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   return d;
 }
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32 (cute::UMMA::InstrDescriptor).
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4)              // D = f32
-         | (1u << 7)            // A = bf16
-         | (1u << 10)           // B = bf16
+// a_fp16 / b_fp16: that operand holds IEEE fp16 instead of bf16 (kind::f16 takes either, per operand, at the same rate)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major, int a_fp16 = 0,
+                                                       int b_fp16 = 0) {
+  return (1u << 4)                          // D = f32
+         | ((a_fp16 ? 0u : 1u) << 7)        // A = bf16 (1) / fp16 (0)
+         | ((b_fp16 ? 0u : 1u) << 10)       // B = bf16 (1) / fp16 (0)
          | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }

@@ -68,6 +68,8 @@ struct ConvGemmArgs {
   int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
   int epi_bufs;                 // staging buffers per epilogue warp (1 or 2; 4 with the fused LayerNorm)
   // fused LayerNorm of the output rows (variant bit 3): ln_out = LN(out) in bf16 through map_o2
+  int in_fp16;                  // A and W operands are IEEE fp16 (MASA feature encoder)
+  int out_fp16;                 // the 16-bit output is IEEE fp16
   int ln_mode;                  // 1 WithBias, 2 BiasFree (as tdr_rownorm)
   float ln_eps;
   const float* ln_w;
@@ -97,7 +99,8 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 
 // V < 0: generic epilogue (any combination of outputs / residuals / pixel (un)shuffle).
 // V >= 0: TMA epilogue specialised at compile time: bit 0 = fp32 output, bit 1 = res2 tile, bit 2 = res1 tile,
-//         bit 3 = fused LayerNorm of the output rows (only with bits 0 and 1, Co <= 96).
+//         bit 3 = fused LayerNorm of the output rows (only with bits 0 and 1, Co <= 96);
+//         bit 4 = the 16-bit output is IEEE fp16 (only V == 16: no residual tiles).
 template <int V>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_constant__ TdrTensorMap map_w,
@@ -106,6 +109,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                  const ConvGemmArgs a) {
   constexpr bool kTma = V >= 0;
   constexpr bool kF32 = kTma && (V & 1), kR2 = kTma && (V & 2), kR1 = kTma && (V & 4), kLN = kTma && (V & 8);
+  constexpr bool kH16 = kTma && (V & 16);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages][barriers][tmem ptr]; base rounded up to 1024 B for SWIZZLE_128B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -209,7 +213,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(kTileM, a.BN, 0, 0);
+    const uint32_t idesc = umma_idesc_bf16(kTileM, a.BN, 0, 0, a.in_fp16, a.in_fp16);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -443,8 +447,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                 y[h2 * 4 + 2] = fmaf((__uint_as_float(t.z) - sub) * rstd, w4.z, b4.z);
                 y[h2 * 4 + 3] = fmaf((__uint_as_float(t.w) - sub) * rstd, w4.w, b4.w);
               }
-              sts128(stg16 + lane * 128 + ((((sb & 1) * 4 + c8) ^ (lane & 7)) << 4), pack2(y[0], y[1]),
-                     pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
+              sts128(stg16 + lane * 128 + ((((sb & 1) * 4 + c8) ^ (lane & 7)) << 4), pack2t<kH16>(y[0], y[1]),
+                     pack2t<kH16>(y[2], y[3]), pack2t<kH16>(y[4], y[5]), pack2t<kH16>(y[6], y[7]));
             }
           }
         }
@@ -575,8 +579,12 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                       v[hh * 8 + 2 * i + 1] += __uint_as_float(tw[i] & 0xffff0000u);
                     }
                   }
-                  sts128(stg_s + off, pack2(v[hh * 8], v[hh * 8 + 1]), pack2(v[hh * 8 + 2], v[hh * 8 + 3]),
-                         pack2(v[hh * 8 + 4], v[hh * 8 + 5]), pack2(v[hh * 8 + 6], v[hh * 8 + 7]));
+                  if constexpr (kH16)
+                    sts128(stg_s + off, pack2h(v[hh * 8], v[hh * 8 + 1]), pack2h(v[hh * 8 + 2], v[hh * 8 + 3]),
+                           pack2h(v[hh * 8 + 4], v[hh * 8 + 5]), pack2h(v[hh * 8 + 6], v[hh * 8 + 7]));
+                  else
+                    sts128(stg_s + off, pack2(v[hh * 8], v[hh * 8 + 1]), pack2(v[hh * 8 + 2], v[hh * 8 + 3]),
+                           pack2(v[hh * 8 + 4], v[hh * 8 + 5]), pack2(v[hh * 8 + 6], v[hh * 8 + 7]));
                 }
               }
             }
@@ -635,7 +643,12 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                   const int ch = j * 2 + hh;
-                  *reinterpret_cast<bf16x8*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) = pack8(v + hh * 8);
+                  const float* vv = v + hh * 8;
+                  if (a.out_fp16)
+                    *reinterpret_cast<uint4*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) =
+                        make_uint4(pack2h(vv[0], vv[1]), pack2h(vv[2], vv[3]), pack2h(vv[4], vv[5]), pack2h(vv[6], vv[7]));
+                  else
+                    *reinterpret_cast<bf16x8*>(stg + lane * 128 + ((ch ^ (lane & 7)) << 4)) = pack8(vv);
                 }
               } else {
 #pragma unroll
@@ -681,8 +694,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                 if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + pix_r * a.out_f32_ld + col) = o;
                 if (a.out_bf16) {
                   uint2 pk;
-                  pk.x = pack2(o.x, o.y);
-                  pk.y = pack2(o.z, o.w);
+                  pk.x = a.out_fp16 ? pack2h(o.x, o.y) : pack2(o.x, o.y);
+                  pk.y = a.out_fp16 ? pack2h(o.z, o.w) : pack2(o.z, o.w);
                   *reinterpret_cast<uint2*>(a.out_bf16 + pix_r * a.out_bf16_ld + col) = pk;
                 }
               }
@@ -724,7 +737,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                 const int co = col0 + i;
                 if (co < a.Co) {
                   if (a.out_f32) a.out_f32[row * a.out_f32_ld + co * 4 + sub] = v[i];
-                  if (a.out_bf16) a.out_bf16[row * a.out_bf16_ld + co * 4 + sub] = __float2bfloat16(v[i]);
+                  if (a.out_bf16)
+                    reinterpret_cast<uint16_t*>(a.out_bf16)[row * a.out_bf16_ld + co * 4 + sub] = pack1r(v[i], a.out_fp16);
                 }
               }
             } else {
@@ -743,8 +757,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                   if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + row * a.out_f32_ld + cq) = o;
                   if (a.out_bf16) {
                     uint2 pk;
-                    pk.x = pack2(o.x, o.y);
-                    pk.y = pack2(o.z, o.w);
+                    pk.x = pack2r(o.x, o.y, a.out_fp16);
+                    pk.y = pack2r(o.z, o.w, a.out_fp16);
                     *reinterpret_cast<uint2*>(a.out_bf16 + row * a.out_bf16_ld + cq) = pk;
                   }
                 }
@@ -871,6 +885,10 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   a.out_f32 = d->out_f32; a.out_f32_ld = d->out_f32_ld;
   a.out_bf16 = reinterpret_cast<bf16*>(d->out_bf16); a.out_bf16_ld = d->out_bf16_ld;
   a.store_mode = d->store_mode;
+  a.in_fp16 = d->in_fp16 ? 1 : 0; a.out_fp16 = d->out_fp16 ? 1 : 0;
+  TDR_CHECK_ARG(!d->out_fp16 || ((d->out_bf16 || d->ln_out_bf16) && !d->res2_bf16),
+                "tdr_conv_gemm: out_fp16 needs a 16-bit output (out_bf16 / ln_out_bf16) and no bf16 residual");
+  TDR_CHECK_ARG(!d->in_fp16 || d->impl == 0, "tdr_conv_gemm: the SIMT restatement reads bf16 operands only");
   const bool want_ln = d->ln_mode != 0;
   TDR_CHECK_ARG(!want_ln || conv_ln_ok(d), "tdr_conv_gemm: fused LayerNorm needs a 1x1 op with fp32 output + fp32 res2, "
                 "no res1, Co <= 96 and 16 B-aligned rows (ln_mode %d, Co %d)", d->ln_mode, d->Co);
@@ -1052,7 +1070,9 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   }
   const size_t smem = smem_need();
   const int grid = a.total_tiles < tdr_num_sms() ? a.total_tiles : tdr_num_sms();
-  const int variant = a.epi_mode == 1 ? (a.out_is_f32 | (d->res2 ? 2 : 0) | (d->res1 ? 4 : 0) | (want_ln ? 8 : 0)) : -1;
+  int variant = a.epi_mode == 1 ? (a.out_is_f32 | (d->res2 ? 2 : 0) | (d->res1 ? 4 : 0) | (want_ln ? 8 : 0)) : -1;
+  if (variant == 0 && a.out_fp16) variant = 16;
+  if (variant == 11 && a.out_fp16) variant = 27;
 #define TDR_LAUNCH_CONV(VV)                                                                                        \
   do {                                                                                                             \
     static bool attr_set = false;                                                                                  \
@@ -1070,6 +1090,8 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     case 3: TDR_LAUNCH_CONV(3); break;
     case 7: TDR_LAUNCH_CONV(7); break;
     case 11: TDR_LAUNCH_CONV(11); break;
+    case 16: TDR_LAUNCH_CONV(16); break;
+    case 27: TDR_LAUNCH_CONV(27); break;
     default: TDR_LAUNCH_CONV(-1); break;
   }
 #undef TDR_LAUNCH_CONV

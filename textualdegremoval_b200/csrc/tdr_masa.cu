@@ -21,19 +21,54 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-__global__ void sqnorm_rows_kernel(const bf16* __restrict__ x, long long ld, long long rows, int C, float* n2) {
+__device__ __forceinline__ void load8(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// v = hi + lo with hi = bf16(v), lo = bf16(v - hi): 16 significand bits in two bf16 numbers (lo keeps bf16's full exponent
+// range, so there is no underflow issue as with an fp16 pair)
+__device__ __forceinline__ void split8(const float* v, float* hi, float* lo) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    hi[e] = __bfloat162float(__float2bfloat16(v[e]));
+    lo[e] = v[e] - hi[e];
+  }
+}
+
+__global__ void sqnorm_rows_kernel(const float* __restrict__ x, long long ld, long long rows, int C, float* n2) {
   const int lane = threadIdx.x & 31;
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
   float s = 0.f;
   for (int v = lane; v < (C >> 3); v += 32) {
     float f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(x + row * ld + v * 8), f);
+    load8(x + row * ld + v * 8, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) s = fmaf(f[e], f[e], s);
   }
   s = warp_sum(s);
   if (lane == 0) n2[row] = s;
+}
+
+// out[r] = [hi | lo | hi] (3C bf16): the A operand of the split-bf16 correlations; the filters are laid out [hi | hi | lo],
+// so one bf16 GEMM over 3C channels accumulates hi*hi + lo*hi + hi*lo in fp32 (the lo*lo term, 2^-16 relative, is dropped)
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, long long ld, long long rows, int C,
+                                                     bf16* __restrict__ out, long long out_ld) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int c = (int)(i % nvec) * 8;
+    float f[8], hi[8], lo[8];
+    load8(x + r * ld + c, f);
+    split8(f, hi, lo);
+    const bf16x8 h8 = pack8(hi);
+    bf16* o = out + r * out_ld + c;
+    *reinterpret_cast<bf16x8*>(o) = h8;
+    *reinterpret_cast<bf16x8*>(o + C) = pack8(lo);
+    *reinterpret_cast<bf16x8*>(o + 2 * C) = h8;
+  }
 }
 
 __global__ void ref_invnorm_kernel(const float* __restrict__ n2, int B, int H, int W, int d0, int d1, int d2, int ndil,
@@ -57,18 +92,19 @@ __global__ void ref_invnorm_kernel(const float* __restrict__ n2, int B, int H, i
 }
 
 // grid (co_pad, B, ndil), block 128
-__global__ void __launch_bounds__(128) coarse_filters_kernel(const bf16* __restrict__ f, int B, int H, int W, int C,
+__global__ void __launch_bounds__(128) coarse_filters_kernel(const float* __restrict__ f, int B, int H, int W, int C,
                                                              int k_y, int k_x, int d0, int d1, int d2, int co_pad,
                                                              bf16* __restrict__ w) {
   __shared__ float red[4];
   const int blk = blockIdx.x, b = blockIdx.y, di = blockIdx.z;
   const int px = W / k_x, py = H / k_y;
   const int nvec = C >> 3;
-  bf16* wout = w + ((((size_t)di * B + b) * 9) * co_pad + blk) * (size_t)C;      // + tap * co_pad * C
+  const size_t C3 = 3 * (size_t)C;                                               // [hi | hi | lo] per filter row
+  bf16* wout = w + ((((size_t)di * B + b) * 9) * co_pad + blk) * C3;             // + tap * co_pad * 3C
   if (blk >= py * px) {
-    for (int i = threadIdx.x; i < 9 * nvec; i += blockDim.x) {
-      const int tap = i / nvec, v = i % nvec;
-      *reinterpret_cast<uint4*>(wout + (size_t)tap * co_pad * C + v * 8) = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 9 * 3 * nvec; i += blockDim.x) {
+      const int tap = i / (3 * nvec), v = i % (3 * nvec);
+      *reinterpret_cast<uint4*>(wout + (size_t)tap * co_pad * C3 + v * 8) = make_uint4(0, 0, 0, 0);
     }
     return;
   }
@@ -81,7 +117,7 @@ __global__ void __launch_bounds__(128) coarse_filters_kernel(const bf16* __restr
     const int yy = clampi(by * k_y - 1 + cy + (tap / 3 - 1) * d, 0, H - 1);
     const int xx = clampi(bx * k_x - 1 + cx + (tap % 3 - 1) * d, 0, W - 1);
     float e[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(f + (((size_t)b * H + yy) * W + xx) * C + v * 8), e);
+    load8(f + (((size_t)b * H + yy) * W + xx) * C + v * 8, e);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s = fmaf(e[j], e[j], s);
   }
@@ -91,11 +127,16 @@ __global__ void __launch_bounds__(128) coarse_filters_kernel(const bf16* __restr
     const int tap = i / nvec, v = i % nvec;
     const int yy = clampi(by * k_y - 1 + cy + (tap / 3 - 1) * d, 0, H - 1);
     const int xx = clampi(bx * k_x - 1 + cx + (tap % 3 - 1) * d, 0, W - 1);
-    float e[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(f + (((size_t)b * H + yy) * W + xx) * C + v * 8), e);
+    float e[8], hi[8], lo[8];
+    load8(f + (((size_t)b * H + yy) * W + xx) * C + v * 8, e);
 #pragma unroll
     for (int j = 0; j < 8; ++j) e[j] *= inv;
-    *reinterpret_cast<bf16x8*>(wout + (size_t)tap * co_pad * C + v * 8) = pack8(e);
+    split8(e, hi, lo);
+    bf16* o = wout + (size_t)tap * co_pad * C3 + v * 8;
+    const bf16x8 h8 = pack8(hi);
+    *reinterpret_cast<bf16x8*>(o) = h8;
+    *reinterpret_cast<bf16x8*>(o + C) = h8;
+    *reinterpret_cast<bf16x8*>(o + 2 * C) = pack8(lo);
   }
 }
 
@@ -142,7 +183,7 @@ __global__ void __launch_bounds__(256) coarse_argmax_kernel(const float* __restr
 }
 
 // grid (nq, nwin), block 128:  w[win][tap][q][C]
-__global__ void __launch_bounds__(128) fine_filters_kernel(const bf16* __restrict__ f, int H, int W, int C, int k_y,
+__global__ void __launch_bounds__(128) fine_filters_kernel(const float* __restrict__ f, int H, int W, int C, int k_y,
                                                            int k_x, bf16* __restrict__ w) {
   __shared__ float red[4];
   const int q = blockIdx.x, win = blockIdx.y;
@@ -158,7 +199,7 @@ __global__ void __launch_bounds__(128) fine_filters_kernel(const bf16* __restric
     const int yy = clampi(by * k_y - 1 + qy + tap / 3, 0, H - 1);
     const int xx = clampi(bx * k_x - 1 + qx + tap % 3, 0, W - 1);
     float e[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(f + (((size_t)b * H + yy) * W + xx) * C + v * 8), e);
+    load8(f + (((size_t)b * H + yy) * W + xx) * C + v * 8, e);
 #pragma unroll
     for (int j = 0; j < 8; ++j) s = fmaf(e[j], e[j], s);
   }
@@ -168,11 +209,16 @@ __global__ void __launch_bounds__(128) fine_filters_kernel(const bf16* __restric
     const int tap = i / nvec, v = i % nvec;
     const int yy = clampi(by * k_y - 1 + qy + tap / 3, 0, H - 1);
     const int xx = clampi(bx * k_x - 1 + qx + tap % 3, 0, W - 1);
-    float e[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(f + (((size_t)b * H + yy) * W + xx) * C + v * 8), e);
+    float e[8], hi[8], lo[8];
+    load8(f + (((size_t)b * H + yy) * W + xx) * C + v * 8, e);
 #pragma unroll
     for (int j = 0; j < 8; ++j) e[j] *= inv;
-    *reinterpret_cast<bf16x8*>(w + (((size_t)win * 9 + tap) * nq + q) * C + v * 8) = pack8(e);
+    split8(e, hi, lo);
+    bf16* o = w + (((size_t)win * 9 + tap) * nq + q) * 3 * (size_t)C + v * 8;       // [hi | hi | lo]
+    const bf16x8 h8 = pack8(hi);
+    *reinterpret_cast<bf16x8*>(o) = h8;
+    *reinterpret_cast<bf16x8*>(o + C) = h8;
+    *reinterpret_cast<bf16x8*>(o + 2 * C) = pack8(lo);
   }
 }
 
@@ -454,10 +500,19 @@ inline int grid1d(long long items, int per_block) {
 
 }  // namespace
 
-extern "C" int tdr_sqnorm_rows(const void* x_bf16, long long ld, long long rows, int C, float* n2, cudaStream_t stream) {
-  TDR_CHECK_ARG(x_bf16 && n2 && C % 8 == 0 && ld % 8 == 0 && rows > 0, "tdr_sqnorm_rows: bad arguments");
+extern "C" int tdr_sqnorm_rows(const float* x, long long ld, long long rows, int C, float* n2, cudaStream_t stream) {
+  TDR_CHECK_ARG(x && n2 && C % 8 == 0 && ld % 4 == 0 && rows > 0 && ((uintptr_t)x & 15) == 0, "tdr_sqnorm_rows: bad arguments");
   const long long blocks = (rows * 32 + 255) / 256;
-  sqnorm_rows_kernel<<<(int)blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x_bf16), ld, rows, C, n2);
+  sqnorm_rows_kernel<<<(int)blocks, 256, 0, stream>>>(x, ld, rows, C, n2);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_masa_split3(const float* x, long long ld, long long rows, int C, void* out_bf16, long long out_ld,
+                               cudaStream_t stream) {
+  TDR_CHECK_ARG(x && out_bf16 && C % 8 == 0 && ld % 4 == 0 && out_ld % 8 == 0 && out_ld >= 3LL * C && rows > 0 &&
+                ((uintptr_t)x & 15) == 0 && ((uintptr_t)out_bf16 & 15) == 0, "tdr_masa_split3: bad arguments");
+  split3_kernel<<<grid1d(rows * (C / 8), 256), 256, 0, stream>>>(x, ld, rows, C, reinterpret_cast<bf16*>(out_bf16), out_ld);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
@@ -471,15 +526,15 @@ extern "C" int tdr_masa_ref_invnorm(const float* n2, int B, int H, int W, const 
   return TDR_OK;
 }
 
-extern "C" int tdr_masa_coarse_filters(const void* f_lq_bf16, int B, int H, int W, int C, int k_y, int k_x,
+extern "C" int tdr_masa_coarse_filters(const float* f_lq, int B, int H, int W, int C, int k_y, int k_x,
                                        const int* host_dils, int ndil, int co_pad, void* w_bf16, cudaStream_t stream) {
-  TDR_CHECK_ARG(f_lq_bf16 && w_bf16 && host_dils && ndil >= 1 && ndil <= 3, "tdr_masa_coarse_filters: bad arguments");
+  TDR_CHECK_ARG(f_lq && w_bf16 && host_dils && ndil >= 1 && ndil <= 3, "tdr_masa_coarse_filters: bad arguments");
   TDR_CHECK_ARG(C % 8 == 0 && H % k_y == 0 && W % k_x == 0, "tdr_masa_coarse_filters: bad geometry");
   TDR_CHECK_ARG(co_pad % 8 == 0 && co_pad >= (H / k_y) * (W / k_x), "tdr_masa_coarse_filters: bad co_pad");
   const int d0 = host_dils[0], d1 = ndil > 1 ? host_dils[1] : 1, d2 = ndil > 2 ? host_dils[2] : 1;
   dim3 grid(co_pad, B, ndil);
-  coarse_filters_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(f_lq_bf16), B, H, W, C, k_y, k_x, d0, d1,
-                                                  d2, co_pad, reinterpret_cast<bf16*>(w_bf16));
+  coarse_filters_kernel<<<grid, 128, 0, stream>>>(f_lq, B, H, W, C, k_y, k_x, d0, d1, d2, co_pad,
+                                                  reinterpret_cast<bf16*>(w_bf16));
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
@@ -495,12 +550,11 @@ extern "C" int tdr_masa_coarse_argmax(const float* score, int B, int Hr, int Wr,
   return TDR_OK;
 }
 
-extern "C" int tdr_masa_fine_filters(const void* f_lq_bf16, int B, int H, int W, int C, int k_y, int k_x, void* w_bf16,
+extern "C" int tdr_masa_fine_filters(const float* f_lq, int B, int H, int W, int C, int k_y, int k_x, void* w_bf16,
                                      cudaStream_t stream) {
-  TDR_CHECK_ARG(f_lq_bf16 && w_bf16 && C % 8 == 0 && H % k_y == 0 && W % k_x == 0, "tdr_masa_fine_filters: bad arguments");
+  TDR_CHECK_ARG(f_lq && w_bf16 && C % 8 == 0 && H % k_y == 0 && W % k_x == 0, "tdr_masa_fine_filters: bad arguments");
   dim3 grid(k_y * k_x, B * (H / k_y) * (W / k_x));
-  fine_filters_kernel<<<grid, 128, 0, stream>>>(reinterpret_cast<const bf16*>(f_lq_bf16), H, W, C, k_y, k_x,
-                                                reinterpret_cast<bf16*>(w_bf16));
+  fine_filters_kernel<<<grid, 128, 0, stream>>>(f_lq, H, W, C, k_y, k_x, reinterpret_cast<bf16*>(w_bf16));
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -34,7 +34,13 @@ static int make_plan(int B, long long P, int C, int heads, GramPlan* p) {
   p->boxes = p->c <= 64 ? 1 : 2;
   p->stages = p->boxes == 1 ? 4 : 3;
   p->tiles_total = (int)((P + kPixTile - 1) / kPixTile);
-  int want = tdr_num_sms() / (B * heads);
+  // The split of the pixel axis is a function of (P, heads) ONLY, never of the batch size: the fp32 partial sums are
+  // then combined in the same order whether a sample is run alone or inside a batch, so a sample's output does not
+  // depend on its batch mates (a different summation order moves the Gram by ~1e-7, which flips bf16 roundings of
+  // Weff downstream and showed up as a 4.5e-3 batch-size dependence of the 512x512 output).  num_sms / heads chunks
+  // per (sample, head) make every sample one full wave of CTAs.
+  (void)B;
+  int want = tdr_num_sms() / heads;
   if (want < 1) want = 1;
   if (want > p->tiles_total) want = p->tiles_total;
   p->tiles_per_chunk = (p->tiles_total + want - 1) / want;
@@ -50,6 +56,7 @@ struct GramArgs {
   long long P;
   GramPlan plan;
   float* partials;
+  int fp16;                     // q, k are IEEE fp16 (inference forward) instead of bf16
 };
 
 __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant__ TdrTensorMap map, const GramArgs a) {
@@ -101,7 +108,7 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = umma_idesc_bf16(pl.M, pl.N, 1, 1);
+    const uint32_t idesc = umma_idesc_bf16(pl.M, pl.N, 1, 1, a.fp16, a.fp16);
     int stage = 0;
     uint32_t phase = 0;
     for (int t = 0; t < ntiles; ++t) {
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
 constexpr int kFoldRows = 8;      // output rows per CTA: small, so that even one (sample, head) spreads over C/8 CTAs
 __global__ void __launch_bounds__(256) mdta_fold_kernel(const float* __restrict__ attn, int C, int heads,
                                                         const float* __restrict__ w_out, bf16* __restrict__ weff,
-                                                        long long weff_ld, bf16* __restrict__ weff_t) {
+                                                        long long weff_ld, bf16* __restrict__ weff_t, int fp16) {
   extern __shared__ float sm[];
   const int c = C / heads;
   const int h = blockIdx.y, b = blockIdx.z;
@@ -275,7 +282,7 @@ __global__ void __launch_bounds__(256) mdta_fold_kernel(const float* __restrict_
     float s = 0.f;
 #pragma unroll 4
     for (int i = 0; i < c; ++i) s = fmaf(wr[i], a[i * c + j], s);
-    weff[((size_t)b * C + co0 + r) * weff_ld + h * c + j] = __float2bfloat16(s);
+    reinterpret_cast<uint16_t*>(weff)[((size_t)b * C + co0 + r) * weff_ld + h * c + j] = pack1r(s, fp16);
     if (weff_t) weff_t[((size_t)b * C + h * c + j) * weff_ld + co0 + r] = __float2bfloat16(s);   // transposed (dgrad)
   }
 }
@@ -289,13 +296,13 @@ extern "C" size_t tdr_mdta_partials_bytes(int B, long long P, int C, int heads) 
 }
 
 extern "C" int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long long P, int C, int heads, float* partials,
-                             cudaStream_t stream) {
+                             int fp16, cudaStream_t stream) {
   TDR_CHECK_ARG(qkv_bf16 && partials && B > 0 && P > 0, "tdr_mdta_gram: bad arguments");
   TDR_CHECK_ARG(ld % 8 == 0 && ld >= 3 * C, "tdr_mdta_gram: ld must be a multiple of 8 and >= 3C");
   GramArgs a;
   TDR_CHECK_ARG(make_plan(B, P, C, heads, &a.plan) == 0,
                 "tdr_mdta_gram: unsupported head width (C=%d heads=%d; need c%%8==0, c<=128, c%%16==0 if c>64)", C, heads);
-  a.B = B; a.C = C; a.heads = heads; a.P = P; a.partials = partials;
+  a.B = B; a.C = C; a.heads = heads; a.P = P; a.partials = partials; a.fp16 = fp16 ? 1 : 0;
   TdrTensorMap map;
   const uint64_t dims[3] = {(uint64_t)(3 * C), (uint64_t)P, (uint64_t)B};
   const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)P};
@@ -317,7 +324,7 @@ extern "C" int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long lon
 
 extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature,
                              const float* w_out, void* weff_bf16, long long weff_ld, float* attn_ws,
-                             void* weff_t_bf16, float* shat_out, cudaStream_t stream) {
+                             void* weff_t_bf16, float* shat_out, int fp16, cudaStream_t stream) {
   TDR_CHECK_ARG(partials && temperature && w_out && weff_bf16 && attn_ws, "tdr_mdta_weff: null pointer");
   GramPlan p;
   TDR_CHECK_ARG(make_plan(B, P, C, heads, &p) == 0, "tdr_mdta_weff: unsupported head width");
@@ -335,7 +342,7 @@ extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, i
   }
   dim3 grid((C + kFoldRows - 1) / kFoldRows, heads, B);
   mdta_fold_kernel<<<grid, 256, smem, stream>>>(attn_ws, C, heads, w_out, reinterpret_cast<bf16*>(weff_bf16), weff_ld,
-                                            reinterpret_cast<bf16*>(weff_t_bf16));
+                                            reinterpret_cast<bf16*>(weff_t_bf16), fp16);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

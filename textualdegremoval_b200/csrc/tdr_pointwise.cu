@@ -70,14 +70,14 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
         x.z = x.z * rstd * ww.z;
         x.w = x.w * rstd * ww.w;
       }
-      if (act == 3) {                   // LeakyReLU(0.01)
+      if ((act & 15) == 3) {            // LeakyReLU(0.01)
         x.x = x.x > 0.f ? x.x : 0.01f * x.x; x.y = x.y > 0.f ? x.y : 0.01f * x.y;
         x.z = x.z > 0.f ? x.z : 0.01f * x.z; x.w = x.w > 0.f ? x.w : 0.01f * x.w;
       }
       if (out) {
         uint2 pk;
-        pk.x = pack2(x.x, x.y);
-        pk.y = pack2(x.z, x.w);
+        pk.x = pack2r(x.x, x.y, act & 16);               // act bit 4: the 16-bit output is IEEE fp16
+        pk.y = pack2r(x.z, x.w, act & 16);
         *reinterpret_cast<uint2*>(out + row * out_ld + idx * 4) = pk;
       }
       if (out32) *reinterpret_cast<float4*>(out32 + row * out32_ld + idx * 4) = x;
@@ -121,6 +121,13 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return r;
 }
 __device__ __forceinline__ f2 bf2_to_f2(uint32_t u) { return pk2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+// two 16-bit values (bf16, or IEEE fp16 when HALF) packed in a 32-bit word -> fp32 pair (exact)
+template <bool HALF>
+__device__ __forceinline__ f2 x2_to_f2(uint32_t u) {
+  float a, b;
+  unpack2t<HALF>(u, a, b);
+  return pk2(a, b);
+}
 
 __device__ __forceinline__ f2 add2(f2 a, f2 b) {
   f2 d;
@@ -333,7 +340,7 @@ struct DwArgs {
 // (training forward; a separate instantiation so that the inference kernel is untouched), 2 gate BACKWARD: recomputes the two depthwise
 // halves (a | b) exactly as the forward does and writes d[a | b] = [dg * b * act'(a) | dg * act(a)] (2 * Cout channels),
 // i.e. tdr_dwconv3x3(gate 0) + tdr_gate_bwd without the round trip of the pre-gate tensor through HBM.
-template <int GATE>
+template <int GATE, bool HALF>
 __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_constant__ TdrTensorMap map, const DwArgs a) {
   constexpr int NH = GATE ? 2 : 1;
   constexpr int VEC = GATE ? 4 : 8;
@@ -428,10 +435,11 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
           const uint32_t* u = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
           for (int e = 0; e < NP; ++e) {
-            const f2 v = bf2_to_f2(u[e]);
+            const f2 v = x2_to_f2<HALF>(u[e]);
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-              acc[(i + k) % 3][h][e] = fma2(w[h][(2 - k) * 3 + kx][e], v, acc[(i + k) % 3][h][e]);
+            for (int k = 0; k < 3; ++k)                    // staged row i feeds output rows i - 2 + k: skip the ones outside
+              if (i + k >= 2 && i + k < kDwRows + 2)       // the tile (20 % of the halo tile's FMAs; i, k are constants)
+                acc[(i + k) % 3][h][e] = fma2(w[h][(2 - k) * 3 + kx][e], v, acc[(i + k) % 3][h][e]);
           }
         }
       if (i >= 2) {                                        // output row y0 + i - 2 (slot i % 3) is complete
@@ -491,7 +499,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
               if (GATE) val = mul2(a.gate == 1 ? gelu2(val) : val, acc[i % 3][NH - 1][e]);
               float a0, a1;
               upk2(val, a0, a1);
-              ou[e] = pack2(a0, a1);
+              ou[e] = pack2t<HALF>(a0, a1);
             }
             *reinterpret_cast<raw_t*>(outp) = o;
           }
@@ -520,7 +528,8 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
                                                                const int* __restrict__ co_map, int Co_p,
                                                                const int* __restrict__ ci_map, int Ci_p,
                                                                const float* __restrict__ scale, bf16* __restrict__ out,
-                                                               long long ld, bf16* __restrict__ out_t, long long ld_t) {
+                                                               long long ld, bf16* __restrict__ out_t, long long ld_t,
+                                                               int fwd_fp16) {
   const long long n_f = out ? (long long)T * Co_p * ld : 0;
   const long long n_t = out_t ? (long long)T * Ci_p * ld_t : 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_f + n_t; i += (long long)gridDim.x * blockDim.x) {
@@ -541,7 +550,8 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
         if (scale) v *= scale[co];
       }
     }
-    (tr ? out_t : out)[i - (tr ? n_f : 0)] = __float2bfloat16(v);
+    if (tr) out_t[i - n_f] = __float2bfloat16(v);
+    else reinterpret_cast<uint16_t*>(out)[i] = pack1r(v, fwd_fp16);
   }
 }
 
@@ -606,7 +616,8 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, long long ld,
 }
 
 __global__ void copy_rows_kernel(const float* __restrict__ src, long long src_ld, long long rows, int C,
-                                 float* __restrict__ dst, long long dst_ld, bf16* __restrict__ d16, long long ld16) {
+                                 float* __restrict__ dst, long long dst_ld, bf16* __restrict__ d16, long long ld16,
+                                 int fp16) {
   const int nvec = C >> 2;
   const long long total = rows * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -617,8 +628,8 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, long long src_ld
     if (dst) *reinterpret_cast<float4*>(dst + r * dst_ld + c) = v;
     if (d16) {
       uint2 pk;
-      pk.x = pack2(v.x, v.y);
-      pk.y = pack2(v.z, v.w);
+      pk.x = pack2r(v.x, v.y, fp16);
+      pk.y = pack2r(v.z, v.w, fp16);
       *reinterpret_cast<uint2*>(d16 + r * ld16 + c) = pk;
     }
   }
@@ -686,7 +697,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_ci_kernel(const float* __re
     for (int px = 0; px < 2; ++px) {
       if (x0 + px >= W) continue;
       const long long pix = ((long long)b * H + y) * W + x0 + px;
-      if (relu) {
+      if (relu & 1) {
 #pragma unroll
         for (int e = 0; e < CPT; ++e) acc[px][e] = fmaxf(acc[px][e], 0.f);
       }
@@ -698,10 +709,96 @@ __global__ void __launch_bounds__(256) conv3x3_small_ci_kernel(const float* __re
       }
       if (o16) {
 #pragma unroll
-        for (int q8 = 0; q8 < CPT / 8; ++q8)
-          *reinterpret_cast<bf16x8*>(o16 + pix * ld16 + cg * CPT + q8 * 8) = pack8(acc[px] + q8 * 8);
+        for (int q8 = 0; q8 < CPT / 8; ++q8) {
+          const float* v = acc[px] + q8 * 8;
+          if (relu & 2)                               // IEEE fp16 output (MASA feature encoder operands)
+            *reinterpret_cast<uint4*>(o16 + pix * ld16 + cg * CPT + q8 * 8) =
+                make_uint4(pack2h(v[0], v[1]), pack2h(v[2], v[3]), pack2h(v[4], v[5]), pack2h(v[6], v[7]));
+          else
+            *reinterpret_cast<bf16x8*>(o16 + pix * ld16 + cg * CPT + q8 * 8) = pack8(v);
+        }
       }
     }
+  }
+}
+
+// fp32 rows -> bf16 and / or fp16 copies (8 channels per thread), optional device-side power-of-two scales
+__global__ void __launch_bounds__(256) cast_rows_kernel(float* __restrict__ src, long long src_ld, long long rows,
+                                                        int C, bf16* __restrict__ d16, long long ld16,
+                                                        __half* __restrict__ dh, long long ldh,
+                                                        const float* __restrict__ scale16,
+                                                        const float* __restrict__ scale_bf16, int rescale_in) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  const float sh = scale16 ? *scale16 : 1.f, sb = scale_bf16 ? *scale_bf16 : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int c = (int)(i % nvec) * 8;
+    float4 a = *reinterpret_cast<const float4*>(src + r * src_ld + c);
+    float4 b = *reinterpret_cast<const float4*>(src + r * src_ld + c + 4);
+    if (d16)
+      *reinterpret_cast<uint4*>(d16 + r * ld16 + c) = make_uint4(pack2(a.x * sb, a.y * sb), pack2(a.z * sb, a.w * sb),
+                                                                 pack2(b.x * sb, b.y * sb), pack2(b.z * sb, b.w * sb));
+    a.x *= sh; a.y *= sh; a.z *= sh; a.w *= sh; b.x *= sh; b.y *= sh; b.z *= sh; b.w *= sh;
+    if (dh)
+      *reinterpret_cast<uint4*>(dh + r * ldh + c) = make_uint4(pack2h(a.x, a.y), pack2h(a.z, a.w), pack2h(b.x, b.y), pack2h(b.z, b.w));
+    if (rescale_in) {
+      *reinterpret_cast<float4*>(src + r * src_ld + c) = a;
+      *reinterpret_cast<float4*>(src + r * src_ld + c + 4) = b;
+    }
+  }
+}
+
+// max |x| over fp32 rows (x >= 0 bit patterns order like unsigned integers) -> state[3]
+__global__ void __launch_bounds__(256) absmax_rows_kernel(const float* __restrict__ x, long long ld, long long rows, int C,
+                                                          float* __restrict__ state) {
+  const int nvec = C >> 2;
+  const long long total = rows * nvec;
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = *reinterpret_cast<const float4*>(x + (i / nvec) * ld + (i % nvec) * 4);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m == m) atomicMax(reinterpret_cast<unsigned int*>(state + 3), __float_as_uint(m));
+}
+
+__global__ void level_scale_finalize_kernel(const float* __restrict__ prev, float* __restrict__ cur) {
+  const float m = cur[3];
+  float r = 1.f;
+  if (m > 64.f && m < 3.0e38f) r = exp2f(ceilf(log2f(m)) - 6.f);          // max |x / r| in (32, 64]
+  const float s = (prev ? prev[0] : 1.f) * r;
+  cur[0] = s;
+  cur[1] = 1.f / s;
+  cur[2] = 1.f / r;
+}
+
+__global__ void __launch_bounds__(256) scale_vec_kernel(const float* __restrict__ v, long long n,
+                                                        const float* __restrict__ scale, float* __restrict__ out) {
+  const float sc = *scale;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = v[i] * sc;
+}
+
+__global__ void __launch_bounds__(256) cvt_f16_bf16_kernel(const __half* __restrict__ src, long long src_ld, long long rows,
+                                                           int C, bf16* __restrict__ dst, long long dst_ld) {
+  const int nvec = C >> 3;
+  const long long total = rows * nvec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int c = (int)(i % nvec) * 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(src + r * src_ld + c);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+      o[k] = pack2(f.x, f.y);
+    }
+    *reinterpret_cast<uint4*>(dst + r * dst_ld + c) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -775,7 +872,7 @@ extern "C" int tdr_rownorm(const float* in, long long in_ld, long long rows, int
   TDR_CHECK_ARG(in && (out_bf16 || out_f32) && rows >= 0 && C > 0, "tdr_rownorm: bad arguments");
   TDR_CHECK_ARG(C % 4 == 0 && in_ld % 4 == 0 && out_ld % 4 == 0 && out_f32_ld % 4 == 0,
                 "tdr_rownorm: C and strides must be multiples of 4");
-  TDR_CHECK_ARG(act == 0 || act == 3, "tdr_rownorm: act must be 0 or 3 (LeakyReLU)");
+  TDR_CHECK_ARG((act & ~16) == 0 || (act & ~16) == 3, "tdr_rownorm: act must be 0 or 3 (LeakyReLU), optionally | 16 (fp16 output)");
   TDR_CHECK_ARG(mode >= 0 && mode <= 2, "tdr_rownorm: bad mode");
   TDR_CHECK_ARG(mode == 0 || weight, "tdr_rownorm: weight required");
   TDR_CHECK_ARG(C <= 4096, "tdr_rownorm: C too large (%d)", C);
@@ -812,7 +909,10 @@ static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int
   const bool bwd = dg_bf16 != nullptr;
   TDR_CHECK_ARG(in_bf16 && out_bf16 && weight, "tdr_dwconv3x3: null pointer");
   TDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "tdr_dwconv3x3: bad dims");
+  const bool half = (gate & 16) != 0;               // bit 4: activations are IEEE fp16 (inference forward), else bf16
+  gate &= 15;
   TDR_CHECK_ARG(gate >= 0 && gate <= 2, "tdr_dwconv3x3: bad gate");
+  TDR_CHECK_ARG(!half || (!dg_bf16 && !y_out), "tdr_dwconv3x3: the training / backward variants take bf16 activations");
   TDR_CHECK_ARG(C % 8 == 0, "tdr_dwconv3x3: C must be a multiple of 8");
   TDR_CHECK_ARG(in_ld % 8 == 0 && out_ld % 4 == 0, "tdr_dwconv3x3: bad strides");
   TDR_CHECK_ARG(((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)out_bf16 & 7) == 0, "tdr_dwconv3x3: alignment");
@@ -822,7 +922,7 @@ static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int
   const bf16* in = reinterpret_cast<const bf16*>(in_bf16);
   bf16* out = reinterpret_cast<bf16*>(out_bf16);
   static const bool use_strip = getenv("TDR_DWCONV_STRIP") != nullptr;     // previous (non-TMA) kernel, experiments only
-  if (use_strip && !bwd) {
+  if (use_strip && !bwd && !half) {
     constexpr int R = 16;
     if (gate) {
       const int items = W * (C / 2 / 4);
@@ -860,16 +960,20 @@ static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int
   const size_t smem = 2 * kDwStageBytes;
   static bool attr_set = false;
   if (!attr_set) {
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  if (bwd) dwconv3x3_tma_kernel<2><<<grid, 256, smem, stream>>>(map, a);
-  else if (gate && y_out) dwconv3x3_tma_kernel<3><<<grid, 256, smem, stream>>>(map, a);
-  else if (gate) dwconv3x3_tma_kernel<1><<<grid, 256, smem, stream>>>(map, a);
-  else dwconv3x3_tma_kernel<0><<<grid, 256, smem, stream>>>(map, a);
+  if (bwd) dwconv3x3_tma_kernel<2, false><<<grid, 256, smem, stream>>>(map, a);
+  else if (gate && y_out) dwconv3x3_tma_kernel<3, false><<<grid, 256, smem, stream>>>(map, a);
+  else if (gate && half) dwconv3x3_tma_kernel<1, true><<<grid, 256, smem, stream>>>(map, a);
+  else if (gate) dwconv3x3_tma_kernel<1, false><<<grid, 256, smem, stream>>>(map, a);
+  else if (half) dwconv3x3_tma_kernel<0, true><<<grid, 256, smem, stream>>>(map, a);
+  else dwconv3x3_tma_kernel<0, false><<<grid, 256, smem, stream>>>(map, a);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
@@ -918,13 +1022,58 @@ extern "C" int tdr_nhwc_to_nchw(const float* src, long long src_ld, int B, int C
 }
 
 extern "C" int tdr_copy_rows_f32(const float* src, long long src_ld, long long rows, int C, float* dst,
-                                 long long dst_ld, void* dst_bf16, long long dst_bf16_ld, cudaStream_t stream) {
+                                 long long dst_ld, void* dst_bf16, long long dst_bf16_ld, int dst16_fp16,
+                                 cudaStream_t stream) {
   TDR_CHECK_ARG(src && (dst || dst_bf16), "tdr_copy_rows_f32: null pointer");
   TDR_CHECK_ARG(C % 4 == 0 && src_ld % 4 == 0 && dst_ld % 4 == 0 && dst_bf16_ld % 4 == 0,
                 "tdr_copy_rows_f32: C / strides must be multiples of 4");
   if (rows == 0) return TDR_OK;
   copy_rows_kernel<<<grid_for(rows * (C / 4), 256, 16), 256, 0, stream>>>(src, src_ld, rows, C, dst, dst_ld,
-                                                                         reinterpret_cast<bf16*>(dst_bf16), dst_bf16_ld);
+                                                                         reinterpret_cast<bf16*>(dst_bf16), dst_bf16_ld,
+                                                                         dst16_fp16);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_cast_rows(float* in, long long in_ld, long long rows, int C, void* out_bf16, long long out_bf16_ld,
+                             void* out_fp16, long long out_fp16_ld, const float* scale16, const float* scale_bf16,
+                             int rescale_in, cudaStream_t stream) {
+  TDR_CHECK_ARG(in && (out_bf16 || out_fp16), "tdr_cast_rows: null pointer");
+  TDR_CHECK_ARG(C % 8 == 0 && in_ld % 4 == 0 && out_bf16_ld % 8 == 0 && out_fp16_ld % 8 == 0 && ((uintptr_t)in & 15) == 0 &&
+                ((uintptr_t)out_bf16 & 15) == 0 && ((uintptr_t)out_fp16 & 15) == 0, "tdr_cast_rows: C %% 8, 16 B-aligned rows");
+  if (rows == 0) return TDR_OK;
+  cast_rows_kernel<<<grid_for(rows * (C / 8), 256, 16), 256, 0, stream>>>(in, in_ld, rows, C, reinterpret_cast<bf16*>(out_bf16),
+                                                                         out_bf16_ld, reinterpret_cast<__half*>(out_fp16),
+                                                                         out_fp16_ld, scale16, scale_bf16, rescale_in);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_masa_level_scale(const float* x, long long ld, long long rows, int C, const float* state_prev,
+                                    float* state_cur, cudaStream_t stream) {
+  TDR_CHECK_ARG(x && state_cur && rows > 0 && C % 4 == 0 && ld % 4 == 0 && ((uintptr_t)x & 15) == 0,
+                "tdr_masa_level_scale: bad arguments");
+  absmax_rows_kernel<<<grid_for(rows * (C / 4), 256, 8), 256, 0, stream>>>(x, ld, rows, C, state_cur);
+  TDR_CHECK_LAUNCH();
+  level_scale_finalize_kernel<<<1, 1, 0, stream>>>(state_prev, state_cur);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_scale_vec(const float* v, long long n, const float* scale, float* out, cudaStream_t stream) {
+  TDR_CHECK_ARG(v && scale && out && n > 0, "tdr_scale_vec: bad arguments");
+  scale_vec_kernel<<<grid_for(n, 256, 4), 256, 0, stream>>>(v, n, scale, out);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_cvt_f16_bf16(const void* in_fp16, long long in_ld, long long rows, int C, void* out_bf16, long long out_ld,
+                                cudaStream_t stream) {
+  TDR_CHECK_ARG(in_fp16 && out_bf16 && C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0 && ((uintptr_t)in_fp16 & 15) == 0 &&
+                ((uintptr_t)out_bf16 & 15) == 0, "tdr_cvt_f16_bf16: C %% 8, 16 B-aligned rows");
+  if (rows == 0) return TDR_OK;
+  cvt_f16_bf16_kernel<<<grid_for(rows * (C / 8), 256, 16), 256, 0, stream>>>(reinterpret_cast<const __half*>(in_fp16), in_ld,
+                                                                            rows, C, reinterpret_cast<bf16*>(out_bf16), out_ld);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
@@ -974,7 +1123,7 @@ extern "C" int tdr_conv3x3_small_co(const void* in_bf16, long long in_ld, int B,
 // SimpleGate (network_nafnet_guided_arch.py:170-175) on bf16 rows: out[r, c] = x[r, c] * x[r, C + c]
 namespace {
 __global__ void __launch_bounds__(256) gate_mul_kernel(const bf16* __restrict__ x, long long ld, long long rows, int C,
-                                                       bf16* __restrict__ out, long long out_ld) {
+                                                       bf16* __restrict__ out, long long out_ld, int fp16) {
   const int nvec = C >> 3;
   const long long total = rows * nvec;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -982,17 +1131,17 @@ __global__ void __launch_bounds__(256) gate_mul_kernel(const bf16* __restrict__ 
     const long long r = i / nvec;
     const int c = (int)(i % nvec) * 8;
     float a[8], b[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(x + r * ld + c), a);
-    unpack8(*reinterpret_cast<const bf16x8*>(x + r * ld + C + c), b);
+    unpack8r(x + r * ld + c, a, fp16);
+    unpack8r(x + r * ld + C + c, b, fp16);
 #pragma unroll
     for (int e = 0; e < 8; ++e) a[e] *= b[e];
-    *reinterpret_cast<bf16x8*>(out + r * out_ld + c) = pack8(a);
+    pack8r(out + r * out_ld + c, a, fp16);
   }
 }
 
 // Global average pool, stage 1: grid (chunks, B); partial[b][chunk][c] = sum over the chunk's pixels of x[b, p, c]
 __global__ void __launch_bounds__(256) pool_partial_kernel(const bf16* __restrict__ x, long long ld, long long P, int C,
-                                                           int chunks, float* __restrict__ partial) {
+                                                           int chunks, float* __restrict__ partial, int fp16) {
   const int nvec = C >> 3;
   const int b = blockIdx.y, chunk = blockIdx.x;
   const long long per = (P + chunks - 1) / chunks;
@@ -1007,7 +1156,7 @@ __global__ void __launch_bounds__(256) pool_partial_kernel(const bf16* __restric
     if (v < nvec && pl < lanes) {
       for (long long p = p0 + pl; p < p1; p += lanes) {
         float f[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(x + ((long long)b * P + p) * ld + v * 8), f);
+        unpack8r(x + ((long long)b * P + p) * ld + v * 8, f, fp16);
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] += f[e];
       }
@@ -1060,25 +1209,25 @@ __global__ void __launch_bounds__(256) sca_fold_kernel(const float* __restrict__
                                                        const float* __restrict__ w3, int Co,
                                                        const float* __restrict__ rowscale, bf16* __restrict__ weff,
                                                        long long weff_ld, bf16* __restrict__ weff_t,
-                                                       long long weff_t_ld) {
+                                                       long long weff_t_ld, int fp16) {
   const long long total = (long long)B * Co * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int ci = (int)(i % C);
     const long long r = i / C;
     const int co = (int)(r % Co), b = (int)(r / Co);
-    const bf16 v = __float2bfloat16(w3[(size_t)co * C + ci] * s[(size_t)b * C + ci] * (rowscale ? rowscale[co] : 1.f));
-    weff[((size_t)b * Co + co) * weff_ld + ci] = v;
-    if (weff_t) weff_t[((size_t)b * C + ci) * weff_t_ld + co] = v;      // transposed copy: dgrad operand
+    const float vf = w3[(size_t)co * C + ci] * s[(size_t)b * C + ci] * (rowscale ? rowscale[co] : 1.f);
+    reinterpret_cast<uint16_t*>(weff)[((size_t)b * Co + co) * weff_ld + ci] = pack1r(vf, fp16);
+    if (weff_t) weff_t[((size_t)b * C + ci) * weff_t_ld + co] = __float2bfloat16(vf);      // transposed copy: dgrad operand
   }
 }
 }  // namespace
 
 extern "C" int tdr_gate_mul(const void* x_bf16, long long ld, long long rows, int C, void* out_bf16, long long out_ld,
-                            cudaStream_t stream) {
+                            int fp16, cudaStream_t stream) {
   TDR_CHECK_ARG(x_bf16 && out_bf16 && rows > 0 && C > 0 && C % 8 == 0 && ld % 8 == 0 && out_ld % 8 == 0,
                 "tdr_gate_mul: bad arguments");
   gate_mul_kernel<<<grid_for(rows * (C / 8), 256, 16), 256, 0, stream>>>(reinterpret_cast<const bf16*>(x_bf16), ld, rows,
-                                                                        C, reinterpret_cast<bf16*>(out_bf16), out_ld);
+                                                                        C, reinterpret_cast<bf16*>(out_bf16), out_ld, fp16);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
@@ -1098,7 +1247,7 @@ extern "C" size_t tdr_naf_sca_workspace_bytes(int B, long long P, int C) {
 extern "C" int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long long P, int C, const float* w_sca,
                                 const float* b_sca, const float* w3, int Co, const float* rowscale, void* weff_bf16,
                                 long long weff_ld, float* workspace, float* mean_out, float* s_out, void* weff_t_bf16,
-                                long long weff_t_ld, cudaStream_t stream) {
+                                long long weff_t_ld, int fp16, cudaStream_t stream) {
   TDR_CHECK_ARG((mean_out == nullptr) == (s_out == nullptr), "tdr_naf_sca_fold: mean_out and s_out go together");
   TDR_CHECK_ARG(!weff_t_bf16 || (weff_t_ld >= Co && weff_t_ld % 8 == 0), "tdr_naf_sca_fold: bad weff_t_ld");
   TDR_CHECK_ARG(g_bf16 && w_sca && w3 && weff_bf16 && workspace, "tdr_naf_sca_fold: null pointer");
@@ -1109,7 +1258,7 @@ extern "C" int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long lo
   float* mean = mean_out ? mean_out : workspace + (size_t)B * chunks * C;
   float* svec = s_out ? s_out : workspace + (size_t)B * chunks * C + (size_t)B * C;
   dim3 g1(chunks, B);
-  pool_partial_kernel<<<g1, 256, 0, stream>>>(reinterpret_cast<const bf16*>(g_bf16), ld, P, C, chunks, workspace);
+  pool_partial_kernel<<<g1, 256, 0, stream>>>(reinterpret_cast<const bf16*>(g_bf16), ld, P, C, chunks, workspace, fp16);
   TDR_CHECK_LAUNCH();
   sca_mean_kernel<<<tdr_cdiv((long long)B * C, 256), 256, 0, stream>>>(workspace, chunks, P, C, B, mean);
   TDR_CHECK_LAUNCH();
@@ -1117,14 +1266,14 @@ extern "C" int tdr_naf_sca_fold(const void* g_bf16, long long ld, int B, long lo
   TDR_CHECK_LAUNCH();
   sca_fold_kernel<<<grid_for((long long)B * Co * C, 256, 8), 256, 0, stream>>>(
       svec, B, C, w3, Co, rowscale, reinterpret_cast<bf16*>(weff_bf16), weff_ld, reinterpret_cast<bf16*>(weff_t_bf16),
-      weff_t_ld);
+      weff_t_ld, fp16);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
 
 extern "C" int tdr_pack_conv_weight(const float* w, int Co, int Ci, int KH, int KW, const int* co_map, int Co_p,
                                     const int* ci_map, int Ci_p, const float* scale, void* out_bf16, long long ld,
-                                    void* out_t_bf16, long long ld_t, cudaStream_t stream) {
+                                    void* out_t_bf16, long long ld_t, int fwd_fp16, cudaStream_t stream) {
   TDR_CHECK_ARG(w && (out_bf16 || out_t_bf16) && Co > 0 && Ci > 0 && KH > 0 && KW > 0 && Co_p > 0 && Ci_p > 0,
                 "tdr_pack_conv_weight: bad arguments");
   TDR_CHECK_ARG((!out_bf16 || ld >= Ci_p) && (!out_t_bf16 || ld_t >= Co_p), "tdr_pack_conv_weight: row stride too small");
@@ -1132,7 +1281,7 @@ extern "C" int tdr_pack_conv_weight(const float* w, int Co, int Ci, int KH, int 
   const long long n = (out_bf16 ? (long long)T * Co_p * ld : 0) + (out_t_bf16 ? (long long)T * Ci_p * ld_t : 0);
   pack_conv_weight_kernel<<<grid_for(n, 256, 8), 256, 0, stream>>>(w, Co, Ci, T, co_map, Co_p, ci_map, Ci_p, scale,
                                                                     reinterpret_cast<bf16*>(out_bf16), ld,
-                                                                    reinterpret_cast<bf16*>(out_t_bf16), ld_t);
+                                                                    reinterpret_cast<bf16*>(out_t_bf16), ld_t, fwd_fp16);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -36,6 +36,7 @@ class ConvGemmDesc(C.Structure):
         ("store_mode", C.c_int), ("impl", C.c_int),
         ("ln_mode", C.c_int), ("ln_eps", C.c_float), ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p),
         ("ln_out_bf16", C.c_void_p), ("ln_out_ld", C.c_longlong),
+        ("in_fp16", C.c_int), ("out_fp16", C.c_int),
     ]
 
 
@@ -59,12 +60,12 @@ SIGNATURES = {
     "tdr_conv3x3_small_co": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "tdr_rownorm": (_i, [_vp, _ll, _ll, _i, _i, _vp, _vp, _f, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_dwconv3x3": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _ll, _vp]),
-    "tdr_gate_mul": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp]),
+    "tdr_gate_mul": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _i, _vp]),
     "tdr_naf_sca_workspace_bytes": (_sz, [_i, _ll, _i]),
-    "tdr_naf_sca_fold": (_i, [_vp, _ll, _i, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _vp]),
+    "tdr_naf_sca_fold": (_i, [_vp, _ll, _i, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "tdr_mdta_partials_bytes": (_sz, [_i, _ll, _i, _i]),
-    "tdr_mdta_gram": (_i, [_vp, _ll, _i, _ll, _i, _i, _vp, _vp]),
-    "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _vp]),
+    "tdr_mdta_gram": (_i, [_vp, _ll, _i, _ll, _i, _i, _vp, _i, _vp]),
+    "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _i, _vp]),
     "tdr_vit_patchify": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
     "tdr_vit_assemble_tokens": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tdr_softmax_rows": (_i, [_vp, _ll, _ll, _i, _f, _vp, _ll, _vp]),
@@ -82,8 +83,14 @@ SIGNATURES = {
     "tdr_psnr_u8_sums": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "tdr_nchw_to_nhwc": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_nhwc_to_nchw": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _i, _vp, _ll, _vp, _vp]),
-    "tdr_copy_rows_f32": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp, _ll, _vp]),
+    "tdr_copy_rows_f32": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp, _ll, _i, _vp]),
     "tdr_sqnorm_rows": (_i, [_vp, _ll, _ll, _i, _vp, _vp]),
+    "tdr_masa_split3": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp]),
+    "tdr_cast_rows": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp, _ll, _vp, _vp, _i, _vp]),
+    "tdr_masa_level_scale": (_i, [_vp, _ll, _ll, _i, _vp, _vp, _vp]),
+    "tdr_scale_vec": (_i, [_vp, _ll, _vp, _vp, _vp]),
+    "tdr_cvt_f16_bf16": (_i, [_vp, _ll, _ll, _i, _vp, _ll, _vp]),
+
     "tdr_masa_ref_invnorm": (_i, [_vp, _i, _i, _i, C.POINTER(_i), _i, _vp, _vp]),
     "tdr_masa_coarse_filters": (_i, [_vp, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _i, _vp, _vp]),
     "tdr_masa_coarse_argmax": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -109,6 +116,7 @@ class WgradDesc(C.Structure):
         ("co_map", C.c_void_p), ("ci_map", C.c_void_p),
         ("accumulate", C.c_int), ("scale", C.c_float),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("scale_ptr", C.c_void_p),
     ]
 
 
@@ -129,7 +137,7 @@ SIGNATURES.update({
     "tdr_scale_add_f32": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _f, _vp, _ll, _vp]),
     "tdr_dot_f32": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _i, _vp, _vp]),
     "tdr_pixel_shuffle_nhwc": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
-    "tdr_pack_conv_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _ll, _vp, _ll, _vp]),
+    "tdr_pack_conv_weight": (_i, [_vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp, _ll, _vp, _ll, _i, _vp]),
     "tdr_pack_dw_weight": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp]),
     "tdr_gather_vec": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "tdr_relu_mask": (_i, [_vp, _ll, _vp, _ll, _ll, _i, _vp, _ll, _vp]),

@@ -12,7 +12,17 @@ import torch
 from . import lib
 
 BF16 = torch.bfloat16
+F16 = torch.float16
 F32 = torch.float32
+
+
+def operand_dtype(train):
+    """16-bit format of the GEMM / depthwise operands and stored intermediates.  Inference: IEEE fp16 -- with bf16's 8
+    significand bits the full-size guided-Restormer output sits at mean |delta| 1.05e-3 / 0.032 dB PSNR-delta from the fp32
+    reference, with fp16's 11 bits it meets the 1e-3 / 0.01 dB bar (tools/operand_format_study.py; same tcgen05 rate,
+    stores saturate at +-65504).  Training: bf16 -- the saved activations are operands of the bf16 gradient GEMMs (tcgen05
+    kind::f16 takes no mixed fp16 x bf16 pairs) and gradients need bf16's exponent range."""
+    return BF16 if train else F16
 
 
 def _stream():
@@ -82,30 +92,32 @@ def _f32c(t):
     return t if (t.dtype == F32 and t.is_contiguous()) else t.float().contiguous()
 
 
-def pack_conv(w, co_map=None, Co_p=None, ci_map=None, Ci_p=None, scale=None, fwd=True, dgrad=False):
+def pack_conv(w, co_map=None, Co_p=None, ci_map=None, Ci_p=None, scale=None, fwd=True, dgrad=False, dt=BF16):
     """nn.Conv2d weight [Co, Ci, kh, kw] -> (bf16 [T, Co_p, ld], bf16 [T, Ci_p, ld_t]): the tdr_conv_gemm operand and its
     transposed, tap-flipped twin (data gradient), each in ONE kernel launch.  co_map / ci_map: int32 DEVICE tensors mapping
-    padded channel -> logical channel (-1 = zero); scale: fp32 [Co] folded into the output channels."""
+    padded channel -> logical channel (-1 = zero); scale: fp32 [Co] folded into the output channels.  dt: 16-bit format
+    of the forward operand (torch.float16 for the inference forward); the twin is always bf16."""
     w = _f32c(w)
     co, ci, kh, kw = w.shape
     Co_p = co if Co_p is None else Co_p
     Ci_p = ci if Ci_p is None else Ci_p
     ld, ld_t = round_up(Ci_p, 8), round_up(Co_p, 8)
-    out = torch.empty((kh * kw, Co_p, ld), dtype=BF16, device=w.device) if fwd else None
+    out = torch.empty((kh * kw, Co_p, ld), dtype=dt, device=w.device) if fwd else None
     out_t = torch.empty((kh * kw, Ci_p, ld_t), dtype=BF16, device=w.device) if dgrad else None
     lib.call("tdr_pack_conv_weight", _p(w), co, ci, kh, kw, _p(co_map), Co_p, _p(ci_map), Ci_p, _p(scale), _p(out), ld,
-             _p(out_t), ld_t, _stream())
+             _p(out_t), ld_t, int(dt == F16), _stream())
     return out, out_t
 
 
-def pack_conv_weight(w: torch.Tensor, ci_map=None, co_map=None) -> torch.Tensor:
+def pack_conv_weight(w: torch.Tensor, ci_map=None, co_map=None, dt=BF16) -> torch.Tensor:
     """[Co, Ci, kh, kw] fp32 -> bf16 [kh*kw, Co, Ci_p] (tap-major, K contiguous, Ci padded to 8) for tdr_conv_gemm.
     Rows are NOT padded: the kernel's TMA box zero-fills beyond Co.
 
     ci_map / co_map: optional (n_padded, index tensor) placing logical channels at padded positions (GDFN halves).
     """
     if ci_map is None and co_map is None and w.dim() == 4 and w.is_cuda:
-        return pack_conv(w)[0]
+        return pack_conv(w, dt=dt)[0]
+    assert dt == BF16
     co, ci, kh, kw = w.shape
     wt = w.detach().permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
     if ci_map is not None:
@@ -174,7 +186,7 @@ def pack_dw_weight(w: torch.Tensor, n=None, idx=None) -> torch.Tensor:
 _ROWS16_DENSE = frozenset(int(v) for v in os.environ.get("TDR_ROWS16_DENSE", "").split(",") if v.strip())
 
 
-def rows16(B, H, W, Cc, dev):
+def rows16(B, H, W, Cc, dev, dt=BF16):
     """bf16 NHWC activation buffer whose row pitch is a multiple of 128 B (64 channels): a view [B,H,W,Cc] of a wider
     allocation.  Rows that straddle 128 B lines (C = 48, 96, 144, 288 ...) cost the TMA loads / stores of the GEMMs up to
     25 % of their bandwidth (tools/probe.py qkv48 vs qkv48_ld192); the pad columns are never read or written."""
@@ -182,20 +194,28 @@ def rows16(B, H, W, Cc, dev):
     if Cc in _ROWS16_DENSE:
         ld = Cc
     if ld == Cc:
-        return torch.empty((B, H, W, Cc), dtype=BF16, device=dev)
-    return torch.empty((B, H, W, ld), dtype=BF16, device=dev)[..., :Cc]
+        return torch.empty((B, H, W, Cc), dtype=dt, device=dev)
+    return torch.empty((B, H, W, ld), dtype=dt, device=dev)[..., :Cc]
 
 
 # ---------------------------------------------------------------------------------------------- ops
 def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, relu=False, gelu=False, rowscale=None,
               alpha=1.0, scale_ptr=None, res1=None, res1_scale=1.0, res2=None, out_f32=None, out_bf16=None,
-              want="bf16", store_mode=0, w_batched=False, w_raw=None, origin=None, window=None, impl=0, ln=None):
+              want="bf16", store_mode=0, w_batched=False, w_raw=None, origin=None, window=None, impl=0, ln=None,
+              out_fp16=None):
     """x: bf16 NHWC view.  wpack: bf16 [T, Co_p, Ci_p].  Returns (out_f32, out_bf16) -- allocated if not given
     according to ``want`` in {"bf16", "f32", "both"}.
 
     ln = (mode, weight, bias, eps, out_bf16_view): also write LayerNorm(out) of the finished fp32 rows (the norm that
-    follows on the residual stream) from the same epilogue; see ``conv_ln_ok``."""
-    assert x.dtype == BF16 and (w_raw is not None or wpack.dtype == BF16)
+    follows on the residual stream) from the same epilogue; see ``conv_ln_ok``.
+
+    fp16 ``x`` and ``wpack`` (the MASA feature encoder's operands) run the same kernel with fp16 operand descriptors;
+    out_fp16: the 16-bit output is IEEE fp16."""
+    in_fp16 = x.dtype == F16
+    assert x.dtype in (BF16, F16) and (w_raw is not None or wpack.dtype == x.dtype)
+    if out_fp16 is None:            # 16-bit outputs keep the operand format unless told otherwise
+        out_fp16 = (out_bf16.dtype == F16) if out_bf16 is not None else ((ln[4].dtype == F16) if ln is not None else in_fp16)
+    o16 = F16 if out_fp16 else BF16
     B, H, W, Cx = x.shape
     Ci = Cx if Ci is None else Ci
     d = lib.ConvGemmDesc()
@@ -235,7 +255,7 @@ def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, 
     if out_f32 is None and want in ("f32", "both"):
         out_f32 = torch.empty(oshape, dtype=F32, device=x.device)
     if out_bf16 is None and want in ("bf16", "both") and not (want == "bf16" and out_f32 is not None):
-        out_bf16 = torch.empty(oshape, dtype=BF16, device=x.device)
+        out_bf16 = torch.empty(oshape, dtype=o16, device=x.device)
     for o in (out_f32, out_bf16, res1, res2):
         if o is not None:
             assert tuple(o.shape) == oshape, f"output/residual shape {tuple(o.shape)} != {oshape}"
@@ -248,20 +268,23 @@ def conv_gemm(x, wpack, Co, *, Ci=None, k=1, stride=1, pad=0, dil=1, bias=None, 
         assert out_f32.dtype == F32
         d.out_f32 = out_f32.data_ptr(); d.out_f32_ld = _ld(out_f32)
     if out_bf16 is not None:
-        assert out_bf16.dtype == BF16
+        assert out_bf16.dtype == o16
         d.out_bf16 = out_bf16.data_ptr(); d.out_bf16_ld = _ld(out_bf16)
+    d.in_fp16 = int(in_fp16)
+    d.out_fp16 = int(bool(out_fp16) and (out_bf16 is not None or ln is not None))
     d.store_mode = store_mode
     d.impl = impl
     ln_out = None
     if ln is not None:
         mode, lw, lb, eps, ln_out = ln
-        assert mode in (1, 2) and ln_out.dtype == BF16 and tuple(ln_out.shape) == oshape and lw.dtype == F32
+        assert mode in (1, 2) and ln_out.dtype == o16 and tuple(ln_out.shape) == oshape and lw.dtype == F32
         d.ln_mode = mode; d.ln_eps = eps; d.ln_weight = lw.data_ptr()
         d.ln_bias = lb.data_ptr() if (lb is not None and mode == 1) else None
         d.ln_out_bf16 = ln_out.data_ptr(); d.ln_out_ld = _ld(ln_out)
     taps = k * k
     _call("tdr_conv_gemm", C.byref(d), _stream(),
-          tag=f"k{k}s{stride}_Ci{Ci}_Co{Co}_{OH}x{OW}" + ("_wb" if w_batched else "") + ("_ln" if ln is not None else ""),
+          tag=f"k{k}s{stride}_Ci{Ci}_Co{Co}_{OH}x{OW}" + ("_wb" if w_batched else "") + ("_ln" if ln is not None else "")
+              + ("_h" if in_fp16 else ""),
           nbytes=nB * nH * nW * Ci * 2 + Co * Ci * taps * 2 * (nB if w_batched else 1) + _nb(out_f32, out_bf16, res1, res2, ln_out),
           flops=2 * nB * OH * OW * Co * Ci * taps)
     return out_f32, out_bf16
@@ -274,25 +297,29 @@ def conv_ln_ok(Co):
     return Co <= 96 and Co % 8 == 0 and os.environ.get("TDR_NO_LN_FUSION", "0") in ("", "0")
 
 
-def rownorm(x32, mode, weight=None, bias=None, eps=1e-5, out=None, leaky=False, out_f32=None, want_bf16=True):
-    """fp32 NHWC view -> bf16 NHWC (and/or fp32).  mode 0 cast, 1 WithBias LN, 2 BiasFree LN; leaky: LeakyReLU(0.01)."""
+def rownorm(x32, mode, weight=None, bias=None, eps=1e-5, out=None, leaky=False, out_f32=None, want_bf16=True, dt=BF16):
+    """fp32 NHWC view -> 16-bit NHWC (bf16, or fp16 when dt / out say so) and/or fp32.  mode 0 cast, 1 WithBias LN,
+    2 BiasFree LN; leaky: LeakyReLU(0.01)."""
     assert x32.dtype == F32
     B, H, W, Cc = x32.shape
     if out is None and want_bf16:
-        out = torch.empty((B, H, W, Cc), dtype=BF16, device=x32.device)
-    _call("tdr_rownorm", _p(x32), _ld(x32), B * H * W, Cc, mode, _p(weight), _p(bias), eps, 3 if leaky else 0, _p(out),
+        out = torch.empty((B, H, W, Cc), dtype=dt, device=x32.device)
+    act = (3 if leaky else 0) | (16 if (out is not None and out.dtype == F16) else 0)
+    _call("tdr_rownorm", _p(x32), _ld(x32), B * H * W, Cc, mode, _p(weight), _p(bias), eps, act, _p(out),
           _ld(out) if out is not None else 0, _p(out_f32), _ld(out_f32) if out_f32 is not None else 0, _stream(),
           tag=f"m{mode}_C{Cc}", nbytes=B * H * W * Cc * (4 + (2 if out is not None else 0) + (4 if out_f32 is not None else 0)))
     return out if out is not None else out_f32
 
 
 def dwconv3x3(x, w9, bias=None, gate=0, out=None):
-    assert x.dtype == BF16 and w9.dtype == F32
+    assert x.dtype in (BF16, F16) and w9.dtype == F32
     B, H, W, Cc = x.shape
     co = Cc // 2 if gate else Cc
     if out is None:
-        out = torch.empty((B, H, W, co), dtype=BF16, device=x.device)
-    _call("tdr_dwconv3x3", _p(x), _ld(x), B, H, W, Cc, _p(w9), _p(bias), gate, _p(out), _ld(out), _stream(),
+        out = torch.empty((B, H, W, co), dtype=x.dtype, device=x.device)
+    assert out.dtype == x.dtype
+    _call("tdr_dwconv3x3", _p(x), _ld(x), B, H, W, Cc, _p(w9), _p(bias), gate | (16 if x.dtype == F16 else 0), _p(out),
+          _ld(out), _stream(),
           tag=f"g{gate}_C{Cc}_{H}x{W}", nbytes=B * H * W * (Cc + co) * 2, flops=2 * 9 * B * H * W * Cc)
     return out
 
@@ -306,10 +333,11 @@ def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False, save=None):
     if nbytes == 0:
         raise lib.TdrError(f"MDTA head width unsupported: C={C_} heads={heads}")
     partials = torch.empty(nbytes // 4, dtype=F32, device=qkv.device)
-    _call("tdr_mdta_gram", _p(qkv), _ld(qkv), B, P, C_, heads, _p(partials), _stream(), tag=f"C{C_}_h{heads}_P{P}",
+    h16 = int(qkv.dtype == F16)
+    _call("tdr_mdta_gram", _p(qkv), _ld(qkv), B, P, C_, heads, _p(partials), h16, _stream(), tag=f"C{C_}_h{heads}_P{P}",
           nbytes=B * P * 2 * C_ * 2, flops=3 * 2 * B * P * C_ * (C_ // heads))
     cp = round_up(C_, 8)
-    weff = torch.empty((B, C_, cp), dtype=BF16, device=qkv.device)
+    weff = torch.empty((B, C_, cp), dtype=qkv.dtype, device=qkv.device)
     attn = torch.empty((B, heads, C_ // heads, C_ // heads), dtype=F32, device=qkv.device)
     weff_t = shat = None
     if save is not None:
@@ -317,7 +345,7 @@ def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False, save=None):
         weff_t = torch.zeros((B, C_, cp), dtype=BF16, device=qkv.device)
         shat = torch.empty((B, heads, c * c + 2 * c), dtype=F32, device=qkv.device)
     _call("tdr_mdta_weff", _p(partials), B, P, C_, heads, _p(temperature), _p(w_out), _p(weff), cp, _p(attn),
-          _p(weff_t), _p(shat), _stream(), tag=f"C{C_}_h{heads}", nbytes=nbytes + _nb(weff))
+          _p(weff_t), _p(shat), h16, _stream(), tag=f"C{C_}_h{heads}", nbytes=nbytes + _nb(weff))
     if save is not None:
         save.update(shat=shat, attn=attn, weff=weff, weff_t=weff_t)
     return (weff, attn) if want_attn else weff
@@ -328,8 +356,8 @@ def gate_mul(x16, out=None):
     B, H, W, C2 = x16.shape
     Cc = C2 // 2
     if out is None:
-        out = torch.empty((B, H, W, Cc), dtype=BF16, device=x16.device)
-    _call("tdr_gate_mul", _p(x16), _ld(x16), B * H * W, Cc, _p(out), _ld(out), _stream(), tag=f"C{Cc}",
+        out = torch.empty((B, H, W, Cc), dtype=x16.dtype, device=x16.device)
+    _call("tdr_gate_mul", _p(x16), _ld(x16), B * H * W, Cc, _p(out), _ld(out), int(x16.dtype == F16), _stream(), tag=f"C{Cc}",
           nbytes=B * H * W * Cc * 6)
     return out
 
@@ -342,7 +370,7 @@ def naf_sca_fold(g16, w_sca, b_sca, w3, rowscale=None, save=None):
     nbytes = lib.load().tdr_naf_sca_workspace_bytes(B, H * W, Cc)
     ws = torch.empty(nbytes // 4, dtype=F32, device=g16.device)
     cp = round_up(Cc, 8)
-    weff = torch.empty((B, Co, cp), dtype=BF16, device=g16.device)
+    weff = torch.empty((B, Co, cp), dtype=g16.dtype, device=g16.device)
     mean = s_vec = weff_t = None
     cop = round_up(Co, 8)
     if save is not None:
@@ -351,7 +379,8 @@ def naf_sca_fold(g16, w_sca, b_sca, w3, rowscale=None, save=None):
         weff_t = torch.zeros((B, Cc, cop), dtype=BF16, device=g16.device)
         save.update(mean=mean, s=s_vec, weff_t=weff_t)
     _call("tdr_naf_sca_fold", _p(g16), _ld(g16), B, H * W, Cc, _p(w_sca), _p(b_sca), _p(w3), Co, _p(rowscale), _p(weff),
-          cp, _p(ws), _p(mean), _p(s_vec), _p(weff_t), cop, _stream(), tag=f"C{Cc}", nbytes=B * H * W * Cc * 2)
+          cp, _p(ws), _p(mean), _p(s_vec), _p(weff_t), cop, int(g16.dtype == F16), _stream(), tag=f"C{Cc}",
+          nbytes=B * H * W * Cc * 2)
     return weff
 
 
@@ -386,16 +415,18 @@ def nhwc_to_nchw(x32, out_h, out_w, res=None):
 def copy_rows(src32, dst32=None, dst16=None):
     B, H, W, Cc = src32.shape
     _call("tdr_copy_rows_f32", _p(src32), _ld(src32), B * H * W, Cc, _p(dst32), _ld(dst32) if dst32 is not None else 0,
-          _p(dst16), _ld(dst16) if dst16 is not None else 0, _stream(), tag=f"C{Cc}",
+          _p(dst16), _ld(dst16) if dst16 is not None else 0, int(dst16 is not None and dst16.dtype == F16), _stream(),
+          tag=f"C{Cc}",
           nbytes=B * H * W * Cc * (4 + (4 if dst32 is not None else 0) + (2 if dst16 is not None else 0)))
 
 
 def conv3x3_small_ci(x32, weight, bias, relu=False, out_f32=None, out_bf16=None):
-    """x32: dense fp32 NHWC [B,H,W,Ci<=8]; weight fp32 [Co,Ci,3,3]."""
+    """x32: dense fp32 NHWC [B,H,W,Ci<=8]; weight fp32 [Co,Ci,3,3].  out_bf16 may be an fp16 tensor (MASA encoder)."""
     B, H, W, Ci = x32.shape
     assert x32.is_contiguous()
     Co = weight.shape[0]
-    _call("tdr_conv3x3_small_ci", _p(x32), B, H, W, Ci, _p(weight), _p(bias), Co, int(relu), _p(out_f32),
+    flags = int(relu) | (2 if (out_bf16 is not None and out_bf16.dtype == F16) else 0)
+    _call("tdr_conv3x3_small_ci", _p(x32), B, H, W, Ci, _p(weight), _p(bias), Co, flags, _p(out_f32),
           _ld(out_f32) if out_f32 is not None else 0, _p(out_bf16), _ld(out_bf16) if out_bf16 is not None else 0,
           _stream(), tag=f"Ci{Ci}_Co{Co}", flops=2 * 9 * B * H * W * Ci * Co,
           nbytes=B * H * W * (Ci * 4 + Co * ((4 if out_f32 is not None else 0) + (2 if out_bf16 is not None else 0))))
@@ -413,11 +444,61 @@ def conv3x3_small_co(x16, weight, bias, res32=None):
 
 
 # ---------------------------------------------------------------------------------------------- MASA
-def sqnorm_rows(x16):
-    B, H, W, Cc = x16.shape
-    n2 = torch.empty((B, H, W), dtype=F32, device=x16.device)
-    _call("tdr_sqnorm_rows", _p(x16), _ld(x16), B * H * W, Cc, _p(n2), _stream())
+def sqnorm_rows(x32):
+    assert x32.dtype == F32
+    B, H, W, Cc = x32.shape
+    n2 = torch.empty((B, H, W), dtype=F32, device=x32.device)
+    _call("tdr_sqnorm_rows", _p(x32), _ld(x32), B * H * W, Cc, _p(n2), _stream())
     return n2
+
+
+def masa_split3(x32):
+    """fp32 NHWC [B,H,W,C] -> bf16 [B,H,W,3C] = [hi | lo | hi]: the A operand of the split-bf16 MASA correlations."""
+    assert x32.dtype == F32
+    B, H, W, Cc = x32.shape
+    out = torch.empty((B, H, W, 3 * Cc), dtype=BF16, device=x32.device)
+    _call("tdr_masa_split3", _p(x32), _ld(x32), B * H * W, Cc, _p(out), 3 * Cc, _stream(), tag=f"C{Cc}",
+          nbytes=B * H * W * Cc * 10)
+    return out
+
+
+def cast_rows(x32, want_bf16=True, want_fp16=False, scale16=None, scale_bf16=None, rescale_in=False):
+    """fp32 NHWC view -> (bf16 copy, fp16 copy) in one pass (None for the one not requested).  scale16 / scale_bf16:
+    1-element DEVICE tensors multiplying the fp16 / bf16 copy; rescale_in: also rewrite x32 *= scale16 in place."""
+    assert x32.dtype == F32
+    B, H, W, Cc = x32.shape
+    o16 = torch.empty((B, H, W, Cc), dtype=BF16, device=x32.device) if want_bf16 else None
+    oh = torch.empty((B, H, W, Cc), dtype=F16, device=x32.device) if want_fp16 else None
+    _call("tdr_cast_rows", _p(x32), _ld(x32), B * H * W, Cc, _p(o16), Cc, _p(oh), Cc, _p(scale16), _p(scale_bf16),
+          int(rescale_in), _stream(), tag=f"C{Cc}",
+          nbytes=B * H * W * Cc * (4 + 2 * (int(want_bf16) + int(want_fp16)) + (4 if rescale_in else 0)))
+    return o16, oh
+
+
+def masa_level_scale(x32, state_prev, state_cur):
+    """state_cur (zeroed fp32 [4]) <- {s, 1/s, 1/r, max|x|}: the power-of-two level scale of the MASA encoder."""
+    B, H, W, Cc = x32.shape
+    _call("tdr_masa_level_scale", _p(x32), _ld(x32), B * H * W, Cc, _p(state_prev), _p(state_cur), _stream(),
+          tag=f"C{Cc}", nbytes=B * H * W * Cc * 4)
+
+
+def scale_vec(v, scale, out=None):
+    out = torch.empty_like(v) if out is None else out
+    lib.call("tdr_scale_vec", _p(v), v.numel(), _p(scale), _p(out), _stream())
+    return out
+
+
+def cvt_f16_bf16(xh):
+    B, H, W, Cc = xh.shape
+    out = torch.empty((B, H, W, Cc), dtype=BF16, device=xh.device)
+    _call("tdr_cvt_f16_bf16", _p(xh), _ld(xh), B * H * W, Cc, _p(out), Cc, _stream(), tag=f"C{Cc}",
+          nbytes=B * H * W * Cc * 4)
+    return out
+
+
+def pack_conv_weight_f16(w):
+    """nn.Conv2d weight [Co,Ci,kh,kw] -> fp16 [kh*kw, Co, Ci_p8] (tdr_conv_gemm operand of the MASA encoder)."""
+    return pack_conv(w, dt=F16)[0]
 
 
 def _iarr(vals):
@@ -432,9 +513,10 @@ def masa_ref_invnorm(n2, dils):
 
 
 def masa_coarse_filters(f_lq, k_y, k_x, dils, co_pad):
+    """f_lq fp32 dense NHWC -> bf16 [ndil, B*9, co_pad, 3C] split filters [hi | hi | lo]."""
     B, H, W, Cc = f_lq.shape
-    assert f_lq.is_contiguous()
-    w = torch.empty((len(dils), B * 9, co_pad, Cc), dtype=BF16, device=f_lq.device)
+    assert f_lq.is_contiguous() and f_lq.dtype == F32
+    w = torch.empty((len(dils), B * 9, co_pad, 3 * Cc), dtype=BF16, device=f_lq.device)
     _call("tdr_masa_coarse_filters", _p(f_lq), B, H, W, Cc, k_y, k_x, _iarr(dils), len(dils), co_pad, _p(w), _stream())
     return w
 
@@ -449,8 +531,9 @@ def masa_coarse_argmax(score, nblk, d_y, d_x):
 
 def masa_fine_filters(f_lq, k_y, k_x):
     B, H, W, Cc = f_lq.shape
+    assert f_lq.is_contiguous() and f_lq.dtype == F32
     nwin = B * (H // k_y) * (W // k_x)
-    w = torch.empty((nwin * 9, k_y * k_x, Cc), dtype=BF16, device=f_lq.device)
+    w = torch.empty((nwin * 9, k_y * k_x, 3 * Cc), dtype=BF16, device=f_lq.device)
     _call("tdr_masa_fine_filters", _p(f_lq), B, H, W, Cc, k_y, k_x, _p(w), _stream())
     return w
 
@@ -555,10 +638,13 @@ def workspace(nbytes, dev):
 
 
 def wgrad(dy16, x16, out, *, Co=None, Ci=None, k=1, stride=1, pad=0, dil=1, per_sample=False, strides=None,
-          co_map=None, ci_map=None, accumulate=True, scale=1.0):
+          co_map=None, ci_map=None, accumulate=True, scale=1.0, scale_ptr=None):
     """Weight gradient of a dense conv.  dy16 bf16 NHWC [B,OH,OW,>=Co], x16 bf16 NHWC [B,H,W,>=Ci]; ``out`` fp32 in
     the PARAMETER layout [Co, Ci, k, k] (default strides) or any layout given by strides=(s_b, s_co, s_ci, s_tap)."""
-    assert dy16.dtype == BF16 and x16.dtype == BF16 and out.dtype == F32
+    assert dy16.dtype == BF16 and out.dtype == F32
+    if x16.dtype == F16:            # MASA encoder tape: the GEMM takes bf16 pairs only (kind::f16 rejects mixed operands)
+        x16 = cvt_f16_bf16(x16)
+    assert x16.dtype == BF16
     B, H, W, Cx = x16.shape
     Co = dy16.shape[3] if Co is None else Co
     Ci = Cx if Ci is None else Ci
@@ -579,6 +665,7 @@ def wgrad(dy16, x16, out, *, Co=None, Ci=None, k=1, stride=1, pad=0, dil=1, per_
     d.co_map = co_map.data_ptr() if co_map is not None else None
     d.ci_map = ci_map.data_ptr() if ci_map is not None else None
     d.accumulate = int(accumulate); d.scale = scale
+    d.scale_ptr = scale_ptr.data_ptr() if scale_ptr is not None else None
     nbytes = lib.load().tdr_wgrad_workspace_bytes(C.byref(d))
     if nbytes == 0:
         raise lib.TdrError(f"tdr_wgrad: unsupported shape Co={Co} Ci={Ci} k={k}")
