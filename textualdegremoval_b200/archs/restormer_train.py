@@ -470,6 +470,11 @@ class NetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, n_inputs, *args):
         inputs, params = args[:n_inputs], args[n_inputs:]
+        if any(t.requires_grad for t in inputs):
+            # the explicit backward schedule produces parameter gradients only (the reference's restoration training
+            # never differentiates w.r.t. lq / ref); refuse instead of silently returning no input gradient
+            raise ops.lib.TdrError("textualdegremoval_b200: gradients w.r.t. the input images are not implemented "
+                                   "(inputs with requires_grad=True); detach them or use torch.no_grad()")
         out, state = net._forward_train(*[t.detach() for t in inputs])
         ctx.net, ctx.state, ctx.params, ctx.n_inputs = net, state, params, n_inputs
         return out

@@ -40,6 +40,7 @@ class FlatGroup:
         self.params = list(params)
         self.lr = lr
         self.tag = "normal"
+        self.steps = 0                                   # updates applied to THIS group (AdamW bias correction)
         offs, n = [], 0
         for p in self.params:
             offs.append(n)
@@ -81,7 +82,11 @@ class DDPStep:
     """all-reduce -> clip -> AdamW -> (EMA).  ``process_group=None`` and world size 1 make it a single-GPU step."""
 
     def __init__(self, named_params, lr, ref_lr, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, max_grad_norm=0.01,
-                 use_grad_clip=True, bucket_bytes=25 * 1024 * 1024, ema_decay=0.0, process_group=None):
+                 use_grad_clip=True, bucket_bytes=25 * 1024 * 1024, ema_decay=0.0, process_group=None, buffers=()):
+        """buffers: the module's buffers (``net_g.buffers()``); with world > 1 they and every parameter are broadcast
+        from rank 0 at construction -- what ``DistributedDataParallel`` does when the reference wraps ``net_g``
+        (models/base_model.py:76-82); the reference seeds each rank with ``manual_seed + rank``
+        (main_train_restoration_with_ref_input.py:55), so without it every rank would train different weights."""
         self.groups = split_param_groups(list(named_params), lr, ref_lr)
         self.weight_decay, self.betas, self.eps = weight_decay, betas, eps
         self.max_grad_norm, self.use_grad_clip = max_grad_norm, use_grad_clip
@@ -90,7 +95,15 @@ class DDPStep:
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.step_count = 0
         self.ema_decay = ema_decay
+        if self.world > 1:
+            for g in self.groups:
+                dist.broadcast(g.flat, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                               group=process_group)
+            for b in buffers:
+                dist.broadcast(b, src=dist.get_global_rank(process_group, 0) if process_group is not None else 0,
+                               group=process_group)
         self.ema = [g.flat.clone() for g in self.groups] if ema_decay > 0 else None
+        self._loss = None
         self._loss_work = None
         dev = self.groups[0].flat.device
         self._on_cuda = dev.type == "cuda"
@@ -143,9 +156,11 @@ class DDPStep:
         for gi, g in enumerate(self.groups):
             if gi in frozen:
                 continue
+            g.steps += 1          # per-group step, as torch.optim.AdamW's per-parameter state['step']: a group that was
+            #                       frozen for fix_iterations starts its bias correction at 1 when it is first updated
             lib.call("tdr_adamw_step", C.c_void_p(g.flat.data_ptr()), C.c_void_p(g.grad.data_ptr()),
                      C.c_void_p(g.m.data_ptr()), C.c_void_p(g.v.data_ptr()), g.n, g.lr, self.betas[0], self.betas[1],
-                     self.eps, self.weight_decay, self.step_count, scale, clip_ptr, _stream())
+                     self.eps, self.weight_decay, g.steps, scale, clip_ptr, _stream())
         if self.ema is not None:
             for g, e in zip(self.groups, self.ema):
                 lib.call("tdr_ema_update", C.c_void_p(e.data_ptr()), C.c_void_p(g.flat.data_ptr()), g.n, self.ema_decay,
@@ -166,13 +181,78 @@ class DDPStep:
         self._loss_work = dist.reduce(self._loss, dst=0, group=self.pg, async_op=True) if self.world > 1 else None
 
     def read_loss(self):
-        """Host read (synchronises): call every print_freq iterations, not every step."""
+        """Host read (synchronises): call every print_freq iterations, not every step.  The rank-averaged value is
+        meaningful on rank 0 only (``dist.reduce`` to dst 0, as base_model.py:369); other ranks get local / world."""
+        if self._loss is None:
+            raise lib.TdrError("DDPStep.read_loss: no step has been taken yet")
         if self._loss_work is not None:
             self._loss_work.wait()
         return float(self._loss.item()) / self.world
 
+    # ---- checkpointing (models/base_model.py:311-351 save_training_state / resume_training) -----------------------------
+    def state_dict(self):
+        """Optimizer state of the flat groups: Adam moments, per-group step counts, the EMA copy."""
+        return dict(step_count=self.step_count,
+                    groups=[dict(tag=g.tag, lr=g.lr, steps=g.steps, m=g.m.detach().cpu().clone(), v=g.v.detach().cpu().clone())
+                            for g in self.groups],
+                    ema=None if self.ema is None else [e.detach().cpu().clone() for e in self.ema])
+
+    def load_state_dict(self, sd):
+        if len(sd["groups"]) != len(self.groups):
+            raise lib.TdrError("DDPStep.load_state_dict: group count mismatch")
+        self.step_count = int(sd["step_count"])
+        for g, st in zip(self.groups, sd["groups"]):
+            if st["m"].numel() != g.m.numel() or st["tag"] != g.tag:
+                raise lib.TdrError(f"DDPStep.load_state_dict: group '{g.tag}' does not match the checkpoint")
+            g.lr, g.steps = float(st["lr"]), int(st["steps"])
+            g.m.copy_(st["m"])
+            g.v.copy_(st["v"])
+        if self.ema is not None and sd.get("ema") is not None:
+            for e, t in zip(self.ema, sd["ema"]):
+                e.copy_(t)
+
     def grad_norm(self):
         return float(self._clip[1].item())
+
+
+class FlatAdamW(torch.optim.Optimizer):
+    """``torch.optim.Optimizer`` face of a ``DDPStep`` so that the reference's model wrapper keeps working unchanged: it is
+    what goes into ``self.optimizers`` (image_restoration_ref_model.py:170-181), so ``setup_schedulers`` /
+    ``update_learning_rate`` (base_model.py:101-205: ``CosineAnnealingRestartCyclicLR`` + warm-up write
+    ``param_groups[i]['lr']``) and ``save_training_state`` / ``resume_training`` (:311-351) act on the fused step.
+    ``step()`` = gradient all-reduce + clip + AdamW (+ EMA) on the flat buffers, with the lr of each ``param_groups``
+    entry; ``state_dict()`` carries the Adam moments, step counts and the EMA copy."""
+
+    def __init__(self, engine: "DDPStep"):
+        self.engine = engine
+        groups = [dict(params=g.params, lr=g.lr, initial_lr=g.lr, betas=engine.betas, eps=engine.eps,
+                       weight_decay=engine.weight_decay, tag=g.tag) for g in engine.groups]
+        super().__init__(groups, dict(lr=engine.groups[0].lr, betas=engine.betas, eps=engine.eps,
+                                      weight_decay=engine.weight_decay))
+
+    def sync_lr(self):
+        for g, pg in zip(self.engine.groups, self.param_groups):
+            g.lr = float(pg["lr"])
+
+    @torch.no_grad()
+    def step(self, closure=None, frozen=()):
+        self.sync_lr()
+        self.engine.step(self.engine.all_reduce_gradients(), frozen=frozen)
+
+    def zero_grad(self, set_to_none=False):
+        self.engine.zero_grad()
+
+    def state_dict(self):
+        return dict(param_groups=[{k: v for k, v in pg.items() if k != "params"} for pg in self.param_groups],
+                    flat=self.engine.state_dict())
+
+    def load_state_dict(self, sd):
+        for pg, st in zip(self.param_groups, sd["param_groups"]):
+            pg.update({k: v for k, v in st.items() if k != "params"})
+        self.engine.load_state_dict(sd["flat"])
+        for pg, g in zip(self.param_groups, self.engine.groups):
+            pg["lr"] = g.lr if "lr" not in pg else pg["lr"]
+        self.sync_lr()
 
 
 class RefGuidedTrainer:
@@ -204,7 +284,12 @@ class RefGuidedTrainer:
         self.engine = DDPStep(net_g.named_parameters(), lr=og.get("lr", 3e-4), ref_lr=og.get("ref_lr", og.get("lr", 3e-4)),
                               weight_decay=og.get("weight_decay", 1e-4), betas=tuple(og.get("betas", (0.9, 0.999))),
                               use_grad_clip=bool(train_opt.get("use_grad_clip", True)),
-                              ema_decay=float(train_opt.get("ema_decay", 0.0)), process_group=process_group)
+                              ema_decay=float(train_opt.get("ema_decay", 0.0)), process_group=process_group,
+                              buffers=list(net_g.buffers()))
+        # the torch.optim.Optimizer face: append it to the reference wrapper's ``self.optimizers`` so
+        # that its LR schedulers and training-state checkpoints drive / persist this step
+        self.optimizer_g = FlatAdamW(self.engine)
+        self.optimizers = [self.optimizer_g]
         net_g.grad_direct = True
         self.net_ext = net_ext
         self.fix_iterations = train_opt.get("fix_iterations")
@@ -231,13 +316,23 @@ class RefGuidedTrainer:
             from .archs.vit_b200 import select_reference_crop
             with torch.no_grad():
                 self.ref_in, _, _ = select_reference_crop(self.net_ext, self.lq, self.ref)
+        # fix_iterations: the ``masa`` group takes no update (and no part in the clipped norm) for the first iterations.
+        # The reference intends this (image_restoration_ref_model.py:203-212) but never triggers it: its option files spell
+        # the key ``param_fix_iterations``, so with the shipped options every parameter always trains --
+        # the same happens here (the key is absent => frozen = ()).  When set, the group's AdamW state starts at its first
+        # real update (per-group step counter), as torch.optim.AdamW would for parameters whose grad was None until then.
         frozen = self._ref_group if (self.fix_iterations is not None and current_iter < self.fix_iterations) else ()
+        if self.gt is None:
+            raise lib.TdrError("RefGuidedTrainer.optimize_parameters: feed_train_data() got no 'gt'")
+        self.optimizer_g.sync_lr()
         self.engine.zero_grad()
         inputs = (self.lq,) if self.ref_in is None else (self.lq, self.ref_in)
         out, state = net._forward_train(*inputs)
         self.output = out
         dout = torch.empty_like(out)
         gt = self.gt.contiguous().float()
+        if tuple(gt.shape) != tuple(out.shape):
+            raise lib.TdrError(f"RefGuidedTrainer: gt shape {tuple(gt.shape)} != network output {tuple(out.shape)}")
         lib.call("tdr_l1_loss_grad", C.c_void_p(out.data_ptr()), C.c_void_p(gt.data_ptr()), out.numel(), self.loss_weight,
                  C.c_void_p(dout.data_ptr()), C.c_void_p(self._loss.data_ptr()), C.c_void_p(self._partial.data_ptr()),
                  _stream())
