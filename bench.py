@@ -1,21 +1,31 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark: restored img/s of the reference-guided Restormer (option 003) at 512x512.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config 2|3|4|5]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one forward restoration pass of RestormerRefFusion (option 003: dim 48, blocks [4,6,6,8], 2 fusion blocks
-per level, nf 48) over a batch of 4 synthetic degraded 512x512 tiles + 4 reference tiles per GPU (BASELINE.json
-configs[2], the configuration the metric is quoted on).  Images are independent units: ranks are replicas over disjoint
-batches, no data-path collective (scaling "weak").
+Default workload = BASELINE.json configs[2] (the configuration the metric is quoted on): one "step" = one forward
+restoration pass of RestormerRefFusion (option 003: dim 48, blocks [4,6,6,8], 2 fusion blocks per level, nf 48) over a
+batch of 4 synthetic degraded 512x512 tiles + 4 reference tiles per GPU.  ``--config`` selects the other BASELINE
+configurations (same JSON line: roofline, cpu_baseline, e2e, clocks):
+    2  Restormer colour denoising (option 017 network), 256x256, batch 8, no guidance path
+    3  reference-guided Restormer (option 003), 512x512, batch 4 / GPU                                   [default]
+    4  CLIP ViT-H/14 + I2T Mapper + TR CleanMapper forward (embedding path), 224x224 crops, batch 32
+    5  reference-guided NAFNet (option 002 network), 512x512, batch 4 / GPU
+Images are independent units: ranks are replicas over disjoint batches, no data-path collective (scaling "weak").
 
-  value  : images/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks)
-  e2e    : images/s through the module's public call with HOST (pinned) inputs and a pinned host output,
-           H2D and D2H copies inside the timed region
+  value   : images/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks)
+  e2e     : images/s through the module's public call with HOST (pinned) inputs and a pinned host output,
+            H2D and D2H copies inside the timed region
   roofline: for the kernel family with the largest share of the step (per-launch CUDA-event timing in a separate,
-           untimed profiling pass): achieved = algorithmic bytes (or flops) / measured time vs MEASURED_PEAKS.json
-  cpu_baseline / --impl reference: the CPU oracle (fp32 restatement of the reference modules, pinned to them by
-           tests/golden) on the host cores -- /root/reference itself does not exist on the GPU box.
+            untimed profiling pass): achieved = algorithmic bytes (or flops) / measured time vs MEASURED_PEAKS.json
+  train_step (configs 2, 3, 5): the full DDP training step, with its own roofline block
+  cpu_baseline / --impl reference: the reference's OWN modules on the host cores (vendored byte-for-byte into
+            oracle/_ref by the recipe oracle/build_ref.py: kind "reference"); the oracle port (kind "port") only when
+            that tree is absent.
+dtype: the inference forward computes on IEEE fp16 tensor-core operands (fp32 accumulation / residual stream / norms):
+bf16's 8 significand bits miss the 0.01 dB parity bar at full depth (0.032 dB), fp16's 11 meet it (0.0007 dB) at the same
+tcgen05 rate; the training step keeps bf16 operands and gradients.
 """
 import argparse
 import json
@@ -34,8 +44,27 @@ OPTION_003 = dict(inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8
                   dual_pixel_task=False, nf=48, ext_n_blocks=[4, 4, 4, 4], reffusion_n_blocks=[2, 2, 2, 2],
                   reffusion_n_blocks_middle=1, scale=1, num_nbr=1, psize=3, lr_block_size=8, ref_down_block_size=1.5,
                   dilations=[1, 2, 3])
+OPTION_017 = dict(inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4,
+                  heads=[1, 2, 4, 8], ffn_expansion_factor=2.66, bias=False, LayerNorm_type="BiasFree",
+                  dual_pixel_task=False)
+OPTION_002 = dict(img_channel=3, width=64, middle_blk_num=1, enc_blk_nums=[1, 1, 1, 28], dec_blk_nums=[1, 1, 1, 1],
+                  nf=64, ext_n_blocks=[4, 4, 4, 4], reffusion_n_blocks=[2, 2, 2, 2, 2], reffusion_n_blocks_middle=1, scale=1,
+                  num_nbr=1, psize=3, lr_block_size=8, ref_down_block_size=1.5, dilations=[1, 2, 3])
 METRIC = "restored img/s @512x512 bf16 guided-Restormer"
 FWD_GFLOP_PER_IMG = 2492.2          # SURVEY.md 8(a) a7, torch flop counter on the reference module
+DTYPE = "fp16"                      # tensor-core operand format of the measured forward (see the module docstring)
+
+# BASELINE.json configs; gflop = forward GFLOP per image from the reference modules' flop count
+CONFIGS = {
+    2: dict(kind="restormer", type="Restormer", opt=OPTION_017, batch=8, size=256, gflop=309.76, guided=False,
+            metric="restored img/s @256x256 bf16 Restormer", what="Restormer option-017 network (BiasFree) forward"),
+    3: dict(kind="guided_restormer", type="RestormerRefFusion", opt=OPTION_003, batch=4, size=512, gflop=FWD_GFLOP_PER_IMG,
+            guided=True, metric=METRIC, what="RestormerRefFusion option-003 forward (restoration)"),
+    4: dict(kind="embed", batch=32, size=224, gflop=323.8 + 64.2, guided=False,
+            metric="embedded img/s CLIP ViT-H/14 + I2T + TR mappers", what="CLIP ViT-H/14 + Mapper + CleanMapper forward"),
+    5: dict(kind="guided_nafnet", type="NAFNetRefFusion", opt=OPTION_002, batch=4, size=512, gflop=2653.9, guided=True,
+            metric="restored img/s @512x512 bf16 guided-NAFNet", what="NAFNetRefFusion option-002 network forward"),
+}
 
 
 def synth_inputs(batch, size, seed):
@@ -57,6 +86,20 @@ def peaks():
         return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
     except Exception:  # noqa: BLE001
         return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def randomise_gates(net):
+    """Un-zero the zero-initialised gates (alpha / beta / gamma) so that the guidance path does real work."""
+    import torch
+    with torch.no_grad():
+        for n_, p_ in net.named_parameters():
+            leaf = n_.rsplit(".", 1)[-1]
+            if leaf == "alpha":
+                p_.uniform_(0.2, 1.0)
+            elif leaf in ("beta", "gamma") and p_.dim() == 4:
+                p_.uniform_(0.1, 1.0)
+            elif leaf == "temperature":
+                p_.uniform_(0.5, 1.5)
 
 
 class ClockSampler:
@@ -103,49 +146,81 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(size, max_seconds, steps=None, warmup=0):
-    """img/s of the CPU oracle (fp32 port of the reference modules) on all host cores, batch 1."""
+def cpu_rate(cfg_id, size, max_seconds, steps=None, warmup=0):
+    """img/s of the reference's CPU path for one BASELINE config on all host cores, batch 1: the reference's own modules
+    (oracle/_ref or /root/reference through oracle.ref_loader: kind "reference"), else the oracle port (kind "port")."""
     import torch
-    from oracle import restormer as O, weights as W
-    from textualdegremoval_b200.archs.restormer_b200_arch import RestormerRefFusion
+    from oracle import ref_loader as R, weights as W
+    cfg = CONFIGS[cfg_id]
     ncores = os.cpu_count() or 1
     torch.set_num_threads(ncores)
-    shapes = {k: v.shape for k, v in RestormerRefFusion(**OPTION_003).state_dict().items()}
-    sd = W.seeded_state_dict(shapes, 0)
+    kind = "reference" if R.available() else "port"
     lq, ref, _ = synth_inputs(1, size, 100)
+    if cfg["kind"] == "embed":
+        import transformers
+        from oracle.make_golden_fullsize import CLIP_VITH
+        clip = transformers.CLIPVisionModel(transformers.CLIPVisionConfig(**CLIP_VITH)).eval()
+        if kind == "reference":
+            from oracle.make_golden import load_mapper_classes
+            Mapper, CleanMapper = load_mapper_classes()
+            m, cm = Mapper(1280, 1024, 20).eval(), CleanMapper(1024, 1024, 20).eval()
+            fn = lambda: cm(m([clip(lq, output_hidden_states=True)[0]]))
+        else:
+            from oracle import vit as OV
+            from textualdegremoval_b200.archs import vit_b200 as VB
+            sm = W.seeded_state_dict({k: v.shape for k, v in VB.Mapper(1280, 1024, 20).state_dict().items()}, 0)
+            sc = W.seeded_state_dict({k: v.shape for k, v in VB.CleanMapper(1024, 1024, 20).state_dict().items()}, 1)
+            fn = lambda: OV.clean_mapper_forward(sc, OV.mapper_forward(sm, clip(lq, output_hidden_states=True)[0], 20), 20)
+        what = "transformers CLIPVisionModel ViT-H/14 + " + ("the reference's Mapper / CleanMapper" if kind == "reference"
+                                                             else "oracle mappers")
+    elif kind == "reference":
+        net = dict(restormer=R.restormer, guided_restormer=R.restormer_ref_fusion, guided_nafnet=R.nafnet_ref_fusion)[
+            cfg["kind"]](**cfg["opt"]).eval()
+        randomise_gates(net)
+        fn = (lambda: net(lq, ref)) if cfg["guided"] else (lambda: net(lq))
+        what = f"the reference's own {cfg['type']} module (unmodified sources, fp32, stock PyTorch CPU ops)"
+    else:
+        from oracle import nafnet as ON, restormer as O
+        from textualdegremoval_b200 import define_network
+        shapes = {k: v.shape for k, v in define_network(dict(type=cfg["type"], **cfg["opt"])).state_dict().items()}
+        sd = W.seeded_state_dict(shapes, 0)
+        fn = dict(restormer=lambda: O.restormer_forward(sd, lq), guided_restormer=lambda: O.restormer_ref_fusion_forward(sd, lq, ref),
+                  guided_nafnet=lambda: ON.nafnet_ref_fusion_forward(sd, lq, ref))[cfg["kind"]]
+        what = "fp32 CPU oracle port of the reference modules"
     times = []
     t_begin = time.perf_counter()
     with torch.no_grad():
         for _ in range(warmup):
-            O.restormer_ref_fusion_forward(sd, lq, ref)
+            fn()
             if time.perf_counter() - t_begin > max_seconds / 2:
                 break
         n = 0
         while True:
             t0 = time.perf_counter()
-            O.restormer_ref_fusion_forward(sd, lq, ref)
+            fn()
             times.append(time.perf_counter() - t0)
             n += 1
             if (steps is not None and n >= steps) or time.perf_counter() - t_begin > max_seconds:
                 break
     mean = sum(times) / len(times)
-    return dict(value=1.0 / mean, unit="img/s", cores=ncores, kind="port", steps=len(times), sec_per_img=mean,
-                sample=f"{len(times)} x 1 image {size}x{size} (lq+ref), fp32 CPU oracle of the reference modules, "
-                       f"torch {torch.__version__} {ncores} threads")
+    return dict(value=1.0 / mean, unit="img/s", cores=ncores, kind=kind, steps=len(times), sec_per_img=mean,
+                sample=f"{len(times)} x 1 image {size}x{size}" + (" (lq+ref)" if cfg["guided"] else "") +
+                       f", {what}, torch {torch.__version__} {ncores} threads")
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores (oracle port; the reference
-    tree is not present on the GPU box).  Rank 0 only."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  Rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
-    r = cpu_oracle_rate(args.size, max_seconds=180.0, steps=args.steps, warmup=min(args.warmup, 1))
+    cfg = CONFIGS[args.config]
+    size = args.size or cfg["size"]
+    r = cpu_rate(args.config, size, max_seconds=180.0, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "img/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": cfg["metric"], "value": r["value"], "unit": "img/s", "n_gpus": args.gpus,
         "steps": r["steps"], "warmup": min(args.warmup, 1), "ms_per_step": 1000.0 * r["sec_per_img"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"RestormerRefFusion option-003 forward, {args.size}x{args.size}, batch 1/step on CPU "
-                               "(bounded sample of the batch-4 GPU step; steps capped at 180 s)"},
+        "config": {"workload": f"{cfg['what']}, {size}x{size}, batch 1/step on CPU (bounded sample of the batch-"
+                               f"{args.batch or cfg['batch']} GPU step; steps capped at 180 s)"},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": r["value"], "unit": "img/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -180,6 +255,65 @@ def run_b200(args):
         return _run_b200(args, out)
 
 
+def _families(prof):
+    fam = {}
+    for name, tag, nb, fl, t in prof:
+        f = fam.setdefault(name, dict(ms=0.0, bytes=0, flops=0, n=0))
+        f["ms"] += t; f["bytes"] += nb; f["flops"] += fl; f["n"] += 1
+    return fam
+
+
+def _dump_prof(prof, path, pk):
+    tags = {}
+    for name, tag, nb, fl, t in prof:
+        d_ = tags.setdefault(f"{name}:{tag}", dict(ms=0.0, n=0, bytes=0, flops=0))
+        d_["ms"] += t; d_["n"] += 1; d_["bytes"] += nb; d_["flops"] += fl
+    rows = sorted(tags.items(), key=lambda kv: -kv[1]["ms"])
+    with open(path, "w") as fh:
+        json.dump([dict(key=k, ms=round(v["ms"], 4), n=v["n"], us_per=round(1e3 * v["ms"] / v["n"], 1),
+                        GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                        TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1),
+                        hbm_frac=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"], 3)) for k, v in rows], fh, indent=0)
+
+
+def _roofline(prof, pk, traffic_key=None):
+    """Roofline block of the kernel family with the largest share of the profiled step: achieved = algorithmic bytes (or
+    flops) of its launches / their summed CUDA-event time, against the measured peaks."""
+    fam = _families(prof)
+    total = sum(f["ms"] for f in fam.values())
+    top = max(fam, key=lambda k: fam[k]["ms"])
+    ft = fam[top]
+    hbm_gbs = ft["bytes"] / (ft["ms"] * 1e-3) / 1e9
+    tflops = ft["flops"] / (ft["ms"] * 1e-3) / 1e12
+    hbm_frac, tc_frac = hbm_gbs / pk["hbm"], tflops / pk["tf_sust"]
+    if hbm_frac >= tc_frac:
+        roof = dict(bound="hbm", achieved=hbm_gbs, peak=pk["hbm"], unit="GB/s", frac=hbm_frac)
+    else:
+        roof = dict(bound="tensor", achieved=tflops, peak=pk["tf_sust"], unit="TFLOP/s", frac=tc_frac)
+    # measured DRAM traffic per launch of that kernel family: one ncu pass over a steady-state step of this same
+    # workload (dram__bytes_read.sum + dram__bytes_write.sum), committed under profiles/ -- not re-measured here
+    traffic, traffic_src = None, None
+    if traffic_key is not None:
+        try:
+            with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as fh:
+                tj = json.load(fh)
+            if tj.get("workload") == traffic_key and top in tj["families"]:
+                traffic = tj["families"][top]["dram_bytes_per_launch"]
+                traffic_src = tj["source"]
+        except Exception:  # noqa: BLE001
+            pass
+    roof.update(kernel=top, launches_per_step=ft["n"], avg_launch_ms=ft["ms"] / ft["n"], share_of_step=ft["ms"] / total,
+                traffic=traffic, traffic_unit="bytes/launch (DRAM read+write, ncu)", traffic_source=traffic_src,
+                algorithmic_bytes_per_launch=ft["bytes"] / ft["n"], peak_source=pk["src"],
+                whole_step=dict(algorithmic_gb=round(sum(f["bytes"] for f in fam.values()) / 1e9, 2),
+                                tflop=round(sum(f["flops"] for f in fam.values()) / 1e12, 2), kernel_ms=round(total, 3),
+                                hbm_frac=round(sum(f["bytes"] for f in fam.values()) / (total * 1e-3) / 1e9 / pk["hbm"], 3)),
+                families={k: dict(ms=round(v["ms"], 3), n=v["n"], GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
+                                  TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1),
+                                  hbm_frac=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"], 3)) for k, v in fam.items()})
+    return roof
+
+
 def _run_b200(args, out):
     import torch
     import torch.distributed as dist
@@ -194,36 +328,56 @@ def _run_b200(args, out):
         dist.init_process_group("nccl", device_id=dev)
     lib.check(lib.load().tdr_check_device(), "tdr_check_device")
 
-    B, S = args.batch, args.size
+    cfg = CONFIGS[args.config]
+    B, S = args.batch or cfg["batch"], args.size or cfg["size"]
     torch.manual_seed(0)                                   # random-init weights of the named architecture
-    net = define_network(dict(type="RestormerRefFusion", **OPTION_003))
-    with torch.no_grad():                                  # un-zero the gates so the guidance path does real work
-        for n_, p_ in net.named_parameters():
-            if n_.endswith("alpha"):
-                p_.uniform_(0.2, 1.0)
-            elif n_.endswith("temperature"):
-                p_.uniform_(0.5, 1.5)
-    net = net.to(dev).eval()
-    lq_h, ref_h, _ = synth_inputs(B, S, 100 + rank)
-    lq_h, ref_h = lq_h.pin_memory(), ref_h.pin_memory()
-    out_h = torch.empty(B, 3, S, S).pin_memory()
-    lq_d, ref_d = lq_h.to(dev), ref_h.to(dev)
+    gt_h = None
+    if cfg["kind"] == "embed":
+        from textualdegremoval_b200.archs import vit_b200 as VB
+        clip = VB.CLIPVisionTower().to(dev).eval()
+        mapper, clean = VB.Mapper(1280, 1024, 20).to(dev).eval(), VB.CleanMapper(1024, 1024, 20).to(dev).eval()
+        net = None
+        g = torch.Generator().manual_seed(100 + rank)
+        x_h = torch.randn(B, 3, S, S, generator=g).pin_memory()       # CLIP-normalised crops (zero mean, unit variance)
+        out_h = torch.empty(B, 20, 1024).pin_memory()
+        x_d = x_h.to(dev)
+        fwd = lambda x: clean(mapper([clip(x, output_hidden_states=True)[0]]))
+        step_resident = lambda: fwd(x_d)
+        h2d, d2h = x_h.numel() * 4, out_h.numel() * 4
+
+        def step_e2e():
+            y = fwd(x_h.to(dev, non_blocking=True))
+            out_h.copy_(y, non_blocking=True)
+            return y
+    else:
+        net = define_network(dict(type=cfg["type"], **cfg["opt"]))
+        randomise_gates(net)
+        net = net.to(dev).eval()
+        lq_h, ref_h, gt_h = synth_inputs(B, S, 100 + rank)
+        if not cfg["guided"]:                              # config 2: Gaussian colour denoising, sigma = 25
+            lq_h = gt_h + (25.0 / 255.0) * torch.randn(gt_h.shape, generator=torch.Generator().manual_seed(rank))
+        lq_h, ref_h = lq_h.contiguous().pin_memory(), ref_h.pin_memory()
+        out_h = torch.empty(B, 3, S, S).pin_memory()
+        lq_d, ref_d = lq_h.to(dev), ref_h.to(dev)
+        if cfg["guided"]:
+            step_resident = lambda: net(lq_d, ref_d)
+            h2d = 2 * B * 3 * S * S * 4
+        else:
+            step_resident = lambda: net(lq_d)
+            h2d = B * 3 * S * S * 4
+        d2h = B * 3 * S * S * 4
+
+        def step_e2e():
+            a = lq_h.to(dev, non_blocking=True)
+            y = net(a, ref_h.to(dev, non_blocking=True)) if cfg["guided"] else net(a)
+            out_h.copy_(y, non_blocking=True)
+            return y
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-
-    def step_resident():
-        return net(lq_d, ref_d)
-
-    def step_e2e():
-        a = lq_h.to(dev, non_blocking=True)
-        b = ref_h.to(dev, non_blocking=True)
-        y = net(a, b)
-        out_h.copy_(y, non_blocking=True)
-        return y
 
     def timed(fn, steps):
         evs = []
@@ -275,7 +429,8 @@ def _run_b200(args, out):
 
     # ---- training step: forward + L1 + backward + gradient all-reduce + clip + AdamW, same batch ----
     train = None
-    if args.train_steps > 0:
+    tprof = None
+    if args.train_steps > 0 and net is not None:
         from textualdegremoval_b200.ddp import RefGuidedTrainer
         torch.cuda.empty_cache()
         torch.cuda.reset_peak_memory_stats()
@@ -284,9 +439,8 @@ def _run_b200(args, out):
                                                      betas=[0.9, 0.999]), use_grad_clip=True,
                                         pixel_opt=dict(type="L1Loss", loss_weight=1.0)),
                               process_group=None)
-        _, _, gt_h = synth_inputs(B, S, 100 + rank)
-        tr.feed_train_data(dict(lq=lq_h, gt=gt_h, ref_in=ref_h))
-        for _ in range(2):
+        tr.feed_train_data(dict(lq=lq_h, gt=gt_h, ref_in=ref_h) if cfg["guided"] else dict(lq=lq_h, gt=gt_h))
+        for _ in range(3):
             tr.optimize_parameters()
         barrier()
         l0 = ops.PROF.launches
@@ -294,8 +448,7 @@ def _run_b200(args, out):
         train_launches = ops.PROF.launches - l0
         barrier()
         loss_val = tr.current_loss()
-        tprof = None
-        if rank == 0 and args.dump_prof_train:
+        if rank == 0:
             ops.PROF.start()
             tr.optimize_parameters()
             tprof = ops.PROF.stop()
@@ -304,18 +457,19 @@ def _run_b200(args, out):
         # the reference's step also selects the reference crop with a frozen DINOv2 ViT-B/14 every iteration
         # (image_restoration_ref_model.py:215-247); with a 512x512 reference there is one candidate (N = 1), the two
         # 518x518 ViT forwards per sample are executed all the same
-        try:
-            from textualdegremoval_b200.archs.vit_b200 import vit_base
-            ext = vit_base(img_size=518, patch_size=14, init_values=1.0, ffn_layer="mlp", block_chunks=0).to(dev).eval()
-            tr.net_ext = ext
-            tr.feed_train_data(dict(lq=lq_h, gt=gt_h, ref=ref_h))
-            tr.optimize_parameters()
-            barrier()
-            train["ms_dino"] = timed(lambda: tr.optimize_parameters(), 2) / 2
-            barrier()
-        except Exception as e:  # noqa: BLE001
-            train["ms_dino"] = None
-            train["dino_error"] = f"{type(e).__name__}: {e}"[:200]
+        if cfg["guided"] and args.config == 3:
+            try:
+                from textualdegremoval_b200.archs.vit_b200 import vit_base
+                ext = vit_base(img_size=518, patch_size=14, init_values=1.0, ffn_layer="mlp", block_chunks=0).to(dev).eval()
+                tr.net_ext = ext
+                tr.feed_train_data(dict(lq=lq_h, gt=gt_h, ref=ref_h))
+                tr.optimize_parameters()
+                barrier()
+                train["ms_dino"] = timed(lambda: tr.optimize_parameters(), 2) / 2
+                barrier()
+            except Exception as e:  # noqa: BLE001
+                train["ms_dino"] = None
+                train["dino_error"] = f"{type(e).__name__}: {e}"[:200]
 
     if world > 1:
         t = torch.tensor([ms, ms_e2e, train["ms"] if train else 0.0], device=dev, dtype=torch.float64)
@@ -329,63 +483,26 @@ def _run_b200(args, out):
         return 0
 
     pk = peaks()
-    fam = {}
-    for name, tag, nb, fl, t in prof:
-        f = fam.setdefault(name, dict(ms=0.0, bytes=0, flops=0, n=0))
-        f["ms"] += t; f["bytes"] += nb; f["flops"] += fl; f["n"] += 1
-    total_prof = sum(f["ms"] for f in fam.values())
     if args.dump_prof:
-        tags = {}
-        for name, tag, nb, fl, t in prof:
-            d_ = tags.setdefault(f"{name}:{tag}", dict(ms=0.0, n=0, bytes=0, flops=0))
-            d_["ms"] += t; d_["n"] += 1; d_["bytes"] += nb; d_["flops"] += fl
-        rows = sorted(tags.items(), key=lambda kv: -kv[1]["ms"])
-        with open(args.dump_prof, "w") as fh:
-            json.dump([dict(key=k, ms=round(v["ms"], 4), n=v["n"], us_per=round(1e3 * v["ms"] / v["n"], 1),
-                            GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
-                            TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1),
-                            hbm_frac=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"], 3)) for k, v in rows], fh,
-                      indent=0)
-    top = max(fam, key=lambda k: fam[k]["ms"])
-    ft = fam[top]
-    hbm_gbs = ft["bytes"] / (ft["ms"] * 1e-3) / 1e9
-    tflops = ft["flops"] / (ft["ms"] * 1e-3) / 1e12
-    hbm_frac, tc_frac = hbm_gbs / pk["hbm"], tflops / pk["tf_sust"]
-    if hbm_frac >= tc_frac:
-        roof = dict(bound="hbm", achieved=hbm_gbs, peak=pk["hbm"], unit="GB/s", frac=hbm_frac)
-    else:
-        roof = dict(bound="tensor", achieved=tflops, peak=pk["tf_sust"], unit="TFLOP/s", frac=tc_frac)
-    # measured DRAM traffic per launch of that kernel family: one ncu pass over a steady-state step of this same
-    # workload (dram__bytes_read.sum + dram__bytes_write.sum), committed under profiles/ -- not re-measured here
-    traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as fh:
-            tj = json.load(fh)
-        if tj.get("workload") == f"{S}x{S}_b{B}" and top in tj["families"]:
-            traffic = tj["families"][top]["dram_bytes_per_launch"]
-            traffic_src = tj["source"]
-    except Exception:  # noqa: BLE001
-        pass
-    roof.update(kernel=top, launches_per_step=ft["n"], avg_launch_ms=ft["ms"] / ft["n"],
-                share_of_step=ft["ms"] / total_prof, traffic=traffic, traffic_unit="bytes/launch (DRAM read+write, ncu)",
-                traffic_source=traffic_src, algorithmic_bytes_per_launch=ft["bytes"] / ft["n"], peak_source=pk["src"],
-                families={k: dict(ms=round(v["ms"], 3), n=v["n"], GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
-                                  TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)) for k, v in fam.items()})
+        _dump_prof(prof, args.dump_prof, pk)
+    roof = _roofline(prof, pk, traffic_key=f"cfg{args.config}_{S}x{S}_b{B}" if args.config != 3 else f"{S}x{S}_b{B}")
     imgs = B * world * args.steps
     value = imgs / (ms * 1e-3)
     e2e = imgs / (ms_e2e * 1e-3)
-    cpu = cpu_oracle_rate(S, max_seconds=45.0, steps=1) if (world == 1 and not args.no_cpu_baseline) else None
+    cpu = cpu_rate(args.config, S, max_seconds=45.0, steps=1) if (world == 1 and not args.no_cpu_baseline) else None
     line = {
-        "metric": METRIC, "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
+        "metric": cfg["metric"], "value": value, "unit": "img/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"RestormerRefFusion option-003 forward (restoration), {S}x{S}, batch {B}/GPU, "
-                               f"lq+ref per image; fp32 residual stream, bf16 GEMM operands",
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": {"workload": f"{cfg['what']}, {S}x{S}, batch {B}/GPU" + (", lq+ref per image" if cfg["guided"] else "") +
+                               "; IEEE fp16 tensor-core operands (bf16 misses the 0.01 dB parity bar at this depth), fp32 "
+                               "accumulation / residual stream / norms",
+                   "baseline_config": args.config,
                    "l2": "256 MB buffer written between timed iterations (L2 flush), outside the event pairs",
-                   "model_gflop_per_img": FWD_GFLOP_PER_IMG,
-                   "model_tflops_achieved": value * FWD_GFLOP_PER_IMG / 1e3 / world},
-        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": 2 * B * 3 * S * S * 4,
-                "d2h_bytes_per_step": B * 3 * S * S * 4, "ms_per_step": ms_e2e / args.steps},
+                   "model_gflop_per_img": cfg["gflop"],
+                   "model_tflops_achieved": value * cfg["gflop"] / 1e3 / world},
+        "e2e": {"value": e2e, "unit": "img/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roof,
@@ -394,22 +511,17 @@ def _run_b200(args, out):
         tsteps = args.train_steps
         line["train_step"] = {
             "what": "RefGuidedTrainer.optimize_parameters: forward + L1 + explicit backward + gradient all-reduce (NCCL, "
-                    "world > 1) + clip 0.01 + AdamW (lr / ref_lr groups), same batch and shapes as the forward metric",
+                    "world > 1) + clip 0.01 + AdamW (lr / ref_lr groups), same batch and shapes as the forward metric; "
+                    "bf16 operands and gradients",
             "value": B * world * tsteps / (train["ms"] * 1e-3), "unit": "img/s", "ms_per_step": train["ms"] / tsteps,
-            "steps": tsteps, "gpu_launches": train["launches"], "loss": train["loss"],
+            "steps": tsteps, "gpu_launches": train["launches"], "loss": train["loss"], "dtype": "bf16",
             "peak_mem_gb": round(train["peak_mem_gb"], 2),
             "ms_per_step_with_dino_select": train.get("ms_dino"),
-            "model_tflops_achieved": 3 * FWD_GFLOP_PER_IMG * B * tsteps / (train["ms"] * 1e-3) / 1e3}
+            "model_tflops_achieved": 3 * cfg["gflop"] * B * world * tsteps / (train["ms"] * 1e-3) / 1e3 / world}
         if tprof is not None:
-            tags = {}
-            for name, tag, nb, fl, t in tprof:
-                d_ = tags.setdefault(f"{name}:{tag}", dict(ms=0.0, n=0, bytes=0, flops=0))
-                d_["ms"] += t; d_["n"] += 1; d_["bytes"] += nb; d_["flops"] += fl
-            rows = sorted(tags.items(), key=lambda kv: -kv[1]["ms"])
-            with open(args.dump_prof_train, "w") as fh:
-                json.dump([dict(key=k, ms=round(v["ms"], 4), n=v["n"], us_per=round(1e3 * v["ms"] / v["n"], 1),
-                                GBps=round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1),
-                                TFLOPs=round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1)) for k, v in rows], fh, indent=0)
+            line["train_step"]["roofline"] = _roofline(tprof, pk)
+            if args.dump_prof_train:
+                _dump_prof(tprof, args.dump_prof_train, pk)
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     out.emit(json.dumps(line))
@@ -424,11 +536,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=4)
-    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--config", type=int, default=3, choices=sorted(CONFIGS), help="BASELINE.json configuration (default 3: "
+                    "the one the metric is quoted on)")
+    ap.add_argument("--batch", type=int, default=0, help="override the configuration's batch per GPU")
+    ap.add_argument("--size", type=int, default=0, help="override the configuration's tile size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-prof", default="", help="write the per-(kernel, shape) event-timed profile to this json")
-    ap.add_argument("--train-steps", type=int, default=3, help="timed training steps reported under train_step (0 = skip)")
+    ap.add_argument("--train-steps", type=int, default=10, help="timed training steps reported under train_step (0 = skip)")
     ap.add_argument("--dump-prof-train", default="", help="per-(kernel, shape) profile of one training step")
     ap.add_argument("--ncu", action="store_true", help="profiling mode: 1 warm-up + --steps forwards, nothing else "
                                                        "(numbers printed under a profiler are never bench values)")

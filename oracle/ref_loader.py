@@ -16,6 +16,11 @@ import sys
 import types
 
 REF_ROOT = os.environ.get("TDR_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "models", "archs")):
+    # the GPU box has no /root/reference: use the byte-for-byte copies vendored by the recipe oracle/build_ref.py
+    _vend = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    if os.path.isdir(os.path.join(_vend, "models", "archs")):
+        REF_ROOT = _vend
 
 
 def available() -> bool:
