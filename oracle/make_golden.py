@@ -37,6 +37,12 @@ GUIDED_CASES = {
                                              heads=[1, 2, 4, 8], nf=16, ext_n_blocks=[2, 1, 1, 1],
                                              reffusion_n_blocks=[1, 1, 1, 1], LayerNorm_type="WithBias"),
                                     seed=22, lq=(1, 3, 120, 130), ref=(1, 3, 128, 192)),
+    # dual-pixel defocus deblurring (options/train_restoration/004_0*.yml): 6 input channels, skip_conv, no image residual
+    "guided_restormer_dual": dict(cfg=dict(inp_channels=6, out_channels=3, dim=16, num_blocks=[1, 1, 1, 1],
+                                           num_refinement_blocks=1, heads=[1, 2, 4, 8], nf=16, ext_n_blocks=[1, 1, 1, 1],
+                                           reffusion_n_blocks=[1, 1, 1, 1], LayerNorm_type="WithBias",
+                                           dual_pixel_task=True),
+                                  seed=23, lq=(1, 6, 128, 128), ref=(1, 6, 128, 128)),
 }
 
 

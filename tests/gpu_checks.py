@@ -707,8 +707,8 @@ def check_guided_golden():
     from oracle.make_golden import guided_inputs
     from textualdegremoval_b200.archs import define_network
     out = []
-    for name in ("guided_restormer_128", "guided_restormer_ragged"):
-        meta, ref = _golden(name)
+    for name in ("guided_restormer_128", "guided_restormer_ragged", "guided_restormer_dual"):
+        meta, ref = _golden(name)           # *_dual: dual_pixel_task (option 004_0: 6 input channels, skip_conv, R:957-961)
         net = define_network(dict(type="RestormerRefFusion", **meta["cfg"]))
         Wt.load_seeded(net, meta["seed"])
         net = net.to(DEV).eval()
@@ -1256,12 +1256,13 @@ def check_guided_grad():
     from oracle.make_golden import guided_inputs
     from textualdegremoval_b200.archs import define_network
     out = []
-    for name in ("guided_restormer_128", "guided_restormer_ragged"):
+    for name in ("guided_restormer_128", "guided_restormer_ragged", "guided_restormer_dual"):
         meta, _ = _golden(name)
         net = define_network(dict(type="RestormerRefFusion", **meta["cfg"]))
         sd = Wt.load_seeded(net, meta["seed"])
         lq, rf = guided_inputs(meta)
-        gt = Wt.seeded_image("gt", meta["lq"], meta["seed"])
+        gshape = (meta["lq"][0], meta["cfg"].get("out_channels", meta["lq"][1])) + tuple(meta["lq"][2:])
+        gt = Wt.seeded_image("gt", gshape, meta["seed"])
         sdg = {k_: v.clone().requires_grad_(True) for k_, v in sd.items()}
         yr = O.restormer_ref_fusion_forward(sdg, lq, rf, meta["cfg"]["heads"])
         lr = (yr - gt).abs().mean()

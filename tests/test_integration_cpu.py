@@ -1,0 +1,112 @@
+"""CPU suite: the drop-in files under integration/ overlaid on a temporary copy of the REFERENCE tree -- option files
+002 / 003 / 017 (and 004_0 with dual_pixel_task) are resolved through the reference's OWN registries
+(models/archs/__init__.py define_network, models/__init__.py create_model) and must come out as the sm_100a classes with
+the reference's parameter counts; the model wrapper must carry the fused optimizer in ``self.optimizers`` so that the
+reference's schedulers act on it.  Needs /root/reference (this container); skipped on the GPU box."""
+import importlib
+import importlib.machinery
+import os
+import shutil
+import sys
+import types
+
+import pytest
+import torch
+import yaml
+
+REF = os.environ.get("TDR_REFERENCE_ROOT", "/root/reference")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models", "archs")), reason="needs the reference tree")
+
+
+class _Stub(types.ModuleType):
+    """Stand-in for third-party packages the reference imports but this image lacks (skimage, lmdb)."""
+
+    def __init__(self, name):
+        super().__init__(name)
+        self.__spec__ = importlib.machinery.ModuleSpec(name, None)
+        self.__path__ = []
+
+    def __getattr__(self, n):
+        if n.startswith("__"):
+            raise AttributeError(n)
+        m = _Stub(self.__name__ + "." + n)
+        sys.modules[m.__name__] = m
+        setattr(self, n, m)
+        return m
+
+
+@pytest.fixture(scope="module")
+def overlaid(tmp_path_factory):
+    tree = str(tmp_path_factory.mktemp("reftree"))
+    for d in ("models", "utils", "losses", "metrics", "options", "data"):
+        shutil.copytree(os.path.join(REF, d), os.path.join(tree, d))
+    for rel in ("models/archs/restormer_b200_arch.py", "models/archs/nafnet_b200_arch.py",
+                "models/image_restoration_ref_b200_model.py"):
+        shutil.copyfile(os.path.join(ROOT, "integration", rel), os.path.join(tree, rel))
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("models", "utils", "losses", "metrics", "data")}
+    for k in saved:
+        del sys.modules[k]
+    for name in ("skimage", "skimage.metrics", "lmdb"):
+        if name not in sys.modules:
+            sys.modules[name] = _Stub(name)
+    sys.path.insert(0, tree)
+    try:
+        yield tree
+    finally:
+        sys.path.remove(tree)
+        for k in [k for k in sys.modules if k.split(".")[0] in ("models", "utils", "losses", "metrics", "data")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def _network_g(tree, stem):
+    path = [f for f in os.listdir(os.path.join(tree, "options", "train_restoration")) if f.startswith(stem)][0]
+    with open(os.path.join(tree, "options", "train_restoration", path)) as fh:
+        return yaml.safe_load(fh)
+
+
+@pytest.mark.parametrize("stem,params", [("003_", 60_096_138), ("017_", 60_075_402), ("002_", 253_219_395),
+                                         ("004_0", None)])
+def test_reference_registry_resolves_to_b200_classes(overlaid, stem, params):
+    archs = importlib.import_module("models.archs")            # the reference's own registry, scanning the overlaid dir
+    opt = _network_g(overlaid, stem)["network_g"]
+    net = archs.define_network(dict(opt))
+    assert type(net).__module__.startswith("textualdegremoval_b200."), type(net).__module__
+    assert type(net).__name__ == opt["type"]
+    if params is not None:
+        assert sum(p.numel() for p in net.parameters()) == params
+    if stem == "004_0":
+        assert net.dual_pixel_task and "skip_conv.weight" in net.state_dict()
+
+
+def test_reference_create_model_builds_the_fused_training_step(overlaid, tmp_path):
+    models = importlib.import_module("models")
+    from textualdegremoval_b200.archs import vit_b200 as VB
+    from textualdegremoval_b200.ddp import FlatAdamW
+    dino = str(tmp_path / "dino.pth")
+    torch.save(VB.vit_base(img_size=518, patch_size=14, init_values=1.0, ffn_layer="mlp", block_chunks=0).state_dict(), dino)
+    opt = _network_g(overlaid, "003_")
+    opt["network_g"].update(num_blocks=[1, 1, 1, 1], num_refinement_blocks=1, ext_n_blocks=[1, 1, 1, 1],
+                            reffusion_n_blocks=[1, 1, 1, 1])      # same option file, shallow stacks: wiring test
+    opt.update(is_train=True, dist=False, num_gpu=0, rank=0, world_size=1)
+    opt["path"] = dict(pretrain_dino=dino, pretrain_network_g=None, experiments_root=str(tmp_path), models=str(tmp_path),
+                       training_states=str(tmp_path), log=str(tmp_path))
+    opt["train"]["ema_decay"] = 0.999
+    model = models.create_model(opt)
+    assert getattr(type(model), "tdr_b200", False) and type(model).__name__ == "RefGuidedImageCleanModel"
+    assert type(model).optimize_parameters.__module__ == "models.image_restoration_ref_b200_model"
+    assert type(model.net_ext).__module__.startswith("textualdegremoval_b200.")
+    assert not isinstance(model.net_g, torch.nn.parallel.DistributedDataParallel)
+    assert len(model.optimizers) == 1 and isinstance(model.optimizers[0], FlatAdamW)
+    lrs = [pg["lr"] for pg in model.optimizers[0].param_groups]
+    assert lrs == pytest.approx([opt["train"]["optim_g"]["lr"], opt["train"]["optim_g"]["ref_lr"]], rel=1e-9)
+    assert len(model.schedulers) == 1                                           # the reference's scheduler took it
+    model.update_learning_rate(1, warmup_iter=opt["train"].get("warmup_iter", -1))
+    model.optimizers[0].sync_lr()
+    assert [g.lr for g in model._trainer.engine.groups] == [pg["lr"] for pg in model.optimizers[0].param_groups]
+    sd = model.optimizers[0].state_dict()
+    assert "flat" in sd and len(sd["flat"]["groups"]) == 2
+    model._sync_ema()                                                           # EMA copy -> net_g_ema (reference key names)
+    a, b = model.net_g.state_dict(), model.net_g_ema.state_dict()
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)

@@ -405,8 +405,6 @@ class RestormerRefFusion(GuidedRestormerTrainMixin, MasaTrainMixin, MasaMixin, _
     def forward(self, inp_img, ref_img, return_aux=False):
         """:747-964 (with the B1 index shift).  NCHW in, NCHW out, arbitrary H, W (zero-padded to x64, cropped)."""
         self._check(inp_img, ref_img)
-        if self.dual_pixel_task:
-            raise TdrError("RestormerRefFusion (B200): dual_pixel_task is not implemented")
         if self._wants_grad() and not return_aux:
             return train_call(self, inp_img, ref_img)
         P = self.prepared()
@@ -439,8 +437,11 @@ class RestormerRefFusion(GuidedRestormerTrainMixin, MasaTrainMixin, MasaMixin, _
                 self._down(xs[-1], P[downs[i]], fbuf[i][..., :d[i]])
             run_stack(fbuf[i], P[f"masa_blk_enc_level{i + 1}"])      # fuse on 2C channels, keep the first C (:907-909)
             x = fbuf[i][..., :d[i]]
+            if i == 0 and self.dual_pixel_task:                      # skip_conv reads inp_enc_level1 (:957-959); the
+                x_in1 = torch.empty((B, h, w, d[0]), dtype=F32, device=dev)     # encoder stack updates x in place
+                ops.copy_rows(x, dst32=x_in1)
             run_stack(x, P[enc_names[i]])
             xs.append(x)
-        out = self._decode(P, xs[3], xs[0], xs[1], xs[2], None)
-        out = ops.nhwc_to_nchw(out, oh, ow, res=lq32)                                       # + inp_img (:962)
+        out = self._decode(P, xs[3], xs[0], xs[1], xs[2], x_in1 if self.dual_pixel_task else None)
+        out = ops.nhwc_to_nchw(out, oh, ow, res=None if self.dual_pixel_task else lq32)      # + inp_img (:962)
         return (out, aux) if return_aux else out

@@ -238,7 +238,7 @@ class RestormerTrainMixin:
             return P
         for name in ["down1_2", "down2_3", "down3_4", "up4_3", "up3_2", "up2_1"]:
             prep_conv_train(getattr(self, name).body[0], P[name])
-        for name in ["reduce_chan_level3", "reduce_chan_level2"]:
+        for name in ["reduce_chan_level3", "reduce_chan_level2"] + (["skip_conv"] if self.dual_pixel_task else []):
             prep_conv_train(getattr(self, name), P[name])
         ow = self.output.weight                                          # [co, 2*dim, 3, 3] -> dgrad pack with Ci = 8
         w8 = torch.zeros(8, ow.shape[1], 3, 3, dtype=ow.dtype, device=ow.device)
@@ -248,7 +248,8 @@ class RestormerTrainMixin:
         return P
 
     # ---- decoder half (R:477-501) ------------------------------------------------------------------------------
-    def _decode_train(self, P, lat, e1, e2, e3, tape, T):
+    def _decode_train(self, P, lat, e1, e2, e3, tape, T, x_in1=None):
+        """x_in1: the level-1 encoder INPUT (fp32 NHWC), needed by the dual-pixel skip conv only (R:494-496, :957-959)."""
         d = self.dims
         dev = lat.device
 
@@ -274,6 +275,9 @@ class RestormerTrainMixin:
         d1, T["s_dec1"] = run_stack_train(d1, P["decoder_level1"], self.decoder_level1, tape,
                                           nxt=P["refinement"][0] if P["refinement"] else None, tail=tail)
         d1, T["s_ref"] = run_stack_train(d1, P["refinement"], self.refinement, tape, xn=tail[0])
+        if self.dual_pixel_task:          # out = output(d1 + skip_conv(inp_enc_level1)), no image residual
+            T["x_in1_16"] = ops.rownorm(x_in1, 0)
+            d1, _ = ops.conv_gemm(T["x_in1_16"], P["skip_conv"]["w"], d[1], bias=P["skip_conv"]["b"], res2=d1, want="f32")
         T["d1"] = d1
         o8, _ = ops.conv_gemm(ops.rownorm(d1, 0), P["output"]["w"], 8, k=3, pad=1, bias=P["output"]["b"], want="f32")
         return o8[..., :P["output"]["Co"]]
@@ -293,6 +297,14 @@ class RestormerTrainMixin:
         if self.output.bias is not None:
             ops.colsum(do8, G(self.output.bias), c_map=m)
         dd1, _ = ops.conv_gemm(do8, P["output"]["wT"], d[1], Ci=8, k=3, pad=1, want="f32")
+        T["dskip"] = None
+        if self.dual_pixel_task:          # gradient of the skip conv branch; its data gradient joins the level-1 input
+            sk = self.skip_conv
+            dd1_16 = ops.rownorm(dd1, 0)
+            ops.wgrad(dd1_16, T["x_in1_16"], G(sk.weight))
+            if sk.bias is not None:
+                ops.colsum(dd1_16, G(sk.bias))
+            T["dskip"], _ = ops.conv_gemm(dd1_16, P["skip_conv"]["wT"], d[0], want="f32")
         dd1 = run_stack_bwd(dd1, tape, T["s_ref"], G)
         dd1 = run_stack_bwd(dd1, tape, T["s_dec1"], G)
         de1_skip = dd1[..., d[0]:]
@@ -321,8 +333,6 @@ class RestormerTrainMixin:
         B, Cin, H, W = inp_img.shape
         if H % 8 or W % 8:
             raise ValueError(f"Restormer needs H, W multiples of 8 (got {H}x{W})")
-        if self.dual_pixel_task:
-            raise ops.lib.TdrError("Restormer (B200): training with dual_pixel_task is not implemented")
         P = self._prep_train(self.prepared(train=True))
         d = self.dims
         dev = inp_img.device
@@ -334,6 +344,7 @@ class RestormerTrainMixin:
         names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
         downs = [None, "down1_2", "down2_3", "down3_4"]
         es = []
+        x_in1 = x
         for i in range(4):
             if i:
                 nxt = torch.empty((B, H >> i, W >> i, d[i]), dtype=F32, device=dev)
@@ -342,8 +353,8 @@ class RestormerTrainMixin:
                 x = nxt
             x, T["s_" + names[i]] = run_stack_train(x, P[names[i]], getattr(self, names[i]), tape)
             es.append(x)
-        out = self._decode_train(P, es[3], es[0], es[1], es[2], tape, T)
-        y = ops.nhwc_to_nchw(out, H, W, res=inp32)
+        out = self._decode_train(P, es[3], es[0], es[1], es[2], tape, T, x_in1=x_in1)
+        y = ops.nhwc_to_nchw(out, H, W, res=None if self.dual_pixel_task else inp32)
         return y, (P, tape, T)
 
     def _backward(self, state, dout, G=None):
@@ -362,6 +373,8 @@ class RestormerTrainMixin:
         dx = run_stack_bwd(dx, tape, T["s_encoder_level2"], G)
         dx = down_bwd(dx, P["down1_2"], T["down1_2"], G, add=de1_skip)
         dx = run_stack_bwd(dx, tape, T["s_encoder_level1"], G)
+        if T.get("dskip") is not None:
+            dx = ops.scale_add(dx, T["dskip"], out=dx)
         pe = self.patch_embed.proj
         dx16 = ops.rownorm(dx, 0)
         ops.wgrad(dx16, T["inp16"], G(pe.weight), k=3, pad=1, ci_map=_head_map(8, pe.in_channels, dx.device))
@@ -376,8 +389,6 @@ class GuidedRestormerTrainMixin(RestormerTrainMixin):
 
     def _forward_train(self, inp_img, ref_img):
         self._check(inp_img, ref_img)
-        if self.dual_pixel_task:
-            raise ops.lib.TdrError("RestormerRefFusion (B200): dual_pixel_task is not implemented")
         P = self._prep_train(self.prepared(train=True))
         E = self._prep_masa_train(P["masa_enc"])
         d = self.dims
@@ -410,10 +421,12 @@ class GuidedRestormerTrainMixin(RestormerTrainMixin):
                 down_train(xs[-1], P[downs[i]], fbuf[i][..., :d[i]], T[downs[i]])
             fuse = f"masa_blk_enc_level{i + 1}"
             y, T["s_" + fuse] = run_stack_train(fbuf[i], P[fuse], getattr(self, fuse), tape)
+            if i == 0:
+                x_in1 = y[..., :d[0]]                  # inp_enc_level1 after the level-1 fusion (R:907-909)
             x, T["s_" + names[i]] = run_stack_train(y[..., :d[i]], P[names[i]], getattr(self, names[i]), tape)
             xs.append(x)
-        out = self._decode_train(P, xs[3], xs[0], xs[1], xs[2], tape, T)
-        y = ops.nhwc_to_nchw(out, oh, ow, res=lq32)
+        out = self._decode_train(P, xs[3], xs[0], xs[1], xs[2], tape, T, x_in1=x_in1)
+        y = ops.nhwc_to_nchw(out, oh, ow, res=None if self.dual_pixel_task else lq32)
         return y, (P, tape, T)
 
     def _backward(self, state, dout, G=None):
@@ -432,6 +445,8 @@ class GuidedRestormerTrainMixin(RestormerTrainMixin):
         dx = dlat
         for i in (3, 2, 1, 0):
             dx = run_stack_bwd(dx, tape, T["s_" + names[i]], G)
+            if i == 0 and T.get("dskip") is not None:
+                dx = ops.scale_add(dx, T["dskip"], out=dx)
             dfo = torch.zeros((B, h >> i, w >> i, 2 * d[i]), dtype=F32, device=dev)     # [dx || 0]: the slice R:907-909
             ops.copy_rows(dx, dst32=dfo[..., :d[i]])
             dfb = run_stack_bwd(dfo, tape, T[f"s_masa_blk_enc_level{i + 1}"], G)
