@@ -254,6 +254,14 @@ CONV_CASES = [
     dict(name="3x3_dil3", Ci=64, Co=64, k=3, pad=3, dil=3, H=16, W=16),
     dict(name="3x3_valid", Ci=64, Co=64, k=3, pad=0, H=15, W=15, B=3),
     dict(name="2x2_stride2", Ci=64, Co=128, k=2, pad=0, stride=2, bias=True, H=16, W=32),
+    # >= 2 pixel tiles per SM: the resident-weight mode of the 1x1 convs (A-only ring, pixel-tile-major items)
+    dict(name="1x1_res_96to288", Ci=96, Co=288, H=160, W=176, B=2, want="bf16"),
+    dict(name="1x1_res_48to144_bias", Ci=48, Co=144, H=192, W=200, B=1, bias=True, want="bf16"),
+    dict(name="1x1_res_96to512", Ci=96, Co=512, H=160, W=160, B=2, want="bf16"),
+    dict(name="1x1_res_256to96_res2", Ci=256, Co=96, H=160, W=160, B=2, bias=True, res2="f32"),
+    dict(name="1x1_res_192to96_fusion", Ci=192, Co=96, H=176, W=160, B=2, bias=True, res1=True, res2="f32",
+         use_scale_ptr=True),
+    dict(name="1x1_res_ragged_40to72", Ci=40, Co=72, H=250, W=170, B=1, want="both"),
 ]
 
 

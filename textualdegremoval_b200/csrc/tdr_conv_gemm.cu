@@ -26,7 +26,7 @@
 
 namespace {
 
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 8;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;                       // bf16 elements = 128 B = one swizzle row
 constexpr int kABytes = kTileM * kChunkK * 2;     // 16 KiB
@@ -64,6 +64,10 @@ struct ConvGemmArgs {
   int halo;                     // 1: stride-1 KxK conv whose weights fit in shared memory: they are loaded ONCE per CTA,
                                 //    and ONE haloed A tile per channel chunk is streamed; taps are descriptor offsets
                                 //    into it (A is fetched once instead of KH*KW times, B never again)
+  int resident_b;               // 1: 1x1 conv whose whole weight matrix fits in shared memory: every (n tile, chunk) slice
+                                //    is loaded ONCE per CTA, the ring holds A chunks only (2-3 pixel tiles of look-ahead
+                                //    instead of ~1.5 items), and the A chunks of a pixel tile are loaded once and multiplied
+                                //    with all n tiles (items are pixel-tile major: by_pixel = 1)
   int halo_bytes;               // bytes of one haloed A tile: (TH + (KH-1)*dil) rows x 16 px x 128 B
   int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
   int epi_bufs;                 // staging buffers per epilogue warp (1 or 2; 4 with the fused LayerNorm)
@@ -118,18 +122,19 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
   const int kStages = a.stages;
   const int a_ring_bytes = a.halo ? kStages * a.halo_bytes : kStages * kABytes;
   uint8_t* smem_b = smem + a_ring_bytes;
-  const int b_ring_bytes = a.halo ? a.KH * a.KW * a.kchunks * b_bytes : kStages * b_bytes;
+  const int b_ring_bytes = a.halo ? a.KH * a.KW * a.kchunks * b_bytes
+                                  : (a.resident_b ? a.n_tiles * a.kchunks * b_bytes : kStages * b_bytes);
   uint8_t* smem_epi = smem_b + b_ring_bytes;                   // kEpiWarps x epi_bufs x 4 KiB staging tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + kEpiWarps * a.epi_bufs * kEpiStageBytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kMaxStages;
+  uint64_t* full = bars;                                       // [kMaxStages]
+  uint64_t* empty = bars + kMaxStages;                         // [kMaxStages]
   uint64_t* tfull = bars + 2 * kMaxStages;                     // [4]
   uint64_t* tempty = bars + 2 * kMaxStages + 4;                // [4]
   uint64_t* rbar = bars + 2 * kMaxStages + 8;                  // [kEpiWarps][2] residual-tile barriers
-  uint64_t* wfull = rbar + 2 * kEpiWarps;                      // halo mode: resident weights have landed
+  uint64_t* wfull = rbar + 2 * kEpiWarps;                      // halo / resident-B mode: the weights have landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wfull + 1);
-  uint64_t* lnbar = bars + 40;                                 // kLN: [4 quadrants][2 sets][3 sub-blocks] residual tiles
-  float2* ln_xch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [2][kEpiWarps][32] (kLN only)
+  uint64_t* lnbar = bars + 48;                                 // kLN: [4 quadrants][2 sets][3 sub-blocks] residual tiles
+  float2* ln_xch = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 1024);  // [2][kEpiWarps][32] (kLN only)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,9 +183,16 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
           for (int tap = 0; tap < taps; ++tap)
             tma_load_3d(smem_b + (kc * taps + tap) * b_bytes, &map_w, wfull, kc * kChunkK, 0, tap);
       }
+      if (a.resident_b) {                      // resident weights: every (n tile, chunk) slice once, one barrier
+        mbar_expect_tx(wfull, (uint32_t)(a.n_tiles * a.kchunks * b_bytes));
+        for (int nt = 0; nt < a.n_tiles; ++nt)
+          for (int kc = 0; kc < a.kchunks; ++kc)
+            tma_load_3d(smem_b + (nt * a.kchunks + kc) * b_bytes, &map_w, wfull, kc * kChunkK, nt * a.BN, 0);
+      }
       for (int sq = 0;; ++sq) {
         int mt, nt;
         if (!conv_item(a, sq, mt, nt)) break;
+        if (a.resident_b && nt != 0) continue;   // the A chunks of a pixel tile are loaded once for all its n tiles
         const int b = mt / tiles_per_img;
         const int r = mt % tiles_per_img;
         const int oy0 = (r / a.tiles_x) * a.TH;
@@ -202,11 +214,12 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
           const int kc = ks % a.kchunks;
           const int ky = tap / a.KW, kx = tap % a.KW;
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], kABytes + b_bytes);
+          mbar_expect_tx(&full[stage], a.resident_b ? kABytes : kABytes + b_bytes);
           tma_load_4d(smem_a + stage * kABytes, &map_a, &full[stage], kc * kChunkK,
                       org_x + ox0 * a.stride - a.pad + kx * a.dil, org_y + oy0 * a.stride - a.pad + ky * a.dil, img);
-          tma_load_3d(smem_b + stage * b_bytes, &map_w, &full[stage], kc * kChunkK, nt * a.BN,
-                      (a.w_batched ? b * taps : 0) + tap);
+          if (!a.resident_b)
+            tma_load_3d(smem_b + stage * b_bytes, &map_w, &full[stage], kc * kChunkK, nt * a.BN,
+                        (a.w_batched ? b * taps : 0) + tap);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -217,7 +230,43 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (;; ++it) {
+    if (a.resident_b) {
+      // pixel-tile major: the kchunks A stages of a pixel tile stay in the ring while every n tile is multiplied with
+      // them; they are released by the commit that follows the LAST n tile's MMAs
+      mbar_wait(wfull, 0);
+      for (int pt = 0;; ++pt) {
+        if (blockIdx.x + pt * (int)gridDim.x >= a.m_tiles) break;
+        const int st0 = stage;
+        const uint32_t ph0 = phase;
+        for (int nt = 0; nt < a.n_tiles; ++nt, ++it) {
+          const int acc = it % a.nacc;
+          const uint32_t acc_phase = (it / a.nacc) & 1;
+          mbar_wait(&tempty[acc], acc_phase ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * a.BN;
+          int st = st0;
+          uint32_t ph = ph0;
+          for (int kc = 0; kc < a.kchunks; ++kc) {
+            if (nt == 0) {
+              mbar_wait(&full[st], ph);
+              tc_fence_after();
+            }
+            if (lane == 0) {
+              const uint64_t da = umma_desc_sw128(smem_u32(smem_a + st * kABytes), 0, 1024);
+              const uint64_t db = umma_desc_sw128(smem_u32(smem_b + (nt * a.kchunks + kc) * b_bytes), 0, 1024);
+#pragma unroll
+              for (int k = 0; k < kChunkK / 16; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0);
+              if (nt == a.n_tiles - 1) umma_commit(&empty[st]);
+              if (kc == a.kchunks - 1) umma_commit(&tfull[acc]);
+            }
+            __syncwarp();
+            if (++st == kStages) { st = 0; ph ^= 1; }
+          }
+          if (nt == a.n_tiles - 1) { stage = st; phase = ph; }
+        }
+      }
+    }
+    for (; !a.resident_b; ++it) {
       int mt_, nt_;
       if (!conv_item(a, it, mt_, nt_)) break;
       const int acc = it % a.nacc;
@@ -956,11 +1005,42 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     a.stages = 4;
   }
   a.kchunks = tdr_cdiv(d->Ci, kChunkK);
+  a.resident_b = 0;
   auto smem_need = [&]() {
-    const size_t ring = a.halo ? (size_t)a.stages * a.halo_bytes + (size_t)d->KH * d->KW * a.kchunks * a.BN * kChunkK * 2
-                               : (size_t)a.stages * (kABytes + a.BN * kChunkK * 2);
-    return 1024 + ring + (size_t)kEpiWarps * a.epi_bufs * kEpiStageBytes + 512 + (want_ln ? 2 * kEpiWarps * 32 * 8 : 0);
+    const size_t bt = (size_t)a.BN * kChunkK * 2;
+    const size_t ring = a.halo ? (size_t)a.stages * a.halo_bytes + (size_t)d->KH * d->KW * a.kchunks * bt
+                               : (a.resident_b ? (size_t)a.stages * kABytes + (size_t)a.n_tiles * a.kchunks * bt
+                                               : (size_t)a.stages * (kABytes + bt));
+    return 1024 + ring + (size_t)kEpiWarps * a.epi_bufs * kEpiStageBytes + 1024 + (want_ln ? 2 * kEpiWarps * 32 * 8 : 0);
   };
+  // Resident-B mode (1x1 convs with shared weights and many pixel tiles per CTA): the whole weight matrix stays in shared
+  // memory, the ring carries A chunks only.  BN = the multiple of the sub-block width with the fewest padded columns;
+  // accepted when at least max(4, kchunks + 2) A stages fit next to the weights and the epilogue staging.
+  if (a.epi_mode == 1 && d->KH * d->KW == 1 && !d->w_batched && d->impl == 0 && d->stride == 1 &&
+      (long long)d->B * a.tiles_y * a.tiles_x >= 2LL * tdr_num_sms() && getenv("TDR_CONV_NO_RESIDENT") == nullptr &&
+      getenv("TDR_CONV_BN") == nullptr && getenv("TDR_CONV_STAGES") == nullptr) {
+    const int sbc = a.out_is_f32 ? 32 : 64;
+    int bn_best = 0, pad_best = 1 << 30;
+    for (int bn = sbc; bn <= 256; bn += sbc) {
+      const int nt = tdr_cdiv(d->Co, bn);
+      const int pad = nt * bn + 48 * nt;                        // same cost model as the streamed-weights plan above
+      if (pad < pad_best || (pad == pad_best && bn > bn_best)) { pad_best = pad; bn_best = bn; }
+    }
+    const int nt = tdr_cdiv(d->Co, bn_best);
+    const size_t bbytes = (size_t)nt * a.kchunks * bn_best * kChunkK * 2;
+    const int tries[2] = {want_ln ? 4 : 2, want_ln ? 4 : (d->res1 ? 2 : 1)};
+    for (int t = 0; t < 2 && !a.resident_b; ++t) {
+      const long long avail = 227LL * 1024 - 1024 - 1024 - (want_ln ? 2 * kEpiWarps * 32 * 8 : 0) - (long long)bbytes -
+                              (long long)kEpiWarps * tries[t] * kEpiStageBytes;
+      int S = (int)(avail / kABytes);
+      if (S > kMaxStages) S = kMaxStages;
+      const int need = a.kchunks + 2 > 4 ? a.kchunks + 2 : 4;
+      if (avail > 0 && S >= need && (!want_ln || nt == 1)) {
+        a.resident_b = 1;
+        a.BN = bn_best; a.n_tiles = nt; a.stages = S; a.epi_bufs = tries[t];
+      }
+    }
+  }
   // Halo mode: stride-1 multi-tap conv, shared (not per-sample) weights that fit in shared memory next to a 3-deep
   // ring of haloed [TH + (KH-1)dil] x 16 px A tiles, a single N tile.  TW = 8 so that every 8-row UMMA group is one
   // image-row segment of the haloed tile.
@@ -993,6 +1073,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   // by_pixel only pays when the n tiles are UNEQUAL (its scheduling granule is n_tiles items, so the tail gets coarser) and
   // there are many pixel tiles per SM
   a.by_pixel = (a.n_tiles > 1 && d->Co % a.BN != 0 && a.m_tiles >= 8 * tdr_num_sms()) ? 1 : 0;
+  if (a.resident_b) a.by_pixel = 1;
   // accumulator ring: as many BN-column buffers as fit in the 512 TMEM columns (2..4) -- a deeper ring keeps more
   // tiles between the MMA issuer and the epilogue in flight
   a.nacc = 512 / a.BN;
@@ -1069,7 +1150,8 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     if (rc) return rc;
   }
   const size_t smem = smem_need();
-  const int grid = a.total_tiles < tdr_num_sms() ? a.total_tiles : tdr_num_sms();
+  int grid = a.total_tiles < tdr_num_sms() ? a.total_tiles : tdr_num_sms();
+  if (a.by_pixel && grid > a.m_tiles) grid = a.m_tiles;
   int variant = a.epi_mode == 1 ? (a.out_is_f32 | (d->res2 ? 2 : 0) | (d->res1 ? 4 : 0) | (want_ln ? 8 : 0)) : -1;
   if (variant == 0 && a.out_fp16) variant = 16;
   if (variant == 11 && a.out_fp16) variant = 27;

@@ -175,28 +175,29 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
   }
 }
 
-// Stage 1 of the finalize: grid (ceil(c/8), heads, B), one warp per attention row.  Reduces the per-chunk partial
-// Grams (deterministic order), applies the F.normalize denominators, temperature and the row softmax.
+// Stage 1 of the finalize: grid (c, heads, B), one CTA of 8 warps per attention row i.  The per-chunk partial Grams are
+// reduced in a FIXED two-level order (warp w sums chunks w, w+8, w+16, ... in order; the 8 warp sums are then added in warp
+// order), so the result is deterministic and a function of (P, heads) only; the 8 warps keep 8 x 4 independent L2 loads
+// in flight instead of one warp walking all ~148 chunks.  Then the F.normalize denominators, temperature and the softmax.
 __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restrict__ partials, int C, int heads,
                                                            int nchunks, const float* __restrict__ temperature,
                                                            float* __restrict__ attn, float* __restrict__ shat_out) {
   const int c = C / heads;
   const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * 8 + warp;
-  if (i >= c) return;
+  const int i = blockIdx.x;
   const size_t psz = (size_t)c * c + 2 * c;
   const float* base = partials + (size_t)(b * heads + h) * nchunks * psz;
+  __shared__ float sg[8][4][32], sk[8][4][32], sq[8];
   float g[4] = {0.f, 0.f, 0.f, 0.f}, nk[4] = {0.f, 0.f, 0.f, 0.f};
   float nq = 0.f;
-  // the chunk loop is a chain of dependent L2 round trips unless several chunks are in flight: 8 at a time (the
-  // summation ORDER stays chunk 0, 1, 2, ... so the result is still deterministic)
-  for (int ch0 = 0; ch0 < nchunks; ch0 += 8) {
-    float tg[8][4], tk[8][4], tq[8];
+  for (int ch0 = warp; ch0 < nchunks; ch0 += 32) {          // 4 chunks of this warp's residue class at a time
+    float tg[4][4], tk[4][4], tq[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const bool in = ch0 + u < nchunks;
-      const float* p = base + (size_t)(in ? ch0 + u : 0) * psz;
+    for (int u = 0; u < 4; ++u) {
+      const int ch = ch0 + 8 * u;
+      const bool in = ch < nchunks;
+      const float* p = base + (size_t)(in ? ch : 0) * psz;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int j = lane + 32 * t;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
       tq[u] = in ? p[c * c + i] : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 4; ++u) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         g[t] += tg[u][t];
@@ -215,6 +216,25 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
       }
       nq += tq[u];
     }
+  }
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    sg[warp][t][lane] = g[t];
+    sk[warp][t][lane] = nk[t];
+  }
+  if (lane == 0) sq[warp] = nq;
+  __syncthreads();
+  if (warp != 0) return;
+  nq = 0.f;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) g[t] = nk[t] = 0.f;
+  for (int w = 0; w < 8; ++w) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      g[t] += sg[w][t][lane];
+      nk[t] += sk[w][t][lane];
+    }
+    nq += sq[w];
   }
   const float nqi = fmaxf(sqrtf(fmaxf(nq, 0.f)), 1e-12f);
   const float temp = temperature[h];
@@ -330,7 +350,7 @@ extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, i
   TDR_CHECK_ARG(make_plan(B, P, C, heads, &p) == 0, "tdr_mdta_weff: unsupported head width");
   TDR_CHECK_ARG(weff_ld >= C && weff_ld % 8 == 0, "tdr_mdta_weff: bad weff_ld");
   {
-    dim3 grid((p.c + 7) / 8, heads, B);
+    dim3 grid(p.c, heads, B);
     mdta_softmax_kernel<<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out);
     TDR_CHECK_LAUNCH();
   }
