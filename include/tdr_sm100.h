@@ -161,6 +161,38 @@ int tdr_cvt_f16_bf16(const void* in_fp16, long long in_ld, long long rows, int C
 int tdr_dwconv3x3(const void* in_bf16, long long in_ld, int B, int H, int W, int C, const float* weight,
                   const float* bias, int gate, void* out_bf16, long long out_ld, cudaStream_t stream);
 
+/* Fused tail of the gated-dconv feed-forward R:236-240 (+ the residual add R:329 / the Res-fusion epilogue R:345-353):
+ *   out = g*alpha * ( W_out . ( gelu(dw3x3(hidden)[:hp]) * dw3x3(hidden)[hp:] ) + bias ) + g*res1_scale*res1 + res2
+ * in ONE kernel: the gated tensor never leaves the SM (depthwise stencil + exact GELU gate on CUDA cores -> SWIZZLE_128B
+ * shared-memory tile -> tcgen05.mma against TMA-loaded slices of W_out, accumulator in TMEM), which removes its 4*hp B
+ * per pixel of HBM traffic and one launch per transformer block.  hidden: 16-bit NHWC [B,H,W,hidden_ld >= 2*hp]
+ * (bf16, or IEEE fp16 when fp16 != 0 -- then w_out is fp16 too); dw_weight fp32 [9][2*hp] tap-major, dw_bias fp32
+ * [2*hp] or NULL; w_out 16-bit [C][w_ld >= hp]; out / res1 / res2 fp32 rows (out may alias res2).
+ * Supported: 16 <= C <= 192, C % 16 == 0, hp % 8 == 0 (tdr_gdfn_tail_supported tells; callers keep the two-kernel
+ * path otherwise). */
+typedef struct tdr_gdfn_tail_desc {
+  const void* hidden;
+  long long hidden_ld;
+  int B, H, W, hp, C;
+  const float* dw_weight;
+  const float* dw_bias;
+  const void* w_out;
+  long long w_ld;
+  const float* bias;
+  float alpha;
+  const float* scale_ptr;
+  const float* res1;
+  long long res1_ld;
+  float res1_scale;
+  const float* res2;
+  long long res2_ld;
+  float* out;
+  long long out_ld;
+  int fp16;
+} tdr_gdfn_tail_desc;
+int tdr_gdfn_tail(const tdr_gdfn_tail_desc* d, cudaStream_t stream);
+int tdr_gdfn_tail_supported(const tdr_gdfn_tail_desc* d);
+
 /* NAFNet pieces (network_nafnet_guided_arch.py, "N:").
  *   tdr_gate_mul     : SimpleGate N:170-175 on bf16 rows, out[r, c] = x[r, c] * x[r, C + c].
  *   tdr_naf_sca_fold : Simplified channel attention N:192-196 folded into conv3 N:229: s = W_sca * avgpool(g) + b_sca,

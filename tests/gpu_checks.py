@@ -388,6 +388,44 @@ def check_fp16_path():
     return out
 
 
+def check_gdfn_tail():
+    """tdr_gdfn_tail (depthwise 3x3 + GELU gate + project_out + residuals in one kernel) vs fp32 CPU math on the same
+    16-bit-rounded operands; the gated intermediate is rounded to the operand format as the kernel does."""
+    ops = _ops()
+    F16 = torch.float16
+    out = []
+    cases = [  # B, H, W, hp, C, fusion, dw_bias, out_bias, dtype
+        (2, 16, 32, 128, 48, False, False, False, BF16), (1, 24, 40, 256, 96, True, True, True, F16),
+        (1, 8, 16, 512, 192, False, True, False, F16), (2, 20, 24, 48, 16, False, True, True, BF16),
+        (1, 19, 37, 88, 32, True, False, True, F16), (3, 64, 48, 256, 96, False, False, False, F16),
+    ]
+    for (B, H, W, hp, Cc, fusion, dwb, ob, dt) in cases:
+        rq = (lambda t: t.to(dt).float())
+        hid = rq(rnd(B, 2 * hp, H, W, seed=hp + H))
+        wdw = rnd(2 * hp, 1, 3, 3, seed=3) * 0.3
+        bdw = rnd(2 * hp, seed=4) * 0.1 if dwb else None
+        wo = rnd(Cc, hp, 1, 1, seed=5) * (1.0 / hp ** 0.5)
+        bo = rnd(Cc, seed=6) * 0.2 if ob else None
+        x0 = rnd(B, Cc, H, W, seed=7)
+        x1 = rnd(B, Cc, H, W, seed=8) if fusion else None
+        alpha = 0.6
+        y = F.conv2d(hid, wdw, bdw, padding=1, groups=2 * hp)
+        gte = rq(F.gelu(y[:, :hp]) * y[:, hp:])
+        ffn = F.conv2d(gte, rq(wo), bo)
+        ref = (x1 + ffn) * alpha + x0 if fusion else ffn + x0
+        hid_d = nhwc(hid.to(dt))
+        w9 = ops.pack_dw_weight(wdw.to(DEV))
+        wp = ops.pack_conv_weight(wo.to(DEV), dt=dt)
+        assert ops.gdfn_tail_supported(hid_d, wp, Cc)
+        x32 = nhwc(x0)
+        ops.gdfn_tail(hid_d, w9, bdw.to(DEV) if dwb else None, wp, Cc, bias=bo.to(DEV) if ob else None,
+                      scale_ptr=torch.tensor([alpha], device=DEV) if fusion else None, res1=nhwc(x1) if fusion else None,
+                      res2=x32, out=x32)
+        out.append(result(f"gdfn_tail_B{B}_{H}x{W}_hp{hp}_C{Cc}_f{int(fusion)}_{'fp16' if dt == F16 else 'bf16'}", nchw(x32), ref,
+                          2e-3 if dt == F16 else 6e-3))
+    return out
+
+
 def check_conv_ln():
     """1x1 conv + residual with the LayerNorm of the finished rows emitted by the same epilogue (norm1 / norm2 of
     R:318-331 folded into the producing conv): fp32 rows must equal the plain epilogue's, the bf16 LN output must match
@@ -1565,6 +1603,7 @@ CHECKS = {
     "conv_tc": check_conv_tc,
     "conv_origin": check_conv_origin,
     "conv_ln": check_conv_ln,
+    "gdfn_tail": check_gdfn_tail,
     "fp16_path": check_fp16_path,
     "input_pipeline": check_input_pipeline,
     "psnr": check_psnr,

@@ -11,9 +11,17 @@ from textualdegremoval_b200.archs import restormer_b200_arch as A
 
 
 class _Recorder:
-    def __init__(self, fuse=True):
+    def __init__(self, fuse=True, gdfn=False):
         self.calls = []
         self.fuse = fuse
+        self.gdfn = gdfn          # fused GDFN tail (tdr_gdfn_tail) available for the shape?
+
+    def gdfn_tail_ok(self, hid, w_out, Cc):
+        return self.gdfn
+
+    def gdfn_tail(self, hid, w9, b9, w_out, Cc, **kw):
+        self.calls.append(("gdfn", Cc, kw.get("res1") is not None, kw.get("scale_ptr") is not None))
+        return kw.get("out")
 
     def conv_ln_ok(self, Co):
         return self.fuse and Co <= 96 and Co % 8 == 0
@@ -75,6 +83,23 @@ def test_stack_chains_norms_through_the_convs(rec):
                                   preps[2]["ln2_w"]]
     assert all(a[0] == 1 and a[3] == 1e-5 for a in ln)
     assert sum(c[0] == "conv" for c in rec.calls) == 12 and sum(c[0] == "dw" for c in rec.calls) == 6   # 9 launches / block
+
+
+def test_fused_gdfn_tail_replaces_the_gate_and_project_out_launches(monkeypatch):
+    """With tdr_gdfn_tail the block is 7 launches: norm1 -> qkv -> dw -> Gram/fold -> attn.v.proj(+norm2) -> project_in ->
+    fused tail; the next block's norm1 runs standalone (the tail emits fp32 rows only)."""
+    r = _Recorder(gdfn=True)
+    monkeypatch.setattr(A, "ops", r)
+    preps = [_prep(96, i) for i in range(3)]
+    A.run_stack(torch.zeros(1, 8, 8, 96), preps)
+    assert sum(c[0] == "rownorm" for c in r.calls) == 3                    # one norm1 per block
+    assert [a[1] for a in _ln_args(r.calls)] == [p["ln2_w"] for p in preps]   # norm2 still comes out of the attn conv
+    assert sum(c[0] == "conv" for c in r.calls) == 9 and sum(c[0] == "dw" for c in r.calls) == 3
+    assert [c for c in r.calls if c[0] == "gdfn"] == [("gdfn", 96, False, False)] * 3
+    r.calls.clear()
+    alpha = torch.ones(1)
+    A.run_stack(torch.zeros(1, 8, 8, 96), [_prep(96, 0, alpha)])
+    assert [c for c in r.calls if c[0] == "gdfn"] == [("gdfn", 96, True, True)]   # Res-fusion epilogue: res1 + alpha
 
 
 def test_stack_boundary_hands_over_the_normalised_rows(rec):

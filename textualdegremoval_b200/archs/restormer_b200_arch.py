@@ -187,6 +187,14 @@ def run_block(x32, p, xn=None, nxt=None):
     if fusion or not fuse_ln:
         xn = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5, out=xn)
     _, hid = ops.conv_gemm(xn, p["w_in"], 2 * hp, bias=p["b_in"])
+    if ops.gdfn_tail_ok(hid, p["w_out"], C_):
+        # depthwise 3x3 + GELU gate + project_out + residual(s) in one kernel: the gated tensor never reaches HBM
+        if fusion:  # out = (x1 + ffn) * alpha + x0
+            ops.gdfn_tail(hid, p["w_dw"], p["b_dw"], p["w_out"], C_, bias=p["b_out"], scale_ptr=p["alpha"], res1=x1,
+                          res2=x32, out=x32)
+        else:
+            ops.gdfn_tail(hid, p["w_dw"], p["b_dw"], p["w_out"], C_, bias=p["b_out"], res2=x32, out=x32)
+        return None
     g = ops.dwconv3x3(hid, p["w_dw"], p["b_dw"], gate=1)
     if fusion:      # out = (x1 + ffn) * alpha + x0
         ops.conv_gemm(g, p["w_out"], C_, bias=p["b_out"], scale_ptr=p["alpha"], res1=x1, res2=x32, out_f32=x32)

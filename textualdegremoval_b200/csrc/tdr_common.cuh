@@ -128,6 +128,15 @@ __device__ __forceinline__ uint4 lds128(uint32_t saddr) {
   return r;
 }
 
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t r;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(saddr) : "memory");
+  return r;
+}
+__device__ __forceinline__ void sts32(uint32_t saddr, uint32_t v) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -159,6 +168,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {
       printf("tdr: mbarrier timeout block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
+// Same, for roles that usually wait long (a whole tile): back off between polls so that the spinning warp does not take
+// issue slots from the working warps of its scheduler.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns = 200) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (1u << 24)) {
+      printf("tdr: mbarrier timeout (sleeping wait) block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
       __trap();
     }
   }

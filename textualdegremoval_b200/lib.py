@@ -40,6 +40,21 @@ class ConvGemmDesc(C.Structure):
     ]
 
 
+class GdfnTailDesc(C.Structure):
+    """Mirror of ``tdr_gdfn_tail_desc`` (include/tdr_sm100.h)."""
+    _fields_ = [
+        ("hidden", C.c_void_p), ("hidden_ld", C.c_longlong),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int), ("hp", C.c_int), ("C", C.c_int),
+        ("dw_weight", C.c_void_p), ("dw_bias", C.c_void_p),
+        ("w_out", C.c_void_p), ("w_ld", C.c_longlong),
+        ("bias", C.c_void_p), ("alpha", C.c_float), ("scale_ptr", C.c_void_p),
+        ("res1", C.c_void_p), ("res1_ld", C.c_longlong), ("res1_scale", C.c_float),
+        ("res2", C.c_void_p), ("res2_ld", C.c_longlong),
+        ("out", C.c_void_p), ("out_ld", C.c_longlong),
+        ("fp16", C.c_int),
+    ]
+
+
 class PatchDesc(C.Structure):
     """Mirror of ``tdr_patch_desc`` (include/tdr_sm100.h)."""
     _fields_ = [("image", C.c_void_p), ("h", C.c_int), ("w", C.c_int), ("top", C.c_int), ("left", C.c_int),
@@ -56,6 +71,8 @@ SIGNATURES = {
     "tdr_conv_gemm": (_i, [C.POINTER(ConvGemmDesc), _vp]),
     "tdr_conv_gemm_ln_supported": (_i, [C.POINTER(ConvGemmDesc)]),
     "tdr_conv_gemm_desc_layout": (None, [C.POINTER(_i)]),
+    "tdr_gdfn_tail": (_i, [C.POINTER(GdfnTailDesc), _vp]),
+    "tdr_gdfn_tail_supported": (_i, [C.POINTER(GdfnTailDesc)]),
     "tdr_conv3x3_small_ci": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _ll, _vp, _ll, _vp]),
     "tdr_conv3x3_small_co": (_i, [_vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "tdr_rownorm": (_i, [_vp, _ll, _ll, _i, _i, _vp, _vp, _f, _i, _vp, _ll, _vp, _ll, _vp]),

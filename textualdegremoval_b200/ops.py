@@ -324,6 +324,56 @@ def dwconv3x3(x, w9, bias=None, gate=0, out=None):
     return out
 
 
+def _gdfn_desc(hid, w9, bias_dw, w_out, Cc, bias, scale_ptr, res1, res1_scale, res2, out):
+    B, H, W, C2 = hid.shape
+    d = lib.GdfnTailDesc()
+    d.hidden = hid.data_ptr(); d.hidden_ld = _ld(hid)
+    d.B = B; d.H = H; d.W = W; d.hp = C2 // 2; d.C = Cc
+    d.dw_weight = w9.data_ptr(); d.dw_bias = bias_dw.data_ptr() if bias_dw is not None else None
+    d.w_out = w_out.data_ptr(); d.w_ld = w_out.shape[-1]
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.alpha = 1.0
+    d.scale_ptr = scale_ptr.data_ptr() if scale_ptr is not None else None
+    if res1 is not None:
+        d.res1 = res1.data_ptr(); d.res1_ld = _ld(res1)
+    d.res1_scale = res1_scale
+    if res2 is not None:
+        d.res2 = res2.data_ptr(); d.res2_ld = _ld(res2)
+    d.out = out.data_ptr(); d.out_ld = _ld(out)
+    d.fp16 = int(hid.dtype == F16)
+    return d
+
+
+def gdfn_tail_supported(hid, w_out, Cc):
+    """Can ``gdfn_tail`` run this shape (16 <= C <= 192, C % 16 == 0, ...)?"""
+    return 16 <= Cc <= 192 and Cc % 16 == 0 and (hid.shape[3] // 2) % 8 == 0 and w_out.dtype == hid.dtype \
+        and w_out.shape[-2] == Cc
+
+
+def gdfn_tail_ok(hid, w_out, Cc):
+    """Does the block schedule use the fused GDFN tail?  OFF by default: the kernel is correct (tests/gpu_checks.py
+    ``gdfn_tail``) but measured 859 us against 713 us for depthwise-gate + project_out as two kernels at hp 256 -> C 96,
+    512x512, batch 4 (tools/probe_gdfn.py; DESIGN.md "Fused GDFN tail: a negative result").  TDR_GDFN_FUSION=1 turns it
+    on for A/B runs."""
+    return os.environ.get("TDR_GDFN_FUSION", "0") not in ("", "0") and gdfn_tail_supported(hid, w_out, Cc)
+
+
+def gdfn_tail(hid, w9, bias_dw, w_out, Cc, bias=None, scale_ptr=None, res1=None, res1_scale=1.0, res2=None, out=None):
+    """Fused GDFN tail (reference R:236-240, :329, :345-353): out = g * (W_out . (gelu(dw(hid)[:hp]) * dw(hid)[hp:]) + bias)
+    + g * res1_scale * res1 + res2, fp32 rows; the gated tensor never reaches HBM.  hid: 16-bit NHWC [B,H,W,2*hp]; w9 fp32
+    [9, 2*hp]; w_out 16-bit [1, C, hp]."""
+    assert hid.dtype in (BF16, F16) and w9.dtype == F32 and w_out.dtype == hid.dtype
+    B, H, W, C2 = hid.shape
+    if out is None:
+        out = torch.empty((B, H, W, Cc), dtype=F32, device=hid.device)
+    d = _gdfn_desc(hid, w9, bias_dw, w_out, Cc, bias, scale_ptr, res1, res1_scale, res2, out)
+    hp = C2 // 2
+    _call("tdr_gdfn_tail", C.byref(d), _stream(), tag=f"hp{hp}_C{Cc}_{H}x{W}",
+          nbytes=B * H * W * (C2 * 2 + Cc * 4 * (1 + int(res1 is not None) + int(res2 is not None))) + Cc * hp * 2,
+          flops=2 * B * H * W * (9 * C2 + hp * Cc))
+    return out
+
+
 def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False, save=None):
     """qkv: bf16 NHWC [B,H,W,>=3C].  Returns Weff bf16 [B, C, C_p] (and attn fp32 [B,heads,c,c]).
     save: optional dict that receives partials / attn / weff / weff_t (what the backward pass needs)."""
