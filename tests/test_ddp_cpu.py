@@ -59,7 +59,17 @@ def _worker(rank, world, port, out):
     loss.backward()
     for p in net.parameters():                 # autograd accumulated INTO the flat views
         assert p.grad.data_ptr() >= min(gr.grad.data_ptr() for gr in eng.groups)
-    for w in eng.all_reduce_gradients():
+    # overlap bookkeeping: modules reported in backward order (head -> masa_enc -> body); slices go out as the finished
+    # tail of each flat buffer grows, the rest in all_reduce_gradients(); every element is reduced exactly once
+    eng.begin_backward()
+    eng.mark_done(net.head)
+    n_early_head = len(eng._early)
+    eng.mark_done(net.masa_enc)
+    eng.mark_done(net.body.bias)                 # a single parameter
+    n_early = len(eng._early)
+    works = eng.all_reduce_gradients()
+    out[f"early_{rank}"] = (n_early_head, n_early, len(works))
+    for w in works:
         w.wait()
     eng.reduce_loss_async(loss)
     avg = torch.cat([p.grad.reshape(-1) for gr in eng.groups for p in gr.params]) / world
@@ -90,6 +100,9 @@ def test_two_rank_gradient_equivalence():
     assert abs(out["loss"] - out["loss_ref"]) < 1e-6
     assert out["cpu_step"] == "refused"          # no CPU fallback for the fused optimizer tail
     for r in (0, 1):
+        e_head, e_all, total = out[f"early_{r}"]
+        # the head alone is smaller than a bucket (nothing sent yet); with masa_enc done the ref group's tail goes out
+        assert e_head == 0 and e_all >= 1 and total > e_all, out[f"early_{r}"]
         assert out[f"param_spread_{r}"] == 0.0 and out[f"is_rank0_init_{r}"], "ranks must start from rank 0's parameters"
         assert out[f"buffer_{r}"] == [0.0, 0.0, 0.0], "buffers must be broadcast from rank 0"
 

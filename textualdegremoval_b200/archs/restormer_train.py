@@ -30,10 +30,16 @@ class Grads:
     ``direct=True``: a parameter that already owns a contiguous fp32 ``.grad`` (the flat DDP buffers of
     ``ddp.FlatGroup``) is accumulated into in place -- no per-step allocation and no extra add pass."""
 
-    def __init__(self, direct=False):
+    def __init__(self, direct=False, on_done=None):
         self.buf = {}
         self.direct = direct
         self.in_place = set()
+        self.on_done = on_done       # ddp.DDPStep.mark_done: lets the gradient all-reduce start during the backward
+
+    def done(self, obj):
+        """The schedule calls this when the gradients of a module (or parameter) are final for this step."""
+        if self.on_done is not None and obj is not None:
+            self.on_done(obj)
 
     def __call__(self, param):
         if param is None:
@@ -185,6 +191,7 @@ def run_stack_bwd(d, tape, span, G):
         want = i > span[0]
         res = run_block_bwd(d, tape[i], G, dout16=d16, want16=want)
         d, d16 = res if want else (res, None)
+        G.done(tape[i]["p"].get("mod"))             # this block's parameter gradients are final
         tape[i] = None                              # free the block's activations as soon as they are consumed
     return d
 
@@ -202,6 +209,7 @@ def down_bwd(dy32, pc, sv, G, add=None):
     dconv = ops.pixel_shuffle(ops.rownorm(dy32, 0), 2)                 # adjoint of the unshuffle store
     x16 = ops.rownorm(sv["x"], 0)
     ops.wgrad(dconv, x16, G(conv.weight), k=3, pad=1)
+    G.done(conv)
     dx, _ = ops.conv_gemm(dconv, pc["wT"], conv.in_channels, k=3, pad=1, want="f32", res2=add)
     return dx
 
@@ -212,6 +220,7 @@ def up_bwd(dy16, pc, x32, G):
     conv = pc["mod"]
     dconv = ops.pixel_shuffle(dy16, 1)                                  # adjoint of the shuffle store
     ops.wgrad(dconv, ops.rownorm(x32, 0), G(conv.weight), k=3, pad=1)
+    G.done(conv)
     dx, _ = ops.conv_gemm(dconv, pc["wT"], conv.in_channels, k=3, pad=1, want="f32")
     return dx
 
@@ -296,6 +305,7 @@ class RestormerTrainMixin:
         ops.wgrad(do8, d1_16, G(self.output.weight), k=3, pad=1, co_map=m)
         if self.output.bias is not None:
             ops.colsum(do8, G(self.output.bias), c_map=m)
+        G.done(self.output)
         dd1, _ = ops.conv_gemm(do8, P["output"]["wT"], d[1], Ci=8, k=3, pad=1, want="f32")
         T["dskip"] = None
         if self.dual_pixel_task:          # gradient of the skip conv branch; its data gradient joins the level-1 input
@@ -304,6 +314,7 @@ class RestormerTrainMixin:
             ops.wgrad(dd1_16, T["x_in1_16"], G(sk.weight))
             if sk.bias is not None:
                 ops.colsum(dd1_16, G(sk.bias))
+            G.done(sk)
             T["dskip"], _ = ops.conv_gemm(dd1_16, P["skip_conv"]["wT"], d[0], want="f32")
         dd1 = run_stack_bwd(dd1, tape, T["s_ref"], G)
         dd1 = run_stack_bwd(dd1, tape, T["s_dec1"], G)
@@ -317,6 +328,7 @@ class RestormerTrainMixin:
             ops.wgrad(dy16, cat16, G(conv.weight))
             if conv.bias is not None:
                 ops.colsum(dy16, G(conv.bias))
+            G.done(conv)
             _, dcat = ops.conv_gemm(dy16, P[red]["wT"], 2 * Cn, Ci=Cn)
             dx = up_bwd(dcat[..., :Cn], P[up], T[key]["x"], G)
             return dx, dcat[..., Cn:]

@@ -122,13 +122,53 @@ class DDPStep:
                 out.append((gi, s, min(g.n, s + self.bucket_elems)))
         return out[::-1]
 
+    # Overlap with the backward pass.  The explicit backward schedule finishes the parameters in (roughly) reverse
+    # registration order, i.e. from the END of each flat buffer towards its start.  The schedule reports finished modules /
+    # parameters (``mark_done``); whenever the finished TAIL of a group's buffer has grown by a bucket, that slice is
+    # all-reduced at once.  ``dist.all_reduce(async_op=True)`` orders the collective after the kernels already queued on
+    # the current stream and runs it on the process group's own stream, so it overlaps the rest of the backward; what is
+    # left (and everything, when nothing was reported) goes out in ``all_reduce_gradients``.
+    def begin_backward(self):
+        self._done = set()
+        self._tail = [len(g.params) - 1 for g in self.groups]      # index of the last parameter not yet sent
+        self._hi = [g.n for g in self.groups]                      # everything in [hi, n) has been sent
+        self._early = []
+
+    def mark_done(self, obj):
+        """obj: an nn.Module or a parameter whose gradient is final for this step."""
+        if self.world == 1 or not hasattr(self, "_done"):
+            return
+        params = [obj] if isinstance(obj, torch.Tensor) else list(obj.parameters())
+        self._done.update(id(p) for p in params)
+        for gi, g in enumerate(self.groups):
+            t = self._tail[gi]
+            while t >= 0 and id(g.params[t]) in self._done:
+                t -= 1
+            lo = g.offsets[t + 1] if t + 1 < len(g.params) else g.n
+            if self._hi[gi] - lo >= self.bucket_elems or (t < 0 and lo < self._hi[gi]):
+                self._tail[gi] = t
+                self._send(gi, lo, self._hi[gi], self._early)
+                self._hi[gi] = lo
+
+    def _send(self, gi, lo, hi, works):
+        g = self.groups[gi]
+        for s in range(hi, lo, -self.bucket_elems):
+            a = max(lo, s - self.bucket_elems)
+            works.append(dist.all_reduce(g.grad[a:s], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+
     def all_reduce_gradients(self):
-        """SUM all-reduce of every bucket (async); averaging is folded into the optimizer kernel."""
+        """SUM all-reduce of every bucket not sent yet (async); averaging is folded into the optimizer kernel.  Returns
+        all outstanding works of this step, the ones issued during the backward included."""
         if self.world == 1:
             return []
-        works = []
-        for gi, s, e in self.buckets():
-            works.append(dist.all_reduce(self.groups[gi].grad[s:e], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
+        if not hasattr(self, "_done"):
+            self.begin_backward()
+        works = self._early
+        for gi in range(len(self.groups)):
+            if self._hi[gi] > 0:
+                self._send(gi, 0, self._hi[gi], works)
+                self._hi[gi] = 0
+        del self._done
         return works
 
     # ---- optimizer tail ------------------------------------------------------------------------------------------
@@ -336,7 +376,8 @@ class RefGuidedTrainer:
         lib.call("tdr_l1_loss_grad", C.c_void_p(out.data_ptr()), C.c_void_p(gt.data_ptr()), out.numel(), self.loss_weight,
                  C.c_void_p(dout.data_ptr()), C.c_void_p(self._loss.data_ptr()), C.c_void_p(self._partial.data_ptr()),
                  _stream())
-        net._backward(state, dout, Grads(direct=True))
+        self.engine.begin_backward()
+        net._backward(state, dout, Grads(direct=True, on_done=self.engine.mark_done))
         works = self.engine.all_reduce_gradients()
         self.engine.step(works, frozen=frozen)
         self.engine.reduce_loss_async(self._loss)
