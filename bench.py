@@ -325,7 +325,8 @@ def _run_b200(args, out):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))   # a mismatch must not hang
     lib.check(lib.load().tdr_check_device(), "tdr_check_device")
 
     cfg = CONFIGS[args.config]
@@ -448,10 +449,14 @@ def _run_b200(args, out):
         train_launches = ops.PROF.launches - l0
         barrier()
         loss_val = tr.current_loss()
+        # per-launch profile of one more step.  EVERY rank runs the step (it contains the gradient all-reduce); only rank 0
+        # records the events
         if rank == 0:
             ops.PROF.start()
-            tr.optimize_parameters()
+        tr.optimize_parameters()
+        if rank == 0:
             tprof = ops.PROF.stop()
+        barrier()
         train = dict(ms=ms_train, launches=train_launches, loss=loss_val,
                      peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30)
         # the reference's step also selects the reference crop with a frozen DINOv2 ViT-B/14 every iteration
