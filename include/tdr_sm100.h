@@ -242,6 +242,13 @@ int tdr_softmax_rows(const float* s, long long ld, long long rows, int n, float 
 /* vt[b, h, d, t] = qkv[b, t, voff + h*hd + d], t padded with zeros to n_pad (K-major operand of p.v) */
 int tdr_vit_transpose_v(const void* qkv_bf16, long long ld, int B, int N, int heads, int hd, int voff, void* vt_bf16,
                         int n_pad, cudaStream_t stream);
+/* Fused multi-head self-attention of the frozen ViTs (models/dino/attention.py:52-68; transformers CLIPAttention as called
+ * from scripts/train/main_train_tr_mapping.py:780): out[b, i, h*hd:(h+1)*hd] = softmax_j(scale q_i.k_j) v_j, one launch per
+ * layer.  qkv: bf16 rows [B, N, ld] holding q | k | v at columns 0 | D | 2D (D = heads * hd); out: bf16 rows [B, N, out_ld].
+ * fp32 scores / online softmax / accumulation (tcgen05 + TMEM), nothing of size N x N touches HBM.  hd in {16, 32, 64, 80}. */
+int tdr_vit_attention_supported(int hd);
+int tdr_vit_attention(const void* qkv_bf16, long long ld, int B, int N, int heads, int hd, float scale, void* out_bf16,
+                      long long out_ld, cudaStream_t stream);
 /* Reference-crop selection (models/image_restoration_ref_model.py:215-247): crop (origin[k] = (image, y0, x0), size
  * crop_h x crop_w) + bilinear resize (align_corners=False) of NCHW fp32 images in one pass, and the cosine similarity
  * between one query feature row per sample and n candidate rows. */

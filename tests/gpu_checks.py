@@ -884,6 +884,18 @@ def check_vit():
     ref = torch.stack([F.interpolate(img[b:b + 1, :, y:y + 32, x:x + 32], size=(28, 42), mode="bilinear")[0]
                        for b, y, x in org.tolist()])
     out.append(result("crop_resize", ops.crop_resize(img.to(DEV), org.to(DEV), (32, 32), (28, 42)), ref, 1e-5))
+    # fused attention (tdr_vit_attention) against fp32 torch on the same bf16-rounded q, k, v: the head dims / token counts
+    # of the towers (hd 64, N 1370; hd 80, N 257), single-tile and ragged key / query tiles, strided (padded) rows
+    for name, (B, N, heads, hd, pad) in dict(dino=(2, 1370, 12, 64, 0), clip=(3, 257, 16, 80, 0), one_tile=(2, 128, 2, 64, 0),
+                                             ragged=(2, 129, 3, 32, 8), tiny=(3, 5, 4, 16, 0), two_tiles=(1, 256, 2, 80, 16)).items():
+        D = heads * hd
+        buf = torch.zeros(B, 1, N, 3 * D + pad, dtype=BF16)
+        buf[..., :3 * D] = (rnd(B, 1, N, 3 * D, seed=N + hd) * 1.5).to(BF16)
+        qkv = buf.to(DEV)[..., :3 * D]
+        o = ops.vit_attention(qkv, heads, hd, hd ** -0.5)
+        q, k, v = [t.reshape(B, N, heads, hd).permute(0, 2, 1, 3) for t in buf[:, 0, :, :3 * D].float().split(D, -1)]
+        want = (torch.softmax(q @ k.transpose(-1, -2) * hd ** -0.5, -1) @ v).permute(0, 2, 1, 3).reshape(B, 1, N, D)
+        out.append(result(f"vit_attention_{name}", o, want, 1e-2))
     # towers
     meta, gold = _golden("dino_vit_tiny")
     net = VB.DinoVisionTransformer(**meta["cfg"])

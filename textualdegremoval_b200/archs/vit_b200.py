@@ -12,11 +12,12 @@
 
 Every dense contraction (patch embedding, qkv/proj/fc1/fc2, q.k^T, p.v, mapper linears) is ``tdr_conv_gemm`` on the flat
 ``[1 x tokens x channels]`` view (tcgen05); LayerNorm is ``tdr_rownorm``; softmax rows, V transposition, token assembly,
-crop/resize, cosine and token-mean are small dedicated kernels.  Attention materialises fp32 scores (first version; a
-fused flash-style kernel is the planned replacement).  This file is not ``*_arch.py``: the restoration arch registry
+crop/resize, cosine and token-mean are small dedicated kernels.  Attention is ``tdr_vit_attention`` (one fused tcgen05
+flash-attention launch per layer; head dims 16/32/64/80); other head dims fall back to the materialised-score schedule.  This file is not ``*_arch.py``: the restoration arch registry
 does not scan it, exactly as the reference imports these classes directly.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -26,6 +27,8 @@ from .. import ops
 from ..lib import TdrError
 
 F32, BF16 = torch.float32, torch.bfloat16
+# A/B knob: keep the first-version schedule (fp32 scores through HBM) instead of tdr_vit_attention
+_MATERIALISED = os.environ.get("TDR_VIT_MATERIALISED_ATTENTION", "0") not in ("", "0")
 
 
 def _f(t):
@@ -45,6 +48,8 @@ def attention(qkv, heads, D):
     """qkv: bf16 [B,1,N,3D] living in a buffer with >= 8 spare rows after it.  softmax(q k^T / sqrt(hd)) v -> bf16 [B,1,N,D]."""
     B, _, N, _ = qkv.shape
     hd = D // heads
+    if ops.vit_attention_supported(hd) and not _MATERIALISED:
+        return ops.vit_attention(qkv, heads, hd, hd ** -0.5)          # one fused launch (tcgen05 flash attention)
     n_pad = ops.round_up(N, 8)
     dev = qkv.device
     scores = torch.empty((heads, B, 1, N, n_pad), dtype=F32, device=dev)

@@ -646,6 +646,21 @@ def vit_transpose_v(qkv, heads, hd, voff, n_pad):
     return vt
 
 
+def vit_attention_supported(hd):
+    return bool(lib.load().tdr_vit_attention_supported(int(hd)))
+
+
+def vit_attention(qkv, heads, hd, scale, out=None):
+    """Fused softmax(scale q k^T) v over bf16 qkv rows [B,1,N,3D] -> bf16 [B,1,N,D] (tdr_vit_attention, one launch)."""
+    B, _, N, _ = qkv.shape
+    D = heads * hd
+    if out is None:
+        out = torch.empty((B, 1, N, D), dtype=BF16, device=qkv.device)
+    _call("tdr_vit_attention", _p(qkv), _ld(qkv), B, N, heads, hd, float(scale), _p(out), _ld(out), _stream(),
+          nbytes=B * N * D * 2 * 4)
+    return out
+
+
 def mean_tokens(x32, t0, n, out, accumulate=False):
     """x32 fp32 [B,1,T,C]; out fp32 [B, C] view (row stride out.stride(0))."""
     B, _, T, Cc = x32.shape
