@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
     for (int t = 0; t < ntiles; ++t) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint32_t sb = sa + pl.boxes_m * kBoxBytes;
         // descriptors are built once per stage and advanced through their start-address field (16 B units): the

@@ -243,6 +243,18 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
+// One lane of the (converged) warp, chosen by the hardware.  Unlike `lane == 0` the compiler knows that exactly one thread
+// runs the guarded region, so register operands of tcgen05.mma / TMA instructions move to uniform registers with a plain
+// R2UR instead of an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop per instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc]; one thread issues for the CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {

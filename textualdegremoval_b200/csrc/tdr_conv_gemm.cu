@@ -71,6 +71,7 @@ struct ConvGemmArgs {
   int halo_bytes;               // bytes of one haloed A tile: (TH + (KH-1)*dil) rows x 16 px x 128 B
   int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
   int epi_bufs;                 // staging buffers per epilogue warp (1 or 2; 4 with the fused LayerNorm)
+  int alt_items;                // TMA epilogue (no LN): the two warp groups take alternate items
   // fused LayerNorm of the output rows (variant bit 3): ln_out = LN(out) in bf16 through map_o2
   int in_fp16;                  // A and W operands are IEEE fp16 (MASA feature encoder)
   int out_fp16;                 // the 16-bit output is IEEE fp16
@@ -158,7 +159,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       for (int i = 0; i < 24; ++i) mbar_init(&lnbar[i], 1);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiWarps);
+      mbar_init(&tempty[i], (kTma && !kLN && a.alt_items) ? kEpiWarps / 2 : kEpiWarps);
     }
     mbar_fence_init();
   }
@@ -174,7 +175,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       if (a.halo) {                            // resident weights: every (chunk, tap) slice once, one barrier
@@ -251,7 +252,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
               mbar_wait(&full[st], ph);
               tc_fence_after();
             }
-            if (lane == 0) {
+            if (elect_one()) {
               const uint64_t da = umma_desc_sw128(smem_u32(smem_a + st * kABytes), 0, 1024);
               const uint64_t db = umma_desc_sw128(smem_u32(smem_b + (nt * a.kchunks + kc) * b_bytes), 0, 1024);
 #pragma unroll
@@ -279,7 +280,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         for (int kc = 0; kc < a.kchunks; ++kc) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             // tap (ky, kx) = the same haloed tile shifted by (ky*dil) rows of 16 px and (kx*dil) px; every 8-pixel
             // UMMA row group is one image-row segment, groups are 2048 B apart (16-px row pitch).  The 128 B
             // swizzle is a function of the absolute smem address, so 128 B-aligned shifted starts need no fix-up
@@ -313,7 +314,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * kABytes), 0, 1024);
           const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * b_bytes), 0, 1024);
 #pragma unroll
@@ -359,6 +360,9 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     for (;; ++it) {
       int mt, nt;
       if (!conv_item(a, it, mt, nt)) break;
+      // TMA epilogue without LayerNorm: the two warps of a TMEM lane quadrant take ALTERNATE items (each does all the
+      // sub-blocks of its items) instead of splitting every item, so that their fence / store / barrier latencies overlap
+      if (kTma && !kLN && a.alt_items && ((it & 1) != half)) continue;
       const int acc = it % a.nacc;
       const uint32_t acc_phase = (it / a.nacc) & 1;
       const int b = mt / tiles_per_img;
@@ -525,12 +529,13 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         const int box_w = a.TW < 32 ? a.TW : 32;                 // pixels per staged image row
         const int tx0 = (r % a.tiles_x) * a.TW + (a.TW > 32 ? quad * 32 : 0);
         const int ty0 = (r / a.tiles_x) * a.TH + (a.TW > 32 ? 0 : quad * (32 / box_w));
+        const int sb0 = a.alt_items ? 0 : half, sbs = a.alt_items ? 1 : 2;   // my sub-blocks: sb0, sb0 + sbs, ...
         int n_my = 0;
-        for (int sb = half; sb < nsb && nt * a.BN + sb * sbc < a.Co; sb += 2) ++n_my;
+        for (int sb = sb0; sb < nsb && nt * a.BN + sb * sbc < a.Co; sb += sbs) ++n_my;
         // lane 0 only: queue the residual tile(s) of my k-th sub-block
         auto issue_res = [&](int k) {
           const int j = dbuf ? (k & 1) : 0;
-          const int col = nt * a.BN + (half + 2 * k) * sbc;
+          const int col = nt * a.BN + (sb0 + sbs * k) * sbc;
           tma_store_wait_read();                                 // earlier stores have finished reading the buffers
           mbar_expect_tx(&rb[j], has_r1 ? 2 * kEpiStageBytes : kEpiStageBytes);
           tma_load_4d(buf + j * kEpiStageBytes, &map_r2, &rb[j], col, tx0, ty0, b);
@@ -546,7 +551,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
           // staging buffer: residual tiles were queued into (k & 1); without residuals consecutive stores simply
           // alternate (across tiles too), so wait_group.read 1 always covers the buffer about to be overwritten
           const int j = has_r2 ? (dbuf ? (k & 1) : 0) : (a.epi_bufs > 1 ? (store_cnt++ % a.epi_bufs) : 0);
-          const int cs = (half + 2 * k) * sbc;
+          const int cs = (sb0 + sbs * k) * sbc;
           uint8_t* const stg = buf + j * kEpiStageBytes;
           uint32_t raw[4][16];
 #pragma unroll
@@ -1086,6 +1091,12 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   uint32_t cols = 32;
   while (cols < (uint32_t)(a.nacc * a.BN)) cols <<= 1;
   a.tmem_cols = cols;
+  // (BN > 192 leaves two accumulators: one per group, and 4 sub-blocks per warp and item measured 3 % slower there)
+  a.alt_items = (a.epi_mode == 1 && !want_ln && a.BN <= 192) ? 1 : 0;
+  if (const char* e = getenv("TDR_CONV_ALT")) {                                  // A/B knob: 0 off, 2 also for BN > 192
+    const int v = atoi(e);
+    a.alt_items = (a.epi_mode == 1 && !want_ln && v != 0 && (a.BN <= 192 || v == 2)) ? 1 : 0;
+  }
 
   if (d->impl == 1) {
     const long long total = (long long)a.B * OH * OW * a.Co;

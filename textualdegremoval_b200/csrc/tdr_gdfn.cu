@@ -100,7 +100,7 @@ gdfn_tail_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
@@ -132,7 +132,7 @@ gdfn_tail_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         mbar_wait_sleep(&a_full[buf], (cnt >> 1) & 1, 100);   // gated tile written (the compute warps waited on full[stage])
         mbar_wait(&full[stage], phase);                // W slice visible to this thread too
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint64_t da = umma_desc_sw128(smem_u32(atile + buf * kATile), 0, 1024);
           const uint64_t db = umma_desc_sw128(smem_u32(ring + stage * a.stage_bytes + 2 * kHaloBytes), 0, 1024);
 #pragma unroll

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < ntiles; ++t) {
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
     for (int t = 0; t < ntiles; ++t) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sq = smem_u32(smem + stage * stage_bytes);
         const uint32_t sk = sq + pl.boxes * kBoxBytes;
         const uint64_t dq0 = umma_desc_sw128(sq, kBoxBytes, 1024), dk0 = umma_desc_sw128(sk, kBoxBytes, 1024);

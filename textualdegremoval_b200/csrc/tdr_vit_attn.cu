@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(128, HD <= 64 ? 2 : 1) vit_attn_kernel(const _
     umma_commit(bar_s);
   };
 
-  if (tid == 0) {
+  const bool leader = warp == 0 && elect_one();           // one lane of warp 0 issues every TMA load and MMA
+  if (leader) {
     load_tile(sQ, bar_q, h * HD, q0);
     load_tile(sK, bar_k, a.D + h * HD, 0);
     load_tile(sV, bar_v, 2 * a.D + h * HD, 0);
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(128, HD <= 64 ? 2 : 1) vit_attn_kernel(const _
     const int valid = min(kKT, a.N - j * kKT);
     mbar_wait(bar_s, j & 1);
     tc_fence_after();
-    if (tid == 0 && j + 1 < nkv) load_tile(sK, bar_k, a.D + h * HD, (j + 1) * kKT);   // S_j is done with K_j
+    if (leader && j + 1 < nkv) load_tile(sK, bar_k, a.D + h * HD, (j + 1) * kKT);   // S_j is done with K_j
     float alpha = 1.f;
     if (active) {
       // pass 1: row maximum over the valid keys of the tile
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(128, HD <= 64 ? 2 : 1) vit_attn_kernel(const _
     fence_proxy_async();                                    // P (generic proxy) -> tcgen05.mma (async proxy)
     tc_fence_before();
     __syncthreads();                                        // P complete, every thread is done reading S_j
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       mbar_wait(bar_v, j & 1);
       const int ksteps = (valid + 15) >> 4;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(128, HD <= 64 ? 2 : 1) vit_attn_kernel(const _
     __syncwarp();
     mbar_wait(bar_o, j & 1);
     tc_fence_after();
-    if (tid == 0 && j + 1 < nkv) load_tile(sV, bar_v, 2 * a.D + h * HD, (j + 1) * kKT);   // P V_j is done with V_j
+    if (leader && j + 1 < nkv) load_tile(sV, bar_v, 2 * a.D + h * HD, (j + 1) * kKT);   // P V_j is done with V_j
     if (active) {
 #pragma unroll
       for (int c0 = 0; c0 < HD; c0 += 16) {
