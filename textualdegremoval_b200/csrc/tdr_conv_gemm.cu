@@ -72,6 +72,9 @@ struct ConvGemmArgs {
   int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
   int epi_bufs;                 // staging buffers per epilogue warp (1 or 2; 4 with the fused LayerNorm)
   int alt_items;                // TMA epilogue (no LN): the two warp groups take alternate items
+  // division by n_tiles / tiles per image / tiles_x as multiply-high + shift (every role recomputes its item's
+  // coordinates per item; the epilogue warps spent 13 % of their samples in the integer-division sequences)
+  uint32_t fd_nt_m, fd_nt_s, fd_tpi_m, fd_tpi_s, fd_tx_m, fd_tx_s;
   // fused LayerNorm of the output rows (variant bit 3): ln_out = LN(out) in bf16 through map_o2
   int in_fp16;                  // A and W operands are IEEE fp16 (MASA feature encoder)
   int out_fp16;                 // the 16-bit output is IEEE fp16
@@ -84,16 +87,28 @@ struct ConvGemmArgs {
 // it-th work item of this CTA -> (pixel tile, n tile).  by_pixel: CTA c owns pixel tiles c, c + grid, ... and walks ALL n tiles
 // of each in turn (balanced even when the n tiles are unequal, and the A tile is re-used from L2); otherwise (fewer pixel
 // tiles than SMs: ViT / mapper linears) items are dealt round-robin so that every SM gets work.
+// n / d for 0 <= n < 2^31 with (m, s) from fast_div_setup(d)
+__device__ __forceinline__ int fdiv(int n, uint32_t m, uint32_t s) {
+  return m ? (int)(__umulhi((uint32_t)n, m) >> s) : n;
+}
 __device__ __forceinline__ bool conv_item(const ConvGemmArgs& a, int it, int& mt, int& nt) {
   if (a.by_pixel) {
-    mt = blockIdx.x + (it / a.n_tiles) * gridDim.x;
-    nt = it % a.n_tiles;
+    const int q = fdiv(it, a.fd_nt_m, a.fd_nt_s);
+    mt = blockIdx.x + q * gridDim.x;
+    nt = it - q * a.n_tiles;
     return mt < a.m_tiles;
   }
   const int tile = blockIdx.x + it * gridDim.x;
-  mt = tile / a.n_tiles;
-  nt = tile % a.n_tiles;
+  mt = fdiv(tile, a.fd_nt_m, a.fd_nt_s);
+  nt = tile - mt * a.n_tiles;
   return tile < a.total_tiles;
+}
+// pixel tile -> (image, tile row, tile column)
+__device__ __forceinline__ void conv_tile_coords(const ConvGemmArgs& a, int mt, int tiles_per_img, int& b, int& ty, int& tx) {
+  b = fdiv(mt, a.fd_tpi_m, a.fd_tpi_s);
+  const int r = mt - b * tiles_per_img;
+  ty = fdiv(r, a.fd_tx_m, a.fd_tx_s);
+  tx = r - ty * a.tiles_x;
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -194,10 +209,10 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         int mt, nt;
         if (!conv_item(a, sq, mt, nt)) break;
         if (a.resident_b && nt != 0) continue;   // the A chunks of a pixel tile are loaded once for all its n tiles
-        const int b = mt / tiles_per_img;
-        const int r = mt % tiles_per_img;
-        const int oy0 = (r / a.tiles_x) * a.TH;
-        const int ox0 = (r % a.tiles_x) * a.TW;
+        int b, tyi, txi;
+        conv_tile_coords(a, mt, tiles_per_img, b, tyi, txi);
+        const int oy0 = tyi * a.TH;
+        const int ox0 = txi * a.TW;
         int img = b, org_y = 0, org_x = 0;
         if (a.origin) { img = a.origin[3 * b]; org_y = a.origin[3 * b + 1]; org_x = a.origin[3 * b + 2]; }
         if (a.halo) {
@@ -344,10 +359,11 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     auto ln_prefetch = [&](int t) {
       int mt2, nt2;
       if (!conv_item(a, t, mt2, nt2)) return;
-      const int b2 = mt2 / tiles_per_img, r2 = mt2 % tiles_per_img;
+      int b2, ty2, tx2;
+      conv_tile_coords(a, mt2, tiles_per_img, b2, ty2, tx2);
       const int bw = a.TW < 32 ? a.TW : 32;
-      const int tx = (r2 % a.tiles_x) * a.TW + (a.TW > 32 ? quad * 32 : 0);
-      const int ty = (r2 / a.tiles_x) * a.TH + (a.TW > 32 ? 0 : quad * (32 / bw));
+      const int tx = tx2 * a.TW + (a.TW > 32 ? quad * 32 : 0);
+      const int ty = ty2 * a.TH + (a.TW > 32 ? 0 : quad * (32 / bw));
       const int set = t & 1, n_sb2 = (a.Co + 31) >> 5;
       for (int sb = half; sb < n_sb2; sb += 2) {
         uint64_t* const bar = &lnbar[quad * 6 + set * 3 + sb];
@@ -365,10 +381,10 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
       if (kTma && !kLN && a.alt_items && ((it & 1) != half)) continue;
       const int acc = it % a.nacc;
       const uint32_t acc_phase = (it / a.nacc) & 1;
-      const int b = mt / tiles_per_img;
-      const int r = mt % tiles_per_img;
-      const int oy = (r / a.tiles_x) * a.TH + my;
-      const int ox = (r % a.tiles_x) * a.TW + mx;
+      int b, tyi, txi;
+      conv_tile_coords(a, mt, tiles_per_img, b, tyi, txi);
+      const int oy = tyi * a.TH + my;
+      const int ox = txi * a.TW + mx;
       const bool valid = (oy < a.OH) && (ox < a.OW);
       const long long pix = ((long long)b * a.OH + oy) * a.OW + ox;
       const float rs = (valid && a.rowscale) ? a.rowscale[pix] : 1.f;
@@ -391,8 +407,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         uint64_t* const rb = lnbar + quad * 6 + set * 3;
         const bool plain = !a.bias && !a.rowscale && !a.act && alpha == 1.f;
         const int box_w = a.TW < 32 ? a.TW : 32;
-        const int tx0 = (r % a.tiles_x) * a.TW + (a.TW > 32 ? quad * 32 : 0);
-        const int ty0 = (r / a.tiles_x) * a.TH + (a.TW > 32 ? 0 : quad * (32 / box_w));
+        const int tx0 = txi * a.TW + (a.TW > 32 ? quad * 32 : 0);
+        const int ty0 = tyi * a.TH + (a.TW > 32 ? 0 : quad * (32 / box_w));
         const int n_sb = (a.Co + 31) >> 5;
         mbar_wait(&tfull[acc], acc_phase);
         tc_fence_after();
@@ -527,8 +543,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         const bool dbuf = a.epi_bufs == 2 && !has_r1;
         const bool plain = !a.bias && !a.rowscale && !a.act && alpha == 1.f;
         const int box_w = a.TW < 32 ? a.TW : 32;                 // pixels per staged image row
-        const int tx0 = (r % a.tiles_x) * a.TW + (a.TW > 32 ? quad * 32 : 0);
-        const int ty0 = (r / a.tiles_x) * a.TH + (a.TW > 32 ? 0 : quad * (32 / box_w));
+        const int tx0 = txi * a.TW + (a.TW > 32 ? quad * 32 : 0);
+        const int ty0 = tyi * a.TH + (a.TW > 32 ? 0 : quad * (32 / box_w));
         const int sb0 = a.alt_items ? 0 : half, sbs = a.alt_items ? 1 : 2;   // my sub-blocks: sb0, sb0 + sbs, ...
         int n_my = 0;
         for (int sb = sb0; sb < nsb && nt * a.BN + sb * sbc < a.Co; sb += sbs) ++n_my;
@@ -891,6 +907,15 @@ __global__ void conv_gemm_simt_kernel(const bf16* __restrict__ in, long long in_
 
 }  // namespace
 
+// (m, s) with n / d == umulhi(n, m) >> s for every 0 <= n < 2^31; m == 0 encodes d == 1
+static void fast_div_setup(int d, uint32_t* m, uint32_t* s) {
+  if (d <= 1) { *m = 0; *s = 0; return; }
+  uint32_t l = 0;
+  while ((1u << l) < (uint32_t)d) ++l;                       // ceil(log2 d)
+  *m = (uint32_t)((((uint64_t)1 << (31 + l)) + (uint64_t)d - 1) / (uint64_t)d);
+  *s = l - 1;
+}
+
 // fused output LayerNorm: what the kLN epilogue covers (see include/tdr_sm100.h)
 static bool conv_ln_ok(const tdr_conv_gemm_desc* d) {
   return d && (d->ln_mode == 1 || d->ln_mode == 2) && d->impl == 0 && d->store_mode == 0 && d->KH == 1 && d->KW == 1 &&
@@ -1091,12 +1116,12 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   uint32_t cols = 32;
   while (cols < (uint32_t)(a.nacc * a.BN)) cols <<= 1;
   a.tmem_cols = cols;
-  // (BN > 192 leaves two accumulators: one per group, and 4 sub-blocks per warp and item measured 3 % slower there)
-  a.alt_items = (a.epi_mode == 1 && !want_ln && a.BN <= 192) ? 1 : 0;
-  if (const char* e = getenv("TDR_CONV_ALT")) {                                  // A/B knob: 0 off, 2 also for BN > 192
-    const int v = atoi(e);
-    a.alt_items = (a.epi_mode == 1 && !want_ln && v != 0 && (a.BN <= 192 || v == 2)) ? 1 : 0;
-  }
+  // (same-box bench step: 50.92 ms split items, 50.35 ms alternate for BN <= 192 only, 50.11 ms alternate everywhere)
+  a.alt_items = (a.epi_mode == 1 && !want_ln) ? 1 : 0;
+  fast_div_setup(a.n_tiles, &a.fd_nt_m, &a.fd_nt_s);
+  fast_div_setup(a.tiles_y * a.tiles_x, &a.fd_tpi_m, &a.fd_tpi_s);
+  fast_div_setup(a.tiles_x, &a.fd_tx_m, &a.fd_tx_s);
+  if (const char* e = getenv("TDR_CONV_ALT")) a.alt_items = a.alt_items && atoi(e) != 0;   // A/B knob
 
   if (d->impl == 1) {
     const long long total = (long long)a.B * OH * OW * a.Co;
