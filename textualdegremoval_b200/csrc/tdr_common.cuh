@@ -36,6 +36,14 @@ void tdr_set_error(const char* fmt, ...);
 #define TDR_CHECK_LAUNCH() TDR_CHECK_CUDA(cudaGetLastError())
 
 static inline int tdr_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+// (m, s) with n / d == __umulhi(n, m) >> s for every 0 <= n < 2^31; m == 0 encodes d == 1 (quotient = n)
+static inline void tdr_fast_div_setup(int d, uint32_t* m, uint32_t* s) {
+  if (d <= 1) { *m = 0; *s = 0; return; }
+  uint32_t l = 0;
+  while ((1u << l) < (uint32_t)d) ++l;                       // ceil(log2 d)
+  *m = (uint32_t)((((uint64_t)1 << (31 + l)) + (uint64_t)d - 1) / (uint64_t)d);
+  *s = l - 1;
+}
 
 int tdr_num_sms();
 

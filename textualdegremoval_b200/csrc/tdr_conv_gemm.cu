@@ -87,7 +87,7 @@ struct ConvGemmArgs {
 // it-th work item of this CTA -> (pixel tile, n tile).  by_pixel: CTA c owns pixel tiles c, c + grid, ... and walks ALL n tiles
 // of each in turn (balanced even when the n tiles are unequal, and the A tile is re-used from L2); otherwise (fewer pixel
 // tiles than SMs: ViT / mapper linears) items are dealt round-robin so that every SM gets work.
-// n / d for 0 <= n < 2^31 with (m, s) from fast_div_setup(d)
+// n / d for 0 <= n < 2^31 with (m, s) from tdr_fast_div_setup(d)
 __device__ __forceinline__ int fdiv(int n, uint32_t m, uint32_t s) {
   return m ? (int)(__umulhi((uint32_t)n, m) >> s) : n;
 }
@@ -907,15 +907,6 @@ __global__ void conv_gemm_simt_kernel(const bf16* __restrict__ in, long long in_
 
 }  // namespace
 
-// (m, s) with n / d == umulhi(n, m) >> s for every 0 <= n < 2^31; m == 0 encodes d == 1
-static void fast_div_setup(int d, uint32_t* m, uint32_t* s) {
-  if (d <= 1) { *m = 0; *s = 0; return; }
-  uint32_t l = 0;
-  while ((1u << l) < (uint32_t)d) ++l;                       // ceil(log2 d)
-  *m = (uint32_t)((((uint64_t)1 << (31 + l)) + (uint64_t)d - 1) / (uint64_t)d);
-  *s = l - 1;
-}
-
 // fused output LayerNorm: what the kLN epilogue covers (see include/tdr_sm100.h)
 static bool conv_ln_ok(const tdr_conv_gemm_desc* d) {
   return d && (d->ln_mode == 1 || d->ln_mode == 2) && d->impl == 0 && d->store_mode == 0 && d->KH == 1 && d->KW == 1 &&
@@ -1118,9 +1109,9 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   a.tmem_cols = cols;
   // (same-box bench step: 50.92 ms split items, 50.35 ms alternate for BN <= 192 only, 50.11 ms alternate everywhere)
   a.alt_items = (a.epi_mode == 1 && !want_ln) ? 1 : 0;
-  fast_div_setup(a.n_tiles, &a.fd_nt_m, &a.fd_nt_s);
-  fast_div_setup(a.tiles_y * a.tiles_x, &a.fd_tpi_m, &a.fd_tpi_s);
-  fast_div_setup(a.tiles_x, &a.fd_tx_m, &a.fd_tx_s);
+  tdr_fast_div_setup(a.n_tiles, &a.fd_nt_m, &a.fd_nt_s);
+  tdr_fast_div_setup(a.tiles_y * a.tiles_x, &a.fd_tpi_m, &a.fd_tpi_s);
+  tdr_fast_div_setup(a.tiles_x, &a.fd_tx_m, &a.fd_tx_s);
   if (const char* e = getenv("TDR_CONV_ALT")) a.alt_items = a.alt_items && atoi(e) != 0;   // A/B knob
 
   if (d->impl == 1) {

@@ -245,7 +245,18 @@ struct DwArgs {
   const float* dg_add;     // optional per-sample term [B][Cout] added to dg (SCA pool gradient)
   bf16* y_out;             // GATE == 1, optional (training): also store the pre-gate halves [a | b] (2 * Cout channels)
   long long y_ld;
+  uint32_t fd_img_m, fd_img_s, fd_tx_m, fd_tx_s;   // n / (tiles_y * tiles_x), n / tiles_x as umulhi + shift
 };
+
+__device__ __forceinline__ int dw_fdiv(int n, uint32_t m, uint32_t s) { return m ? (int)(__umulhi((uint32_t)n, m) >> s) : n; }
+// spatial tile index -> (image, first row, first column)
+__device__ __forceinline__ void dw_tile_coords(const DwArgs& a, int sp, int& b, int& y0, int& x0) {
+  b = dw_fdiv(sp, a.fd_img_m, a.fd_img_s);
+  const int r = sp - b * (a.tiles_y * a.tiles_x);
+  const int ty = dw_fdiv(r, a.fd_tx_m, a.fd_tx_s);
+  y0 = ty * kDwRows;
+  x0 = (r - ty * a.tiles_x) * kDwCols;
+}
 
 // GATE: 0 plain, 1 gated forward (a.gate 1 = GELU gate, 2 = SimpleGate), 3 = 1 + the pre-gate tensor is stored too
 // (training forward; a separate instantiation so that the inference kernel is untouched), 2 gate BACKWARD: recomputes the two depthwise
@@ -279,10 +290,8 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
   const int grp = blockIdx.x / a.chunks, ngrp = gridDim.x / a.chunks;
   const int n_spatial = a.B * a.tiles_y * a.tiles_x;
   auto issue = [&](int sp, int stage) {                    // thread 0 only
-    int r = sp;
-    const int b = r / (a.tiles_y * a.tiles_x);
-    r %= a.tiles_y * a.tiles_x;
-    const int y0 = (r / a.tiles_x) * kDwRows, x0 = (r % a.tiles_x) * kDwCols;
+    int b, y0, x0;
+    dw_tile_coords(a, sp, b, y0, x0);
     uint8_t* dst = dsm + stage * kDwStageBytes;
     mbar_expect_tx(&full[stage], NH * BOX_BYTES);
 #pragma unroll
@@ -317,10 +326,8 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
   for (int sp = grp; sp < n_spatial; sp += ngrp, ++it) {
     const int stage = it & 1;
     if (tid == 0 && sp + ngrp < n_spatial) issue(sp + ngrp, stage ^ 1);
-    int r = sp;
-    const int b = r / (a.tiles_y * a.tiles_x);
-    r %= a.tiles_y * a.tiles_x;
-    const int y0 = (r / a.tiles_x) * kDwRows, x0 = (r % a.tiles_x) * kDwCols;
+    int b, y0, x0;
+    dw_tile_coords(a, sp, b, y0, x0);
     mbar_wait(&full[stage], (it >> 1) & 1);
     const uint8_t* tile_s = dsm + stage * kDwStageBytes + xl * PIX_PITCH + cgi * (VEC * 2);
     f2 acc[3][NH][NP];
@@ -850,6 +857,8 @@ static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int
   DwArgs a;
   a.B = B; a.H = H; a.W = W; a.C = C; a.Cout = gate ? C / 2 : C;
   a.tiles_x = tdr_cdiv(W, kDwCols); a.tiles_y = tdr_cdiv(H, kDwRows);
+  tdr_fast_div_setup(a.tiles_y * a.tiles_x, &a.fd_img_m, &a.fd_img_s);
+  tdr_fast_div_setup(a.tiles_x, &a.fd_tx_m, &a.fd_tx_s);
   const int cb = gate ? 32 : 64;
   a.chunks = tdr_cdiv(a.Cout, cb);
   a.total_tiles = B * a.tiles_x * a.tiles_y * a.chunks;
