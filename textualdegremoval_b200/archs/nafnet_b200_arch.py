@@ -270,12 +270,16 @@ class NAFNetRefFusion(GuidedNAFTrainMixin, MasaTrainMixin, MasaMixin, _NAFBase):
         mult = self.padder_size * self.lr_block_size
         h, w = ops.round_up(oh, mult), ops.round_up(ow, mult)
         hr, wr = ops.round_up(ref.shape[2], mult), ops.round_up(ref.shape[3], mult)
-        lq32, ref32 = ops.nchw_to_nhwc(inp, h, w), ops.nchw_to_nhwc(ref, hr, wr)
         E = P["masa_enc"]
-        if (h, w) == (hr, wr):
-            fb, d32 = self._masa_encode(E, torch.cat([lq32, ref32], 0))
+        if (h, w) == (hr, wr):           # shared weights: lq and ref run through the encoder as one batch
+            both = torch.empty((2 * B, h, w, inp.shape[1]), dtype=F32, device=dev)
+            lq32, ref32 = both[:B], both[B:]
+            ops.nchw_to_nhwc_into(inp, h, w, dst32=lq32)
+            ops.nchw_to_nhwc_into(ref, hr, wr, dst32=ref32)
+            fb, d32 = self._masa_encode(E, both)
             f_lq, f_ref, lq_d32, ref_d32 = [t[:B] for t in fb], [t[B:] for t in fb], d32[:B], d32[B:]
         else:
+            lq32, ref32 = ops.nchw_to_nhwc(inp, h, w), ops.nchw_to_nhwc(ref, hr, wr)
             (f_lq, lq_d32), (f_ref, ref_d32) = self._masa_encode(E, lq32), self._masa_encode(E, ref32)
         nlev = len(f_ref)
         chans = [self.width * 2 ** i for i in range(nlev)]

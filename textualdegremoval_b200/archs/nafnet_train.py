@@ -253,11 +253,18 @@ class GuidedNAFTrainMixin(NAFTrainMixin):
         mult = self.padder_size * self.lr_block_size
         h, w = ops.round_up(oh, mult), ops.round_up(ow, mult)
         hr, wr = ops.round_up(ref.shape[2], mult), ops.round_up(ref.shape[3], mult)
-        lq32, ref32 = ops.nchw_to_nhwc(inp, h, w), ops.nchw_to_nhwc(ref, hr, wr)
-        lq16, ref16 = self._image16(inp, h, w), self._image16(ref, hr, wr)
+        if (h, w) == (hr, wr):           # lq and ref share one batch buffer (no concatenation copy)
+            both32 = torch.empty((2 * B, h, w, inp.shape[1]), dtype=F32, device=dev)
+            both16 = torch.zeros((2 * B, h, w, 8), dtype=BF16, device=dev)
+            lq32, ref32, lq16, ref16 = both32[:B], both32[B:], both16[:B], both16[B:]
+            ops.nchw_to_nhwc_into(inp, h, w, dst32=lq32, dst16=lq16)
+            ops.nchw_to_nhwc_into(ref, hr, wr, dst32=ref32, dst16=ref16)
+        else:
+            lq32, ref32 = ops.nchw_to_nhwc(inp, h, w), ops.nchw_to_nhwc(ref, hr, wr)
+            lq16, ref16 = self._image16(inp, h, w), self._image16(ref, hr, wr)
         tape, T = [], dict(hw=(h, w), B=B, inp16=lq16)
         if (h, w) == (hr, wr):
-            fb, d32, et = self._masa_encode_train(E, torch.cat([lq32, ref32], 0), torch.cat([lq16, ref16], 0))
+            fb, d32, et = self._masa_encode_train(E, both32, both16)
             f_lq, f_ref, lq_d32, ref_d32 = [t[:B] for t in fb], [t[B:] for t in fb], d32[:B], d32[B:]
             T["enc"] = [(et, fb)]
         else:

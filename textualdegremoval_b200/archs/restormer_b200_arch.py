@@ -422,13 +422,16 @@ class RestormerRefFusion(GuidedRestormerTrainMixin, MasaTrainMixin, MasaMixin, _
         mult = self.padder_size * self.lr_block_size
         h, w = ops.round_up(oh, mult), ops.round_up(ow, mult)
         hr, wr = ops.round_up(ref_img.shape[2], mult), ops.round_up(ref_img.shape[3], mult)
-        lq32 = ops.nchw_to_nhwc(inp_img, h, w)
-        ref32 = ops.nchw_to_nhwc(ref_img, hr, wr)
         E = P["masa_enc"]
-        if (h, w) == (hr, wr):           # shared weights: run lq and ref as one batch
-            fb, d32 = self._masa_encode(E, torch.cat([lq32, ref32], 0))
+        if (h, w) == (hr, wr):           # shared weights: lq and ref run through the encoder as one batch
+            both = torch.empty((2 * B, h, w, inp_img.shape[1]), dtype=F32, device=dev)
+            lq32, ref32 = both[:B], both[B:]
+            ops.nchw_to_nhwc_into(inp_img, h, w, dst32=lq32)
+            ops.nchw_to_nhwc_into(ref_img, hr, wr, dst32=ref32)
+            fb, d32 = self._masa_encode(E, both)
             f_lq, f_ref, lq_d32, ref_d32 = [t[:B] for t in fb], [t[B:] for t in fb], d32[:B], d32[B:]
         else:
+            lq32, ref32 = ops.nchw_to_nhwc(inp_img, h, w), ops.nchw_to_nhwc(ref_img, hr, wr)
             (f_lq, lq_d32), (f_ref, ref_d32) = self._masa_encode(E, lq32), self._masa_encode(E, ref32)
         # fusion buffers [x || warp] per level, fp32 residual streams
         fbuf = [torch.empty((B, h >> i, w >> i, 2 * d[i]), dtype=F32, device=dev) for i in range(4)]

@@ -409,11 +409,18 @@ class GuidedRestormerTrainMixin(RestormerTrainMixin):
         mult = self.padder_size * self.lr_block_size
         h, w = ops.round_up(oh, mult), ops.round_up(ow, mult)
         hr, wr = ops.round_up(ref_img.shape[2], mult), ops.round_up(ref_img.shape[3], mult)
-        lq32, ref32 = ops.nchw_to_nhwc(inp_img, h, w), ops.nchw_to_nhwc(ref_img, hr, wr)
-        lq16, ref16 = self._image16(inp_img, h, w), self._image16(ref_img, hr, wr)
+        if (h, w) == (hr, wr):           # lq and ref share one batch buffer (no concatenation copy)
+            both32 = torch.empty((2 * B, h, w, inp_img.shape[1]), dtype=F32, device=dev)
+            both16 = torch.zeros((2 * B, h, w, 8), dtype=BF16, device=dev)
+            lq32, ref32, lq16, ref16 = both32[:B], both32[B:], both16[:B], both16[B:]
+            ops.nchw_to_nhwc_into(inp_img, h, w, dst32=lq32, dst16=lq16)
+            ops.nchw_to_nhwc_into(ref_img, hr, wr, dst32=ref32, dst16=ref16)
+        else:
+            lq32, ref32 = ops.nchw_to_nhwc(inp_img, h, w), ops.nchw_to_nhwc(ref_img, hr, wr)
+            lq16, ref16 = self._image16(inp_img, h, w), self._image16(ref_img, hr, wr)
         tape, T = [], dict(hw=(h, w), B=B, inp16=lq16)
         if (h, w) == (hr, wr):           # shared weights: lq and ref as one batch
-            fb, d32, et = self._masa_encode_train(E, torch.cat([lq32, ref32], 0), torch.cat([lq16, ref16], 0))
+            fb, d32, et = self._masa_encode_train(E, both32, both16)
             f_lq, f_ref, lq_d32, ref_d32 = [t[:B] for t in fb], [t[B:] for t in fb], d32[:B], d32[B:]
             T["enc"] = [(et, fb)]
         else:

@@ -34,6 +34,52 @@ __device__ __forceinline__ float ex2f(float x) {
   return r;
 }
 
+// Online-softmax update of one thread's query row with one tile of scores (TMEM row at `trow`): running max / sum, the
+// rescale factor alpha of what was accumulated so far, and P = exp2(c s - c m) as the bf16 K-major A operand in shared
+// memory (SWIZZLE_128B: 16-byte chunk q of row r sits at q ^ (r & 7)).  MASK: keys >= valid do not exist (last tile).
+template <bool MASK>
+__device__ __forceinline__ void softmax_tile(uint32_t trow, int valid, float c, float& m_run, float& l_run, float& alpha,
+                                             uint32_t p_row, int sw) {
+  // pass 1: row maximum over the keys of the tile
+  float mt = -INFINITY;
+  for (int c0 = 0; c0 < valid; c0 += 32) {
+    uint32_t s[32];
+    tmem_ld16(trow + c0, s);
+    tmem_ld16(trow + c0 + 16, s + 16);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (!MASK || c0 + i < valid) mt = fmaxf(mt, __uint_as_float(s[i]));
+  }
+  const float m_new = fmaxf(m_run, mt);
+  alpha = ex2f((m_run - m_new) * c);                       // first tile: exp2(-inf) = 0
+  m_run = m_new;
+  const float mc = m_new * c;
+  float lsum = 0.f;
+  // pass 2: probabilities
+  const int vend = (valid + 15) & ~15;
+  for (int c0 = 0; c0 < vend; c0 += 32) {
+    uint32_t s[32];
+    tmem_ld16(trow + c0, s);
+    tmem_ld16(trow + c0 + 16, s + 16);
+    tmem_ld_wait();
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float p0 = (!MASK || c0 + i < valid) ? ex2f(fmaf(__uint_as_float(s[i]), c, -mc)) : 0.f;
+      const float p1 = (!MASK || c0 + i + 1 < valid) ? ex2f(fmaf(__uint_as_float(s[i + 1]), c, -mc)) : 0.f;
+      lsum += p0 + p1;
+      pk[i >> 1] = pack2(p0, p1);
+    }
+    const uint32_t base = p_row + (c0 >> 6) * kBox;
+    const int q8 = (c0 & 63) >> 3;                          // first 16-byte chunk of this 32-key group within the row
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      sts128(base + (((q8 + g) ^ sw) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+  }
+  l_run = l_run * alpha + lsum;
+}
+
 template <int HD>
 __global__ void __launch_bounds__(128, HD <= 64 ? 2 : 1) vit_attn_kernel(const __grid_constant__ TdrTensorMap map,
                                                                          const VitAttnArgs a) {
@@ -112,44 +158,9 @@ __global__ void __launch_bounds__(128, HD <= 64 ? 2 : 1) vit_attn_kernel(const _
     if (leader && j + 1 < nkv) load_tile(sK, bar_k, a.D + h * HD, (j + 1) * kKT);   // S_j is done with K_j
     float alpha = 1.f;
     if (active) {
-      // pass 1: row maximum over the valid keys of the tile
-      float mt = -INFINITY;
-      for (int c0 = 0; c0 < valid; c0 += 32) {
-        uint32_t s[32];
-        tmem_ld16(tS + lane_off + c0, s);
-        tmem_ld16(tS + lane_off + c0 + 16, s + 16);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c0 + i < valid) mt = fmaxf(mt, __uint_as_float(s[i]));
-      }
-      const float m_new = fmaxf(m_run, mt);
-      alpha = ex2f((m_run - m_new) * a.c);                 // first tile: exp2(-inf) = 0
-      m_run = m_new;
-      const float mc = m_new * a.c;
-      float lsum = 0.f;
-      // pass 2: p = exp2(c s - c m) -> bf16 A operand (K-major, SWIZZLE_128B: 16-byte chunk q of row r sits at q ^ (r & 7))
-      const int vend = (valid + 15) & ~15;
-      for (int c0 = 0; c0 < vend; c0 += 32) {
-        uint32_t s[32];
-        tmem_ld16(tS + lane_off + c0, s);
-        tmem_ld16(tS + lane_off + c0 + 16, s + 16);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const float p0 = c0 + i < valid ? ex2f(fmaf(__uint_as_float(s[i]), a.c, -mc)) : 0.f;
-          const float p1 = c0 + i + 1 < valid ? ex2f(fmaf(__uint_as_float(s[i + 1]), a.c, -mc)) : 0.f;
-          lsum += p0 + p1;
-          pk[i >> 1] = pack2(p0, p1);
-        }
-        const uint32_t base = p_row + (c0 >> 6) * kBox;
-        const int q8 = (c0 & 63) >> 3;                      // first 16-byte chunk of this 32-key group within the row
-#pragma unroll
-        for (int g = 0; g < 4; ++g)
-          sts128(base + (((q8 + g) ^ sw) << 4), pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-      }
-      l_run = l_run * alpha + lsum;
+      // full tiles (all but the last) skip the key mask: the compare / select pairs are a third of the softmax issue slots
+      if (valid == kKT) softmax_tile<false>(tS + lane_off, valid, a.c, m_run, l_run, alpha, p_row, sw);
+      else softmax_tile<true>(tS + lane_off, valid, a.c, m_run, l_run, alpha, p_row, sw);
     }
     fence_proxy_async();                                    // P (generic proxy) -> tcgen05.mma (async proxy)
     tc_fence_before();
