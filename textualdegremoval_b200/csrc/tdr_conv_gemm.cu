@@ -243,6 +243,9 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc = umma_idesc_bf16(kTileM, a.BN, 0, 0, a.in_fp16, a.in_fp16);
+    // K = 16 steps that hold real channels in the LAST 64-channel chunk (the rest of the chunk is TMA zero fill: Ci = 48
+    // needs 3 of the 4 steps, Ci = 96 needs 4 + 2): skipping the all-zero steps saves a quarter of the MMAs at Ci = 48 / 96
+    const int klast = (a.Ci - (a.kchunks - 1) * kChunkK + 15) >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -271,7 +274,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
               const uint64_t da = umma_desc_sw128(smem_u32(smem_a + st * kABytes), 0, 1024);
               const uint64_t db = umma_desc_sw128(smem_u32(smem_b + (nt * a.kchunks + kc) * b_bytes), 0, 1024);
 #pragma unroll
-              for (int k = 0; k < kChunkK / 16; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0);
+              for (int k = 0; k < kChunkK / 16; ++k)
+                if (kc < a.kchunks - 1 || k < klast) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0);
               if (nt == a.n_tiles - 1) umma_commit(&empty[st]);
               if (kc == a.kchunks - 1) umma_commit(&tfull[acc]);
             }
@@ -306,12 +310,13 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
             uint64_t db = umma_desc_sw128(smem_u32(smem_b + kc * taps * b_bytes), 0, 1024);
             const uint32_t b_step = (uint32_t)b_bytes >> 4;
             uint32_t accum = kc != 0;
+            const int nk = kc < a.kchunks - 1 ? kChunkK / 16 : klast;
             for (int ky = 0; ky < a.KH; ++ky) {
               uint64_t da = da0 + (uint64_t)((ky * a.dil * 16) << 3);
               for (int kx = 0; kx < a.KW; ++kx) {
 #pragma unroll
                 for (int k = 0; k < kChunkK / 16; ++k) {
-                  umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                  if (k < nk) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
                   accum = 1;
                 }
                 da += (uint64_t)(a.dil << 3);
@@ -326,15 +331,17 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         }
         continue;
       }
-      for (int ks = 0; ks < ksteps; ++ks) {
+      for (int ks = 0, kc = 0; ks < ksteps; ++ks) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
+        const int nk = kc < a.kchunks - 1 ? kChunkK / 16 : klast;     // k-step ks = (tap, chunk kc), chunk fastest
+        if (++kc == a.kchunks) kc = 0;
         if (elect_one()) {
           const uint64_t da = umma_desc_sw128(smem_u32(smem_a + stage * kABytes), 0, 1024);
           const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * b_bytes), 0, 1024);
 #pragma unroll
           for (int k = 0; k < kChunkK / 16; ++k)                  // K advance = 32 B = 2 units of the address field
-            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+            if (k < nk) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
           umma_commit(&empty[stage]);                   // smem stage reusable once these MMAs retire
           if (ks == ksteps - 1) umma_commit(&tfull[acc]);
         }
