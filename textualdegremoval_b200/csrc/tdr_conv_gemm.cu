@@ -68,7 +68,9 @@ struct ConvGemmArgs {
                                 //    is loaded ONCE per CTA, the ring holds A chunks only (2-3 pixel tiles of look-ahead
                                 //    instead of ~1.5 items), and the A chunks of a pixel tile are loaded once and multiplied
                                 //    with all n tiles (items are pixel-tile major: by_pixel = 1)
-  int halo_bytes;               // bytes of one haloed A tile: (TH + (KH-1)*dil) rows x 16 px x 128 B
+  int halo_bytes;               // ring slot of one haloed A tile: (TH + (KH-1)*dil) rows x halo_pitch px x 128 B, rounded to 1 KB
+  int halo_pitch;               // pixels per staged image row: 8 + (KW-1)*dil (exactly what the taps touch)
+  int halo_tx;                  // bytes one haloed box delivers (unrounded)
   int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
   int epi_bufs;                 // staging buffers per epilogue warp (1 or 2; 4 with the fused LayerNorm)
   int alt_items;                // TMA epilogue (no LN): the two warp groups take alternate items
@@ -218,7 +220,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         if (a.halo) {
           for (int kc = 0; kc < a.kchunks; ++kc) {
             mbar_wait(&empty[stage], phase ^ 1);
-            mbar_expect_tx(&full[stage], a.halo_bytes);
+            mbar_expect_tx(&full[stage], a.halo_tx);
             tma_load_4d(smem_a + stage * a.halo_bytes, &map_a, &full[stage], kc * kChunkK, org_x + ox0 - a.pad,
                         org_y + oy0 - a.pad, img);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -300,19 +302,20 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           if (elect_one()) {
-            // tap (ky, kx) = the same haloed tile shifted by (ky*dil) rows of 16 px and (kx*dil) px; every 8-pixel
-            // UMMA row group is one image-row segment, groups are 2048 B apart (16-px row pitch).  The 128 B
-            // swizzle is a function of the absolute smem address, so 128 B-aligned shifted starts need no fix-up
-            // (verified on device: descriptor base-offset must stay 0).
+            // tap (ky, kx) = the same haloed tile shifted by (ky*dil) rows of halo_pitch px and (kx*dil) px; every
+            // 8-pixel UMMA row group is one image-row segment, groups are halo_pitch * 128 B apart.  The 128 B
+            // swizzle is a function of the absolute smem address, so 128 B-aligned group starts need no fix-up
+            // (verified on device: descriptor base-offset must stay 0).  The staged row holds exactly the 8 + (KW-1)
+            // dil pixels the taps touch (a 16-px row made the L2 -> SM traffic 2.25x the useful bytes).
             // The single issuing thread is instruction-bound (ncu: tensor pipe 23 % busy at N = 64), so descriptors
             // are built ONCE per stage and advanced by adding to their 14-bit start-address field (16 B units).
-            const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a + stage * a.halo_bytes), 0, 2048);
+            const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a + stage * a.halo_bytes), 0, (uint32_t)a.halo_pitch * 128);
             uint64_t db = umma_desc_sw128(smem_u32(smem_b + kc * taps * b_bytes), 0, 1024);
             const uint32_t b_step = (uint32_t)b_bytes >> 4;
             uint32_t accum = kc != 0;
             const int nk = kc < a.kchunks - 1 ? kChunkK / 16 : klast;
             for (int ky = 0; ky < a.KH; ++ky) {
-              uint64_t da = da0 + (uint64_t)((ky * a.dil * 16) << 3);
+              uint64_t da = da0 + (uint64_t)((ky * a.dil * a.halo_pitch) << 3);
               for (int kx = 0; kx < a.KW; ++kx) {
 #pragma unroll
                 for (int k = 0; k < kChunkK / 16; ++k) {
@@ -1074,15 +1077,20 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   // image-row segment of the haloed tile.
   if (d->impl == 0 && d->stride == 1 && d->KH * d->KW > 1 && (d->KW - 1) * d->dil <= 8 && OH > 1 && !d->w_batched &&
       a.n_tiles == 1 && getenv("TDR_CONV_NO_HALO") == nullptr) {
-    const int halo_bytes = (16 + (d->KH - 1) * d->dil) * 16 * 128;
-    const size_t need = 1024 + (size_t)3 * halo_bytes + (size_t)d->KH * d->KW * a.kchunks * a.BN * kChunkK * 2 +
-                        (size_t)kEpiWarps * kEpiStageBytes + 512;
-    if (need <= 227 * 1024) {
+    const int pitch = 8 + (d->KW - 1) * d->dil;
+    const int tx = (16 + (d->KH - 1) * d->dil) * pitch * 128;
+    const int halo_bytes = (tx + 1023) & ~1023;
+    const size_t fixed = 1024 + (size_t)d->KH * d->KW * a.kchunks * a.BN * kChunkK * 2 +
+                         (size_t)kEpiWarps * (d->res1 ? 2 : 1) * kEpiStageBytes + 1024;
+    if (fixed + (size_t)3 * halo_bytes <= 227 * 1024) {
       a.halo = 1;
       a.halo_bytes = halo_bytes;
+      a.halo_pitch = pitch;
+      a.halo_tx = tx;
       a.TW = 8; a.TH = 16;
       a.tiles_x = tdr_cdiv(OW, a.TW); a.tiles_y = tdr_cdiv(OH, a.TH);
-      a.stages = 3;
+      int st = (int)((227 * 1024 - fixed) / halo_bytes);     // as deep a ring of haloed tiles as fits (3..6)
+      a.stages = st > 6 ? 6 : st;
       a.epi_bufs = d->res1 ? 2 : 1;
     }
   }
@@ -1164,7 +1172,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     const uint64_t strides[3] = {(uint64_t)d->in_ld * 2, (uint64_t)d->in_ld * 2 * img_w,
                                  (uint64_t)d->in_ld * 2 * img_w * img_h};
     uint32_t box[4] = {(uint32_t)kChunkK, (uint32_t)(a.TW * d->stride), (uint32_t)(a.TH * d->stride), 1};
-    if (a.halo) { box[1] = 16; box[2] = (uint32_t)(a.TH + (d->KH - 1) * d->dil); }
+    if (a.halo) { box[1] = (uint32_t)a.halo_pitch; box[2] = (uint32_t)(a.TH + (d->KH - 1) * d->dil); }
     const uint32_t es[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
     int rc = tdr_make_tensor_map_bf16(&map_a, d->in, 4, dims, strides, box, es);
     if (rc) return rc;
