@@ -249,6 +249,14 @@ int tdr_vit_transpose_v(const void* qkv_bf16, long long ld, int B, int N, int he
 int tdr_vit_attention_supported(int hd);
 int tdr_vit_attention(const void* qkv_bf16, long long ld, int B, int N, int heads, int hd, float scale, void* out_bf16,
                       long long out_ld, cudaStream_t stream);
+/* PromptGenBlock.forward (models/archs/network_promptir_guided_arch.py:424-440) between the spatial mean and the 3x3 conv:
+ * out[b, k] = softmax_k(linear_layer(emb[b]))  (L <= 8 prompts), and
+ * out16[b, y, x, d] = bilinear(sum_k wts[b, k] * prompt_param[k, d])(y, x), F.interpolate(mode="bilinear") semantics,
+ * written NHWC in the 16-bit operand format of the conv that follows (fp16 != 0: IEEE fp16, else bf16). */
+int tdr_prompt_weights(const float* emb, long long emb_ld, const float* weight, const float* bias, int B, int C, int L,
+                       float* out, cudaStream_t stream);
+int tdr_prompt_mix_resize(const float* prompt, int L, int D, int S, const float* wts, int B, int H, int W, void* out16,
+                          long long out_ld, int fp16, cudaStream_t stream);
 /* Reference-crop selection (models/image_restoration_ref_model.py:215-247): crop (origin[k] = (image, y0, x0), size
  * crop_h x crop_w) + bilinear resize (align_corners=False) of NCHW fp32 images in one pass, and the cosine similarity
  * between one query feature row per sample and n candidate rows. */

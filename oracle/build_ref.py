@@ -18,6 +18,7 @@ DST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 FILES = [
     "models/archs/network_restormer_guided_arch.py",
     "models/archs/network_nafnet_guided_arch.py",
+    "models/archs/network_promptir_guided_arch.py",
     "models/archs/nafnet_arch_utils.py",
     "models/archs/nafnet_local_arch.py",
     "scripts/train/main_train_tr_mapping.py",

@@ -61,6 +61,16 @@ NAF_GUIDED_CASES = {
 }
 
 
+# PromptIRRefFusion: the prompt blocks hard-code lin_dim 96 / 192 / 384, i.e. dim = 48 is the only width the reference
+# class can run with; decoder=True is the only mode whose forward runs at all
+PROMPTIR_CASES = {
+    "guided_promptir_128": dict(cfg=dict(dim=48, num_blocks=[1, 1, 1, 1], num_refinement_blocks=1, heads=[1, 2, 4, 8],
+                                         nf=48, ext_n_blocks=[1, 1, 1, 1], reffusion_n_blocks=[1, 1, 1, 1],
+                                         LayerNorm_type="WithBias", decoder=True),
+                                seed=51, lq=(1, 3, 128, 128), ref=(1, 3, 128, 128)),
+}
+
+
 def denoise_inputs(case):
     """The reference's deterministic test-noise recipe (data/restoration_dataset.py:479-480): np.random.seed(0) then
     N(0, (sigma/255)^2) added to a seeded clean tile."""
@@ -97,6 +107,20 @@ def main():
         y = net(lq, ref)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(case), out=y.numpy())
         print(name, tuple(y.shape), float(y.abs().max()))
+
+
+def main_promptir():
+    from . import promptir as OP
+    torch.set_grad_enabled(False)
+    for name, case in PROMPTIR_CASES.items():
+        net = R.promptir_ref_fusion(**case["cfg"])
+        sd = W.load_seeded(net, case["seed"])
+        lq, ref = guided_inputs(case)
+        y = net(lq, ref)
+        yo = OP.promptir_ref_fusion_forward(sd, lq, ref, case["cfg"]["heads"])
+        meta = dict(case, oracle_vs_reference_max=float((y - yo).abs().max()))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), out=y.numpy())
+        print(name, tuple(y.shape), float(y.abs().max()), "oracle vs reference", meta["oracle_vs_reference_max"])
 
 
 VIT_CASES = {
@@ -228,3 +252,4 @@ if __name__ == "__main__":
     main_grads()
     main_nafnet()
     main_vit()
+    main_promptir()

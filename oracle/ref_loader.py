@@ -63,6 +63,13 @@ def restormer_ref_fusion(**kw):
     return net
 
 
+def promptir_ref_fusion(**kw):
+    net = load_arch("network_promptir_guided_arch").PromptIRRefFusion(**kw)
+    orig = net.masa_enc.forward
+    net.masa_enc.forward = lambda x: [None] + orig(x)   # B1 index shim (same Encoder class as the guided Restormer)
+    return net
+
+
 def nafnet(**kw):
     return load_arch("network_nafnet_guided_arch").NAFNet(**kw)
 

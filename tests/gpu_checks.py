@@ -766,6 +766,56 @@ def check_guided_golden():
     return out
 
 
+def check_promptir():
+    """PromptIRRefFusion (decoder=True) -- the prompt kernels and the wide-head (c = 176) Gram against
+    torch, then the whole net against the golden fixture made by the unmodified reference module."""
+    from oracle import weights as Wt
+    from oracle.make_golden import guided_inputs
+    from textualdegremoval_b200.archs import define_network
+    ops = _ops()
+    out = []
+    # PromptGenBlock pieces (network_promptir_guided_arch.py:424-440)
+    B, C_, L, D, S, H, W = 3, 96, 5, 64, 16, 24, 40
+    emb = rnd(B, C_, seed=1)
+    lw, lb = rnd(L, C_, seed=2) * 0.3, rnd(L, seed=3)
+    wts = ops.prompt_weights(emb.to(DEV), lw.to(DEV), lb.to(DEV))
+    wts_ref = torch.softmax(F.linear(emb, lw, lb), 1)
+    out.append(result("prompt_weights", wts, wts_ref, 1e-5))
+    pp = torch.rand(L, D, S, S, generator=torch.Generator().manual_seed(4))
+    want = F.interpolate((wts_ref.view(B, L, 1, 1, 1) * pp.unsqueeze(0)).sum(1), (H, W), mode="bilinear")
+    for dt in (torch.float16, BF16):
+        o16 = torch.empty(B, H, W, D, dtype=dt, device=DEV)
+        ops.prompt_mix_resize(pp.to(DEV), wts_ref.to(DEV), H, W, o16)
+        out.append(result(f"prompt_mix_resize_{str(dt)[6:]}", o16.permute(0, 3, 1, 2), want, 8e-3 if dt == BF16 else 1e-3))
+    # wide heads: c = 176 (noise_level3: 704 channels, 4 heads) through the generic Gram + softmax + fold
+    for (C2, heads, Hh, Ww, Bb) in ((704, 4, 16, 16, 2), (352, 2, 9, 13, 1)):
+        c = C2 // heads
+        qkv = q(rnd(Bb, 3 * C2, Hh, Ww, seed=C2 + heads))
+        temp = torch.rand(heads, generator=torch.Generator().manual_seed(1)) + 0.5
+        wpo = rnd(C2, C2, seed=2) / C2 ** 0.5
+        qq, kk, vv = qkv.view(Bb, 3, heads, c, Hh * Ww).unbind(1)
+        qn = qq / qq.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        kn = kk / kk.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        attn = torch.softmax(qn @ kn.transpose(-1, -2) * temp.view(1, heads, 1, 1), -1)
+        weff_ref = torch.zeros(Bb, C2, C2)
+        for h in range(heads):
+            weff_ref[:, :, h * c:(h + 1) * c] = wpo[:, h * c:(h + 1) * c] @ attn[:, h]
+        weff, attn_g = ops.mdta_weff(nhwc(qkv.to(BF16)), C2, heads, temp.to(DEV), wpo.to(DEV), want_attn=True)
+        out.append(result(f"mdta_wide_attn_C{C2}_h{heads}", attn_g, attn, 2e-3))
+        out.append(result(f"mdta_wide_weff_C{C2}_h{heads}", weff[..., :C2], weff_ref, 8e-3))
+    # end to end
+    meta, ref = _golden("guided_promptir_128")
+    net = define_network(dict(type="PromptIRRefFusion", **meta["cfg"]))
+    Wt.load_seeded(net, meta["seed"])
+    net = net.to(DEV).eval()
+    lq, rf = guided_inputs(meta)
+    with torch.no_grad():
+        y = net(lq.to(DEV), rf.to(DEV)).cpu()
+    out.append(guided_result("golden_guided_promptir_128", y, ref))
+    out.append(psnr_delta_result("guided_promptir_128", y, ref, meta["seed"]))
+    return out
+
+
 class _ForcedMatches:
     """Test hook: run a guided net with the ORACLE's coarse / fine matches instead of its own arg-max results (the
     confidence is re-read from our own correlation at the forced index).  Around 1 % of the fine searches of a
@@ -1626,6 +1676,7 @@ CHECKS = {
     "guided_stages": check_guided_stages,
     "guided_golden": check_guided_golden,
     "nafnet": check_nafnet,
+    "promptir": check_promptir,
     "vit": check_vit,
     "optim": check_optim,
     "wgrad": check_wgrad,

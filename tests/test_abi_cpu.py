@@ -207,3 +207,22 @@ def test_dino_state_dict_keys_match_reference():
     b = ref_vit_base(**kw).state_dict()
     assert list(a) == list(b)
     assert all(a[k].shape == b[k].shape for k in b)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="/root/reference not present")
+def test_promptir_state_dict_keys_match_reference():
+    """PromptIRRefFusion (N3): same keys, order and shapes as the reference for both decoder modes; the registry resolves
+    the type; decoder=False fails the way the reference's own forward does (Upsample(dim*4) on the dim*8 latent)."""
+    from oracle import ref_loader as R
+    from textualdegremoval_b200 import define_network
+    cfg = dict(dim=48, num_blocks=[1, 2, 1, 1], num_refinement_blocks=2, heads=[1, 2, 4, 8], nf=48,
+               ext_n_blocks=[2, 1, 1, 1], reffusion_n_blocks=[1, 2, 1, 1], LayerNorm_type="WithBias", bias=False)
+    for dec in (False, True):
+        a = define_network(dict(type="PromptIRRefFusion", decoder=dec, **cfg))
+        b = R.promptir_ref_fusion(decoder=dec, **cfg).state_dict()
+        assert list(a.state_dict()) == list(b)
+        assert all(a.state_dict()[k].shape == b[k].shape for k in b)
+    net = define_network(dict(type="PromptIRRefFusion", decoder=False, **cfg))
+    net._check = lambda *ts: None                       # get past the CUDA-tensor check: the shape error comes first
+    with torch.no_grad(), pytest.raises(RuntimeError, match="expected input to have 192 channels, but got 384"):
+        net(torch.rand(1, 3, 64, 64), torch.rand(1, 3, 64, 64))

@@ -410,12 +410,10 @@ class RestormerRefFusion(GuidedRestormerTrainMixin, MasaTrainMixin, MasaMixin, _
         P["masa_enc"] = enc
         return P
 
-    def forward(self, inp_img, ref_img, return_aux=False):
-        """:747-964 (with the B1 index shift).  NCHW in, NCHW out, arbitrary H, W (zero-padded to x64, cropped)."""
-        self._check(inp_img, ref_img)
-        if self._wants_grad() and not return_aux:
-            return train_call(self, inp_img, ref_img)
-        P = self.prepared()
+    def _guided_encode(self, P, inp_img, ref_img, return_aux=False):
+        """MASA guidance + the four encoder levels (:753-936).  Returns (per-level fp32 NHWC encoder outputs, the level-1
+        input copy for ``dual_pixel_task``, the padded NHWC lq image, (H, W) of the input, aux, the [x || warp] buffers)."""
+        x_in1 = None
         d = self.dims
         dev = inp_img.device
         B, _, oh, ow = inp_img.shape
@@ -453,6 +451,15 @@ class RestormerRefFusion(GuidedRestormerTrainMixin, MasaTrainMixin, MasaMixin, _
                 ops.copy_rows(x, dst32=x_in1)
             run_stack(x, P[enc_names[i]])
             xs.append(x)
+        return xs, x_in1, lq32, (oh, ow), aux, fbuf
+
+    def forward(self, inp_img, ref_img, return_aux=False):
+        """:747-964 (with the B1 index shift).  NCHW in, NCHW out, arbitrary H, W (zero-padded to x64, cropped)."""
+        self._check(inp_img, ref_img)
+        if self._wants_grad() and not return_aux:
+            return train_call(self, inp_img, ref_img)
+        P = self.prepared()
+        xs, x_in1, lq32, (oh, ow), aux, _ = self._guided_encode(P, inp_img, ref_img, return_aux)
         out = self._decode(P, xs[3], xs[0], xs[1], xs[2], x_in1 if self.dual_pixel_task else None)
         out = ops.nhwc_to_nchw(out, oh, ow, res=None if self.dual_pixel_task else lq32)      # + inp_img (:962)
         return (out, aux) if return_aux else out

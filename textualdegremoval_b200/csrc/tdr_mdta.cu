@@ -22,11 +22,24 @@ constexpr int kBoxBytes = 64 * kPixTile * 2;
 struct GramPlan {
   int c, M, N, boxes, stages, nchunks, tiles_per_chunk, tiles_total;
   uint32_t tmem_cols;
+  int generic;            // heads wider than 128 channels (PromptIR's prompt-interaction blocks, c = 176): SIMT Gram
 };
+
+constexpr int kGenChunkPix = 2048;     // pixels per partial of the generic Gram (a function of P only)
 
 static int make_plan(int B, long long P, int C, int heads, GramPlan* p) {
   if (heads <= 0 || C % heads != 0) return -1;
   p->c = C / heads;
+  p->generic = 0;
+  if (p->c % 8 == 0 && p->c > 128 && p->c <= 224) {       // 224: the fold kernel keeps c x c floats in shared memory
+    // Wide heads occur only at the coarse levels (a few thousand pixels): a shared-memory tiled SIMT Gram is enough.
+    p->generic = 1;
+    p->M = p->N = p->c; p->boxes = 0; p->stages = 0; p->tmem_cols = 0;
+    p->tiles_total = (int)((P + kGenChunkPix - 1) / kGenChunkPix);
+    p->tiles_per_chunk = 1;
+    p->nchunks = p->tiles_total;
+    return 0;
+  }
   if (p->c % 8 != 0 || p->c > 128) return -1;
   if (p->c > 64 && p->c % 16 != 0) return -1;
   p->M = p->c <= 64 ? 64 : 128;
@@ -175,10 +188,71 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
   }
 }
 
+// Generic Gram for heads wider than 128 channels: grid (32x32 tiles of the c x c Gram, pixel chunk, B * heads), 256 threads.
+// Same partial layout as the tcgen05 kernel ([c*c Gram | c sum q^2 | c sum k^2] per chunk), fp32 FMA over 16-bit operands.
+__global__ void __launch_bounds__(256) mdta_gram_generic_kernel(const uint16_t* __restrict__ qkv, long long ld, int C,
+                                                                int heads, long long P, int nchunks,
+                                                                float* __restrict__ partials, int fp16) {
+  const int c = C / heads;
+  const int nt = (c + 31) >> 5;
+  const int ti = blockIdx.x / nt, tj = blockIdx.x % nt;
+  const int chunk = blockIdx.y;
+  const int b = blockIdx.z / heads, h = blockIdx.z % heads;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // thread -> column tx, rows ty*4 .. ty*4+3
+  __shared__ float sq[32][33], sk[32][33];
+  const long long p0 = (long long)chunk * kGenChunkPix;
+  const long long p1 = p0 + kGenChunkPix < P ? p0 + kGenChunkPix : P;
+  const uint16_t* base = qkv + (size_t)b * P * ld;
+  const int qi = h * c + ti * 32, kj = C + h * c + tj * 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float nq = 0.f, nk = 0.f;                                          // ty == 0 threads: sum of squares of column tx
+  for (long long pp = p0; pp < p1; pp += 32) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {                                     // 32 pixels x 32 channels of q and of k
+      const int pr = ty * 4 + r;
+      const long long pix = pp + pr;
+      float vq = 0.f, vk = 0.f;
+      if (pix < p1) {
+        float d;
+        if (ti * 32 + tx < c) unpack2r(base[pix * ld + qi + tx], vq, d, fp16);
+        if (tj * 32 + tx < c) unpack2r(base[pix * ld + kj + tx], vk, d, fp16);
+      }
+      sq[pr][tx] = vq;
+      sk[pr][tx] = vk;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int pr = 0; pr < 32; ++pr) {
+      const float kv = sk[pr][tx];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] = fmaf(sq[pr][ty * 4 + r], kv, acc[r]);
+    }
+    if (ty == 0) {
+#pragma unroll 8
+      for (int pr = 0; pr < 32; ++pr) {
+        nq = fmaf(sq[pr][tx], sq[pr][tx], nq);
+        nk = fmaf(sk[pr][tx], sk[pr][tx], nk);
+      }
+    }
+    __syncthreads();
+  }
+  float* out = partials + ((size_t)(b * heads + h) * nchunks + chunk) * ((size_t)c * c + 2 * c);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = ti * 32 + ty * 4 + r, j = tj * 32 + tx;
+    if (i < c && j < c) out[(size_t)i * c + j] = acc[r];
+  }
+  if (ty == 0) {
+    if (tj == 0 && ti * 32 + tx < c) out[(size_t)c * c + ti * 32 + tx] = nq;
+    if (ti == 0 && tj * 32 + tx < c) out[(size_t)c * c + c + tj * 32 + tx] = nk;
+  }
+}
+
 // Stage 1 of the finalize: grid (c, heads, B), one CTA of 8 warps per attention row i.  The per-chunk partial Grams are
 // reduced in a FIXED two-level order (warp w sums chunks w, w+8, w+16, ... in order; the 8 warp sums are then added in warp
 // order), so the result is deterministic and a function of (P, heads) only; the 8 warps keep 8 x 4 independent L2 loads
 // in flight instead of one warp walking all ~148 chunks.  Then the F.normalize denominators, temperature and the softmax.
+template <int T>   // T * 32 >= c columns per attention row: 4 (c <= 128) or 8 (wide heads)
 __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restrict__ partials, int C, int heads,
                                                            int nchunks, const float* __restrict__ temperature,
                                                            float* __restrict__ attn, float* __restrict__ shat_out) {
@@ -188,18 +262,20 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
   const int i = blockIdx.x;
   const size_t psz = (size_t)c * c + 2 * c;
   const float* base = partials + (size_t)(b * heads + h) * nchunks * psz;
-  __shared__ float sg[8][4][32], sk[8][4][32], sq[8];
-  float g[4] = {0.f, 0.f, 0.f, 0.f}, nk[4] = {0.f, 0.f, 0.f, 0.f};
+  __shared__ float sg[8][T][32], sk[8][T][32], sq[8];
+  float g[T], nk[T];
+#pragma unroll
+  for (int t = 0; t < T; ++t) g[t] = nk[t] = 0.f;
   float nq = 0.f;
   for (int ch0 = warp; ch0 < nchunks; ch0 += 32) {          // 4 chunks of this warp's residue class at a time
-    float tg[4][4], tk[4][4], tq[4];
+    float tg[4][T], tk[4][T], tq[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int ch = ch0 + 8 * u;
       const bool in = ch < nchunks;
       const float* p = base + (size_t)(in ? ch : 0) * psz;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < T; ++t) {
         const int j = lane + 32 * t;
         const bool ok = in && j < c;
         tg[u][t] = ok ? p[i * c + j] : 0.f;
@@ -210,7 +286,7 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < T; ++t) {
         g[t] += tg[u][t];
         nk[t] += tk[u][t];
       }
@@ -218,7 +294,7 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
     }
   }
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < T; ++t) {
     sg[warp][t][lane] = g[t];
     sk[warp][t][lane] = nk[t];
   }
@@ -227,10 +303,10 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
   if (warp != 0) return;
   nq = 0.f;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) g[t] = nk[t] = 0.f;
+  for (int t = 0; t < T; ++t) g[t] = nk[t] = 0.f;
   for (int w = 0; w < 8; ++w) {
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
+    for (int t = 0; t < T; ++t) {
       g[t] += sg[w][t][lane];
       nk[t] += sk[w][t][lane];
     }
@@ -243,7 +319,7 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
   float* so = shat_out ? shat_out + (size_t)(b * heads + h) * psz : nullptr;
   if (so && lane == 0) so[(size_t)c * c + i] = nqi;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < T; ++t) {
     const int j = lane + 32 * t;
     if (j < c) {
       const float nkj = fmaxf(sqrtf(fmaxf(nk[t], 0.f)), 1e-12f);
@@ -259,7 +335,7 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   float sum = 0.f;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < T; ++t) {
     const int j = lane + 32 * t;
     if (j < c) {
       g[t] = __expf(g[t] - mx);
@@ -270,7 +346,7 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
   const float inv = 1.f / sum;
   float* out = attn + ((size_t)(b * heads + h) * c + i) * c;
 #pragma unroll
-  for (int t = 0; t < 4; ++t) {
+  for (int t = 0; t < T; ++t) {
     const int j = lane + 32 * t;
     if (j < c) out[j] = g[t] * inv;
   }
@@ -323,6 +399,15 @@ extern "C" int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long lon
   TDR_CHECK_ARG(make_plan(B, P, C, heads, &a.plan) == 0,
                 "tdr_mdta_gram: unsupported head width (C=%d heads=%d; need c%%8==0, c<=128, c%%16==0 if c>64)", C, heads);
   a.B = B; a.C = C; a.heads = heads; a.P = P; a.partials = partials; a.fp16 = fp16 ? 1 : 0;
+  if (a.plan.generic) {
+    const int nt = (a.plan.c + 31) / 32;
+    TDR_CHECK_ARG((long long)B * heads <= 65535 && a.plan.nchunks <= 65535, "tdr_mdta_gram: grid too large");
+    dim3 grid(nt * nt, a.plan.nchunks, B * heads);
+    mdta_gram_generic_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint16_t*>(qkv_bf16), ld, C, heads, P,
+                                                       a.plan.nchunks, partials, a.fp16);
+    TDR_CHECK_LAUNCH();
+    return TDR_OK;
+  }
   TdrTensorMap map;
   const uint64_t dims[3] = {(uint64_t)(3 * C), (uint64_t)P, (uint64_t)B};
   const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)P};
@@ -351,13 +436,14 @@ extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, i
   TDR_CHECK_ARG(weff_ld >= C && weff_ld % 8 == 0, "tdr_mdta_weff: bad weff_ld");
   {
     dim3 grid(p.c, heads, B);
-    mdta_softmax_kernel<<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out);
+    if (p.c <= 128) mdta_softmax_kernel<4><<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out);
+    else mdta_softmax_kernel<8><<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out);
     TDR_CHECK_LAUNCH();
   }
   const size_t smem = ((size_t)p.c * p.c + kFoldRows * p.c) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(mdta_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(mdta_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   dim3 grid((C + kFoldRows - 1) / kFoldRows, heads, B);

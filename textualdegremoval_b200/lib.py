@@ -89,6 +89,8 @@ SIGNATURES = {
     "tdr_vit_transpose_v": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "tdr_vit_attention_supported": (_i, [_i]),
     "tdr_vit_attention": (_i, [_vp, _ll, _i, _i, _i, _i, _f, _vp, _ll, _vp]),
+    "tdr_prompt_weights": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp]),
+    "tdr_prompt_mix_resize": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _ll, _i, _vp]),
     "tdr_crop_resize": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "tdr_cosine_rows": (_i, [_vp, _vp, _i, _i, _ll, _vp, _vp]),
     "tdr_mean_tokens": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _ll, _i, _vp]),

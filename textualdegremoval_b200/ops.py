@@ -646,6 +646,25 @@ def vit_transpose_v(qkv, heads, hd, voff, n_pad):
     return vt
 
 
+def prompt_weights(emb, weight, bias):
+    """softmax(linear_layer(emb), dim=1): emb fp32 [B, C] (row stride emb.stride(0)), weight fp32 [L, C] -> fp32 [B, L]."""
+    B, C_ = emb.shape
+    L = weight.shape[0]
+    out = torch.empty((B, L), dtype=F32, device=emb.device)
+    _call("tdr_prompt_weights", _p(emb), emb.stride(0), _p(weight), _p(bias), B, C_, L, _p(out), _stream())
+    return out
+
+
+def prompt_mix_resize(prompt, wts, H, W, out16):
+    """prompt fp32 [L, D, S, S] (prompt_param), wts fp32 [B, L] -> out16 (NHWC 16-bit view [B,H,W,D]) =
+    bilinear resize of the weighted prompt sum (tdr_prompt_mix_resize)."""
+    L, D, S, _ = prompt.shape
+    B = wts.shape[0]
+    _call("tdr_prompt_mix_resize", _p(prompt), L, D, S, _p(wts), B, H, W, _p(out16), _ld(out16),
+          1 if out16.dtype == F16 else 0, _stream(), nbytes=B * H * W * D * 2)
+    return out16
+
+
 def vit_attention_supported(hd):
     return bool(lib.load().tdr_vit_attention_supported(int(hd)))
 
