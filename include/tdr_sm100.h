@@ -224,7 +224,11 @@ int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, c
                   const float* w_out /* fp32 [C][C] */, void* weff_bf16, long long weff_ld, float* attn_ws,
                   void* weff_t_bf16 /* optional: Weff[b]^T, same ld (the dgrad operand of the training step) */,
                   float* shat_out /* optional fp32 [B][heads][c*c + 2c]: normalised Gram | |q| | |k| (for tdr_mdta_bwd) */,
-                  int fp16 /* Weff is written as IEEE fp16 (weff_t stays bf16) */, cudaStream_t stream);
+                  int fp16 /* Weff is written as IEEE fp16 (weff_t stays bf16) */,
+                  const float* topk_w /* optional fp32 [4]: top-k sparse attention of the DRSformer family
+                                         (network_drsformer_guided_arch.py:296-327) -- attn = sum_i topk_w[i] * softmax over the
+                                         int(c/2), int(2c/3), int(3c/4), int(4c/5) largest entries of each row */,
+                  cudaStream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * ViT encoder / mapper glue (DINOv2 ViT-B/14 models/dino/*.py "D:", CLIP ViT-H/14 via transformers, mappers "M:" =
@@ -249,6 +253,20 @@ int tdr_vit_transpose_v(const void* qkv_bf16, long long ld, int B, int N, int he
 int tdr_vit_attention_supported(int hd);
 int tdr_vit_attention(const void* qkv_bf16, long long ld, int B, int N, int heads, int hd, float scale, void* out_bf16,
                       long long out_ld, cudaStream_t stream);
+/* Generic grouped / depthwise K x K stencil over NHWC 16-bit rows (DRSformer MSFN :216-256 and MEFC experts :454-520):
+ * out16[b,y,x,co] = act(bias[co] + sum_{j<ipg} sum_taps weight[co][j][ky][kx] * in16[b, y+(ky-K/2)dil, x+(kx-K/2)dil, idx[co*ipg+j]])
+ * with zero padding; ipg in {1, 2}, K in {1, 3, 5, 7}; act 1 = ReLU; pool != 0: AvgPool2d(3, 1, 1, count_include_pad=False).
+ * The index table expresses depthwise (idx[co] = co), grouped 2 -> 1 convs and the reference's chunk / cat re-orderings. */
+int tdr_grouped_stencil(const void* in16, long long in_ld, int B, int H, int W, int Co, int ipg, const int* idx,
+                        const float* weight, const float* bias, int K, int dil, int act, int pool, void* out16,
+                        long long out_ld, int fp16, cudaStream_t stream);
+/* MEFC (network_drsformer_guided_arch.py:371-549): the gate softmax_ops(Linear(ReLU(Linear(avgpool(x))))) of OALayer /
+ * subnet.forward as [B, O = steps * num_ops] fp32, and the per-sample 1x1 weights of OperationLayer._out with the gate of
+ * a step folded into their column blocks (out16[b][co][k*C + ci] = weight[co][k*C + ci] * gate[b][k]). */
+int tdr_mefc_gate(const float* emb, long long emb_ld, int B, int C, const float* w1, const float* b1, int H1, const float* w2,
+                  const float* b2, int O, int num_ops, float* out, cudaStream_t stream);
+int tdr_mefc_mix_weights(const float* weight, int Co, int Ci, int C, const float* gate, long long gate_ld, int B, void* out16,
+                         long long ld, int fp16, cudaStream_t stream);
 /* PromptGenBlock.forward (models/archs/network_promptir_guided_arch.py:424-440) between the spatial mean and the 3x3 conv:
  * out[b, k] = softmax_k(linear_layer(emb[b]))  (L <= 8 prompts), and
  * out16[b, y, x, d] = bilinear(sum_k wts[b, k] * prompt_param[k, d])(y, x), F.interpolate(mode="bilinear") semantics,

@@ -19,6 +19,8 @@ FILES = [
     "models/archs/network_restormer_guided_arch.py",
     "models/archs/network_nafnet_guided_arch.py",
     "models/archs/network_promptir_guided_arch.py",
+    "models/archs/network_drsformer_guided_arch.py",
+    "models/archs/network_drsformer_guided_arch_200L_SPA.py",
     "models/archs/nafnet_arch_utils.py",
     "models/archs/nafnet_local_arch.py",
     "scripts/train/main_train_tr_mapping.py",

@@ -71,6 +71,19 @@ PROMPTIR_CASES = {
 }
 
 
+DRS_CASES = {
+    # option 007 (Rain200L / SPA variant, no MEFC) and options 008-010 (MEFC encoder_level0 + refinement), small widths
+    "guided_drsformer_spa_128": dict(spa=True, cfg=dict(dim=16, num_blocks=[1, 1, 1, 1], heads=[1, 2, 4, 8], nf=16,
+                                                        ext_n_blocks=[1, 1, 1, 1], reffusion_n_blocks=[1, 1, 1, 1],
+                                                        LayerNorm_type="WithBias"),
+                                     seed=71, lq=(1, 3, 128, 128), ref=(1, 3, 128, 128)),
+    "guided_drsformer_128": dict(spa=False, cfg=dict(dim=16, num_blocks=[1, 1, 1, 1], heads=[1, 2, 4, 8], nf=16,
+                                                     ext_n_blocks=[1, 1, 1, 1], reffusion_n_blocks=[1, 1, 1, 1],
+                                                     LayerNorm_type="WithBias"),
+                                 seed=72, lq=(1, 3, 128, 128), ref=(1, 3, 128, 128)),
+}
+
+
 def denoise_inputs(case):
     """The reference's deterministic test-noise recipe (data/restoration_dataset.py:479-480): np.random.seed(0) then
     N(0, (sigma/255)^2) added to a seeded clean tile."""
@@ -118,6 +131,20 @@ def main_promptir():
         lq, ref = guided_inputs(case)
         y = net(lq, ref)
         yo = OP.promptir_ref_fusion_forward(sd, lq, ref, case["cfg"]["heads"])
+        meta = dict(case, oracle_vs_reference_max=float((y - yo).abs().max()))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), out=y.numpy())
+        print(name, tuple(y.shape), float(y.abs().max()), "oracle vs reference", meta["oracle_vs_reference_max"])
+
+
+def main_drsformer():
+    from . import drsformer as OD
+    torch.set_grad_enabled(False)
+    for name, case in DRS_CASES.items():
+        net = R.drsformer_ref_fusion(spa=case["spa"], **case["cfg"]).eval()
+        sd = W.load_seeded(net, case["seed"])
+        lq, ref = guided_inputs(case)
+        y = net(lq, ref)
+        yo = OD.drsformer_ref_fusion_forward(sd, lq, ref, case["cfg"]["heads"])
         meta = dict(case, oracle_vs_reference_max=float((y - yo).abs().max()))
         np.savez_compressed(os.path.join(OUT, name + ".npz"), meta=json.dumps(meta), out=y.numpy())
         print(name, tuple(y.shape), float(y.abs().max()), "oracle vs reference", meta["oracle_vs_reference_max"])
@@ -253,3 +280,4 @@ if __name__ == "__main__":
     main_nafnet()
     main_vit()
     main_promptir()
+    main_drsformer()

@@ -70,6 +70,21 @@ def promptir_ref_fusion(**kw):
     return net
 
 
+def drsformer_ref_fusion(spa=False, **kw):
+    if spa:
+        # the shipped 200L_SPA file uses functools.partial without importing functools (NameError in Encoder.__init__,
+        # i.e. option 007 cannot construct its network upstream): the missing name is injected, the source is untouched
+        import functools
+        mod = load_arch("network_drsformer_guided_arch_200L_SPA")
+        mod.functools = functools
+        net = mod.DRSformer200L_SPA_RefFusion(**kw)
+    else:
+        net = load_arch("network_drsformer_guided_arch").DRSformerRefFusion(**kw)
+    orig = net.masa_enc.forward
+    net.masa_enc.forward = lambda x: [None] + orig(x)   # B1 index shim (same Encoder class as the guided Restormer)
+    return net
+
+
 def nafnet(**kw):
     return load_arch("network_nafnet_guided_arch").NAFNet(**kw)
 

@@ -816,6 +816,86 @@ def check_promptir():
     return out
 
 
+def check_drsformer():
+    """the DRSformer family -- top-k sparse attention fold, generic grouped / depthwise stencils, MEFC gate
+    and per-sample reduction weights against torch, then both networks against the golden fixtures made by the unmodified
+    reference modules (options 007 and 008-010)."""
+    from oracle import weights as Wt
+    from oracle.make_golden import guided_inputs
+    from textualdegremoval_b200.archs import define_network
+    ops = _ops()
+    out = []
+    # TKSA: attn = sum_i w_i softmax(top-k_i masked scores), folded into project_out
+    for (C2, heads, Hh, Ww, Bb) in ((48, 1, 16, 24, 2), (96, 2, 12, 12, 1), (192, 2, 8, 8, 1)):
+        c = C2 // heads
+        qkv = q(rnd(Bb, 3 * C2, Hh, Ww, seed=C2 + heads))
+        temp = torch.rand(heads, generator=torch.Generator().manual_seed(1)) + 0.5
+        wpo = rnd(C2, C2, seed=2) / C2 ** 0.5
+        tw = torch.tensor([0.2, 0.35, 0.15, 0.3])
+        qq, kk, vv = qkv.view(Bb, 3, heads, c, Hh * Ww).unbind(1)
+        qn = qq / qq.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        kn = kk / kk.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+        sc = qn @ kn.transpose(-1, -2) * temp.view(1, heads, 1, 1)
+        attn = torch.zeros_like(sc)
+        for wi, k_ in zip(tw, (int(c / 2), int(c * 2 / 3), int(c * 3 / 4), int(c * 4 / 5))):
+            idx = torch.topk(sc, k=k_, dim=-1)[1]
+            mask = torch.zeros_like(sc).scatter_(-1, idx, 1.)
+            attn = attn + wi * torch.where(mask > 0, sc, torch.full_like(sc, float("-inf"))).softmax(-1)
+        weff_ref = torch.zeros(Bb, C2, C2)
+        for h in range(heads):
+            weff_ref[:, :, h * c:(h + 1) * c] = wpo[:, h * c:(h + 1) * c] @ attn[:, h]
+        weff, attn_g = ops.mdta_weff(nhwc(qkv.to(BF16)), C2, heads, temp.to(DEV), wpo.to(DEV), want_attn=True,
+                                     topk_w=tw.to(DEV))
+        out.append(result(f"tksa_attn_C{C2}_h{heads}", attn_g, attn, 2e-3))
+        out.append(result(f"tksa_weff_C{C2}_h{heads}", weff[..., :C2], weff_ref, 8e-3))
+    # generic stencils against F.conv2d on the same 16-bit-rounded inputs
+    B, H, W, C_ = 2, 19, 45, 24
+    x = q(rnd(B, C_, H, W, seed=5))
+    x16 = nhwc(x.to(BF16))
+    idx = torch.arange(C_, dtype=torch.int32, device=DEV)
+    for K, dil in ((1, 1), (3, 1), (5, 1), (7, 1), (3, 2), (5, 2), (7, 2)):
+        w = rnd(C_, 1, K, K, seed=K + dil) / K
+        o = torch.empty(B, H, W, C_, dtype=BF16, device=DEV)
+        ops.grouped_stencil(x16, idx, w.to(DEV), None, K, o, dil=dil, relu=(K == 5))
+        want = F.conv2d(x, w, padding=dil * (K - 1) // 2, dilation=dil, groups=C_)
+        out.append(result(f"stencil_dw_k{K}_d{dil}", o.permute(0, 3, 1, 2), F.relu(want) if K == 5 else want, 8e-3))
+    o = torch.empty(B, H, W, C_, dtype=BF16, device=DEV)
+    ops.grouped_stencil(x16, idx, None, None, 3, o, pool=True)
+    out.append(result("stencil_avgpool3", o.permute(0, 3, 1, 2), F.avg_pool2d(x, 3, 1, 1, count_include_pad=False), 8e-3))
+    for K in (3, 5):                                     # Conv2d(2h, h, K, groups=h) over a permuted channel table
+        hch = 11
+        perm = torch.randperm(2 * hch, generator=torch.Generator().manual_seed(K))
+        w = rnd(hch, 2, K, K, seed=20 + K) / K
+        bias = rnd(hch, seed=30 + K)
+        xin = q(rnd(B, C_, H, W, seed=6))
+        o = torch.zeros(B, H, W, 16, dtype=BF16, device=DEV)
+        ops.grouped_stencil(nhwc(xin.to(BF16)), perm.to(torch.int32).to(DEV), w.to(DEV), bias.to(DEV), K, o[..., 3:3 + hch],
+                            relu=True)
+        want = F.relu(F.conv2d(xin[:, perm], w, bias, padding=K // 2, groups=hch))
+        out.append(result(f"stencil_grouped_k{K}", o[..., 3:3 + hch].permute(0, 3, 1, 2), want, 8e-3))
+    # MEFC gate and per-sample reduction weights
+    emb = rnd(3, 32, seed=7)
+    w1, b1, w2, b2 = rnd(64, 32, seed=8) * 0.2, rnd(64, seed=9), rnd(32, 64, seed=10) * 0.2, rnd(32, seed=11)
+    g = ops.mefc_gate(emb.to(DEV), w1.to(DEV), b1.to(DEV), w2.to(DEV), b2.to(DEV), 8)
+    g_ref = torch.softmax(F.linear(F.relu(F.linear(emb, w1, b1)), w2, b2).view(3, 4, 8), -1)
+    out.append(result("mefc_gate", g, g_ref, 1e-5))
+    wo = rnd(16, 8 * 16, seed=12)
+    wm = ops.mefc_mix_weights(wo.to(DEV), g[:, 2], 16, BF16)
+    out.append(result("mefc_mix_weights", wm[..., :128], wo.unsqueeze(0) * g_ref[:, 2].repeat_interleave(16, -1).unsqueeze(1), 8e-3))
+    # end to end
+    for name, typ in (("guided_drsformer_spa_128", "DRSformer200L_SPA_RefFusion"), ("guided_drsformer_128", "DRSformerRefFusion")):
+        meta, ref = _golden(name)
+        net = define_network(dict(type=typ, **meta["cfg"]))
+        Wt.load_seeded(net, meta["seed"])
+        net = net.to(DEV).eval()
+        lq, rf = guided_inputs(meta)
+        with torch.no_grad():
+            y = net(lq.to(DEV), rf.to(DEV)).cpu()
+        out.append(guided_result(f"golden_{name}", y, ref))
+        out.append(psnr_delta_result(name, y, ref, meta["seed"]))
+    return out
+
+
 class _ForcedMatches:
     """Test hook: run a guided net with the ORACLE's coarse / fine matches instead of its own arg-max results (the
     confidence is re-read from our own correlation at the forced index).  Around 1 % of the fine searches of a
@@ -1677,6 +1757,7 @@ CHECKS = {
     "guided_golden": check_guided_golden,
     "nafnet": check_nafnet,
     "promptir": check_promptir,
+    "drsformer": check_drsformer,
     "vit": check_vit,
     "optim": check_optim,
     "wgrad": check_wgrad,

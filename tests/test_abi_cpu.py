@@ -226,3 +226,17 @@ def test_promptir_state_dict_keys_match_reference():
     net._check = lambda *ts: None                       # get past the CUDA-tensor check: the shape error comes first
     with torch.no_grad(), pytest.raises(RuntimeError, match="expected input to have 192 channels, but got 384"):
         net(torch.rand(1, 3, 64, 64), torch.rand(1, 3, 64, 64))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="/root/reference not present")
+def test_drsformer_state_dict_keys_match_reference():
+    """DRSformerRefFusion / DRSformer200L_SPA_RefFusion (N3): same keys, order and shapes as the reference classes."""
+    from oracle import ref_loader as R
+    from textualdegremoval_b200 import define_network
+    cfg = dict(dim=16, num_blocks=[1, 2, 1, 1], heads=[1, 2, 4, 8], nf=16, ext_n_blocks=[2, 1, 1, 1],
+               reffusion_n_blocks=[1, 2, 1, 1], LayerNorm_type="WithBias", bias=True)
+    for spa, typ in ((False, "DRSformerRefFusion"), (True, "DRSformer200L_SPA_RefFusion")):
+        a = define_network(dict(type=typ, **cfg)).state_dict()
+        b = R.drsformer_ref_fusion(spa=spa, **cfg).state_dict()
+        assert list(a) == list(b), typ
+        assert all(a[k].shape == b[k].shape for k in b), typ

@@ -42,6 +42,7 @@ def overlaid(tmp_path_factory):
     for d in ("models", "utils", "losses", "metrics", "options", "data"):
         shutil.copytree(os.path.join(REF, d), os.path.join(tree, d))
     for rel in ("models/archs/restormer_b200_arch.py", "models/archs/nafnet_b200_arch.py",
+                "models/archs/promptir_b200_arch.py", "models/archs/drsformer_b200_arch.py",
                 "models/image_restoration_ref_b200_model.py"):
         shutil.copyfile(os.path.join(ROOT, "integration", rel), os.path.join(tree, rel))
     saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("models", "utils", "losses", "metrics", "data")}
@@ -67,7 +68,8 @@ def _network_g(tree, stem):
 
 
 @pytest.mark.parametrize("stem,params", [("003_", 60_096_138), ("017_", 60_075_402), ("002_", 253_219_395),
-                                         ("004_0", None)])
+                                         ("004_0", None), ("001_", None), ("007_", None), ("008_", None), ("009_", None),
+                                         ("010_", None)])
 def test_reference_registry_resolves_to_b200_classes(overlaid, stem, params):
     archs = importlib.import_module("models.archs")            # the reference's own registry, scanning the overlaid dir
     opt = _network_g(overlaid, stem)["network_g"]

@@ -47,6 +47,8 @@ class PromptIRRefFusion(MasaMixin, nn.Module):
     _check = RestormerRefFusion._check
     _prep_key = RestormerRefFusion._prep_key
     prepared = RestormerRefFusion.prepared
+    _run_stack = staticmethod(run_stack)
+    _after_patch_embed = RestormerRefFusion._after_patch_embed
     dual_pixel_task = False
 
     def __init__(self, inp_channels=3, out_channels=3, dim=48, num_blocks=[4, 6, 6, 8], num_refinement_blocks=4,

@@ -219,6 +219,11 @@ def run_stack(x32, preps, xn=None, nxt=None, tail=None):
 class _RestormerBase(nn.Module):
     """Shared U-Net body (:412-461) + decoder schedule."""
 
+    _run_stack = staticmethod(run_stack)       # block-stack runner (the DRSformer family swaps in its own blocks)
+
+    def _after_patch_embed(self, P, x32):      # hook: DRSformer's MEFC ``encoder_level0`` runs here
+        pass
+
     def _build_body(self, inp_channels, out_channels, dim, num_blocks, num_refinement_blocks, heads,
                     ffn_expansion_factor, bias, LayerNorm_type, dual_pixel_task, fusion_blocks=None):
         kw = dict(ffn_expansion_factor=ffn_expansion_factor, bias=bias, LayerNorm_type=LayerNorm_type)
@@ -438,18 +443,20 @@ class RestormerRefFusion(GuidedRestormerTrainMixin, MasaTrainMixin, MasaMixin, _
             aux.update(feat_lq=f_lq, feat_ref=f_ref, deep32_lq=lq_d32, deep32_ref=ref_d32, deep_scale=self._masa_last_scale[-1],
                        warps=[fbuf[i][..., d[i]:].clone() for i in range(4)])
         ops.conv3x3_small_ci(lq32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=fbuf[0][..., :d[0]])
+        self._after_patch_embed(P, fbuf[0][..., :d[0]])
         enc_names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
         downs = [None, "down1_2", "down2_3", "down3_4"]
         xs = []
         for i in range(4):
             if i:
                 self._down(xs[-1], P[downs[i]], fbuf[i][..., :d[i]])
-            run_stack(fbuf[i], P[f"masa_blk_enc_level{i + 1}"])      # fuse on 2C channels, keep the first C (:907-909)
+            if not (i == 0 and getattr(self, "skip_level1_fusion", False)):
+                self._run_stack(fbuf[i], P[f"masa_blk_enc_level{i + 1}"])  # fuse on 2C channels, keep the first C (:907-909)
             x = fbuf[i][..., :d[i]]
             if i == 0 and self.dual_pixel_task:                      # skip_conv reads inp_enc_level1 (:957-959); the
                 x_in1 = torch.empty((B, h, w, d[0]), dtype=F32, device=dev)     # encoder stack updates x in place
                 ops.copy_rows(x, dst32=x_in1)
-            run_stack(x, P[enc_names[i]])
+            self._run_stack(x, P[enc_names[i]])
             xs.append(x)
         return xs, x_in1, lq32, (oh, ow), aux, fbuf
 

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libtdr_sm100.so")
-SOURCES = ["tdr_runtime.cu", "tdr_conv_gemm.cu", "tdr_mdta.cu", "tdr_pointwise.cu", "tdr_masa.cu", "tdr_vit.cu", "tdr_vit_attn.cu", "tdr_prompt.cu", "tdr_optim.cu", "tdr_backward.cu", "tdr_input.cu", "tdr_gdfn.cu"]
+SOURCES = ["tdr_runtime.cu", "tdr_conv_gemm.cu", "tdr_mdta.cu", "tdr_pointwise.cu", "tdr_masa.cu", "tdr_vit.cu", "tdr_vit_attn.cu", "tdr_prompt.cu", "tdr_stencil_generic.cu", "tdr_optim.cu", "tdr_backward.cu", "tdr_input.cu", "tdr_gdfn.cu"]
 HEADERS = ["tdr_common.cuh", "tdr_stencil.cuh", os.path.join("..", "..", "include", "tdr_sm100.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 

@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(256) mdta_gram_generic_kernel(const uint16_t* 
 template <int T>   // T * 32 >= c columns per attention row: 4 (c <= 128) or 8 (wide heads)
 __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restrict__ partials, int C, int heads,
                                                            int nchunks, const float* __restrict__ temperature,
-                                                           float* __restrict__ attn, float* __restrict__ shat_out) {
+                                                           float* __restrict__ attn, float* __restrict__ shat_out,
+                                                           const float* __restrict__ topk_w) {
   const int c = C / heads;
   const int h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -333,6 +334,52 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
     }
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float* out = attn + ((size_t)(b * heads + h) * c + i) * c;
+  if (topk_w) {
+    // Top-k sparse attention (DRSformer TKSA, network_drsformer_guided_arch.py:296-327): four softmaxes over the
+    // int(c/2), int(2c/3), int(3c/4), int(4c/5) largest entries of the row, mixed with the learnable attn1..attn4.
+    int rank[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) rank[t] = 0;
+    for (int tt = 0; tt < T; ++tt) {
+      for (int src = 0; src < 32; ++src) {
+        const int jj = src + 32 * tt;
+        if (jj >= c) break;
+        float mine = 0.f;
+#pragma unroll
+        for (int t = 0; t < T; ++t) mine = t == tt ? g[t] : mine;
+        const float v = __shfl_sync(0xffffffffu, mine, src);
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+          const int j = lane + 32 * t;
+          rank[t] += (j < c && (v > g[t] || (v == g[t] && jj < j))) ? 1 : 0;
+        }
+      }
+    }
+    const int kk[4] = {(int)(c / 2.0), (int)(c * 2 / 3.0), (int)(c * 3 / 4.0), (int)(c * 4 / 5.0)};
+    float e[T], s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int j = lane + 32 * t;
+      e[t] = j < c ? __expf(g[t] - mx) : 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s4[q] += (j < c && rank[t] < kk[q]) ? e[t] : 0.f;
+    }
+    float coef[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) coef[q] = topk_w[q] / warp_sum(s4[q]);
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const int j = lane + 32 * t;
+      if (j < c) {
+        float wsum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wsum += rank[t] < kk[q] ? coef[q] : 0.f;
+        out[j] = e[t] * wsum;
+      }
+    }
+    return;
+  }
   float sum = 0.f;
 #pragma unroll
   for (int t = 0; t < T; ++t) {
@@ -344,7 +391,6 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
   }
   sum = warp_sum(sum);
   const float inv = 1.f / sum;
-  float* out = attn + ((size_t)(b * heads + h) * c + i) * c;
 #pragma unroll
   for (int t = 0; t < T; ++t) {
     const int j = lane + 32 * t;
@@ -429,15 +475,15 @@ extern "C" int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long lon
 
 extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, int heads, const float* temperature,
                              const float* w_out, void* weff_bf16, long long weff_ld, float* attn_ws,
-                             void* weff_t_bf16, float* shat_out, int fp16, cudaStream_t stream) {
+                             void* weff_t_bf16, float* shat_out, int fp16, const float* topk_w, cudaStream_t stream) {
   TDR_CHECK_ARG(partials && temperature && w_out && weff_bf16 && attn_ws, "tdr_mdta_weff: null pointer");
   GramPlan p;
   TDR_CHECK_ARG(make_plan(B, P, C, heads, &p) == 0, "tdr_mdta_weff: unsupported head width");
   TDR_CHECK_ARG(weff_ld >= C && weff_ld % 8 == 0, "tdr_mdta_weff: bad weff_ld");
   {
     dim3 grid(p.c, heads, B);
-    if (p.c <= 128) mdta_softmax_kernel<4><<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out);
-    else mdta_softmax_kernel<8><<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out);
+    if (p.c <= 128) mdta_softmax_kernel<4><<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out, topk_w);
+    else mdta_softmax_kernel<8><<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out, topk_w);
     TDR_CHECK_LAUNCH();
   }
   const size_t smem = ((size_t)p.c * p.c + kFoldRows * p.c) * sizeof(float);

@@ -1,0 +1,198 @@
+// Generic grouped / depthwise K x K stencil (K in {1, 3, 5, 7}, any dilation with dil * (K - 1) / 2 <= 6) over NHWC 16-bit
+// activations, for the DRSformer family of the reference (/root/reference/models/archs/network_drsformer_guided_arch.py):
+//   * MSFN feed-forward :216-256 -- depthwise 3x3 / 5x5 + ReLU on the 2h hidden channels, then the grouped convs
+//     ``Conv2d(2h, h, k, groups=h)`` (two input channels per output channel) over the re-interleaved halves;
+//   * MEFC experts :454-520 -- SepConv / DilConv depthwise stages (1x1 .. 7x7, dilation 2), AvgPool2d(3, count_include_pad
+//     = False) :440.
+// Every output channel names its ``ipg`` (1 or 2) input channels through an index table, so the chunk / cat re-orderings
+// of the reference (:243-252) are address arithmetic, never copies.  A CTA computes an 8 x 32 pixel tile of 8 output
+// channels from a haloed fp32 tile in shared memory (each staged value is reused K*K times); fp32 accumulation.
+// These layers are HBM / shared-memory-bound byte work on CUDA cores; the 3x3 depthwise convs of the Restormer blocks keep
+// their dedicated TMA kernel (tdr_dwconv3x3).
+#include "tdr_common.cuh"
+
+namespace {
+
+constexpr int kTH = 8, kTW = 32, kCo = 8;        // tile: 8 rows x 32 columns x 8 output channels
+
+struct StencilArgs {
+  const uint16_t* in; long long in_ld;
+  int B, H, W, Co, ipg, K, dil, act, pool, fp16;
+  const int* idx; const float* w; const float* bias;
+  uint16_t* out; long long out_ld;
+  int tiles_x, tiles_y;
+};
+
+__global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs a) {
+  extern __shared__ float tile[];                  // [nci][TH + 2p][TW + 2p]
+  __shared__ int s_idx[kCo * 2];
+  const int p = a.dil * (a.K - 1) / 2;
+  const int th = kTH + 2 * p, tw = kTW + 2 * p;
+  const int nci = kCo * a.ipg;
+  int t = blockIdx.x;
+  const int tx = t % a.tiles_x; t /= a.tiles_x;
+  const int ty = t % a.tiles_y;
+  const int b = t / a.tiles_y;
+  const int co0 = blockIdx.y * kCo;
+  const int y0 = ty * kTH, x0 = tx * kTW;
+  if (threadIdx.x < nci) {
+    const int co = co0 + threadIdx.x / a.ipg;
+    s_idx[threadIdx.x] = co < a.Co ? a.idx[(size_t)co * a.ipg + threadIdx.x % a.ipg] : -1;
+  }
+  __syncthreads();
+  // stage the haloed input tile: consecutive threads read consecutive (mostly contiguous) channels of one pixel
+  const uint16_t* img = a.in + (size_t)b * a.H * a.W * a.in_ld;
+  for (int i = threadIdx.x; i < th * tw * nci; i += blockDim.x) {
+    const int ci = i % nci, px = i / nci;
+    const int yy = y0 - p + px / tw, xx = x0 - p + px % tw;
+    const int ch = s_idx[ci];
+    float v = 0.f, d;
+    if (ch >= 0 && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W)
+      unpack2r(img[((size_t)yy * a.W + xx) * a.in_ld + ch], v, d, a.fp16);
+    tile[(ci * th + px / tw) * tw + px % tw] = v;
+  }
+  __syncthreads();
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+  const int y = y0 + ly, x = x0 + lx;
+  if (y >= a.H || x >= a.W) return;
+  uint16_t* orow = a.out + (((size_t)b * a.H + y) * a.W + x) * a.out_ld;
+  const int kk = a.K * a.K;
+  uint16_t res[kCo];
+  const int nco = a.Co - co0 < kCo ? a.Co - co0 : kCo;
+#pragma unroll 1
+  for (int c = 0; c < kCo; ++c) {
+    const int co = co0 + c;
+    if (co >= a.Co) { res[c] = 0; continue; }
+    float acc = a.bias ? a.bias[co] : 0.f;
+    if (a.pool) {                                  // AvgPool2d(3, 1, 1, count_include_pad=False)
+      int cnt = 0;
+      for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+          const int yy = y + ky - 1, xx = x + kx - 1;
+          if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+            ++cnt;
+            acc += tile[(c * th + ly + ky) * tw + lx + kx];
+          }
+        }
+      acc /= (float)cnt;
+    } else {
+      for (int j = 0; j < a.ipg; ++j) {
+        const float* tp = tile + (size_t)(c * a.ipg + j) * th * tw;
+        const float* wp = a.w + ((size_t)co * a.ipg + j) * kk;
+        for (int ky = 0; ky < a.K; ++ky)
+          for (int kx = 0; kx < a.K; ++kx)
+            acc = fmaf(wp[ky * a.K + kx], tp[(ly + ky * a.dil) * tw + lx + kx * a.dil], acc);
+      }
+    }
+    if (a.act == 1) acc = fmaxf(acc, 0.f);
+    res[c] = pack1r(acc, a.fp16);
+  }
+  if (nco == kCo && ((reinterpret_cast<uintptr_t>(orow + co0) & 15) == 0)) {      // one 16-byte store per pixel
+    uint4 v;
+    v.x = res[0] | ((uint32_t)res[1] << 16); v.y = res[2] | ((uint32_t)res[3] << 16);
+    v.z = res[4] | ((uint32_t)res[5] << 16); v.w = res[6] | ((uint32_t)res[7] << 16);
+    *reinterpret_cast<uint4*>(orow + co0) = v;
+  } else {
+    for (int c = 0; c < nco; ++c) orow[co0 + c] = res[c];
+  }
+}
+
+// MEFC gate (OALayer.forward :423-432 + the softmax of subnet.forward :541-543): one CTA per sample,
+//   out[b, s, :] = softmax_over_ops( W2 relu(W1 emb[b] + b1) + b2 ) viewed as [steps, num_ops]
+__global__ void __launch_bounds__(128) mefc_gate_kernel(const float* __restrict__ emb, long long emb_ld, int C,
+                                                        const float* __restrict__ w1, const float* __restrict__ b1, int H1,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2, int O,
+                                                        int num_ops, float* __restrict__ out) {
+  __shared__ float h[256], o[256];
+  const int b = blockIdx.x;
+  const float* e = emb + (size_t)b * emb_ld;
+  for (int i = threadIdx.x; i < H1; i += blockDim.x) {
+    float s = b1 ? b1[i] : 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(w1[(size_t)i * C + c], e[c], s);
+    h[i] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < O; i += blockDim.x) {
+    float s = b2 ? b2[i] : 0.f;
+    for (int c = 0; c < H1; ++c) s = fmaf(w2[(size_t)i * H1 + c], h[c], s);
+    o[i] = s;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < O; i += blockDim.x) {
+    const int g0 = i / num_ops * num_ops;
+    float mx = -INFINITY, sum = 0.f;
+    for (int j = 0; j < num_ops; ++j) mx = fmaxf(mx, o[g0 + j]);
+    for (int j = 0; j < num_ops; ++j) sum += expf(o[g0 + j] - mx);
+    out[(size_t)b * O + i] = expf(o[i] - mx) / sum;
+  }
+}
+
+// Per-sample weights of OperationLayer._out (:378-388): states[k] = op_k(x) * w[b, k] are concatenated and reduced by a 1x1
+// conv, i.e. the conv's weight columns of block k are scaled by w[b, k]:  out16[b][co][k*C + ci] = W[co][k*C + ci] * gate[b, k]
+__global__ void mefc_mix_weights_kernel(const float* __restrict__ w, int Co, int Ci, int C, const float* __restrict__ gate,
+                                        long long gate_ld, int B, uint16_t* __restrict__ out, long long ld, int fp16) {
+  const long long total = (long long)B * Co * Ci;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Ci);
+    const int co = (int)((i / Ci) % Co);
+    const int b = (int)(i / ((long long)Ci * Co));
+    out[((size_t)b * Co + co) * ld + ci] = pack1r(w[(size_t)co * Ci + ci] * gate[(size_t)b * gate_ld + ci / C], fp16);
+  }
+}
+
+}  // namespace
+
+extern "C" int tdr_mefc_gate(const float* emb, long long emb_ld, int B, int C, const float* w1, const float* b1, int H1,
+                             const float* w2, const float* b2, int O, int num_ops, float* out, cudaStream_t stream) {
+  TDR_CHECK_ARG(emb && w1 && w2 && out && B > 0 && C > 0 && H1 > 0 && H1 <= 256 && O > 0 && O <= 256 && num_ops > 0 &&
+                O % num_ops == 0 && emb_ld >= C, "tdr_mefc_gate: bad arguments (hidden / output widths <= 256)");
+  mefc_gate_kernel<<<B, 128, 0, stream>>>(emb, emb_ld, C, w1, b1, H1, w2, b2, O, num_ops, out);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_mefc_mix_weights(const float* weight, int Co, int Ci, int C, const float* gate, long long gate_ld, int B,
+                                    void* out16, long long ld, int fp16, cudaStream_t stream) {
+  TDR_CHECK_ARG(weight && gate && out16 && Co > 0 && Ci > 0 && C > 0 && Ci % C == 0 && B > 0 && ld >= Ci && ld % 8 == 0,
+                "tdr_mefc_mix_weights: bad arguments");
+  const long long total = (long long)B * Co * Ci;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mefc_mix_weights_kernel<<<(unsigned)blocks, 256, 0, stream>>>(weight, Co, Ci, C, gate, gate_ld, B,
+                                                               reinterpret_cast<uint16_t*>(out16), ld, fp16);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+// out16[b, y, x, co] = act( bias[co] + sum_{j < ipg} sum_{taps} w[co][j][ky][kx] * in16[b, y + (ky - K/2) dil, x + (kx - K/2) dil, idx[co * ipg + j]] )
+// zero padding; pool != 0: AvgPool2d(3, stride 1, padding 1, count_include_pad=False) of channel idx[co] (w ignored).
+// ``out16`` points at the first output slot (a channel slice of a wider buffer is fine); fp16: IEEE fp16 rows, else bf16.
+extern "C" int tdr_grouped_stencil(const void* in16, long long in_ld, int B, int H, int W, int Co, int ipg, const int* idx,
+                                   const float* weight, const float* bias, int K, int dil, int act, int pool, void* out16,
+                                   long long out_ld, int fp16, cudaStream_t stream) {
+  TDR_CHECK_ARG(in16 && out16 && idx && (weight || pool) && B > 0 && H > 0 && W > 0 && Co > 0,
+                "tdr_grouped_stencil: bad arguments");
+  TDR_CHECK_ARG((ipg == 1 || ipg == 2) && (K == 1 || K == 3 || K == 5 || K == 7) && dil >= 1 && dil * (K - 1) / 2 <= 6,
+                "tdr_grouped_stencil: ipg in {1, 2}, K in {1, 3, 5, 7}, dil * (K - 1) / 2 <= 6 (got ipg %d K %d dil %d)", ipg, K, dil);
+  TDR_CHECK_ARG(!pool || (K == 3 && dil == 1 && ipg == 1), "tdr_grouped_stencil: pooling is 3x3, one input channel");
+  TDR_CHECK_ARG(act == 0 || act == 1, "tdr_grouped_stencil: act must be 0 or 1 (ReLU)");
+  StencilArgs a;
+  a.in = reinterpret_cast<const uint16_t*>(in16); a.in_ld = in_ld;
+  a.B = B; a.H = H; a.W = W; a.Co = Co; a.ipg = ipg; a.K = K; a.dil = dil; a.act = act; a.pool = pool; a.fp16 = fp16 ? 1 : 0;
+  a.idx = idx; a.w = weight; a.bias = bias;
+  a.out = reinterpret_cast<uint16_t*>(out16); a.out_ld = out_ld;
+  a.tiles_x = tdr_cdiv(W, kTW); a.tiles_y = tdr_cdiv(H, kTH);
+  const int p = dil * (K - 1) / 2;
+  const size_t smem = (size_t)kCo * ipg * (kTH + 2 * p) * (kTW + 2 * p) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  TDR_CHECK_ARG(smem <= 64 * 1024, "tdr_grouped_stencil: tile does not fit (%zu bytes)", smem);
+  TDR_CHECK_ARG((long long)a.tiles_x * a.tiles_y * B < (1LL << 31) && tdr_cdiv(Co, kCo) <= 65535, "tdr_grouped_stencil: grid");
+  dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), (unsigned)tdr_cdiv(Co, kCo));
+  grouped_stencil_kernel<<<grid, 256, smem, stream>>>(a);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}

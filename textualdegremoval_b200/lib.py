@@ -82,13 +82,16 @@ SIGNATURES = {
     "tdr_naf_sca_fold": (_i, [_vp, _ll, _i, _ll, _i, _vp, _vp, _vp, _i, _vp, _vp, _ll, _vp, _vp, _vp, _vp, _ll, _i, _vp]),
     "tdr_mdta_partials_bytes": (_sz, [_i, _ll, _i, _i]),
     "tdr_mdta_gram": (_i, [_vp, _ll, _i, _ll, _i, _i, _vp, _i, _vp]),
-    "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _i, _vp]),
+    "tdr_mdta_weff": (_i, [_vp, _i, _ll, _i, _i, _vp, _vp, _vp, _ll, _vp, _vp, _vp, _i, _vp, _vp]),
+    "tdr_grouped_stencil": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _ll, _i, _vp]),
     "tdr_vit_patchify": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _ll, _vp]),
     "tdr_vit_assemble_tokens": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tdr_softmax_rows": (_i, [_vp, _ll, _ll, _i, _f, _vp, _ll, _vp]),
     "tdr_vit_transpose_v": (_i, [_vp, _ll, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "tdr_vit_attention_supported": (_i, [_i]),
     "tdr_vit_attention": (_i, [_vp, _ll, _i, _i, _i, _i, _f, _vp, _ll, _vp]),
+    "tdr_mefc_gate": (_i, [_vp, _ll, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp]),
+    "tdr_mefc_mix_weights": (_i, [_vp, _i, _i, _i, _vp, _ll, _i, _vp, _ll, _i, _vp]),
     "tdr_prompt_weights": (_i, [_vp, _ll, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "tdr_prompt_mix_resize": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _ll, _i, _vp]),
     "tdr_crop_resize": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp]),

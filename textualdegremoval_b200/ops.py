@@ -374,9 +374,10 @@ def gdfn_tail(hid, w9, bias_dw, w_out, Cc, bias=None, scale_ptr=None, res1=None,
     return out
 
 
-def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False, save=None):
+def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False, save=None, topk_w=None):
     """qkv: bf16 NHWC [B,H,W,>=3C].  Returns Weff bf16 [B, C, C_p] (and attn fp32 [B,heads,c,c]).
-    save: optional dict that receives partials / attn / weff / weff_t (what the backward pass needs)."""
+    save: optional dict that receives partials / attn / weff / weff_t (what the backward pass needs).
+    topk_w: optional fp32 [4] device tensor -> top-k sparse attention mix (DRSformer TKSA)."""
     B, H, W, _ = qkv.shape
     P = H * W
     nbytes = lib.load().tdr_mdta_partials_bytes(B, P, C_, heads)
@@ -395,7 +396,7 @@ def mdta_weff(qkv, C_, heads, temperature, w_out, want_attn=False, save=None):
         weff_t = torch.zeros((B, C_, cp), dtype=BF16, device=qkv.device)
         shat = torch.empty((B, heads, c * c + 2 * c), dtype=F32, device=qkv.device)
     _call("tdr_mdta_weff", _p(partials), B, P, C_, heads, _p(temperature), _p(w_out), _p(weff), cp, _p(attn),
-          _p(weff_t), _p(shat), h16, _stream(), tag=f"C{C_}_h{heads}", nbytes=nbytes + _nb(weff))
+          _p(weff_t), _p(shat), h16, _p(topk_w), _stream(), tag=f"C{C_}_h{heads}", nbytes=nbytes + _nb(weff))
     if save is not None:
         save.update(shat=shat, attn=attn, weff=weff, weff_t=weff_t)
     return (weff, attn) if want_attn else weff
@@ -644,6 +645,38 @@ def vit_transpose_v(qkv, heads, hd, voff, n_pad):
     vt = torch.empty((B, heads, hd, n_pad), dtype=BF16, device=qkv.device)
     _call("tdr_vit_transpose_v", _p(qkv), _ld(qkv), B, N, heads, hd, voff, _p(vt), n_pad, _stream())
     return vt
+
+
+def grouped_stencil(x16, idx, weight, bias, K, out16, dil=1, relu=False, pool=False):
+    """Generic grouped / depthwise stencil (tdr_grouped_stencil): x16 NHWC 16-bit view; idx int32 [Co * ipg] input channel
+    table; weight fp32 [Co, ipg, K, K]; out16: NHWC 16-bit view whose channel count is Co (a slice of a wider buffer)."""
+    B, H, W, _ = x16.shape
+    Co = out16.shape[-1]
+    ipg = idx.numel() // Co
+    assert ipg * Co == idx.numel() and out16.dtype == x16.dtype
+    _call("tdr_grouped_stencil", _p(x16), _ld(x16), B, H, W, Co, ipg, _p(idx), _p(weight), _p(bias), K, dil, int(relu),
+          int(pool), _p(out16), _ld(out16), int(x16.dtype == F16), _stream(), tag=f"k{K}d{dil}g{ipg}_C{Co}",
+          nbytes=B * H * W * (Co * ipg + Co) * 2)
+    return out16
+
+
+def mefc_gate(emb, w1, b1, w2, b2, num_ops):
+    """softmax over ops of Linear(ReLU(Linear(emb))): emb fp32 [B, C] -> fp32 [B, steps, num_ops] (tdr_mefc_gate)."""
+    B, C_ = emb.shape
+    H1, O = w1.shape[0], w2.shape[0]
+    out = torch.empty((B, O // num_ops, num_ops), dtype=F32, device=emb.device)
+    _call("tdr_mefc_gate", _p(emb), emb.stride(0), B, C_, _p(w1), _p(b1), H1, _p(w2), _p(b2), O, num_ops, _p(out), _stream())
+    return out
+
+
+def mefc_mix_weights(w32, gate, C_, dt):
+    """w32 fp32 [Co, n*C]; gate fp32 [B, n] view (row stride gate.stride(0)) -> 16-bit per-sample weights [B, Co, ld]."""
+    Co, Ci = w32.shape
+    B = gate.shape[0]
+    ld = round_up(Ci, 8)
+    out = torch.empty((B, Co, ld), dtype=dt, device=w32.device)
+    _call("tdr_mefc_mix_weights", _p(w32), Co, Ci, C_, _p(gate), gate.stride(0), B, _p(out), ld, int(dt == F16), _stream())
+    return out
 
 
 def prompt_weights(emb, weight, bias):
