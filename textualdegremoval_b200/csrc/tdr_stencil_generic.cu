@@ -6,7 +6,8 @@
 //     = False) :440.
 // Every output channel names its ``ipg`` (1 or 2) input channels through an index table, so the chunk / cat re-orderings
 // of the reference (:243-252) are address arithmetic, never copies.  A CTA computes an 8 x 32 pixel tile of 8 output
-// channels from a haloed fp32 tile in shared memory (each staged value is reused K*K times); fp32 accumulation.
+// channels from a haloed fp32 tile in shared memory (each staged value is reused K*K times); fp32 accumulation;
+// a thread owns 2 channels x 4 adjacent pixels with the taps in registers.
 // These layers are HBM / shared-memory-bound byte work on CUDA cores; the 3x3 depthwise convs of the Restormer blocks keep
 // their dedicated TMA kernel (tdr_dwconv3x3).
 #include "tdr_common.cuh"
@@ -23,10 +24,14 @@ struct StencilArgs {
   int tiles_x, tiles_y;
 };
 
+// Thread mapping: 256 threads = 4 channel pairs x 64 pixel quads; a thread computes 2 output channels x 4 horizontally
+// adjacent pixels.  Per (channel, input, tap row) it loads the 4 + (K-1) dil staged values once and reuses each for up to K
+// outputs; the K*K taps of the channel sit in registers (K is a template parameter, so the loops unroll).
+template <int K>
 __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs a) {
   extern __shared__ float tile[];                  // [nci][TH + 2p][TW + 2p]
   __shared__ int s_idx[kCo * 2];
-  const int p = a.dil * (a.K - 1) / 2;
+  const int p = a.dil * (K - 1) / 2;
   const int th = kTH + 2 * p, tw = kTW + 2 * p;
   const int nci = kCo * a.ipg;
   int t = blockIdx.x;
@@ -40,60 +45,115 @@ __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs 
     s_idx[threadIdx.x] = co < a.Co ? a.idx[(size_t)co * a.ipg + threadIdx.x % a.ipg] : -1;
   }
   __syncthreads();
-  // stage the haloed input tile: consecutive threads read consecutive (mostly contiguous) channels of one pixel
+  // stage the haloed input tile.  Fast path: the CTA's input channels are groups of 8 contiguous, 16-byte aligned
+  // channels (depthwise tables, and grouped tables away from the half boundary): one 128-bit load per (pixel, group).
   const uint16_t* img = a.in + (size_t)b * a.H * a.W * a.in_ld;
-  for (int i = threadIdx.x; i < th * tw * nci; i += blockDim.x) {
-    const int ci = i % nci, px = i / nci;
-    const int yy = y0 - p + px / tw, xx = x0 - p + px % tw;
-    const int ch = s_idx[ci];
-    float v = 0.f, d;
-    if (ch >= 0 && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W)
-      unpack2r(img[((size_t)yy * a.W + xx) * a.in_ld + ch], v, d, a.fp16);
-    tile[(ci * th + px / tw) * tw + px % tw] = v;
+  bool vec = (a.in_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && co0 + kCo <= a.Co;
+  for (int i = 0; i < nci && vec; ++i) vec = s_idx[i] == s_idx[i & ~7] + (i & 7) && (s_idx[i & ~7] & 7) == 0;
+  if (vec) {
+    const int ng = nci >> 3;
+    for (int i = threadIdx.x; i < th * tw * ng; i += blockDim.x) {
+      const int g = i % ng, px = i / ng;
+      const int yy = y0 - p + px / tw, xx = x0 - p + px % tw;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) unpack8r(img + ((size_t)yy * a.W + xx) * a.in_ld + s_idx[g * 8], v, a.fp16);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) tile[((g * 8 + e) * th + px / tw) * tw + px % tw] = v[e];
+    }
+  } else {
+    for (int i = threadIdx.x; i < th * tw * nci; i += blockDim.x) {
+      const int ci = i % nci, px = i / nci;
+      const int yy = y0 - p + px / tw, xx = x0 - p + px % tw;
+      const int ch = s_idx[ci];
+      float v = 0.f, d;
+      if (ch >= 0 && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W)
+        unpack2r(img[((size_t)yy * a.W + xx) * a.in_ld + ch], v, d, a.fp16);
+      tile[(ci * th + px / tw) * tw + px % tw] = v;
+    }
   }
   __syncthreads();
-  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-  const int y = y0 + ly, x = x0 + lx;
-  if (y >= a.H || x >= a.W) return;
-  uint16_t* orow = a.out + (((size_t)b * a.H + y) * a.W + x) * a.out_ld;
-  const int kk = a.K * a.K;
-  uint16_t res[kCo];
-  const int nco = a.Co - co0 < kCo ? a.Co - co0 : kCo;
-#pragma unroll 1
-  for (int c = 0; c < kCo; ++c) {
-    const int co = co0 + c;
-    if (co >= a.Co) { res[c] = 0; continue; }
-    float acc = a.bias ? a.bias[co] : 0.f;
+  const int cp = threadIdx.x >> 6, q = threadIdx.x & 63;          // channel pair, pixel quad
+  const int ly = q >> 3, lx = (q & 7) * 4;
+  const int y = y0 + ly;
+  constexpr int NV = 4 + (K - 1) * 2;                              // staged values per tap row at dil <= 2
+  uint16_t res[2][4];
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {
+    const int c = cp * 2 + cc, co = co0 + c;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) res[cc][i] = 0;
+    if (co >= a.Co || y >= a.H) continue;
+    float acc[4];
+    const float bias = a.bias ? a.bias[co] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] = bias;
     if (a.pool) {                                  // AvgPool2d(3, 1, 1, count_include_pad=False)
-      int cnt = 0;
-      for (int ky = 0; ky < 3; ++ky)
-        for (int kx = 0; kx < 3; ++kx) {
-          const int yy = y + ky - 1, xx = x + kx - 1;
-          if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
-            ++cnt;
-            acc += tile[(c * th + ly + ky) * tw + lx + kx];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int x = x0 + lx + i;
+        int cnt = 0;
+        float sum = 0.f;
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx) {
+            const int yy = y + ky - 1, xx = x + kx - 1;
+            if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
+              ++cnt;
+              sum += tile[(c * th + ly + ky) * tw + lx + i + kx];
+            }
           }
-        }
-      acc /= (float)cnt;
+        acc[i] = cnt ? sum / (float)cnt : 0.f;
+      }
     } else {
       for (int j = 0; j < a.ipg; ++j) {
         const float* tp = tile + (size_t)(c * a.ipg + j) * th * tw;
-        const float* wp = a.w + ((size_t)co * a.ipg + j) * kk;
-        for (int ky = 0; ky < a.K; ++ky)
-          for (int kx = 0; kx < a.K; ++kx)
-            acc = fmaf(wp[ky * a.K + kx], tp[(ly + ky * a.dil) * tw + lx + kx * a.dil], acc);
+        const float* wp = a.w + ((size_t)co * a.ipg + j) * (K * K);
+        float w[K * K];
+#pragma unroll
+        for (int i = 0; i < K * K; ++i) w[i] = __ldg(wp + i);
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+          const float* row = tp + (ly + ky * a.dil) * tw + lx;
+          float v[NV];
+          const int nv = 4 + (K - 1) * a.dil;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) v[i] = i < nv ? row[i] : 0.f;
+          if (a.dil == 1) {
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[i] = fmaf(w[ky * K + kx], v[i + kx], acc[i]);
+          } else {
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[i] = fmaf(w[ky * K + kx], v[i + 2 * kx], acc[i]);
+          }
+        }
       }
     }
-    if (a.act == 1) acc = fmaxf(acc, 0.f);
-    res[c] = pack1r(acc, a.fp16);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) res[cc][i] = pack1r(a.act == 1 ? fmaxf(acc[i], 0.f) : acc[i], a.fp16);
   }
-  if (nco == kCo && ((reinterpret_cast<uintptr_t>(orow + co0) & 15) == 0)) {      // one 16-byte store per pixel
-    uint4 v;
-    v.x = res[0] | ((uint32_t)res[1] << 16); v.y = res[2] | ((uint32_t)res[3] << 16);
-    v.z = res[4] | ((uint32_t)res[5] << 16); v.w = res[6] | ((uint32_t)res[7] << 16);
-    *reinterpret_cast<uint4*>(orow + co0) = v;
-  } else {
-    for (int c = 0; c < nco; ++c) orow[co0 + c] = res[c];
+  // results -> shared memory [pixel][8 channels] (over the consumed input tile), then one 128-bit store per pixel
+  __syncthreads();
+  uint16_t* so = reinterpret_cast<uint16_t*>(tile);
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) so[(ly * kTW + lx + i) * kCo + cp * 2 + cc] = res[cc][i];
+  __syncthreads();
+  {
+    const int px = threadIdx.x, py = px / kTW, pxx = px % kTW;
+    const int yy = y0 + py, xx = x0 + pxx;
+    if (yy < a.H && xx < a.W) {
+      uint16_t* dst = a.out + (((size_t)b * a.H + yy) * a.W + xx) * a.out_ld + co0;
+      const int nco = a.Co - co0 < kCo ? a.Co - co0 : kCo;
+      if (nco == kCo && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(so + px * kCo);
+      } else {
+        for (int c = 0; c < nco; ++c) dst[c] = so[px * kCo + c];
+      }
+    }
   }
 }
 
@@ -172,8 +232,8 @@ extern "C" int tdr_grouped_stencil(const void* in16, long long in_ld, int B, int
                                    long long out_ld, int fp16, cudaStream_t stream) {
   TDR_CHECK_ARG(in16 && out16 && idx && (weight || pool) && B > 0 && H > 0 && W > 0 && Co > 0,
                 "tdr_grouped_stencil: bad arguments");
-  TDR_CHECK_ARG((ipg == 1 || ipg == 2) && (K == 1 || K == 3 || K == 5 || K == 7) && dil >= 1 && dil * (K - 1) / 2 <= 6,
-                "tdr_grouped_stencil: ipg in {1, 2}, K in {1, 3, 5, 7}, dil * (K - 1) / 2 <= 6 (got ipg %d K %d dil %d)", ipg, K, dil);
+  TDR_CHECK_ARG((ipg == 1 || ipg == 2) && (K == 1 || K == 3 || K == 5 || K == 7) && (dil == 1 || dil == 2),
+                "tdr_grouped_stencil: ipg in {1, 2}, K in {1, 3, 5, 7}, dil in {1, 2} (got ipg %d K %d dil %d)", ipg, K, dil);
   TDR_CHECK_ARG(!pool || (K == 3 && dil == 1 && ipg == 1), "tdr_grouped_stencil: pooling is 3x3, one input channel");
   TDR_CHECK_ARG(act == 0 || act == 1, "tdr_grouped_stencil: act must be 0 or 1 (ReLU)");
   StencilArgs a;
@@ -186,13 +246,21 @@ extern "C" int tdr_grouped_stencil(const void* in16, long long in_ld, int B, int
   const size_t smem = (size_t)kCo * ipg * (kTH + 2 * p) * (kTW + 2 * p) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
   }
   TDR_CHECK_ARG(smem <= 64 * 1024, "tdr_grouped_stencil: tile does not fit (%zu bytes)", smem);
   TDR_CHECK_ARG((long long)a.tiles_x * a.tiles_y * B < (1LL << 31) && tdr_cdiv(Co, kCo) <= 65535, "tdr_grouped_stencil: grid");
   dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), (unsigned)tdr_cdiv(Co, kCo));
-  grouped_stencil_kernel<<<grid, 256, smem, stream>>>(a);
+  switch (K) {
+    case 1: grouped_stencil_kernel<1><<<grid, 256, smem, stream>>>(a); break;
+    case 3: grouped_stencil_kernel<3><<<grid, 256, smem, stream>>>(a); break;
+    case 5: grouped_stencil_kernel<5><<<grid, 256, smem, stream>>>(a); break;
+    default: grouped_stencil_kernel<7><<<grid, 256, smem, stream>>>(a); break;
+  }
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
