@@ -507,6 +507,12 @@ typedef struct tdr_patch_desc {
 int tdr_prepare_patches(const tdr_patch_desc* descs_device, const tdr_patch_desc* descs_host /* same content, validated */,
                         int n, int channels, int out_h, int out_w, int bgr2rgb, const float* mean /* host [channels] or NULL */,
                         const float* stdv /* host [channels] or NULL */, float* out, cudaStream_t stream);
+/* Training noise of the Gaussian-denoising datasets (data/restoration_dataset.py:474-476): out = img + fl(n * level[b]) with
+ * level[b] = sigma_b / 255 per sample (device array; `sigma_type` constant / random / choice is the caller's draw).
+ * noise != NULL: n = caller-supplied standard normals (bit-identical to the reference's mul_ / add_ for that draw);
+ * noise == NULL: n from a Philox4x32-10 stream keyed by (seed, sample, element) + Box-Muller (no host RNG, no H2D copy). */
+int tdr_add_gaussian_noise(const float* img, const float* noise, const float* level_device, int B, long long per_sample,
+                           unsigned long long seed, float* out, cudaStream_t stream);
 
 /* Validation PSNR (use_image: true) without a device->host image copy: per image the exact integer
  * sum (q1 - q2)^2 over the crop_border-trimmed window and max(q1), q = tensor2img's uint8 quantisation

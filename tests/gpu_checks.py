@@ -499,6 +499,30 @@ def check_input_pipeline():
     gray = rng.randint(0, 256, (20, 20, 1)).astype(np.uint8)
     got = ops.prepare_patches([torch.from_numpy(gray).to(DEV)], [(2, 3, 6)], 16)
     out.append(result("prepare_patches_gray_rot270", got, torch.from_numpy(IP.prepare_patch(gray, 2, 3, 6, 16))[None], 0.0))
+    # training noise (data/restoration_dataset.py:474-476): with the reference's own CPU draw the result is bit-identical
+    g = torch.Generator().manual_seed(9)
+    img = torch.rand(3, 3, 64, 80, generator=g)
+    sig = [15.0, 37.5, 50.0]
+    noise = torch.randn(img.shape, generator=g)
+    want = torch.stack([img[b].clone().add_(noise[b].clone().mul_(torch.FloatTensor([sig[b]]) / 255.0).float()) for b in range(3)])
+    got = ops.add_gaussian_noise(img.to(DEV), sig, noise=noise.to(DEV))
+    out.append(result("gaussian_noise_given_draw", got, want, 0.0))
+    # device-side draw (Philox + Box-Muller): moments, reproducibility from the seed, independence of samples / seeds
+    big = torch.zeros(2, 3, 512, 512, device=DEV)
+    z1 = ops.add_gaussian_noise(big, 255.0, seed=1234)
+    z2 = ops.add_gaussian_noise(big, 255.0, seed=1234)
+    z3 = ops.add_gaussian_noise(big, 255.0, seed=1235)
+    n = z1.numel()
+    zz = z1.double()
+    mean, var = zz.mean().item(), zz.var().item()
+    kurt = ((zz - mean) ** 4).mean().item() / var ** 2
+    tail = (zz.abs() > 3).double().mean().item()                     # P(|z| > 3) = 2.6998e-3
+    corr = lambda a, b: float((a.double().flatten() * b.double().flatten()).mean())
+    stats = dict(mean=abs(mean) < 5 / n ** 0.5, var=abs(var - 1) < 5e-3, kurt=abs(kurt - 3) < 3e-2, tail=abs(tail - 2.6998e-3) < 3e-4,
+                 same_seed=bool((z1 == z2).all()), other_seed=abs(corr(z1, z3)) < 5e-3, samples=abs(corr(z1[0], z1[1])) < 5e-3,
+                 neighbours=abs(corr(z1.flatten()[:-1], z1.flatten()[1:])) < 5e-3)
+    out.append(dict(name="gaussian_noise_device_draw", max_err=0.0 if all(stats.values()) else 1.0, tol=0.0, ok=all(stats.values()),
+                    note=f"mean {mean:.2e} var {var:.5f} kurtosis {kurt:.4f} P(|z|>3) {tail:.3e}; {stats}"))
     return out
 
 

@@ -155,3 +155,73 @@ extern "C" int tdr_psnr_u8_sums(const float* img1, const float* img2, int B, int
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
+
+
+// ------------------------------------------------------------------------------------------------ Gaussian training noise
+// Dataset_GaussianDenoisingWithRef.__getitem__ (data/restoration_dataset.py:474-476):
+//     noise_level = sigma / 255;  noise = torch.randn(img.size()).mul_(noise_level);  img_lq.add_(noise)
+// on the device.  Two modes: (a) `noise` given (standard normals drawn by the caller, e.g. from the reference's CPU
+// generator): out = img + fl(noise * level), the same two roundings as mul_ / add_, i.e. bit-identical to the reference
+// for that draw; (b) `noise` null: standard normals from a counter-based Philox4x32-10 stream keyed by (seed, sample,
+// element / 4) + Box-Muller, so a batch needs no host RNG, no H2D copy of the noise and is reproducible from the seed.
+namespace {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void gaussian_noise_kernel(const float* __restrict__ img, const float* __restrict__ noise,
+                                      const float* __restrict__ level, long long per_sample, int B,
+                                      unsigned long long seed, float* __restrict__ out) {
+  const long long quads = (per_sample + 3) / 4;
+  const long long total = quads * B;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / quads);
+    const long long qd = i % quads;
+    const float lv = level[b];
+    float z[4];
+    if (!noise) {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)qd, (uint32_t)(qd >> 32), (uint32_t)b, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+      // two Box-Muller pairs from four 32-bit words; u in (0, 1]
+      const float u0 = ((float)r[0] + 1.0f) * 2.3283064365386963e-10f, u1 = ((float)r[2] + 1.0f) * 2.3283064365386963e-10f;
+      const float a0 = (float)r[1] * 1.4629180792671596e-9f, a1 = (float)r[3] * 1.4629180792671596e-9f;   // 2 pi / 2^32
+      const float m0 = sqrtf(-2.f * logf(u0)), m1 = sqrtf(-2.f * logf(u1));
+      float s0, c0, s1, c1;
+      sincosf(a0, &s0, &c0);
+      sincosf(a1, &s1, &c1);
+      z[0] = m0 * c0; z[1] = m0 * s0; z[2] = m1 * c1; z[3] = m1 * s1;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long j = qd * 4 + e;
+      if (j < per_sample) {
+        const long long o = (long long)b * per_sample + j;
+        const float n = noise ? noise[o] : z[e];
+        out[o] = __fadd_rn(img[o], __fmul_rn(n, lv));         // mul_ then add_: two roundings, no FMA contraction
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int tdr_add_gaussian_noise(const float* img, const float* noise, const float* level_device, int B,
+                                      long long per_sample, unsigned long long seed, float* out, cudaStream_t stream) {
+  TDR_CHECK_ARG(img && level_device && out && B > 0 && per_sample > 0, "tdr_add_gaussian_noise: bad arguments");
+  const long long total = (per_sample + 3) / 4 * B;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 16) blocks = 148LL * 16;
+  gaussian_noise_kernel<<<(unsigned)blocks, 256, 0, stream>>>(img, noise, level_device, per_sample, B, seed, out);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}

@@ -982,6 +982,27 @@ def prepare_patches(frames, crops, size, bgr2rgb=True, mean=None, std=None, out=
     return out
 
 
+def add_gaussian_noise(img, sigma, noise=None, seed=0, out=None):
+    """Training noise of the Gaussian-denoising datasets (data/restoration_dataset.py:474-476) on the device.
+    img: fp32 CUDA [B, ...]; sigma: per-sample noise levels in 8-bit units (float, sequence or tensor) -> img + n * sigma/255.
+    noise: standard normals with img's shape (then the result equals the reference's for that draw, bit for bit);
+    None: drawn on the device from a Philox stream keyed by ``seed`` (reproducible, no host RNG)."""
+    assert img.dtype == F32 and img.is_cuda and img.is_contiguous()
+    B = img.shape[0]
+    lv = torch.as_tensor(sigma, dtype=F32).reshape(-1)
+    if lv.numel() == 1:
+        lv = lv.expand(B)
+    assert lv.numel() == B
+    lv = (lv / 255.0).contiguous().to(img.device)       # torch.FloatTensor([sigma]) / 255.0, as the reference computes it
+    if noise is not None:
+        assert noise.shape == img.shape and noise.dtype == F32 and noise.is_cuda and noise.is_contiguous()
+    if out is None:
+        out = torch.empty_like(img)
+    _call("tdr_add_gaussian_noise", _p(img), _p(noise), _p(lv), B, img.numel() // B, int(seed), _p(out), _stream(),
+          nbytes=img.numel() * (12 if noise is not None else 8))
+    return out
+
+
 def psnr_u8(result, gt, crop_border=0):
     """Validation PSNR of ``calculate_psnr(tensor2img(result), tensor2img(gt), crop_border)`` (metrics/psnr_ssim.py:9-63,
     utils/utils_image.py:129-191; ``test_y_channel=False``) per image of fp32 NCHW CUDA batches: the uint8 quantisation
