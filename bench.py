@@ -468,9 +468,10 @@ def _run_b200(args, out):
                 ext = vit_base(img_size=518, patch_size=14, init_values=1.0, ffn_layer="mlp", block_chunks=0).to(dev).eval()
                 tr.net_ext = ext
                 tr.feed_train_data(dict(lq=lq_h, gt=gt_h, ref=ref_h))
-                tr.optimize_parameters()
+                for _ in range(2):          # two warm-up steps: the ViT's buffers join the allocator's cached blocks
+                    tr.optimize_parameters()
                 barrier()
-                train["ms_dino"] = timed(lambda: tr.optimize_parameters(), 2) / 2
+                train["ms_dino"] = timed(lambda: tr.optimize_parameters(), 3) / 3
                 barrier()
             except Exception as e:  # noqa: BLE001
                 train["ms_dino"] = None
