@@ -74,6 +74,10 @@ struct ConvGemmArgs {
   int stages;                   // smem pipeline depth; in halo mode: depth of the haloed-A ring
   int epi_bufs;                 // staging buffers per epilogue warp (1 or 2; 4 with the fused LayerNorm)
   int alt_items;                // TMA epilogue (no LN): the two warp groups take alternate items
+  int pair;                     // streamed-weight multi-tap convs (C >= 96 dense 3x3): TWO pixel tiles share every weight
+                                // tile of the ring (M = 256 per B fetch, two TMEM accumulators): the per-tile weight
+                                // re-fetch was ~2/3 of the L2 -> SM traffic, which bounds these convs
+  int pair_tiles;               // ceil(m_tiles / 2) * n_tiles
   // division by n_tiles / tiles per image / tiles_x as multiply-high + shift (every role recomputes its item's
   // coordinates per item; the epilogue warps spent 13 % of their samples in the integer-division sequences)
   uint32_t fd_nt_m, fd_nt_s, fd_tpi_m, fd_tpi_s, fd_tx_m, fd_tx_s;
@@ -94,6 +98,14 @@ __device__ __forceinline__ int fdiv(int n, uint32_t m, uint32_t s) {
   return m ? (int)(__umulhi((uint32_t)n, m) >> s) : n;
 }
 __device__ __forceinline__ bool conv_item(const ConvGemmArgs& a, int it, int& mt, int& nt) {
+  if (a.pair) {                                   // items 2q, 2q + 1 = the two pixel tiles of pair q (same n tile); an odd
+    const int tile = blockIdx.x + (it >> 1) * gridDim.x;      // tail yields a ghost tile past the last image: its TMA loads
+    if (tile >= a.pair_tiles) return false;                   // are zero fill and its TMA stores are clipped
+    const int mp = fdiv(tile, a.fd_nt_m, a.fd_nt_s);
+    nt = tile - mp * a.n_tiles;
+    mt = 2 * mp + (it & 1);
+    return true;
+  }
   if (a.by_pixel) {
     const int q = fdiv(it, a.fd_nt_m, a.fd_nt_s);
     mt = blockIdx.x + q * gridDim.x;
@@ -138,7 +150,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
   const int b_bytes = a.BN * kChunkK * 2;
   uint8_t* smem_a = smem;
   const int kStages = a.stages;
-  const int a_ring_bytes = a.halo ? kStages * a.halo_bytes : kStages * kABytes;
+  const int a_stage_bytes = a.pair ? 2 * kABytes : kABytes;
+  const int a_ring_bytes = a.halo ? kStages * a.halo_bytes : kStages * a_stage_bytes;
   uint8_t* smem_b = smem + a_ring_bytes;
   const int b_ring_bytes = a.halo ? a.KH * a.KW * a.kchunks * b_bytes
                                   : (a.resident_b ? a.n_tiles * a.kchunks * b_bytes : kStages * b_bytes);
@@ -223,6 +236,26 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
             mbar_expect_tx(&full[stage], a.halo_tx);
             tma_load_4d(smem_a + stage * a.halo_bytes, &map_a, &full[stage], kc * kChunkK, org_x + ox0 - a.pad,
                         org_y + oy0 - a.pad, img);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
+        if (a.pair) {
+          if (sq & 1) continue;                  // one producer pass per pair: item sq + 1 is the second pixel tile
+          int b1, ty1, tx1;
+          conv_tile_coords(a, mt + 1, tiles_per_img, b1, ty1, tx1);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const int tap = ks / a.kchunks;
+            const int kc = ks % a.kchunks;
+            const int ky = tap / a.KW, kx = tap % a.KW;
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], 2 * kABytes + b_bytes);
+            uint8_t* sa = smem_a + stage * a_stage_bytes;
+            tma_load_4d(sa, &map_a, &full[stage], kc * kChunkK, ox0 * a.stride - a.pad + kx * a.dil,
+                        oy0 * a.stride - a.pad + ky * a.dil, b);
+            tma_load_4d(sa + kABytes, &map_a, &full[stage], kc * kChunkK, tx1 * a.TW * a.stride - a.pad + kx * a.dil,
+                        ty1 * a.TH * a.stride - a.pad + ky * a.dil, b1);
+            tma_load_3d(smem_b + stage * b_bytes, &map_w, &full[stage], kc * kChunkK, nt * a.BN, tap);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
           continue;
@@ -328,6 +361,38 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
             }
             umma_commit(&empty[stage]);
             if (kc == a.kchunks - 1) umma_commit(&tfull[acc]);
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
+      if (a.pair) {
+        if (it & 1) continue;                    // the pair's second item shares this pass (its accumulator is acc + 1)
+        const int acc1 = (it + 1) % a.nacc;
+        mbar_wait(&tempty[acc1], (((it + 1) / a.nacc) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem1 = tmem_base + acc1 * a.BN;
+        for (int ks = 0, kc = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const int nk = kc < a.kchunks - 1 ? kChunkK / 16 : klast;
+          if (++kc == a.kchunks) kc = 0;
+          if (elect_one()) {
+            const uint64_t da0 = umma_desc_sw128(smem_u32(smem_a + stage * a_stage_bytes), 0, 1024);
+            const uint64_t da1 = umma_desc_sw128(smem_u32(smem_a + stage * a_stage_bytes + kABytes), 0, 1024);
+            const uint64_t db = umma_desc_sw128(smem_u32(smem_b + stage * b_bytes), 0, 1024);
+#pragma unroll
+            for (int k = 0; k < kChunkK / 16; ++k)
+              if (k < nk) {
+                umma_bf16(d_tmem, da0 + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+                umma_bf16(d_tmem1, da1 + 2 * k, db + 2 * k, idesc, (ks | k) != 0);
+              }
+            umma_commit(&empty[stage]);
+            if (ks == ksteps - 1) {
+              umma_commit(&tfull[acc]);
+              umma_commit(&tfull[acc1]);
+            }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -1041,7 +1106,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     const size_t bt = (size_t)a.BN * kChunkK * 2;
     const size_t ring = a.halo ? (size_t)a.stages * a.halo_bytes + (size_t)d->KH * d->KW * a.kchunks * bt
                                : (a.resident_b ? (size_t)a.stages * kABytes + (size_t)a.n_tiles * a.kchunks * bt
-                                               : (size_t)a.stages * (kABytes + bt));
+                                               : (size_t)a.stages * ((a.pair ? 2 : 1) * kABytes + bt));
     return 1024 + ring + (size_t)kEpiWarps * a.epi_bufs * kEpiStageBytes + 1024 + (want_ln ? 2 * kEpiWarps * 32 * 8 : 0);
   };
   // Resident-B mode (1x1 convs with shared weights and many pixel tiles per CTA): the whole weight matrix stays in shared
@@ -1094,6 +1159,14 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
       a.epi_bufs = d->res1 ? 2 : 1;
     }
   }
+  // Pair mode: streamed-weight multi-tap convs with many pixel tiles per CTA (dense 3x3 at C >= 96, stride 1 or 2).
+  a.pair = 0;
+  if (a.epi_mode == 1 && !want_ln && !a.halo && !a.resident_b && d->impl == 0 && d->KH * d->KW > 1 && !d->w_batched &&
+      !d->origin && !d->rowscale && (a.n_tiles == 1 || d->Co % a.BN == 0) && 2 * a.BN <= 512 &&
+      (long long)d->B * a.tiles_y * a.tiles_x * a.n_tiles >= 2LL * tdr_num_sms() && getenv("TDR_CONV_NO_PAIR") == nullptr) {
+    a.pair = 1;
+    if (a.stages > 4) a.stages = 4;
+  }
   const bool bufs_forced = getenv("TDR_CONV_EPIBUFS") != nullptr;
   while (smem_need() > 227 * 1024) {
     if ((bufs_forced || want_ln) && a.stages > 2) --a.stages;
@@ -1110,6 +1183,8 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   // there are many pixel tiles per SM
   a.by_pixel = (a.n_tiles > 1 && d->Co % a.BN != 0 && a.m_tiles >= 8 * tdr_num_sms()) ? 1 : 0;
   if (a.resident_b) a.by_pixel = 1;
+  a.pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
+  if (a.pair && (a.by_pixel || a.stages < 3)) a.pair = 0;
   // accumulator ring: as many BN-column buffers as fit in the 512 TMEM columns (2..4) -- a deeper ring keeps more
   // tiles between the MMA issuer and the epilogue in flight
   a.nacc = 512 / a.BN;
@@ -1192,8 +1267,12 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
     if (rc) return rc;
   }
   const size_t smem = smem_need();
+  if (getenv("TDR_CONV_DEBUG"))
+    fprintf(stderr, "conv_gemm plan: Ci %d Co %d k%d BN %d n_tiles %d stages %d epi_bufs %d halo %d resident %d pair %d by_pixel %d nacc %d\n",
+            d->Ci, d->Co, d->KH, a.BN, a.n_tiles, a.stages, a.epi_bufs, a.halo, a.resident_b, a.pair, a.by_pixel, a.nacc);
   int grid = a.total_tiles < tdr_num_sms() ? a.total_tiles : tdr_num_sms();
   if (a.by_pixel && grid > a.m_tiles) grid = a.m_tiles;
+  if (a.pair && grid > a.pair_tiles) grid = a.pair_tiles;
   int variant = a.epi_mode == 1 ? (a.out_is_f32 | (d->res2 ? 2 : 0) | (d->res1 ? 4 : 0) | (want_ln ? 8 : 0)) : -1;
   if (variant == 0 && a.out_fp16) variant = 16;
   if (variant == 11 && a.out_fp16) variant = 27;

@@ -129,6 +129,10 @@ PROBES = {
     "c3x3_48": lambda: conv(8, 512, 512, 48, 48, k=3, relu=True),
     "c3x3_96": lambda: conv(8, 256, 256, 96, 96, k=3, relu=True),
     "c3x3_384": lambda: conv(8, 64, 64, 384, 384, k=3, relu=True),
+    "c3x3_192": lambda: conv(8, 128, 128, 192, 192, k=3, relu=True),
+    "c3x3_256": lambda: conv(8, 128, 128, 256, 256, k=3, relu=True),
+    "c3x3_512": lambda: conv(8, 64, 64, 512, 512, k=3, relu=True),
+    "c3x3_96s2": lambda: conv(8, 256, 256, 96, 192, k=3, relu=True, stride=2),
     "dwg512": lambda: dw(4, 512, 512, 512, 1),
     "dw288": lambda: dw(4, 512, 512, 288, 0),
     "dw288_ld320": lambda: dw(4, 512, 512, 288, 0, pitched=True),
