@@ -1161,7 +1161,7 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   }
   // Pair mode: streamed-weight multi-tap convs with many pixel tiles per CTA (dense 3x3 at C >= 96, stride 1 or 2).
   a.pair = 0;
-  if (a.epi_mode == 1 && !want_ln && !a.halo && !a.resident_b && d->impl == 0 && d->KH * d->KW > 1 && !d->w_batched &&
+  if (a.epi_mode == 1 && !want_ln && !a.halo && !a.resident_b && d->impl == 0 && (d->KH * d->KW > 1 || getenv("TDR_CONV_PAIR_1X1") != nullptr) && !d->w_batched &&
       !d->origin && !d->rowscale && (a.n_tiles == 1 || d->Co % a.BN == 0) && 2 * a.BN <= 512 &&
       (long long)d->B * a.tiles_y * a.tiles_x * a.n_tiles >= 2LL * tdr_num_sms() && getenv("TDR_CONV_NO_PAIR") == nullptr) {
     a.pair = 1;
