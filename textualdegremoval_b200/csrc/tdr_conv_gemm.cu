@@ -1164,8 +1164,10 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
   if (a.epi_mode == 1 && !want_ln && !a.halo && !a.resident_b && d->impl == 0 && (d->KH * d->KW > 1 || getenv("TDR_CONV_PAIR_1X1") != nullptr) && !d->w_batched &&
       !d->origin && !d->rowscale && (a.n_tiles == 1 || d->Co % a.BN == 0) && 2 * a.BN <= 512 &&
       (long long)d->B * a.tiles_y * a.tiles_x * a.n_tiles >= 2LL * tdr_num_sms() && getenv("TDR_CONV_NO_PAIR") == nullptr) {
-    a.pair = 1;
-    if (a.stages > 4) a.stages = 4;
+    // BN = 256 leaves two accumulators, both owned by the pair: no MMA / epilogue overlap.  With short K (Ci <= 256) that
+    // loss outweighs the saved traffic (256->256 @128^2: 126 -> 144 us), with long K it does not (512->512: 128 -> 114 us)
+    a.pair = (a.BN > 192 && a.kchunks < 6) ? 0 : 1;
+    if (a.pair && a.stages > 4) a.stages = 4;
   }
   const bool bufs_forced = getenv("TDR_CONV_EPIBUFS") != nullptr;
   while (smem_need() > 227 * 1024) {
