@@ -440,6 +440,10 @@ int tdr_gather_vec(const float* v, const int* map, int n, int n_src, float* out,
 int tdr_nchw_to_nhwc(const float* src, int B, int C, int H, int W, int pad_h, int pad_w /* zero-padded output size */,
                      float* dst_f32, long long dst_f32_ld, void* dst_bf16, long long dst_bf16_ld, cudaStream_t stream);
 /* dst[b,c,y,x] = src[b,y,x,c] (+ res[b,y,x,c], e.g. the `+ inp_img` of R:499,962), cropped to out_h x out_w. */
+/* NCHW fp32 image -> dense 16-bit NHWC rows [B, pad_h, pad_w, C16], zero beyond (C, H, W): the 16-byte-row operand that lets
+ * the image-boundary 3x3 convs (OverlapPatchEmbed :362-370, Encoder.conv_L1 :106) run on tdr_conv_gemm. */
+int tdr_image_to_rows16(const float* src, int B, int C, int H, int W, int pad_h, int pad_w, int C16, void* dst16, int fp16,
+                        cudaStream_t stream);
 int tdr_nhwc_to_nchw(const float* src, long long src_ld, int B, int C, int H, int W /* source size */, int out_h,
                      int out_w /* crop */, const float* res /* NHWC fp32 or NULL */, long long res_ld, float* dst,
                      cudaStream_t stream);

@@ -61,7 +61,8 @@ class MasaMixin:
         nlev = self.masa_enc.levels
         for i in range(1, nlev + 1):
             c = getattr(self.masa_enc, f"conv_L{i}")
-            enc[f"conv_L{i}"] = dict(w=_f(c.weight), b=_f(c.bias)) if i == 1 else prep_conv_f16(c)
+            enc[f"conv_L{i}"] = dict(w=_f(c.weight), b=_f(c.bias), w16=ops.pack_conv(c.weight, Ci_p=8, dt=F16)[0],
+                                     Co=c.out_channels) if i == 1 else prep_conv_f16(c)
             enc[f"blk_L{i}"] = [(prep_conv_f16(b.conv1), prep_conv_f16(b.conv2))
                                 for b in getattr(self.masa_enc, f"blk_L{i}")]
         # biases grouped by the level scale they are expressed in (see _masa_encode): group L = the residual blocks of
@@ -96,7 +97,7 @@ class MasaMixin:
     # first activation (tdr_masa_level_scale: no host sync; scaling by 2^k changes no mantissa, so the result does not
     # depend on the choice).  Biases enter as b / s_L; the bf16 level outputs are multiplied back; the searches are
     # scale-invariant (cosine similarities), so the deepest fp32 features stay in scaled units.
-    def _masa_encode(self, E, img32, tape=None):
+    def _masa_encode(self, E, img32, tape=None, img16=None):
         """Returns (feats, deep32): bf16 NHWC features per level (finest first, unscaled) and the fp32 deepest-level
         stream (in units of its level scale).  tape: optional dict that receives every saved activation (scaled units)
         and the level-scale states ``S`` (training forward)."""
@@ -106,8 +107,13 @@ class MasaMixin:
         nlev = self.masa_enc.levels
         S = E["state_init"].clone()              # S[l] = {s, 1/s, 1/r, max}; level 1 is unscaled
         x32 = torch.empty((B, H, W, self.masa_enc.nf), dtype=F32, device=dev)
-        xh = torch.empty((B, H, W, self.masa_enc.nf), dtype=F16, device=dev)
-        ops.conv3x3_small_ci(img32, E["conv_L1"]["w"], E["conv_L1"]["b"], relu=True, out_f32=x32, out_bf16=xh)
+        xh = torch.empty((B, H, W, self.masa_enc.nf), dtype=F16, device=dev) if img16 is None else None
+        if img16 is not None:       # tensor-core path: 8-channel fp16 image rows, K = 16 per tap, then one cast pass
+            ops.conv_gemm(img16, E["conv_L1"]["w16"], E["conv_L1"]["Co"], Ci=8, k=3, pad=1, bias=E["conv_L1"]["b"], relu=True,
+                          out_f32=x32)
+            _, xh = ops.cast_rows(x32, want_bf16=False, want_fp16=True)
+        else:
+            ops.conv3x3_small_ci(img32, E["conv_L1"]["w"], E["conv_L1"]["b"], relu=True, out_f32=x32, out_bf16=xh)
         xb = None
         bias_next = None                         # conv_L{lvl+1}'s bias in units of s_lvl
         for lvl in range(1, nlev + 1):

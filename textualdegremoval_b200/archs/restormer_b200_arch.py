@@ -284,6 +284,8 @@ class _RestormerBase(nn.Module):
         for name in ["reduce_chan_level3", "reduce_chan_level2"]:
             P[name] = _prep_conv(getattr(self, name), dt)
         P["patch_embed"] = dict(w=_f(self.patch_embed.proj.weight), b=_f(self.patch_embed.proj.bias))
+        if not train and self.patch_embed.proj.in_channels <= 8:
+            P["patch_embed"]["w16"] = ops.pack_conv(self.patch_embed.proj.weight, Ci_p=8, dt=dt)[0]
         # output conv (:640): 3 (or 1) output channels are zero-padded to 8 so that it runs on the tensor-core path
         ow = self.output.weight
         co = ow.shape[0]
@@ -367,7 +369,11 @@ class Restormer(RestormerTrainMixin, _RestormerBase):
         dev = inp_img.device
         inp32 = ops.nchw_to_nhwc(inp_img, H, W)
         x1 = torch.empty((B, H, W, d[0]), dtype=F32, device=dev)
-        ops.conv3x3_small_ci(inp32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=x1)
+        if ops.SMALL_CI_TC and "w16" in P["patch_embed"]:
+            ops.conv_gemm(ops.image_to_rows16(inp_img, H, W, F16), P["patch_embed"]["w16"], d[0], Ci=8, k=3, pad=1,
+                          bias=P["patch_embed"]["b"], out_f32=x1)
+        else:
+            ops.conv3x3_small_ci(inp32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=x1)
         x_in1 = x1.clone() if self.dual_pixel_task else None
         e1 = run_stack(x1, P["encoder_level1"])
         e2 = torch.empty((B, H // 2, W // 2, d[1]), dtype=F32, device=dev)
@@ -431,18 +437,32 @@ class RestormerRefFusion(GuidedRestormerTrainMixin, MasaTrainMixin, MasaMixin, _
             lq32, ref32 = both[:B], both[B:]
             ops.nchw_to_nhwc_into(inp_img, h, w, dst32=lq32)
             ops.nchw_to_nhwc_into(ref_img, hr, wr, dst32=ref32)
-            fb, d32 = self._masa_encode(E, both)
+            both16 = lq16 = None
+            if ops.SMALL_CI_TC:          # 8-channel fp16 image rows: conv_L1 / patch_embed run on tdr_conv_gemm
+                both16 = torch.empty((2 * B, h, w, 8), dtype=F16, device=dev)
+                ops.image_to_rows16(inp_img, h, w, F16, out=both16[:B])
+                ops.image_to_rows16(ref_img, hr, wr, F16, out=both16[B:])
+                lq16 = both16[:B]
+            fb, d32 = self._masa_encode(E, both, img16=both16 if ops.SMALL_CI_TC_MASA else None)
             f_lq, f_ref, lq_d32, ref_d32 = [t[:B] for t in fb], [t[B:] for t in fb], d32[:B], d32[B:]
         else:
             lq32, ref32 = ops.nchw_to_nhwc(inp_img, h, w), ops.nchw_to_nhwc(ref_img, hr, wr)
-            (f_lq, lq_d32), (f_ref, ref_d32) = self._masa_encode(E, lq32), self._masa_encode(E, ref32)
+            lq16 = ops.image_to_rows16(inp_img, h, w, F16) if ops.SMALL_CI_TC else None
+            ref16 = ops.image_to_rows16(ref_img, hr, wr, F16) if ops.SMALL_CI_TC else None
+            m16 = ops.SMALL_CI_TC_MASA
+            (f_lq, lq_d32), (f_ref, ref_d32) = (self._masa_encode(E, lq32, img16=lq16 if m16 else None),
+                                                self._masa_encode(E, ref32, img16=ref16 if m16 else None))
         # fusion buffers [x || warp] per level, fp32 residual streams
         fbuf = [torch.empty((B, h >> i, w >> i, 2 * d[i]), dtype=F32, device=dev) for i in range(4)]
         aux = self._masa_warp(lq_d32, ref_d32, f_ref, h, w, hr, wr, [fbuf[i][..., d[i]:] for i in range(4)])
         if return_aux:                   # the fusion blocks overwrite the warp halves in place
             aux.update(feat_lq=f_lq, feat_ref=f_ref, deep32_lq=lq_d32, deep32_ref=ref_d32, deep_scale=self._masa_last_scale[-1],
                        warps=[fbuf[i][..., d[i]:].clone() for i in range(4)])
-        ops.conv3x3_small_ci(lq32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=fbuf[0][..., :d[0]])
+        if lq16 is not None and "w16" in P["patch_embed"]:
+            ops.conv_gemm(lq16, P["patch_embed"]["w16"], d[0], Ci=8, k=3, pad=1, bias=P["patch_embed"]["b"],
+                          out_f32=fbuf[0][..., :d[0]])
+        else:
+            ops.conv3x3_small_ci(lq32, P["patch_embed"]["w"], P["patch_embed"]["b"], out_f32=fbuf[0][..., :d[0]])
         self._after_patch_embed(P, fbuf[0][..., :d[0]])
         enc_names = ["encoder_level1", "encoder_level2", "encoder_level3", "latent"]
         downs = [None, "down1_2", "down2_3", "down3_4"]

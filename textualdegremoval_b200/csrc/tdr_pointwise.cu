@@ -518,6 +518,23 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, int B, int C,
   }
 }
 
+// NCHW fp32 image -> zero-padded 16-bit NHWC rows with C16 >= C channels (all C16 are written): the tensor-core operand of
+// the image-boundary 3x3 convs (patch_embed, MASA conv_L1), whose 3 input channels are padded to one 16-byte TMA row
+__global__ void image_to_rows16_kernel(const float* __restrict__ src, int B, int C, int H, int W, int PH, int PW, int C16,
+                                       uint16_t* __restrict__ dst, int fp16) {
+  const long long total = (long long)B * PH * PW * C16;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C16);
+    long long p = i / C16;
+    const int x = (int)(p % PW);
+    const int y = (int)((p / PW) % PH);
+    const int b = (int)(p / ((long long)PW * PH));
+    const float v = (c < C && y < H && x < W) ? src[(((long long)b * C + c) * H + y) * W + x] : 0.f;
+    dst[i] = pack1r(v, fp16);
+  }
+}
+
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ src, long long ld, int B, int C, int H, int W, int OH,
                                     int OW, const float* __restrict__ res, long long res_ld,
                                     float* __restrict__ dst) {
@@ -927,6 +944,17 @@ extern "C" int tdr_nchw_to_nhwc(const float* src, int B, int C, int H, int W, in
   const long long total = (long long)B * pad_h * pad_w * C;
   nchw_to_nhwc_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(src, B, C, H, W, pad_h, pad_w, dst_f32, dst_f32_ld,
                                                                     reinterpret_cast<bf16*>(dst_bf16), dst_bf16_ld);
+  TDR_CHECK_LAUNCH();
+  return TDR_OK;
+}
+
+extern "C" int tdr_image_to_rows16(const float* src, int B, int C, int H, int W, int pad_h, int pad_w, int C16, void* dst16,
+                                   int fp16, cudaStream_t stream) {
+  TDR_CHECK_ARG(src && dst16 && pad_h >= H && pad_w >= W && B > 0 && C > 0 && C16 >= C && C16 % 8 == 0,
+                "tdr_image_to_rows16: bad arguments (C16 must be a multiple of 8, >= C)");
+  const long long total = (long long)B * pad_h * pad_w * C16;
+  image_to_rows16_kernel<<<grid_for(total, 256, 16), 256, 0, stream>>>(src, B, C, H, W, pad_h, pad_w, C16,
+                                                                       reinterpret_cast<uint16_t*>(dst16), fp16);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -103,6 +103,7 @@ SIGNATURES = {
     "tdr_adamw_step": (_i, [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _vp, _vp]),
     "tdr_ema_update": (_i, [_vp, _vp, _ll, _f, _vp]),
     "tdr_l1_loss_grad": (_i, [_vp, _vp, _ll, _f, _vp, _vp, _vp, _vp]),
+    "tdr_image_to_rows16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "tdr_add_gaussian_noise": (_i, [_vp, _vp, _vp, _i, _ll, C.c_ulonglong, _vp, _vp]),
     "tdr_prepare_patches": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "tdr_psnr_u8_sums": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),

@@ -452,6 +452,25 @@ def nchw_to_nhwc_into(x, pad_h, pad_w, dst32=None, dst16=None):
           _p(dst16), _ld(dst16) if dst16 is not None else 0, _stream())
 
 
+# Opt-in knob (measured, not adopted): the image-boundary 3x3 convs (3 input channels) on the tensor-core path instead of the
+# exact fp32 tdr_conv3x3_small_ci.  "1": patch_embed, "2": also the MASA encoder's first conv.  On B200 it saves 0.15-0.4 ms of
+# the 47 ms step but rounds the image and the first layer's weights to fp16: guided Restormer 512^2 mean |delta| 1.09e-4 ->
+# 1.27e-4 (63.97 -> 63.26 dB), Restormer 256^2 66.6 -> 65.8 dB.  Parity comes first, so the default stays off.
+SMALL_CI_TC = os.environ.get("TDR_SMALL_CI_TC", "0") not in ("", "0")
+SMALL_CI_TC_MASA = os.environ.get("TDR_SMALL_CI_TC", "0") == "2"
+
+
+def image_to_rows16(x, pad_h, pad_w, dt, out=None, c16=8):
+    """NCHW fp32 image -> zero-padded 16-bit NHWC rows [B, pad_h, pad_w, c16] (tdr_image_to_rows16)."""
+    x = x.contiguous().float()
+    B, Cc, H, W = x.shape
+    if out is None:
+        out = torch.empty((B, pad_h, pad_w, c16), dtype=dt, device=x.device)
+    assert out.is_contiguous() and tuple(out.shape) == (B, pad_h, pad_w, c16)
+    _call("tdr_image_to_rows16", _p(x), B, Cc, H, W, pad_h, pad_w, c16, _p(out), int(out.dtype == F16), _stream())
+    return out
+
+
 def nhwc_to_nchw(x32, out_h, out_w, res=None):
     """NHWC fp32 view -> dense NCHW (cropped); optionally adds an NHWC fp32 residual with the same channel count."""
     B, H, W, Cc = x32.shape
