@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include "tdr_common.cuh"
+#include "tdr_stencil.cuh"
 
 namespace {
 
@@ -123,6 +124,18 @@ __device__ __forceinline__ void conv_tile_coords(const ConvGemmArgs& a, int mt, 
   const int r = mt - b * tiles_per_img;
   ty = fdiv(r, a.fd_tx_m, a.fd_tx_s);
   tx = r - ty * a.tiles_x;
+}
+
+// exact GELU on 16 epilogue values: the packed logistic-polynomial form of tdr_stencil.cuh (|error| <= 2 fp32 ulp) -- erff
+// per element made the GELU epilogue of the ViT fc1 GEMMs cost as much as the GEMM itself (170 vs 92 us at CLIP-H fc1)
+__device__ __forceinline__ void gelu16(float* v) {
+#pragma unroll
+  for (int i = 0; i < 16; i += 2) {
+    float a, b;
+    upk2(gelu2(pk2(v[i], v[i + 1])), a, b);
+    v[i] = a;
+    v[i + 1] = b;
+  }
 }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -686,7 +699,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                   for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
                 } else if (a.act == 2) {
 #pragma unroll
-                  for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], 2);
+                  gelu16(v);
                 }
                 if (alpha != 1.f) {
 #pragma unroll
@@ -780,7 +793,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                 for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
               } else if (a.act == 2) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], 2);
+                gelu16(v);
               }
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] *= alpha;
@@ -869,7 +882,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             } else if (a.act == 2) {
   #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], 2);
+              gelu16(v);
             }
   #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] *= alpha;

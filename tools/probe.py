@@ -126,6 +126,10 @@ PROBES = {
     "pout96wb": lambda: conv(4, 512, 512, 96, 96, want="f32", res=True),
     "pout128": lambda: conv(4, 512, 512, 128, 48, want="f32", res=True),
     "pin192": lambda: conv(4, 128, 128, 192, 1024),
+    "vit_fc1": lambda: conv(1, 1, 8224, 1280, 5120),          # CLIP ViT-H/14 fc1 over 32 x 257 tokens (flat GEMM view)
+    "vit_fc2": lambda: conv(1, 1, 8224, 5120, 1280, want="f32", res=True),   # CLIP fc2 + residual (fp32 stream)
+    "vit_proj": lambda: conv(1, 1, 8224, 1280, 1280, want="f32", res=True),
+    "vit_qkv": lambda: conv(1, 1, 10960, 768, 2304),          # DINOv2 ViT-B/14 qkv over 8 x 1370 tokens
     "c3x3_48": lambda: conv(8, 512, 512, 48, 48, k=3, relu=True),
     "c3x3_96": lambda: conv(8, 256, 256, 96, 96, k=3, relu=True),
     "c3x3_384": lambda: conv(8, 64, 64, 384, 384, k=3, relu=True),
