@@ -303,6 +303,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= (uint64_t)2 << 61;   // SWIZZLE_128B
   return d;
 }
+// Same with SWIZZLE_64B (layout type 4): rows of 64 B (32 bf16); an 8-row group is 512 B.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)4 << 61;   // SWIZZLE_64B
+  return d;
+}
 // Instruction descriptor for kind::f16, bf16 x bf16 -> fp32 (cute::UMMA::InstrDescriptor).
 // a_fp16 / b_fp16: that operand holds IEEE fp16 instead of bf16 (kind::f16 takes either, per operand, at the same rate)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major, int a_fp16 = 0,
@@ -322,6 +332,9 @@ struct TdrTensorMap {
 };
 int tdr_make_tensor_map_bf16(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
+// bf16, SWIZZLE_64B (box inner dimension <= 32 elements = 64 B)
+int tdr_make_tensor_map_bf16_sw64(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                  const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);
 // bf16, SWIZZLE_NONE (plain row-major box in shared memory)
 int tdr_make_tensor_map_bf16_noswizzle(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
                                        const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides);

@@ -21,6 +21,9 @@ constexpr int kBoxBytes = 64 * kPixTile * 2;
 
 struct GramPlan {
   int c, M, N, boxes, stages, nchunks, tiles_per_chunk, tiles_total;
+  int box_ch, box_bytes;  // channels / bytes per TMA box: 64 ch SWIZZLE_128B, or 32 ch SWIZZLE_64B when that tiles c exactly
+                          // (c = 96: three 32-channel boxes read exactly q and k; two 64-channel boxes over-read 1.33x --
+                          // ncu measured 570 MB of DRAM reads for 403 MB of q, k)
   uint32_t tmem_cols;
   int generic;            // heads wider than 128 channels (PromptIR's prompt-interaction blocks, c = 176): SIMT Gram
 };
@@ -46,6 +49,16 @@ static int make_plan(int B, long long P, int C, int heads, GramPlan* p) {
   p->N = p->c;
   p->boxes = p->c <= 64 ? 1 : 2;
   p->stages = p->boxes == 1 ? 4 : 3;
+  p->box_ch = 64;
+  p->box_bytes = kBoxBytes;
+  // Measured and NOT adopted (opt-in knob): the exact-width boxes cut the DRAM reads but the kernel gets slower (156 vs 138 us
+  // at C = 96, 512^2, batch 4): 1.5x the TMA requests on 64-byte rows cost more than the saved 1.33x over-read.
+  if (p->c == 96 && getenv("TDR_GRAM_SW64") != nullptr) {
+    p->box_ch = 32;
+    p->box_bytes = 32 * kPixTile * 2;
+    p->boxes = 3;
+    p->stages = 4;
+  }
   p->tiles_total = (int)((P + kPixTile - 1) / kPixTile);
   // The split of the pixel axis is a function of (P, heads) ONLY, never of the batch size: the fp32 partial sums are
   // then combined in the same order whether a sample is run alone or inside a batch, so a sample's output does not
@@ -76,8 +89,8 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const GramPlan& pl = a.plan;
-  const int stage_bytes = 2 * pl.boxes * kBoxBytes;          // q boxes then k boxes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.stages * stage_bytes);
+  const int stage_bytes = 2 * pl.boxes * pl.box_bytes;       // q boxes then k boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.stages * stage_bytes + pl.box_bytes);   // after the over-read pad
   uint64_t* full = bars;
   uint64_t* empty = bars + pl.stages;
   uint64_t* tfull = bars + 2 * pl.stages;
@@ -114,8 +127,8 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
         mbar_expect_tx(&full[stage], stage_bytes);
         uint8_t* base = smem + stage * stage_bytes;
         for (int j = 0; j < pl.boxes; ++j) {
-          tma_load_3d(base + j * kBoxBytes, &map, &full[stage], h * pl.c + 64 * j, pix0, b);
-          tma_load_3d(base + (pl.boxes + j) * kBoxBytes, &map, &full[stage], a.C + h * pl.c + 64 * j, pix0, b);
+          tma_load_3d(base + j * pl.box_bytes, &map, &full[stage], h * pl.c + pl.box_ch * j, pix0, b);
+          tma_load_3d(base + (pl.boxes + j) * pl.box_bytes, &map, &full[stage], a.C + h * pl.c + pl.box_ch * j, pix0, b);
         }
         if (++stage == pl.stages) { stage = 0; phase ^= 1; }
       }
@@ -129,13 +142,16 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sq = smem_u32(smem + stage * stage_bytes);
-        const uint32_t sk = sq + pl.boxes * kBoxBytes;
-        const uint64_t dq0 = umma_desc_sw128(sq, kBoxBytes, 1024), dk0 = umma_desc_sw128(sk, kBoxBytes, 1024);
+        const uint32_t sk = sq + pl.boxes * pl.box_bytes;
+        const bool sw64 = pl.box_ch == 32;
+        // MN-major operands: rows (pixels) of 128 B (64 B with SWIZZLE_64B), an 8-row group is 1024 (512) B = SBO, the
+        // channel chunks are box_bytes apart (LBO); 16 pixels (one K step) = 2048 (1024) B = 128 (64) address units
+        const uint64_t dq0 = sw64 ? umma_desc_sw64(sq, pl.box_bytes, 512) : umma_desc_sw128(sq, pl.box_bytes, 1024);
+        const uint64_t dk0 = sw64 ? umma_desc_sw64(sk, pl.box_bytes, 512) : umma_desc_sw128(sk, pl.box_bytes, 1024);
+        const uint32_t kstep = sw64 ? 64 : 128;
 #pragma unroll
         for (int ks = 0; ks < kPixTile / 16; ++ks) {
-          // 16 pixels (K) = two 8-row swizzle atoms of 1024 B = 128 units of the descriptor's start-address field;
-          // 64-channel chunks are kBoxBytes apart (LBO)
-          const uint64_t dq = dq0 + ks * 128, dk = dk0 + ks * 128;
+          const uint64_t dq = dq0 + ks * kstep, dk = dk0 + ks * kstep;
           const uint32_t accum = (t | ks) != 0;
           umma_bf16(tmem_base + 0 * pl.N, dq, dk, idesc, accum);
           umma_bf16(tmem_base + 1 * pl.N, dq, dq, idesc, accum);
@@ -457,11 +473,13 @@ extern "C" int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long lon
   TdrTensorMap map;
   const uint64_t dims[3] = {(uint64_t)(3 * C), (uint64_t)P, (uint64_t)B};
   const uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)P};
-  const uint32_t box[3] = {64, (uint32_t)kPixTile, 1};
+  const uint32_t box[3] = {(uint32_t)a.plan.box_ch, (uint32_t)kPixTile, 1};
   const uint32_t es[3] = {1, 1, 1};
-  int rc = tdr_make_tensor_map_bf16(&map, qkv_bf16, 3, dims, strides, box, es);
+  int rc = a.plan.box_ch == 32 ? tdr_make_tensor_map_bf16_sw64(&map, qkv_bf16, 3, dims, strides, box, es)
+                               : tdr_make_tensor_map_bf16(&map, qkv_bf16, 3, dims, strides, box, es);
   if (rc) return rc;
-  const size_t smem = 1024 + (size_t)a.plan.stages * 2 * a.plan.boxes * kBoxBytes + 256;
+  // + one box: with three 32-channel boxes the M = 128 operand reads a fourth (unused) chunk past k's last box
+  const size_t smem = 1024 + (size_t)a.plan.stages * 2 * a.plan.boxes * a.plan.box_bytes + 256 + a.plan.box_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     TDR_CHECK_CUDA(cudaFuncSetAttribute(mdta_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -70,6 +70,12 @@ int tdr_make_tensor_map_bf16_noswizzle(TdrTensorMap* out, const void* base, int 
                   CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
+int tdr_make_tensor_map_bf16_sw64(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
+                                  const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
+  return make_map(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, elem_strides,
+                  CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
 int tdr_make_tensor_map_bf16(TdrTensorMap* out, const void* base, int rank, const uint64_t* dims,
                              const uint64_t* strides_bytes, const uint32_t* box, const uint32_t* elem_strides) {
   return make_map(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, elem_strides);
