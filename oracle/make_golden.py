@@ -77,6 +77,11 @@ DRS_CASES = {
                                                         ext_n_blocks=[1, 1, 1, 1], reffusion_n_blocks=[1, 1, 1, 1],
                                                         LayerNorm_type="WithBias"),
                                      seed=71, lq=(1, 3, 128, 128), ref=(1, 3, 128, 128)),
+    # conv biases, BiasFree LayerNorm and a ragged input size (zero-padded to a multiple of 64 and cropped back)
+    "guided_drsformer_spa_bias_ragged": dict(spa=True, cfg=dict(dim=16, num_blocks=[1, 1, 1, 1], heads=[1, 2, 4, 8], nf=16,
+                                                                ext_n_blocks=[1, 1, 1, 1], reffusion_n_blocks=[1, 1, 1, 1],
+                                                                LayerNorm_type="BiasFree", bias=True),
+                                             seed=73, lq=(1, 3, 120, 136), ref=(1, 3, 128, 192)),
     "guided_drsformer_128": dict(spa=False, cfg=dict(dim=16, num_blocks=[1, 1, 1, 1], heads=[1, 2, 4, 8], nf=16,
                                                      ext_n_blocks=[1, 1, 1, 1], reffusion_n_blocks=[1, 1, 1, 1],
                                                      LayerNorm_type="WithBias"),

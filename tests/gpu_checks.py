@@ -907,7 +907,9 @@ def check_drsformer():
     wm = ops.mefc_mix_weights(wo.to(DEV), g[:, 2], 16, BF16)
     out.append(result("mefc_mix_weights", wm[..., :128], wo.unsqueeze(0) * g_ref[:, 2].repeat_interleave(16, -1).unsqueeze(1), 8e-3))
     # end to end
-    for name, typ in (("guided_drsformer_spa_128", "DRSformer200L_SPA_RefFusion"), ("guided_drsformer_128", "DRSformerRefFusion")):
+    for name, typ in (("guided_drsformer_spa_128", "DRSformer200L_SPA_RefFusion"),
+                      ("guided_drsformer_spa_bias_ragged", "DRSformer200L_SPA_RefFusion"),
+                      ("guided_drsformer_128", "DRSformerRefFusion")):
         meta, ref = _golden(name)
         net = define_network(dict(type=typ, **meta["cfg"]))
         Wt.load_seeded(net, meta["seed"])
