@@ -167,6 +167,7 @@ def _prep_block(blk):
     # depthwise 3x3 / 5x5 on the 2h hidden channels -> D = [dw3 | dw5], each half P2 slots wide
     p["idx_dw"] = _arange(2 * h, dev)
     p["w3"], p["b3"] = _f(f.dwconv3x3.weight), _f(f.dwconv3x3.bias)
+    p["w3_tma"], _, p["b3_tma"] = ops.pack_dw(f.dwconv3x3.weight, f.dwconv3x3.bias, c_map=m2, C_p=P2)   # tdr_dwconv3x3 (TMA)
     p["w5"], p["b5"] = _f(f.dwconv5x5.weight), _f(f.dwconv5x5.bias)
     # grouped convs: x1 = cat[dw3[:h], dw5[:h]], x2 = cat[dw3[h:], dw5[h:]] (:246-247); group g reads channels 2g, 2g+1
     i = torch.arange(2 * h, device=dev)
@@ -229,7 +230,7 @@ def run_block(x32, p):
     xn = ops.rownorm(x1, p["ln_mode"], p["ln2_w"], p["ln2_b"], 1e-5, out=xn)
     _, hid = ops.conv_gemm(xn, p["w_in"], P2, bias=p["b_in"])
     D = torch.empty((B, H, W, 2 * P2), dtype=dt, device=dev)
-    ops.grouped_stencil(hid, p["idx_dw"], p["w3"], p["b3"], 3, D[..., :2 * h], relu=True)
+    ops.dwconv3x3(hid, p["w3_tma"], p["b3_tma"], out=D[..., :P2], relu=True)        # pad channels: zero taps -> zeros
     ops.grouped_stencil(hid, p["idx_dw"], p["w5"], p["b5"], 5, D[..., P2:P2 + 2 * h], relu=True)
     Y = torch.empty((B, H, W, P2), dtype=dt, device=dev)
     ops.grouped_stencil(D, p["idx_g3"], p["w3_1"], p["b3_1"], 3, Y[..., :h], relu=True)

@@ -245,6 +245,7 @@ struct DwArgs {
   const float* dg_add;     // optional per-sample term [B][Cout] added to dg (SCA pool gradient)
   bf16* y_out;             // GATE == 1, optional (training): also store the pre-gate halves [a | b] (2 * Cout channels)
   long long y_ld;
+  int relu;                // GATE == 0: ReLU on the output
   uint32_t fd_img_m, fd_img_s, fd_tx_m, fd_tx_s;   // n / (tiles_y * tiles_x), n / tiles_x as umulhi + shift
 };
 
@@ -417,6 +418,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
               if (GATE) val = mul2(a.gate == 1 ? gelu2(val) : val, acc[i % 3][NH - 1][e]);
               float a0, a1;
               upk2(val, a0, a1);
+              if (!GATE && a.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
               ou[e] = pack2t<HALF>(a0, a1);
             }
             *reinterpret_cast<raw_t*>(outp) = o;
@@ -845,7 +847,9 @@ static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int
   TDR_CHECK_ARG(in_bf16 && out_bf16 && weight, "tdr_dwconv3x3: null pointer");
   TDR_CHECK_ARG(B > 0 && H > 0 && W > 0 && C > 0, "tdr_dwconv3x3: bad dims");
   const bool half = (gate & 16) != 0;               // bit 4: activations are IEEE fp16 (inference forward), else bf16
+  const bool relu = (gate & 32) != 0;               // bit 5: ReLU on the (ungated) output -- DRSformer MSFN dwconv3x3 :242
   gate &= 15;
+  TDR_CHECK_ARG(!relu || (gate == 0 && !dg_bf16), "tdr_dwconv3x3: ReLU goes with the plain (ungated) forward only");
   TDR_CHECK_ARG(gate >= 0 && gate <= 2, "tdr_dwconv3x3: bad gate");
   TDR_CHECK_ARG(!half || (!dg_bf16 && !y_out), "tdr_dwconv3x3: the training / backward variants take bf16 activations");
   TDR_CHECK_ARG(C % 8 == 0, "tdr_dwconv3x3: C must be a multiple of 8");
@@ -882,6 +886,7 @@ static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int
   a.wt = weight; a.bias = bias; a.gate = gate; a.out = out; a.out_ld = out_ld;
   a.dg = reinterpret_cast<const bf16*>(dg_bf16); a.dg_ld = dg_ld; a.dg_add = dg_add;
   a.y_out = reinterpret_cast<bf16*>(y_out); a.y_ld = y_ld;
+  a.relu = relu ? 1 : 0;
   TdrTensorMap map;
   const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   const uint64_t strides[3] = {(uint64_t)in_ld * 2, (uint64_t)in_ld * 2 * W, (uint64_t)in_ld * 2 * W * H};

@@ -33,6 +33,9 @@ __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs 
   __shared__ int s_idx[kCo * 2];
   const int p = a.dil * (K - 1) / 2;
   const int th = kTH + 2 * p, tw = kTW + 2 * p;
+  // row pitch == 1 (mod 4): a warp reads 4 rows x 8 quads (lane stride 4 floats within a row); with an even pitch rows
+  // collide 4-way on the shared-memory banks, with pitch 4m + 1 the 32 lanes hit 32 different banks
+  const int twp = tw + ((1 - tw) & 3);
   const int nci = kCo * a.ipg;
   int t = blockIdx.x;
   const int tx = t % a.tiles_x; t /= a.tiles_x;
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs 
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) unpack8r(img + ((size_t)yy * a.W + xx) * a.in_ld + s_idx[g * 8], v, a.fp16);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) tile[((g * 8 + e) * th + px / tw) * tw + px % tw] = v[e];
+      for (int e = 0; e < 8; ++e) tile[((g * 8 + e) * th + px / tw) * twp + px % tw] = v[e];
     }
   } else {
     for (int i = threadIdx.x; i < th * tw * nci; i += blockDim.x) {
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs 
       float v = 0.f, d;
       if (ch >= 0 && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W)
         unpack2r(img[((size_t)yy * a.W + xx) * a.in_ld + ch], v, d, a.fp16);
-      tile[(ci * th + px / tw) * tw + px % tw] = v;
+      tile[(ci * th + px / tw) * twp + px % tw] = v;
     }
   }
   __syncthreads();
@@ -98,21 +101,21 @@ __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs 
             const int yy = y + ky - 1, xx = x + kx - 1;
             if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) {
               ++cnt;
-              sum += tile[(c * th + ly + ky) * tw + lx + i + kx];
+              sum += tile[(c * th + ly + ky) * twp + lx + i + kx];
             }
           }
         acc[i] = cnt ? sum / (float)cnt : 0.f;
       }
     } else {
       for (int j = 0; j < a.ipg; ++j) {
-        const float* tp = tile + (size_t)(c * a.ipg + j) * th * tw;
+        const float* tp = tile + (size_t)(c * a.ipg + j) * th * twp;
         const float* wp = a.w + ((size_t)co * a.ipg + j) * (K * K);
         float w[K * K];
 #pragma unroll
         for (int i = 0; i < K * K; ++i) w[i] = __ldg(wp + i);
 #pragma unroll
         for (int ky = 0; ky < K; ++ky) {
-          const float* row = tp + (ly + ky * a.dil) * tw + lx;
+          const float* row = tp + (ly + ky * a.dil) * twp + lx;
           float v[NV];
           const int nv = 4 + (K - 1) * a.dil;
 #pragma unroll
@@ -243,7 +246,8 @@ extern "C" int tdr_grouped_stencil(const void* in16, long long in_ld, int B, int
   a.out = reinterpret_cast<uint16_t*>(out16); a.out_ld = out_ld;
   a.tiles_x = tdr_cdiv(W, kTW); a.tiles_y = tdr_cdiv(H, kTH);
   const int p = dil * (K - 1) / 2;
-  const size_t smem = (size_t)kCo * ipg * (kTH + 2 * p) * (kTW + 2 * p) * sizeof(float);
+  const int tw = kTW + 2 * p;
+  const size_t smem = (size_t)kCo * ipg * (kTH + 2 * p) * (tw + ((1 - tw) & 3)) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));

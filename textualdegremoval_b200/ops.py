@@ -311,15 +311,15 @@ def rownorm(x32, mode, weight=None, bias=None, eps=1e-5, out=None, leaky=False, 
     return out if out is not None else out_f32
 
 
-def dwconv3x3(x, w9, bias=None, gate=0, out=None):
-    assert x.dtype in (BF16, F16) and w9.dtype == F32
+def dwconv3x3(x, w9, bias=None, gate=0, out=None, relu=False):
+    assert x.dtype in (BF16, F16) and w9.dtype == F32 and not (relu and gate)
     B, H, W, Cc = x.shape
     co = Cc // 2 if gate else Cc
     if out is None:
         out = torch.empty((B, H, W, co), dtype=x.dtype, device=x.device)
     assert out.dtype == x.dtype
-    _call("tdr_dwconv3x3", _p(x), _ld(x), B, H, W, Cc, _p(w9), _p(bias), gate | (16 if x.dtype == F16 else 0), _p(out),
-          _ld(out), _stream(),
+    _call("tdr_dwconv3x3", _p(x), _ld(x), B, H, W, Cc, _p(w9), _p(bias), gate | (16 if x.dtype == F16 else 0) | (32 if relu else 0),
+          _p(out), _ld(out), _stream(),
           tag=f"g{gate}_C{Cc}_{H}x{W}", nbytes=B * H * W * (Cc + co) * 2, flops=2 * 9 * B * H * W * Cc)
     return out
 
