@@ -27,7 +27,7 @@ struct StencilArgs {
 // Thread mapping: 256 threads = 4 channel pairs x 64 pixel quads; a thread computes 2 output channels x 4 horizontally
 // adjacent pixels.  Per (channel, input, tap row) it loads the 4 + (K-1) dil staged values once and reuses each for up to K
 // outputs; the K*K taps of the channel sit in registers (K is a template parameter, so the loops unroll).
-template <int K>
+template <int K, int IPG>
 __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs a) {
   extern __shared__ float tile[];                  // [nci][TH + 2p][TW + 2p]
   __shared__ int s_idx[kCo * 2];
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs 
   // row pitch == 1 (mod 4): a warp reads 4 rows x 8 quads (lane stride 4 floats within a row); with an even pitch rows
   // collide 4-way on the shared-memory banks, with pitch 4m + 1 the 32 lanes hit 32 different banks
   const int twp = tw + ((1 - tw) & 3);
-  const int nci = kCo * a.ipg;
+  constexpr int nci = kCo * IPG;
   int t = blockIdx.x;
   const int tx = t % a.tiles_x; t /= a.tiles_x;
   const int ty = t % a.tiles_y;
@@ -44,8 +44,8 @@ __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs 
   const int co0 = blockIdx.y * kCo;
   const int y0 = ty * kTH, x0 = tx * kTW;
   if (threadIdx.x < nci) {
-    const int co = co0 + threadIdx.x / a.ipg;
-    s_idx[threadIdx.x] = co < a.Co ? a.idx[(size_t)co * a.ipg + threadIdx.x % a.ipg] : -1;
+    const int co = co0 + threadIdx.x / IPG;
+    s_idx[threadIdx.x] = co < a.Co ? a.idx[(size_t)co * IPG + threadIdx.x % IPG] : -1;
   }
   __syncthreads();
   // stage the haloed input tile.  Fast path: the CTA's input channels are groups of 8 contiguous, 16-byte aligned
@@ -53,25 +53,35 @@ __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs 
   const uint16_t* img = a.in + (size_t)b * a.H * a.W * a.in_ld;
   bool vec = (a.in_ld & 7) == 0 && (reinterpret_cast<uintptr_t>(a.in) & 15) == 0 && co0 + kCo <= a.Co;
   for (int i = 0; i < nci && vec; ++i) vec = s_idx[i] == s_idx[i & ~7] + (i & 7) && (s_idx[i & ~7] & 7) == 0;
+  // (row loops instead of a flat index: the flat form spent most of the kernel's instructions on runtime div / mod)
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (vec) {
-    const int ng = nci >> 3;
-    for (int i = threadIdx.x; i < th * tw * ng; i += blockDim.x) {
-      const int g = i % ng, px = i / ng;
-      const int yy = y0 - p + px / tw, xx = x0 - p + px % tw;
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (yy >= 0 && yy < a.H && xx >= 0 && xx < a.W) unpack8r(img + ((size_t)yy * a.W + xx) * a.in_ld + s_idx[g * 8], v, a.fp16);
+    constexpr int ng = nci >> 3;
+    for (int r = wid; r < th; r += 8) {
+      const int yy = y0 - p + r;
+      const bool row_ok = yy >= 0 && yy < a.H;
+      for (int j = lane; j < tw * ng; j += 32) {
+        const int g = j % ng, xc = j / ng;
+        const int xx = x0 - p + xc;
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (row_ok && xx >= 0 && xx < a.W) unpack8r(img + ((size_t)yy * a.W + xx) * a.in_ld + s_idx[g * 8], v, a.fp16);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) tile[((g * 8 + e) * th + px / tw) * twp + px % tw] = v[e];
+        for (int e = 0; e < 8; ++e) tile[((g * 8 + e) * th + r) * twp + xc] = v[e];
+      }
     }
   } else {
-    for (int i = threadIdx.x; i < th * tw * nci; i += blockDim.x) {
-      const int ci = i % nci, px = i / nci;
-      const int yy = y0 - p + px / tw, xx = x0 - p + px % tw;
-      const int ch = s_idx[ci];
-      float v = 0.f, d;
-      if (ch >= 0 && yy >= 0 && yy < a.H && xx >= 0 && xx < a.W)
-        unpack2r(img[((size_t)yy * a.W + xx) * a.in_ld + ch], v, d, a.fp16);
-      tile[(ci * th + px / tw) * twp + px % tw] = v;
+    for (int r = wid; r < th; r += 8) {
+      const int yy = y0 - p + r;
+      const bool row_ok = yy >= 0 && yy < a.H;
+      for (int j = lane; j < tw * nci; j += 32) {
+        const int ci = j % nci, xc = j / nci;
+        const int xx = x0 - p + xc;
+        const int ch = s_idx[ci];
+        float v = 0.f, d;
+        if (ch >= 0 && row_ok && xx >= 0 && xx < a.W)
+          unpack2r(img[((size_t)yy * a.W + xx) * a.in_ld + ch], v, d, a.fp16);
+        tile[(ci * th + r) * twp + xc] = v;
+      }
     }
   }
   __syncthreads();
@@ -107,9 +117,10 @@ __global__ void __launch_bounds__(256) grouped_stencil_kernel(const StencilArgs 
         acc[i] = cnt ? sum / (float)cnt : 0.f;
       }
     } else {
-      for (int j = 0; j < a.ipg; ++j) {
-        const float* tp = tile + (size_t)(c * a.ipg + j) * th * twp;
-        const float* wp = a.w + ((size_t)co * a.ipg + j) * (K * K);
+#pragma unroll
+      for (int j = 0; j < IPG; ++j) {
+        const float* tp = tile + (size_t)(c * IPG + j) * th * twp;
+        const float* wp = a.w + ((size_t)co * IPG + j) * (K * K);
         float w[K * K];
 #pragma unroll
         for (int i = 0; i < K * K; ++i) w[i] = __ldg(wp + i);
@@ -248,23 +259,28 @@ extern "C" int tdr_grouped_stencil(const void* in16, long long in_ld, int B, int
   const int p = dil * (K - 1) / 2;
   const int tw = kTW + 2 * p;
   const size_t smem = (size_t)kCo * ipg * (kTH + 2 * p) * (tw + ((1 - tw) & 3)) * sizeof(float);
+#define TDR_STENCIL_ATTR(KK, II) \
+  TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel<KK, II>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024))
   static bool attr_set = false;
   if (!attr_set) {
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    TDR_CHECK_CUDA(cudaFuncSetAttribute(grouped_stencil_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    TDR_STENCIL_ATTR(1, 1); TDR_STENCIL_ATTR(3, 1); TDR_STENCIL_ATTR(5, 1); TDR_STENCIL_ATTR(7, 1);
+    TDR_STENCIL_ATTR(1, 2); TDR_STENCIL_ATTR(3, 2); TDR_STENCIL_ATTR(5, 2); TDR_STENCIL_ATTR(7, 2);
     attr_set = true;
   }
+#undef TDR_STENCIL_ATTR
   TDR_CHECK_ARG(smem <= 64 * 1024, "tdr_grouped_stencil: tile does not fit (%zu bytes)", smem);
   TDR_CHECK_ARG((long long)a.tiles_x * a.tiles_y * B < (1LL << 31) && tdr_cdiv(Co, kCo) <= 65535, "tdr_grouped_stencil: grid");
   dim3 grid((unsigned)(a.tiles_x * a.tiles_y * B), (unsigned)tdr_cdiv(Co, kCo));
+#define TDR_STENCIL_GO(KK) \
+  do { if (ipg == 1) grouped_stencil_kernel<KK, 1><<<grid, 256, smem, stream>>>(a); \
+       else grouped_stencil_kernel<KK, 2><<<grid, 256, smem, stream>>>(a); } while (0)
   switch (K) {
-    case 1: grouped_stencil_kernel<1><<<grid, 256, smem, stream>>>(a); break;
-    case 3: grouped_stencil_kernel<3><<<grid, 256, smem, stream>>>(a); break;
-    case 5: grouped_stencil_kernel<5><<<grid, 256, smem, stream>>>(a); break;
-    default: grouped_stencil_kernel<7><<<grid, 256, smem, stream>>>(a); break;
+    case 1: TDR_STENCIL_GO(1); break;
+    case 3: TDR_STENCIL_GO(3); break;
+    case 5: TDR_STENCIL_GO(5); break;
+    default: TDR_STENCIL_GO(7); break;
   }
+#undef TDR_STENCIL_GO
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
