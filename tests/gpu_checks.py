@@ -262,6 +262,12 @@ CONV_CASES = [
     dict(name="1x1_res_192to96_fusion", Ci=192, Co=96, H=176, W=160, B=2, bias=True, res1=True, res2="f32",
          use_scale_ptr=True),
     dict(name="1x1_res_ragged_40to72", Ci=40, Co=72, H=250, W=170, B=1, want="both"),
+    # pair mode (two pixel tiles per streamed weight tile: dense 3x3 at C >= 96 with >= 2 items per SM); 323 = odd number
+    # of pixel tiles -> the last pair has a ghost tile whose loads are TMA zero fill and whose stores are clipped
+    dict(name="3x3_pair_96_odd_tiles", Ci=96, Co=96, k=3, pad=1, H=152, W=272, B=1, bias=True, relu=True, want="bf16"),
+    dict(name="3x3_pair_128_res2", Ci=128, Co=128, k=3, pad=1, H=160, W=144, B=2, bias=True, res2="f32"),
+    dict(name="3x3_pair_stride2_96to192", Ci=96, Co=192, k=3, pad=1, stride=2, H=304, W=272, B=1, relu=True, want="bf16"),
+    dict(name="3x3_pair_384_2ntiles", Ci=384, Co=384, k=3, pad=1, H=64, W=80, B=3, want="bf16"),
 ]
 
 

@@ -142,6 +142,9 @@ PROBES = {
     "dw288_ld320": lambda: dw(4, 512, 512, 288, 0, pitched=True),
     "dwg2048": lambda: dw(4, 64, 64, 2048, 1),
     "ln96": lambda: ln(4, 512, 512, 96),
+    "ln1280": lambda: ln(1, 1, 8224, 1280),
+    "ln1280_32": lambda: ln(1, 1, 32, 1280),
+    "ln768": lambda: ln(1, 1, 10960, 768),
     "gram96": lambda: gram(4, 512, 512, 96, 1),
 }
 
