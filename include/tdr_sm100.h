@@ -38,6 +38,10 @@ const char* tdr_last_error(void);
 int tdr_version(void);
 /* 0 if the current device is sm_100 (B200), TDR_ENOSUP otherwise. */
 int tdr_check_device(void);
+/* Programmatic dependent launch of the hot kernels (their prologues overlap the previous kernel's tail).  Off by default
+ * (measured neutral); TDR_PDL=1 in the environment or tdr_set_pdl(1) turns it on.  Sets the switch, returns the previous
+ * value.  Results do not depend on it. */
+int tdr_set_pdl(int on);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Implicit-GEMM convolution (tcgen05 + TMA).  Replaces nn.Conv2d for: 1x1 convs R:229,234,252,254,613,619;

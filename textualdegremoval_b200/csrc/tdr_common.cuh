@@ -46,6 +46,10 @@ static inline void tdr_fast_div_setup(int d, uint32_t* m, uint32_t* s) {
 }
 
 int tdr_num_sms();
+// Programmatic dependent launch: 1 lets the hot kernels' prologues (barrier init, TMEM allocation, tensor-map prefetch,
+// CTA launch) overlap the tail of the previous kernel in the stream.  Off by default (TDR_PDL=1 / tdr_set_pdl(1) turn
+// it on): measured neutral on the forward step and 2 % slower on the training step (profiles/r02b_pdl_ab.txt).
+int tdr_pdl_enabled();
 
 // ------------------------------------------------------------------------------------------------
 // device helpers
@@ -115,6 +119,13 @@ __device__ __forceinline__ void pack8r(void* p, const float* f, int fp16) {
                                             pack2r(f[6], f[7], fp16));
 }
 __device__ __forceinline__ uint16_t pack1r(float a, int fp16) { return (uint16_t)(pack2r(a, 0.f, fp16) & 0xffffu); }
+
+// Programmatic dependent launch.  Contract for every kernel launched through tdr_launch_pdl: pdl_wait() comes before the
+// first access to global memory that is not a launch parameter (it returns once the previous kernel in the stream has
+// finished and its writes are visible), and pdl_launch() comes after it and after every dynamic resource (TMEM) is
+// held, so that the next kernel's CTAs may be placed as soon as this kernel's CTAs free their SMs.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -324,6 +335,25 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
          ((uint32_t)(M >> 4) << 24);
 }
 #endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// <<<grid, block, smem, stream>>> with the programmatic-stream-serialization attribute (see pdl_wait above)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t tdr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = tdr_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 // host: build a CUtensorMap (bf16, SWIZZLE_128B, zero OOB fill).  dims/strides innermost first;
 // strides_bytes has rank-1 entries (stride of dim 1..rank-1).  Returns 0 or TDR_E*.

@@ -211,6 +211,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();          // everything above overlapped the previous kernel's tail; global memory is touched from here on
+  pdl_launch();
 
   const int taps = a.KH * a.KW;
   const int ksteps = taps * a.kchunks;
@@ -1299,7 +1301,8 @@ extern "C" int tdr_conv_gemm(const tdr_conv_gemm_desc* d, cudaStream_t stream) {
                                           227 * 1024));                                                            \
       attr_set = true;                                                                                             \
     }                                                                                                              \
-    conv_gemm_kernel<VV><<<grid, kThreads, smem, stream>>>(map_a, map_w, map_o, map_r2, map_r1, map_o2, a);        \
+    TDR_CHECK_CUDA(tdr_launch_pdl(conv_gemm_kernel<VV>, dim3(grid), dim3(kThreads), smem, stream, map_a, map_w,    \
+                                  map_o, map_r2, map_r1, map_o2, a));                                              \
   } while (0)
   switch (variant) {
     case 0: TDR_LAUNCH_CONV(0); break;

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(192, 1) mdta_gram_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -280,6 +282,8 @@ __global__ void __launch_bounds__(256) mdta_softmax_kernel(const float* __restri
   const size_t psz = (size_t)c * c + 2 * c;
   const float* base = partials + (size_t)(b * heads + h) * nchunks * psz;
   __shared__ float sg[8][T][32], sk[8][T][32], sq[8];
+  pdl_wait();
+  pdl_launch();
   float g[T], nk[T];
 #pragma unroll
   for (int t = 0; t < T; ++t) g[t] = nk[t] = 0.f;
@@ -426,12 +430,16 @@ __global__ void __launch_bounds__(256) mdta_fold_kernel(const float* __restrict_
   float* a = sm;                   // [c][c]
   float* wsm = sm + c * c;         // [kFoldRows][c]
   const float* src = attn + (size_t)(b * heads + h) * c * c;
-  for (int t = threadIdx.x; t < (c * c) >> 2; t += blockDim.x)          // c % 8 == 0: float4 staging
-    reinterpret_cast<float4*>(a)[t] = reinterpret_cast<const float4*>(src)[t];
+  // w_out is a parameter (never written by the softmax kernel that precedes this one in the stream): staged while
+  // that kernel drains
   for (int t = threadIdx.x; t < kFoldRows * c; t += blockDim.x) {
     const int co = co0 + t / c;
     wsm[t] = co < C ? w_out[(size_t)co * C + h * c + t % c] : 0.f;
   }
+  pdl_wait();
+  pdl_launch();
+  for (int t = threadIdx.x; t < (c * c) >> 2; t += blockDim.x)          // c % 8 == 0: float4 staging
+    reinterpret_cast<float4*>(a)[t] = reinterpret_cast<const float4*>(src)[t];
   __syncthreads();
   for (int idx = threadIdx.x; idx < kFoldRows * c; idx += blockDim.x) {
     const int r = idx / c, j = idx % c;
@@ -486,7 +494,7 @@ extern "C" int tdr_mdta_gram(const void* qkv_bf16, long long ld, int B, long lon
     attr_set = true;
   }
   dim3 grid(a.plan.nchunks, heads, B);
-  mdta_gram_kernel<<<grid, 192, smem, stream>>>(map, a);
+  TDR_CHECK_CUDA(tdr_launch_pdl(mdta_gram_kernel, grid, dim3(192), smem, stream, map, a));
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
@@ -500,8 +508,12 @@ extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, i
   TDR_CHECK_ARG(weff_ld >= C && weff_ld % 8 == 0, "tdr_mdta_weff: bad weff_ld");
   {
     dim3 grid(p.c, heads, B);
-    if (p.c <= 128) mdta_softmax_kernel<4><<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out, topk_w);
-    else mdta_softmax_kernel<8><<<grid, 256, 0, stream>>>(partials, C, heads, p.nchunks, temperature, attn_ws, shat_out, topk_w);
+    if (p.c <= 128)
+      TDR_CHECK_CUDA(tdr_launch_pdl(mdta_softmax_kernel<4>, grid, dim3(256), 0, stream, partials, C, heads, p.nchunks,
+                                    temperature, attn_ws, shat_out, topk_w));
+    else
+      TDR_CHECK_CUDA(tdr_launch_pdl(mdta_softmax_kernel<8>, grid, dim3(256), 0, stream, partials, C, heads, p.nchunks,
+                                    temperature, attn_ws, shat_out, topk_w));
     TDR_CHECK_LAUNCH();
   }
   const size_t smem = ((size_t)p.c * p.c + kFoldRows * p.c) * sizeof(float);
@@ -511,8 +523,8 @@ extern "C" int tdr_mdta_weff(const float* partials, int B, long long P, int C, i
     attr_set = true;
   }
   dim3 grid((C + kFoldRows - 1) / kFoldRows, heads, B);
-  mdta_fold_kernel<<<grid, 256, smem, stream>>>(attn_ws, C, heads, w_out, reinterpret_cast<bf16*>(weff_bf16), weff_ld,
-                                            reinterpret_cast<bf16*>(weff_t_bf16), fp16);
+  TDR_CHECK_CUDA(tdr_launch_pdl(mdta_fold_kernel, grid, dim3(256), smem, stream, attn_ws, C, heads, w_out,
+                                reinterpret_cast<bf16*>(weff_bf16), weff_ld, reinterpret_cast<bf16*>(weff_t_bf16), fp16));
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const float* __restrict__ 
   const long long row = warp_id * rpw + sub;
   const int nvec = C >> 2;
   const bool row_ok = row < rows;
+  pdl_wait();
+  pdl_launch();
   float4 v[NV];
   float s = 0.f;
 #pragma unroll
@@ -284,6 +286,8 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_wait();
+  pdl_launch();
 
   // CTA -> (channel chunk, spatial group): the chunk is fixed for the CTA's lifetime (taps stay in registers) and the
   // CTAs running concurrently cover ALL chunks of neighbouring spatial tiles, so whole pixel rows are touched together.
@@ -667,6 +671,8 @@ __global__ void __launch_bounds__(256) cast_rows_kernel(float* __restrict__ src,
                                                         const float* __restrict__ scale_bf16, int rescale_in) {
   const int nvec = C >> 3;
   const long long total = rows * nvec;
+  pdl_wait();
+  pdl_launch();
   const float sh = scale16 ? *scale16 : 1.f, sb = scale_bf16 ? *scale_bf16 : 1.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -824,7 +830,8 @@ extern "C" int tdr_rownorm(const float* in, long long in_ld, long long rows, int
   const int blocks = (int)((warps + 7) / 8);
   bf16* o = reinterpret_cast<bf16*>(out_bf16);
 #define TDR_RN(NV) \
-  rownorm_kernel<NV><<<blocks, 256, 0, stream>>>(in, in_ld, rows, C, mode, weight, bias, eps, act, o, out_ld, out_f32, out_f32_ld, G)
+  TDR_CHECK_CUDA(tdr_launch_pdl(rownorm_kernel<NV>, dim3(blocks), dim3(256), 0, stream, in, in_ld, rows, C, mode, weight, bias, eps, \
+                                act, o, out_ld, out_f32, out_f32_ld, G))
   if (nv <= 1) TDR_RN(1);
   else if (nv <= 2) TDR_RN(2);
   else if (nv <= 3) TDR_RN(3);
@@ -910,12 +917,12 @@ static int dwconv_launch(const void* in_bf16, long long in_ld, int B, int H, int
     TDR_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_tma_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  if (bwd) dwconv3x3_tma_kernel<2, false><<<grid, 256, smem, stream>>>(map, a);
-  else if (gate && y_out) dwconv3x3_tma_kernel<3, false><<<grid, 256, smem, stream>>>(map, a);
-  else if (gate && half) dwconv3x3_tma_kernel<1, true><<<grid, 256, smem, stream>>>(map, a);
-  else if (gate) dwconv3x3_tma_kernel<1, false><<<grid, 256, smem, stream>>>(map, a);
-  else if (half) dwconv3x3_tma_kernel<0, true><<<grid, 256, smem, stream>>>(map, a);
-  else dwconv3x3_tma_kernel<0, false><<<grid, 256, smem, stream>>>(map, a);
+  if (bwd) TDR_CHECK_CUDA(tdr_launch_pdl(dwconv3x3_tma_kernel<2, false>, dim3(grid), dim3(256), smem, stream, map, a));
+  else if (gate && y_out) TDR_CHECK_CUDA(tdr_launch_pdl(dwconv3x3_tma_kernel<3, false>, dim3(grid), dim3(256), smem, stream, map, a));
+  else if (gate && half) TDR_CHECK_CUDA(tdr_launch_pdl(dwconv3x3_tma_kernel<1, true>, dim3(grid), dim3(256), smem, stream, map, a));
+  else if (gate) TDR_CHECK_CUDA(tdr_launch_pdl(dwconv3x3_tma_kernel<1, false>, dim3(grid), dim3(256), smem, stream, map, a));
+  else if (half) TDR_CHECK_CUDA(tdr_launch_pdl(dwconv3x3_tma_kernel<0, true>, dim3(grid), dim3(256), smem, stream, map, a));
+  else TDR_CHECK_CUDA(tdr_launch_pdl(dwconv3x3_tma_kernel<0, false>, dim3(grid), dim3(256), smem, stream, map, a));
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }
@@ -995,9 +1002,9 @@ extern "C" int tdr_cast_rows(float* in, long long in_ld, long long rows, int C, 
   TDR_CHECK_ARG(C % 8 == 0 && in_ld % 4 == 0 && out_bf16_ld % 8 == 0 && out_fp16_ld % 8 == 0 && ((uintptr_t)in & 15) == 0 &&
                 ((uintptr_t)out_bf16 & 15) == 0 && ((uintptr_t)out_fp16 & 15) == 0, "tdr_cast_rows: C %% 8, 16 B-aligned rows");
   if (rows == 0) return TDR_OK;
-  cast_rows_kernel<<<grid_for(rows * (C / 8), 256, 16), 256, 0, stream>>>(in, in_ld, rows, C, reinterpret_cast<bf16*>(out_bf16),
-                                                                         out_bf16_ld, reinterpret_cast<__half*>(out_fp16),
-                                                                         out_fp16_ld, scale16, scale_bf16, rescale_in);
+  TDR_CHECK_CUDA(tdr_launch_pdl(cast_rows_kernel, dim3(grid_for(rows * (C / 8), 256, 16)), dim3(256), 0, stream, in, in_ld, rows,
+                                C, reinterpret_cast<bf16*>(out_bf16), out_bf16_ld, reinterpret_cast<__half*>(out_fp16),
+                                out_fp16_ld, scale16, scale_bf16, rescale_in));
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -32,6 +32,20 @@ int tdr_num_sms() {
   return n;
 }
 
+static int g_pdl = -1;
+int tdr_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("TDR_PDL");
+    g_pdl = (e && e[0] == '1') ? 1 : 0;      // opt-in: measured neutral on the forward step, see DESIGN.md
+  }
+  return g_pdl;
+}
+extern "C" int tdr_set_pdl(int on) {
+  const int prev = tdr_pdl_enabled();
+  g_pdl = on ? 1 : 0;
+  return prev;
+}
+
 extern "C" int tdr_check_device(void) {
   int dev = 0, major = 0, minor = 0;
   TDR_CHECK_CUDA(cudaGetDevice(&dev));

@@ -68,6 +68,7 @@ SIGNATURES = {
     "tdr_last_error": (C.c_char_p, []),
     "tdr_version": (_i, []),
     "tdr_check_device": (_i, []),
+    "tdr_set_pdl": (_i, [_i]),
     "tdr_conv_gemm": (_i, [C.POINTER(ConvGemmDesc), _vp]),
     "tdr_conv_gemm_ln_supported": (_i, [C.POINTER(ConvGemmDesc)]),
     "tdr_conv_gemm_desc_layout": (None, [C.POINTER(_i)]),
