@@ -577,9 +577,11 @@ __global__ void copy_rows_kernel(const float* __restrict__ src, long long src_ld
 }
 
 // ------------------------------------------------------------------------------------------------ small convs
-// Ci <= 8 input channels (fp32 NHWC image), Co % 8 == 0 outputs.  A thread owns TWO horizontally adjacent pixels and
-// 16 output channels: the 3x4 input window is loaded once into registers, every weight read from shared memory
-// ([ci*9+tap][Co], broadcast across the warp) feeds two pixels, and each pixel's 16 outputs are stored as 64 B runs.
+// Ci <= 8 input channels (fp32 NHWC image), Co % 8 == 0 outputs.  A thread owns TWO horizontally adjacent pixels: the
+// 3x4 input window is loaded once into registers and the thread walks the output channels in groups of 16, so every
+// weight read from shared memory ([ci*9+tap][Co]) is one warp-wide broadcast (all lanes are on the same channel group:
+// lanes on different groups made every LDS.128 a two-way bank conflict, 128 B apart) that feeds two pixels, and each
+// pixel's 16 outputs are stored as 64 B runs.
 template <int CI, int CPT>
 __global__ void __launch_bounds__(256) conv3x3_small_ci_kernel(const float* __restrict__ in, int B, int H, int W,
                                                                const float* __restrict__ weight,
@@ -594,11 +596,9 @@ __global__ void __launch_bounds__(256) conv3x3_small_ci_kernel(const float* __re
   __syncthreads();
   const int ncg = Co / CPT;                               // CPT-channel groups (16, or 8 when Co % 16 != 0)
   const int wp = (W + 1) >> 1;                            // pixel pairs per row
-  const long long total = (long long)B * H * wp * ncg;
-  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(it % ncg);
-    long long p = it / ncg;
+  const long long total = (long long)B * H * wp;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
     const int xp = (int)(p % wp);
     const int y = (int)((p / wp) % H);
     const int b = (int)(p / ((long long)wp * H));
@@ -614,6 +614,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_ci_kernel(const float* __re
 #pragma unroll
         for (int ci = 0; ci < CI; ++ci) win[dy][dx][ci] = ok ? __ldg(ip + ci) : 0.f;
       }
+    for (int cg = 0; cg < ncg; ++cg) {
     float acc[2][CPT];
 #pragma unroll
     for (int e = 0; e < CPT; ++e) acc[0][e] = acc[1][e] = bias ? bias[cg * CPT + e] : 0.f;
@@ -660,6 +661,7 @@ __global__ void __launch_bounds__(256) conv3x3_small_ci_kernel(const float* __re
         }
       }
     }
+    }   // cg
   }
 }
 
@@ -1046,7 +1048,7 @@ extern "C" int tdr_conv3x3_small_ci(const float* in, int B, int H, int W, int Ci
                 "tdr_conv3x3_small_ci: need 1 <= Ci <= 8 and Co %% 8 == 0 (got Ci=%d Co=%d)", Ci, Co);
   TDR_CHECK_ARG(out_f32_ld % 4 == 0 && out_bf16_ld % 8 == 0, "tdr_conv3x3_small_ci: bad strides");
   const int cpt = Co % 16 == 0 ? 16 : 8;
-  const long long items = (long long)B * H * ((W + 1) / 2) * (Co / cpt);
+  const long long items = (long long)B * H * ((W + 1) / 2);
   const size_t smem = (size_t)Co * Ci * 9 * sizeof(float);
   bf16* o16 = reinterpret_cast<bf16*>(out_bf16);
 #define TDR_SCI(N)                                                                                                   \

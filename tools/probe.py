@@ -149,6 +149,21 @@ PROBES = {
 }
 
 
+def small_ci(B, H, W, Co, f32=True, f16=True):
+    x = torch.rand(B, H, W, 3, device=DEV)
+    w = torch.randn(Co, 3, 3, 3, device=DEV) * 0.1
+    b = torch.randn(Co, device=DEV) * 0.1
+    o32 = torch.empty(B, H, W, Co, device=DEV) if f32 else None
+    o16 = torch.empty(B, H, W, Co, device=DEV, dtype=torch.float16) if f16 else None
+    nbytes = B * H * W * (12 + Co * ((4 if f32 else 0) + (2 if f16 else 0)))
+    return (lambda: ops.conv3x3_small_ci(x, w, b, relu=True, out_f32=o32, out_bf16=o16)), nbytes, 2 * 27 * B * H * W * Co
+
+
+PROBES["sci_b4"] = lambda: small_ci(4, 512, 512, 48)
+PROBES["sci_b8"] = lambda: small_ci(8, 512, 512, 48)
+PROBES["sci_b4_f32"] = lambda: small_ci(4, 512, 512, 48, f16=False)
+
+
 def main():
     names = sys.argv[1:] or list(PROBES)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
