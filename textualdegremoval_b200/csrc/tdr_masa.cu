@@ -255,23 +255,35 @@ __global__ void fine_argmax_kernel(const float* __restrict__ corr, int npos, int
   }
 }
 
+// Every quotient below is a multiply-high by a host-prepared constant (tdr_fast_div_setup): the kernel used to spend
+// most of its issue slots in ~30 runtime integer divisions per thread for 9 gathered 16-byte loads.
+struct TransferDiv {
+  uint32_t nvec_m, nvec_s, ow_m, ow_s, oh_m, oh_s, wy_m, wy_s, wx_m, wx_s, s_m, s_s, dx_m, dx_s;
+};
+__device__ __forceinline__ int tr_fdiv(int n, uint32_t m, uint32_t s) { return m ? (int)(__umulhi((uint32_t)n, m) >> s) : n; }
+
 __global__ void __launch_bounds__(256) transfer_kernel(const bf16* __restrict__ f, int B, int Hs, int Ws, int C,
                                                        const int* __restrict__ origin, const int* __restrict__ index,
                                                        const float* __restrict__ att, int py, int px, int k_y, int k_x,
                                                        int d_x, int s, float* __restrict__ o32, long long ld32,
-                                                       bf16* __restrict__ o16, long long ld16) {
+                                                       bf16* __restrict__ o16, long long ld16, const TransferDiv fd) {
   const int OH = py * k_y * s, OW = px * k_x * s;
   const int nvec = C >> 3;
   const int nq = k_y * k_x, nblk = py * px;
-  const long long total = (long long)B * OH * OW * nvec;
+  const int total = B * OH * OW * nvec;                   // < 2^31 (checked by the caller)
   const float inv_s = 1.f / (float)s;
-  for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < total;
-       it += (long long)gridDim.x * blockDim.x) {
-    const int v = (int)(it % nvec);
-    const long long p = it / nvec;
-    const int X = (int)(p % OW), Y = (int)((p / OW) % OH), b = (int)(p / ((long long)OW * OH));
-    const int tby = Y / (k_y * s), Yl = Y % (k_y * s);
-    const int tbx = X / (k_x * s), Xl = X % (k_x * s);
+  for (long long it64 = blockIdx.x * (long long)blockDim.x + threadIdx.x; it64 < total;
+       it64 += (long long)gridDim.x * blockDim.x) {
+    const int it = (int)it64;
+    const int p = tr_fdiv(it, fd.nvec_m, fd.nvec_s);
+    const int v = it - p * nvec;
+    const int t = tr_fdiv(p, fd.ow_m, fd.ow_s);
+    const int X = p - t * OW;
+    const int b = tr_fdiv(t, fd.oh_m, fd.oh_s);
+    const int Y = t - b * OH;
+    const int tby = tr_fdiv(Y, fd.wy_m, fd.wy_s), Yl = Y - tby * (k_y * s);
+    const int tbx = tr_fdiv(X, fd.wx_m, fd.wx_s), Xl = X - tbx * (k_x * s);
+    const int qy0 = tr_fdiv(Yl, fd.s_m, fd.s_s), qx0 = tr_fdiv(Xl, fd.s_m, fd.s_s);
     const int win = b * nblk + tby * px + tbx;
     const int y1 = origin[3 * win + 1] * s, x1 = origin[3 * win + 2] * s;
     const int* idx = index + (size_t)win * nq;
@@ -281,15 +293,16 @@ __global__ void __launch_bounds__(256) transfer_kernel(const bf16* __restrict__ 
     int cnt = 0;
 #pragma unroll
     for (int oy = -1; oy <= 1; ++oy) {
-      const int qy = Yl / s + oy;
+      const int qy = qy0 + oy;
       if (qy < 0 || qy >= k_y) continue;
 #pragma unroll
       for (int ox = -1; ox <= 1; ++ox) {
-        const int qx = Xl / s + ox;
+        const int qx = qx0 + ox;
         if (qx < 0 || qx >= k_x) continue;
         const int j = idx[qy * k_x + qx];
-        const int sy = y1 + (j / d_x) * s + (Yl - qy * s + s);
-        const int sx = x1 + (j % d_x) * s + (Xl - qx * s + s);
+        const int jy = tr_fdiv(j, fd.dx_m, fd.dx_s);
+        const int sy = y1 + jy * s + (Yl - qy * s + s);
+        const int sx = x1 + (j - jy * d_x) * s + (Xl - qx * s + s);
         ++cnt;
         if (sy >= 0 && sy < Hs && sx >= 0 && sx < Ws) {
           float e8[8];
@@ -313,11 +326,11 @@ __global__ void __launch_bounds__(256) transfer_kernel(const bf16* __restrict__ 
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] *= scale;
     if (o32) {
-      float4* q4 = reinterpret_cast<float4*>(o32 + p * ld32 + v * 8);
+      float4* q4 = reinterpret_cast<float4*>(o32 + (long long)p * ld32 + v * 8);
       q4[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
       q4[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
-    if (o16) *reinterpret_cast<bf16x8*>(o16 + p * ld16 + v * 8) = pack8(acc);
+    if (o16) *reinterpret_cast<bf16x8*>(o16 + (long long)p * ld16 + v * 8) = pack8(acc);
   }
 }
 
@@ -583,9 +596,19 @@ extern "C" int tdr_masa_transfer(const void* f_ref_bf16, int B, int Hr_s, int Wr
   TDR_CHECK_ARG(f_ref_bf16 && origin && index && att && (out || out_bf16), "tdr_masa_transfer: null pointer");
   TDR_CHECK_ARG(C % 8 == 0 && s >= 1 && out_ld % 4 == 0 && out_bf16_ld % 8 == 0, "tdr_masa_transfer: bad arguments");
   const long long items = (long long)B * py * k_y * s * px * k_x * s * (C / 8);
+  TDR_CHECK_ARG(items < (1ll << 31) && k_y >= 1 && k_x >= 1 && d_x >= 1 && py >= 1 && px >= 1,
+                "tdr_masa_transfer: %lld output vectors (limit 2^31 per call: split the batch)", items);
+  TransferDiv fd;
+  tdr_fast_div_setup(C / 8, &fd.nvec_m, &fd.nvec_s);
+  tdr_fast_div_setup(px * k_x * s, &fd.ow_m, &fd.ow_s);
+  tdr_fast_div_setup(py * k_y * s, &fd.oh_m, &fd.oh_s);
+  tdr_fast_div_setup(k_y * s, &fd.wy_m, &fd.wy_s);
+  tdr_fast_div_setup(k_x * s, &fd.wx_m, &fd.wx_s);
+  tdr_fast_div_setup(s, &fd.s_m, &fd.s_s);
+  tdr_fast_div_setup(d_x, &fd.dx_m, &fd.dx_s);
   transfer_kernel<<<grid1d(items, 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(f_ref_bf16), B, Hr_s, Wr_s, C,
                                                           origin, index, att, py, px, k_y, k_x, d_x, s, out, out_ld,
-                                                          reinterpret_cast<bf16*>(out_bf16), out_bf16_ld);
+                                                          reinterpret_cast<bf16*>(out_bf16), out_bf16_ld, fd);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -146,6 +146,10 @@ PROBES = {
     "ln1280_32": lambda: ln(1, 1, 32, 1280),
     "ln768": lambda: ln(1, 1, 10960, 768),
     "gram96": lambda: gram(4, 512, 512, 96, 1),
+    "gram96_h2": lambda: gram(4, 256, 256, 96, 2),
+    "gram192_h4": lambda: gram(4, 128, 128, 192, 4),
+    "gram384_h8": lambda: gram(4, 64, 64, 384, 8),
+    "gram48": lambda: gram(4, 512, 512, 48, 1),
 }
 
 
