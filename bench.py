@@ -404,16 +404,47 @@ def _run_b200(args, out):
             torch.cuda.profiler.stop()
         out.emit(json.dumps({"ncu_mode": True, "launches_per_step": ops.PROF.launches // (1 + args.steps)}))
         return 0
+    launch_mode = "eager (one host launch per kernel)"
+    step_eager = step_resident
     with torch.no_grad():
+        l0 = ops.PROF.launches
+        step_resident()
+        launches_per_step = ops.PROF.launches - l0
+        if not args.no_graph:
+            # the public serving path for fixed tile shapes: the forward captured once, one cudaGraphLaunch per step
+            # (same kernels and launch parameters, bit-identical output: tests/gpu_checks.py graph_replay)
+            try:
+                from textualdegremoval_b200.graphs import GraphedForward
+                if cfg["kind"] == "embed":
+                    gf = GraphedForward(fwd, x_d)
+                    step_resident = lambda: gf(x_d)                       # noqa: E731
+
+                    def step_e2e():
+                        y = gf(x_h)
+                        out_h.copy_(y, non_blocking=True)
+                        return y
+                else:
+                    gin_d = (lq_d, ref_d) if cfg["guided"] else (lq_d,)
+                    gin_h = (lq_h, ref_h) if cfg["guided"] else (lq_h,)
+                    gf = GraphedForward(net, *gin_d)
+                    step_resident = lambda: gf(*gin_d)                    # noqa: E731
+
+                    def step_e2e():
+                        y = gf(*gin_h)                                     # pinned host -> the graph's input buffers
+                        out_h.copy_(y, non_blocking=True)
+                        return y
+                launch_mode = (f"cuda_graph: GraphedForward replays the forward's {launches_per_step} libtdr_sm100 kernel "
+                               f"launches with one cudaGraphLaunch per step")
+            except Exception as e:  # noqa: BLE001
+                launch_mode = f"eager (graph capture failed: {type(e).__name__}: {e})"[:240]
         for _ in range(max(args.warmup, 3)):
             step_resident()
         barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        l0 = ops.PROF.launches
         ms = timed(step_resident, args.steps)
-        launches = ops.PROF.launches - l0
+        launches = launches_per_step * args.steps
         barrier()
         clocks = sampler.stop() if rank == 0 else None
         for _ in range(2):
@@ -421,6 +452,15 @@ def _run_b200(args, out):
         barrier()
         ms_e2e = timed(step_e2e, args.steps)
         barrier()
+        ms_eager = None
+        if step_eager is not step_resident:    # informational: the same forward, one host launch per kernel
+            for _ in range(2):
+                step_eager()
+            ms_eager = timed(step_eager, args.steps)
+        barrier()
+        step_resident = step_eager            # the per-launch profile below times the eager launches
+        gf = None
+        torch.cuda.empty_cache()
         # per-launch profile (untimed pass) for the roofline of the dominant kernel
         prof = None
         if rank == 0:
@@ -513,6 +553,10 @@ def _run_b200(args, out):
         "clocks": clocks,
         "roofline": roof,
     }
+    line["config"]["launch"] = launch_mode
+    if ms_eager is not None:
+        line["eager_launch"] = {"ms_per_step": ms_eager / args.steps, "value": B * args.steps / (ms_eager * 1e-3), "unit": "img/s",
+                                "what": "same forward with one host launch per kernel (this rank)"}
     if train is not None:
         tsteps = args.train_steps
         line["train_step"] = {
@@ -547,6 +591,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the configuration's batch per GPU")
     ap.add_argument("--size", type=int, default=0, help="override the configuration's tile size")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time the forward with one host launch per kernel instead of "
+                    "the CUDA-graph replay (GraphedForward)")
     ap.add_argument("--dump-prof", default="", help="write the per-(kernel, shape) event-timed profile to this json")
     ap.add_argument("--train-steps", type=int, default=10, help="timed training steps reported under train_step (0 = skip)")
     ap.add_argument("--dump-prof-train", default="", help="per-(kernel, shape) profile of one training step")

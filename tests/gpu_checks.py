@@ -1767,7 +1767,57 @@ def check_fullsize_golden():
     return out
 
 
+def check_graph_replay():
+    """GraphedForward (CUDA-graph replay of the inference forward) returns the eager path's bits, for new inputs too, and
+    refuses a different shape.  The timing note is informational (one image: the coarse levels are launch-bound)."""
+    from textualdegremoval_b200.archs import define_network
+    from textualdegremoval_b200.graphs import GraphedForward
+    from oracle.make_golden import GUIDED_CASES
+    out = []
+    meta = GUIDED_CASES["guided_restormer_128"]
+    torch.manual_seed(3)
+    net = define_network(dict(type="RestormerRefFusion", **meta["cfg"]))
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if n.endswith("alpha"):
+                p.uniform_(0.2, 1.0)
+    net = net.to(DEV).eval()
+    g = torch.Generator().manual_seed(11)
+    xs = [(torch.rand(1, 3, 128, 128, generator=g).to(DEV), torch.rand(1, 3, 128, 128, generator=g).to(DEV))
+          for _ in range(3)]
+    with torch.no_grad():
+        eager = [net(a, b).clone() for a, b in xs]
+    fwd = GraphedForward(net, *xs[0])
+    for i, (a, b) in enumerate(xs):
+        out.append(result(f"graph_replay_equals_eager_{i}", fwd(a, b).clone(), eager[i], 0.0, note="bit-identical"))
+    try:
+        fwd(torch.rand(1, 3, 64, 64, device=DEV), xs[0][1])
+        refused = False
+    except ValueError:
+        refused = True
+    out.append(dict(name="graph_replay_refuses_other_shape", max_err=0.0, tol=0.0, ok=refused, note=""))
+
+    def ms(fn, n=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / n
+    with torch.no_grad():
+        t_eager = ms(lambda: net(*xs[0]))
+    t_graph = ms(lambda: fwd(*xs[0]))
+    out.append(dict(name="graph_replay_timing_128", max_err=0.0, tol=0.0, ok=True,
+                    note=f"1 x 128x128 guided forward: eager {t_eager:.3f} ms, graph replay {t_graph:.3f} ms"))
+    return out
+
+
 CHECKS = {
+    "graph_replay": check_graph_replay,
     "layout": check_layout,
     "rownorm": check_rownorm,
     "dwconv": check_dwconv,

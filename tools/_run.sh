@@ -1,10 +1,11 @@
 mkdir -p gpurun_out/r02b
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --no-cpu-baseline --train-steps 3 --dump-prof gpurun_out/r02b/prof_a.json > gpurun_out/r02b/bench_a.json 2> gpurun_out/r02b/bench_a.err
+python bench.py --no-cpu-baseline --train-steps 3 > gpurun_out/r02b/bench_c3.json 2> gpurun_out/r02b/bench_c3.err; tail -c 300 gpurun_out/r02b/bench_c3.err
+for c in 2 4 5; do
+python bench.py --config $c --no-cpu-baseline --train-steps 0 > gpurun_out/r02b/bench_c$c.json 2> gpurun_out/r02b/bench_c$c.err; tail -c 300 gpurun_out/r02b/bench_c$c.err
+done
 python - <<'P'
 import json
-d=json.loads(open("gpurun_out/r02b/bench_a.json").read().strip().splitlines()[-1])
-print(d["ms_per_step"], d["value"], d["e2e"]["value"], d.get("train_step",{}).get("ms_per_step"), d["clocks"], d["roofline"]["frac"])
-for k,v in d["roofline"]["families"].items():
-    if v["ms"]>0.3: print(k, v)
+for c in (3,2,4,5):
+    d=json.loads(open(f"gpurun_out/r02b/bench_c{c}.json").read().strip().splitlines()[-1])
+    print(c, round(d["ms_per_step"],3), round(d["value"],2), round(d["e2e"]["value"],2), d.get("eager_launch"), d["config"]["launch"][:60], d["gpu_launches"], d["clocks"]["sm_mhz"], d.get("train_step",{}).get("ms_per_step"))
 P
