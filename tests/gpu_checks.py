@@ -1349,6 +1349,10 @@ def check_bwd_pointwise():
     t = q(rnd(2, 16, 6, 10, seed=13))                                       # NCHW
     out.append(result("pixel_unshuffle", nchw(ops.pixel_shuffle(nhwc(t.to(BF16)), 1)), F.pixel_unshuffle(t, 2), 0.0))
     out.append(result("pixel_shuffle", nchw(ops.pixel_shuffle(nhwc(t.to(BF16)), 2)), F.pixel_shuffle(t, 2), 0.0))
+    for cc, hh, ww in ((96, 6, 10), (64, 8, 4), (24, 6, 6)):                # 16-byte vector kernels (C % 32 / C % 8) + fallback
+        t = q(rnd(3, cc, hh, ww, seed=16 + cc))
+        out.append(result(f"pixel_unshuffle_C{cc}", nchw(ops.pixel_shuffle(nhwc(t.to(BF16)), 1)), F.pixel_unshuffle(t, 2), 0.0))
+        out.append(result(f"pixel_shuffle_C{cc}", nchw(ops.pixel_shuffle(nhwc(t.to(BF16)), 2)), F.pixel_shuffle(t, 2), 0.0))
     yy, dd = q(rnd(1, 5, 5, 64, seed=14)), q(rnd(1, 5, 5, 64, seed=15))
     out.append(result("relu_mask", ops.relu_mask(yy.to(BF16).to(DEV), dd.to(BF16).to(DEV)), dd * (yy > 0), 0.0))
     return out

@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(256) mdta_bwd_kernel(const MdtaBwdArgs a) {
     float s = 0.f;
     for (int k = tid; k < 256; k += 32) s += red[k];
     s = warp_sum(s);
-    if (tid == 0) a.dtemp_part[b * a.heads + h] = s;
+    if (tid == 0 && blockIdx.z == 0) a.dtemp_part[b * a.heads + h] = s;
   }
   for (int j = tid; j < c; j += 256) {
     float s = 0.f;
@@ -884,21 +884,25 @@ __global__ void __launch_bounds__(256) mdta_bwd_kernel(const MdtaBwdArgs a) {
   // rows of M (zero outside this head's blocks):
   //   dq_i = sum_j dS_hat[i][j] / (nq_i nk_j) * k_j - r_i / nq_i^2 * q_i
   //   dk_j = sum_i dS_hat[i][j] / (nq_i nk_j) * q_i - s_j / nk_j^2 * k_j
+  // The (sample, head) is shared by gridDim.z CTAs: every one repeats the small c x c part above (bit-identical) and writes
+  // the rows i = blockIdx.z, blockIdx.z + gridDim.z, ... -- one CTA per (sample, head) left the [2C x 2C] writer on
+  // heads * B SMs.
   bf16* mq = a.mqk + (size_t)b * 2 * C * a.mqk_ld;
-  for (int t = tid; t < c * 2 * C; t += 256) {
-    const int i = t / (2 * C), col = t % (2 * C);
-    float vq = 0.f, vk = 0.f;
-    if (col >= C + h * c && col < C + h * c + c) {          // k columns
-      const int j = col - C - h * c;
-      vq = dat[i * ld + j] / (nq[i] * nk[j]);
-      if (j == i) vk = -ss[i] / (nk[i] * nk[i]);
-    } else if (col >= h * c && col < h * c + c) {           // q columns
-      const int j = col - h * c;
-      vk = dat[j * ld + i] / (nq[j] * nk[i]);
-      if (j == i) vq = -rr[i] / (nq[i] * nq[i]);
+  for (int i = blockIdx.z; i < c; i += gridDim.z) {
+    for (int col = tid; col < 2 * C; col += 256) {
+      float vq = 0.f, vk = 0.f;
+      if (col >= C + h * c && col < C + h * c + c) {          // k columns
+        const int j = col - C - h * c;
+        vq = dat[i * ld + j] / (nq[i] * nk[j]);
+        if (j == i) vk = -ss[i] / (nk[i] * nk[i]);
+      } else if (col >= h * c && col < h * c + c) {           // q columns
+        const int j = col - h * c;
+        vk = dat[j * ld + i] / (nq[j] * nk[i]);
+        if (j == i) vq = -rr[i] / (nq[i] * nq[i]);
+      }
+      mq[(size_t)(h * c + i) * a.mqk_ld + col] = __float2bfloat16(vq);
+      mq[(size_t)(C + h * c + i) * a.mqk_ld + col] = __float2bfloat16(vk);
     }
-    mq[(size_t)(h * c + i) * a.mqk_ld + col] = __float2bfloat16(vq);
-    mq[(size_t)(C + h * c + i) * a.mqk_ld + col] = __float2bfloat16(vk);
   }
 }
 
@@ -966,6 +970,59 @@ __global__ void __launch_bounds__(256) pixel_shuffle_kernel(const bf16* __restri
     } else {
       const int s = c & 3;
       out[((((long long)b * (H * 2) + y * 2 + (s >> 1)) * (W * 2)) + x * 2 + (s & 1)) * out_ld + (c >> 2)] = v;
+    }
+  }
+}
+
+// Vector forms of the two modes (the element-wise kernel above ran at 0.10 of HBM: four 64-bit divisions and one 2-byte
+// scattered store per element).  Unshuffle: a thread owns one OUTPUT pixel and 8 input channels -- four 16-byte loads
+// (the 2x2 input pixels), interleaved in registers, four 16-byte stores (32 consecutive output channels).
+__global__ void __launch_bounds__(256) pixel_unshuffle_vec_kernel(const uint16_t* __restrict__ in, long long in_ld, int B,
+                                                                  int H, int W, int C, uint16_t* __restrict__ out,
+                                                                  long long out_ld) {
+  const int nv = C >> 3, OW = W >> 1, OH = H >> 1;
+  const unsigned total = (unsigned)B * OH * OW * nv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned v = i % nv, p = i / nv;
+    const unsigned x = p % OW, t = p / OW, y = t % OH, b = t / OH;
+    uint4 r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      r[q] = *reinterpret_cast<const uint4*>(in + (((long long)b * H + 2 * y + (q >> 1)) * W + 2 * x + (q & 1)) * in_ld + v * 8);
+    const uint16_t* e = reinterpret_cast<const uint16_t*>(r);            // e[q * 8 + c]
+    uint16_t o[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) o[c * 4 + q] = e[q * 8 + c];
+    uint4* dst = reinterpret_cast<uint4*>(out + (((long long)b * OH + y) * OW + x) * out_ld + v * 32);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dst[k] = reinterpret_cast<const uint4*>(o)[k];
+  }
+}
+
+// Shuffle: a thread owns one INPUT pixel and 32 input channels -- four 16-byte loads, de-interleaved into the four
+// sub-pixels' 8 consecutive output channels, four 16-byte stores.
+__global__ void __launch_bounds__(256) pixel_shuffle_vec_kernel(const uint16_t* __restrict__ in, long long in_ld, int B,
+                                                                int H, int W, int C, uint16_t* __restrict__ out,
+                                                                long long out_ld) {
+  const int nv = C >> 5;
+  const unsigned total = (unsigned)B * H * W * nv;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned v = i % nv, p = i / nv;
+    const unsigned x = p % W, t = p / W, y = t % H, b = t / H;
+    uint4 r[4];
+    const uint4* src = reinterpret_cast<const uint4*>(in + (long long)p * in_ld + v * 32);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = src[k];
+    const uint16_t* e = reinterpret_cast<const uint16_t*>(r);            // e[co * 4 + s]
+#pragma unroll
+    for (int sp = 0; sp < 4; ++sp) {
+      uint16_t o[8];
+#pragma unroll
+      for (int co = 0; co < 8; ++co) o[co] = e[co * 4 + sp];
+      *reinterpret_cast<uint4*>(out + (((long long)b * (2 * H) + 2 * y + (sp >> 1)) * (2 * W) + 2 * x + (sp & 1)) * out_ld + v * 8) =
+          *reinterpret_cast<const uint4*>(o);
     }
   }
 }
@@ -1317,7 +1374,10 @@ extern "C" int tdr_mdta_bwd(const float* shat, const float* attn, int B, long lo
     TDR_CHECK_CUDA(cudaFuncSetAttribute(mdta_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
-  mdta_bwd_kernel<<<dim3(heads, B), 256, smem, stream>>>(a);
+  int nz = tdr_cdiv(tdr_num_sms(), heads * B);
+  if (nz > c) nz = c;
+  if (nz < 1) nz = 1;
+  mdta_bwd_kernel<<<dim3(heads, B, nz), 256, smem, stream>>>(a);
   TDR_CHECK_LAUNCH();
   reduce_parts_kernel<<<tdr_cdiv(C * C, 256), 256, 0, stream>>>(dwout_part, B, C * C, dw_out, 1, nullptr, accumulate, 1.f);
   TDR_CHECK_LAUNCH();
@@ -1356,8 +1416,17 @@ extern "C" int tdr_pixel_shuffle_nhwc(const void* in_bf16, long long in_ld, int 
                                       void* out_bf16, long long out_ld, cudaStream_t stream) {
   TDR_CHECK_ARG(in_bf16 && out_bf16 && B > 0 && H > 0 && W > 0 && C > 0, "tdr_pixel_shuffle_nhwc: bad arguments");
   TDR_CHECK_ARG(mode == 1 ? (H % 2 == 0 && W % 2 == 0) : (mode == 2 && C % 4 == 0), "tdr_pixel_shuffle_nhwc: bad mode/shape");
-  pixel_shuffle_kernel<<<grid_for((long long)B * H * W * C, 256, 16), 256, 0, stream>>>(
-      reinterpret_cast<const bf16*>(in_bf16), in_ld, B, H, W, C, mode, reinterpret_cast<bf16*>(out_bf16), out_ld);
+  const bool aligned = in_ld % 8 == 0 && out_ld % 8 == 0 && ((uintptr_t)in_bf16 & 15) == 0 && ((uintptr_t)out_bf16 & 15) == 0 &&
+                       (long long)B * H * W * C < (1ll << 31);
+  if (mode == 1 && aligned && C % 8 == 0)
+    pixel_unshuffle_vec_kernel<<<grid_for((long long)B * (H / 2) * (W / 2) * (C / 8), 256, 16), 256, 0, stream>>>(
+        reinterpret_cast<const uint16_t*>(in_bf16), in_ld, B, H, W, C, reinterpret_cast<uint16_t*>(out_bf16), out_ld);
+  else if (mode == 2 && aligned && C % 32 == 0)
+    pixel_shuffle_vec_kernel<<<grid_for((long long)B * H * W * (C / 32), 256, 16), 256, 0, stream>>>(
+        reinterpret_cast<const uint16_t*>(in_bf16), in_ld, B, H, W, C, reinterpret_cast<uint16_t*>(out_bf16), out_ld);
+  else
+    pixel_shuffle_kernel<<<grid_for((long long)B * H * W * C, 256, 16), 256, 0, stream>>>(
+        reinterpret_cast<const bf16*>(in_bf16), in_ld, B, H, W, C, mode, reinterpret_cast<bf16*>(out_bf16), out_ld);
   TDR_CHECK_LAUNCH();
   return TDR_OK;
 }

@@ -28,6 +28,11 @@ def main(path):
         for i, k in enumerate(head):
             if k in KEYS:
                 print(f"  {k:<72} {r[i]:>16} {units[i]}")
+        pipes = [(float(r[i]), k) for i, k in enumerate(head)
+                 if "pipe_" in k and k.endswith("pct_of_peak_sustained_active") and k not in KEYS and r[i]]
+        for v, k in sorted(pipes, reverse=True)[:8]:
+            if v >= 1.0:
+                print(f"  {k:<72} {v:>16.2f} %")
         stalls = [(float(r[i]), k) for i, k in enumerate(head)
                   if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and r[i]]
         print("  top stall reasons (warps per issue-active cycle):")
