@@ -762,8 +762,11 @@ struct SgemmArgs {
 };
 
 __global__ void __launch_bounds__(256) sgemm_batched_kernel(const SgemmArgs a) {
-  __shared__ float As[16][65];
-  __shared__ float Bs[16][65];
+  // K tile of 32 with the next tile's global loads in flight (registers) while the current one is multiplied: these
+  // products are a handful of CTAs walking K = C serially, i.e. bound by the load latency per K step.
+  constexpr int KT = 32, NL = KT * 64 / 256;
+  __shared__ float As[KT][65];
+  __shared__ float Bs[KT][65];
   const int b1 = blockIdx.z / a.nb2, b2 = blockIdx.z % a.nb2;
   const float* A = a.A + b1 * a.a_b1 + b2 * a.a_b2;
   const float* Bm = a.B + b1 * a.b_b1 + b2 * a.b_b2;
@@ -775,22 +778,36 @@ __global__ void __launch_bounds__(256) sgemm_batched_kernel(const SgemmArgs a) {
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < a.K; k0 += 16) {
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+  float ra[NL], rb[NL];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const int e = threadIdx.x + l * 256;
       int kk, mm;
-      if (a.sam == 1) { mm = e & 63; kk = e >> 6; } else { kk = e & 15; mm = e >> 4; }     // coalesce along the unit stride
+      if (a.sam == 1) { mm = e & 63; kk = e >> 6; } else { kk = e & (KT - 1); mm = e / KT; }   // coalesce along the unit stride
       const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < a.M && k < a.K) ? A[m * a.sam + k * a.sak] : 0.f;
+      ra[l] = (m < a.M && k < a.K) ? A[m * a.sam + k * a.sak] : 0.f;
+      int nn;
+      if (a.sbn == 1) { nn = e & 63; kk = e >> 6; } else { kk = e & (KT - 1); nn = e / KT; }
+      const int n = n0 + nn, k2 = k0 + kk;
+      rb[l] = (n < a.N && k2 < a.K) ? Bm[k2 * a.sbk + n * a.sbn] : 0.f;
     }
-    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-      int kk, nn;
-      if (a.sbn == 1) { nn = e & 63; kk = e >> 6; } else { kk = e & 15; nn = e >> 4; }
-      const int n = n0 + nn, k = k0 + kk;
-      Bs[kk][nn] = (n < a.N && k < a.K) ? Bm[k * a.sbk + n * a.sbn] : 0.f;
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < a.K; k0 += KT) {
+#pragma unroll
+    for (int l = 0; l < NL; ++l) {
+      const int e = threadIdx.x + l * 256;
+      int kk, mm, nn;
+      if (a.sam == 1) { mm = e & 63; kk = e >> 6; } else { kk = e & (KT - 1); mm = e / KT; }
+      As[kk][mm] = ra[l];
+      if (a.sbn == 1) { nn = e & 63; kk = e >> 6; } else { kk = e & (KT - 1); nn = e / KT; }
+      Bs[kk][nn] = rb[l];
     }
     __syncthreads();
+    if (k0 + KT < a.K) fetch(k0 + KT);
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
+    for (int kk = 0; kk < KT; ++kk) {
       float av[4], bv[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) { av[i] = As[kk][ty + 16 * i]; bv[i] = Bs[kk][tx + 16 * i]; }
