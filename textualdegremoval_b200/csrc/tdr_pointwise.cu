@@ -366,8 +366,12 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
           }
         }
       if (i >= 2) {                                        // output row y0 + i - 2 (slot i % 3) is complete
-        if (st_ok && y0 + i - 2 < a.H) {
+        // The gate arithmetic runs unconditionally and only the stores are predicated: inside a divergent region the
+        // GELU of row r could not be interleaved with the taps of row r + 1 (BSSY / BSYNC around every row).
+        const bool row_ok = st_ok && y0 + i - 2 < a.H;
+        {
           if constexpr (GATE == 2) {
+           if (row_ok) {
             const raw_t gr = *reinterpret_cast<const raw_t*>(dgp);
             const uint32_t* gu = reinterpret_cast<const uint32_t*>(&gr);
             raw_t oa, ob;
@@ -398,10 +402,11 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
             }
             *reinterpret_cast<raw_t*>(outp) = oa;
             *reinterpret_cast<raw_t*>(outp + a.Cout) = ob;
+           }
           } else {
             raw_t o;
             uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
-            if constexpr (GATE == 3) {                      // training: keep the pre-gate tensor for the gate backward
+            if (GATE == 3 && row_ok) {                      // training: keep the pre-gate tensor for the gate backward
               raw_t ya, yb;
               uint32_t* yau = reinterpret_cast<uint32_t*>(&ya);
               uint32_t* ybu = reinterpret_cast<uint32_t*>(&yb);
@@ -425,7 +430,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
               if (!GATE && a.relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); }
               ou[e] = pack2t<HALF>(a0, a1);
             }
-            *reinterpret_cast<raw_t*>(outp) = o;
+            if (row_ok) *reinterpret_cast<raw_t*>(outp) = o;
           }
         }
         outp += (long long)a.W * a.out_ld;
