@@ -335,13 +335,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
     dw_tile_coords(a, sp, b, y0, x0);
     mbar_wait(&full[stage], (it >> 1) & 1);
     const uint8_t* tile_s = dsm + stage * kDwStageBytes + xl * PIX_PITCH + cgi * (VEC * 2);
-    f2 acc[3][NH][NP];
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int h = 0; h < NH; ++h)
-#pragma unroll
-        for (int e = 0; e < NP; ++e) acc[k][h][e] = bv[h][e];
+    f2 acc[3][NH][NP];                                     // a slot is (re)started by its first tap: fma(w00, v, bias)
     const int x = x0 + xl;
     bf16* outp = a.out + (((long long)b * a.H + y0) * a.W + x) * a.out_ld + c0;
     const bf16* dgp = GATE == 2 ? a.dg + (((long long)b * a.H + y0) * a.W + x) * a.dg_ld + c0 : nullptr;
@@ -362,7 +356,8 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
 #pragma unroll
             for (int k = 0; k < 3; ++k)                    // staged row i feeds output rows i - 2 + k: skip the ones outside
               if (i + k >= 2 && i + k < kDwRows + 2)       // the tile (20 % of the halo tile's FMAs; i, k are constants)
-                acc[(i + k) % 3][h][e] = fma2(w[h][(2 - k) * 3 + kx][e], v, acc[(i + k) % 3][h][e]);
+                acc[(i + k) % 3][h][e] = fma2(w[h][(2 - k) * 3 + kx][e], v,
+                                              (k == 2 && kx == 0) ? bv[h][e] : acc[(i + k) % 3][h][e]);
           }
         }
       if (i >= 2) {                                        // output row y0 + i - 2 (slot i % 3) is complete
@@ -437,10 +432,6 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
         if (GATE == 2) dgp += (long long)a.W * a.dg_ld;
         if (GATE == 3) yp += (long long)a.W * a.y_ld;
       }
-#pragma unroll
-      for (int h = 0; h < NH; ++h)
-#pragma unroll
-        for (int e = 0; e < NP; ++e) acc[i % 3][h][e] = bv[h][e];
     }
     __syncthreads();                                       // everyone is done with this stage before it is refilled
   }
