@@ -366,8 +366,13 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
         const bool row_ok = st_ok && y0 + i - 2 < a.H;
         {
           if constexpr (GATE == 2) {
-           if (row_ok) {
-            const raw_t gr = *reinterpret_cast<const raw_t*>(dgp);
+            raw_t gr;
+            {
+              uint32_t* gz = reinterpret_cast<uint32_t*>(&gr);
+#pragma unroll
+              for (int e = 0; e < NP; ++e) gz[e] = 0u;
+            }
+            if (row_ok) gr = *reinterpret_cast<const raw_t*>(dgp);
             const uint32_t* gu = reinterpret_cast<const uint32_t*>(&gr);
             raw_t oa, ob;
             uint32_t* oau = reinterpret_cast<uint32_t*>(&oa);
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
             for (int e = 0; e < NP; ++e) {
               const f2 av = acc[i % 3][0][e], bvv = acc[i % 3][1][e];
               f2 gv = bf2_to_f2(gu[e]);
-              if (a.dg_add)
+              if (a.dg_add && row_ok)
                 gv = fma2(pk2(1.f, 1.f), gv, pk2(a.dg_add[(long long)b * a.Cout + c0 + 2 * e],
                                                   a.dg_add[(long long)b * a.Cout + c0 + 2 * e + 1]));
               f2 da, db;
@@ -395,9 +400,10 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_tma_kernel(const __grid_cons
               upk2(db, t0, t1);
               obu[e] = pack2(t0, t1);
             }
-            *reinterpret_cast<raw_t*>(outp) = oa;
-            *reinterpret_cast<raw_t*>(outp + a.Cout) = ob;
-           }
+            if (row_ok) {
+              *reinterpret_cast<raw_t*>(outp) = oa;
+              *reinterpret_cast<raw_t*>(outp + a.Cout) = ob;
+            }
           } else {
             raw_t o;
             uint32_t* ou = reinterpret_cast<uint32_t*>(&o);
