@@ -259,10 +259,8 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
           if (sq & 1) continue;                  // one producer pass per pair: item sq + 1 is the second pixel tile
           int b1, ty1, tx1;
           conv_tile_coords(a, mt + 1, tiles_per_img, b1, ty1, tx1);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const int tap = ks / a.kchunks;
-            const int kc = ks % a.kchunks;
-            const int ky = tap / a.KW, kx = tap % a.KW;
+          // (tap, kc, ky, kx) advance as counters: four runtime divisions per stage were most of the producer's work
+          for (int ks = 0, tap = 0, kc = 0, ky = 0, kx = 0; ks < ksteps; ++ks) {
             mbar_wait(&empty[stage], phase ^ 1);
             mbar_expect_tx(&full[stage], 2 * kABytes + b_bytes);
             uint8_t* sa = smem_a + stage * a_stage_bytes;
@@ -272,13 +270,11 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
                         ty1 * a.TH * a.stride - a.pad + ky * a.dil, b1);
             tma_load_3d(smem_b + stage * b_bytes, &map_w, &full[stage], kc * kChunkK, nt * a.BN, tap);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
+            if (++kc == a.kchunks) { kc = 0; ++tap; if (++kx == a.KW) { kx = 0; ++ky; } }
           }
           continue;
         }
-        for (int ks = 0; ks < ksteps; ++ks) {
-          const int tap = ks / a.kchunks;
-          const int kc = ks % a.kchunks;
-          const int ky = tap / a.KW, kx = tap % a.KW;
+        for (int ks = 0, tap = 0, kc = 0, ky = 0, kx = 0; ks < ksteps; ++ks) {
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], a.resident_b ? kABytes : kABytes + b_bytes);
           tma_load_4d(smem_a + stage * kABytes, &map_a, &full[stage], kc * kChunkK,
@@ -287,6 +283,7 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
             tma_load_3d(smem_b + stage * b_bytes, &map_w, &full[stage], kc * kChunkK, nt * a.BN,
                         (a.w_batched ? b * taps : 0) + tap);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++kc == a.kchunks) { kc = 0; ++tap; if (++kx == a.KW) { kx = 0; ++ky; } }
         }
       }
     }
@@ -299,6 +296,11 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    // accumulator index / barrier parity of item `it` (= it % nacc, (it / nacc) & 1) kept as counters: the runtime
+    // divisions sat between two items' MMAs on the issuing warp
+    int acc_c = 0;
+    uint32_t acc_ph = 0;
+    auto acc_next = [&]() { if (++acc_c == a.nacc) { acc_c = 0; acc_ph ^= 1; } };
     if (a.resident_b) {
       // pixel-tile major: the kchunks A stages of a pixel tile stay in the ring while every n tile is multiplied with
       // them; they are released by the commit that follows the LAST n tile's MMAs
@@ -307,9 +309,9 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         if (blockIdx.x + pt * (int)gridDim.x >= a.m_tiles) break;
         const int st0 = stage;
         const uint32_t ph0 = phase;
-        for (int nt = 0; nt < a.n_tiles; ++nt, ++it) {
-          const int acc = it % a.nacc;
-          const uint32_t acc_phase = (it / a.nacc) & 1;
+        for (int nt = 0; nt < a.n_tiles; ++nt, ++it, acc_next()) {
+          const int acc = acc_c;
+          const uint32_t acc_phase = acc_ph;
           mbar_wait(&tempty[acc], acc_phase ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * a.BN;
@@ -336,11 +338,12 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         }
       }
     }
-    for (; !a.resident_b; ++it) {
+    for (; !a.resident_b; ++it, acc_next()) {
       int mt_, nt_;
       if (!conv_item(a, it, mt_, nt_)) break;
-      const int acc = it % a.nacc;
-      const uint32_t acc_phase = (it / a.nacc) & 1;
+      const int acc = acc_c;
+      const uint32_t acc_phase = acc_ph;
+      if (a.pair && (it & 1)) continue;          // the pair's second item was issued with the first (accumulator acc)
       mbar_wait(&tempty[acc], acc_phase ^ 1);          // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * a.BN;
@@ -383,9 +386,9 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         continue;
       }
       if (a.pair) {
-        if (it & 1) continue;                    // the pair's second item shares this pass (its accumulator is acc + 1)
-        const int acc1 = (it + 1) % a.nacc;
-        mbar_wait(&tempty[acc1], (((it + 1) / a.nacc) & 1) ^ 1);
+        const int acc1 = acc + 1 == a.nacc ? 0 : acc + 1;      // the pair's second item (it + 1)
+        const uint32_t acc1_phase = acc1 == 0 ? acc_phase ^ 1 : acc_phase;
+        mbar_wait(&tempty[acc1], acc1_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem1 = tmem_base + acc1 * a.BN;
         for (int ks = 0, kc = 0; ks < ksteps; ++ks) {
@@ -463,14 +466,16 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
     };
     if (kLN && lane == 0) ln_prefetch(0);
     int it = 0;
-    for (;; ++it) {
+    int acc_c = 0;                             // it % nacc and (it / nacc) & 1 as counters
+    uint32_t acc_ph = 0;
+    for (;; ++it, acc_c = (acc_c + 1 == a.nacc ? 0 : acc_c + 1), acc_ph ^= (acc_c == 0)) {
       int mt, nt;
       if (!conv_item(a, it, mt, nt)) break;
       // TMA epilogue without LayerNorm: the two warps of a TMEM lane quadrant take ALTERNATE items (each does all the
       // sub-blocks of its items) instead of splitting every item, so that their fence / store / barrier latencies overlap
       if (kTma && !kLN && a.alt_items && ((it & 1) != half)) continue;
-      const int acc = it % a.nacc;
-      const uint32_t acc_phase = (it / a.nacc) & 1;
+      const int acc = acc_c;
+      const uint32_t acc_phase = acc_ph;
       int b, tyi, txi;
       conv_tile_coords(a, mt, tiles_per_img, b, tyi, txi);
       const int oy = tyi * a.TH + my;
