@@ -134,11 +134,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      // (tx, ty, b) of the CTA's first pixel tile by division ONCE, then advanced as counters: the single producer
+      // thread used to run five runtime divisions per stage next to its TMA issues
+      int tx = tile0 % pl.tiles_x, ty = (tile0 / pl.tiles_x) % pl.tiles_y;
+      int b = a.per_sample ? bz : tile0 / pl.tiles_x / pl.tiles_y;
       for (int t = 0; t < ntiles; ++t) {
-        int tile = tile0 + t;
-        const int tx = tile % pl.tiles_x; tile /= pl.tiles_x;
-        const int ty = tile % pl.tiles_y;
-        const int b = a.per_sample ? bz : tile / pl.tiles_y;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], stage_bytes);
         uint8_t* base = smem + stage * stage_bytes;
@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
             tma_load_4d(base + pl.boxes_m * kBoxBytes + k3 * kHaloXBytes, &map_x, &full[stage], 0, tx * pl.TW + k3 - 1,
                         ty * pl.TH - 1, b);
           if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+          if (++tx == pl.tiles_x) { tx = 0; if (++ty == pl.tiles_y) { ty = 0; if (!a.per_sample) ++b; } }
           continue;
         }
         const int x0 = tx * pl.TW * a.stride + kx * a.dil - a.pad;
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_kernel(const __grid_constant__ T
         for (int j = 0; j < pl.boxes_n; ++j)
           tma_load_4d(base + (pl.boxes_m + j) * kBoxBytes, &map_x, &full[stage], nt * pl.BN + 64 * j, x0, y0, b);
         if (++stage == pl.stages) { stage = 0; phase ^= 1; }
+        if (++tx == pl.tiles_x) { tx = 0; if (++ty == pl.tiles_y) { ty = 0; if (!a.per_sample) ++b; } }
       }
     }
   } else if (warp == 1) {
