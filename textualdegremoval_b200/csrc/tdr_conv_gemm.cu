@@ -661,7 +661,9 @@ conv_gemm_kernel(const __grid_constant__ TdrTensorMap map_a, const __grid_consta
         for (int k = 0; k < n_my; ++k) {
           // staging buffer: residual tiles were queued into (k & 1); without residuals consecutive stores simply
           // alternate (across tiles too), so wait_group.read 1 always covers the buffer about to be overwritten
-          const int j = has_r2 ? (dbuf ? (k & 1) : 0) : (a.epi_bufs > 1 ? (store_cnt++ % a.epi_bufs) : 0);
+          int j = 0;
+          if (has_r2) j = dbuf ? (k & 1) : 0;
+          else if (a.epi_bufs > 1) { j = store_cnt; if (++store_cnt == a.epi_bufs) store_cnt = 0; }   // round robin
           const int cs = (sb0 + sbs * k) * sbc;
           uint8_t* const stg = buf + j * kEpiStageBytes;
           uint32_t raw[4][16];
