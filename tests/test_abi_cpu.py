@@ -240,3 +240,17 @@ def test_drsformer_state_dict_keys_match_reference():
         b = R.drsformer_ref_fusion(spa=spa, **cfg).state_dict()
         assert list(a) == list(b), typ
         assert all(a[k].shape == b[k].shape for k in b), typ
+
+
+def test_graphed_forward_refuses_cpu_tensors():
+    """GraphedForward (CUDA-graph replay of an inference forward) is a GPU-only path: no silent CPU execution."""
+    from textualdegremoval_b200.graphs import GraphedForward
+    with pytest.raises(AssertionError, match="CUDA tensors only"):
+        GraphedForward(lambda x: x, torch.zeros(1, 3, 8, 8))
+
+
+def test_pdl_switch_round_trips(tdr_lib):
+    """tdr_set_pdl returns the previous value (programmatic dependent launch is opt-in; results do not depend on it)."""
+    prev = tdr_lib.tdr_set_pdl(1)
+    assert tdr_lib.tdr_set_pdl(prev) == 1
+    assert tdr_lib.tdr_set_pdl(prev) == prev
